@@ -1,0 +1,170 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE -- never imported by the product package).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+PARITY UNPINNED by reference fixtures (see rsrec_oracle.h); pinned by oracle/dense_check.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "librsrec_oracle.so")
+_lib = None
+
+c_i32p = C.POINTER(C.c_int32)
+c_dp = C.POINTER(C.c_double)
+c_vp = C.c_void_p
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "rsrec_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "librsrec_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_create.restype = c_vp
+        _lib.orc_create.argtypes = [C.c_int] * 5 + [c_vp, c_vp]
+        _lib.orc_destroy.argtypes = [c_vp]
+        _lib.orc_set_hamiltonian.argtypes = [c_vp] * 7 + [C.c_int]
+        _lib.orc_set_operator.argtypes = [c_vp, C.c_int, c_vp, c_vp]
+        _lib.orc_set_use_mask.argtypes = [c_vp, C.c_int]
+        _lib.orc_set_threads.argtypes = [C.c_int]
+        _lib.orc_get_max_threads.restype = C.c_int
+        _lib.orc_lanczos_block.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp]
+        _lib.orc_lanczos_scalar.argtypes = [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]
+        _lib.orc_cheb_moments.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
+        _lib.orc_cheb_moments_random.argtypes = [c_vp, C.c_int, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
+        _lib.orc_kubo_moments.argtypes = [c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
+        _lib.orc_zsqr.argtypes = [c_vp, C.c_int, C.c_int]
+        _lib.orc_ham_vec_matmul.argtypes = [c_vp, c_vp, c_vp, C.c_double, C.c_double, c_vp]
+        _lib.orc_velo_vec_matmul.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp]
+        _lib.orc_heev18.argtypes = [c_vp, c_vp]
+        _lib.orc_last_irnum.argtypes = [c_vp]
+        _lib.orc_last_irnum.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_vp)
+
+
+def _f(a, dtype):
+    return None if a is None else np.asfortranarray(a, dtype=dtype)
+
+
+class Oracle:
+    """Holds one (lattice, hamiltonian) pair; methods mirror the reference's `recursion` procedures."""
+
+    def __init__(self, lat, ham, use_mask: bool = True, threads: int | None = None):
+        L = lib()
+        self.lat, self.ham = lat, ham
+        self.nn = _f(lat.nn, np.int32)
+        self.iz = _f(lat.iz, np.int32)
+        self._keep = [_f(getattr(ham, k), np.complex128) for k in ("ee", "eeo", "hall", "hallo", "lsham", "enim")]
+        self.h = L.orc_create(lat.kk, lat.ncols, lat.nslot, lat.ntype, lat.nmax, _p(self.nn), _p(self.iz))
+        L.orc_set_hamiltonian(self.h, *[_p(a) for a in self._keep], int(ham.hoh))
+        self._ops = [_f(getattr(ham, k, None), np.complex128) for k in ("v_a", "v_b")]
+        self._vops = [_f(getattr(ham, k, None), np.complex128) for k in ("vo_a", "vo_b")]
+        if self._ops[0] is not None:
+            L.orc_set_operator(self.h, ord("a"), _p(self._ops[0]), _p(self._vops[0]))
+            L.orc_set_operator(self.h, ord("b"), _p(self._ops[1]), _p(self._vops[1]))
+        L.orc_set_use_mask(self.h, int(use_mask))
+        if threads:
+            L.orc_set_threads(threads)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _units(site_i, site_j, asign, bsign):
+        si = np.ascontiguousarray(site_i, dtype=np.int32)
+        n = len(si)
+        sj = np.zeros(n, np.int32) if site_j is None else np.ascontiguousarray(site_j, dtype=np.int32)
+        a = np.ones(n, np.complex128) if asign is None else np.ascontiguousarray(asign, dtype=np.complex128)
+        b = np.ones(n, np.complex128) if bsign is None else np.ascontiguousarray(bsign, dtype=np.complex128)
+        return n, si, sj, a, b
+
+    def lanczos_block(self, site_i, lld, site_j=None, asign=None, bsign=None):
+        n, si, sj, a, b = self._units(site_i, site_j, asign, bsign)
+        a_b = np.zeros((18, 18, lld, n), np.complex128, order="F")
+        b2_b = np.zeros((18, 18, lld, n), np.complex128, order="F")
+        lib().orc_lanczos_block(self.h, n, _p(si), _p(sj), _p(a), _p(b), lld, _p(a_b), _p(b2_b))
+        return a_b, b2_b
+
+    def lanczos_scalar(self, sites, lld):
+        s = np.ascontiguousarray(sites, dtype=np.int32)
+        a = np.zeros((lld, 18, len(s)), np.float64, order="F")
+        b2 = np.zeros((lld, 18, len(s)), np.float64, order="F")
+        lib().orc_lanczos_scalar(self.h, len(s), _p(s), lld, _p(a), _p(b2))
+        return a, b2
+
+    def cheb_moments(self, site_i, lld, a, b, site_j=None, asign=None, bsign=None):
+        n, si, sj, as_, bs_ = self._units(site_i, site_j, asign, bsign)
+        mu = np.zeros((18, 18, 2 * lld + 2, n), np.complex128, order="F")
+        rc = lib().orc_cheb_moments(self.h, n, _p(si), _p(sj), _p(as_), _p(bs_), lld, a, b, _p(mu))
+        return mu, rc
+
+    def cheb_moments_random(self, phases, lld, a, b):
+        ph = np.asfortranarray(phases, dtype=np.float64)
+        nvec = ph.shape[1]
+        mu = np.zeros((18, 18, 2 * lld + 2, nvec), np.complex128, order="F")
+        rc = lib().orc_cheb_moments_random(self.h, nvec, _p(ph), lld, a, b, _p(mu))
+        return mu, rc
+
+    def kubo_moments(self, cond_ll, a, b, start_sites=None, phases=None):
+        if start_sites is not None:
+            s = np.ascontiguousarray(start_sites, dtype=np.int32)
+            n, kind, ph = len(s), 0, None
+        else:
+            ph = np.asfortranarray(phases, dtype=np.float64)
+            n, kind, s = ph.shape[1], 1, None
+        mu = np.zeros((18, 18, cond_ll, cond_ll, n), np.complex128, order="F")
+        rc = lib().orc_kubo_moments(self.h, n, kind, _p(s), _p(ph), cond_ll, a, b, _p(mu))
+        assert rc == 0
+        return mu
+
+    def zsqr(self, b2_b):
+        out = np.array(b2_b, dtype=np.complex128, order="F", copy=True)
+        lib().orc_zsqr(_p(out), out.shape[2], out.shape[3])
+        return out
+
+    def ham_vec_matmul(self, psi_in, a, b, izero):
+        pin = np.asfortranarray(psi_in, dtype=np.complex128)
+        out = np.zeros_like(pin, order="F")
+        iz = np.ascontiguousarray(izero, dtype=np.int32).copy()
+        lib().orc_ham_vec_matmul(self.h, _p(pin), _p(out), a, b, _p(iz))
+        return out, iz
+
+    def velo_vec_matmul(self, slot, psi_in, izero):
+        pin = np.asfortranarray(psi_in, dtype=np.complex128)
+        out = np.zeros_like(pin, order="F")
+        iz = np.ascontiguousarray(izero, dtype=np.int32).copy()
+        lib().orc_velo_vec_matmul(self.h, ord(slot), _p(pin), _p(out), _p(iz))
+        return out, iz
+
+    def last_irnum(self):
+        return lib().orc_last_irnum(self.h)
+
+
+def heev18(m):
+    u = np.array(m, dtype=np.complex128, order="F", copy=True)
+    ev = np.zeros(18)
+    lib().orc_heev18(_p(u), _p(ev))
+    return ev, u
+
+
+def cheb_scale(emin: float, emax: float):
+    """a, b of `recursion.f90:3078-3079`."""
+    return (emax - emin) / (2 - 0.3), (emax + emin) / 2
