@@ -1,0 +1,116 @@
+/*
+ * rsrec.h -- C ABI of the B200-native recursion engine (librsrec.so).
+ *
+ * Drop-in boundary for the hot path of rslmtoasa/rslmtoasa: the type-bound procedures of
+ * `type recursion` (reference source/recursion.f90:41-116).  The reference has no FFI; a Fortran host binds these
+ * entry points with ISO_C_BINDING (see INTEGRATION.md / fortran/rsrec_c_mod.f90) and keeps its derived-type API.
+ *
+ * Conventions (identical to the reference's arrays, so the host passes its members unchanged):
+ *   - every array is Fortran column-major; `rsrec_cplx` == complex(c_double_complex) == complex(rp);
+ *   - site and type indices are 1-based, `nn(i,1)` is the slot count, `nn(i,j)=0` means "no neighbour";
+ *   - every function returns 0 on success, <0 on error; rsrec_last_error() gives the message the host passes to
+ *     g_logger%fatal (reference logger.f90:186-193).  RSREC_EDIVERGED mirrors the Chebyshev guard
+ *     `sum(real(mu)) > 1000 -> fatal` (recursion.f90:2594, 2760);
+ *   - calls are synchronous on return (results are in the host arrays); a handle is not thread-safe; one handle
+ *     per process/GPU, like one `recursion` object per MPI rank in the reference (mpi.f90:32-58).
+ *   - there is NO CPU fallback: if no CUDA device is usable rsrec_create fails with RSREC_ECUDA.
+ */
+#ifndef RSREC_H
+#define RSREC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+typedef struct { double re, im; } rsrec_cplx;
+#else
+#include <complex.h>
+typedef double _Complex rsrec_cplx;
+#endif
+
+typedef struct rsrec_handle_s *rsrec_handle;
+
+#define RSREC_OK 0
+#define RSREC_EINVAL (-1)    /* bad argument / call order */
+#define RSREC_EDIVERGED (-2) /* Chebyshev moments did not converge (energy window too small) */
+#define RSREC_ECUDA (-3)     /* CUDA runtime error, or no device */
+#define RSREC_ENOMEM (-4)    /* device memory exhausted */
+
+const char *rsrec_last_error(void);
+/* library/ABI version, and the SM architecture the kernels were compiled for (100 => sm_100a) */
+int rsrec_version(void);
+int rsrec_compiled_arch(void);
+
+/* recursion constructor (recursion.f90:132-143, allocation 3713-3826): sizes come from
+ * lattice%kk, size(lattice%nn,2), size(hamiltonian%ee,3) = maxval(nn(:,1))+1 (hamiltonian.f90:294),
+ * lattice%ntype, lattice%nmax. */
+int rsrec_create(rsrec_handle *h, int device_ordinal, int kk, int ncols, int nslot, int ntype, int nmax);
+int rsrec_destroy(rsrec_handle h);
+
+/* lattice%nn(kk,ncols), lattice%iz(kk) (lattice.f90:1856-1860, 204).  Upload after the Hamiltonian build because
+ * chbar_nc may zero entries of nn (hamiltonian.f90:2350-2352). */
+int rsrec_set_lattice(rsrec_handle h, const int32_t *nn, const int32_t *iz);
+
+/* hamiltonian%{ee,eeo}(18,18,nslot,ntype), {hall,hallo}(18,18,nslot,nmax), {lsham,enim}(18,18,ntype), hoh
+ * (hamiltonian.f90:52-66,294-301).  Called once per SCF iteration after build_bulkham/build_locham
+ * (self.f90:777-797).  eeo/hallo/enim may be NULL when hoh==0; hall/hallo may be NULL when nmax==0. */
+int rsrec_set_hamiltonian(rsrec_handle h, const rsrec_cplx *ee, const rsrec_cplx *eeo, const rsrec_cplx *hall,
+                          const rsrec_cplx *hallo, const rsrec_cplx *lsham, const rsrec_cplx *enim, int hoh);
+
+/* Kubo operators hamiltonian%{v_a,vo_a} (slot 'a') / {v_b,vo_b} (slot 'b'), (18,18,nslot,ntype)
+ * (recursion.f90:242-262).  vo_op may be NULL when hoh==0. */
+int rsrec_set_operator(rsrec_handle h, int slot, const rsrec_cplx *v_op, const rsrec_cplx *vo_op);
+
+/* recur_b (recursion.f90:1807-1866) when site_j==NULL or site_j[u]==0, recur_b_ij (1655-1737) otherwise:
+ * unit u starts from asign[u]*I on site_i[u] and bsign[u]*I on site_j[u] (NULL signs => 1).  crecal_b
+ * (1873-1973) runs lld-1 steps.  a_b, b2_b: (18,18,lld,nunits); b2_b holds B^2 (not B) like the reference. */
+int rsrec_lanczos_block(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j,
+                        const rsrec_cplx *asign, const rsrec_cplx *bsign, int lld, rsrec_cplx *a_b, rsrec_cplx *b2_b);
+
+/* recur/crecal/hop (recursion.f90:3485-3532, 3423-3478, 3310-3416; nsp=1 only, like the reference).
+ * a, b2: real (lld,18,nunits) = this%a(:, :, unit, 1), this%b2(:, :, unit, 1). */
+int rsrec_lanczos_scalar(rsrec_handle h, int nunits, const int32_t *sites, int lld, double *a, double *b2);
+
+/* zsqr (recursion.f90:1980-2023): b2_b(18,18,lld,na) <- (b2_b)^(1/2), in place. */
+int rsrec_zsqr(rsrec_handle h, rsrec_cplx *b2_b, int lld, int na);
+
+/* chebyshev_recur (recursion.f90:3057-3130) / chebyshev_recur_ij (2376-2487): a_scale, b_shift are the caller's
+ * a=(emax-emin)/(2-0.3), b=(emax+emin)/2 (3078-3079).  mu_n: (18,18,2*lld+2,nunits). */
+int rsrec_cheb_moments(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j,
+                       const rsrec_cplx *asign, const rsrec_cplx *bsign, int lld, double a_scale, double b_shift,
+                       rsrec_cplx *mu_n);
+
+/* The same moment recursion (cheb_0th_mom, cheb_1st_mom, chebyshev_recur_ll) started from the KPM random-phase
+ * block exp(2 pi i u_k) I / sqrt(kk) of recursion.f90:1131-1143; phases u: (kk,nvec) from the host because the
+ * reference's random_seed() is not repeatable.  mu_n: (18,18,2*lld+2,nvec). */
+int rsrec_cheb_moments_random(rsrec_handle h, int nvec, const double *phases, int lld, double a_scale,
+                              double b_shift, rsrec_cplx *mu_n);
+
+/* compute_moments_stochastic (recursion.f90:979-1234).  start_kind 0: per_type, start_sites[i] = atlist(i);
+ * 1: random_vec, phases (kk,nstart).  mu_nm: (18,18,cond_ll,cond_ll,nstart) = mu_nm_stochastic. */
+int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites,
+                       const double *phases, int cond_ll, double a_scale, double b_shift, rsrec_cplx *mu_nm);
+
+/* ham_vec_matmul / ham_hoh_vec_matmul (recursion.f90:913-977 / 785-911): psi_out = (H psi_in - b psi_in)/a,
+ * psi_*: (18,18,kk) host arrays.  velo_vec_matmul / velo_hoh_vec_matmul (587-783): psi_out = v_op psi_in. */
+int rsrec_ham_vec_matmul(rsrec_handle h, const rsrec_cplx *psi_in, rsrec_cplx *psi_out, double a_scale, double b_shift);
+int rsrec_velo_vec_matmul(rsrec_handle h, int slot, const rsrec_cplx *psi_in, rsrec_cplx *psi_out);
+
+/* ---- device-resident stepping (what bench.py times as `value`; the calls above are the `e2e` path) ----
+ * begin: upload start vectors, compute mu(1), mu(2) on the device.  run_steps: enqueue n chebyshev_recur_ll steps on
+ * the handle's stream without host synchronisation.  end: wait, download mu_n(18,18,2*lld+2,nvec). */
+int rsrec_cheb_begin_random(rsrec_handle h, int nvec, const double *phases, int lld, double a_scale, double b_shift);
+int rsrec_cheb_begin_sites(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j,
+                           const rsrec_cplx *asign, const rsrec_cplx *bsign, int lld, double a_scale, double b_shift);
+int rsrec_cheb_run_steps(rsrec_handle h, int nsteps);
+int rsrec_cheb_end(rsrec_handle h, rsrec_cplx *mu_n);
+int rsrec_synchronize(rsrec_handle h);
+/* the cudaStream_t all kernels of this handle are launched on (so callers can record events on it) */
+void *rsrec_stream(rsrec_handle h);
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+long long rsrec_launch_count(rsrec_handle h);
+/* select kernel family: 0 = SIMT reference kernels, 1 = DMMA (FP64 tensor core) pipeline (default) */
+int rsrec_set_kernel_family(rsrec_handle h, int family);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSREC_H */

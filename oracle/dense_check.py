@@ -57,7 +57,7 @@ def start_block(lat, site_i, site_j=0, asign=1.0, bsign=1.0):
 def random_block(lat, u):
     W = np.zeros((NB * lat.kk, NB), dtype=np.complex128)
     for k in range(lat.kk):
-        W[NB * k:NB * (k + 1)] = np.exp(2j * np.pi * u[k]) * np.eye(NB) / np.sqrt(lat.kk)
+        W[NB * k:NB * (k + 1)] = np.exp(2j * np.pi * u[k]) * np.eye(NB) / float(np.sqrt(np.float32(lat.kk)))
     return W
 
 

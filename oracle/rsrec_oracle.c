@@ -628,7 +628,9 @@ int orc_cheb_moments(orc_ctx *c, int nunits, const int32_t *site_i, const int32_
 
 static void random_start(const orc_ctx *c, const double *u, cplx *psiref) {
   const int kk = c->kk;
-  const double nrm = sqrt((double)kk);
+  /* `sqrt(real(this%lattice%kk))` is evaluated in DEFAULT (single) real kind in the reference (no
+   * -fdefault-real-8 in its build flags), then promoted: keep that, it matters at the 1e-8 level. */
+  const double nrm = (double)sqrtf((float)kk);
   zero_blocks(psiref, kk);
   for (int k = 1; k <= kk; k++) {
     const cplx ph = cexp(2.0 * M_PI * I * u[k - 1]);

@@ -1,0 +1,68 @@
+"""ctypes binding of include/rsrec.h (the same symbols a Fortran ISO_C_BINDING module binds)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+SYMBOLS = [
+    "rsrec_last_error", "rsrec_version", "rsrec_compiled_arch", "rsrec_create", "rsrec_destroy", "rsrec_set_lattice",
+    "rsrec_set_hamiltonian", "rsrec_set_operator", "rsrec_lanczos_block", "rsrec_lanczos_scalar", "rsrec_zsqr",
+    "rsrec_cheb_moments", "rsrec_cheb_moments_random", "rsrec_kubo_moments", "rsrec_ham_vec_matmul",
+    "rsrec_velo_vec_matmul", "rsrec_cheb_begin_random", "rsrec_cheb_begin_sites", "rsrec_cheb_run_steps",
+    "rsrec_cheb_end", "rsrec_synchronize", "rsrec_stream", "rsrec_launch_count", "rsrec_set_kernel_family",
+]
+
+
+class RsrecError(RuntimeError):
+    """Raised where the Fortran host would call g_logger%fatal (reference logger.f90:186-193)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rsrec error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """Load librsrec.so (never builds implicitly on a GPU box: the .so travels in-tree).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError(f"{_build.LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(_build.LIB)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    L.rsrec_last_error.restype = C.c_char_p
+    L.rsrec_create.argtypes = [C.POINTER(vp), i, i, i, i, i, i]
+    L.rsrec_destroy.argtypes = [vp]
+    L.rsrec_set_lattice.argtypes = [vp, vp, vp]
+    L.rsrec_set_hamiltonian.argtypes = [vp, vp, vp, vp, vp, vp, vp, i]
+    L.rsrec_set_operator.argtypes = [vp, i, vp, vp]
+    L.rsrec_lanczos_block.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp]
+    L.rsrec_lanczos_scalar.argtypes = [vp, i, vp, i, vp, vp]
+    L.rsrec_zsqr.argtypes = [vp, vp, i, i]
+    L.rsrec_cheb_moments.argtypes = [vp, i, vp, vp, vp, vp, i, d, d, vp]
+    L.rsrec_cheb_moments_random.argtypes = [vp, i, vp, i, d, d, vp]
+    L.rsrec_kubo_moments.argtypes = [vp, i, i, vp, vp, i, d, d, vp]
+    L.rsrec_ham_vec_matmul.argtypes = [vp, vp, vp, d, d]
+    L.rsrec_velo_vec_matmul.argtypes = [vp, i, vp, vp]
+    L.rsrec_cheb_begin_random.argtypes = [vp, i, vp, i, d, d]
+    L.rsrec_cheb_begin_sites.argtypes = [vp, i, vp, vp, vp, vp, i, d, d]
+    L.rsrec_cheb_run_steps.argtypes = [vp, i]
+    L.rsrec_cheb_end.argtypes = [vp, vp]
+    L.rsrec_synchronize.argtypes = [vp]
+    L.rsrec_stream.argtypes = [vp]
+    L.rsrec_stream.restype = vp
+    L.rsrec_launch_count.argtypes = [vp]
+    L.rsrec_launch_count.restype = C.c_longlong
+    L.rsrec_set_kernel_family.argtypes = [vp, i]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RsrecError(rc, load().rsrec_last_error().decode())

@@ -1,0 +1,146 @@
+// eig18.cuh -- device-side 18x18 Hermitian eigen-decomposition and matrix square roots.
+//
+// Replaces the serial LAPACK zheev calls on the critical path of crecal_b (recursion.f90:1938-1959) and zsqr
+// (recursion.f90:1980-2023).  One CTA of 324 threads per matrix: two-sided Jacobi with the round-robin parallel
+// ordering (17 rounds x 9 disjoint rotations per sweep), thread (r,c) updates element (r,c) of A and V.
+#pragma once
+#include "common.cuh"
+
+struct Eig18Smem {
+  double Ar[BLKC], Ai[BLKC], Vr[BLKC], Vi[BLKC];  // [r + 18 c]
+  double cs[9], sr[9], si[9];                     // rotation: cos, sin*phase
+  int pp[9], qq[9], pair_of[NB];
+  double ev[NB];
+  double tot;
+};
+
+// A (Hermitian, upper triangle trusted like zheev 'U') -> eigenvalues s.ev, eigenvectors s.V (columns).
+__device__ void eig18_jacobi(Eig18Smem &s) {
+  const int tid = threadIdx.x, r = tid % NB, c = tid / NB;
+  // symmetrise from the upper triangle
+  __syncthreads();
+  double ar = s.Ar[tid], ai = s.Ai[tid];
+  if (r > c) { ar = s.Ar[c + NB * r]; ai = -s.Ai[c + NB * r]; }
+  if (r == c) ai = 0.0;
+  __syncthreads();
+  s.Ar[tid] = ar; s.Ai[tid] = ai;
+  s.Vr[tid] = (r == c) ? 1.0 : 0.0; s.Vi[tid] = 0.0;
+  if (tid == 0) s.tot = 0.0;
+  __syncthreads();
+  atomicAdd(&s.tot, ar * ar + ai * ai);
+  __syncthreads();
+  const double thresh = 1e-64 * s.tot;
+  for (int sweep = 0; sweep < 40; sweep++) {
+    const int notconv = __syncthreads_or(r != c && (s.Ar[tid] * s.Ar[tid] + s.Ai[tid] * s.Ai[tid]) > thresh);
+    if (!notconv) break;
+    for (int t = 0; t < 17; t++) {
+      if (tid < 9) {
+        int a_, b_;
+        if (tid == 0) { a_ = 17; b_ = t; } else { a_ = (t + tid) % 17; b_ = (t - tid + 17) % 17; }
+        const int p = min(a_, b_), q = max(a_, b_);
+        s.pp[tid] = p; s.qq[tid] = q; s.pair_of[p] = tid; s.pair_of[q] = tid;
+        const double pr = s.Ar[p + NB * q], pi = s.Ai[p + NB * q];
+        const double mag = sqrt(pr * pr + pi * pi);
+        double cs = 1.0, sr = 0.0, si = 0.0;
+        if (mag > 1e-300) {
+          const double app = s.Ar[p + NB * p], aqq = s.Ar[q + NB * q];
+          const double tau = (aqq - app) / (2.0 * mag);
+          const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          cs = 1.0 / sqrt(1.0 + tt * tt);
+          const double sn = tt * cs;
+          sr = sn * pr / mag; si = sn * pi / mag;  // sn * e^{i phi}
+        }
+        s.cs[tid] = cs; s.sr[tid] = sr; s.si[tid] = si;
+      }
+      __syncthreads();
+      // R restricted to (p,q): R_pp = cs, R_pq = (sr + i si), R_qp = -(sr - i si), R_qq = cs
+      const int kc = s.pair_of[c], pc = s.pp[kc], qc = s.qq[kc];
+      const int kr = s.pair_of[r], pr_ = s.pp[kr], qr_ = s.qq[kr];
+      double Rpc_r, Rpc_i, Rqc_r, Rqc_i;  // R[pc][c], R[qc][c]
+      if (c == pc) { Rpc_r = s.cs[kc]; Rpc_i = 0.0; Rqc_r = -s.sr[kc]; Rqc_i = s.si[kc]; }
+      else         { Rpc_r = s.sr[kc]; Rpc_i = s.si[kc]; Rqc_r = s.cs[kc]; Rqc_i = 0.0; }
+      double Rpr_r, Rpr_i, Rqr_r, Rqr_i;  // R[pr][r], R[qr][r]
+      if (r == pr_) { Rpr_r = s.cs[kr]; Rpr_i = 0.0; Rqr_r = -s.sr[kr]; Rqr_i = s.si[kr]; }
+      else          { Rpr_r = s.sr[kr]; Rpr_i = s.si[kr]; Rqr_r = s.cs[kr]; Rqr_i = 0.0; }
+      // (A R)[x][c] for x = pr_, qr_
+      double x1r, x1i, x2r, x2i;
+      {
+        const double a1r = s.Ar[pr_ + NB * pc], a1i = s.Ai[pr_ + NB * pc], a2r = s.Ar[pr_ + NB * qc], a2i = s.Ai[pr_ + NB * qc];
+        x1r = a1r * Rpc_r - a1i * Rpc_i + a2r * Rqc_r - a2i * Rqc_i;
+        x1i = a1r * Rpc_i + a1i * Rpc_r + a2r * Rqc_i + a2i * Rqc_r;
+        const double b1r = s.Ar[qr_ + NB * pc], b1i = s.Ai[qr_ + NB * pc], b2r = s.Ar[qr_ + NB * qc], b2i = s.Ai[qr_ + NB * qc];
+        x2r = b1r * Rpc_r - b1i * Rpc_i + b2r * Rqc_r - b2i * Rqc_i;
+        x2i = b1r * Rpc_i + b1i * Rpc_r + b2r * Rqc_i + b2i * Rqc_r;
+      }
+      // A'[r][c] = conj(R[pr][r]) x1 + conj(R[qr][r]) x2
+      double nr = Rpr_r * x1r + Rpr_i * x1i + Rqr_r * x2r + Rqr_i * x2i;
+      double ni = Rpr_r * x1i - Rpr_i * x1r + Rqr_r * x2i - Rqr_i * x2r;
+      // V'[r][c] = V[r][pc] R[pc][c] + V[r][qc] R[qc][c]
+      const double v1r = s.Vr[r + NB * pc], v1i = s.Vi[r + NB * pc], v2r = s.Vr[r + NB * qc], v2i = s.Vi[r + NB * qc];
+      const double wr = v1r * Rpc_r - v1i * Rpc_i + v2r * Rqc_r - v2i * Rqc_i;
+      const double wi = v1r * Rpc_i + v1i * Rpc_r + v2r * Rqc_i + v2i * Rqc_r;
+      // the rotated pair is annihilated exactly; diagonals are real
+      if ((r == pr_ && c == qr_) || (r == qr_ && c == pr_)) { nr = 0.0; ni = 0.0; }
+      if (r == c) ni = 0.0;
+      __syncthreads();
+      s.Ar[tid] = nr; s.Ai[tid] = ni; s.Vr[tid] = wr; s.Vi[tid] = wi;
+      __syncthreads();
+    }
+  }
+  if (tid < NB) s.ev[tid] = s.Ar[tid + NB * tid];
+  __syncthreads();
+}
+
+// out(r,c) = sum_k V(r,k) f_k conj(V(c,k)), complex col-major interleaved
+__device__ __forceinline__ void eig18_func(const Eig18Smem &s, const double *f, double *out) {
+  const int tid = threadIdx.x, r = tid % NB, c = tid / NB;
+  double orr = 0, oi = 0;
+#pragma unroll
+  for (int k = 0; k < NB; k++) {
+    const double ar = s.Vr[r + NB * k], ai = s.Vi[r + NB * k], br = s.Vr[c + NB * k], bi = -s.Vi[c + NB * k];
+    orr += f[k] * (ar * br - ai * bi);
+    oi += f[k] * (ar * bi + ai * br);
+  }
+  out[2 * tid] = orr; out[2 * tid + 1] = oi;
+}
+
+// crecal_b "B_n+1": reduce the B^2 partials of unit blockIdx.x (fixed order), record B^2 in the history slot,
+// then B = U sqrt(L) U^H and B^-1 = U L^-1/2 U^H.  diag != 0: scalar Lanczos, everything diagonal & real.
+__global__ void __launch_bounds__(BLKC) k_lz_eig(const double *part, int nctas, double *b2_hist_slot, size_t hstride,
+                                                 double *Bmat, double *Bimat, size_t bstride, int diag) {
+  __shared__ Eig18Smem s;
+  __shared__ double f1[NB], f2[NB];
+  const int tid = threadIdx.x, unit = blockIdx.x, r = tid % NB, c = tid / NB;
+  const double *pp = part + (size_t)unit * nctas * (2 * BLKD);
+  double mr = 0, mi = 0;
+  for (int cta = 0; cta < nctas; cta++) { mr += pp[(size_t)cta * (2 * BLKD) + 2 * tid]; mi += pp[(size_t)cta * (2 * BLKD) + 2 * tid + 1]; }
+  if (diag) { if (r != c) mr = 0.0; mi = 0.0; }
+  b2_hist_slot[(size_t)unit * hstride + 2 * tid] = mr;
+  b2_hist_slot[(size_t)unit * hstride + 2 * tid + 1] = mi;
+  double *B = Bmat + (size_t)unit * bstride, *Bi = Bimat + (size_t)unit * bstride;
+  if (diag) {
+    const double sq = sqrt(mr);
+    B[2 * tid] = (r == c) ? sq : 0.0; B[2 * tid + 1] = 0.0;
+    Bi[2 * tid] = (r == c) ? 1.0 / sq : 0.0; Bi[2 * tid + 1] = 0.0;
+    return;
+  }
+  s.Ar[tid] = mr; s.Ai[tid] = mi;
+  eig18_jacobi(s);
+  if (tid < NB) { f1[tid] = sqrt(s.ev[tid]); f2[tid] = 1.0 / f1[tid]; }  // NaN for ev<0, like the reference
+  __syncthreads();
+  eig18_func(s, f1, B);
+  eig18_func(s, f2, Bi);
+}
+
+// zsqr: in-place square root of a batch of Hermitian PSD 18x18 matrices (complex col-major)
+__global__ void __launch_bounds__(BLKC) k_zsqr(double *mats) {
+  __shared__ Eig18Smem s;
+  __shared__ double f1[NB];
+  const int tid = threadIdx.x;
+  double *m = mats + (size_t)blockIdx.x * BLKD;
+  s.Ar[tid] = m[2 * tid]; s.Ai[tid] = m[2 * tid + 1];
+  eig18_jacobi(s);
+  if (tid < NB) f1[tid] = sqrt(s.ev[tid]);
+  __syncthreads();
+  eig18_func(s, f1, m);
+}

@@ -1,0 +1,785 @@
+// rsrec.cu -- C ABI (include/rsrec.h) and host orchestration of the B200-native recursion engine.
+//
+// Host-side structure mirrors the reference drivers: recur_b / recur_b_ij / crecal_b (recursion.f90:1655-1973),
+// recur / crecal (3423-3532), chebyshev_recur(_ij) (2376-2487, 3057-3130), compute_moments_stochastic (979-1234).
+// All arithmetic runs in CUDA kernels; the host only sequences launches.  No CPU fallback exists.
+#include "../../include/rsrec.h"
+#include "common.cuh"
+#include "kernels_simt.cuh"
+#include "eig18.cuh"
+#include "kernels_dmma.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                                         \
+  do {                                                                                                      \
+    cudaError_t e_ = (x);                                                                                   \
+    if (e_ != cudaSuccess) {                                                                                \
+      cudaGetLastError();                                                                                   \
+      return fail(e_ == cudaErrorMemoryAllocation ? RSREC_ENOMEM : RSREC_ECUDA,                             \
+                  std::string(#x) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                                       \
+  } while (0)
+#define TRY(x) do { int rc_ = (x); if (rc_ != RSREC_OK) return rc_; } while (0)
+
+typedef rsrec_cplx cplx;
+
+struct DevBuf {
+  double *p = nullptr;
+  size_t n = 0;  // doubles
+};
+
+struct rsrec_handle_s {
+  int dev = 0, kk = 0, ncols = 0, nslot = 0, ntype = 0, nmax = 0, hoh = 0, ncls = 0;
+  int family = 1;
+  int sms = 148;
+  cudaStream_t st = nullptr;
+  long long launches = 0;
+  int last_parts = 0;  // partial-sum slots per unit written by the last fused apply
+  // host copies of the reference arrays (small) so that device sets can be (re)built in any call order
+  std::vector<int32_t> nn, iz;
+  std::vector<cplx> ee, eeo, hall, hallo, lsham, enim, v_a, v_b, vo_a, vo_b;
+  bool have_lat = false, have_ham = false, have_op[2] = {false, false}, dirty = true;
+  // device operator data
+  int32_t *d_nbr = nullptr, *d_cls = nullptr;
+  DevBuf Hmain, Hh, Hho_neg, Hx, Hscalar, Hva, Hvb, Hvoa_neg, Hvob_neg;
+  DmmaTiles tiles;
+  // work vectors and small matrices
+  std::vector<DevBuf> vecs;
+  DevBuf part, A, B, Bi, mu, ahist, b2hist, scratch;
+  int32_t *d_si = nullptr, *d_sj = nullptr;
+  double *d_as = nullptr, *d_bs = nullptr;
+  int units_cap = 0;
+  // Chebyshev stepping session
+  struct {
+    bool active = false;
+    int nunits = 0, lld = 0, done = 0, nctas = 0;
+    double a = 1, b = 0;
+    int i0 = 0, i1 = 1;  // indices into vecs of psi0, psi1
+  } cheb;
+};
+typedef rsrec_handle_s H;
+
+// ------------------------------------------------------------------------------------------------------------
+static int dev_alloc(DevBuf &b, size_t n, bool zero) {
+  if (b.n < n) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.n = 0;
+    CUDA_TRY(cudaMalloc(&b.p, n * sizeof(double)));
+    b.n = n;
+    if (zero) CUDA_TRY(cudaMemset(b.p, 0, n * sizeof(double)));
+  }
+  return RSREC_OK;
+}
+static void dev_free(DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.n = 0; }
+
+static size_t vstride(const H *h) { return (size_t)(h->kk + 1) * BLKD; }
+
+static int get_vec(H *h, int idx, int nunits, double **out) {
+  if ((int)h->vecs.size() <= idx) h->vecs.resize(idx + 1);
+  size_t need = vstride(h) * nunits;
+  if (h->vecs[idx].n < need) {
+    dev_free(h->vecs[idx]);
+    TRY(dev_alloc(h->vecs[idx], need, true));
+  }
+  *out = h->vecs[idx].p;
+  return RSREC_OK;
+}
+static int zero_vec(H *h, double *v, int nunits) {
+  CUDA_TRY(cudaMemsetAsync(v, 0, vstride(h) * nunits * sizeof(double), h->st));
+  return RSREC_OK;
+}
+
+// host complex col-major block (r + 18 k) -> device row layout [r*36 + k | r*36 + 18 + k], scaled
+static void pack_block(const cplx *src, double *dst, double scale) {
+  for (int k = 0; k < NB; k++)
+    for (int r = 0; r < NB; r++) {
+      dst[r * COLD + k] = scale * src[r + NB * k].re;
+      dst[r * COLD + NB + k] = scale * src[r + NB * k].im;
+    }
+}
+static void add_block(const cplx *src, double *dst) {
+  for (int k = 0; k < NB; k++)
+    for (int r = 0; r < NB; r++) {
+      dst[r * COLD + k] += src[r + NB * k].re;
+      dst[r * COLD + NB + k] += src[r + NB * k].im;
+    }
+}
+
+static int upload(DevBuf &b, const std::vector<double> &host) {
+  TRY(dev_alloc(b, host.size(), false));
+  CUDA_TRY(cudaMemcpy(b.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return RSREC_OK;
+}
+
+// Build the device operator sets from the host copies (the "device-resident CSR-of-blocks" export of the
+// hamiltonian builder and the device index array of the lattice): classes 0..ntype-1 = bulk types (ee),
+// ntype..ntype+nmax-1 = site-indexed local region (hall) -- hamiltonian.f90:1553-1667, lattice.f90:1856-1860.
+static int ensure_ready(H *h) {
+  if (!h->have_lat) return fail(RSREC_EINVAL, "rsrec_set_lattice has not been called");
+  if (!h->have_ham) return fail(RSREC_EINVAL, "rsrec_set_hamiltonian has not been called");
+  if (!h->dirty) return RSREC_OK;
+  const int kk = h->kk, nslot = h->nslot, ncls = h->ncls, ng = h->ncols;
+  // neighbour table [slot][site], slot 0 = self, missing -> kk
+  std::vector<int32_t> nbr((size_t)ng * kk), cls(kk);
+  for (int i = 0; i < kk; i++) {
+    const int nr = h->nn[i];
+    if (nr > ng) return fail(RSREC_EINVAL, "nn(i,1) exceeds the second dimension of nn");
+    nbr[i] = i;
+    for (int j = 1; j < ng; j++) {
+      int nb = (j < nr) ? h->nn[(size_t)i + (size_t)kk * j] : 0;
+      if (nb < 0 || nb > kk) return fail(RSREC_EINVAL, "nn entry out of range");
+      nbr[(size_t)j * kk + i] = nb == 0 ? kk : nb - 1;
+    }
+    const int t = h->iz[i];
+    if (t < 1 || t > h->ntype) return fail(RSREC_EINVAL, "iz entry out of range");
+    cls[i] = (i < h->nmax) ? h->ntype + i : t - 1;
+  }
+  if (!h->d_nbr) CUDA_TRY(cudaMalloc(&h->d_nbr, nbr.size() * sizeof(int32_t)));
+  if (!h->d_cls) CUDA_TRY(cudaMalloc(&h->d_cls, cls.size() * sizeof(int32_t)));
+  CUDA_TRY(cudaMemcpy(h->d_nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_cls, cls.data(), cls.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+
+  auto src_block = [&](const std::vector<cplx> &ty, const std::vector<cplx> &loc, int c, int m) -> const cplx * {
+    if (c < h->ntype) return ty.data() + (size_t)BLKC * (m + (size_t)nslot * c);
+    return loc.data() + (size_t)BLKC * (m + (size_t)nslot * (c - h->ntype));
+  };
+  auto cls_type = [&](int c) { return c < h->ntype ? c : h->iz[c - h->ntype] - 1; };
+  const size_t setn = (size_t)ncls * nslot * BLKD;
+  std::vector<double> hm(setn, 0.0), hs(setn, 0.0);
+  for (int c = 0; c < ncls; c++)
+    for (int m = 0; m < nslot; m++) {
+      const cplx *b = src_block(h->ee, h->hall, c, m);
+      double *d = hm.data() + ((size_t)c * nslot + m) * BLKD;
+      pack_block(b, d, 1.0);
+      if (m == 0) add_block(h->lsham.data() + (size_t)BLKC * cls_type(c), d);  // locham = H_on + lsham (1582, 1608)
+      // scalar recursion: only the two 9x9 spin-diagonal sub-blocks act, no lsham (recursion.f90:3337-3342)
+      double *s = hs.data() + ((size_t)c * nslot + m) * BLKD;
+      for (int k = 0; k < NB; k++)
+        for (int r = 0; r < NB; r++)
+          if ((r < 9) == (k < 9)) { s[r * COLD + k] = b[r + NB * k].re; s[r * COLD + NB + k] = b[r + NB * k].im; }
+    }
+  TRY(upload(h->Hmain, hm));
+  TRY(upload(h->Hscalar, hs));
+  if (h->hoh) {
+    std::vector<double> hh(setn, 0.0), ho(setn, 0.0), hx((size_t)ncls * BLKD, 0.0);
+    for (int c = 0; c < ncls; c++) {
+      for (int m = 0; m < nslot; m++) {
+        pack_block(src_block(h->ee, h->hall, c, m), hh.data() + ((size_t)c * nslot + m) * BLKD, 1.0);
+        pack_block(src_block(h->eeo, h->hallo, c, m), ho.data() + ((size_t)c * nslot + m) * BLKD, -1.0);
+      }
+      pack_block(h->enim.data() + (size_t)BLKC * cls_type(c), hx.data() + (size_t)c * BLKD, 1.0);
+      add_block(h->lsham.data() + (size_t)BLKC * cls_type(c), hx.data() + (size_t)c * BLKD);
+    }
+    TRY(upload(h->Hh, hh));
+    TRY(upload(h->Hho_neg, ho));
+    TRY(upload(h->Hx, hx));
+  }
+  // velocity operators are type-indexed; the reference skips the site-indexed region entirely
+  // (loops start at nmax+1, recursion.f90:603-634): local classes keep zero blocks.
+  for (int s = 0; s < 2; s++) {
+    if (!h->have_op[s]) continue;
+    const std::vector<cplx> &v = s == 0 ? h->v_a : h->v_b, &vo = s == 0 ? h->vo_a : h->vo_b;
+    std::vector<double> hv(setn, 0.0), hvo(setn, 0.0);
+    for (int c = 0; c < h->ntype; c++)
+      for (int m = 0; m < nslot; m++) {
+        pack_block(v.data() + (size_t)BLKC * (m + (size_t)nslot * c), hv.data() + ((size_t)c * nslot + m) * BLKD, 1.0);
+        if (h->hoh && !vo.empty() && m > 0)  // on-site vo term is commented out in the reference (761)
+          pack_block(vo.data() + (size_t)BLKC * (m + (size_t)nslot * c), hvo.data() + ((size_t)c * nslot + m) * BLKD, -1.0);
+      }
+    TRY(upload(s == 0 ? h->Hva : h->Hvb, hv));
+    if (h->hoh) TRY(upload(s == 0 ? h->Hvoa_neg : h->Hvob_neg, hvo));
+  }
+  TRY(dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls));
+  h->dirty = false;
+  return RSREC_OK;
+}
+
+static int ensure_units(H *h, int nunits) {
+  if (h->units_cap >= nunits) return RSREC_OK;
+  if (h->d_si) { cudaFree(h->d_si); cudaFree(h->d_sj); cudaFree(h->d_as); cudaFree(h->d_bs); }
+  CUDA_TRY(cudaMalloc(&h->d_si, nunits * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&h->d_sj, nunits * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&h->d_as, nunits * 2 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->d_bs, nunits * 2 * sizeof(double)));
+  h->units_cap = nunits;
+  return RSREC_OK;
+}
+
+static int nctas_for(const H *h, int nunits) {
+  int n = (h->sms * 6 + nunits - 1) / nunits;
+  return std::max(1, std::min(n, h->kk));
+}
+
+// largest unit batch whose `nvec` work vectors fit in free device memory (keeps 10% headroom)
+static int unit_batch(H *h, int nunits, int nvec) {
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  size_t held = 0;
+  for (auto &v : h->vecs) held += v.n * sizeof(double);
+  double avail = 0.9 * (double)(fr + held);
+  size_t per = vstride(h) * sizeof(double) * nvec;
+  int nb = (int)std::max(1.0, std::floor(avail / (double)per));
+  return std::min(nunits, nb);
+}
+
+// ---- operator application: out = epilogue( H src ) for a unit batch ---------------------------------------
+enum OpKind { OP_HAM = 0, OP_SCALAR = 1, OP_VELO_A = 2, OP_VELO_B = 3 };
+
+static int launch_apply(H *h, ApplyParams &p, int nunits, int nctas) {
+  if (h->family == 1 && dmma_supported(p)) {
+    TRY(dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches));
+    h->last_parts = dmma_parts_for(h->tiles, h->sms, nunits);
+    return RSREC_OK;
+  }
+  h->last_parts = nctas;
+  dim3 grid(nctas, nunits);
+  k_apply_simt<<<grid, SIMT_THREADS, 0, h->st>>>(p);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return RSREC_OK;
+}
+
+// out = epi( Op * in ).  tmp: scratch vector for the two-pass hoh forms.  part: gram partial buffer or null.
+static int apply_op(H *h, OpKind op, const double *in, double *out, const double *prev, double *tmp, int epi,
+                    double a, double b, int nunits, int nctas, double *part) {
+  ApplyParams p;
+  memset(&p, 0, sizeof(p));
+  p.kk = h->kk; p.nslot_h = h->nslot; p.ngather = h->ncols; p.vstride = vstride(h);
+  p.nbr = h->d_nbr; p.cls = h->d_cls; p.in = in; p.prev = prev; p.out = out; p.a = a; p.b = b; p.epi = epi; p.part = part;
+  const bool hoh = h->hoh && op != OP_SCALAR;
+  if (!hoh) {
+    const double *Hs = op == OP_HAM ? h->Hmain.p : op == OP_SCALAR ? h->Hscalar.p : op == OP_VELO_A ? h->Hva.p : h->Hvb.p;
+    p.g[0] = GatherTerm{Hs, in, 0};
+    p.ngterms = 1;
+    return launch_apply(h, p, nunits, nctas);
+  }
+  // pass A: tmp = h * in  (first sweep of the hoh routines, e.g. recursion.f90:1455-1477)
+  ApplyParams pa = p;
+  pa.g[0] = GatherTerm{h->Hh.p, in, 0};
+  pa.ngterms = 1; pa.epi = EPI_STORE; pa.out = tmp; pa.part = nullptr; pa.prev = nullptr;
+  TRY(launch_apply(h, pa, nunits, nctas));
+  if (op == OP_HAM) {
+    // pass B: acc = -(h o)*tmp + (e_nu + l.s)*in + tmp   (H = h - hoh + e_nu + l.s, recursion.f90:1543)
+    p.g[0] = GatherTerm{h->Hho_neg.p, tmp, 0};
+    p.ngterms = 1; p.Hx = h->Hx.p; p.srcx = in; p.addend = tmp;
+  } else {
+    // velo_hoh_vec_matmul: out = v*in - sum_{nb>=2} vo(nb) * (ee*in)(nn)   (recursion.f90:704-778)
+    p.g[0] = GatherTerm{op == OP_VELO_A ? h->Hva.p : h->Hvb.p, in, 0};
+    p.g[1] = GatherTerm{op == OP_VELO_A ? h->Hvoa_neg.p : h->Hvob_neg.p, tmp, 1};
+    p.ngterms = 2;
+  }
+  return launch_apply(h, p, nunits, nctas);
+}
+
+static int launch_gram(H *h, const double *X, const double *Y, int nunits, int nctas, double *part) {
+  dim3 grid(nctas, nunits);
+  k_gram_simt<<<grid, SIMT_THREADS, 0, h->st>>>(X, Y, h->kk, vstride(h), vstride(h), part);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return RSREC_OK;
+}
+static int launch_reduce(H *h, int nunits, int nctas, int mode, double *d0, double *d1, size_t dstride,
+                         const double *m0, const double *m1) {
+  k_reduce_parts<<<nunits, 256, 0, h->st>>>(h->part.p, nctas, mode, d0, d1, dstride, m0, m1);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return RSREC_OK;
+}
+
+static int upload_units(H *h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                        const cplx *bsign) {
+  TRY(ensure_units(h, nunits));
+  std::vector<int32_t> sj(nunits, 0);
+  std::vector<double> as(2 * nunits), bs(2 * nunits);
+  for (int u = 0; u < nunits; u++) {
+    if (site_i[u] < 1 || site_i[u] > h->kk) return fail(RSREC_EINVAL, "start site out of range");
+    if (site_j) {
+      if (site_j[u] < 0 || site_j[u] > h->kk) return fail(RSREC_EINVAL, "start site j out of range");
+      sj[u] = site_j[u];
+    }
+    as[2 * u] = asign ? asign[u].re : 1.0; as[2 * u + 1] = asign ? asign[u].im : 0.0;
+    bs[2 * u] = bsign ? bsign[u].re : 1.0; bs[2 * u + 1] = bsign ? bsign[u].im : 0.0;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->d_si, site_i, nunits * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_sj, sj.data(), nunits * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_as, as.data(), 2 * nunits * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_bs, bs.data(), 2 * nunits * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaStreamSynchronize(h->st));  // host staging vectors go out of scope
+  return RSREC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Block / scalar Lanczos driver: crecal_b (recursion.f90:1873-1973) for a batch of units, entirely on the device.
+static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*18x18xlld complex per unit*/,
+                         double *b2_host) {
+  const int nctas = nctas_for(h, nunits);
+  double *psi, *pmn, *tmp = nullptr;
+  TRY(get_vec(h, 0, nunits, &psi));
+  TRY(get_vec(h, 1, nunits, &pmn));
+  if (h->hoh && !diag) TRY(get_vec(h, 2, nunits, &tmp));
+  TRY(dev_alloc(h->part, (size_t)nunits * nctas * 2 * BLKD, false));
+  TRY(dev_alloc(h->A, (size_t)nunits * BLKD, false));
+  TRY(dev_alloc(h->B, (size_t)nunits * BLKD, false));
+  TRY(dev_alloc(h->Bi, (size_t)nunits * BLKD, false));
+  const size_t hs = (size_t)lld * BLKD;  // history stride per unit (doubles)
+  TRY(dev_alloc(h->ahist, (size_t)nunits * hs, false));
+  TRY(dev_alloc(h->b2hist, (size_t)nunits * hs, false));
+  TRY(zero_vec(h, psi, nunits));
+  TRY(zero_vec(h, pmn, nunits));
+  CUDA_TRY(cudaMemsetAsync(h->ahist.p, 0, (size_t)nunits * hs * sizeof(double), h->st));
+  CUDA_TRY(cudaMemsetAsync(h->b2hist.p, 0, (size_t)nunits * hs * sizeof(double), h->st));
+  k_init_site_start<<<nunits, 32, 0, h->st>>>(psi, vstride(h), h->d_si, h->d_sj, h->d_as, h->d_bs, nunits);
+  k_set_identity<<<nunits, 64, 0, h->st>>>(h->b2hist.p, hs, nunits);  // b2temp_b(:,:,1) = I
+  h->launches += 2;
+  for (int ll = 0; ll < lld - 1; ll++) {
+    // hop_b / hop_b_hoh: pmn = H psi - pmn ; A = sum psi^H H psi
+    TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, h->part.p));
+    TRY(launch_reduce(h, nunits, nctas, diag ? 2 : 0, h->A.p, nullptr, BLKD, nullptr, nullptr));
+    CUDA_TRY(cudaMemcpy2DAsync(h->ahist.p + (size_t)ll * BLKD, hs * sizeof(double), h->A.p, BLKD * sizeof(double),
+                               BLKD * sizeof(double), nunits, cudaMemcpyDeviceToDevice, h->st));
+    // pmn -= psi A ; B2 = sum pmn^H pmn
+    dim3 grid(nctas, nunits);
+    k_lz_ortho_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->A.p, BLKD, h->kk, vstride(h), h->part.p);
+    // B2 -> history slot ll+1, B, B^-1
+    k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->part.p, nctas, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
+                                         BLKD, diag ? 1 : 0);
+    // psi = pmn B^-1 ; pmn = psi_old B
+    k_lz_rotate_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->B.p, h->Bi.p, BLKD, h->kk, vstride(h));
+    h->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaMemcpyAsync(a_host, h->ahist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaMemcpyAsync(b2_host, h->b2hist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Chebyshev session: cheb_0th_mom, cheb_1st_mom(_hoh), chebyshev_recur_ll(_hoh).
+static int cheb_begin_common(H *h, int nunits, int lld, double a, double b) {
+  if (lld < 0) return fail(RSREC_EINVAL, "lld must be >= 0");
+  if (a == 0.0) return fail(RSREC_EINVAL, "a_scale must be non-zero");
+  auto &c = h->cheb;
+  c.nunits = nunits; c.lld = lld; c.a = a; c.b = b; c.done = 0; c.i0 = 0; c.i1 = 1;
+  c.nctas = nctas_for(h, nunits);
+  TRY(dev_alloc(h->part, (size_t)nunits * std::max(c.nctas, dmma_max_ctas(h->sms)) * 2 * BLKD, false));
+  TRY(dev_alloc(h->mu, (size_t)nunits * (2 * lld + 2) * BLKD, false));
+  CUDA_TRY(cudaMemsetAsync(h->mu.p, 0, (size_t)nunits * (2 * lld + 2) * BLKD * sizeof(double), h->st));
+  return RSREC_OK;
+}
+// psi0 (vecs[0]) holds the start vector = psiref.  Computes mu(1), mu(2) and psi1.
+static int cheb_first_moments(H *h) {
+  auto &c = h->cheb;
+  double *p0, *p1, *tmp = nullptr;
+  TRY(get_vec(h, 0, c.nunits, &p0));
+  TRY(get_vec(h, 1, c.nunits, &p1));
+  if (h->hoh) TRY(get_vec(h, 2, c.nunits, &tmp));
+  const size_t ms = (size_t)(2 * c.lld + 2) * BLKD;
+  TRY(launch_gram(h, p0, p0, c.nunits, c.nctas, h->part.p));
+  TRY(launch_reduce(h, c.nunits, c.nctas, 0, h->mu.p, nullptr, ms, nullptr, nullptr));
+  TRY(apply_op(h, OP_HAM, p0, p1, nullptr, tmp, EPI_HAM, c.a, c.b, c.nunits, c.nctas, nullptr));
+  TRY(launch_gram(h, p0, p1, c.nunits, c.nctas, h->part.p));
+  TRY(launch_reduce(h, c.nunits, c.nctas, 0, h->mu.p + BLKD, nullptr, ms, nullptr, nullptr));
+  c.active = true;
+  return RSREC_OK;
+}
+static int cheb_steps(H *h, int nsteps) {
+  auto &c = h->cheb;
+  if (!c.active) return fail(RSREC_EINVAL, "no Chebyshev session (call rsrec_cheb_begin_* first)");
+  if (c.done + nsteps > c.lld) return fail(RSREC_EINVAL, "more steps than lld requested");
+  double *tmp = nullptr;
+  if (h->hoh) TRY(get_vec(h, 2, c.nunits, &tmp));
+  const size_t ms = (size_t)(2 * c.lld + 2) * BLKD;
+  for (int s = 0; s < nsteps; s++) {
+    const int ll = c.done + 1;
+    double *p0 = h->vecs[c.i0].p, *p1 = h->vecs[c.i1].p;
+    // psi2 = 2 (H psi1 - b psi1)/a - psi0, written over psi0; D1 = sum psi1^H psi1, D2 = sum psi2^H psi1
+    TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB, c.a, c.b, c.nunits, c.nctas, h->part.p));
+    const int nparts = h->last_parts;
+    // mu(2ll+1) = 2 D1 - mu(1), mu(2ll+2) = 2 D2 - mu(2)
+    TRY(launch_reduce(h, c.nunits, nparts, 1, h->mu.p + (size_t)(2 * ll) * BLKD,
+                      h->mu.p + (size_t)(2 * ll + 1) * BLKD, ms, h->mu.p, h->mu.p + BLKD));
+    std::swap(c.i0, c.i1);
+    c.done++;
+  }
+  return RSREC_OK;
+}
+static int cheb_finish(H *h, cplx *mu_n) {
+  auto &c = h->cheb;
+  const size_t n = (size_t)c.nunits * (2 * c.lld + 2) * BLKD;
+  CUDA_TRY(cudaMemcpyAsync(mu_n, h->mu.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  c.active = false;
+  // the reference's divergence guard (recursion.f90:2594): sum(real(mu(:,:,2ll+2))) > 1000 -> fatal
+  const double *m = (const double *)mu_n;
+  for (int u = 0; u < c.nunits; u++)
+    for (int k = 3; k < 2 * c.lld + 2; k += 2) {
+      double s = 0.0;
+      const double *blk = m + ((size_t)u * (2 * c.lld + 2) + k) * BLKD;
+      for (int e = 0; e < BLKC; e++) s += blk[2 * e];
+      if (!(s <= 1000.0))
+        return fail(RSREC_EDIVERGED, "Chebyshev moments did not converge. Check energy limits energy_min and energy_max");
+    }
+  return RSREC_OK;
+}
+
+// ============================================================================================================
+extern "C" {
+
+const char *rsrec_last_error(void) { return g_err.c_str(); }
+int rsrec_version(void) { return 100; }
+int rsrec_compiled_arch(void) { return 100; }
+
+int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, int ntype, int nmax) {
+  if (!out) return fail(RSREC_EINVAL, "null handle pointer");
+  *out = nullptr;
+  if (kk < 1 || ncols < 1 || nslot < ncols || ntype < 1 || nmax < 0 || nmax > kk)
+    return fail(RSREC_EINVAL, "rsrec_create: inconsistent sizes (need kk>=1, 1<=ncols<=nslot, ntype>=1, 0<=nmax<=kk)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(RSREC_ECUDA, std::string("no CUDA device available (this library has no CPU path): ") + cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev) return fail(RSREC_EINVAL, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(RSREC_ECUDA, std::string("kernels are built for sm_100a only; device is ") + prop.name);
+  H *h = new H();
+  h->dev = device; h->kk = kk; h->ncols = ncols; h->nslot = nslot; h->ntype = ntype; h->nmax = nmax;
+  h->ncls = ntype + nmax; h->sms = prop.multiProcessorCount;
+  if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  TRY(dmma_configure());
+  *out = h;
+  return RSREC_OK;
+}
+
+int rsrec_destroy(rsrec_handle h) {
+  if (!h) return RSREC_OK;
+  cudaSetDevice(h->dev);
+  cudaStreamSynchronize(h->st);
+  for (auto &v : h->vecs) dev_free(v);
+  DevBuf *bufs[] = {&h->Hmain, &h->Hh, &h->Hho_neg, &h->Hx, &h->Hscalar, &h->Hva, &h->Hvb, &h->Hvoa_neg, &h->Hvob_neg,
+                    &h->part, &h->A, &h->B, &h->Bi, &h->mu, &h->ahist, &h->b2hist, &h->scratch};
+  for (auto b : bufs) dev_free(*b);
+  dmma_free_tiles(h->tiles);
+  if (h->d_nbr) cudaFree(h->d_nbr);
+  if (h->d_cls) cudaFree(h->d_cls);
+  if (h->d_si) { cudaFree(h->d_si); cudaFree(h->d_sj); cudaFree(h->d_as); cudaFree(h->d_bs); }
+  cudaStreamDestroy(h->st);
+  delete h;
+  return RSREC_OK;
+}
+
+int rsrec_set_kernel_family(rsrec_handle h, int family) {
+  if (!h || family < 0 || family > 1) return fail(RSREC_EINVAL, "bad kernel family");
+  h->family = family;
+  return RSREC_OK;
+}
+
+int rsrec_set_lattice(rsrec_handle h, const int32_t *nn, const int32_t *iz) {
+  if (!h || !nn || !iz) return fail(RSREC_EINVAL, "rsrec_set_lattice: null argument");
+  h->nn.assign(nn, nn + (size_t)h->kk * h->ncols);
+  h->iz.assign(iz, iz + h->kk);
+  h->have_lat = true; h->dirty = true;
+  return RSREC_OK;
+}
+
+int rsrec_set_hamiltonian(rsrec_handle h, const cplx *ee, const cplx *eeo, const cplx *hall, const cplx *hallo,
+                          const cplx *lsham, const cplx *enim, int hoh) {
+  if (!h || !ee || !lsham) return fail(RSREC_EINVAL, "rsrec_set_hamiltonian: ee and lsham are required");
+  if (h->nmax > 0 && !hall) return fail(RSREC_EINVAL, "rsrec_set_hamiltonian: hall is required when nmax > 0");
+  if (hoh && (!eeo || !enim || (h->nmax > 0 && !hallo)))
+    return fail(RSREC_EINVAL, "rsrec_set_hamiltonian: eeo, enim (and hallo when nmax > 0) are required when hoh is set");
+  const size_t nt = (size_t)BLKC * h->nslot * h->ntype, nl = (size_t)BLKC * h->nslot * h->nmax, n1 = (size_t)BLKC * h->ntype;
+  h->ee.assign(ee, ee + nt);
+  h->lsham.assign(lsham, lsham + n1);
+  if (h->nmax > 0) h->hall.assign(hall, hall + nl); else h->hall.clear();
+  if (hoh) {
+    h->eeo.assign(eeo, eeo + nt);
+    h->enim.assign(enim, enim + n1);
+    if (h->nmax > 0) h->hallo.assign(hallo, hallo + nl); else h->hallo.clear();
+  }
+  h->hoh = hoh ? 1 : 0;
+  h->have_ham = true; h->dirty = true;
+  return RSREC_OK;
+}
+
+int rsrec_set_operator(rsrec_handle h, int slot, const cplx *v_op, const cplx *vo_op) {
+  if (!h || !v_op || (slot != 'a' && slot != 'b')) return fail(RSREC_EINVAL, "rsrec_set_operator: slot must be 'a' or 'b'");
+  const size_t nt = (size_t)BLKC * h->nslot * h->ntype;
+  const int s = slot == 'a' ? 0 : 1;
+  (s == 0 ? h->v_a : h->v_b).assign(v_op, v_op + nt);
+  if (vo_op) (s == 0 ? h->vo_a : h->vo_b).assign(vo_op, vo_op + nt); else (s == 0 ? h->vo_a : h->vo_b).clear();
+  h->have_op[s] = true; h->dirty = true;
+  return RSREC_OK;
+}
+
+int rsrec_lanczos_block(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                        const cplx *bsign, int lld, cplx *a_b, cplx *b2_b) {
+  if (!h || nunits < 0 || !a_b || !b2_b || lld < 1 || (nunits > 0 && !site_i)) return fail(RSREC_EINVAL, "rsrec_lanczos_block: bad argument");
+  if (nunits == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
+  for (int u0 = 0; u0 < nunits; u0 += ub) {
+    const int n = std::min(ub, nunits - u0);
+    TRY(upload_units(h, n, site_i + u0, site_j ? site_j + u0 : nullptr, asign ? asign + u0 : nullptr, bsign ? bsign + u0 : nullptr));
+    TRY(lanczos_batch(h, n, lld, false, (double *)(a_b + (size_t)u0 * lld * BLKC), (double *)(b2_b + (size_t)u0 * lld * BLKC)));
+  }
+  return RSREC_OK;
+}
+
+int rsrec_lanczos_scalar(rsrec_handle h, int nunits, const int32_t *sites, int lld, double *a, double *b2) {
+  if (!h || nunits < 0 || !a || !b2 || lld < 1 || (nunits > 0 && !sites)) return fail(RSREC_EINVAL, "rsrec_lanczos_scalar: bad argument");
+  if (nunits == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  // The 18 independent scalar recursions of a site (one per start orbital, recursion.f90:3499-3520) are the 18
+  // columns of one block vector with diagonal A and B: run them together and keep Re(diag).
+  const int ub = unit_batch(h, nunits, 2);
+  std::vector<double> ah((size_t)ub * lld * BLKD), bh((size_t)ub * lld * BLKD);
+  for (int u0 = 0; u0 < nunits; u0 += ub) {
+    const int n = std::min(ub, nunits - u0);
+    TRY(upload_units(h, n, sites + u0, nullptr, nullptr, nullptr));
+    TRY(lanczos_batch(h, n, lld, true, ah.data(), bh.data()));
+    for (int u = 0; u < n; u++)
+      for (int l = 0; l < NB; l++)
+        for (int ll = 0; ll < lld; ll++) {
+          const size_t src = ((size_t)u * lld + ll) * BLKD + 2 * (l + NB * l);
+          a[(size_t)ll + (size_t)lld * (l + (size_t)NB * (u0 + u))] = ah[src];
+          b2[(size_t)ll + (size_t)lld * (l + (size_t)NB * (u0 + u))] = bh[src];
+        }
+  }
+  return RSREC_OK;
+}
+
+int rsrec_zsqr(rsrec_handle h, cplx *b2_b, int lld, int na) {
+  if (!h || !b2_b || lld < 0 || na < 0) return fail(RSREC_EINVAL, "rsrec_zsqr: bad argument");
+  const size_t nmat = (size_t)lld * na;
+  if (nmat == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(dev_alloc(h->scratch, nmat * BLKD, false));
+  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, b2_b, nmat * BLKD * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  k_zsqr<<<(unsigned)nmat, BLKC, 0, h->st>>>(h->scratch.p);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(b2_b, h->scratch.p, nmat * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_cheb_begin_sites(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                           const cplx *bsign, int lld, double a, double b) {
+  if (!h || nunits < 1 || !site_i) return fail(RSREC_EINVAL, "rsrec_cheb_begin_sites: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  if (unit_batch(h, nunits, h->hoh ? 3 : 2) < nunits) return fail(RSREC_ENOMEM, "unit batch does not fit in device memory");
+  TRY(upload_units(h, nunits, site_i, site_j, asign, bsign));
+  TRY(cheb_begin_common(h, nunits, lld, a, b));
+  double *p0, *p1;
+  TRY(get_vec(h, 0, nunits, &p0));
+  TRY(get_vec(h, 1, nunits, &p1));
+  TRY(zero_vec(h, p0, nunits));
+  TRY(zero_vec(h, p1, nunits));
+  k_init_site_start<<<nunits, 32, 0, h->st>>>(p0, vstride(h), h->d_si, h->d_sj, h->d_as, h->d_bs, nunits);
+  h->launches++;
+  return cheb_first_moments(h);
+}
+
+int rsrec_cheb_begin_random(rsrec_handle h, int nvec, const double *phases, int lld, double a, double b) {
+  if (!h || nvec < 1 || !phases) return fail(RSREC_EINVAL, "rsrec_cheb_begin_random: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  if (unit_batch(h, nvec, h->hoh ? 3 : 2) < nvec) return fail(RSREC_ENOMEM, "vector batch does not fit in device memory");
+  TRY(cheb_begin_common(h, nvec, lld, a, b));
+  double *p0, *p1;
+  TRY(get_vec(h, 0, nvec, &p0));
+  TRY(get_vec(h, 1, nvec, &p1));
+  TRY(zero_vec(h, p0, nvec));
+  TRY(zero_vec(h, p1, nvec));
+  TRY(dev_alloc(h->scratch, (size_t)h->kk * nvec, false));
+  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, phases, (size_t)h->kk * nvec * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  k_init_random_start<<<h->sms * 4, 256, 0, h->st>>>(p0, vstride(h), h->scratch.p, h->kk, nvec);
+  h->launches++;
+  return cheb_first_moments(h);
+}
+
+int rsrec_cheb_run_steps(rsrec_handle h, int nsteps) {
+  if (!h || nsteps < 0) return fail(RSREC_EINVAL, "rsrec_cheb_run_steps: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  return cheb_steps(h, nsteps);
+}
+
+int rsrec_cheb_end(rsrec_handle h, cplx *mu_n) {
+  if (!h || !mu_n) return fail(RSREC_EINVAL, "rsrec_cheb_end: bad argument");
+  if (!h->cheb.active) return fail(RSREC_EINVAL, "no Chebyshev session");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  return cheb_finish(h, mu_n);
+}
+
+int rsrec_cheb_moments(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                       const cplx *bsign, int lld, double a, double b, cplx *mu_n) {
+  if (!h || nunits < 0 || !mu_n || (nunits > 0 && !site_i)) return fail(RSREC_EINVAL, "rsrec_cheb_moments: bad argument");
+  if (nunits == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
+  int rc_all = RSREC_OK;
+  for (int u0 = 0; u0 < nunits; u0 += ub) {
+    const int n = std::min(ub, nunits - u0);
+    TRY(rsrec_cheb_begin_sites(h, n, site_i + u0, site_j ? site_j + u0 : nullptr, asign ? asign + u0 : nullptr,
+                               bsign ? bsign + u0 : nullptr, lld, a, b));
+    TRY(cheb_steps(h, lld));
+    int rc = cheb_finish(h, mu_n + (size_t)u0 * (2 * lld + 2) * BLKC);
+    if (rc == RSREC_EDIVERGED) rc_all = rc; else TRY(rc);
+  }
+  return rc_all;
+}
+
+int rsrec_cheb_moments_random(rsrec_handle h, int nvec, const double *phases, int lld, double a, double b, cplx *mu_n) {
+  if (!h || nvec < 0 || !mu_n || (nvec > 0 && !phases)) return fail(RSREC_EINVAL, "rsrec_cheb_moments_random: bad argument");
+  if (nvec == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  const int ub = unit_batch(h, nvec, h->hoh ? 3 : 2);
+  int rc_all = RSREC_OK;
+  for (int u0 = 0; u0 < nvec; u0 += ub) {
+    const int n = std::min(ub, nvec - u0);
+    TRY(rsrec_cheb_begin_random(h, n, phases + (size_t)u0 * h->kk, lld, a, b));
+    TRY(cheb_steps(h, lld));
+    int rc = cheb_finish(h, mu_n + (size_t)u0 * (2 * lld + 2) * BLKC);
+    if (rc == RSREC_EDIVERGED) rc_all = rc; else TRY(rc);
+  }
+  return rc_all;
+}
+
+// host (18,18,kk) complex <-> device RI36 through the scratch buffer
+static int upload_vec(H *h, const cplx *src, double *dst) {
+  TRY(dev_alloc(h->scratch, (size_t)h->kk * BLKD, false));
+  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, src, (size_t)h->kk * BLKD * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  k_host_to_ri36<<<h->sms * 4, 256, 0, h->st>>>(h->scratch.p, dst, h->kk);
+  h->launches++;
+  return RSREC_OK;
+}
+static int download_vec(H *h, const double *src, cplx *dst) {
+  TRY(dev_alloc(h->scratch, (size_t)h->kk * BLKD, false));
+  k_ri36_to_host<<<h->sms * 4, 256, 0, h->st>>>(src, h->scratch.p, h->kk);
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(dst, h->scratch.p, (size_t)h->kk * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_ham_vec_matmul(rsrec_handle h, const cplx *psi_in, cplx *psi_out, double a, double b) {
+  if (!h || !psi_in || !psi_out || a == 0.0) return fail(RSREC_EINVAL, "rsrec_ham_vec_matmul: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  double *vin, *vout, *tmp = nullptr;
+  TRY(get_vec(h, 0, 1, &vin));
+  TRY(get_vec(h, 1, 1, &vout));
+  if (h->hoh) TRY(get_vec(h, 2, 1, &tmp));
+  TRY(upload_vec(h, psi_in, vin));
+  TRY(apply_op(h, OP_HAM, vin, vout, nullptr, tmp, EPI_HAM, a, b, 1, nctas_for(h, 1), nullptr));
+  return download_vec(h, vout, psi_out);
+}
+
+int rsrec_velo_vec_matmul(rsrec_handle h, int slot, const cplx *psi_in, cplx *psi_out) {
+  if (!h || !psi_in || !psi_out || (slot != 'a' && slot != 'b')) return fail(RSREC_EINVAL, "rsrec_velo_vec_matmul: bad argument");
+  if (!h->have_op[slot == 'a' ? 0 : 1]) return fail(RSREC_EINVAL, "rsrec_set_operator has not been called for this slot");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  double *vin, *vout, *tmp = nullptr;
+  TRY(get_vec(h, 0, 1, &vin));
+  TRY(get_vec(h, 1, 1, &vout));
+  if (h->hoh) TRY(get_vec(h, 2, 1, &tmp));
+  TRY(upload_vec(h, psi_in, vin));
+  TRY(apply_op(h, slot == 'a' ? OP_VELO_A : OP_VELO_B, vin, vout, nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas_for(h, 1), nullptr));
+  return download_vec(h, vout, psi_out);
+}
+
+// compute_moments_stochastic (recursion.f90:1105-1230): left vectors T_m|r> are stored (like the reference's
+// left_vec), the right chain v_a T_n v_b |r> is contracted against all of them after every step.
+int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
+                       int M, double a, double b, cplx *mu_nm) {
+  if (!h || nstart < 0 || M < 1 || !mu_nm || a == 0.0) return fail(RSREC_EINVAL, "rsrec_kubo_moments: bad argument");
+  if (start_kind == 0 ? !start_sites : !phases) return fail(RSREC_EINVAL, "rsrec_kubo_moments: missing start data");
+  if (!h->have_op[0] || !h->have_op[1]) return fail(RSREC_EINVAL, "rsrec_set_operator must be called for slots 'a' and 'b'");
+  if (nstart == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  if (unit_batch(h, 1, M + 6) < 1) return fail(RSREC_ENOMEM, "left-vector storage does not fit in device memory");
+  const int nctas = nctas_for(h, 1);
+  // vecs: 0 psiref, 1 tmp(hoh), 2 v0, 3 v1, 4 right, 5 spare, 6.. left[m]
+  double *psiref, *tmp, *v0, *v1, *right, *spare;
+  TRY(get_vec(h, 0, 1, &psiref)); TRY(get_vec(h, 1, 1, &tmp)); TRY(get_vec(h, 2, 1, &v0));
+  TRY(get_vec(h, 3, 1, &v1)); TRY(get_vec(h, 4, 1, &right)); TRY(get_vec(h, 5, 1, &spare));
+  std::vector<double *> left(M);
+  for (int m = 0; m < M; m++) TRY(get_vec(h, 6 + m, 1, &left[m]));
+  TRY(dev_alloc(h->part, (size_t)nctas * 2 * BLKD, false));
+  TRY(dev_alloc(h->mu, (size_t)M * M * BLKD, false));
+  const int32_t one = 1;
+  for (int s = 0; s < nstart; s++) {
+    TRY(zero_vec(h, psiref, 1));
+    if (start_kind == 0) {
+      TRY(upload_units(h, 1, start_sites + s, nullptr, nullptr, nullptr));
+      k_init_site_start<<<1, 32, 0, h->st>>>(psiref, vstride(h), h->d_si, h->d_sj, h->d_as, h->d_bs, 1);
+    } else {
+      TRY(dev_alloc(h->scratch, (size_t)h->kk, false));
+      CUDA_TRY(cudaMemcpyAsync(h->scratch.p, phases + (size_t)s * h->kk, (size_t)h->kk * sizeof(double), cudaMemcpyHostToDevice, h->st));
+      k_init_random_start<<<h->sms * 4, 256, 0, h->st>>>(psiref, vstride(h), h->scratch.p, h->kk, 1);
+    }
+    h->launches++;
+    (void)one;
+    // left chain: T_1 = start, T_2 = H~ T_1, T_m = 2 H~ T_{m-1} - T_{m-2}
+    CUDA_TRY(cudaMemcpyAsync(left[0], psiref, vstride(h) * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    if (M > 1) TRY(apply_op(h, OP_HAM, left[0], left[1], nullptr, tmp, EPI_HAM, a, b, 1, nctas, nullptr));
+    for (int m = 2; m < M; m++)
+      TRY(apply_op(h, OP_HAM, left[m - 1], left[m], left[m - 2], tmp, EPI_CHEB_NOGRAM, a, b, 1, nctas, nullptr));
+    // right chain
+    TRY(apply_op(h, OP_VELO_B, psiref, v0, nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas, nullptr));
+    double *c0 = v0, *c1 = v1, *c2 = spare;  // T_{n-2}, T_{n-1}, scratch
+    for (int n = 0; n < M; n++) {
+      double *cur;
+      if (n == 0) {
+        cur = c0;
+      } else if (n == 1) {
+        TRY(apply_op(h, OP_HAM, c0, c1, nullptr, tmp, EPI_HAM, a, b, 1, nctas, nullptr));
+        cur = c1;
+      } else {
+        TRY(apply_op(h, OP_HAM, c1, c2, c0, tmp, EPI_CHEB_NOGRAM, a, b, 1, nctas, nullptr));
+        double *t = c0; c0 = c1; c1 = c2; c2 = t;
+        cur = c1;
+      }
+      TRY(apply_op(h, OP_VELO_A, cur, right, nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas, nullptr));
+      for (int m = 0; m < M; m++) {
+        TRY(launch_gram(h, left[m], right, 1, nctas, h->part.p));
+        // mu_nm_stochastic(:,:,n,m,i)
+        TRY(launch_reduce(h, 1, nctas, 0, h->mu.p + ((size_t)n + (size_t)M * m) * BLKD, nullptr, 0, nullptr, nullptr));
+      }
+    }
+    CUDA_TRY(cudaMemcpyAsync(mu_nm + (size_t)s * M * M * BLKC, h->mu.p, (size_t)M * M * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+  }
+  return RSREC_OK;
+}
+
+int rsrec_synchronize(rsrec_handle h) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+void *rsrec_stream(rsrec_handle h) { return h ? (void *)h->st : nullptr; }
+long long rsrec_launch_count(rsrec_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

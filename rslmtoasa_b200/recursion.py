@@ -1,0 +1,262 @@
+"""Host-side mirror of the reference's `type recursion` (source/recursion.f90:41-116) on top of the C ABI.
+
+Same procedure names, the same result members with the same shapes and index conventions, and the same error
+behaviour (a fatal condition raises instead of `g_logger%fatal`).  Everything numerical happens inside
+librsrec.so on the GPU; this module only marshals the reference's arrays.
+
+    rec = Recursion(hamiltonian, lattice, control, energy)      # recursion(hamiltonian_obj, energy_obj), 132-143
+    rec.recur_b()            -> rec.a_b, rec.b2_b (18,18,lld,nrec_local), rec.a, rec.b2      (1807-1866)
+    rec.recur_b_ij()         -> rec.a_b, rec.b2_b (18,18,lld,4*njij_local)                   (1655-1737)
+    rec.recur()              -> rec.a, rec.b2 (lld,18,nrec_local,1)                          (3485-3532)
+    rec.chebyshev_recur()    -> rec.mu_n (18,18,2*lld+2,nrec_local)                          (3057-3130)
+    rec.chebyshev_recur_ij() -> rec.mu_n (18,18,2*lld+2,4*njij_local)                        (2376-2487)
+    rec.compute_moments_stochastic() -> rec.mu_nm_stochastic (18,18,M,M,ntype|nvec)          (979-1234)
+    rec.zsqr()               -> rec.b2_b <- sqrt                                             (1980-2023)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import numpy as np
+
+from . import _lib
+from .synthetic import partition
+
+NB = 18
+ONE_OVER_SQRT_TWO = 1.0 / np.sqrt(2.0)
+
+
+@dataclasses.dataclass
+class Control:
+    """The `&control` entries the recursion reads (reference control.f90:356-384)."""
+    lld: int = 16
+    recur: str = "block"            # lanczos | block | chebyshev
+    cond_ll: int = 200
+    cond_calctype: str = "per_type"  # per_type | random_vec
+    random_vec_num: int = 1
+
+
+@dataclasses.dataclass
+class Energy:
+    """`&energy energy_min, energy_max` (reference energy.f90); defines the Chebyshev scale a and shift b."""
+    energy_min: float = -1.5
+    energy_max: float = 1.5
+
+    def scale_shift(self):
+        # recursion.f90:3078-3079
+        return (self.energy_max - self.energy_min) / (2 - 0.3), (self.energy_max + self.energy_min) / 2
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _fc(a):
+    return None if a is None else np.asfortranarray(a, dtype=np.complex128)
+
+
+class Recursion:
+    def __init__(self, hamiltonian, lattice, control: Control | None = None, energy: Energy | None = None,
+                 device: int = 0, rank: int = 0, numprocs: int = 1, ijpair=None, atlist=None, phases=None):
+        self.hamiltonian, self.lattice = hamiltonian, lattice
+        self.control = control or Control()
+        self.en = energy or Energy()
+        self.rank, self.numprocs = rank, numprocs
+        self.ijpair = None if ijpair is None else np.asarray(ijpair, dtype=np.int32).reshape(-1, 2)
+        self.atlist = atlist
+        self.phases = phases          # (kk, random_vec_num): the host supplies the random numbers
+        self.a = self.b2 = self.a_b = self.b2_b = self.mu_n = self.mu_nm_stochastic = None
+        L = _lib.load()
+        self._L = L
+        self._h = C.c_void_p()
+        _lib.check(L.rsrec_create(C.byref(self._h), device, lattice.kk, lattice.ncols, lattice.nslot, lattice.ntype,
+                                  lattice.nmax))
+        self.upload()
+
+    # -- data export of the lattice / hamiltonian builders ------------------------------------------------
+    def upload(self):
+        """Re-export nn/iz and the block sets (what `self%run_recursion` does every SCF iteration, self.f90:777-797)."""
+        L, lat, ham = self._L, self.lattice, self.hamiltonian
+        nn = np.asfortranarray(lat.nn, dtype=np.int32)
+        iz = np.ascontiguousarray(lat.iz, dtype=np.int32)
+        _lib.check(L.rsrec_set_lattice(self._h, _p(nn), _p(iz)))
+        arrs = [_fc(getattr(ham, k, None)) for k in ("ee", "eeo", "hall", "hallo", "lsham", "enim")]
+        _lib.check(L.rsrec_set_hamiltonian(self._h, *[_p(x) for x in arrs], int(bool(ham.hoh))))
+        if getattr(ham, "v_a", None) is not None:
+            for slot in ("a", "b"):
+                v, vo = _fc(getattr(ham, "v_" + slot)), _fc(getattr(ham, "vo_" + slot, None))
+                _lib.check(L.rsrec_set_operator(self._h, ord(slot), _p(v), _p(vo)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.rsrec_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers --------------------------------------------------------------------------------------------
+    def _local_units(self, n):
+        s, e = partition(self.rank, self.numprocs, n)   # get_mpi_variables, mpi.f90:32-58
+        return s, e
+
+    def set_kernel_family(self, family: int):
+        _lib.check(self._L.rsrec_set_kernel_family(self._h, family))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.rsrec_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.rsrec_stream(self._h) or 0)
+
+    def _pair_units(self):
+        """Unit list of recur_b_ij / chebyshev_recur_ij: slot ij_loc*4-4+reci; i==j keeps only reci=1 with signs 1,1."""
+        s, e = self._local_units(len(self.ijpair))
+        nloc = max(e - s + 1, 0)
+        slots, si, sj, asg, bsg = [], [], [], [], []
+        signs = [(1, 1), (1, -1), (1, 1j), (1, -1j)]
+        for ij in range(s, e + 1):
+            i, j = (int(v) for v in self.ijpair[ij - 1])
+            for reci in range(1, 5):
+                if i == j and reci > 1:
+                    continue
+                a_, b_ = ((1.0, 1.0) if i == j else
+                          (signs[reci - 1][0] * ONE_OVER_SQRT_TWO, signs[reci - 1][1] * ONE_OVER_SQRT_TWO))
+                slots.append((ij - s) * 4 + reci - 1)
+                si.append(i); sj.append(j); asg.append(a_); bsg.append(b_)
+        return nloc, slots, (np.array(si, np.int32), np.array(sj, np.int32), np.array(asg, np.complex128),
+                             np.array(bsg, np.complex128))
+
+    # -- block Lanczos --------------------------------------------------------------------------------------
+    def _lanczos_block(self, si, sj, asg, bsg):
+        lld, n = self.control.lld, len(si)
+        a_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        b2_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        _lib.check(self._L.rsrec_lanczos_block(self._h, n, _p(si), _p(sj), _p(asg), _p(bsg), lld, _p(a_b), _p(b2_b)))
+        return a_b, b2_b
+
+    def recur_b(self):
+        s, e = self._local_units(len(self.lattice.irec))
+        sites = np.ascontiguousarray(self.lattice.irec[s - 1:e], dtype=np.int32)
+        self.a_b, self.b2_b = self._lanczos_block(sites, None, None, None)
+        lld = self.control.lld
+        self.a = np.zeros((lld, NB, len(sites), 3), order="F")
+        self.b2 = np.zeros((lld, NB, len(sites), 3), order="F")
+        d = np.arange(NB)
+        self.a[:, :, :, 0] = np.real(self.a_b[d, d]).transpose(1, 0, 2)    # a(ll,l,i,1) = real(atemp_b(l,l,ll))
+        self.b2[:, :, :, 0] = np.real(self.b2_b[d, d]).transpose(1, 0, 2)
+
+    def recur_b_ij(self):
+        nloc, slots, (si, sj, asg, bsg) = self._pair_units()
+        a_b, b2_b = self._lanczos_block(si, sj, asg, bsg)
+        lld = self.control.lld
+        self.a_b = np.zeros((NB, NB, lld, 4 * nloc), np.complex128, order="F")
+        self.b2_b = np.zeros((NB, NB, lld, 4 * nloc), np.complex128, order="F")
+        self.a_b[..., slots] = a_b
+        self.b2_b[..., slots] = b2_b
+
+    def zsqr(self):
+        b = np.asfortranarray(self.b2_b)
+        _lib.check(self._L.rsrec_zsqr(self._h, _p(b), b.shape[2], b.shape[3]))
+        self.b2_b = b
+
+    # -- scalar Lanczos -------------------------------------------------------------------------------------
+    def recur(self):
+        s, e = self._local_units(len(self.lattice.irec))
+        sites = np.ascontiguousarray(self.lattice.irec[s - 1:e], dtype=np.int32)
+        lld = self.control.lld
+        a = np.zeros((lld, NB, len(sites)), order="F")
+        b2 = np.zeros((lld, NB, len(sites)), order="F")
+        _lib.check(self._L.rsrec_lanczos_scalar(self._h, len(sites), _p(sites), lld, _p(a), _p(b2)))
+        self.a = np.zeros((lld, NB, len(sites), 3), order="F")
+        self.b2 = np.zeros((lld, NB, len(sites), 3), order="F")
+        self.a[..., 0], self.b2[..., 0] = a, b2
+
+    # -- Chebyshev ------------------------------------------------------------------------------------------
+    def _cheb(self, si, sj, asg, bsg):
+        lld, n = self.control.lld, len(si)
+        a, b = self.en.scale_shift()
+        mu = np.zeros((NB, NB, 2 * lld + 2, n), np.complex128, order="F")
+        _lib.check(self._L.rsrec_cheb_moments(self._h, n, _p(si), _p(sj), _p(asg), _p(bsg), lld, a, b, _p(mu)))
+        return mu
+
+    def chebyshev_recur(self):
+        s, e = self._local_units(len(self.lattice.irec))
+        sites = np.ascontiguousarray(self.lattice.irec[s - 1:e], dtype=np.int32)
+        self.mu_n = self._cheb(sites, None, None, None)
+
+    def chebyshev_recur_ij(self):
+        nloc, slots, (si, sj, asg, bsg) = self._pair_units()
+        mu = self._cheb(si, sj, asg, bsg)
+        self.mu_n = np.zeros((NB, NB, 2 * self.control.lld + 2, 4 * nloc), np.complex128, order="F")
+        self.mu_n[..., slots] = mu
+
+    def chebyshev_recur_random(self, phases=None):
+        """KPM moments from random-phase start blocks (the start vector of recursion.f90:1131-1143), sharded over
+        ranks with the reference's block rule; the caller all-reduces `mu_n.sum(-1)`."""
+        ph = np.asfortranarray(self.phases if phases is None else phases, dtype=np.float64)
+        s, e = self._local_units(ph.shape[1])
+        loc = np.asfortranarray(ph[:, s - 1:e])
+        lld = self.control.lld
+        a, b = self.en.scale_shift()
+        mu = np.zeros((NB, NB, 2 * lld + 2, loc.shape[1]), np.complex128, order="F")
+        if loc.shape[1]:
+            _lib.check(self._L.rsrec_cheb_moments_random(self._h, loc.shape[1], _p(loc), lld, a, b, _p(mu)))
+        self.mu_n = mu
+
+    # -- Kubo-Bastin ----------------------------------------------------------------------------------------
+    def compute_moments_stochastic(self):
+        M = self.control.cond_ll
+        a, b = self.en.scale_shift()
+        if self.control.cond_calctype == "per_type":
+            sites = np.ascontiguousarray(self.atlist, dtype=np.int32)
+            mu = np.zeros((NB, NB, M, M, len(sites)), np.complex128, order="F")
+            _lib.check(self._L.rsrec_kubo_moments(self._h, len(sites), 0, _p(sites), None, M, a, b, _p(mu)))
+        else:
+            ph = np.asfortranarray(self.phases, dtype=np.float64)
+            mu = np.zeros((NB, NB, M, M, ph.shape[1]), np.complex128, order="F")
+            _lib.check(self._L.rsrec_kubo_moments(self._h, ph.shape[1], 1, None, _p(ph), M, a, b, _p(mu)))
+        self.mu_nm_stochastic = mu
+
+    # -- single operator applications -------------------------------------------------------------------------
+    def ham_vec_matmul(self, psi_in, a, b):
+        pin = _fc(psi_in)
+        out = np.zeros_like(pin, order="F")
+        _lib.check(self._L.rsrec_ham_vec_matmul(self._h, _p(pin), _p(out), a, b))
+        return out
+
+    def velo_vec_matmul(self, slot, psi_in):
+        pin = _fc(psi_in)
+        out = np.zeros_like(pin, order="F")
+        _lib.check(self._L.rsrec_velo_vec_matmul(self._h, ord(slot), _p(pin), _p(out)))
+        return out
+
+    # -- device-resident stepping (bench) -----------------------------------------------------------------------
+    def cheb_begin_random(self, phases, lld):
+        ph = np.asfortranarray(phases, dtype=np.float64)
+        a, b = self.en.scale_shift()
+        self._sess = (ph.shape[1], lld)
+        _lib.check(self._L.rsrec_cheb_begin_random(self._h, ph.shape[1], _p(ph), lld, a, b))
+
+    def cheb_begin_sites(self, sites, lld):
+        si = np.ascontiguousarray(sites, dtype=np.int32)
+        a, b = self.en.scale_shift()
+        self._sess = (len(si), lld)
+        _lib.check(self._L.rsrec_cheb_begin_sites(self._h, len(si), _p(si), None, None, None, lld, a, b))
+
+    def cheb_run_steps(self, n):
+        _lib.check(self._L.rsrec_cheb_run_steps(self._h, n))
+
+    def cheb_end(self):
+        n, lld = self._sess
+        mu = np.zeros((NB, NB, 2 * lld + 2, n), np.complex128, order="F")
+        _lib.check(self._L.rsrec_cheb_end(self._h, _p(mu)))
+        return mu
+
+    def synchronize(self):
+        _lib.check(self._L.rsrec_synchronize(self._h))

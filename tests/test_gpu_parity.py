@@ -1,0 +1,211 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: a_n/b_n 1e-10 relative (over the stable depth), mu_n 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from tests.cases import case, relerr, EMIN, EMAX
+
+pytestmark = pytest.mark.gpu
+
+TOL_AB = 1e-10
+TOL_MU = 1e-9
+
+
+def _rec(lat, ham, **kw):
+    from rslmtoasa_b200 import Recursion, Control, Energy
+    ctl = Control(**{k: v for k, v in kw.items() if k in ("lld", "cond_ll", "cond_calctype", "random_vec_num")})
+    extra = {k: v for k, v in kw.items() if k in ("ijpair", "atlist", "phases", "rank", "numprocs")}
+    return Recursion(ham, lat, ctl, Energy(EMIN, EMAX), **extra)
+
+
+@pytest.mark.parametrize("family", [0, 1])
+@pytest.mark.parametrize("name", ["bulk", "bulk_hoh", "surface", "impurity", "impurity_hoh", "pbc", "tiny"])
+def test_recur_b(oracle_mod, name, family):
+    lat, ham = case(name)
+    lld = 8
+    rec = _rec(lat, ham, lld=lld)
+    rec.set_kernel_family(family)
+    rec.recur_b()
+    orc = oracle_mod.Oracle(lat, ham)
+    a_b, b2_b = orc.lanczos_block(lat.irec, lld)
+    assert rec.a_b.shape == a_b.shape
+    assert relerr(rec.a_b, a_b) < TOL_AB
+    assert relerr(rec.b2_b, b2_b) < TOL_AB
+    d = np.arange(18)
+    assert np.array_equal(rec.a[:, :, :, 0], np.real(rec.a_b[d, d]).transpose(1, 0, 2))
+
+
+@pytest.mark.parametrize("family", [0, 1])
+@pytest.mark.parametrize("name", ["bulk", "impurity_hoh"])
+def test_recur_b_ij(oracle_mod, name, family):
+    lat, ham = case(name)
+    lld = 6
+    pairs = np.array([[1, 2], [3, 3], [2, 7]], dtype=np.int32)
+    rec = _rec(lat, ham, lld=lld, ijpair=pairs)
+    rec.set_kernel_family(family)
+    rec.recur_b_ij()
+    orc = oracle_mod.Oracle(lat, ham)
+    s = 1 / np.sqrt(2)
+    signs = [(s, s), (s, -s), (s, 1j * s), (s, -1j * s)]
+    for ij, (i, j) in enumerate(pairs):
+        for reci in range(4):
+            slot = ij * 4 + reci
+            if i == j and reci > 0:
+                assert not rec.a_b[..., slot].any()
+                continue
+            a_, b_ = (1.0, 1.0) if i == j else signs[reci]
+            a_b, b2_b = orc.lanczos_block([i], lld, site_j=[j], asign=[a_], bsign=[b_])
+            assert relerr(rec.a_b[..., slot], a_b[..., 0]) < TOL_AB
+            assert relerr(rec.b2_b[..., slot], b2_b[..., 0]) < TOL_AB
+
+
+@pytest.mark.parametrize("name", ["bulk", "impurity"])
+def test_recur_scalar(oracle_mod, name):
+    lat, ham = case(name)
+    lld = 9
+    rec = _rec(lat, ham, lld=lld)
+    rec.recur()
+    a, b2 = oracle_mod.Oracle(lat, ham).lanczos_scalar(lat.irec, lld)
+    assert relerr(rec.a[..., 0], a) < TOL_AB
+    assert relerr(rec.b2[..., 0], b2) < TOL_AB
+
+
+def test_zsqr(oracle_mod):
+    lat, ham = case("bulk")
+    rec = _rec(lat, ham, lld=6)
+    rec.recur_b()
+    ref = oracle_mod.Oracle(lat, ham).zsqr(rec.b2_b)
+    b2 = rec.b2_b.copy()
+    rec.zsqr()
+    assert relerr(rec.b2_b, ref) < 1e-10
+    for ll in range(6):
+        assert relerr(rec.b2_b[:, :, ll, 0] @ rec.b2_b[:, :, ll, 0], b2[:, :, ll, 0]) < 1e-11
+
+
+@pytest.mark.parametrize("family", [0, 1])
+@pytest.mark.parametrize("name", ["bulk", "bulk_hoh", "surface", "impurity", "impurity_hoh", "pbc", "tiny"])
+def test_chebyshev_recur(oracle_mod, name, family):
+    lat, ham = case(name)
+    lld = 12
+    rec = _rec(lat, ham, lld=lld)
+    rec.set_kernel_family(family)
+    rec.chebyshev_recur()
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    mu, rc = oracle_mod.Oracle(lat, ham).cheb_moments(lat.irec, lld, a, b)
+    assert rc == 0
+    assert rec.mu_n.shape == mu.shape
+    assert relerr(rec.mu_n, mu) < TOL_MU
+
+
+@pytest.mark.parametrize("family", [0, 1])
+def test_chebyshev_recur_ij(oracle_mod, family):
+    lat, ham = case("bulk")
+    lld = 7
+    pairs = np.array([[1, 4], [5, 5]], dtype=np.int32)
+    rec = _rec(lat, ham, lld=lld, ijpair=pairs)
+    rec.set_kernel_family(family)
+    rec.chebyshev_recur_ij()
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    orc = oracle_mod.Oracle(lat, ham)
+    s = 1 / np.sqrt(2)
+    mu, _ = orc.cheb_moments([1, 1, 1, 1, 5], lld, a, b, site_j=[4, 4, 4, 4, 5],
+                             asign=[s, s, s, s, 1.0], bsign=[s, -s, 1j * s, -1j * s, 1.0])
+    assert relerr(rec.mu_n[..., [0, 1, 2, 3, 4]], mu) < TOL_MU
+    assert not rec.mu_n[..., 5:].any()
+
+
+@pytest.mark.parametrize("family", [0, 1])
+@pytest.mark.parametrize("name", ["pbc", "bulk_hoh"])
+def test_chebyshev_random(oracle_mod, name, family):
+    from rslmtoasa_b200 import synthetic as S
+    lat, ham = case(name)
+    lld = 10
+    ph = S.random_phases(lat.kk, 3)
+    rec = _rec(lat, ham, lld=lld, phases=ph)
+    rec.set_kernel_family(family)
+    rec.chebyshev_recur_random()
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    mu, rc = oracle_mod.Oracle(lat, ham).cheb_moments_random(ph, lld, a, b)
+    assert relerr(rec.mu_n, mu) < TOL_MU
+
+
+def test_chebyshev_diverged(oracle_mod):
+    """energy window far too small -> the reference calls fatal; we return RSREC_EDIVERGED."""
+    from rslmtoasa_b200 import Recursion, Control, Energy, RsrecError
+    lat, ham = case("bulk")
+    rec = Recursion(ham, lat, Control(lld=40), Energy(-0.05, 0.05))
+    with pytest.raises(RsrecError) as ei:
+        rec.chebyshev_recur()
+    assert ei.value.code == -2
+    a, b = oracle_mod.cheb_scale(-0.05, 0.05)
+    _, rc = oracle_mod.Oracle(lat, ham).cheb_moments(lat.irec, 40, a, b)
+    assert rc == -2
+
+
+@pytest.mark.parametrize("name", ["pbc", "impurity", "pbc_hoh"])
+def test_ham_and_velo_vec_matmul(oracle_mod, name):
+    lat, ham = case(name)
+    if getattr(ham, "v_a", None) is None:
+        from rslmtoasa_b200 import synthetic as S
+        h2 = S.make_hamiltonian(lat, seed=20260103, velocity=True)
+        ham.v_a, ham.v_b = h2.v_a, h2.v_b
+    rng = np.random.default_rng(5)
+    psi = np.asfortranarray(rng.normal(size=(18, 18, lat.kk)) + 1j * rng.normal(size=(18, 18, lat.kk)))
+    rec = _rec(lat, ham)
+    orc = oracle_mod.Oracle(lat, ham)
+    ones = np.ones(lat.kk + 1, np.int32); ones[0] = 0
+    a, b = 1.7, -0.2
+    ref, _ = orc.ham_vec_matmul(psi, a, b, ones)
+    assert relerr(rec.ham_vec_matmul(psi, a, b), ref) < 1e-12
+    for slot in "ab":
+        ref, _ = orc.velo_vec_matmul(slot, psi, ones)
+        assert relerr(rec.velo_vec_matmul(slot, psi), ref) < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["per_type", "random_vec"])
+@pytest.mark.parametrize("name", ["pbc", "pbc_hoh"])
+def test_compute_moments_stochastic(oracle_mod, name, kind):
+    from rslmtoasa_b200 import synthetic as S
+    lat, ham = case(name)
+    M = 6
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    orc = oracle_mod.Oracle(lat, ham)
+    if kind == "per_type":
+        rec = _rec(lat, ham, cond_ll=M, cond_calctype=kind, atlist=[1])
+        ref = orc.kubo_moments(M, a, b, start_sites=[1])
+    else:
+        ph = S.random_phases(lat.kk, 2)
+        rec = _rec(lat, ham, cond_ll=M, cond_calctype=kind, phases=ph)
+        ref = orc.kubo_moments(M, a, b, phases=ph)
+    rec.compute_moments_stochastic()
+    assert rec.mu_nm_stochastic.shape == ref.shape
+    assert relerr(rec.mu_nm_stochastic, ref) < TOL_MU
+
+
+def test_rank_partition_matches_reference_rule():
+    """units are sharded with get_mpi_variables' rule; concatenating the shards reproduces the 1-rank result."""
+    lat, ham = case("surface")
+    full = _rec(lat, ham, lld=5)
+    full.chebyshev_recur()
+    parts = []
+    for r in range(3):
+        rec = _rec(lat, ham, lld=5, rank=r, numprocs=3)
+        rec.chebyshev_recur()
+        parts.append(rec.mu_n)
+    assert np.array_equal(np.concatenate(parts, axis=-1), full.mu_n)
+
+
+def test_device_resident_stepping_matches_one_shot():
+    from rslmtoasa_b200 import synthetic as S
+    lat, ham = case("pbc")
+    ph = S.random_phases(lat.kk, 2)
+    rec = _rec(lat, ham, lld=9, phases=ph)
+    rec.chebyshev_recur_random()
+    rec.cheb_begin_random(ph, 9)
+    rec.cheb_run_steps(4)
+    rec.cheb_run_steps(5)
+    mu = rec.cheb_end()
+    assert np.array_equal(mu, rec.mu_n)
+    assert rec.launch_count > 0
