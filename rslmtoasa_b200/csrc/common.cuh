@@ -4,9 +4,9 @@
 // (kk+1) site blocks of 648 doubles; column c of a site occupies 36 consecutive doubles, real parts of rows 0..17
 // first, imaginary parts next:  re(k,c) = blk[c*36 + k],  im(k,c) = blk[c*36 + 18 + k].  Block kk is the "null
 // site": always zero, target of nn(i,j)=0 entries, so gathers need no branch.  A Hamiltonian block H(18,18) is
-// held row-wise the same way:  re H(r,k) = blk[r*36 + k],  im H(r,k) = blk[r*36 + 18 + k].  With this layout a
-// complex 18x18x18 product is the real product  [Cr;Ci](36 x n) = [[Hr,-Hi],[Hi,Hr]] (36x36) * [Pr;Pi] (36 x n),
-// which is what the FP64 tensor-core (DMMA m8n8k4) kernels consume; every block is 5184 B = the reference's size.
+// held as its 36x36 REAL embedding ("HR36", row-major, 1296 doubles):  Hreal = [[Hr,-Hi],[Hi,Hr]], so that a
+// complex 18x18x18 product is the real product  [Cr;Ci](36 x n) = Hreal (36x36) * [Pr;Pi] (36 x n), which is what
+// the FP64 tensor-core (DMMA m8n8k4) kernels consume without any sign/offset fix-ups in the inner loop.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,7 +14,8 @@
 #define NB 18
 #define BLKC 324      // complex elements per block
 #define BLKD 648      // doubles per block
-#define COLD 36       // doubles per RI36 column / H row
+#define COLD 36       // doubles per RI36 column / HR36 row
+#define HBLK 1296     // doubles per HR36 Hamiltonian block (36x36 real embedding)
 
 enum Epilogue {
   EPI_STORE = 0,  // out = acc
@@ -25,7 +26,7 @@ enum Epilogue {
 };
 
 struct GatherTerm {
-  const double *H;    // [ncls][nslot_h][648]
+  const double *H;    // [ncls][nslot_h][HBLK]
   const double *src;  // block vector(s) gathered through the neighbour table
   int first_slot;     // 0 = include the on-site slot, 1 = neighbours only
 };

@@ -1,12 +1,462 @@
-// kernels_dmma.cuh -- FP64 tensor-core (DMMA m8n8k4) pipeline (kernel family 1).  STUB: filled in next.
+// kernels_dmma.cuh -- FP64 tensor-core pipeline (kernel family 1), hand-written for sm_100a.
+//
+// The 18-column block recursion is FP64-COMPUTE bound on B200 (~51 flop/B against a machine balance of
+// ~6 flop/B), so the hot loops run on the FP64 tensor pipe: `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4), measured at
+// 37.1 TFLOP/s on this B200 against 33.6 for plain DFMA (profiles/r01_fp64_peak_microbench.txt).  tcgen05/TMEM
+// has no FP64 kind, so DMMA is the Blackwell tensor path for this arithmetic.
+//
+// k_apply_dmma: persistent, warp-specialised gather-SpMV.  A CTA owns a tile of 8 sites (144 vector columns) of one
+// Hamiltonian class.  For every neighbour slot the producer warp issues TMA bulk copies (cp.async.bulk, one 5184 B
+// psi block per neighbour + one 10368 B HR36 Hamiltonian block) into a 3-stage shared-memory ring guarded by
+// mbarriers; 8 consumer warps compute  C^T[n][r] += Psi[k'][n] * Hreal[r][k']  (M = 144 site-columns, N = 36 -> 40
+// output rows, K = 36) with DMMA and keep the accumulators in registers across all slots.  The 90 (m-tile, n-tile)
+// units of a stage are split 22/23/22/23 over the four SM sub-partitions.  The epilogue (scale/shift, three-term
+// update) is applied straight from the accumulator fragments with 16 B global accesses; the on-site slot is
+// scheduled last so that psi_self is still in shared memory when the epilogue needs it.
+//
+// k_gram_dmma: D = sum_sites Y^H X (and X^H X) as real DMMA products on the RI36 columns:  Re D(i,j) = <Ycol_i, Xcol_j>,
+// Im D(i,j) = <Ycol_i, J Xcol_j>.  One site per warp per step, per-warp 2-stage TMA ring, 25 accumulator tiles per warp.
 #pragma once
 #include "common.cuh"
+#include <algorithm>
 #include <vector>
-struct DmmaTiles { int ntiles = 0; };
-static int dmma_configure() { return 0; }
-static int dmma_build_tiles(DmmaTiles &, const std::vector<int32_t> &, const std::vector<int32_t> &, int, int, int) { return 0; }
-static void dmma_free_tiles(DmmaTiles &) {}
-static bool dmma_supported(const ApplyParams &) { return false; }
-static int dmma_max_ctas(int sms) { return sms; }
-static int dmma_parts_for(const DmmaTiles &, int sms, int) { return sms; }
-static int dmma_launch_apply(DmmaTiles &, ApplyParams &, int, int, cudaStream_t, long long *) { return -1; }
+
+#define DM_S 8                               // sites per tile
+#define DM_STAGES 3
+#define DM_STAGE_D (HBLK + DM_S * BLKD)      // doubles per stage: H block + 8 psi blocks = 6480 (51840 B)
+#define DM_CONSUMERS 8
+#define DM_THREADS (32 * (DM_CONSUMERS + 1))
+#define DM_MAXST 48
+#define DM_SMEM_BYTES (DM_STAGES * DM_STAGE_D * 8 + 64)
+
+struct DmmaTiles {
+  int ntiles = 0, ng = 0, kk = 0;
+  int32_t *d_sites = nullptr;  // [ntiles][8]      site ids (kk = null)
+  int32_t *d_cls = nullptr;    // [ntiles]
+  int32_t *d_nbr = nullptr;    // [ntiles][ng][8]  neighbour site ids per slot
+};
+
+struct DmmaStages {  // stage list of one tile, in execution order (self stage last)
+  const double *H[DM_MAXST];
+  const double *src[DM_MAXST];
+  int hstride[DM_MAXST];  // doubles between classes
+  int slot[DM_MAXST];     // neighbour slot, 0 = self
+  int n;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---- fused gather-SpMV + epilogue ---------------------------------------------------------------------------
+template <int EPI, bool ADDEND>
+__global__ void __launch_bounds__(DM_THREADS, 1)
+k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_sites, const int32_t *__restrict__ tile_cls,
+             const int32_t *__restrict__ tile_nbr, int ntiles, int nunits) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stages = reinterpret_cast<double *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)DM_STAGES * DM_STAGE_D * 8);
+  uint64_t *empty = full + DM_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < DM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], DM_CONSUMERS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nst = st.n, ng = p.ngather;
+  const double inv_a = 1.0 / p.a;  // the epilogue multiplies by 1/a (<= 1 ulp from the reference's division)
+
+  if (warp == DM_CONSUMERS) {
+    // ===== producer warp: TMA bulk copies =====
+    uint32_t it = 0;
+    for (int u = 0; u < nunits; u++) {
+      const size_t uo = (size_t)u * p.vstride;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int cls = tile_cls[tile];
+        for (int j = 0; j < nst; j++, it++) {
+          const int slot = it % DM_STAGES;
+          mbar_wait(&empty[slot], ((it / DM_STAGES) & 1) ^ 1);
+          double *sm = stages + (size_t)slot * DM_STAGE_D;
+          if (lane == 0) mbar_expect_tx(&full[slot], DM_STAGE_D * 8);
+          __syncwarp();
+          if (lane < DM_S) {
+            const int m = st.slot[j];
+            const int site = (m == 0) ? tile_sites[tile * DM_S + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + lane];
+            bulk_g2s(sm + HBLK + lane * BLKD, st.src[j] + uo + (size_t)site * BLKD, BLKD * 8, &full[slot]);
+          } else if (lane == DM_S) {
+            bulk_g2s(sm, st.H[j] + (size_t)cls * st.hstride[j], HBLK * 8, &full[slot]);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps: DMMA =====
+  const int g = lane >> 2, q = lane & 3;
+  const int sp = warp & 3;            // SM sub-partition this warp lands on
+  const bool first = warp < 4;        // first warp of the sub-partition also owns part of an extra m-tile
+  const int mt0 = first ? 4 * sp : 4 * sp + 2, mt1 = mt0 + 1, mt2 = 16 + (sp >> 1);
+  const int x_lo = first ? ((sp & 1) ? 2 : 0) : 0, x_hi = first ? ((sp & 1) ? 5 : 2) : 0;  // n-tiles of the extra tile
+  int aoff[3], boff[5];
+  aoff[0] = HBLK + (mt0 * 8 + g) * COLD + q;
+  aoff[1] = HBLK + (mt1 * 8 + g) * COLD + q;
+  aoff[2] = HBLK + (mt2 * 8 + g) * COLD + q;
+#pragma unroll
+  for (int nt = 0; nt < 5; nt++) boff[nt] = min(nt * 8 + g, 35) * COLD + q;
+
+  uint32_t it = 0;
+  for (int u = 0; u < nunits; u++) {
+    const size_t uo = (size_t)u * p.vstride;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      double acc[3][5][2];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++) acc[i][nt][0] = acc[i][nt][1] = 0.0;
+      // global element offsets of this lane's accumulator rows (one site-column per m-tile)
+      size_t goff[3];
+      bool gval[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const int n = (i == 0 ? mt0 : i == 1 ? mt1 : mt2) * 8 + g;
+        const int site = tile_sites[tile * DM_S + n / NB];
+        gval[i] = site < p.kk;
+        goff[i] = uo + (size_t)site * BLKD + (n % NB) * COLD + 2 * q;
+      }
+      double2 pv[3][5];  // prefetched `prev` (psi0 / pmn) fragments
+      for (int j = 0; j < nst; j++, it++) {
+        const int slot = it % DM_STAGES;
+        if ((EPI == EPI_CHEB_NOGRAM || EPI == EPI_HOP) && j == nst - 1) {
+          // issue the epilogue's global loads now; they land while the last stage is being computed
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int nt = 0; nt < 5; nt++) {
+              const bool own = (i < 2) || (nt >= x_lo && nt < x_hi);
+              const bool ok = own && gval[i] && (nt < 4 || q < 2);
+              pv[i][nt] = ok ? __ldg(reinterpret_cast<const double2 *>(p.prev + goff[i] + nt * 8)) : make_double2(0.0, 0.0);
+            }
+        }
+        mbar_wait(&full[slot], (it / DM_STAGES) & 1);
+        const double *sm = stages + (size_t)slot * DM_STAGE_D;
+#pragma unroll
+        for (int ks = 0; ks < 9; ks++) {
+          double b[5];
+#pragma unroll
+          for (int nt = 0; nt < 5; nt++) b[nt] = sm[boff[nt] + 4 * ks];
+          const double a0 = sm[aoff[0] + 4 * ks], a1 = sm[aoff[1] + 4 * ks];
+#pragma unroll
+          for (int nt = 0; nt < 5; nt++) {
+            dmma(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
+            dmma(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
+          }
+          if (first) {
+            const double a2 = sm[aoff[2] + 4 * ks];
+#pragma unroll
+            for (int nt = 0; nt < 5; nt++)
+              if (nt >= x_lo && nt < x_hi) dmma(acc[2][nt][0], acc[2][nt][1], a2, b[nt]);
+          }
+        }
+        if (j < nst - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+      }
+      // ===== epilogue from the accumulator fragments; the last stage (self blocks of `in`) is still held =====
+      const int lslot = (it - 1) % DM_STAGES;
+      const double *sm = stages + (size_t)lslot * DM_STAGE_D;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        if (i == 2 && !first) continue;
+        const int n = (i == 0 ? mt0 : i == 1 ? mt1 : mt2) * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++) {
+          const bool own = (i < 2) || (nt >= x_lo && nt < x_hi);
+          if (!own || !gval[i] || !(nt < 4 || q < 2)) continue;
+          double v0 = acc[i][nt][0], v1 = acc[i][nt][1];
+          const size_t go = goff[i] + nt * 8;
+          if (ADDEND) {
+            const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go));
+            v0 += ad.x; v1 += ad.y;
+          }
+          if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
+            const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + nt * 8 + 2 * q);
+            v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
+            if (EPI == EPI_CHEB_NOGRAM) { v0 = 2.0 * v0 - pv[i][nt].x; v1 = 2.0 * v1 - pv[i][nt].y; }
+          } else if (EPI == EPI_HOP) {
+            v0 = v0 - pv[i][nt].x; v1 = v1 - pv[i][nt].y;
+          }
+          *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[lslot]);
+    }
+  }
+}
+
+// ---- Gram reductions on the tensor pipe -------------------------------------------------------------------------
+#define GR_WARPS 8
+#define GR_THREADS (32 * GR_WARPS)
+#define GR_STAGE_D (2 * BLKD)   // X block + Y block
+#define GR_SMEM_BYTES (GR_WARPS * 2 * GR_STAGE_D * 8 + GR_WARPS * 2 * 8)
+
+// two != 0:  part[.][0] = sum X^H X, part[.][1] = sum Y^H X;   two == 0:  part[.][0] = sum Y^H X, part[.][1] = 0.
+// grid = (ctas, nunits); partials in complex column-major (i + 18 j) like the host arrays.
+__global__ void __launch_bounds__(GR_THREADS, 1)
+k_gram_dmma(const double *__restrict__ X, const double *__restrict__ Y, int two, int kk, size_t xstride, size_t ystride,
+            double *part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sbase = reinterpret_cast<double *>(smem_raw);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)GR_WARPS * 2 * GR_STAGE_D * 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int unit = blockIdx.y;
+  const double *Xu = X + (size_t)unit * xstride, *Yu = Y + (size_t)unit * ystride;
+  double *wsm = sbase + (size_t)warp * 2 * GR_STAGE_D;
+  uint64_t *wbar = bars + warp * 2;
+  if (lane == 0) { mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  // fragment source offsets (doubles, relative to the stage base: X block at 0, Y block at BLKD)
+  const int nmt = two ? 5 : 3;
+  int aoff[5], boff[5], bneg_from[5];  // B operand: k' >= bneg_from -> negate (never: 99)
+  bool bswap[5];
+#pragma unroll
+  for (int mt = 0; mt < 5; mt++) {
+    const int i = mt * 8 + g;
+    if (two) aoff[mt] = (i < NB) ? i * COLD : BLKD + min(i - NB, NB - 1) * COLD;
+    else aoff[mt] = BLKD + min(i, NB - 1) * COLD;
+  }
+#pragma unroll
+  for (int nt = 0; nt < 5; nt++) {
+    const int j = nt * 8 + g;
+    bswap[nt] = j >= NB;
+    boff[nt] = (j < NB ? j : min(j - NB, NB - 1)) * COLD;
+  }
+  double acc[5][5][2];
+#pragma unroll
+  for (int mt = 0; mt < 5; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+  const int stride = gridDim.x * GR_WARPS;
+  const int s0 = blockIdx.x * GR_WARPS + warp;
+  // prologue: up to two sites in flight
+  for (int pf = 0; pf < 2; pf++) {
+    const int site = s0 + pf * stride;
+    if (site < kk && lane == 0) {
+      mbar_expect_tx(&wbar[pf], GR_STAGE_D * 8);
+      bulk_g2s(wsm + (size_t)pf * GR_STAGE_D, Xu + (size_t)site * BLKD, BLKD * 8, &wbar[pf]);
+      bulk_g2s(wsm + (size_t)pf * GR_STAGE_D + BLKD, Yu + (size_t)site * BLKD, BLKD * 8, &wbar[pf]);
+    }
+  }
+  int itn = 0;
+  for (int site = s0; site < kk; site += stride, itn++) {
+    const int slot = itn & 1;
+    mbar_wait(&wbar[slot], (itn >> 1) & 1);
+    const double *sm = wsm + (size_t)slot * GR_STAGE_D;
+#pragma unroll
+    for (int ks = 0; ks < 9; ks++) {
+      const int k = 4 * ks + q;
+      double b[5];
+#pragma unroll
+      for (int nt = 0; nt < 5; nt++) {
+        // Re part: Xcol_j[k'];  Im part: (J X)col_j[k'] = k'<18 ? Xcol[k'+18] : -Xcol[k'-18]
+        const int kk2 = bswap[nt] ? (k < NB ? k + NB : k - NB) : k;
+        double v = sm[boff[nt] + kk2];
+        if (bswap[nt] && k >= NB) v = -v;
+        b[nt] = v;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 5; mt++) {
+        if (mt >= nmt) continue;
+        const double a = sm[aoff[mt] + k];
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++) dmma(acc[mt][nt][0], acc[mt][nt][1], a, b[nt]);
+      }
+    }
+    __syncwarp();
+    const int nsite = site + 2 * stride;
+    if (nsite < kk && lane == 0) {
+      mbar_expect_tx(&wbar[slot], GR_STAGE_D * 8);
+      bulk_g2s(wsm + (size_t)slot * GR_STAGE_D, Xu + (size_t)nsite * BLKD, BLKD * 8, &wbar[slot]);
+      bulk_g2s(wsm + (size_t)slot * GR_STAGE_D + BLKD, Yu + (size_t)nsite * BLKD, BLKD * 8, &wbar[slot]);
+    }
+  }
+  // fixed-order cross-warp reduction through shared memory (reusing the staging area): red[warp][40][40]
+  __syncthreads();
+  double *red = sbase;  // 8 * 1600 doubles = 102400 B <= staging size
+#pragma unroll
+  for (int mt = 0; mt < 5; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) {
+      red[(size_t)warp * 1600 + (mt * 8 + g) * 40 + nt * 8 + 2 * q] = acc[mt][nt][0];
+      red[(size_t)warp * 1600 + (mt * 8 + g) * 40 + nt * 8 + 2 * q + 1] = acc[mt][nt][1];
+    }
+  __syncthreads();
+  double *pp = part + ((size_t)unit * gridDim.x + blockIdx.x) * (2 * BLKD);
+  for (int e = tid; e < 2 * BLKD; e += GR_THREADS) {
+    const int which = e / BLKD, idx = e % BLKD, ce = idx >> 1, im = idx & 1, i = ce % NB, j = ce / NB;
+    double s = 0.0;
+    if (two || which == 0) {
+      const int row = (two ? which * NB : 0) + i, col = im * NB + j;
+      for (int w = 0; w < GR_WARPS; w++) s += red[(size_t)w * 1600 + row * 40 + col];
+    }
+    pp[e] = s;
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+static int dmma_configure() {
+  cudaError_t e;
+#define DM_ATTR(K) \
+  if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES)) != cudaSuccess) return -3;
+  DM_ATTR((k_apply_dmma<EPI_STORE, false>))
+  DM_ATTR((k_apply_dmma<EPI_STORE, true>))
+  DM_ATTR((k_apply_dmma<EPI_HAM, false>))
+  DM_ATTR((k_apply_dmma<EPI_HAM, true>))
+  DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, false>))
+  DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, true>))
+  DM_ATTR((k_apply_dmma<EPI_HOP, false>))
+  DM_ATTR((k_apply_dmma<EPI_HOP, true>))
+#undef DM_ATTR
+  if ((e = cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES)) != cudaSuccess) return -3;
+  return 0;
+}
+
+static void dmma_free_tiles(DmmaTiles &t) {
+  if (t.d_sites) cudaFree(t.d_sites);
+  if (t.d_cls) cudaFree(t.d_cls);
+  if (t.d_nbr) cudaFree(t.d_nbr);
+  t = DmmaTiles();
+}
+
+// Tiles = up to 8 sites of one Hamiltonian class, ordered by their first site so that consecutive CTAs touch
+// neighbouring parts of the vector (L2 reuse of the gathered blocks).  nbr: [ng][kk], cls: [kk].
+static int dmma_build_tiles(DmmaTiles &t, const std::vector<int32_t> &nbr, const std::vector<int32_t> &cls, int kk, int ng,
+                            int ncls) {
+  dmma_free_tiles(t);
+  std::vector<std::vector<int32_t>> by_cls(ncls);
+  for (int i = 0; i < kk; i++) by_cls[cls[i]].push_back(i);
+  struct T { int32_t s[DM_S]; int32_t c; };
+  std::vector<T> tiles;
+  for (int c = 0; c < ncls; c++)
+    for (size_t o = 0; o < by_cls[c].size(); o += DM_S) {
+      T x;
+      x.c = c;
+      for (int k = 0; k < DM_S; k++) x.s[k] = (o + k < by_cls[c].size()) ? by_cls[c][o + k] : kk;
+      tiles.push_back(x);
+    }
+  std::sort(tiles.begin(), tiles.end(), [](const T &a, const T &b) { return a.s[0] < b.s[0]; });
+  const int nt = (int)tiles.size();
+  std::vector<int32_t> hs((size_t)nt * DM_S), hc(nt), hn((size_t)nt * ng * DM_S);
+  for (int i = 0; i < nt; i++) {
+    hc[i] = tiles[i].c;
+    for (int k = 0; k < DM_S; k++) {
+      const int s = tiles[i].s[k];
+      hs[(size_t)i * DM_S + k] = s;
+      for (int m = 0; m < ng; m++) hn[((size_t)i * ng + m) * DM_S + k] = (s < kk) ? nbr[(size_t)m * kk + s] : kk;
+    }
+  }
+  if (cudaMalloc(&t.d_sites, hs.size() * 4) != cudaSuccess || cudaMalloc(&t.d_cls, hc.size() * 4) != cudaSuccess ||
+      cudaMalloc(&t.d_nbr, hn.size() * 4) != cudaSuccess)
+    return -4;
+  cudaMemcpy(t.d_sites, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_cls, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_nbr, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice);
+  t.ntiles = nt; t.ng = ng; t.kk = kk;
+  return 0;
+}
+
+// The epilogues that read `in` need its self blocks in the last pipeline stage.
+static bool dmma_supported(const ApplyParams &p) {
+  // EPI_CHEB / EPI_HOP carry reductions: the caller runs EPI_CHEB_NOGRAM / EPI_STORE + k_gram_dmma instead
+  if (p.epi == EPI_CHEB || p.epi == EPI_HOP) return false;
+  int nst = 0;
+  for (int t = 0; t < p.ngterms; t++) nst += p.ngather - p.g[t].first_slot;
+  if (p.Hx) nst++;
+  if (nst < 1 || nst > DM_MAXST) return false;
+  if (p.epi == EPI_HAM || p.epi == EPI_CHEB_NOGRAM) {
+    if (p.Hx) return p.srcx == p.in;
+    return p.ngterms == 1 && p.g[0].first_slot == 0 && p.g[0].src == p.in;
+  }
+  return true;
+}
+static int dmma_grid(const DmmaTiles &t, int sms) { return std::max(1, std::min(t.ntiles, sms)); }
+static int dmma_gram_ctas(int kk, int sms) { return std::max(1, std::min(sms, (kk + GR_WARPS - 1) / GR_WARPS)); }
+
+static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, cudaStream_t st, long long *launches) {
+  DmmaStages sg;
+  sg.n = 0;
+  // neighbour slots of every term first, then the on-site slots, then the on-site extra term (self stage last)
+  for (int pass = 0; pass < 2; pass++)
+    for (int tm = 0; tm < p.ngterms; tm++)
+      for (int m = (pass == 0 ? std::max(1, p.g[tm].first_slot) : 0); m < (pass == 0 ? p.ngather : 1); m++) {
+        if (pass == 1 && p.g[tm].first_slot > 0) continue;
+        sg.H[sg.n] = p.g[tm].H + (size_t)m * HBLK;
+        sg.src[sg.n] = p.g[tm].src;
+        sg.hstride[sg.n] = p.nslot_h * HBLK;
+        sg.slot[sg.n] = m;
+        sg.n++;
+      }
+  if (p.Hx) {
+    sg.H[sg.n] = p.Hx; sg.src[sg.n] = p.srcx; sg.hstride[sg.n] = HBLK; sg.slot[sg.n] = 0;
+    sg.n++;
+  }
+  const int grid = dmma_grid(t, sms);
+#define DM_LAUNCH(E, A) \
+  k_apply_dmma<E, A><<<grid, DM_THREADS, DM_SMEM_BYTES, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr, t.ntiles, nunits)
+  const bool ad = p.addend != nullptr;
+  switch (p.epi) {
+    case EPI_STORE: if (ad) DM_LAUNCH(EPI_STORE, true); else DM_LAUNCH(EPI_STORE, false); break;
+    case EPI_HAM: if (ad) DM_LAUNCH(EPI_HAM, true); else DM_LAUNCH(EPI_HAM, false); break;
+    case EPI_CHEB_NOGRAM: if (ad) DM_LAUNCH(EPI_CHEB_NOGRAM, true); else DM_LAUNCH(EPI_CHEB_NOGRAM, false); break;
+    case EPI_HOP: if (ad) DM_LAUNCH(EPI_HOP, true); else DM_LAUNCH(EPI_HOP, false); break;
+    default: return -1;
+  }
+#undef DM_LAUNCH
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+static int dmma_launch_gram(const double *X, const double *Y, int two, int kk, size_t vstride, int nunits, int sms,
+                            double *part, cudaStream_t st, long long *launches) {
+  dim3 grid(dmma_gram_ctas(kk, sms), nunits);
+  k_gram_dmma<<<grid, GR_THREADS, GR_SMEM_BYTES, st>>>(X, Y, two, kk, vstride, vstride, part);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

@@ -9,11 +9,12 @@
 #define SIMT_THREADS 324
 
 __device__ __forceinline__ void load_block_T(const double *__restrict__ g, double *s_re, double *s_im, int tid) {
-  // H block rows [r*36 + k | r*36+18+k]  ->  smem [k][r] (re, im) so that lanes (consecutive r) are conflict-free
+  // HR36 block (Hr = rows 0..17, Hi = rows 18..35 of the first 18 columns)  ->  smem [k][r] (re, im) so that
+  // lanes (consecutive r) are conflict-free
   for (int e = tid; e < BLKC; e += SIMT_THREADS) {
     int r = e / NB, k = e % NB;
     s_re[k * NB + r] = g[r * COLD + k];
-    s_im[k * NB + r] = g[r * COLD + NB + k];
+    s_im[k * NB + r] = g[(r + NB) * COLD + k];
   }
 }
 __device__ __forceinline__ void load_block(const double *__restrict__ g, double *s, int tid) {
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_apply_simt(ApplyParams p) {
         const int nb = p.nbr[(size_t)m * p.kk + site];
         if (nb == p.kk) continue;  // null site: contributes exact zeros
         __syncthreads();
-        load_block_T(gt.H + ((size_t)cls * p.nslot_h + m) * BLKD, Hs_re, Hs_im, tid);
+        load_block_T(gt.H + ((size_t)cls * p.nslot_h + m) * HBLK, Hs_re, Hs_im, tid);
         load_block(gt.src + uo + (size_t)nb * BLKD, Ps, tid);
         __syncthreads();
         mac_block(Hs_re, Hs_im, Ps, r, c, ar, ai);
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_apply_simt(ApplyParams p) {
     }
     if (p.Hx) {
       __syncthreads();
-      load_block_T(p.Hx + (size_t)cls * BLKD, Hs_re, Hs_im, tid);
+      load_block_T(p.Hx + (size_t)cls * HBLK, Hs_re, Hs_im, tid);
       load_block(p.srcx + uo + (size_t)site * BLKD, Ps, tid);
       __syncthreads();
       mac_block(Hs_re, Hs_im, Ps, r, c, ar, ai);
@@ -155,8 +156,10 @@ __global__ void k_reduce_parts(const double *part, int nctas, int mode, double *
 }
 
 // pmn -= psi * A ;  B2 partial += pmn^H pmn          crecal_b, recursion.f90:1922-1934
-__global__ void __launch_bounds__(SIMT_THREADS) k_lz_ortho_simt(const double *psi, double *pmn, const double *Amat,
-                                                                size_t astride, int kk, size_t vstride, double *part) {
+// hpsi != null: pmn = hpsi - pmn first (the hop_b update, recursion.f90:1641, when the SpMV kernel only stored H psi)
+__global__ void __launch_bounds__(SIMT_THREADS) k_lz_ortho_simt(const double *psi, double *pmn, const double *hpsi,
+                                                                const double *Amat, size_t astride, int kk,
+                                                                size_t vstride, double *part) {
   __shared__ double As_re[BLKC], As_im[BLKC], Ps[BLKD], Xs[BLKD];
   const int tid = threadIdx.x, r = tid % NB, c = tid / NB, unit = blockIdx.y;
   const size_t uo = (size_t)unit * vstride;
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_lz_ortho_simt(const double *ps
     __syncthreads();
     const size_t so = uo + (size_t)site * BLKD + c * COLD + r;
     double ar = pmn[so], ai = pmn[so + NB];
+    if (hpsi) { ar = hpsi[so] - ar; ai = hpsi[so + NB] - ai; }
 #pragma unroll
     for (int k = 0; k < NB; k++) {  // (psi A)(r,c) = sum_k psi(r,k) A(k,c)
       const double pr = Ps[k * COLD + r], pi = Ps[k * COLD + NB + r];

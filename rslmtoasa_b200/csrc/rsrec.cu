@@ -97,20 +97,20 @@ static int zero_vec(H *h, double *v, int nunits) {
   return RSREC_OK;
 }
 
-// host complex col-major block (r + 18 k) -> device row layout [r*36 + k | r*36 + 18 + k], scaled
-static void pack_block(const cplx *src, double *dst, double scale) {
+// host complex col-major block (r + 18 k) -> HR36 real embedding [[Hr,-Hi],[Hi,Hr]] (36x36 row-major), scaled
+static void add_block(const cplx *src, double *dst, double scale = 1.0) {
   for (int k = 0; k < NB; k++)
     for (int r = 0; r < NB; r++) {
-      dst[r * COLD + k] = scale * src[r + NB * k].re;
-      dst[r * COLD + NB + k] = scale * src[r + NB * k].im;
+      const double re = scale * src[r + NB * k].re, im = scale * src[r + NB * k].im;
+      dst[r * COLD + k] += re;
+      dst[r * COLD + NB + k] -= im;
+      dst[(r + NB) * COLD + k] += im;
+      dst[(r + NB) * COLD + NB + k] += re;
     }
 }
-static void add_block(const cplx *src, double *dst) {
-  for (int k = 0; k < NB; k++)
-    for (int r = 0; r < NB; r++) {
-      dst[r * COLD + k] += src[r + NB * k].re;
-      dst[r * COLD + NB + k] += src[r + NB * k].im;
-    }
+static void pack_block(const cplx *src, double *dst, double scale) {
+  for (int e = 0; e < HBLK; e++) dst[e] = 0.0;
+  add_block(src, dst, scale);
 }
 
 static int upload(DevBuf &b, const std::vector<double> &host) {
@@ -152,31 +152,35 @@ static int ensure_ready(H *h) {
     return loc.data() + (size_t)BLKC * (m + (size_t)nslot * (c - h->ntype));
   };
   auto cls_type = [&](int c) { return c < h->ntype ? c : h->iz[c - h->ntype] - 1; };
-  const size_t setn = (size_t)ncls * nslot * BLKD;
+  const size_t setn = (size_t)ncls * nslot * HBLK;
   std::vector<double> hm(setn, 0.0), hs(setn, 0.0);
   for (int c = 0; c < ncls; c++)
     for (int m = 0; m < nslot; m++) {
       const cplx *b = src_block(h->ee, h->hall, c, m);
-      double *d = hm.data() + ((size_t)c * nslot + m) * BLKD;
+      double *d = hm.data() + ((size_t)c * nslot + m) * HBLK;
       pack_block(b, d, 1.0);
       if (m == 0) add_block(h->lsham.data() + (size_t)BLKC * cls_type(c), d);  // locham = H_on + lsham (1582, 1608)
       // scalar recursion: only the two 9x9 spin-diagonal sub-blocks act, no lsham (recursion.f90:3337-3342)
-      double *s = hs.data() + ((size_t)c * nslot + m) * BLKD;
+      cplx sd[BLKC];
       for (int k = 0; k < NB; k++)
-        for (int r = 0; r < NB; r++)
-          if ((r < 9) == (k < 9)) { s[r * COLD + k] = b[r + NB * k].re; s[r * COLD + NB + k] = b[r + NB * k].im; }
+        for (int r = 0; r < NB; r++) {
+          const bool keep = (r < 9) == (k < 9);
+          sd[r + NB * k].re = keep ? b[r + NB * k].re : 0.0;
+          sd[r + NB * k].im = keep ? b[r + NB * k].im : 0.0;
+        }
+      pack_block(sd, hs.data() + ((size_t)c * nslot + m) * HBLK, 1.0);
     }
   TRY(upload(h->Hmain, hm));
   TRY(upload(h->Hscalar, hs));
   if (h->hoh) {
-    std::vector<double> hh(setn, 0.0), ho(setn, 0.0), hx((size_t)ncls * BLKD, 0.0);
+    std::vector<double> hh(setn, 0.0), ho(setn, 0.0), hx((size_t)ncls * HBLK, 0.0);
     for (int c = 0; c < ncls; c++) {
       for (int m = 0; m < nslot; m++) {
-        pack_block(src_block(h->ee, h->hall, c, m), hh.data() + ((size_t)c * nslot + m) * BLKD, 1.0);
-        pack_block(src_block(h->eeo, h->hallo, c, m), ho.data() + ((size_t)c * nslot + m) * BLKD, -1.0);
+        pack_block(src_block(h->ee, h->hall, c, m), hh.data() + ((size_t)c * nslot + m) * HBLK, 1.0);
+        pack_block(src_block(h->eeo, h->hallo, c, m), ho.data() + ((size_t)c * nslot + m) * HBLK, -1.0);
       }
-      pack_block(h->enim.data() + (size_t)BLKC * cls_type(c), hx.data() + (size_t)c * BLKD, 1.0);
-      add_block(h->lsham.data() + (size_t)BLKC * cls_type(c), hx.data() + (size_t)c * BLKD);
+      pack_block(h->enim.data() + (size_t)BLKC * cls_type(c), hx.data() + (size_t)c * HBLK, 1.0);
+      add_block(h->lsham.data() + (size_t)BLKC * cls_type(c), hx.data() + (size_t)c * HBLK);
     }
     TRY(upload(h->Hh, hh));
     TRY(upload(h->Hho_neg, ho));
@@ -190,14 +194,14 @@ static int ensure_ready(H *h) {
     std::vector<double> hv(setn, 0.0), hvo(setn, 0.0);
     for (int c = 0; c < h->ntype; c++)
       for (int m = 0; m < nslot; m++) {
-        pack_block(v.data() + (size_t)BLKC * (m + (size_t)nslot * c), hv.data() + ((size_t)c * nslot + m) * BLKD, 1.0);
+        pack_block(v.data() + (size_t)BLKC * (m + (size_t)nslot * c), hv.data() + ((size_t)c * nslot + m) * HBLK, 1.0);
         if (h->hoh && !vo.empty() && m > 0)  // on-site vo term is commented out in the reference (761)
-          pack_block(vo.data() + (size_t)BLKC * (m + (size_t)nslot * c), hvo.data() + ((size_t)c * nslot + m) * BLKD, -1.0);
+          pack_block(vo.data() + (size_t)BLKC * (m + (size_t)nslot * c), hvo.data() + ((size_t)c * nslot + m) * HBLK, -1.0);
       }
     TRY(upload(s == 0 ? h->Hva : h->Hvb, hv));
     if (h->hoh) TRY(upload(s == 0 ? h->Hvoa_neg : h->Hvob_neg, hvo));
   }
-  TRY(dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls));
+  if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
   h->dirty = false;
   return RSREC_OK;
 }
@@ -235,8 +239,9 @@ enum OpKind { OP_HAM = 0, OP_SCALAR = 1, OP_VELO_A = 2, OP_VELO_B = 3 };
 
 static int launch_apply(H *h, ApplyParams &p, int nunits, int nctas) {
   if (h->family == 1 && dmma_supported(p)) {
-    TRY(dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches));
-    h->last_parts = dmma_parts_for(h->tiles, h->sms, nunits);
+    if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches) != 0)
+      return fail(RSREC_ECUDA, std::string("k_apply_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->last_parts = 0;
     return RSREC_OK;
   }
   h->last_parts = nctas;
@@ -279,16 +284,27 @@ static int apply_op(H *h, OpKind op, const double *in, double *out, const double
   return launch_apply(h, p, nunits, nctas);
 }
 
+// part[unit][cta][0] = sum_sites X^H Y  (k_gram_simt / k_gram_dmma argument order: first factor is conjugated)
 static int launch_gram(H *h, const double *X, const double *Y, int nunits, int nctas, double *part) {
+  if (h->family == 1) {
+    if (dmma_launch_gram(Y, X, 0, h->kk, vstride(h), nunits, h->sms, part, h->st, &h->launches) != 0)
+      return fail(RSREC_ECUDA, std::string("k_gram_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    h->last_parts = dmma_gram_ctas(h->kk, h->sms);
+    return RSREC_OK;
+  }
   dim3 grid(nctas, nunits);
   k_gram_simt<<<grid, SIMT_THREADS, 0, h->st>>>(X, Y, h->kk, vstride(h), vstride(h), part);
   h->launches++;
+  h->last_parts = nctas;
   CUDA_TRY(cudaGetLastError());
   return RSREC_OK;
 }
-static int launch_reduce(H *h, int nunits, int nctas, int mode, double *d0, double *d1, size_t dstride,
+static size_t part_doubles(const H *h, int nunits, int nctas) {
+  return (size_t)nunits * std::max(nctas, dmma_gram_ctas(h->kk, h->sms)) * 2 * BLKD;
+}
+static int launch_reduce(H *h, int nunits, int /*nctas*/, int mode, double *d0, double *d1, size_t dstride,
                          const double *m0, const double *m1) {
-  k_reduce_parts<<<nunits, 256, 0, h->st>>>(h->part.p, nctas, mode, d0, d1, dstride, m0, m1);
+  k_reduce_parts<<<nunits, 256, 0, h->st>>>(h->part.p, h->last_parts, mode, d0, d1, dstride, m0, m1);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return RSREC_OK;
@@ -325,7 +341,9 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   TRY(get_vec(h, 0, nunits, &psi));
   TRY(get_vec(h, 1, nunits, &pmn));
   if (h->hoh && !diag) TRY(get_vec(h, 2, nunits, &tmp));
-  TRY(dev_alloc(h->part, (size_t)nunits * nctas * 2 * BLKD, false));
+  double *hpsi = nullptr;
+  if (h->family == 1) TRY(get_vec(h, 3, nunits, &hpsi));
+  TRY(dev_alloc(h->part, part_doubles(h, nunits, nctas), false));
   TRY(dev_alloc(h->A, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->B, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->Bi, (size_t)nunits * BLKD, false));
@@ -341,15 +359,21 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   h->launches += 2;
   for (int ll = 0; ll < lld - 1; ll++) {
     // hop_b / hop_b_hoh: pmn = H psi - pmn ; A = sum psi^H H psi
-    TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, h->part.p));
+    if (h->family == 1) {  // tensor-pipe SpMV stores H psi; A = sum psi^H (H psi) on the tensor pipe too
+      TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, hpsi, nullptr, tmp, EPI_STORE, 1.0, 0.0, nunits, nctas, nullptr));
+      TRY(launch_gram(h, psi, hpsi, nunits, nctas, h->part.p));
+    } else {
+      TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, h->part.p));
+    }
     TRY(launch_reduce(h, nunits, nctas, diag ? 2 : 0, h->A.p, nullptr, BLKD, nullptr, nullptr));
     CUDA_TRY(cudaMemcpy2DAsync(h->ahist.p + (size_t)ll * BLKD, hs * sizeof(double), h->A.p, BLKD * sizeof(double),
                                BLKD * sizeof(double), nunits, cudaMemcpyDeviceToDevice, h->st));
     // pmn -= psi A ; B2 = sum pmn^H pmn
     dim3 grid(nctas, nunits);
-    k_lz_ortho_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->A.p, BLKD, h->kk, vstride(h), h->part.p);
+    k_lz_ortho_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, hpsi, h->A.p, BLKD, h->kk, vstride(h), h->part.p);
+    h->last_parts = nctas;
     // B2 -> history slot ll+1, B, B^-1
-    k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->part.p, nctas, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
+    k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->part.p, h->last_parts, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
                                          BLKD, diag ? 1 : 0);
     // psi = pmn B^-1 ; pmn = psi_old B
     k_lz_rotate_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->B.p, h->Bi.p, BLKD, h->kk, vstride(h));
@@ -370,7 +394,7 @@ static int cheb_begin_common(H *h, int nunits, int lld, double a, double b) {
   auto &c = h->cheb;
   c.nunits = nunits; c.lld = lld; c.a = a; c.b = b; c.done = 0; c.i0 = 0; c.i1 = 1;
   c.nctas = nctas_for(h, nunits);
-  TRY(dev_alloc(h->part, (size_t)nunits * std::max(c.nctas, dmma_max_ctas(h->sms)) * 2 * BLKD, false));
+  TRY(dev_alloc(h->part, part_doubles(h, nunits, c.nctas), false));
   TRY(dev_alloc(h->mu, (size_t)nunits * (2 * lld + 2) * BLKD, false));
   CUDA_TRY(cudaMemsetAsync(h->mu.p, 0, (size_t)nunits * (2 * lld + 2) * BLKD * sizeof(double), h->st));
   return RSREC_OK;
@@ -402,7 +426,14 @@ static int cheb_steps(H *h, int nsteps) {
     const int ll = c.done + 1;
     double *p0 = h->vecs[c.i0].p, *p1 = h->vecs[c.i1].p;
     // psi2 = 2 (H psi1 - b psi1)/a - psi0, written over psi0; D1 = sum psi1^H psi1, D2 = sum psi2^H psi1
-    TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB, c.a, c.b, c.nunits, c.nctas, h->part.p));
+    if (h->family == 1) {
+      TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB_NOGRAM, c.a, c.b, c.nunits, c.nctas, nullptr));
+      if (dmma_launch_gram(p1, p0, 1, h->kk, vstride(h), c.nunits, h->sms, h->part.p, h->st, &h->launches) != 0)
+        return fail(RSREC_ECUDA, std::string("k_gram_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+      h->last_parts = dmma_gram_ctas(h->kk, h->sms);
+    } else {
+      TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB, c.a, c.b, c.nunits, c.nctas, h->part.p));
+    }
     const int nparts = h->last_parts;
     // mu(2ll+1) = 2 D1 - mu(1), mu(2ll+2) = 2 D2 - mu(2)
     TRY(launch_reduce(h, c.nunits, nparts, 1, h->mu.p + (size_t)(2 * ll) * BLKD,
@@ -459,7 +490,7 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   h->ncls = ntype + nmax; h->sms = prop.multiProcessorCount;
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  TRY(dmma_configure());
+  if (dmma_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
   *out = h;
   return RSREC_OK;
 }
@@ -726,7 +757,7 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
   TRY(get_vec(h, 3, 1, &v1)); TRY(get_vec(h, 4, 1, &right)); TRY(get_vec(h, 5, 1, &spare));
   std::vector<double *> left(M);
   for (int m = 0; m < M; m++) TRY(get_vec(h, 6 + m, 1, &left[m]));
-  TRY(dev_alloc(h->part, (size_t)nctas * 2 * BLKD, false));
+  TRY(dev_alloc(h->part, part_doubles(h, 1, nctas), false));
   TRY(dev_alloc(h->mu, (size_t)M * M * BLKD, false));
   const int32_t one = 1;
   for (int s = 0; s < nstart; s++) {
