@@ -107,6 +107,13 @@ int rsrec_synchronize(rsrec_handle h);
 void *rsrec_stream(rsrec_handle h);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long rsrec_launch_count(rsrec_handle h);
+/* host<->device bytes this handle has moved so far (uploads of lattice/Hamiltonian/start data, downloads of results) */
+long long rsrec_h2d_bytes(rsrec_handle h);
+long long rsrec_d2h_bytes(rsrec_handle h);
+/* per-kernel timing of the gather-SpMV launches with CUDA events on the handle's stream: enable, run, read
+ * (read synchronises, returns the summed duration and the number of launches, and resets the counters) */
+int rsrec_profile(rsrec_handle h, int enable);
+int rsrec_profile_read(rsrec_handle h, double *total_ms, int *nlaunches);
 /* select kernel family: 0 = SIMT reference kernels, 1 = DMMA (FP64 tensor core) pipeline (default) */
 int rsrec_set_kernel_family(rsrec_handle h, int family);
 

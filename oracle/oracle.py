@@ -44,6 +44,7 @@ def lib():
         _lib.orc_lanczos_scalar.argtypes = [c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp]
         _lib.orc_cheb_moments.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
         _lib.orc_cheb_moments_random.argtypes = [c_vp, C.c_int, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
+        _lib.orc_cheb_time_steps.argtypes = [c_vp, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
         _lib.orc_kubo_moments.argtypes = [c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
         _lib.orc_zsqr.argtypes = [c_vp, C.c_int, C.c_int]
         _lib.orc_ham_vec_matmul.argtypes = [c_vp, c_vp, c_vp, C.c_double, C.c_double, c_vp]
@@ -122,6 +123,14 @@ class Oracle:
         mu = np.zeros((18, 18, 2 * lld + 2, nvec), np.complex128, order="F")
         rc = lib().orc_cheb_moments_random(self.h, nvec, _p(ph), lld, a, b, _p(mu))
         return mu, rc
+
+    def cheb_time_steps(self, phases, nsteps, a, b):
+        """seconds for `nsteps` chebyshev_recur_ll steps of one random vector (CPU baseline)."""
+        ph = np.ascontiguousarray(phases, dtype=np.float64)
+        sec = C.c_double(0.0)
+        rc = lib().orc_cheb_time_steps(self.h, _p(ph), nsteps, a, b, C.byref(sec))
+        assert rc == 0
+        return sec.value
 
     def kubo_moments(self, cond_ll, a, b, start_sites=None, phases=None):
         if start_sites is not None:

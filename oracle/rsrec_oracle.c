@@ -653,6 +653,37 @@ int orc_cheb_moments_random(orc_ctx *c, int nvec, const double *phases, int lld,
   return rc;
 }
 
+/* CPU-baseline timing hook: the chebyshev_recur_ll loop alone (what the reference's g_timer labels
+ * '<PSI_0|PSI_n>', recursion.f90:3121-3127), wall-clock seconds for `nsteps` steps of one random-phase vector. */
+int orc_cheb_time_steps(orc_ctx *c, const double *phases, int nsteps, double a, double b, double *seconds) {
+  const int kk = c->kk;
+  cplx *psiref = (cplx *)malloc(sizeof(cplx) * (size_t)BLK * kk);
+  cplx *mu = (cplx *)calloc((size_t)BLK * (2 * nsteps + 2), sizeof(cplx));
+  for (int i = 0; i <= kk; i++) c->izero[i] = (i > 0);
+  zero_blocks(c->psi1, kk); zero_blocks(c->psi2, kk);
+  random_start(c, phases, psiref);
+  memcpy(c->psi0, psiref, sizeof(cplx) * (size_t)BLK * kk);
+  cheb_0th_mom(c, psiref);
+  memcpy(mu, c->cheb_mom_temp, sizeof(cplx) * BLK);
+  cheb_1st_mom(c, psiref, a, b);
+  memcpy(mu + BLK, c->cheb_mom_temp, sizeof(cplx) * BLK);
+  memcpy(c->izero, c->idum, sizeof(int32_t) * (kk + 1));
+#ifdef _OPENMP
+  double t0 = omp_get_wtime();
+#else
+  double t0 = 0.0;
+#endif
+  for (int ll = 1; ll <= nsteps; ll++) chebyshev_recur_ll(c, ll, a, b, mu);
+#ifdef _OPENMP
+  *seconds = omp_get_wtime() - t0;
+#else
+  *seconds = -1.0;
+#endif
+  double chk = creal(mu[(size_t)BLK * (2 * nsteps)]);
+  free(psiref); free(mu);
+  return chk == chk ? 0 : -1;
+}
+
 /* ===================== H~ and velocity applications, Kubo-Bastin moments ===================== */
 /* ham_vec_matmul / ham_hoh_vec_matmul: recursion.f90:913-977 / 785-911 (uses the MEMBER idum; caller copies) */
 static void ham_apply(orc_ctx *c, const cplx *in, cplx *out, double a, double b) {

@@ -50,6 +50,8 @@ int orc_cheb_moments(orc_ctx *c, int nunits, const int32_t *site_i, const int32_
  * (start vector of recursion.f90:1131-1143 fed to the chebyshev_recur_ll loop); phases: kk x nvec. */
 int orc_cheb_moments_random(orc_ctx *c, int nvec, const double *phases, int lld, double a, double b,
                             orc_cplx *mu_n);
+/* timing hook for the CPU baseline: seconds spent in `nsteps` chebyshev_recur_ll steps of one random vector */
+int orc_cheb_time_steps(orc_ctx *c, const double *phases, int nsteps, double a, double b, double *seconds);
 /* compute_moments_stochastic: recursion.f90:979-1234.  start_kind 0 = per_type (start_sites[i] = atlist(i)),
  * 1 = random_vec (phases kk x nstart).  mu_nm: 18x18xMxMxnstart. */
 int orc_kubo_moments(orc_ctx *c, int nstart, int start_kind, const int32_t *start_sites, const double *phases,

@@ -14,6 +14,7 @@ SYMBOLS = [
     "rsrec_cheb_moments", "rsrec_cheb_moments_random", "rsrec_kubo_moments", "rsrec_ham_vec_matmul",
     "rsrec_velo_vec_matmul", "rsrec_cheb_begin_random", "rsrec_cheb_begin_sites", "rsrec_cheb_run_steps",
     "rsrec_cheb_end", "rsrec_synchronize", "rsrec_stream", "rsrec_launch_count", "rsrec_set_kernel_family",
+    "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read",
 ]
 
 
@@ -59,6 +60,12 @@ def load():
     L.rsrec_launch_count.argtypes = [vp]
     L.rsrec_launch_count.restype = C.c_longlong
     L.rsrec_set_kernel_family.argtypes = [vp, i]
+    L.rsrec_h2d_bytes.argtypes = [vp]
+    L.rsrec_h2d_bytes.restype = C.c_longlong
+    L.rsrec_d2h_bytes.argtypes = [vp]
+    L.rsrec_d2h_bytes.restype = C.c_longlong
+    L.rsrec_profile.argtypes = [vp, i]
+    L.rsrec_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i)]
     _lib = L
     return L
 

@@ -43,6 +43,10 @@ struct rsrec_handle_s {
   cudaStream_t st = nullptr;
   long long launches = 0;
   int last_parts = 0;  // partial-sum slots per unit written by the last fused apply
+  long long h2d_bytes = 0, d2h_bytes = 0;  // bytes moved over PCIe/C2C by this handle (bench.py's e2e accounting)
+  bool profile = false;                    // record CUDA events around every gather-SpMV launch
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
   // host copies of the reference arrays (small) so that device sets can be (re)built in any call order
   std::vector<int32_t> nn, iz;
   std::vector<cplx> ee, eeo, hall, hallo, lsham, enim, v_a, v_b, vo_a, vo_b;
@@ -113,9 +117,11 @@ static void pack_block(const cplx *src, double *dst, double scale) {
   add_block(src, dst, scale);
 }
 
+static long long g_upload_bytes = 0;  // folded into the handle's h2d counter by ensure_ready
 static int upload(DevBuf &b, const std::vector<double> &host) {
   TRY(dev_alloc(b, host.size(), false));
   CUDA_TRY(cudaMemcpy(b.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
+  g_upload_bytes += (long long)(host.size() * sizeof(double));
   return RSREC_OK;
 }
 
@@ -126,6 +132,7 @@ static int ensure_ready(H *h) {
   if (!h->have_lat) return fail(RSREC_EINVAL, "rsrec_set_lattice has not been called");
   if (!h->have_ham) return fail(RSREC_EINVAL, "rsrec_set_hamiltonian has not been called");
   if (!h->dirty) return RSREC_OK;
+  g_upload_bytes = 0;
   const int kk = h->kk, nslot = h->nslot, ncls = h->ncls, ng = h->ncols;
   // neighbour table [slot][site], slot 0 = self, missing -> kk
   std::vector<int32_t> nbr((size_t)ng * kk), cls(kk);
@@ -146,6 +153,7 @@ static int ensure_ready(H *h) {
   if (!h->d_cls) CUDA_TRY(cudaMalloc(&h->d_cls, cls.size() * sizeof(int32_t)));
   CUDA_TRY(cudaMemcpy(h->d_nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(h->d_cls, cls.data(), cls.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  h->h2d_bytes += (long long)((nbr.size() + cls.size()) * sizeof(int32_t));
 
   auto src_block = [&](const std::vector<cplx> &ty, const std::vector<cplx> &loc, int c, int m) -> const cplx * {
     if (c < h->ntype) return ty.data() + (size_t)BLKC * (m + (size_t)nslot * c);
@@ -202,6 +210,7 @@ static int ensure_ready(H *h) {
     if (h->hoh) TRY(upload(s == 0 ? h->Hvoa_neg : h->Hvob_neg, hvo));
   }
   if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
+  h->h2d_bytes += g_upload_bytes + (long long)h->tiles.ntiles * (DM_S + 1 + (long long)ng * DM_S) * 4;
   h->dirty = false;
   return RSREC_OK;
 }
@@ -237,7 +246,22 @@ static int unit_batch(H *h, int nunits, int nvec) {
 // ---- operator application: out = epilogue( H src ) for a unit batch ---------------------------------------
 enum OpKind { OP_HAM = 0, OP_SCALAR = 1, OP_VELO_A = 2, OP_VELO_B = 3 };
 
+static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas);
 static int launch_apply(H *h, ApplyParams &p, int nunits, int nctas) {
+  if (!h->profile) return launch_apply_inner(h, p, nunits, nctas);
+  if (h->prof_used == h->prof_events.size()) {
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    h->prof_events.push_back({a, b});
+  }
+  auto &ev = h->prof_events[h->prof_used++];
+  CUDA_TRY(cudaEventRecord(ev.first, h->st));
+  int rc = launch_apply_inner(h, p, nunits, nctas);
+  CUDA_TRY(cudaEventRecord(ev.second, h->st));
+  return rc;
+}
+static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas) {
   if (h->family == 1 && dmma_supported(p)) {
     if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches) != 0)
       return fail(RSREC_ECUDA, std::string("k_apply_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -324,10 +348,10 @@ static int upload_units(H *h, int nunits, const int32_t *site_i, const int32_t *
     as[2 * u] = asign ? asign[u].re : 1.0; as[2 * u + 1] = asign ? asign[u].im : 0.0;
     bs[2 * u] = bsign ? bsign[u].re : 1.0; bs[2 * u + 1] = bsign ? bsign[u].im : 0.0;
   }
-  CUDA_TRY(cudaMemcpyAsync(h->d_si, site_i, nunits * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
-  CUDA_TRY(cudaMemcpyAsync(h->d_sj, sj.data(), nunits * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
-  CUDA_TRY(cudaMemcpyAsync(h->d_as, as.data(), 2 * nunits * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  CUDA_TRY(cudaMemcpyAsync(h->d_bs, bs.data(), 2 * nunits * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_si, site_i, nunits * sizeof(int32_t), cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)(nunits * sizeof(int32_t));
+  CUDA_TRY(cudaMemcpyAsync(h->d_sj, sj.data(), nunits * sizeof(int32_t), cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)(nunits * sizeof(int32_t));
+  CUDA_TRY(cudaMemcpyAsync(h->d_as, as.data(), 2 * nunits * sizeof(double), cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)(2 * nunits * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(h->d_bs, bs.data(), 2 * nunits * sizeof(double), cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)(2 * nunits * sizeof(double));
   CUDA_TRY(cudaStreamSynchronize(h->st));  // host staging vectors go out of scope
   return RSREC_OK;
 }
@@ -380,8 +404,8 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     h->launches += 3;
     CUDA_TRY(cudaGetLastError());
   }
-  CUDA_TRY(cudaMemcpyAsync(a_host, h->ahist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CUDA_TRY(cudaMemcpyAsync(b2_host, h->b2hist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaMemcpyAsync(a_host, h->ahist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(b2_host, h->b2hist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double));
   CUDA_TRY(cudaStreamSynchronize(h->st));
   return RSREC_OK;
 }
@@ -446,7 +470,7 @@ static int cheb_steps(H *h, int nsteps) {
 static int cheb_finish(H *h, cplx *mu_n) {
   auto &c = h->cheb;
   const size_t n = (size_t)c.nunits * (2 * c.lld + 2) * BLKD;
-  CUDA_TRY(cudaMemcpyAsync(mu_n, h->mu.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaMemcpyAsync(mu_n, h->mu.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)(n * sizeof(double));
   CUDA_TRY(cudaStreamSynchronize(h->st));
   c.active = false;
   // the reference's divergence guard (recursion.f90:2594): sum(real(mu(:,:,2ll+2))) > 1000 -> fatal
@@ -507,6 +531,7 @@ int rsrec_destroy(rsrec_handle h) {
   if (h->d_nbr) cudaFree(h->d_nbr);
   if (h->d_cls) cudaFree(h->d_cls);
   if (h->d_si) { cudaFree(h->d_si); cudaFree(h->d_sj); cudaFree(h->d_as); cudaFree(h->d_bs); }
+  for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaStreamDestroy(h->st);
   delete h;
   return RSREC_OK;
@@ -601,11 +626,11 @@ int rsrec_zsqr(rsrec_handle h, cplx *b2_b, int lld, int na) {
   if (nmat == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(dev_alloc(h->scratch, nmat * BLKD, false));
-  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, b2_b, nmat * BLKD * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, b2_b, nmat * BLKD * sizeof(double), cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)(nmat * BLKD * sizeof(double));
   k_zsqr<<<(unsigned)nmat, BLKC, 0, h->st>>>(h->scratch.p);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(b2_b, h->scratch.p, nmat * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaMemcpyAsync(b2_b, h->scratch.p, nmat * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)(nmat * BLKD * sizeof(double));
   CUDA_TRY(cudaStreamSynchronize(h->st));
   return RSREC_OK;
 }
@@ -640,7 +665,7 @@ int rsrec_cheb_begin_random(rsrec_handle h, int nvec, const double *phases, int 
   TRY(zero_vec(h, p0, nvec));
   TRY(zero_vec(h, p1, nvec));
   TRY(dev_alloc(h->scratch, (size_t)h->kk * nvec, false));
-  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, phases, (size_t)h->kk * nvec * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, phases, (size_t)h->kk * nvec * sizeof(double), cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)((size_t)h->kk * nvec * sizeof(double));
   k_init_random_start<<<h->sms * 4, 256, 0, h->st>>>(p0, vstride(h), h->scratch.p, h->kk, nvec);
   h->launches++;
   return cheb_first_moments(h);
@@ -698,7 +723,7 @@ int rsrec_cheb_moments_random(rsrec_handle h, int nvec, const double *phases, in
 // host (18,18,kk) complex <-> device RI36 through the scratch buffer
 static int upload_vec(H *h, const cplx *src, double *dst) {
   TRY(dev_alloc(h->scratch, (size_t)h->kk * BLKD, false));
-  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, src, (size_t)h->kk * BLKD * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(h->scratch.p, src, (size_t)h->kk * BLKD * sizeof(double), cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)((size_t)h->kk * BLKD * sizeof(double));
   k_host_to_ri36<<<h->sms * 4, 256, 0, h->st>>>(h->scratch.p, dst, h->kk);
   h->launches++;
   return RSREC_OK;
@@ -707,7 +732,7 @@ static int download_vec(H *h, const double *src, cplx *dst) {
   TRY(dev_alloc(h->scratch, (size_t)h->kk * BLKD, false));
   k_ri36_to_host<<<h->sms * 4, 256, 0, h->st>>>(src, h->scratch.p, h->kk);
   h->launches++;
-  CUDA_TRY(cudaMemcpyAsync(dst, h->scratch.p, (size_t)h->kk * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CUDA_TRY(cudaMemcpyAsync(dst, h->scratch.p, (size_t)h->kk * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)h->kk * BLKD * sizeof(double));
   CUDA_TRY(cudaStreamSynchronize(h->st));
   return RSREC_OK;
 }
@@ -767,7 +792,7 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
       k_init_site_start<<<1, 32, 0, h->st>>>(psiref, vstride(h), h->d_si, h->d_sj, h->d_as, h->d_bs, 1);
     } else {
       TRY(dev_alloc(h->scratch, (size_t)h->kk, false));
-      CUDA_TRY(cudaMemcpyAsync(h->scratch.p, phases + (size_t)s * h->kk, (size_t)h->kk * sizeof(double), cudaMemcpyHostToDevice, h->st));
+      CUDA_TRY(cudaMemcpyAsync(h->scratch.p, phases + (size_t)s * h->kk, (size_t)h->kk * sizeof(double), cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)((size_t)h->kk * sizeof(double));
       k_init_random_start<<<h->sms * 4, 256, 0, h->st>>>(psiref, vstride(h), h->scratch.p, h->kk, 1);
     }
     h->launches++;
@@ -799,7 +824,7 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
         TRY(launch_reduce(h, 1, nctas, 0, h->mu.p + ((size_t)n + (size_t)M * m) * BLKD, nullptr, 0, nullptr, nullptr));
       }
     }
-    CUDA_TRY(cudaMemcpyAsync(mu_nm + (size_t)s * M * M * BLKC, h->mu.p, (size_t)M * M * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaMemcpyAsync(mu_nm + (size_t)s * M * M * BLKC, h->mu.p, (size_t)M * M * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)M * M * BLKD * sizeof(double));
     CUDA_TRY(cudaStreamSynchronize(h->st));
   }
   return RSREC_OK;
@@ -811,6 +836,28 @@ int rsrec_synchronize(rsrec_handle h) {
   return RSREC_OK;
 }
 void *rsrec_stream(rsrec_handle h) { return h ? (void *)h->st : nullptr; }
+long long rsrec_h2d_bytes(rsrec_handle h) { return h ? h->h2d_bytes : 0; }
+long long rsrec_d2h_bytes(rsrec_handle h) { return h ? h->d2h_bytes : 0; }
+int rsrec_profile(rsrec_handle h, int enable) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  h->profile = enable != 0;
+  h->prof_used = 0;
+  return RSREC_OK;
+}
+int rsrec_profile_read(rsrec_handle h, double *total_ms, int *nlaunches) {
+  if (!h || !total_ms || !nlaunches) return fail(RSREC_EINVAL, "rsrec_profile_read: bad argument");
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  double tot = 0.0;
+  for (size_t i = 0; i < h->prof_used; i++) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second));
+    tot += ms;
+  }
+  *total_ms = tot;
+  *nlaunches = (int)h->prof_used;
+  h->prof_used = 0;
+  return RSREC_OK;
+}
 long long rsrec_launch_count(rsrec_handle h) { return h ? h->launches : 0; }
 
 }  // extern "C"

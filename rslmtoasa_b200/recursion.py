@@ -258,5 +258,22 @@ class Recursion:
         _lib.check(self._L.rsrec_cheb_end(self._h, _p(mu)))
         return mu
 
+    @property
+    def h2d_bytes(self) -> int:
+        return int(self._L.rsrec_h2d_bytes(self._h))
+
+    @property
+    def d2h_bytes(self) -> int:
+        return int(self._L.rsrec_d2h_bytes(self._h))
+
+    def profile(self, enable: bool):
+        _lib.check(self._L.rsrec_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """-> (summed gather-SpMV kernel milliseconds, launches) since profiling was enabled."""
+        ms, n = C.c_double(0.0), C.c_int(0)
+        _lib.check(self._L.rsrec_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def synchronize(self):
         _lib.check(self._L.rsrec_synchronize(self._h))

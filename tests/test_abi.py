@@ -1,0 +1,112 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/rsrec.h declares, fails loudly
+without a GPU, and the host-side mirror keeps the reference's unit/rank bookkeeping."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from rslmtoasa_b200 import build as B, _lib
+    B.build_library()          # nvcc cross-compiles for sm_100a without a GPU
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "rsrec.h")).read()
+    declared = set(re.findall(r"\b(rsrec_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 24
+    from rslmtoasa_b200 import _lib
+    assert declared == set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_compiled_for_sm_100a_only(lib):
+    assert lib.rsrec_compiled_arch() == 100
+    import subprocess
+    from rslmtoasa_b200 import build as B
+    out = subprocess.run(["cuobjdump", "-lelf", B.LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out
+
+
+def test_sass_uses_fp64_tensor_pipe_and_tma(lib):
+    """DMMA = the FP64 tensor instruction, UBLKCP = TMA bulk copy, SYNCS = mbarrier (B200_PROFILING.md evidence)."""
+    import subprocess
+    from rslmtoasa_b200 import build as B
+    sass = subprocess.run(["cuobjdump", "-sass", B.LIB], capture_output=True, text=True).stdout
+    assert sass.count("DMMA.8x8x4") > 100
+    assert "UBLKCP" in sass and "SYNCS.PHASECHK" in sass
+
+
+def test_no_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rslmtoasa_b200 import Recursion, RsrecError
+    from tests.cases import case
+    lat, ham = case("tiny")
+    with pytest.raises(RsrecError) as ei:
+        Recursion(ham, lat)
+    assert ei.value.code == -3 and "no CPU path" in str(ei.value)
+
+
+def test_bad_arguments(lib):
+    h = ctypes.c_void_p()
+    assert lib.rsrec_create(ctypes.byref(h), 0, 0, 15, 16, 1, 0) == -1      # kk < 1
+    assert b"inconsistent sizes" in lib.rsrec_last_error()
+    assert lib.rsrec_create(ctypes.byref(h), 0, 10, 15, 3, 1, 0) == -1      # nslot < ncols
+    assert lib.rsrec_destroy(None) == 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rslmtoasa_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|rsrec_oracle|\borc_[a-z]|oracle/", txt, re.M), f
+
+
+def test_partition_is_get_mpi_variables():
+    """mpi.f90:32-58: n/p each, the first n mod p ranks get one more, contiguous 1-based ranges"""
+    from rslmtoasa_b200.synthetic import partition
+    for n in (1, 6, 7, 16, 61):
+        for p in (1, 2, 3, 4, 8):
+            prev_end, total = 0, 0
+            for r in range(p):
+                s, e = partition(r, p, n)
+                cnt = e - s + 1
+                assert s == prev_end + 1
+                assert cnt == n // p + (1 if r < n % p else 0)
+                prev_end, total = e, total + cnt
+            assert total == n
+
+
+def test_pair_unit_slots_follow_recur_b_ij():
+    """result slot ij_loc*4-4+reci, i==j keeps only reci=1 with signs (1,1) (recursion.f90:1672-1721)"""
+    from rslmtoasa_b200.recursion import Recursion
+    r = Recursion.__new__(Recursion)
+    r.rank, r.numprocs = 0, 1
+    r.ijpair = np.array([[1, 2], [3, 3]], dtype=np.int32)
+    nloc, slots, (si, sj, asg, bsg) = r._pair_units()
+    assert nloc == 2 and slots == [0, 1, 2, 3, 4]
+    s = 1 / np.sqrt(2)
+    assert np.allclose(asg, [s, s, s, s, 1.0]) and np.allclose(bsg, [s, -s, 1j * s, -1j * s, 1.0])
+    assert list(si) == [1, 1, 1, 1, 3] and list(sj) == [2, 2, 2, 2, 3]
+
+
+def test_synthetic_lattices_match_survey_sizes():
+    from rslmtoasa_b200 import synthetic as S
+    assert S.sphere_cluster("bcc", 80.0).kk == 5984          # config 1 (kk = 5984)
+    assert S.sphere_cluster("bcc", 60.0).kk == 3838          # config 3
+    lat = S.periodic_bcc(6, 5, 4)
+    opp = S._opposite_slots(S.BCC_DISP)
+    for m in range(1, 15):                                    # reciprocity of the neighbour table
+        j = lat.nn[:, m] - 1
+        assert (lat.nn[j, opp[m]] - 1 == np.arange(lat.kk)).all()
