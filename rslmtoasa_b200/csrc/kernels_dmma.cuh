@@ -10,7 +10,7 @@
 // psi block per neighbour + one 10368 B HR36 Hamiltonian block) into a 3-stage shared-memory ring guarded by
 // mbarriers; 8 consumer warps compute  C^T[n][r] += Psi[k'][n] * Hreal[r][k']  (M = 144 site-columns, N = 36 -> 40
 // output rows, K = 36) with DMMA and keep the accumulators in registers across all slots.  The 90 (m-tile, n-tile)
-// units of a stage are split 22/23/22/23 over the four SM sub-partitions.  The epilogue (scale/shift, three-term
+// units of a stage are split 22/22/23/23 over the four SM sub-partitions (11 or 12 per warp).  The epilogue (scale/shift, three-term
 // update) is applied straight from the accumulator fragments with 16 B global accesses; the on-site slot is
 // scheduled last so that psi_self is still in shared memory when the epilogue needs it.
 //
@@ -22,7 +22,7 @@
 #include <vector>
 
 #define DM_S 8                               // sites per tile
-#define DM_STAGES 3
+#define DM_STAGES 4
 #define DM_STAGE_D (HBLK + DM_S * BLKD)      // doubles per stage: H block + 8 psi blocks = 6480 (51840 B)
 #define DM_CONSUMERS 8
 #define DM_THREADS (32 * (DM_CONSUMERS + 1))
@@ -80,6 +80,134 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
+// One consumer warp of k_apply_dmma.  XN = number of units this warp owns in its shared m-tile (compile time so that
+// no DMMA is ever issued predicated-off: a predicated-off DMMA still occupies the tensor pipe).
+template <int EPI, bool ADDEND, int XN>
+__device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaStages &st,
+                                              const int32_t *__restrict__ tile_sites, double *stages, uint64_t *full,
+                                              uint64_t *empty, int ntiles, int nunits, int warp, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const int nst = st.n;
+  const double inv_a = 1.0 / p.a;  // the epilogue multiplies by 1/a (<= 1 ulp from the reference's division)
+  const int mt0 = 2 * warp, mt1 = 2 * warp + 1, mt2 = 16 + (warp >> 2);
+  const int w4 = warp & 3;
+  const int xn0 = (warp == 6) ? 2 : (warp == 7) ? 4 : w4;  // first extra n-tile
+  const int xn1 = xn0 + 1;                                  // second one (XN == 2 only)
+  int aoff[3], boff[5], xoff[2];
+  aoff[0] = HBLK + (mt0 * 8 + g) * COLD + q;
+  aoff[1] = HBLK + (mt1 * 8 + g) * COLD + q;
+  aoff[2] = HBLK + (mt2 * 8 + g) * COLD + q;
+#pragma unroll
+  for (int nt = 0; nt < 5; nt++) boff[nt] = min(nt * 8 + g, 35) * COLD + q;
+  xoff[0] = min(xn0 * 8 + g, 35) * COLD + q;
+  xoff[1] = min(xn1 * 8 + g, 35) * COLD + q;
+
+  uint32_t it = 0;
+  for (int u = 0; u < nunits; u++) {
+    const size_t uo = (size_t)u * p.vstride;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      double acc[2][5][2], xacc[XN][2];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++) acc[i][nt][0] = acc[i][nt][1] = 0.0;
+#pragma unroll
+      for (int x = 0; x < XN; x++) xacc[x][0] = xacc[x][1] = 0.0;
+      // global element offsets of this lane's accumulator rows (one site-column per m-tile)
+      size_t goff[3];
+      bool gval[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const int n = (i == 0 ? mt0 : i == 1 ? mt1 : mt2) * 8 + g;
+        const int site = tile_sites[tile * DM_S + n / NB];
+        gval[i] = site < p.kk;
+        goff[i] = uo + (size_t)site * BLKD + (n % NB) * COLD + 2 * q;
+      }
+      double2 pv[2][5], xpv[XN];  // prefetched `prev` (psi0) fragments
+      for (int j = 0; j < nst; j++, it++) {
+        const int slot = it % DM_STAGES;
+        if (EPI == EPI_CHEB_NOGRAM && j == nst - 1) {
+          // issue the epilogue's global loads now; they land while the last stage is being computed
+#pragma unroll
+          for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int nt = 0; nt < 5; nt++)
+              pv[i][nt] = (gval[i] && (nt < 4 || q < 2)) ? __ldg(reinterpret_cast<const double2 *>(p.prev + goff[i] + nt * 8))
+                                                         : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int x = 0; x < XN; x++) {
+            const int nt = x == 0 ? xn0 : xn1;
+            xpv[x] = (gval[2] && (nt < 4 || q < 2)) ? __ldg(reinterpret_cast<const double2 *>(p.prev + goff[2] + nt * 8))
+                                                    : make_double2(0.0, 0.0);
+          }
+        }
+        mbar_wait(&full[slot], (it / DM_STAGES) & 1);
+        const double *sm = stages + (size_t)slot * DM_STAGE_D;
+        // fragments of k-step ks+1 are loaded before the DMMAs of k-step ks are issued (register double buffering)
+        double b[2][5], a[2][3], xb[2][XN];
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++) b[0][nt] = sm[boff[nt]];
+#pragma unroll
+        for (int i = 0; i < 3; i++) a[0][i] = sm[aoff[i]];
+#pragma unroll
+        for (int x = 0; x < XN; x++) xb[0][x] = sm[xoff[x]];
+#pragma unroll
+        for (int ks = 0; ks < 9; ks++) {
+          const int c = ks & 1, n = c ^ 1;
+          if (ks < 8) {
+#pragma unroll
+            for (int nt = 0; nt < 5; nt++) b[n][nt] = sm[boff[nt] + 4 * (ks + 1)];
+#pragma unroll
+            for (int i = 0; i < 3; i++) a[n][i] = sm[aoff[i] + 4 * (ks + 1)];
+#pragma unroll
+            for (int x = 0; x < XN; x++) xb[n][x] = sm[xoff[x] + 4 * (ks + 1)];
+          }
+#pragma unroll
+          for (int nt = 0; nt < 5; nt++) {
+            dmma(acc[0][nt][0], acc[0][nt][1], a[c][0], b[c][nt]);
+            dmma(acc[1][nt][0], acc[1][nt][1], a[c][1], b[c][nt]);
+          }
+#pragma unroll
+          for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], a[c][2], xb[c][x]);
+        }
+        if (j < nst - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+      }
+      // ===== epilogue from the accumulator fragments; the last stage (self blocks of `in`) is still held =====
+      const int lslot = (it - 1) % DM_STAGES;
+      const double *sm = stages + (size_t)lslot * DM_STAGE_D;
+      auto finish = [&](double v0, double v1, int n, int nt, size_t go, double2 prev) {
+        if (ADDEND) {
+          const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go));
+          v0 += ad.x; v1 += ad.y;
+        }
+        if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
+          const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + nt * 8 + 2 * q);
+          v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
+          if (EPI == EPI_CHEB_NOGRAM) { v0 = 2.0 * v0 - prev.x; v1 = 2.0 * v1 - prev.y; }
+        }
+        *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
+      };
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int n = (i == 0 ? mt0 : mt1) * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++)
+          if (gval[i] && (nt < 4 || q < 2)) finish(acc[i][nt][0], acc[i][nt][1], n, nt, goff[i] + nt * 8, pv[i][nt]);
+      }
+#pragma unroll
+      for (int x = 0; x < XN; x++) {
+        const int nt = x == 0 ? xn0 : xn1;
+        if (gval[2] && (nt < 4 || q < 2)) finish(xacc[x][0], xacc[x][1], mt2 * 8 + g, nt, goff[2] + nt * 8, xpv[x]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[lslot]);
+    }
+  }
+}
+
 // ---- fused gather-SpMV + epilogue ---------------------------------------------------------------------------
 template <int EPI, bool ADDEND>
 __global__ void __launch_bounds__(DM_THREADS, 1)
@@ -96,136 +224,51 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
   }
   __syncthreads();
   const int nst = st.n, ng = p.ngather;
-  const double inv_a = 1.0 / p.a;  // the epilogue multiplies by 1/a (<= 1 ulp from the reference's division)
 
   if (warp == DM_CONSUMERS) {
     // ===== producer warp: TMA bulk copies =====
-    uint32_t it = 0;
-    for (int u = 0; u < nunits; u++) {
-      const size_t uo = (size_t)u * p.vstride;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int cls = tile_cls[tile];
-        for (int j = 0; j < nst; j++, it++) {
-          const int slot = it % DM_STAGES;
-          mbar_wait(&empty[slot], ((it / DM_STAGES) & 1) ^ 1);
-          double *sm = stages + (size_t)slot * DM_STAGE_D;
-          if (lane == 0) mbar_expect_tx(&full[slot], DM_STAGE_D * 8);
-          __syncwarp();
-          if (lane < DM_S) {
-            const int m = st.slot[j];
-            const int site = (m == 0) ? tile_sites[tile * DM_S + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + lane];
-            bulk_g2s(sm + HBLK + lane * BLKD, st.src[j] + uo + (size_t)site * BLKD, BLKD * 8, &full[slot]);
-          } else if (lane == DM_S) {
-            bulk_g2s(sm, st.H[j] + (size_t)cls * st.hstride[j], HBLK * 8, &full[slot]);
-          }
-        }
+    // The (site index, class) of stage it+1 is fetched from global memory while the warp waits for the ring slot of
+    // stage `it`, so the index-load latency is off the critical path of the pipeline.
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total = (uint32_t)nunits * (uint32_t)max(my_tiles, 0) * (uint32_t)nst;
+    auto fetch = [&](uint32_t i, int &site, int &cls, int &u) {
+      const uint32_t per_u = (uint32_t)my_tiles * nst;
+      u = i / per_u;
+      const uint32_t r = i - (uint32_t)u * per_u;
+      const int tile = blockIdx.x + (r / nst) * gridDim.x, j = r % nst;
+      cls = tile_cls[tile];
+      const int m = st.slot[j];
+      site = (lane < DM_S) ? ((m == 0) ? tile_sites[tile * DM_S + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + lane]) : 0;
+    };
+    int site = 0, cls = 0, u = 0;
+    if (total > 0) fetch(0, site, cls, u);
+    for (uint32_t it = 0; it < total; it++) {
+      int nsite = 0, ncls = 0, nu = 0;
+      if (it + 1 < total) fetch(it + 1, nsite, ncls, nu);
+      const int slot = it % DM_STAGES, j = it % nst;
+      mbar_wait(&empty[slot], ((it / DM_STAGES) & 1) ^ 1);
+      double *sm = stages + (size_t)slot * DM_STAGE_D;
+      if (lane == 0) mbar_expect_tx(&full[slot], DM_STAGE_D * 8);
+      __syncwarp();
+      if (lane < DM_S) {
+        bulk_g2s(sm + HBLK + lane * BLKD, st.src[j] + (size_t)u * p.vstride + (size_t)site * BLKD, BLKD * 8, &full[slot]);
+      } else if (lane == DM_S) {
+        bulk_g2s(sm, st.H[j] + (size_t)cls * st.hstride[j], HBLK * 8, &full[slot]);
       }
+      site = nsite; cls = ncls; u = nu;
     }
     return;
   }
 
   // ===== consumer warps: DMMA =====
-  const int g = lane >> 2, q = lane & 3;
-  const int sp = warp & 3;            // SM sub-partition this warp lands on
-  const bool first = warp < 4;        // first warp of the sub-partition also owns part of an extra m-tile
-  const int mt0 = first ? 4 * sp : 4 * sp + 2, mt1 = mt0 + 1, mt2 = 16 + (sp >> 1);
-  const int x_lo = first ? ((sp & 1) ? 2 : 0) : 0, x_hi = first ? ((sp & 1) ? 5 : 2) : 0;  // n-tiles of the extra tile
-  int aoff[3], boff[5];
-  aoff[0] = HBLK + (mt0 * 8 + g) * COLD + q;
-  aoff[1] = HBLK + (mt1 * 8 + g) * COLD + q;
-  aoff[2] = HBLK + (mt2 * 8 + g) * COLD + q;
-#pragma unroll
-  for (int nt = 0; nt < 5; nt++) boff[nt] = min(nt * 8 + g, 35) * COLD + q;
-
-  uint32_t it = 0;
-  for (int u = 0; u < nunits; u++) {
-    const size_t uo = (size_t)u * p.vstride;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      double acc[3][5][2];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int nt = 0; nt < 5; nt++) acc[i][nt][0] = acc[i][nt][1] = 0.0;
-      // global element offsets of this lane's accumulator rows (one site-column per m-tile)
-      size_t goff[3];
-      bool gval[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const int n = (i == 0 ? mt0 : i == 1 ? mt1 : mt2) * 8 + g;
-        const int site = tile_sites[tile * DM_S + n / NB];
-        gval[i] = site < p.kk;
-        goff[i] = uo + (size_t)site * BLKD + (n % NB) * COLD + 2 * q;
-      }
-      double2 pv[3][5];  // prefetched `prev` (psi0 / pmn) fragments
-      for (int j = 0; j < nst; j++, it++) {
-        const int slot = it % DM_STAGES;
-        if ((EPI == EPI_CHEB_NOGRAM || EPI == EPI_HOP) && j == nst - 1) {
-          // issue the epilogue's global loads now; they land while the last stage is being computed
-#pragma unroll
-          for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int nt = 0; nt < 5; nt++) {
-              const bool own = (i < 2) || (nt >= x_lo && nt < x_hi);
-              const bool ok = own && gval[i] && (nt < 4 || q < 2);
-              pv[i][nt] = ok ? __ldg(reinterpret_cast<const double2 *>(p.prev + goff[i] + nt * 8)) : make_double2(0.0, 0.0);
-            }
-        }
-        mbar_wait(&full[slot], (it / DM_STAGES) & 1);
-        const double *sm = stages + (size_t)slot * DM_STAGE_D;
-#pragma unroll
-        for (int ks = 0; ks < 9; ks++) {
-          double b[5];
-#pragma unroll
-          for (int nt = 0; nt < 5; nt++) b[nt] = sm[boff[nt] + 4 * ks];
-          const double a0 = sm[aoff[0] + 4 * ks], a1 = sm[aoff[1] + 4 * ks];
-#pragma unroll
-          for (int nt = 0; nt < 5; nt++) {
-            dmma(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
-            dmma(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
-          }
-          if (first) {
-            const double a2 = sm[aoff[2] + 4 * ks];
-#pragma unroll
-            for (int nt = 0; nt < 5; nt++)
-              if (nt >= x_lo && nt < x_hi) dmma(acc[2][nt][0], acc[2][nt][1], a2, b[nt]);
-          }
-        }
-        if (j < nst - 1) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[slot]);
-        }
-      }
-      // ===== epilogue from the accumulator fragments; the last stage (self blocks of `in`) is still held =====
-      const int lslot = (it - 1) % DM_STAGES;
-      const double *sm = stages + (size_t)lslot * DM_STAGE_D;
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        if (i == 2 && !first) continue;
-        const int n = (i == 0 ? mt0 : i == 1 ? mt1 : mt2) * 8 + g;
-#pragma unroll
-        for (int nt = 0; nt < 5; nt++) {
-          const bool own = (i < 2) || (nt >= x_lo && nt < x_hi);
-          if (!own || !gval[i] || !(nt < 4 || q < 2)) continue;
-          double v0 = acc[i][nt][0], v1 = acc[i][nt][1];
-          const size_t go = goff[i] + nt * 8;
-          if (ADDEND) {
-            const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go));
-            v0 += ad.x; v1 += ad.y;
-          }
-          if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
-            const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + nt * 8 + 2 * q);
-            v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
-            if (EPI == EPI_CHEB_NOGRAM) { v0 = 2.0 * v0 - pv[i][nt].x; v1 = 2.0 * v1 - pv[i][nt].y; }
-          } else if (EPI == EPI_HOP) {
-            v0 = v0 - pv[i][nt].x; v1 = v1 - pv[i][nt].y;
-          }
-          *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[lslot]);
-    }
-  }
+  // 90 (m-tile, n-tile) units per k-step.  Every warp owns two full m-tiles (10 units) plus 1 or 2 units of the two
+  // shared m-tiles 16/17, so the sub-partitions carry 22/22/23/23 units and the two warps of a sub-partition stay
+  // within one unit of each other (both keep the tensor pipe fed).
+  //   m-tile 16: w0:n0  w1:n1  w2:n2  w3:n3,n4        m-tile 17: w4:n0  w5:n1  w6:n2,n3  w7:n4
+  if (warp == 3 || warp == 6)
+    dmma_consumer<EPI, ADDEND, 2>(p, st, tile_sites, stages, full, empty, ntiles, nunits, warp, lane);
+  else
+    dmma_consumer<EPI, ADDEND, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, warp, lane);
 }
 
 // ---- Gram reductions on the tensor pipe -------------------------------------------------------------------------
@@ -351,8 +394,6 @@ static int dmma_configure() {
   DM_ATTR((k_apply_dmma<EPI_HAM, true>))
   DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, false>))
   DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, true>))
-  DM_ATTR((k_apply_dmma<EPI_HOP, false>))
-  DM_ATTR((k_apply_dmma<EPI_HOP, true>))
 #undef DM_ATTR
   if ((e = cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES)) != cudaSuccess) return -3;
   return 0;
@@ -445,7 +486,6 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
     case EPI_STORE: if (ad) DM_LAUNCH(EPI_STORE, true); else DM_LAUNCH(EPI_STORE, false); break;
     case EPI_HAM: if (ad) DM_LAUNCH(EPI_HAM, true); else DM_LAUNCH(EPI_HAM, false); break;
     case EPI_CHEB_NOGRAM: if (ad) DM_LAUNCH(EPI_CHEB_NOGRAM, true); else DM_LAUNCH(EPI_CHEB_NOGRAM, false); break;
-    case EPI_HOP: if (ad) DM_LAUNCH(EPI_HOP, true); else DM_LAUNCH(EPI_HOP, false); break;
     default: return -1;
   }
 #undef DM_LAUNCH
