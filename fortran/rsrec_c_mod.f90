@@ -1,0 +1,184 @@
+!------------------------------------------------------------------------------
+! rsrec_c_mod -- ISO_C_BINDING interface of librsrec.so (include/rsrec.h).
+!
+! This is the thin layer BASELINE.json's north star asks for: the Fortran host of
+! rslmtoasa keeps its `recursion` / `hamiltonian` / `lattice` derived types and calls
+! the CUDA engine through these bindings.  One interface per C entry point, argument
+! for argument; arrays are passed as they are held by the reference (column-major,
+! complex(rp) == complex(c_double_complex), default integers == integer(c_int32_t)).
+!
+! NOT compiled in the build container (no Fortran compiler there); compile it next to
+! source/*.f90 and link with -lrsrec (see INTEGRATION.md).
+!------------------------------------------------------------------------------
+module rsrec_c_mod
+   use, intrinsic :: iso_c_binding
+   implicit none
+   private
+
+   integer(c_int), parameter, public :: RSREC_OK = 0, RSREC_EINVAL = -1, RSREC_EDIVERGED = -2, &
+                                        RSREC_ECUDA = -3, RSREC_ENOMEM = -4
+
+   public :: rsrec_create, rsrec_destroy, rsrec_set_lattice, rsrec_set_hamiltonian, rsrec_set_operator
+   public :: rsrec_lanczos_block, rsrec_lanczos_scalar, rsrec_zsqr, rsrec_cheb_moments, rsrec_cheb_moments_random
+   public :: rsrec_kubo_moments, rsrec_ham_vec_matmul, rsrec_velo_vec_matmul, rsrec_last_error_f, rsrec_check
+
+   interface
+      function rsrec_last_error() bind(C, name='rsrec_last_error') result(msg)
+         import :: c_ptr
+         type(c_ptr) :: msg
+      end function
+
+      ! recursion constructor: recursion.f90:132-143 / allocation 3713-3826
+      function rsrec_create(h, device_ordinal, kk, ncols, nslot, ntype, nmax) bind(C, name='rsrec_create') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), intent(out) :: h
+         integer(c_int), value :: device_ordinal, kk, ncols, nslot, ntype, nmax
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_destroy(h) bind(C, name='rsrec_destroy') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int) :: rc
+      end function
+
+      ! lattice%nn(kk, ncols), lattice%iz(kk)
+      function rsrec_set_lattice(h, nn, iz) bind(C, name='rsrec_set_lattice') result(rc)
+         import :: c_ptr, c_int, c_int32_t
+         type(c_ptr), value :: h
+         integer(c_int32_t), intent(in) :: nn(*), iz(*)
+         integer(c_int) :: rc
+      end function
+
+      ! hamiltonian%ee, eeo, hall, hallo, lsham, enim, hoh   (pass c_null_ptr for unused arrays)
+      function rsrec_set_hamiltonian(h, ee, eeo, hall, hallo, lsham, enim, hoh) &
+         bind(C, name='rsrec_set_hamiltonian') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h, ee, eeo, hall, hallo, lsham, enim
+         integer(c_int), value :: hoh
+         integer(c_int) :: rc
+      end function
+
+      ! hamiltonian%v_a/vo_a (slot = iachar('a')) or v_b/vo_b (slot = iachar('b'))
+      function rsrec_set_operator(h, slot, v_op, vo_op) bind(C, name='rsrec_set_operator') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h, v_op, vo_op
+         integer(c_int), value :: slot
+         integer(c_int) :: rc
+      end function
+
+      ! recur_b / recur_b_ij (+ crecal_b): a_b, b2_b (18,18,lld,nunits)
+      function rsrec_lanczos_block(h, nunits, site_i, site_j, asign, bsign, lld, a_b, b2_b) &
+         bind(C, name='rsrec_lanczos_block') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nunits, lld
+         integer(c_int32_t), intent(in) :: site_i(*), site_j(*)
+         complex(c_double_complex), intent(in) :: asign(*), bsign(*)
+         complex(c_double_complex), intent(out) :: a_b(18, 18, lld, *), b2_b(18, 18, lld, *)
+         integer(c_int) :: rc
+      end function
+
+      ! recur (nsp = 1): a, b2 (lld,18,nunits)
+      function rsrec_lanczos_scalar(h, nunits, sites, lld, a, b2) bind(C, name='rsrec_lanczos_scalar') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: nunits, lld
+         integer(c_int32_t), intent(in) :: sites(*)
+         real(c_double), intent(out) :: a(lld, 18, *), b2(lld, 18, *)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_zsqr(h, b2_b, lld, na) bind(C, name='rsrec_zsqr') result(rc)
+         import :: c_ptr, c_int, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: lld, na
+         complex(c_double_complex), intent(inout) :: b2_b(18, 18, lld, *)
+         integer(c_int) :: rc
+      end function
+
+      ! chebyshev_recur / chebyshev_recur_ij: mu_n (18,18,2*lld+2,nunits)
+      function rsrec_cheb_moments(h, nunits, site_i, site_j, asign, bsign, lld, a_scale, b_shift, mu_n) &
+         bind(C, name='rsrec_cheb_moments') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nunits, lld
+         integer(c_int32_t), intent(in) :: site_i(*), site_j(*)
+         complex(c_double_complex), intent(in) :: asign(*), bsign(*)
+         real(c_double), value :: a_scale, b_shift
+         complex(c_double_complex), intent(out) :: mu_n(18, 18, 2*lld + 2, *)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_cheb_moments_random(h, nvec, phases, lld, a_scale, b_shift, mu_n) &
+         bind(C, name='rsrec_cheb_moments_random') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nvec, lld
+         real(c_double), intent(in) :: phases(*)
+         real(c_double), value :: a_scale, b_shift
+         complex(c_double_complex), intent(out) :: mu_n(18, 18, 2*lld + 2, *)
+         integer(c_int) :: rc
+      end function
+
+      ! compute_moments_stochastic: mu_nm (18,18,cond_ll,cond_ll,nstart)
+      function rsrec_kubo_moments(h, nstart, start_kind, start_sites, phases, cond_ll, a_scale, b_shift, mu_nm) &
+         bind(C, name='rsrec_kubo_moments') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h, start_sites, phases
+         integer(c_int), value :: nstart, start_kind, cond_ll
+         real(c_double), value :: a_scale, b_shift
+         complex(c_double_complex), intent(out) :: mu_nm(18, 18, cond_ll, cond_ll, *)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_ham_vec_matmul(h, psi_in, psi_out, a_scale, b_shift) bind(C, name='rsrec_ham_vec_matmul') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         complex(c_double_complex), intent(in) :: psi_in(18, 18, *)
+         complex(c_double_complex), intent(out) :: psi_out(18, 18, *)
+         real(c_double), value :: a_scale, b_shift
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_velo_vec_matmul(h, slot, psi_in, psi_out) bind(C, name='rsrec_velo_vec_matmul') result(rc)
+         import :: c_ptr, c_int, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: slot
+         complex(c_double_complex), intent(in) :: psi_in(18, 18, *)
+         complex(c_double_complex), intent(out) :: psi_out(18, 18, *)
+         integer(c_int) :: rc
+      end function
+   end interface
+
+contains
+
+   !> C string of rsrec_last_error() as a Fortran string
+   function rsrec_last_error_f() result(msg)
+      character(len=:), allocatable :: msg
+      character(kind=c_char), pointer :: p(:)
+      type(c_ptr) :: cp
+      integer :: n
+      cp = rsrec_last_error()
+      msg = ''
+      if (.not. c_associated(cp)) return
+      call c_f_pointer(cp, p, [1024])
+      n = 0
+      do while (n < 1024)
+         if (p(n + 1) == c_null_char) exit
+         n = n + 1
+      end do
+      allocate (character(len=n) :: msg)
+      if (n > 0) msg = transfer(p(1:n), msg)
+   end function
+
+   !> maps a non-zero status to the reference's fatal convention (logger.f90:186-193)
+   subroutine rsrec_check(rc, file, line)
+      use logger_mod, only: g_logger
+      integer(c_int), intent(in) :: rc
+      character(len=*), intent(in) :: file
+      integer, intent(in) :: line
+      if (rc /= RSREC_OK) call g_logger%fatal('rsrec: '//rsrec_last_error_f(), file, line)
+   end subroutine
+
+end module rsrec_c_mod

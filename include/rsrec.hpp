@@ -1,0 +1,181 @@
+// rsrec.hpp -- C++ host-side mirror of the reference's `type recursion` (source/recursion.f90:41-116) on top of the
+// C ABI in rsrec.h.  Header-only; same procedure names, same result members (column-major, reference shapes), same
+// error behaviour (a fatal condition throws where the reference calls g_logger%fatal).  The structs `lattice`,
+// `hamiltonian`, `control`, `energy` carry exactly the members of the reference types that the recursion reads.
+#pragma once
+#include "rsrec.h"
+
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace rsrec {
+
+using cplx = std::complex<double>;
+
+struct fatal : std::runtime_error {  // g_logger%fatal (logger.f90:186-193)
+  int code;
+  fatal(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+  if (rc != RSREC_OK) throw fatal(rc, rsrec_last_error());
+}
+
+struct lattice {  // lattice.f90:144-309 (members on the hot path)
+  int kk = 0, ncols = 0, ntype = 1, nmax = 0;
+  std::vector<int32_t> nn;      // (kk, ncols) column-major
+  std::vector<int32_t> iz;      // (kk)
+  std::vector<int32_t> irec;    // (nrec) recursion sites
+  std::vector<int32_t> ijpair;  // (njij, 2) column-major
+  int nslot() const {
+    int m = 0;
+    for (int i = 0; i < kk; i++) m = nn[i] > m ? nn[i] : m;
+    return m + 1;  // hamiltonian.f90:294
+  }
+};
+struct hamiltonian {  // hamiltonian.f90:52-66
+  std::vector<cplx> ee, eeo, hall, hallo, lsham, enim, v_a, v_b, vo_a, vo_b;
+  bool hoh = false;
+};
+struct control {  // control.f90:356-384
+  int lld = 16, cond_ll = 200;
+};
+struct energy {
+  double energy_min = -1.5, energy_max = 1.5;
+};
+struct mpi_vars {  // mpi.f90:32-58 (get_mpi_variables)
+  int start_atom = 1, end_atom = 0, atoms_per_process = 0;
+  static mpi_vars get(int rank, int numprocs, int n) {
+    mpi_vars v;
+    v.atoms_per_process = n / numprocs;
+    const int rem = n % numprocs;
+    if (rank < rem) {
+      v.atoms_per_process += 1;
+      v.start_atom = rank * v.atoms_per_process + 1;
+    } else {
+      v.start_atom = rank * v.atoms_per_process + rem + 1;
+    }
+    v.end_atom = v.start_atom + v.atoms_per_process - 1;
+    return v;
+  }
+};
+
+class recursion {
+ public:
+  // results, reference shapes
+  std::vector<cplx> a_b, b2_b;   // (18,18,lld,nunits)
+  std::vector<double> a, b2;     // (lld,18,nunits)   [this%a(:,:,:,1)]
+  std::vector<cplx> mu_n;        // (18,18,2*lld+2,nunits)
+  std::vector<cplx> mu_nm_stochastic;
+
+  recursion(const hamiltonian &h, const lattice &l, const control &c, const energy &e, int device = 0, int rank = 0,
+            int numprocs = 1)
+      : ham_(h), lat_(l), ctl_(c), en_(e), rank_(rank), np_(numprocs) {
+    check(rsrec_create(&h_, device, l.kk, l.ncols, l.nslot(), l.ntype, l.nmax));
+    upload();
+  }
+  ~recursion() { rsrec_destroy(h_); }
+  recursion(const recursion &) = delete;
+
+  void upload() {
+    check(rsrec_set_lattice(h_, lat_.nn.data(), lat_.iz.data()));
+    check(rsrec_set_hamiltonian(h_, p(ham_.ee), p(ham_.eeo), p(ham_.hall), p(ham_.hallo), p(ham_.lsham), p(ham_.enim),
+                                ham_.hoh));
+    if (!ham_.v_a.empty()) {
+      check(rsrec_set_operator(h_, 'a', p(ham_.v_a), p(ham_.vo_a)));
+      check(rsrec_set_operator(h_, 'b', p(ham_.v_b), p(ham_.vo_b)));
+    }
+  }
+
+  void recur_b() {  // recursion.f90:1807-1866
+    const auto sites = local_sites();
+    const int n = (int)sites.size(), lld = ctl_.lld;
+    a_b.assign((size_t)324 * lld * n, 0.0);
+    b2_b.assign((size_t)324 * lld * n, 0.0);
+    check(rsrec_lanczos_block(h_, n, sites.data(), nullptr, nullptr, nullptr, lld, rc(a_b), rc(b2_b)));
+    a.assign((size_t)lld * 18 * n, 0.0);
+    b2.assign((size_t)lld * 18 * n, 0.0);
+    for (int u = 0; u < n; u++)
+      for (int l = 0; l < 18; l++)
+        for (int ll = 0; ll < lld; ll++) {
+          a[ll + (size_t)lld * (l + 18 * u)] = a_b[(l + 18 * l) + (size_t)324 * (ll + (size_t)lld * u)].real();
+          b2[ll + (size_t)lld * (l + 18 * u)] = b2_b[(l + 18 * l) + (size_t)324 * (ll + (size_t)lld * u)].real();
+        }
+  }
+  void recur() {  // recursion.f90:3485-3532
+    const auto sites = local_sites();
+    const int n = (int)sites.size(), lld = ctl_.lld;
+    a.assign((size_t)lld * 18 * n, 0.0);
+    b2.assign((size_t)lld * 18 * n, 0.0);
+    check(rsrec_lanczos_scalar(h_, n, sites.data(), lld, a.data(), b2.data()));
+  }
+  void zsqr() {  // recursion.f90:1980-2023
+    const int lld = ctl_.lld;
+    check(rsrec_zsqr(h_, rc(b2_b), lld, (int)(b2_b.size() / ((size_t)324 * lld))));
+  }
+  void chebyshev_recur() {  // recursion.f90:3057-3130
+    const auto sites = local_sites();
+    const int n = (int)sites.size(), lld = ctl_.lld;
+    mu_n.assign((size_t)324 * (2 * lld + 2) * n, 0.0);
+    check(rsrec_cheb_moments(h_, n, sites.data(), nullptr, nullptr, nullptr, lld, scale(), shift(), rc(mu_n)));
+  }
+  // recur_b_ij / chebyshev_recur_ij (recursion.f90:1655-1737 / 2376-2487): slot ij_loc*4-4+reci
+  void recur_b_ij() { pair_run(true); }
+  void chebyshev_recur_ij() { pair_run(false); }
+
+  double scale() const { return (en_.energy_max - en_.energy_min) / (2 - 0.3); }  // recursion.f90:3078
+  double shift() const { return (en_.energy_max + en_.energy_min) / 2; }          // recursion.f90:3079
+  rsrec_handle handle() const { return h_; }
+
+ private:
+  static const rsrec_cplx *p(const std::vector<cplx> &v) { return v.empty() ? nullptr : reinterpret_cast<const rsrec_cplx *>(v.data()); }
+  static rsrec_cplx *rc(std::vector<cplx> &v) { return reinterpret_cast<rsrec_cplx *>(v.data()); }
+  std::vector<int32_t> local_sites() const {
+    const auto v = mpi_vars::get(rank_, np_, (int)lat_.irec.size());
+    return std::vector<int32_t>(lat_.irec.begin() + (v.start_atom - 1), lat_.irec.begin() + v.end_atom);
+  }
+  void pair_run(bool lanczos) {
+    const int njij = (int)lat_.ijpair.size() / 2, lld = ctl_.lld;
+    const auto v = mpi_vars::get(rank_, np_, njij);
+    const int nloc = v.atoms_per_process;
+    std::vector<int32_t> si, sj, slots;
+    std::vector<cplx> as, bs;
+    const double s = 1.0 / std::sqrt(2.0);
+    const cplx sg[4] = {{s, 0}, {-s, 0}, {0, s}, {0, -s}};
+    for (int ij = v.start_atom; ij <= v.end_atom; ij++) {
+      const int i = lat_.ijpair[ij - 1], j = lat_.ijpair[ij - 1 + njij];
+      for (int reci = 0; reci < 4; reci++) {
+        if (i == j && reci > 0) continue;
+        si.push_back(i); sj.push_back(j);
+        as.push_back(i == j ? cplx(1.0) : cplx(s));
+        bs.push_back(i == j ? cplx(1.0) : sg[reci]);
+        slots.push_back((ij - v.start_atom) * 4 + reci);
+      }
+    }
+    const int n = (int)si.size();
+    const size_t per = lanczos ? (size_t)324 * lld : (size_t)324 * (2 * lld + 2);
+    std::vector<cplx> r1(per * n), r2(lanczos ? per * n : 0);
+    if (lanczos)
+      check(rsrec_lanczos_block(h_, n, si.data(), sj.data(), p(as), p(bs), lld, rc(r1), rc(r2)));
+    else
+      check(rsrec_cheb_moments(h_, n, si.data(), sj.data(), p(as), p(bs), lld, scale(), shift(), rc(r1)));
+    std::vector<cplx> &o1 = lanczos ? a_b : mu_n;
+    o1.assign(per * 4 * nloc, 0.0);
+    if (lanczos) b2_b.assign(per * 4 * nloc, 0.0);
+    for (int u = 0; u < n; u++) {
+      std::copy(r1.begin() + per * u, r1.begin() + per * (u + 1), o1.begin() + per * slots[u]);
+      if (lanczos) std::copy(r2.begin() + per * u, r2.begin() + per * (u + 1), b2_b.begin() + per * slots[u]);
+    }
+  }
+  const hamiltonian &ham_;
+  const lattice &lat_;
+  control ctl_;
+  energy en_;
+  int rank_, np_;
+  rsrec_handle h_ = nullptr;
+};
+
+}  // namespace rsrec
