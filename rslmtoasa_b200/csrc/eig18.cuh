@@ -29,7 +29,9 @@ __device__ void eig18_jacobi(Eig18Smem &s) {
   __syncthreads();
   atomicAdd(&s.tot, ar * ar + ai * ai);
   __syncthreads();
-  const double thresh = 1e-64 * s.tot;
+  // |a_ij|^2 <= 1e-40 ||A||_F^2: off-diagonal elements perturb eigenvalues at second order (~1e-40 ||A||),
+  // far below double precision; Jacobi converges quadratically so this saves about one sweep over 1e-64.
+  const double thresh = 1e-40 * s.tot;
   for (int sweep = 0; sweep < 40; sweep++) {
     const int notconv = __syncthreads_or(r != c && (s.Ar[tid] * s.Ar[tid] + s.Ai[tid] * s.Ai[tid]) > thresh);
     if (!notconv) break;
@@ -40,15 +42,16 @@ __device__ void eig18_jacobi(Eig18Smem &s) {
         const int p = min(a_, b_), q = max(a_, b_);
         s.pp[tid] = p; s.qq[tid] = q; s.pair_of[p] = tid; s.pair_of[q] = tid;
         const double pr = s.Ar[p + NB * q], pi = s.Ai[p + NB * q];
-        const double mag = sqrt(pr * pr + pi * pi);
+        const double m2 = pr * pr + pi * pi;  // |a_pq|^2
         double cs = 1.0, sr = 0.0, si = 0.0;
-        if (mag > 1e-300) {
-          const double app = s.Ar[p + NB * p], aqq = s.Ar[q + NB * q];
-          const double tau = (aqq - app) / (2.0 * mag);
-          const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          cs = 1.0 / sqrt(1.0 + tt * tt);
-          const double sn = tt * cs;
-          sr = sn * pr / mag; si = sn * pi / mag;  // sn * e^{i phi}
+        if (m2 > 1e-300) {
+          // t = tan(theta) = sign(z) |a_pq| / (|z| + sqrt(z^2 + |a_pq|^2)),  z = (a_qq - a_pp)/2.  With u = t/|a_pq|
+          // the rotation is cs = 1/sqrt(1 + u^2 |a_pq|^2), sn e^{i phi} = cs * u * a_pq: one sqrt, one division and
+          // one rsqrt on the critical path instead of three square roots and four divisions.
+          const double z = 0.5 * (s.Ar[q + NB * q] - s.Ar[p + NB * p]);
+          const double u = (z >= 0.0 ? 1.0 : -1.0) / (fabs(z) + sqrt(z * z + m2));
+          cs = rsqrt(1.0 + u * u * m2);
+          sr = cs * u * pr; si = cs * u * pi;
         }
         s.cs[tid] = cs; s.sr[tid] = sr; s.si[tid] = si;
       }
@@ -104,16 +107,14 @@ __device__ __forceinline__ void eig18_func(const Eig18Smem &s, const double *f, 
   out[2 * tid] = orr; out[2 * tid + 1] = oi;
 }
 
-// crecal_b "B_n+1": reduce the B^2 partials of unit blockIdx.x (fixed order), record B^2 in the history slot,
-// then B = U sqrt(L) U^H and B^-1 = U L^-1/2 U^H.  diag != 0: scalar Lanczos, everything diagonal & real.
-__global__ void __launch_bounds__(BLKC) k_lz_eig(const double *part, int nctas, double *b2_hist_slot, size_t hstride,
+// crecal_b "B_n+1": take the reduced B^2 of unit blockIdx.x (k_reduce_parts), record it in the history slot, then
+// B = U sqrt(L) U^H and B^-1 = U L^-1/2 U^H.  diag != 0: scalar Lanczos, everything diagonal & real.
+__global__ void __launch_bounds__(BLKC) k_lz_eig(const double *b2, size_t b2stride, double *b2_hist_slot, size_t hstride,
                                                  double *Bmat, double *Bimat, size_t bstride, int diag) {
   __shared__ Eig18Smem s;
   __shared__ double f1[NB], f2[NB];
   const int tid = threadIdx.x, unit = blockIdx.x, r = tid % NB, c = tid / NB;
-  const double *pp = part + (size_t)unit * nctas * (2 * BLKD);
-  double mr = 0, mi = 0;
-  for (int cta = 0; cta < nctas; cta++) { mr += pp[(size_t)cta * (2 * BLKD) + 2 * tid]; mi += pp[(size_t)cta * (2 * BLKD) + 2 * tid + 1]; }
+  double mr = b2[(size_t)unit * b2stride + 2 * tid], mi = b2[(size_t)unit * b2stride + 2 * tid + 1];
   if (diag) { if (r != c) mr = 0.0; mi = 0.0; }
   b2_hist_slot[(size_t)unit * hstride + 2 * tid] = mr;
   b2_hist_slot[(size_t)unit * hstride + 2 * tid + 1] = mi;

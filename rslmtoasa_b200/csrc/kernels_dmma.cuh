@@ -493,10 +493,10 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
-static int dmma_launch_gram(const double *X, const double *Y, int two, int kk, size_t vstride, int nunits, int sms,
-                            double *part, cudaStream_t st, long long *launches) {
-  dim3 grid(dmma_gram_ctas(kk, sms), nunits);
-  k_gram_dmma<<<grid, GR_THREADS, GR_SMEM_BYTES, st>>>(X, Y, two, kk, vstride, vstride, part);
+static int dmma_launch_gram(const double *X, size_t xstride, const double *Y, size_t ystride, int two, int kk,
+                            int nunits, int ctas, double *part, cudaStream_t st, long long *launches) {
+  dim3 grid(ctas, nunits);
+  k_gram_dmma<<<grid, GR_THREADS, GR_SMEM_BYTES, st>>>(X, Y, two, kk, xstride, ystride, part);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

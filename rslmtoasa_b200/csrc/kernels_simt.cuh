@@ -128,30 +128,36 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gram_simt(const double *X, con
 }
 
 // Fixed-order reduction of the per-CTA partials: out[unit][which] (complex 18x18, host layout) = sum_cta part.
+// One warp per matrix element: lane l sums partials l, l+32, ... in order, then a fixed xor-shuffle tree --
+// deterministic for a given partial count, and ~40x shorter latency than one thread walking all partials.
 // mode 0: plain store to dst0 (+ dst1 for matrix 1 if non-null)
 // mode 1: Chebyshev finish: dst0 = 2*D1 - mu0, dst1 = 2*D2 - mu1   (recursion.f90:2591-2592)
 // mode 2: diagonal projection (scalar Lanczos): keep Re(diag) only
+// grid = (ceil(2*648 / warps_per_block), nunits)
 __global__ void k_reduce_parts(const double *part, int nctas, int mode, double *dst0, double *dst1, size_t dstride,
                                const double *mu0, const double *mu1) {
-  const int unit = blockIdx.x;
-  for (int e = threadIdx.x; e < 2 * BLKD; e += blockDim.x) {
-    const double *pp = part + (size_t)unit * nctas * (2 * BLKD) + e;
-    double s = 0.0;
-    for (int cta = 0; cta < nctas; cta++) s += pp[(size_t)cta * (2 * BLKD)];
-    const int which = e / BLKD, idx = e % BLKD;
-    if (mode == 1) {
-      const double *m = which ? mu1 : mu0;
-      double *d = which ? dst1 : dst0;
-      d[(size_t)unit * dstride + idx] = 2.0 * s - m[(size_t)unit * dstride + idx];
-    } else {
-      double *d = which ? dst1 : dst0;
-      if (!d) continue;
-      if (mode == 2) {
-        const int ce = idx / 2, im = idx & 1, i = ce % NB, j = ce / NB;
-        if (i != j || im) s = 0.0;
-      }
-      d[(size_t)unit * dstride + idx] = s;
+  const int unit = blockIdx.y, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= 2 * BLKD) return;
+  const double *pp = part + (size_t)unit * nctas * (2 * BLKD) + e;
+  double s = 0.0;
+  for (int cta = lane; cta < nctas; cta += 32) s += pp[(size_t)cta * (2 * BLKD)];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
+  const int which = e / BLKD, idx = e % BLKD;
+  if (mode == 1) {
+    const double *m = which ? mu1 : mu0;
+    double *d = which ? dst1 : dst0;
+    d[(size_t)unit * dstride + idx] = 2.0 * s - m[(size_t)unit * dstride + idx];
+  } else {
+    double *d = which ? dst1 : dst0;
+    if (!d) return;
+    if (mode == 2) {
+      const int ce = idx / 2, im = idx & 1, i = ce % NB, j = ce / NB;
+      if (i != j || im) s = 0.0;
     }
+    d[(size_t)unit * dstride + idx] = s;
   }
 }
 

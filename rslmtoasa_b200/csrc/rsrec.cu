@@ -57,7 +57,7 @@ struct rsrec_handle_s {
   DmmaTiles tiles;
   // work vectors and small matrices
   std::vector<DevBuf> vecs;
-  DevBuf part, A, B, Bi, mu, ahist, b2hist, scratch;
+  DevBuf part, A, B, Bi, B2, mu, ahist, b2hist, scratch;
   int32_t *d_si = nullptr, *d_sj = nullptr;
   double *d_as = nullptr, *d_bs = nullptr;
   int units_cap = 0;
@@ -308,27 +308,36 @@ static int apply_op(H *h, OpKind op, const double *in, double *out, const double
   return launch_apply(h, p, nunits, nctas);
 }
 
-// part[unit][cta][0] = sum_sites X^H Y  (k_gram_simt / k_gram_dmma argument order: first factor is conjugated)
-static int launch_gram(H *h, const double *X, const double *Y, int nunits, int nctas, double *part) {
+// part[unit][cta][0] = sum_sites X^H Y  (first factor conjugated); xs/ys: doubles between units (0 = shared vector)
+static int launch_gram_strided(H *h, const double *X, size_t xs, const double *Y, size_t ys, int nunits, int nctas,
+                               double *part) {
   if (h->family == 1) {
-    if (dmma_launch_gram(Y, X, 0, h->kk, vstride(h), nunits, h->sms, part, h->st, &h->launches) != 0)
+    // many units in one launch (Kubo contraction): fewer CTAs per unit, the grid is filled by the unit dimension
+    const int ctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms + nunits - 1) / nunits));
+    if (dmma_launch_gram(Y, ys, X, xs, 0, h->kk, nunits, ctas, part, h->st, &h->launches) != 0)
       return fail(RSREC_ECUDA, std::string("k_gram_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-    h->last_parts = dmma_gram_ctas(h->kk, h->sms);
+    h->last_parts = ctas;
     return RSREC_OK;
   }
-  dim3 grid(nctas, nunits);
-  k_gram_simt<<<grid, SIMT_THREADS, 0, h->st>>>(X, Y, h->kk, vstride(h), vstride(h), part);
+  const int ctas = std::max(1, std::min(nctas, (6 * h->sms + nunits - 1) / nunits));
+  dim3 grid(ctas, nunits);
+  k_gram_simt<<<grid, SIMT_THREADS, 0, h->st>>>(X, Y, h->kk, xs, ys, part);
   h->launches++;
-  h->last_parts = nctas;
+  h->last_parts = ctas;
   CUDA_TRY(cudaGetLastError());
   return RSREC_OK;
 }
+static int launch_gram(H *h, const double *X, const double *Y, int nunits, int nctas, double *part) {
+  return launch_gram_strided(h, X, vstride(h), Y, vstride(h), nunits, nctas, part);
+}
 static size_t part_doubles(const H *h, int nunits, int nctas) {
-  return (size_t)nunits * std::max(nctas, dmma_gram_ctas(h->kk, h->sms)) * 2 * BLKD;
+  const int simt = std::max(1, std::min(nctas, (6 * h->sms + nunits - 1) / nunits));
+  const int dm = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms + nunits - 1) / nunits));
+  return (size_t)nunits * std::max(std::max(simt, dm), std::min(nctas, nctas_for(h, nunits))) * 2 * BLKD;
 }
 static int launch_reduce(H *h, int nunits, int /*nctas*/, int mode, double *d0, double *d1, size_t dstride,
                          const double *m0, const double *m1) {
-  k_reduce_parts<<<nunits, 256, 0, h->st>>>(h->part.p, h->last_parts, mode, d0, d1, dstride, m0, m1);
+  k_reduce_parts<<<dim3((2 * BLKD + 7) / 8, nunits), 256, 0, h->st>>>(h->part.p, h->last_parts, mode, d0, d1, dstride, m0, m1);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return RSREC_OK;
@@ -371,6 +380,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   TRY(dev_alloc(h->A, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->B, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->Bi, (size_t)nunits * BLKD, false));
+  TRY(dev_alloc(h->B2, (size_t)nunits * BLKD, false));
   const size_t hs = (size_t)lld * BLKD;  // history stride per unit (doubles)
   TRY(dev_alloc(h->ahist, (size_t)nunits * hs, false));
   TRY(dev_alloc(h->b2hist, (size_t)nunits * hs, false));
@@ -397,7 +407,8 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     k_lz_ortho_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, hpsi, h->A.p, BLKD, h->kk, vstride(h), h->part.p);
     h->last_parts = nctas;
     // B2 -> history slot ll+1, B, B^-1
-    k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->part.p, h->last_parts, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
+    TRY(launch_reduce(h, nunits, nctas, 0, h->B2.p, nullptr, BLKD, nullptr, nullptr));
+    k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->B2.p, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
                                          BLKD, diag ? 1 : 0);
     // psi = pmn B^-1 ; pmn = psi_old B
     k_lz_rotate_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->B.p, h->Bi.p, BLKD, h->kk, vstride(h));
@@ -452,9 +463,10 @@ static int cheb_steps(H *h, int nsteps) {
     // psi2 = 2 (H psi1 - b psi1)/a - psi0, written over psi0; D1 = sum psi1^H psi1, D2 = sum psi2^H psi1
     if (h->family == 1) {
       TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB_NOGRAM, c.a, c.b, c.nunits, c.nctas, nullptr));
-      if (dmma_launch_gram(p1, p0, 1, h->kk, vstride(h), c.nunits, h->sms, h->part.p, h->st, &h->launches) != 0)
+      const int gctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms + c.nunits - 1) / c.nunits));
+      if (dmma_launch_gram(p1, vstride(h), p0, vstride(h), 1, h->kk, c.nunits, gctas, h->part.p, h->st, &h->launches) != 0)
         return fail(RSREC_ECUDA, std::string("k_gram_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-      h->last_parts = dmma_gram_ctas(h->kk, h->sms);
+      h->last_parts = gctas;
     } else {
       TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB, c.a, c.b, c.nunits, c.nctas, h->part.p));
     }
@@ -525,7 +537,7 @@ int rsrec_destroy(rsrec_handle h) {
   cudaStreamSynchronize(h->st);
   for (auto &v : h->vecs) dev_free(v);
   DevBuf *bufs[] = {&h->Hmain, &h->Hh, &h->Hho_neg, &h->Hx, &h->Hscalar, &h->Hva, &h->Hvb, &h->Hvoa_neg, &h->Hvob_neg,
-                    &h->part, &h->A, &h->B, &h->Bi, &h->mu, &h->ahist, &h->b2hist, &h->scratch};
+                    &h->part, &h->A, &h->B, &h->Bi, &h->B2, &h->mu, &h->ahist, &h->b2hist, &h->scratch};
   for (auto b : bufs) dev_free(*b);
   dmma_free_tiles(h->tiles);
   if (h->d_nbr) cudaFree(h->d_nbr);
@@ -781,8 +793,10 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
   TRY(get_vec(h, 0, 1, &psiref)); TRY(get_vec(h, 1, 1, &tmp)); TRY(get_vec(h, 2, 1, &v0));
   TRY(get_vec(h, 3, 1, &v1)); TRY(get_vec(h, 4, 1, &right)); TRY(get_vec(h, 5, 1, &spare));
   std::vector<double *> left(M);
-  for (int m = 0; m < M; m++) TRY(get_vec(h, 6 + m, 1, &left[m]));
-  TRY(dev_alloc(h->part, part_doubles(h, 1, nctas), false));
+  double *leftbuf;  // the reference's left_vec(18,18,kk,cond_ll): one batched allocation, unit m = T_m|r>
+  TRY(get_vec(h, 6, M, &leftbuf));
+  for (int m = 0; m < M; m++) left[m] = leftbuf + (size_t)m * vstride(h);
+  TRY(dev_alloc(h->part, part_doubles(h, M, nctas), false));
   TRY(dev_alloc(h->mu, (size_t)M * M * BLKD, false));
   const int32_t one = 1;
   for (int s = 0; s < nstart; s++) {
@@ -818,11 +832,9 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
         cur = c1;
       }
       TRY(apply_op(h, OP_VELO_A, cur, right, nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas, nullptr));
-      for (int m = 0; m < M; m++) {
-        TRY(launch_gram(h, left[m], right, 1, nctas, h->part.p));
-        // mu_nm_stochastic(:,:,n,m,i)
-        TRY(launch_reduce(h, 1, nctas, 0, h->mu.p + ((size_t)n + (size_t)M * m) * BLKD, nullptr, 0, nullptr, nullptr));
-      }
+      // mu_nm_stochastic(:,:,n,m,i) = sum_k left_vec(:,:,k,m)^H right_vec(:,:,k) for all m in one launch (1220-1228)
+      TRY(launch_gram_strided(h, leftbuf, vstride(h), right, 0, M, nctas, h->part.p));
+      TRY(launch_reduce(h, M, nctas, 0, h->mu.p + (size_t)n * BLKD, nullptr, (size_t)M * BLKD, nullptr, nullptr));
     }
     CUDA_TRY(cudaMemcpyAsync(mu_nm + (size_t)s * M * M * BLKC, h->mu.p, (size_t)M * M * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)M * M * BLKD * sizeof(double));
     CUDA_TRY(cudaStreamSynchronize(h->st));

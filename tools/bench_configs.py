@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Times BASELINE.json configs 1-4 (full sizes) through the reference-facing API (host arrays in, host arrays out),
+with the CPU oracle beside it on a bounded number of steps, and checks parity where the oracle runs in seconds.
+Output: one JSON object per config (stdout) -> profiles/rNN_configs.json."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rslmtoasa_b200 import Recursion, Control, Energy, synthetic as S  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+EMIN, EMAX = -2.0, 2.0
+
+
+def relerr(x, r):
+    return float(np.abs(x - r).max() / np.abs(r).max())
+
+
+def timed(fn, reps=3):
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run(name, lat, ham, lld, what, cpu=True, **kw):
+    ctl = Control(lld=lld, **{k: v for k, v in kw.items() if k in ("cond_ll", "cond_calctype")})
+    extra = {k: v for k, v in kw.items() if k in ("ijpair", "atlist", "phases")}
+    rec = Recursion(ham, lat, ctl, Energy(EMIN, EMAX), **extra)
+    out = {"config": name, "kk": lat.kk, "ntype": lat.ntype, "nmax": lat.nmax, "nslots": lat.ncols, "hoh": bool(ham.hoh),
+           "units": int(len(lat.irec)), "lld": lld, "what": what}
+    a, b = O.cheb_scale(EMIN, EMAX)
+    orc = O.Oracle(lat, ham) if cpu else None
+    if what == "recur_b":
+        t = timed(rec.recur_b)
+        steps = (lld - 1) * len(lat.irec)
+        if cpu:
+            t0 = time.perf_counter(); ra, rb = orc.lanczos_block(lat.irec, lld); tc = time.perf_counter() - t0
+            out["relerr_a_b"], out["relerr_b2_b"] = relerr(rec.a_b, ra), relerr(rec.b2_b, rb)
+    elif what == "chebyshev_recur":
+        t = timed(rec.chebyshev_recur)
+        steps = lld * len(lat.irec)
+        if cpu:
+            t0 = time.perf_counter(); rm, _ = orc.cheb_moments(lat.irec, lld, a, b); tc = time.perf_counter() - t0
+            out["relerr_mu_n"] = relerr(rec.mu_n, rm)
+    elif what == "recur":
+        t = timed(rec.recur)
+        steps = (lld - 1) * 18 * len(lat.irec)   # 18 scalar recursions per site
+        if cpu:
+            t0 = time.perf_counter(); ra, rb = orc.lanczos_scalar(lat.irec, lld); tc = time.perf_counter() - t0
+            out["relerr_a"], out["relerr_b2"] = relerr(rec.a[..., 0], ra), relerr(rec.b2[..., 0], rb)
+    elif what == "kubo":
+        M = kw["cond_ll"]
+        t = timed(rec.compute_moments_stochastic, reps=1)
+        nst = len(kw["atlist"]) if "atlist" in kw else kw["phases"].shape[1]
+        steps = 3 * M * nst                       # SpMV-equivalents: M left + M right + M velocity
+        if cpu:
+            t0 = time.perf_counter()
+            rm = orc.kubo_moments(M, a, b, start_sites=kw.get("atlist"), phases=kw.get("phases"))
+            tc = time.perf_counter() - t0
+            out["relerr_mu_nm"] = relerr(rec.mu_nm_stochastic, rm)
+    out.update({"gpu_seconds": t, "gpu_steps_per_s": steps / t, "steps": steps, "launches": rec.launch_count})
+    if cpu:
+        out.update({"cpu_seconds": tc, "cpu_steps_per_s": steps / tc, "cpu_threads": O.lib().orc_get_max_threads(),
+                    "speedup": tc / t})
+    print(json.dumps(out), flush=True)
+    rec.close()
+
+
+def main():
+    quick = "--quick" in sys.argv
+    # config 1: bulk bcc Fe, rc = 80 -> kk = 5984, 1 type, 1 unit, lld = 21, block Lanczos (hoh F/T) + Chebyshev lld=100
+    lat = S.sphere_cluster("bcc", 80.0)
+    run("1 bulk bccFe block", lat, S.make_hamiltonian(lat, seed=20260101), 21, "recur_b")
+    run("1 bulk bccFe block hoh", lat, S.make_hamiltonian(lat, seed=20260101, hoh=True), 21, "recur_b")
+    run("1 bulk bccFe chebyshev", lat, S.make_hamiltonian(lat, seed=20260101), 100, "chebyshev_recur")
+    ham = S.make_hamiltonian(lat, seed=20260101, spin_orbit=False)
+    run("1 bulk bccFe lanczos (scalar, nsp=1)", lat, ham, 21, "recur")
+    # config 2: surface: fcc sphere r2 = 100 (16756 sites), 7 layer types, 19 slots, 6 units batched
+    lat = S.sphere_cluster("fcc", 100.0, ntype=7, type_rule="layer")
+    lat.irec = np.array([1, 2, 3, 14, 15, 20], dtype=np.int32)
+    run("2 surface fcc 6 units block", lat, S.make_hamiltonian(lat, seed=20260102), 21, "recur_b")
+    run("2 surface fcc 6 units chebyshev", lat, S.make_hamiltonian(lat, seed=20260102), 100, "chebyshev_recur", cpu=not quick)
+    # config 3: impurity: B2 sphere r2 = 60 (3838 sites), 3 types, 15 site-indexed sites
+    lat = S.sphere_cluster("bcc", 60.0, ntype=3, nmax=15, type_rule="b2")
+    run("3 impurity B2 nmax=15 block", lat, S.make_hamiltonian(lat, seed=20260103), 21, "recur_b")
+    run("3 impurity B2 nmax=15 block hoh", lat, S.make_hamiltonian(lat, seed=20260103, hoh=True), 21, "recur_b")
+    # config 4: conductivity: bcc PBC 20^3 cells (SURVEY: kk = 8000 -> 10x20x20 cells x 2), Kubo moments
+    lat = S.periodic_bcc(10, 20, 20)
+    ham = S.make_hamiltonian(lat, seed=20260104, velocity=True)
+    run("4 conductivity per_type cond_ll=50", lat, ham, 21, "kubo", cond_ll=50, cond_calctype="per_type", atlist=[1], cpu=not quick)
+    if not quick:
+        run("4 conductivity random_vec cond_ll=300", lat, ham, 21, "kubo", cond_ll=300, cond_calctype="random_vec",
+            phases=S.random_phases(lat.kk, 1), cpu=False)
+
+
+if __name__ == "__main__":
+    main()
