@@ -383,6 +383,209 @@ k_gram_dmma(const double *__restrict__ X, const double *__restrict__ Y, int two,
   }
 }
 
+// ---- right-multiplications of crecal_b on the tensor pipe ------------------------------------------------------
+// X(18,18,site) * M(18x18) for every site is, in RI36/real form,  OUT[(s,k)][c'] = sum_j' Xhat_s[k][j'] Mhat[j'][c']
+// with Xhat = [Xre | Xim] (18x36) and Mhat = [[Mre, Mim],[-Mim, Mre]] (36x36): M = 144 rows per 8-site tile (exact),
+// N = 36 -> 40, K = 36 -- the same 90-unit shape as one SpMV stage, with the tile read "transposed" from shared
+// memory.  These passes are HBM-bound (2.5 flop/B), so tiles are contiguous 41 kB TMA bulk copies, 2-stage ring.
+//   RM_ORTHO : pmn <- (hpsi - pmn) - psi*A            (hop_b 1641 + crecal_b 1927;  hpsi == nullptr: pmn - psi*A)
+//   RM_ROTATE: psi <- pmn*Binv ; pmn <- psi_old*B     (crecal_b 1966-1967)
+enum RmulMode { RM_ORTHO = 0, RM_ROTATE = 1 };
+#define RM_TILE_D (DM_S * BLKD)                       // 5184 doubles = 41472 B
+#define RM_SMEM_BYTES (2 * 2 * RM_TILE_D * 8 + 2 * HBLK * 8 + 64)
+
+template <int XN>
+__device__ __forceinline__ void rmul_product(const double *xs, const double *ts, const int (&aoff)[3], const int (&koff)[9],
+                                             const int (&boff)[5], const int (&xoff)[2], double (&acc)[2][5][2],
+                                             double (&xacc)[2][2]) {
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) acc[i][nt][0] = acc[i][nt][1] = 0.0;
+#pragma unroll
+  for (int x = 0; x < 2; x++) xacc[x][0] = xacc[x][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 9; ks++) {
+    double b[5], xb[2];
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) b[nt] = ts[boff[nt] + 4 * ks];
+#pragma unroll
+    for (int x = 0; x < XN; x++) xb[x] = ts[xoff[x] + 4 * ks];
+    const double a0 = xs[aoff[0] + koff[ks]], a1 = xs[aoff[1] + koff[ks]], a2 = xs[aoff[2] + koff[ks]];
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) {
+      dmma(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
+      dmma(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
+    }
+#pragma unroll
+    for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], a2, xb[x]);
+  }
+}
+
+template <int MODE, int XN>
+__device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const double *hpsi, int kk, double *tiles,
+                                              const double *tmat, uint64_t *full, uint64_t *empty, int warp, int lane) {
+  const int g = lane >> 2, q = lane & 3;
+  const int mt[3] = {2 * warp, 2 * warp + 1, 16 + (warp >> 2)};
+  const int w4 = warp & 3;
+  const int xn[2] = {(warp == 6) ? 2 : (warp == 7) ? 4 : w4, ((warp == 6) ? 2 : (warp == 7) ? 4 : w4) + 1};
+  int aoff[3], koff[9], boff[5], xoff[2], rows[3], rowk[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int n = mt[i] * 8 + g;
+    rows[i] = n / NB; rowk[i] = n % NB;
+    aoff[i] = rows[i] * BLKD + rowk[i];
+  }
+#pragma unroll
+  for (int ks = 0; ks < 9; ks++) { const int j = 4 * ks + q; koff[ks] = (j % NB) * COLD + (j / NB) * NB; }
+#pragma unroll
+  for (int nt = 0; nt < 5; nt++) boff[nt] = min(nt * 8 + g, 35) * COLD + q;
+#pragma unroll
+  for (int x = 0; x < 2; x++) xoff[x] = min(xn[x] * 8 + g, 35) * COLD + q;
+  const int ntiles = (kk + DM_S - 1) / DM_S;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    const int slot = it & 1;
+    const double *sm = tiles + (size_t)slot * 2 * RM_TILE_D;
+    const int site0 = tile * DM_S;
+    // output element (row n = (s,k), column c') -> RI36 offset
+    auto gofs = [&](int i, int c) { return (size_t)(site0 + rows[i]) * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
+    auto valid = [&](int i, int c) { return c < 2 * NB && site0 + rows[i] < kk; };
+    double acc[2][5][2], xacc[2][2];
+    if (MODE == RM_ORTHO) {
+      // prefetch the addends (hpsi - pmn) in the accumulator-fragment pattern while the tile lands
+      double ad[2][5][2], xad[2][2];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c = nt * 8 + 2 * q + e;
+            double v = 0.0;
+            if (valid(i, c)) { const size_t o = gofs(i, c); v = hpsi ? hpsi[o] - pmn[o] : pmn[o]; }
+            ad[i][nt][e] = v;
+          }
+#pragma unroll
+      for (int x = 0; x < XN; x++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = xn[x] * 8 + 2 * q + e;
+          double v = 0.0;
+          if (valid(2, c)) { const size_t o = gofs(2, c); v = hpsi ? hpsi[o] - pmn[o] : pmn[o]; }
+          xad[x][e] = v;
+        }
+      mbar_wait(&full[slot], (it >> 1) & 1);
+      rmul_product<XN>(sm, tmat, aoff, koff, boff, xoff, acc, xacc);  // psi * (-A)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int nt = 0; nt < 5; nt++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c = nt * 8 + 2 * q + e;
+            if (valid(i, c)) pmn[gofs(i, c)] = ad[i][nt][e] + acc[i][nt][e];
+          }
+#pragma unroll
+      for (int x = 0; x < XN; x++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = xn[x] * 8 + 2 * q + e;
+          if (valid(2, c)) pmn[gofs(2, c)] = xad[x][e] + xacc[x][e];
+        }
+    } else {
+      mbar_wait(&full[slot], (it >> 1) & 1);
+      // tile 0 = pmn, tile 1 = psi;  tmat 0 = Binv, tmat 1 = B
+#pragma unroll
+      for (int pass = 0; pass < 2; pass++) {
+        rmul_product<XN>(sm + (size_t)pass * RM_TILE_D, tmat + (size_t)pass * HBLK, aoff, koff, boff, xoff, acc, xacc);
+        if (pass == 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+        double *out = pass == 0 ? psi : pmn;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int nt = 0; nt < 5; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int c = nt * 8 + 2 * q + e;
+              if (valid(i, c)) out[gofs(i, c)] = acc[i][nt][e];
+            }
+#pragma unroll
+        for (int x = 0; x < XN; x++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int c = xn[x] * 8 + 2 * q + e;
+            if (valid(2, c)) out[gofs(2, c)] = xacc[x][e];
+          }
+      }
+    }
+  }
+}
+
+// grid = (ctas, nunits).  m0/m1: complex column-major 18x18 per unit (stride mstride doubles): ORTHO m0 = A;
+// ROTATE m0 = Binv, m1 = B.
+template <int MODE>
+__global__ void __launch_bounds__(DM_THREADS, 1)
+k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const double *m0, const double *m1, size_t mstride,
+            int kk, size_t vstride) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);                       // [2 slots][2 tiles]
+  double *tmat = tiles + 2 * 2 * RM_TILE_D;                                   // [2][36x36]: T[c'][j'] = Mhat[j'][c']
+  uint64_t *full = reinterpret_cast<uint64_t *>(tmat + 2 * HBLK);
+  uint64_t *empty = full + 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, unit = blockIdx.y;
+  double *psi = psi_all + (size_t)unit * vstride, *pmn = pmn_all + (size_t)unit * vstride;
+  const double *hpsi = hpsi_all ? hpsi_all + (size_t)unit * vstride : nullptr;
+  if (tid == 0) {
+    for (int s = 0; s < 2; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], DM_CONSUMERS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // Mhat^T for the one or two matrices: Mhat = [[Mre, Mim],[-Mim, Mre]]; ORTHO multiplies by -A
+  for (int e = tid; e < 2 * HBLK; e += DM_THREADS) {
+    const int w = e / HBLK, r = e % HBLK, c = r / COLD, j = r % COLD;  // T[c'][j']
+    double v = 0.0;
+    if (w == 0 || MODE == RM_ROTATE) {
+      const double *m = (w == 0 ? m0 : m1) + (size_t)unit * mstride;
+      const double re = m[2 * ((j % NB) + NB * (c % NB))], im = m[2 * ((j % NB) + NB * (c % NB)) + 1];
+      v = (j < NB) == (c < NB) ? re : (j < NB ? im : -im);
+      if (MODE == RM_ORTHO) v = -v;
+    }
+    tmat[e] = v;
+  }
+  __syncthreads();
+  const int ntiles = (kk + DM_S - 1) / DM_S;
+  if (warp == DM_CONSUMERS) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int slot = it & 1;
+        mbar_wait(&empty[slot], ((it >> 1) & 1) ^ 1);
+        const int site0 = tile * DM_S, ns = min(DM_S, kk - site0);
+        const uint32_t bytes = (uint32_t)ns * BLKD * 8;
+        double *sm = tiles + (size_t)slot * 2 * RM_TILE_D;
+        if (MODE == RM_ORTHO) {
+          mbar_expect_tx(&full[slot], bytes);
+          bulk_g2s(sm, psi + (size_t)site0 * BLKD, bytes, &full[slot]);
+        } else {
+          mbar_expect_tx(&full[slot], 2 * bytes);
+          bulk_g2s(sm, pmn + (size_t)site0 * BLKD, bytes, &full[slot]);
+          bulk_g2s(sm + RM_TILE_D, psi + (size_t)site0 * BLKD, bytes, &full[slot]);
+        }
+      }
+    }
+    return;
+  }
+  if (warp == 3 || warp == 6)
+    rmul_consumer<MODE, 2>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane);
+  else
+    rmul_consumer<MODE, 1>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 static int dmma_configure() {
   cudaError_t e;
@@ -396,6 +599,8 @@ static int dmma_configure() {
   DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, true>))
 #undef DM_ATTR
   if ((e = cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES)) != cudaSuccess) return -3;
+  if ((e = cudaFuncSetAttribute(k_rmul_dmma<RM_ORTHO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES)) != cudaSuccess) return -3;
+  if ((e = cudaFuncSetAttribute(k_rmul_dmma<RM_ROTATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES)) != cudaSuccess) return -3;
   return 0;
 }
 
@@ -497,6 +702,19 @@ static int dmma_launch_gram(const double *X, size_t xstride, const double *Y, si
                             int nunits, int ctas, double *part, cudaStream_t st, long long *launches) {
   dim3 grid(ctas, nunits);
   k_gram_dmma<<<grid, GR_THREADS, GR_SMEM_BYTES, st>>>(X, Y, two, kk, xstride, ystride, part);
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+static int dmma_launch_rmul(int mode, double *psi, double *pmn, const double *hpsi, const double *m0, const double *m1,
+                            size_t mstride, int kk, size_t vstride, int nunits, int sms, cudaStream_t st,
+                            long long *launches) {
+  const int ntiles = (kk + DM_S - 1) / DM_S;
+  dim3 grid(std::max(1, std::min(ntiles, (sms + nunits - 1) / nunits)), nunits);
+  if (mode == RM_ORTHO)
+    k_rmul_dmma<RM_ORTHO><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride);
+  else
+    k_rmul_dmma<RM_ROTATE><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

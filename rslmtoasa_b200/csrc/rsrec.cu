@@ -404,15 +404,28 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
                                BLKD * sizeof(double), nunits, cudaMemcpyDeviceToDevice, h->st));
     // pmn -= psi A ; B2 = sum pmn^H pmn
     dim3 grid(nctas, nunits);
-    k_lz_ortho_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, hpsi, h->A.p, BLKD, h->kk, vstride(h), h->part.p);
-    h->last_parts = nctas;
+    if (h->family == 1) {
+      if (dmma_launch_rmul(RM_ORTHO, psi, pmn, hpsi, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches) != 0)
+        return fail(RSREC_ECUDA, std::string("k_rmul_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+      TRY(launch_gram(h, pmn, pmn, nunits, nctas, h->part.p));
+    } else {
+      k_lz_ortho_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, hpsi, h->A.p, BLKD, h->kk, vstride(h), h->part.p);
+      h->last_parts = nctas;
+      h->launches++;
+    }
     // B2 -> history slot ll+1, B, B^-1
     TRY(launch_reduce(h, nunits, nctas, 0, h->B2.p, nullptr, BLKD, nullptr, nullptr));
     k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->B2.p, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
                                          BLKD, diag ? 1 : 0);
+    h->launches++;
     // psi = pmn B^-1 ; pmn = psi_old B
-    k_lz_rotate_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->B.p, h->Bi.p, BLKD, h->kk, vstride(h));
-    h->launches += 3;
+    if (h->family == 1) {
+      if (dmma_launch_rmul(RM_ROTATE, psi, pmn, nullptr, h->Bi.p, h->B.p, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches) != 0)
+        return fail(RSREC_ECUDA, std::string("k_rmul_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    } else {
+      k_lz_rotate_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->B.p, h->Bi.p, BLKD, h->kk, vstride(h));
+      h->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
   }
   CUDA_TRY(cudaMemcpyAsync(a_host, h->ahist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double));
