@@ -209,3 +209,64 @@ def test_device_resident_stepping_matches_one_shot():
     mu = rec.cheb_end()
     assert np.array_equal(mu, rec.mu_n)
     assert rec.launch_count > 0
+
+
+# ---- BASELINE.json full sizes: size-independent properties (the oracle cannot run these in seconds) ----------
+def test_full_size_1M_sites_properties():
+    """config 5 (1M-site bcc, KPM random vector): mu_0 = kk/sqrtf(kk)^2 I exactly-ish, moments of a Hermitian H are
+    Hermitian, the stochastic trace of T_1 is small, and stepping in two chunks equals one shot (determinism)."""
+    from rslmtoasa_b200 import Recursion, Control, Energy, synthetic as S
+    lat = S.periodic_bcc(100, 100, 50)
+    assert lat.kk == 1_000_000
+    ham = S.make_hamiltonian(lat, seed=20260105)
+    ph = S.random_phases(lat.kk, 1, seed=20260105)
+    rec = Recursion(ham, lat, Control(lld=4), Energy(EMIN, EMAX), phases=ph)
+    rec.chebyshev_recur_random()
+    mu = rec.mu_n[..., 0]
+    nrm = float(np.sqrt(np.float32(lat.kk)))
+    assert relerr(mu[:, :, 0], np.eye(18) * lat.kk / nrm ** 2) < 1e-12
+    for k in range(mu.shape[2]):
+        assert np.abs(mu[:, :, k] - mu[:, :, k].conj().T).max() < 1e-10
+    assert np.abs(mu).max() < 1.5                     # |T_n| <= 1 inside the window
+    rec.cheb_begin_random(ph, 4)
+    rec.cheb_run_steps(1)
+    rec.cheb_run_steps(3)
+    assert np.array_equal(rec.cheb_end()[..., 0], mu)  # bit-reproducible run to run
+
+
+def test_kernel_families_agree_at_config1_size():
+    """config 1 (bulk bcc Fe, kk = 5984): tensor-pipe and SIMT families against each other at full size, plus
+    the invariants of the block recursion (B^2 Hermitian positive definite, A Hermitian, mu_0 = I)."""
+    from rslmtoasa_b200 import Recursion, Control, Energy, synthetic as S
+    lat = S.sphere_cluster("bcc", 80.0)
+    ham = S.make_hamiltonian(lat, seed=20260101)
+    out = []
+    for fam in (0, 1):
+        rec = Recursion(ham, lat, Control(lld=21), Energy(EMIN, EMAX))
+        rec.set_kernel_family(fam)
+        rec.recur_b()
+        rec.chebyshev_recur()
+        out.append((rec.a_b.copy(), rec.b2_b.copy(), rec.mu_n.copy()))
+    assert relerr(out[1][0], out[0][0]) < 1e-11 and relerr(out[1][1], out[0][1]) < 1e-11
+    assert relerr(out[1][2], out[0][2]) < 1e-12
+    a_b, b2_b, mu = out[1]
+    assert relerr(mu[:, :, 0, 0], np.eye(18)) < 1e-14
+    for ll in range(21):
+        assert relerr(b2_b[:, :, ll, 0], b2_b[:, :, ll, 0].conj().T) < 1e-12
+        assert np.linalg.eigvalsh(b2_b[:, :, ll, 0]).min() > 0
+        assert np.abs(a_b[:, :, ll, 0] - a_b[:, :, ll, 0].conj().T).max() < 1e-11
+
+
+def test_linearity_of_ham_vec_matmul_at_config4_size():
+    """config 4 lattice (kk = 8000 PBC): H~(x + c y) = H~ x + c H~ y, and <x|H y> = <H x|y> for the Hermitian H"""
+    from rslmtoasa_b200 import Recursion, Control, Energy, synthetic as S
+    lat = S.periodic_bcc(10, 20, 20)
+    ham = S.make_hamiltonian(lat, seed=20260104)
+    rec = Recursion(ham, lat, Control(), Energy(EMIN, EMAX))
+    rng = np.random.default_rng(11)
+    x = np.asfortranarray(rng.normal(size=(18, 18, lat.kk)) + 1j * rng.normal(size=(18, 18, lat.kk)))
+    y = np.asfortranarray(rng.normal(size=(18, 18, lat.kk)) + 1j * rng.normal(size=(18, 18, lat.kk)))
+    c = 0.3 - 0.7j
+    hx, hy, hxy = rec.ham_vec_matmul(x, 1.0, 0.0), rec.ham_vec_matmul(y, 1.0, 0.0), rec.ham_vec_matmul(x + c * y, 1.0, 0.0)
+    assert relerr(hxy, hx + c * hy) < 1e-13
+    assert abs(np.vdot(x, hy) - np.vdot(hx, y)) / abs(np.vdot(x, hy)) < 1e-12
