@@ -34,6 +34,7 @@ struct DmmaTiles {
   int32_t *d_sites = nullptr;  // [ntiles][8]      site ids (kk = null)
   int32_t *d_cls = nullptr;    // [ntiles]
   int32_t *d_nbr = nullptr;    // [ntiles][ng][8]  neighbour site ids per slot
+  std::vector<int32_t> h_sites;  // host copy of d_sites (for the active-region planner)
 };
 
 struct DmmaStages {  // stage list of one tile, in execution order (self stage last)
@@ -85,7 +86,9 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 template <int EPI, bool ADDEND, int XN>
 __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaStages &st,
                                               const int32_t *__restrict__ tile_sites, double *stages, uint64_t *full,
-                                              uint64_t *empty, int ntiles, int nunits, int warp, int lane) {
+                                              uint64_t *empty, int ntiles, int nunits,
+                                              const int32_t *__restrict__ order, const int32_t *__restrict__ cnt,
+                                              int warp, int lane) {
   const int g = lane >> 2, q = lane & 3;
   const int nst = st.n;
   const double inv_a = 1.0 / p.a;  // the epilogue multiplies by 1/a (<= 1 ulp from the reference's division)
@@ -105,7 +108,9 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
   uint32_t it = 0;
   for (int u = 0; u < nunits; u++) {
     const size_t uo = (size_t)u * p.vstride;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n_u = cnt ? cnt[u] : ntiles;
+    for (int ti = blockIdx.x; ti < n_u; ti += gridDim.x) {
+      const int tile = order ? order[(size_t)u * ntiles + ti] : ti;
       double acc[2][5][2], xacc[XN][2];
 #pragma unroll
       for (int i = 0; i < 2; i++)
@@ -212,7 +217,11 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
 template <int EPI, bool ADDEND>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_sites, const int32_t *__restrict__ tile_cls,
-             const int32_t *__restrict__ tile_nbr, int ntiles, int nunits) {
+             const int32_t *__restrict__ tile_nbr, int ntiles, int nunits, const int32_t *__restrict__ order,
+             const int32_t *__restrict__ cnt) {
+  // order/cnt (optional): per unit, the tiles reachable from the unit's start sites sorted by the step at which they
+  // are first reached, and how many of them are reachable at this step -- the reference's izero/irlist bookkeeping
+  // (recursion.f90:1629-1636): unreached tiles hold exact zeros and are skipped.
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stages = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)DM_STAGES * DM_STAGE_D * 8);
@@ -227,35 +236,35 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
 
   if (warp == DM_CONSUMERS) {
     // ===== producer warp: TMA bulk copies =====
-    // The (site index, class) of stage it+1 is fetched from global memory while the warp waits for the ring slot of
-    // stage `it`, so the index-load latency is off the critical path of the pipeline.
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t total = (uint32_t)nunits * (uint32_t)max(my_tiles, 0) * (uint32_t)nst;
-    auto fetch = [&](uint32_t i, int &site, int &cls, int &u) {
-      const uint32_t per_u = (uint32_t)my_tiles * nst;
-      u = i / per_u;
-      const uint32_t r = i - (uint32_t)u * per_u;
-      const int tile = blockIdx.x + (r / nst) * gridDim.x, j = r % nst;
+    // The (site index, class) of the next stage is fetched from global memory while the warp waits for the ring slot
+    // of the current one, so the index-load latency is off the critical path of the pipeline.
+    int cu = 0, ci = blockIdx.x, cj = 0;  // cursor: unit, position in the unit's tile list, stage
+    auto count = [&](int u) { return cnt ? cnt[u] : ntiles; };
+    auto settle = [&](int &u, int &i) { while (u < nunits && i >= count(u)) { u++; i = blockIdx.x; } };
+    auto fetch = [&](int u, int i, int j, int &site, int &cls) {
+      const int tile = order ? order[(size_t)u * ntiles + i] : i;
       cls = tile_cls[tile];
       const int m = st.slot[j];
       site = (lane < DM_S) ? ((m == 0) ? tile_sites[tile * DM_S + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + lane]) : 0;
     };
-    int site = 0, cls = 0, u = 0;
-    if (total > 0) fetch(0, site, cls, u);
-    for (uint32_t it = 0; it < total; it++) {
-      int nsite = 0, ncls = 0, nu = 0;
-      if (it + 1 < total) fetch(it + 1, nsite, ncls, nu);
-      const int slot = it % DM_STAGES, j = it % nst;
+    settle(cu, ci);
+    int site = 0, cls = 0;
+    if (cu < nunits) fetch(cu, ci, cj, site, cls);
+    for (uint32_t it = 0; cu < nunits; it++) {
+      int nu = cu, ni = ci, nj = cj + 1, nsite = 0, ncls = 0;
+      if (nj == nst) { nj = 0; ni += gridDim.x; settle(nu, ni); }
+      if (nu < nunits) fetch(nu, ni, nj, nsite, ncls);
+      const int slot = it % DM_STAGES;
       mbar_wait(&empty[slot], ((it / DM_STAGES) & 1) ^ 1);
       double *sm = stages + (size_t)slot * DM_STAGE_D;
       if (lane == 0) mbar_expect_tx(&full[slot], DM_STAGE_D * 8);
       __syncwarp();
       if (lane < DM_S) {
-        bulk_g2s(sm + HBLK + lane * BLKD, st.src[j] + (size_t)u * p.vstride + (size_t)site * BLKD, BLKD * 8, &full[slot]);
+        bulk_g2s(sm + HBLK + lane * BLKD, st.src[cj] + (size_t)cu * p.vstride + (size_t)site * BLKD, BLKD * 8, &full[slot]);
       } else if (lane == DM_S) {
-        bulk_g2s(sm, st.H[j] + (size_t)cls * st.hstride[j], HBLK * 8, &full[slot]);
+        bulk_g2s(sm, st.H[cj] + (size_t)cls * st.hstride[cj], HBLK * 8, &full[slot]);
       }
-      site = nsite; cls = ncls; u = nu;
+      cu = nu; ci = ni; cj = nj; site = nsite; cls = ncls;
     }
     return;
   }
@@ -266,9 +275,9 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
   // within one unit of each other (both keep the tensor pipe fed).
   //   m-tile 16: w0:n0  w1:n1  w2:n2  w3:n3,n4        m-tile 17: w4:n0  w5:n1  w6:n2,n3  w7:n4
   if (warp == 3 || warp == 6)
-    dmma_consumer<EPI, ADDEND, 2>(p, st, tile_sites, stages, full, empty, ntiles, nunits, warp, lane);
+    dmma_consumer<EPI, ADDEND, 2>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
   else
-    dmma_consumer<EPI, ADDEND, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, warp, lane);
+    dmma_consumer<EPI, ADDEND, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
 }
 
 // ---- Gram reductions on the tensor pipe -------------------------------------------------------------------------
@@ -645,6 +654,7 @@ static int dmma_build_tiles(DmmaTiles &t, const std::vector<int32_t> &nbr, const
   cudaMemcpy(t.d_cls, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(t.d_nbr, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice);
   t.ntiles = nt; t.ng = ng; t.kk = kk;
+  t.h_sites = hs;
   return 0;
 }
 
@@ -665,7 +675,8 @@ static bool dmma_supported(const ApplyParams &p) {
 static int dmma_grid(const DmmaTiles &t, int sms) { return std::max(1, std::min(t.ntiles, sms)); }
 static int dmma_gram_ctas(int kk, int sms) { return std::max(1, std::min(sms, (kk + GR_WARPS - 1) / GR_WARPS)); }
 
-static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, cudaStream_t st, long long *launches) {
+static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, cudaStream_t st, long long *launches,
+                             const int32_t *order = nullptr, const int32_t *cnt = nullptr) {
   DmmaStages sg;
   sg.n = 0;
   // neighbour slots of every term first, then the on-site slots, then the on-site extra term (self stage last)
@@ -685,7 +696,7 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
   }
   const int grid = dmma_grid(t, sms);
 #define DM_LAUNCH(E, A) \
-  k_apply_dmma<E, A><<<grid, DM_THREADS, DM_SMEM_BYTES, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr, t.ntiles, nunits)
+  k_apply_dmma<E, A><<<grid, DM_THREADS, DM_SMEM_BYTES, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr, t.ntiles, nunits, order, cnt)
   const bool ad = p.addend != nullptr;
   switch (p.epi) {
     case EPI_STORE: if (ad) DM_LAUNCH(EPI_STORE, true); else DM_LAUNCH(EPI_STORE, false); break;

@@ -61,6 +61,14 @@ struct rsrec_handle_s {
   int32_t *d_si = nullptr, *d_sj = nullptr;
   double *d_as = nullptr, *d_bs = nullptr;
   int units_cap = 0;
+  // active-region plan (the reference's izero/irlist): tiles reachable per step from the units' start sites
+  std::vector<int32_t> radj_off, radj;  // reverse adjacency of the neighbour table (who gathers from site a)
+  struct {
+    bool on = false;
+    int level = 0, maxlevel = 0, nunits = 0;
+    int32_t *d_order = nullptr, *d_counts = nullptr;
+    size_t order_cap = 0, counts_cap = 0;
+  } plan;
   // Chebyshev stepping session
   struct {
     bool active = false;
@@ -154,6 +162,16 @@ static int ensure_ready(H *h) {
   CUDA_TRY(cudaMemcpy(h->d_nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(h->d_cls, cls.data(), cls.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   h->h2d_bytes += (long long)((nbr.size() + cls.size()) * sizeof(int32_t));
+  {  // reverse adjacency (CSR): radj[a] = sites i that gather from a (i != a), for the breadth-first reach levels
+    h->radj_off.assign(kk + 1, 0);
+    for (int j = 1; j < ng; j++)
+      for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj_off[a + 1]++; }
+    for (int a = 0; a < kk; a++) h->radj_off[a + 1] += h->radj_off[a];
+    h->radj.resize(h->radj_off[kk]);
+    std::vector<int32_t> fill(h->radj_off.begin(), h->radj_off.end() - 1);
+    for (int j = 1; j < ng; j++)
+      for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj[fill[a]++] = i; }
+  }
 
   auto src_block = [&](const std::vector<cplx> &ty, const std::vector<cplx> &loc, int c, int m) -> const cplx * {
     if (c < h->ntype) return ty.data() + (size_t)BLKC * (m + (size_t)nslot * c);
@@ -246,6 +264,62 @@ static int unit_batch(H *h, int nunits, int nvec) {
 // ---- operator application: out = epilogue( H src ) for a unit batch ---------------------------------------
 enum OpKind { OP_HAM = 0, OP_SCALAR = 1, OP_VELO_A = 2, OP_VELO_B = 3 };
 
+// Active-region plan for site-started recursions.  level(site) = number of operator applications after which the
+// site can be non-zero (start sites: 0); a tile is processed by the k-th application iff its smallest level <= k.
+// This is exactly the set the reference tracks with izero/idum/irlist (recursion.f90:1604-1636); skipped tiles hold
+// exact zeros, so results are unchanged.
+static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *site_j) {
+  h->plan.on = false;
+  if (h->family != 1 || (size_t)nunits * h->kk > (size_t)64 << 20) return RSREC_OK;
+  const int kk = h->kk, nt = h->tiles.ntiles;
+  std::vector<int32_t> order((size_t)nunits * nt), level(kk), tl(nt), frontier, next;
+  std::vector<std::vector<int32_t>> cum(nunits);
+  int maxlevel = 0;
+  for (int u = 0; u < nunits; u++) {
+    std::fill(level.begin(), level.end(), INT32_MAX);
+    frontier.clear();
+    for (int s : {site_i[u] - 1, site_j ? site_j[u] - 1 : -1})
+      if (s >= 0 && level[s] != 0) { level[s] = 0; frontier.push_back(s); }
+    for (int L = 1; !frontier.empty(); L++) {
+      next.clear();
+      for (int a : frontier)
+        for (int e = h->radj_off[a]; e < h->radj_off[a + 1]; e++) {
+          const int i = h->radj[e];
+          if (level[i] == INT32_MAX) { level[i] = L; next.push_back(i); }
+        }
+      frontier.swap(next);
+    }
+    int ml = 0;
+    for (int t = 0; t < nt; t++) {
+      int m = INT32_MAX;
+      for (int k = 0; k < DM_S; k++) { const int s = h->tiles.h_sites[(size_t)t * DM_S + k]; if (s < kk) m = std::min(m, level[s]); }
+      tl[t] = m;
+      if (m != INT32_MAX) ml = std::max(ml, m);
+    }
+    maxlevel = std::max(maxlevel, ml);
+    // counting sort by level (stable: tile order inside a level is kept for L2 locality)
+    std::vector<int32_t> c(ml + 2, 0);
+    for (int t = 0; t < nt; t++) if (tl[t] != INT32_MAX) c[tl[t] + 1]++;
+    for (int L = 0; L <= ml; L++) c[L + 1] += c[L];
+    cum[u].assign(c.begin() + 1, c.end());  // cum[L] = tiles with level <= L
+    std::vector<int32_t> pos(c.begin(), c.end() - 1);
+    int32_t *o = order.data() + (size_t)u * nt;
+    for (int t = 0; t < nt; t++) if (tl[t] != INT32_MAX) o[pos[tl[t]]++] = t;
+  }
+  std::vector<int32_t> counts((size_t)(maxlevel + 1) * nunits);
+  for (int L = 0; L <= maxlevel; L++)
+    for (int u = 0; u < nunits; u++) counts[(size_t)L * nunits + u] = cum[u][std::min<size_t>(L, cum[u].size() - 1)];
+  auto &pl = h->plan;
+  if (pl.order_cap < order.size()) { if (pl.d_order) cudaFree(pl.d_order); CUDA_TRY(cudaMalloc(&pl.d_order, order.size() * 4)); pl.order_cap = order.size(); }
+  if (pl.counts_cap < counts.size()) { if (pl.d_counts) cudaFree(pl.d_counts); CUDA_TRY(cudaMalloc(&pl.d_counts, counts.size() * 4)); pl.counts_cap = counts.size(); }
+  CUDA_TRY(cudaMemcpyAsync(pl.d_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(pl.d_counts, counts.data(), counts.size() * 4, cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  h->h2d_bytes += (long long)((order.size() + counts.size()) * 4);
+  pl.on = true; pl.level = 0; pl.maxlevel = maxlevel; pl.nunits = nunits;
+  return RSREC_OK;
+}
+
 static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas);
 static int launch_apply(H *h, ApplyParams &p, int nunits, int nctas) {
   if (!h->profile) return launch_apply_inner(h, p, nunits, nctas);
@@ -263,7 +337,13 @@ static int launch_apply(H *h, ApplyParams &p, int nunits, int nctas) {
 }
 static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas) {
   if (h->family == 1 && dmma_supported(p)) {
-    if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches) != 0)
+    const int32_t *order = nullptr, *cnt = nullptr;
+    if (h->plan.on && h->plan.nunits == nunits) {  // this application reaches level+1
+      h->plan.level = std::min(h->plan.level + 1, h->plan.maxlevel);
+      order = h->plan.d_order;
+      cnt = h->plan.d_counts + (size_t)h->plan.level * nunits;
+    }
+    if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches, order, cnt) != 0)
       return fail(RSREC_ECUDA, std::string("k_apply_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->last_parts = 0;
     return RSREC_OK;
@@ -386,6 +466,8 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   TRY(dev_alloc(h->b2hist, (size_t)nunits * hs, false));
   TRY(zero_vec(h, psi, nunits));
   TRY(zero_vec(h, pmn, nunits));
+  if (hpsi) TRY(zero_vec(h, hpsi, nunits));  // tiles the active-region plan skips must read as zeros
+  if (tmp) TRY(zero_vec(h, tmp, nunits));
   CUDA_TRY(cudaMemsetAsync(h->ahist.p, 0, (size_t)nunits * hs * sizeof(double), h->st));
   CUDA_TRY(cudaMemsetAsync(h->b2hist.p, 0, (size_t)nunits * hs * sizeof(double), h->st));
   k_init_site_start<<<nunits, 32, 0, h->st>>>(psi, vstride(h), h->d_si, h->d_sj, h->d_as, h->d_bs, nunits);
@@ -555,6 +637,8 @@ int rsrec_destroy(rsrec_handle h) {
   dmma_free_tiles(h->tiles);
   if (h->d_nbr) cudaFree(h->d_nbr);
   if (h->d_cls) cudaFree(h->d_cls);
+  if (h->plan.d_order) cudaFree(h->plan.d_order);
+  if (h->plan.d_counts) cudaFree(h->plan.d_counts);
   if (h->d_si) { cudaFree(h->d_si); cudaFree(h->d_sj); cudaFree(h->d_as); cudaFree(h->d_bs); }
   for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaStreamDestroy(h->st);
@@ -616,6 +700,7 @@ int rsrec_lanczos_block(rsrec_handle h, int nunits, const int32_t *site_i, const
   for (int u0 = 0; u0 < nunits; u0 += ub) {
     const int n = std::min(ub, nunits - u0);
     TRY(upload_units(h, n, site_i + u0, site_j ? site_j + u0 : nullptr, asign ? asign + u0 : nullptr, bsign ? bsign + u0 : nullptr));
+    TRY(plan_build(h, n, site_i + u0, site_j ? site_j + u0 : nullptr));
     TRY(lanczos_batch(h, n, lld, false, (double *)(a_b + (size_t)u0 * lld * BLKC), (double *)(b2_b + (size_t)u0 * lld * BLKC)));
   }
   return RSREC_OK;
@@ -633,6 +718,7 @@ int rsrec_lanczos_scalar(rsrec_handle h, int nunits, const int32_t *sites, int l
   for (int u0 = 0; u0 < nunits; u0 += ub) {
     const int n = std::min(ub, nunits - u0);
     TRY(upload_units(h, n, sites + u0, nullptr, nullptr, nullptr));
+    TRY(plan_build(h, n, sites + u0, nullptr));
     TRY(lanczos_batch(h, n, lld, true, ah.data(), bh.data()));
     for (int u = 0; u < n; u++)
       for (int l = 0; l < NB; l++)
@@ -667,12 +753,14 @@ int rsrec_cheb_begin_sites(rsrec_handle h, int nunits, const int32_t *site_i, co
   TRY(ensure_ready(h));
   if (unit_batch(h, nunits, h->hoh ? 3 : 2) < nunits) return fail(RSREC_ENOMEM, "unit batch does not fit in device memory");
   TRY(upload_units(h, nunits, site_i, site_j, asign, bsign));
+  TRY(plan_build(h, nunits, site_i, site_j));
   TRY(cheb_begin_common(h, nunits, lld, a, b));
   double *p0, *p1;
   TRY(get_vec(h, 0, nunits, &p0));
   TRY(get_vec(h, 1, nunits, &p1));
   TRY(zero_vec(h, p0, nunits));
   TRY(zero_vec(h, p1, nunits));
+  if (h->hoh) { double *t2; TRY(get_vec(h, 2, nunits, &t2)); TRY(zero_vec(h, t2, nunits)); }
   k_init_site_start<<<nunits, 32, 0, h->st>>>(p0, vstride(h), h->d_si, h->d_sj, h->d_as, h->d_bs, nunits);
   h->launches++;
   return cheb_first_moments(h);
@@ -683,6 +771,7 @@ int rsrec_cheb_begin_random(rsrec_handle h, int nvec, const double *phases, int 
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
   if (unit_batch(h, nvec, h->hoh ? 3 : 2) < nvec) return fail(RSREC_ENOMEM, "vector batch does not fit in device memory");
+  h->plan.on = false;  // every site is active from the start
   TRY(cheb_begin_common(h, nvec, lld, a, b));
   double *p0, *p1;
   TRY(get_vec(h, 0, nvec, &p0));
@@ -771,6 +860,7 @@ int rsrec_ham_vec_matmul(rsrec_handle h, const cplx *psi_in, cplx *psi_out, doub
   TRY(get_vec(h, 1, 1, &vout));
   if (h->hoh) TRY(get_vec(h, 2, 1, &tmp));
   TRY(upload_vec(h, psi_in, vin));
+  h->plan.on = false;
   TRY(apply_op(h, OP_HAM, vin, vout, nullptr, tmp, EPI_HAM, a, b, 1, nctas_for(h, 1), nullptr));
   return download_vec(h, vout, psi_out);
 }
@@ -785,6 +875,7 @@ int rsrec_velo_vec_matmul(rsrec_handle h, int slot, const cplx *psi_in, cplx *ps
   TRY(get_vec(h, 1, 1, &vout));
   if (h->hoh) TRY(get_vec(h, 2, 1, &tmp));
   TRY(upload_vec(h, psi_in, vin));
+  h->plan.on = false;
   TRY(apply_op(h, slot == 'a' ? OP_VELO_A : OP_VELO_B, vin, vout, nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas_for(h, 1), nullptr));
   return download_vec(h, vout, psi_out);
 }
@@ -800,6 +891,7 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
   if (unit_batch(h, 1, M + 6) < 1) return fail(RSREC_ENOMEM, "left-vector storage does not fit in device memory");
+  h->plan.on = false;
   const int nctas = nctas_for(h, 1);
   // vecs: 0 psiref, 1 tmp(hoh), 2 v0, 3 v1, 4 right, 5 spare, 6.. left[m]
   double *psiref, *tmp, *v0, *v1, *right, *spare;
