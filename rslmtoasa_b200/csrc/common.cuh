@@ -44,6 +44,7 @@ struct ApplyParams {
   const double *in;        // the vector the epilogue calls "in" (psi1 / psi)
   const double *prev;      // EPI_CHEB: psi0;  EPI_HOP: pmn (== out)
   double *out;
+  double *out2;            // EPI_HOP (tensor pipeline): second output = H in (hpsi) next to out = H in - prev
   double a, b;
   int epi;
   double *part;            // gram partials [unit][cta][2][648] (EPI_CHEB: D1,D2; EPI_HOP: A,unused)

@@ -131,7 +131,7 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
       double2 pv[2][5], xpv[XN];  // prefetched `prev` (psi0) fragments
       for (int j = 0; j < nst; j++, it++) {
         const int slot = it % DM_STAGES;
-        if (EPI == EPI_CHEB_NOGRAM && j == nst - 1) {
+        if ((EPI == EPI_CHEB_NOGRAM || EPI == EPI_HOP) && j == nst - 1) {
           // issue the epilogue's global loads now; they land while the last stage is being computed
 #pragma unroll
           for (int i = 0; i < 2; i++)
@@ -192,6 +192,10 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
           const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + nt * 8 + 2 * q);
           v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
           if (EPI == EPI_CHEB_NOGRAM) { v0 = 2.0 * v0 - prev.x; v1 = 2.0 * v1 - prev.y; }
+        }
+        if (EPI == EPI_HOP) {  // hop_b: hpsi = H psi (kept for A = psi^H hpsi), pmn = hpsi - pmn (recursion.f90:1641)
+          *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
+          v0 -= prev.x; v1 -= prev.y;
         }
         *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
       };
@@ -397,7 +401,7 @@ k_gram_dmma(const double *__restrict__ X, const double *__restrict__ Y, int two,
 // with Xhat = [Xre | Xim] (18x36) and Mhat = [[Mre, Mim],[-Mim, Mre]] (36x36): M = 144 rows per 8-site tile (exact),
 // N = 36 -> 40, K = 36 -- the same 90-unit shape as one SpMV stage, with the tile read "transposed" from shared
 // memory.  These passes are HBM-bound (2.5 flop/B), so tiles are contiguous 41 kB TMA bulk copies, 2-stage ring.
-//   RM_ORTHO : pmn <- (hpsi - pmn) - psi*A            (hop_b 1641 + crecal_b 1927;  hpsi == nullptr: pmn - psi*A)
+//   RM_ORTHO : pmn <- pmn - psi*A                     (crecal_b 1927; pmn already holds hpsi - pmn_old from EPI_HOP)
 //   RM_ROTATE: psi <- pmn*Binv ; pmn <- psi_old*B     (crecal_b 1966-1967)
 enum RmulMode { RM_ORTHO = 0, RM_ROTATE = 1 };
 #define RM_TILE_D (DM_S * BLKD)                       // 5184 doubles = 41472 B
@@ -462,8 +466,11 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
     auto valid = [&](int i, int c) { return c < 2 * NB && site0 + rows[i] < kk; };
     double acc[2][5][2], xacc[2][2];
     if (MODE == RM_ORTHO) {
-      // prefetch the addends (hpsi - pmn) in the accumulator-fragment pattern while the tile lands
-      double ad[2][5][2], xad[2][2];
+      // tile 0 = psi, tile 1 = pmn (the addend, read from shared memory in the accumulator-fragment pattern)
+      mbar_wait(&full[slot], (it >> 1) & 1);
+      rmul_product<XN>(sm, tmat, aoff, koff, boff, xoff, acc, xacc);  // psi * (-A)
+      const double *ad = sm + RM_TILE_D;
+      auto sofs = [&](int i, int c) { return rows[i] * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
 #pragma unroll
       for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -471,21 +478,15 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
 #pragma unroll
           for (int e = 0; e < 2; e++) {
             const int c = nt * 8 + 2 * q + e;
-            double v = 0.0;
-            if (valid(i, c)) { const size_t o = gofs(i, c); v = hpsi ? hpsi[o] - pmn[o] : pmn[o]; }
-            ad[i][nt][e] = v;
+            if (valid(i, c)) acc[i][nt][e] += ad[sofs(i, c)];
           }
 #pragma unroll
       for (int x = 0; x < XN; x++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int c = xn[x] * 8 + 2 * q + e;
-          double v = 0.0;
-          if (valid(2, c)) { const size_t o = gofs(2, c); v = hpsi ? hpsi[o] - pmn[o] : pmn[o]; }
-          xad[x][e] = v;
+          if (valid(2, c)) xacc[x][e] += ad[sofs(2, c)];
         }
-      mbar_wait(&full[slot], (it >> 1) & 1);
-      rmul_product<XN>(sm, tmat, aoff, koff, boff, xoff, acc, xacc);  // psi * (-A)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[slot]);
 #pragma unroll
@@ -495,14 +496,14 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
 #pragma unroll
           for (int e = 0; e < 2; e++) {
             const int c = nt * 8 + 2 * q + e;
-            if (valid(i, c)) pmn[gofs(i, c)] = ad[i][nt][e] + acc[i][nt][e];
+            if (valid(i, c)) pmn[gofs(i, c)] = acc[i][nt][e];
           }
 #pragma unroll
       for (int x = 0; x < XN; x++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int c = xn[x] * 8 + 2 * q + e;
-          if (valid(2, c)) pmn[gofs(2, c)] = xad[x][e] + xacc[x][e];
+          if (valid(2, c)) pmn[gofs(2, c)] = xacc[x][e];
         }
     } else {
       mbar_wait(&full[slot], (it >> 1) & 1);
@@ -578,8 +579,9 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
         const uint32_t bytes = (uint32_t)ns * BLKD * 8;
         double *sm = tiles + (size_t)slot * 2 * RM_TILE_D;
         if (MODE == RM_ORTHO) {
-          mbar_expect_tx(&full[slot], bytes);
+          mbar_expect_tx(&full[slot], 2 * bytes);
           bulk_g2s(sm, psi + (size_t)site0 * BLKD, bytes, &full[slot]);
+          bulk_g2s(sm + RM_TILE_D, pmn + (size_t)site0 * BLKD, bytes, &full[slot]);
         } else {
           mbar_expect_tx(&full[slot], 2 * bytes);
           bulk_g2s(sm, pmn + (size_t)site0 * BLKD, bytes, &full[slot]);
@@ -606,6 +608,8 @@ static int dmma_configure() {
   DM_ATTR((k_apply_dmma<EPI_HAM, true>))
   DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, false>))
   DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, true>))
+  DM_ATTR((k_apply_dmma<EPI_HOP, false>))
+  DM_ATTR((k_apply_dmma<EPI_HOP, true>))
 #undef DM_ATTR
   if ((e = cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES)) != cudaSuccess) return -3;
   if ((e = cudaFuncSetAttribute(k_rmul_dmma<RM_ORTHO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES)) != cudaSuccess) return -3;
@@ -660,8 +664,8 @@ static int dmma_build_tiles(DmmaTiles &t, const std::vector<int32_t> &nbr, const
 
 // The epilogues that read `in` need its self blocks in the last pipeline stage.
 static bool dmma_supported(const ApplyParams &p) {
-  // EPI_CHEB / EPI_HOP carry reductions: the caller runs EPI_CHEB_NOGRAM / EPI_STORE + k_gram_dmma instead
-  if (p.epi == EPI_CHEB || p.epi == EPI_HOP) return false;
+  // EPI_CHEB carries reductions: the caller runs EPI_CHEB_NOGRAM + k_gram_dmma instead; EPI_HOP needs out2 (hpsi)
+  if (p.epi == EPI_CHEB || (p.epi == EPI_HOP && !p.out2)) return false;
   int nst = 0;
   for (int t = 0; t < p.ngterms; t++) nst += p.ngather - p.g[t].first_slot;
   if (p.Hx) nst++;
@@ -702,6 +706,7 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
     case EPI_STORE: if (ad) DM_LAUNCH(EPI_STORE, true); else DM_LAUNCH(EPI_STORE, false); break;
     case EPI_HAM: if (ad) DM_LAUNCH(EPI_HAM, true); else DM_LAUNCH(EPI_HAM, false); break;
     case EPI_CHEB_NOGRAM: if (ad) DM_LAUNCH(EPI_CHEB_NOGRAM, true); else DM_LAUNCH(EPI_CHEB_NOGRAM, false); break;
+    case EPI_HOP: if (ad) DM_LAUNCH(EPI_HOP, true); else DM_LAUNCH(EPI_HOP, false); break;
     default: return -1;
   }
 #undef DM_LAUNCH

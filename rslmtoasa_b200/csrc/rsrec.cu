@@ -43,6 +43,8 @@ struct rsrec_handle_s {
   cudaStream_t st = nullptr;
   long long launches = 0;
   int last_parts = 0;  // partial-sum slots per unit written by the last fused apply
+  double *out2 = nullptr;  // second output of the next EPI_HOP application (hpsi)
+  int sqrt_method = 1;     // B = (B^2)^1/2: 1 = Newton-Schulz with Jacobi fallback, 0 = Jacobi eigen-decomposition
   long long h2d_bytes = 0, d2h_bytes = 0;  // bytes moved over PCIe/C2C by this handle (bench.py's e2e accounting)
   bool profile = false;                    // record CUDA events around every gather-SpMV launch
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -363,6 +365,7 @@ static int apply_op(H *h, OpKind op, const double *in, double *out, const double
   memset(&p, 0, sizeof(p));
   p.kk = h->kk; p.nslot_h = h->nslot; p.ngather = h->ncols; p.vstride = vstride(h);
   p.nbr = h->d_nbr; p.cls = h->d_cls; p.in = in; p.prev = prev; p.out = out; p.a = a; p.b = b; p.epi = epi; p.part = part;
+  p.out2 = h->out2;
   const bool hoh = h->hoh && op != OP_SCALAR;
   if (!hoh) {
     const double *Hs = op == OP_HAM ? h->Hmain.p : op == OP_SCALAR ? h->Hscalar.p : op == OP_VELO_A ? h->Hva.p : h->Hvb.p;
@@ -373,7 +376,7 @@ static int apply_op(H *h, OpKind op, const double *in, double *out, const double
   // pass A: tmp = h * in  (first sweep of the hoh routines, e.g. recursion.f90:1455-1477)
   ApplyParams pa = p;
   pa.g[0] = GatherTerm{h->Hh.p, in, 0};
-  pa.ngterms = 1; pa.epi = EPI_STORE; pa.out = tmp; pa.part = nullptr; pa.prev = nullptr;
+  pa.ngterms = 1; pa.epi = EPI_STORE; pa.out = tmp; pa.out2 = nullptr; pa.part = nullptr; pa.prev = nullptr;
   TRY(launch_apply(h, pa, nunits, nctas));
   if (op == OP_HAM) {
     // pass B: acc = -(h o)*tmp + (e_nu + l.s)*in + tmp   (H = h - hoh + e_nu + l.s, recursion.f90:1543)
@@ -475,8 +478,10 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   h->launches += 2;
   for (int ll = 0; ll < lld - 1; ll++) {
     // hop_b / hop_b_hoh: pmn = H psi - pmn ; A = sum psi^H H psi
-    if (h->family == 1) {  // tensor-pipe SpMV stores H psi; A = sum psi^H (H psi) on the tensor pipe too
-      TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, hpsi, nullptr, tmp, EPI_STORE, 1.0, 0.0, nunits, nctas, nullptr));
+    if (h->family == 1) {  // tensor-pipe SpMV: hpsi = H psi, pmn = hpsi - pmn; A = sum psi^H hpsi on the tensor pipe too
+      h->out2 = hpsi;
+      TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, nullptr));
+      h->out2 = nullptr;
       TRY(launch_gram(h, psi, hpsi, nunits, nctas, h->part.p));
     } else {
       TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, h->part.p));
@@ -487,7 +492,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     // pmn -= psi A ; B2 = sum pmn^H pmn
     dim3 grid(nctas, nunits);
     if (h->family == 1) {
-      if (dmma_launch_rmul(RM_ORTHO, psi, pmn, hpsi, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches) != 0)
+      if (dmma_launch_rmul(RM_ORTHO, psi, pmn, nullptr, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches) != 0)
         return fail(RSREC_ECUDA, std::string("k_rmul_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       TRY(launch_gram(h, pmn, pmn, nunits, nctas, h->part.p));
     } else {
@@ -498,7 +503,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     // B2 -> history slot ll+1, B, B^-1
     TRY(launch_reduce(h, nunits, nctas, 0, h->B2.p, nullptr, BLKD, nullptr, nullptr));
     k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->B2.p, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
-                                         BLKD, diag ? 1 : 0);
+                                         BLKD, diag ? 1 : 0, h->sqrt_method);
     h->launches++;
     // psi = pmn B^-1 ; pmn = psi_old B
     if (h->family == 1) {
@@ -620,6 +625,7 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   h->dev = device; h->kk = kk; h->ncols = ncols; h->nslot = nslot; h->ntype = ntype; h->nmax = nmax;
   h->ncls = ntype + nmax; h->sms = prop.multiProcessorCount;
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
+  if (const char *f = getenv("RSREC_SQRT_METHOD")) h->sqrt_method = atoi(f);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   if (dmma_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
   *out = h;
