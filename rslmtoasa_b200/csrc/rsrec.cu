@@ -8,6 +8,7 @@
 #include "kernels_simt.cuh"
 #include "eig18.cuh"
 #include "kernels_dmma.cuh"
+#include "kernels_kubo.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -627,7 +628,7 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
   if (const char *f = getenv("RSREC_SQRT_METHOD")) h->sqrt_method = atoi(f);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  if (dmma_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
+  if (dmma_configure() != 0 || kubo_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
   *out = h;
   return RSREC_OK;
 }
@@ -896,20 +897,28 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
   if (nstart == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
-  if (unit_batch(h, 1, M + 6) < 1) return fail(RSREC_ENOMEM, "left-vector storage does not fit in device memory");
+  const bool gemm = h->family == 1;  // tensor pipeline: batched GEMM contraction (kernels_kubo.cuh)
+  const int M4 = gemm ? (M + KB_MB - 1) / KB_MB * KB_MB : M;
+  if (unit_batch(h, 1, M4 + 6 + (gemm ? KB_NR : 0)) < 1) return fail(RSREC_ENOMEM, "left-vector storage does not fit in device memory");
   h->plan.on = false;
   const int nctas = nctas_for(h, 1);
-  // vecs: 0 psiref, 1 tmp(hoh), 2 v0, 3 v1, 4 right, 5 spare, 6.. left[m]
+  // vecs: 0 psiref, 1 tmp(hoh), 2 v0, 3 v1, 4 right, 5 spare, 6 left[m] (batched), 7 ring of KB_NR right vectors
   double *psiref, *tmp, *v0, *v1, *right, *spare;
   TRY(get_vec(h, 0, 1, &psiref)); TRY(get_vec(h, 1, 1, &tmp)); TRY(get_vec(h, 2, 1, &v0));
   TRY(get_vec(h, 3, 1, &v1)); TRY(get_vec(h, 4, 1, &right)); TRY(get_vec(h, 5, 1, &spare));
   std::vector<double *> left(M);
-  double *leftbuf;  // the reference's left_vec(18,18,kk,cond_ll): one batched allocation, unit m = T_m|r>
-  TRY(get_vec(h, 6, M, &leftbuf));
+  double *leftbuf, *ring = nullptr;  // the reference's left_vec(18,18,kk,cond_ll): one batched allocation, unit m = T_m|r>
+  TRY(get_vec(h, 6, M4, &leftbuf));
   for (int m = 0; m < M; m++) left[m] = leftbuf + (size_t)m * vstride(h);
-  TRY(dev_alloc(h->part, part_doubles(h, M, nctas), false));
+  if (gemm) {
+    TRY(get_vec(h, 7, KB_NR, &ring));
+    TRY(zero_vec(h, ring, KB_NR));
+    if (M4 > M) TRY(zero_vec(h, leftbuf + (size_t)M * vstride(h), M4 - M));  // padding rows of the last left block
+    TRY(dev_alloc(h->part, kubo_part_doubles(M4 / KB_MB, h->kk, h->sms), false));
+  } else {
+    TRY(dev_alloc(h->part, part_doubles(h, M, nctas), false));
+  }
   TRY(dev_alloc(h->mu, (size_t)M * M * BLKD, false));
-  const int32_t one = 1;
   for (int s = 0; s < nstart; s++) {
     TRY(zero_vec(h, psiref, 1));
     if (start_kind == 0) {
@@ -921,7 +930,6 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
       k_init_random_start<<<h->sms * 4, 256, 0, h->st>>>(psiref, vstride(h), h->scratch.p, h->kk, 1);
     }
     h->launches++;
-    (void)one;
     // left chain: T_1 = start, T_2 = H~ T_1, T_m = 2 H~ T_{m-1} - T_{m-2}
     CUDA_TRY(cudaMemcpyAsync(left[0], psiref, vstride(h) * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
     if (M > 1) TRY(apply_op(h, OP_HAM, left[0], left[1], nullptr, tmp, EPI_HAM, a, b, 1, nctas, nullptr));
@@ -942,10 +950,19 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
         double *t = c0; c0 = c1; c1 = c2; c2 = t;
         cur = c1;
       }
-      TRY(apply_op(h, OP_VELO_A, cur, right, nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas, nullptr));
-      // mu_nm_stochastic(:,:,n,m,i) = sum_k left_vec(:,:,k,m)^H right_vec(:,:,k) for all m in one launch (1220-1228)
-      TRY(launch_gram_strided(h, leftbuf, vstride(h), right, 0, M, nctas, h->part.p));
-      TRY(launch_reduce(h, M, nctas, 0, h->mu.p + (size_t)n * BLKD, nullptr, (size_t)M * BLKD, nullptr, nullptr));
+      // mu_nm_stochastic(:,:,n,m,i) = sum_k left_vec(:,:,k,m)^H right_vec(:,:,k) for all m (1220-1228)
+      if (gemm) {
+        // right vectors are collected KB_NR at a time, then contracted against every left vector in one GEMM
+        TRY(apply_op(h, OP_VELO_A, cur, ring + (size_t)(n % KB_NR) * vstride(h), nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas, nullptr));
+        if (n % KB_NR == KB_NR - 1 || n == M - 1) {
+          if (kubo_launch(leftbuf, vstride(h), M, ring, vstride(h), h->kk, n - n % KB_NR, h->part.p, h->mu.p, h->sms, h->st, &h->launches) != 0)
+            return fail(RSREC_ECUDA, std::string("k_kubo_gemm launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+      } else {
+        TRY(apply_op(h, OP_VELO_A, cur, right, nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas, nullptr));
+        TRY(launch_gram_strided(h, leftbuf, vstride(h), right, 0, M, nctas, h->part.p));
+        TRY(launch_reduce(h, M, nctas, 0, h->mu.p + (size_t)n * BLKD, nullptr, (size_t)M * BLKD, nullptr, nullptr));
+      }
     }
     CUDA_TRY(cudaMemcpyAsync(mu_nm + (size_t)s * M * M * BLKC, h->mu.p, (size_t)M * M * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)M * M * BLKD * sizeof(double));
     CUDA_TRY(cudaStreamSynchronize(h->st));

@@ -164,12 +164,12 @@ def test_ham_and_velo_vec_matmul(oracle_mod, name):
         assert relerr(rec.velo_vec_matmul(slot, psi), ref) < 1e-12
 
 
-@pytest.mark.parametrize("kind", ["per_type", "random_vec"])
+@pytest.mark.parametrize("kind,M", [("per_type", 6), ("random_vec", 6), ("per_type", 1), ("random_vec", 9), ("random_vec", 4)])
 @pytest.mark.parametrize("name", ["pbc", "pbc_hoh"])
-def test_compute_moments_stochastic(oracle_mod, name, kind):
+def test_compute_moments_stochastic(oracle_mod, name, kind, M):
+    """M = 1, 4, 6, 9 cover full, partial and single left blocks / right batches of the GEMM contraction."""
     from rslmtoasa_b200 import synthetic as S
     lat, ham = case(name)
-    M = 6
     a, b = oracle_mod.cheb_scale(EMIN, EMAX)
     orc = oracle_mod.Oracle(lat, ham)
     if kind == "per_type":
