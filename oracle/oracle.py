@@ -20,8 +20,8 @@ c_vp = C.c_void_p
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "rsrec_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("rsrec_oracle.c", "rsrec_oracle_post.c", "rsrec_oracle.h")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "librsrec_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
@@ -177,3 +177,147 @@ def heev18(m):
 def cheb_scale(emin: float, emax: float):
     """a, b of `recursion.f90:3078-3079`."""
     return (emax - emin) / (2 - 0.3), (emax + emin) / 2
+
+
+# ---- consumers either side of the hot path (SURVEY.md 8f; rsrec_oracle_post.c) -----------------------------------
+def _post():
+    L = lib()
+    if not getattr(L, "_post_ready", False):
+        L.orc_emami.argtypes = [C.c_int, c_vp, c_vp, c_vp, c_vp]
+        L.orc_bpopt.argtypes = [C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.orc_get_terminf.argtypes = [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp]
+        L.orc_bgreen.argtypes = [c_vp, c_vp, C.c_int, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_double, C.c_double,
+                                 C.c_int, c_vp]
+        L.orc_block_green.argtypes = [c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, C.c_int, c_vp]
+        L.orc_jackson_kernel.argtypes = [C.c_int, c_vp]
+        L.orc_lorentz_kernel.argtypes = [C.c_int, C.c_double, c_vp]
+        L.orc_chebyshev_green.argtypes = [c_vp, C.c_int, C.c_int, c_vp, C.c_int, C.c_double, C.c_double, c_vp, c_vp]
+        L.orc_bprldos.argtypes = [C.c_double, c_vp, c_vp, C.c_int, c_vp]
+        L.orc_bprldos.restype = C.c_double
+        L.orc_density.argtypes = [c_vp, c_vp, C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp]
+        L.orc_sgreen.argtypes = [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp]
+        L.orc_gamma_nm.argtypes = [c_vp, C.c_int, C.c_int, C.c_double, C.c_double, c_vp]
+        L.orc_conductivity_integrand.argtypes = [c_vp, C.c_int, C.c_int, c_vp, C.c_int, C.c_double, C.c_double, C.c_int,
+                                                 c_vp, c_vp]
+        L._post_ready = True
+    return L
+
+
+def e_mesh(energy_min, energy_max, channels_ldos, fermi):
+    """energy%e_mesh (energy.f90:175-208) -> ene(channels_ldos+10) (channels_ldos made odd-compatible like the reference)."""
+    if channels_ldos % 2 != 0:
+        channels_ldos -= 1
+    edel = (energy_max - energy_min) / channels_ldos
+    edel = (fermi - energy_min) / np.rint((fermi - energy_min) / edel)
+    return energy_min + edel * np.arange(channels_ldos + 10, dtype=np.float64)
+
+
+def emami(a, b):
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    emax, emin = C.c_double(0), C.c_double(0)
+    _post().orc_emami(len(a), _p(a), _p(b), C.byref(emax), C.byref(emin))
+    return emax.value, emin.value
+
+
+def bpopt(a, rb):
+    a = np.ascontiguousarray(a, np.float64); rb = np.ascontiguousarray(rb, np.float64)
+    ainf, rbinf, ifail = C.c_double(0), C.c_double(0), C.c_int(0)
+    _post().orc_bpopt(len(a), _p(a), _p(rb), C.byref(ainf), C.byref(rbinf), C.byref(ifail))
+    return ainf.value, rbinf.value, ifail.value
+
+
+def get_terminf(a_b, b_b):
+    a_b = _f(a_b, np.complex128); b_b = _f(b_b, np.complex128)
+    ll, na = a_b.shape[2], a_b.shape[3]
+    a_inf = np.zeros((18, 18, na), order="F"); b_inf = np.zeros((18, 18, na), order="F")
+    a0 = np.zeros(na); b0 = np.zeros(na)
+    _post().orc_get_terminf(_p(a_b), _p(b_b), na, ll, _p(a_inf), _p(b_inf), _p(a0), _p(b0))
+    return a_inf, b_inf, a0, b0
+
+
+def bgreen(a_b, b_b, ene, a_inf, b_inf, eta=0.0, sym_term=False, ie_start=1, ie_len=None):
+    """one unit: a_b, b_b (18,18,ll); returns g_out (18,18,nv)."""
+    a_b = _f(a_b, np.complex128); b_b = _f(b_b, np.complex128)
+    ene = np.ascontiguousarray(ene, np.float64)
+    nv = len(ene)
+    g = np.zeros((18, 18, nv), np.complex128, order="F")
+    ai = _f(a_inf, np.float64); bi = _f(b_inf, np.float64)
+    _post().orc_bgreen(_p(a_b), _p(b_b), a_b.shape[2], _p(ene), nv, ie_start, nv if ie_len is None else ie_len, _p(ai),
+                       _p(bi), complex(eta).real, complex(eta).imag, int(sym_term), _p(g))
+    return g
+
+
+def block_green(a_b, b_b, ene, sym_term=False):
+    a_b = _f(a_b, np.complex128); b_b = _f(b_b, np.complex128)
+    ene = np.ascontiguousarray(ene, np.float64)
+    ll, na, nv = a_b.shape[2], a_b.shape[3], len(ene)
+    g0 = np.zeros((18, 18, nv, na), np.complex128, order="F")
+    _post().orc_block_green(_p(a_b), _p(b_b), na, ll, _p(ene), nv, int(sym_term), _p(g0))
+    return g0
+
+
+def jackson_kernel(n):
+    k = np.zeros(n)
+    _post().orc_jackson_kernel(n, _p(k))
+    return k
+
+
+def lorentz_kernel(n, lam):
+    k = np.zeros(n)
+    _post().orc_lorentz_kernel(n, lam, _p(k))
+    return k
+
+
+def chebyshev_green(mu_n, ene, energy_min, energy_max):
+    mu_n = _f(mu_n, np.complex128)
+    ene = np.ascontiguousarray(ene, np.float64)
+    nk, na, nv = mu_n.shape[2], mu_n.shape[3], len(ene)
+    mu_ng = np.zeros_like(mu_n, order="F")
+    g0 = np.zeros((18, 18, nv, na), np.complex128, order="F")
+    _post().orc_chebyshev_green(_p(mu_n), na, (nk - 2) // 2, _p(ene), nv, energy_min, energy_max, _p(mu_ng), _p(g0))
+    return mu_ng, g0
+
+
+def bprldos(e, a, b2, edges):
+    a = np.ascontiguousarray(a, np.float64); b2 = np.ascontiguousarray(b2, np.float64)
+    ed = np.ascontiguousarray(edges, np.float64)
+    return _post().orc_bprldos(e, _p(a), _p(b2), len(a), _p(ed))
+
+
+def density(a, b2, ene, dw_l, cshi):
+    """a, b2: (lld,18) of one (atom, direction); returns tdens (18,nv)."""
+    a = _f(a, np.float64); b2 = _f(b2, np.float64)
+    ene = np.ascontiguousarray(ene, np.float64)
+    dw = np.ascontiguousarray(dw_l, np.float64); cs = np.ascontiguousarray(cshi, np.float64)
+    td = np.zeros((18, len(ene)), order="F")
+    _post().orc_density(_p(a), _p(b2), a.shape[0], _p(ene), len(ene), _p(dw), _p(cs), _p(td))
+    return td
+
+
+def sgreen(a, b2, nmdir, ene, dw_l, cshi):
+    """a, b2: (lld,18,na,3) like recursion%a; dw_l, cshi: (18,na); returns g0 (18,18,nv,na)."""
+    a = _f(a, np.float64); b2 = _f(b2, np.float64)
+    ene = np.ascontiguousarray(ene, np.float64)
+    dw = _f(dw_l, np.float64); cs = _f(cshi, np.float64)
+    lld, na, nv = a.shape[0], a.shape[2], len(ene)
+    g0 = np.zeros((18, 18, nv, na), np.complex128, order="F")
+    _post().orc_sgreen(_p(a), _p(b2), lld, na, nmdir, _p(ene), nv, _p(dw), _p(cs), _p(g0))
+    return g0
+
+
+def gamma_nm(ene, M, energy_min, energy_max):
+    ene = np.ascontiguousarray(ene, np.float64)
+    g = np.zeros((len(ene), M, M), np.complex128, order="F")
+    _post().orc_gamma_nm(_p(ene), len(ene), M, energy_min, energy_max, _p(g))
+    return g
+
+
+def conductivity_integrand(mu_nm, ene, energy_min, energy_max, per_type):
+    mu = _f(mu_nm, np.complex128)
+    ene = np.ascontiguousarray(ene, np.float64)
+    M, nloop, nv = mu.shape[2], mu.shape[4], len(ene)
+    integ = np.zeros((18, nv), np.complex128, order="F")
+    integ_at = np.zeros((18, nv, nloop), np.complex128, order="F")
+    _post().orc_conductivity_integrand(_p(mu), M, nloop, _p(ene), nv, energy_min, energy_max, int(per_type), _p(integ),
+                                       _p(integ_at))
+    return integ, integ_at

@@ -67,6 +67,35 @@ int orc_heev18(orc_cplx *u, double *ev);
 /* number of active sites after the last hop (this%irnum) */
 int orc_last_irnum(const orc_ctx *c);
 
+
+/* ---- consumers either side of the hot path, rsrec_oracle_post.c -------------------------------- */
+/* emami / bpopt (recursion.f90:3589-3706 / 3540-3581) with 0-based arrays: as, bs (n); a, rb (ll), n = ll-1 */
+void orc_emami(int n, const double *as, const double *bs, double *emax, double *emin);
+void orc_bpopt(int ll, const double *a, const double *rb, double *ainf, double *rbinf, int *ifail);
+/* get_terminf (recursion.f90:2092-2138): a_b, b_b (18,18,ll,na) -> a_inf, b_inf (18,18,na), a_inf0, b_inf0 (na) */
+void orc_get_terminf(const orc_cplx *a_b, const orc_cplx *b_b, int na, int ll, double *a_inf, double *b_inf,
+                     double *a_inf0, double *b_inf0);
+/* bgreen (green.f90:1191-1339) for one unit; block_green (588-621) for na units, eta = 0, all channels */
+void orc_bgreen(const orc_cplx *a_b, const orc_cplx *b_b, int ll, const double *e, int nv, int ie_start, int ie_len,
+                const double *a_inf, const double *b_inf, double eta_re, double eta_im, int sym_term, orc_cplx *g_out);
+void orc_block_green(const orc_cplx *a_b, const orc_cplx *b_b, int na, int ll, const double *e, int nv, int sym_term,
+                     orc_cplx *g0);
+void orc_jackson_kernel(int n, double *k);
+void orc_lorentz_kernel(int n, double lambda, double *k);
+/* chebyshev_green (green.f90:1030-1108) */
+void orc_chebyshev_green(const orc_cplx *mu_n, int na, int lld, const double *ene, int nv, double energy_min,
+                         double energy_max, orc_cplx *mu_ng, orc_cplx *g0);
+/* bprldos / density (density_of_states.f90:378-407 / 248-372), sgreen (green.f90:628-705) */
+double orc_bprldos(double e, const double *a, const double *b2, int ll, const double *ei);
+void orc_density(const double *a, const double *b2, int lld, const double *ene, int nv, const double *dw_l,
+                 const double *cshi, double *tdens);
+void orc_sgreen(const double *a, const double *b2, int lld, int na, int nmdir, const double *ene, int nv,
+                const double *dw_l, const double *cshi, orc_cplx *g0);
+/* calculate_gamma_nm / integrand of calculate_conductivity_tensor (conductivity.f90:158-306) */
+void orc_gamma_nm(const double *ene, int nv, int M, double energy_min, double energy_max, orc_cplx *gamma);
+void orc_conductivity_integrand(const orc_cplx *mu_nm, int M, int nloop, const double *ene, int nv, double energy_min,
+                                double energy_max, int per_type, orc_cplx *integrand, orc_cplx *integrand_at);
+
 #ifdef __cplusplus
 }
 #endif

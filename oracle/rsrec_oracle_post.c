@@ -1,0 +1,466 @@
+/*
+ * rsrec_oracle_post.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE) for the consumers either side of the
+ * recursion hot path.  See rsrec_oracle.h.
+ *
+ * PARITY UNPINNED by reference fixtures (the reference pins only end-to-end etot/DOS files and cannot be compiled
+ * here); pinned by the independent numpy restatement in oracle/dense_check.py and by invariants in tests/.
+ *
+ * Restates, statement for statement:
+ *   emami               recursion.f90:3589-3706      bpopt               recursion.f90:3540-3581
+ *   get_cinf            recursion.f90:2030-2086      get_terminf         recursion.f90:2092-2138
+ *   bgreen              green.f90:1191-1339          block_green         green.f90:588-621
+ *   chebyshev_green     green.f90:1030-1108          jackson_kernel      math.f90:1641-1655
+ *   density / bprldos   density_of_states.f90:248-372 / 378-407          sgreen   green.f90:628-705
+ *   calculate_gamma_nm / calculate_conductivity_tensor (integrand)  conductivity.f90:158-306, lorentz_kernel math.f90:1663-1677
+ * LAPACK zgetrf/zgetri of bgreen are restated as LU with partial pivoting (izamax's |re|+|im| pivot rule) followed
+ * by column-wise triangular solves.
+ *
+ * This file is compiled with -ffp-contract=off: the terminator bisection (emami/bpopt) is branchy and its decisions
+ * must not depend on FMA contraction, so that the CUDA kernel (which uses explicit round-to-nearest mul/add/div) can
+ * be compared bit for bit.
+ */
+#include "rsrec_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define NB 18
+#define BLK (NB * NB)
+typedef orc_cplx cplx;
+static const double PI_RP = 3.14159265358979323846; /* math.f90:70 */
+
+/* ---- emami (recursion.f90:3589-3706): max/min eigenvalue of a symmetric tridiagonal by bisection ------------ */
+/* as, bs: 1-based arrays of length nl (index 0 unused).  Early `goto 1000` returns the bisection state as is. */
+static void emami(int nl, const double *as, const double *bs, int n, double *emax_o, double *emin_o) {
+  double a[nl + 2], b[nl + 2];
+  double emax0 = -1.0e6, emin0 = +1.0e6, emax, emin, e = 0.0, e1, e2, p, dele, x1, x2;
+  const double relfeh = ldexp(1.0, -39), eps = 1.0e-6;
+  int i, istop, num;
+  for (i = 1; i <= n; i++) { a[i] = as[i]; b[i] = bs[i]; }
+  b[1] = 0.0;
+  b[n + 1] = 0.0;
+  for (i = 1; i <= n; i++) {
+    x1 = a[i] + fabs(b[i]) + fabs(b[i + 1]);
+    x2 = a[i] - fabs(b[i]) - fabs(b[i + 1]);
+    if (emax0 <= x1) emax0 = x1;
+    if (emin0 > x2) emin0 = x2;
+  }
+  /* EMAX */
+  istop = 0; emax = emax0; emin = emin0;
+  for (;;) {
+    e = (emax + emin) / 2.0;
+    istop++;
+    if (istop > 50) { *emax_o = emax; *emin_o = emin; return; }
+    num = 0;
+    p = a[1] - e;
+    if (p < 0.0) num++;
+    for (i = 2; i <= n; i++) {
+      if (p == 0.0) p = (a[i] - e) - fabs(b[i]) / relfeh;
+      else p = (a[i] - e) - (b[i] * b[i]) / p;
+      if (p < 0.0) num++;
+    }
+    if (num == n) emax = e;
+    if (num < n) emin = e;
+    dele = fabs((emax - emin) / ((emax + emin) / 2.0));
+    if (dele <= eps) break;
+  }
+  e1 = e;
+  /* EMIN */
+  istop = 0; emax = e1; emin = emin0;
+  for (;;) {
+    e = (emax + emin) / 2.0;
+    istop++;
+    if (istop > 50) { *emax_o = emax; *emin_o = emin; return; }
+    num = 0;
+    p = a[1] - e;
+    if (p < 0.0) num++;
+    for (i = 2; i <= n; i++) {
+      if (p == 0.0) p = (a[i] - e) - fabs(b[i]) / relfeh;
+      else p = (a[i] - e) - (b[i] * b[i]) / p;
+      if (p < 0.0) num++;
+    }
+    if (num == 0) emin = e;
+    if (num > 0) emax = e;
+    dele = fabs((emax - emin) / ((emax + emin) / 2.0));
+    if (dele <= eps) break;
+  }
+  e2 = e;
+  *emax_o = e1;
+  *emin_o = e2;
+}
+
+/* ---- bpopt (recursion.f90:3540-3581): Beer-Pettifor terminator.  a, rb: 1-based, length ll --------------------- */
+static void bpopt(int ll, const double *a, const double *rb, int n, double *ainf_o, double *rbinf_o, int *ifail) {
+  double az[ll + 2], rbz[ll + 2];
+  double ainf, bm, bmax = 0.0, bmin = 0.0;
+  const double eps = 1.0e-05;
+  int i, jiter = 0;
+  memset(az, 0, sizeof(az));
+  memset(rbz, 0, sizeof(rbz)); /* RBZ(1) is never set by the reference; emami overwrites B(1) with 0 */
+  *ifail = 0;
+  ainf = a[n];
+  for (;;) {
+    jiter++;
+    az[1] = 0.5 * (a[1] - ainf);
+    for (i = 2; i <= n - 1; i++) {
+      az[i] = 0.5 * (a[i] - ainf);
+      rbz[i] = 0.5 * rb[i];
+    }
+    az[n] = a[n] - ainf;
+    rbz[n] = 1.0 / sqrt(2.0) * rb[n];
+    emami(ll, az, rbz, n, &bmax, &bmin);
+    bm = bmax + bmin;
+    bm = fabs(bm);
+    ainf = ainf + (bmax + bmin);
+    if (bm <= eps) break;
+    else if (jiter > 300) { *ifail = 1; break; }
+  }
+  *ainf_o = ainf;
+  *rbinf_o = (bmax - bmin) / 2.0;
+}
+
+/* for tests: the two primitives with 0-based C arrays */
+void orc_emami(int n, const double *as, const double *bs, double *emax, double *emin) {
+  double a[n + 3], b[n + 3];
+  for (int i = 1; i <= n; i++) { a[i] = as[i - 1]; b[i] = bs[i - 1]; }
+  emami(n + 1, a, b, n, emax, emin);
+}
+void orc_bpopt(int ll, const double *a0, const double *rb0, double *ainf, double *rbinf, int *ifail) {
+  double a[ll + 2], rb[ll + 2];
+  for (int i = 1; i <= ll; i++) { a[i] = a0[i - 1]; rb[i] = rb0[i - 1]; }
+  bpopt(ll, a, rb, ll - 1, ainf, rbinf, ifail);
+}
+
+/* ---- get_terminf (recursion.f90:2092-2138) with get_cinf (2030-2086) inlined -----------------------------------
+ * a_b, b_b: (18,18,ll,na) complex (b_b after zsqr, as block_green passes it); a_inf, b_inf: (18,18,na) real;
+ * a_inf0, b_inf0: (na). */
+void orc_get_terminf(const cplx *a_b, const cplx *b_b, int na, int ll, double *a_inf, double *b_inf, double *a_inf0,
+                     double *b_inf0) {
+  double aa[ll + 2], bb[ll + 2];
+  for (int n = 0; n < na; n++) {
+    double *ai = a_inf + (size_t)BLK * n, *bi = b_inf + (size_t)BLK * n;
+    for (int nl = 0; nl < BLK; nl++) { /* get_cinf: alpha(nl,l) = Acoef_r(i,j,l), nl = i + 18 (j-1) */
+      int ifail;
+      for (int l = 1; l <= ll; l++) {
+        aa[l] = creal(a_b[nl + (size_t)BLK * ((l - 1) + (size_t)ll * n)]);
+        bb[l] = creal(b_b[nl + (size_t)BLK * ((l - 1) + (size_t)ll * n)]);
+      }
+      bpopt(ll, aa, bb, ll - 1, &ai[nl], &bi[nl], &ifail);
+    }
+    for (int j = 0; j < NB; j++) {
+      for (int i = 0; i < NB; i++) {
+        if (isnan(ai[i + NB * j])) ai[i + NB * j] = 0.0;
+        if (isnan(bi[i + NB * j])) bi[i + NB * j] = 0.0;
+      }
+      if (ai[j + NB * j] == 0.0) ai[j + NB * j] = 0.5;
+      if (bi[j + NB * j] == 0.0) bi[j + NB * j] = 0.5;
+    }
+    a_inf0[n] = 0.0;
+    for (int i = 0; i < NB; i++) a_inf0[n] = a_inf0[n] + ai[i + NB * i];
+    a_inf0[n] = a_inf0[n] / NB;
+    bi[0 + NB * 0] = bi[0 + NB * 0] * 1.01;
+    bi[9 + NB * 9] = bi[9 + NB * 9] * 1.01;
+    b_inf0[n] = 0.0;
+    for (int i = 0; i < NB; i++) b_inf0[n] = b_inf0[n] + bi[i + NB * i];
+    b_inf0[n] = b_inf0[n] / NB;
+  }
+}
+
+/* ---- 18x18 complex inverse: zgetrf + zgetri semantics (partial pivoting, |re|+|im| pivot rule) ------------------ */
+static double cabs1(cplx z) { return fabs(creal(z)) + fabs(cimag(z)); }
+static int inv18(cplx *A /* column-major, in place */) {
+  int piv[NB];
+  cplx lu[BLK], x[NB];
+  memcpy(lu, A, sizeof(lu));
+  for (int k = 0; k < NB; k++) {
+    int p = k;
+    double best = cabs1(lu[k + NB * k]);
+    for (int i = k + 1; i < NB; i++)
+      if (cabs1(lu[i + NB * k]) > best) { best = cabs1(lu[i + NB * k]); p = i; }
+    piv[k] = p;
+    if (best == 0.0) return k + 1;
+    if (p != k)
+      for (int j = 0; j < NB; j++) { cplx t = lu[k + NB * j]; lu[k + NB * j] = lu[p + NB * j]; lu[p + NB * j] = t; }
+    const cplx r = 1.0 / lu[k + NB * k];
+    for (int i = k + 1; i < NB; i++) lu[i + NB * k] *= r;
+    for (int j = k + 1; j < NB; j++) {
+      const cplx u = lu[k + NB * j];
+      for (int i = k + 1; i < NB; i++) lu[i + NB * j] -= lu[i + NB * k] * u;
+    }
+  }
+  for (int c = 0; c < NB; c++) { /* solve A x = e_c:  P A = L U */
+    for (int i = 0; i < NB; i++) x[i] = (i == c) ? 1.0 : 0.0;
+    for (int k = 0; k < NB; k++) { cplx t = x[k]; x[k] = x[piv[k]]; x[piv[k]] = t; }
+    for (int i = 0; i < NB; i++)
+      for (int k = 0; k < i; k++) x[i] -= lu[i + NB * k] * x[k];
+    for (int i = NB - 1; i >= 0; i--) {
+      for (int k = i + 1; k < NB; k++) x[i] -= lu[i + NB * k] * x[k];
+      x[i] /= lu[i + NB * i];
+    }
+    for (int i = 0; i < NB; i++) A[i + NB * c] = x[i];
+  }
+  return 0;
+}
+
+/* ---- bgreen (green.f90:1191-1339) for one unit --------------------------------------------------------------
+ * a_b, b_b: (18,18,ll) of the unit (b_b = B after zsqr); e: energy mesh (nv); g_out: (18,18,nv), zeroed first, only
+ * channels ie_start..ie_start+ie_len-1 (1-based) are filled; a_inf, b_inf: (18,18) real. */
+void orc_bgreen(const cplx *a_b, const cplx *b_b, int ll, const double *e, int nv, int ie_start, int ie_len,
+                const double *a_inf, const double *b_inf, double eta_re, double eta_im, int sym_term, cplx *g_out) {
+  const cplx eta = eta_re + I * eta_im;
+  const int llinf = ll;
+  const double a_diag = (a_inf[0] + a_inf[9 + NB * 9]) * 0.5, b_diag = (b_inf[0] + b_inf[9 + NB * 9]) * 0.5;
+  memset(g_out, 0, sizeof(cplx) * BLK * (size_t)nv);
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int ei = ie_start; ei <= ie_start + ie_len - 1; ei++) {
+    cplx Q[BLK], W[BLK], B2z[BLK], T[BLK];
+    const double en = e[ei - 1];
+    for (int i = 0; i < BLK; i++) Q[i] = 0.0;
+    if (sym_term) {
+      for (int i = 0; i < NB; i++) {
+        const double etop = a_diag + 2.0 * b_diag, ebot = a_diag - 2.0 * b_diag;
+        const double ea = en - etop, eb = en - ebot;
+        const cplx det = ea * eb;
+        const cplx zoff = csqrt(det);
+        Q[i + NB * i] = (en + eta - a_diag - zoff) * 0.5;
+      }
+    } else {
+      for (int i = 0; i < NB; i++) {
+        double etop, ebot;
+        if (i == 0 || i == 9) {
+          etop = a_inf[i + NB * i] + 2 * b_inf[i + NB * i] * 1.025;
+          ebot = a_inf[i + NB * i] - 2 * b_inf[i + NB * i] * 1.025;
+        } else {
+          etop = a_inf[i + NB * i] + 2 * b_inf[i + NB * i];
+          ebot = a_inf[i + NB * i] - 2 * b_inf[i + NB * i];
+        }
+        const double ea = en - etop, eb = en - ebot;
+        const cplx det = ea * eb;
+        const cplx zoff = csqrt(det);
+        Q[i + NB * i] = ((en + eta) - a_inf[i + NB * i] - creal(zoff) - cimag(zoff) * I) * 0.5;
+      }
+    }
+    for (int l = llinf - 1; l >= 1; l--) {
+      const int ln = l < ll ? l : ll;
+      const cplx *A = a_b + (size_t)BLK * (ln - 1), *B = b_b + (size_t)BLK * (ln - 1);
+      for (int j = 0; j < NB; j++)
+        for (int i = 0; i < NB; i++) {
+          /* P = Z + eta where real(Z) /= 0, Z = e*one; the `abs(Q) < 10**(-12)` test of the reference is integer
+           * exponentiation (= 0) and never true */
+          const double z = (i == j) ? en : 0.0;
+          const cplx P = (z != 0.0) ? (z + eta) : (cplx)z;
+          Q[i + NB * j] = P - A[i + NB * j] - Q[i + NB * j];
+          B2z[i + NB * j] = B[i + NB * j];
+        }
+      inv18(Q);
+      for (int j = 0; j < NB; j++) /* W = Q B2z */
+        for (int i = 0; i < NB; i++) {
+          cplx s = 0.0;
+          for (int k = 0; k < NB; k++) s += Q[i + NB * k] * B2z[k + NB * j];
+          W[i + NB * j] = s;
+        }
+      for (int j = 0; j < NB; j++) /* Q = B2z^H W */
+        for (int i = 0; i < NB; i++) {
+          cplx s = 0.0;
+          for (int k = 0; k < NB; k++) s += conj(B2z[k + NB * i]) * W[k + NB * j];
+          T[i + NB * j] = s;
+        }
+      memcpy(Q, T, sizeof(Q));
+    }
+    for (int i = 0; i < BLK; i++) g_out[i + (size_t)BLK * (ei - 1)] += Q[i];
+  }
+}
+
+/* block_green (green.f90:588-621): get_terminf + bgreen over all channels with eta = 0, for na units.
+ * g0: (18,18,nv,na). */
+void orc_block_green(const cplx *a_b, const cplx *b_b, int na, int ll, const double *e, int nv, int sym_term,
+                     cplx *g0) {
+  double *a_inf = malloc(sizeof(double) * BLK * na), *b_inf = malloc(sizeof(double) * BLK * na);
+  double *a0 = malloc(sizeof(double) * na), *b0 = malloc(sizeof(double) * na);
+  orc_get_terminf(a_b, b_b, na, ll, a_inf, b_inf, a0, b0);
+  for (int n = 0; n < na; n++)
+    orc_bgreen(a_b + (size_t)BLK * ll * n, b_b + (size_t)BLK * ll * n, ll, e, nv, 1, nv, a_inf + (size_t)BLK * n,
+               b_inf + (size_t)BLK * n, 0.0, 0.0, sym_term, g0 + (size_t)BLK * nv * n);
+  free(a_inf); free(b_inf); free(a0); free(b0);
+}
+
+/* ---- jackson_kernel (math.f90:1641-1655) --------------------------------------------------------------------- */
+void orc_jackson_kernel(int n, double *k) {
+  const float bign = (float)n; /* real(bign): default (single) real, exact for these sizes */
+  for (int ll = 1; ll <= n; ll++) {
+    const double theta = PI_RP * ((float)ll - 1.0f) / (bign + 1.0f);
+    k[ll - 1] = (double)(bign - ((float)ll - 1.0f) + 1.0f) * cos(theta) + sin(theta) / tan(PI_RP / (bign + 1.0f));
+    k[ll - 1] = k[ll - 1] / (bign + 1.0f);
+  }
+}
+/* ---- lorentz_kernel (math.f90:1663-1677): theta's quotient is SINGLE precision in the reference ---------------- */
+void orc_lorentz_kernel(int n, double lambda, double *k) {
+  for (int ll = 1; ll <= n; ll++) {
+    const float q = ((float)ll - 1.0f) / (float)n;
+    const float s = 1.0f - q;
+    const double theta = lambda * (double)s;
+    k[ll - 1] = sinh(theta) / sinh(lambda);
+  }
+}
+
+/* ---- chebyshev_green (green.f90:1030-1108) ---------------------------------------------------------------------
+ * mu_n: (18,18,2lld+2,na); outputs mu_ng (same shape, kernel-weighted) and g0 (18,18,nv,na). */
+void orc_chebyshev_green(const cplx *mu_n, int na, int lld, const double *ene, int nv, double energy_min,
+                         double energy_max, cplx *mu_ng, cplx *g0) {
+  const int nk = 2 * lld + 2;
+  const double a = (energy_max - energy_min) / (2 - 0.3), b = (energy_max + energy_min) / 2;
+  double *kernel = malloc(sizeof(double) * nk);
+  orc_jackson_kernel(nk, kernel);
+  memset(g0, 0, sizeof(cplx) * BLK * (size_t)nv * na);
+  for (int n = 0; n < na; n++) {
+    const cplx *mu = mu_n + (size_t)BLK * nk * n;
+    cplx *mg = mu_ng + (size_t)BLK * nk * n;
+    for (int i = 0; i < nk; i++)
+      for (int lm = 0; lm < BLK; lm++) mg[lm + (size_t)BLK * i] = mu[lm + (size_t)BLK * i] * kernel[i];
+    for (int i = 1; i < nk; i++)
+      for (int lm = 0; lm < BLK; lm++) mg[lm + (size_t)BLK * i] = mg[lm + (size_t)BLK * i] * 2.0;
+#pragma omp parallel for
+    for (int ie = 0; ie < nv; ie++) {
+      cplx *g = g0 + (size_t)BLK * (ie + (size_t)nv * n);
+      const double w = (ene[ie] - b) / a;
+      for (int i = 1; i <= nk; i++) {
+        const cplx exp_factor = -I * cexp(-I * (double)(i - 1) * acos(w));
+        for (int lm = 0; lm < BLK; lm++) g[lm] = g[lm] + mg[lm + (size_t)BLK * (i - 1)] * exp_factor;
+      }
+      const double den = sqrt((a * a) - ((ene[ie] - b) * (ene[ie] - b)));
+      for (int lm = 0; lm < BLK; lm++) g[lm] = g[lm] / den;
+    }
+  }
+  free(kernel);
+}
+
+/* ---- bprldos (density_of_states.f90:378-407).  a, b2: 0-based arrays of length ll ----------------------------- */
+double orc_bprldos(double e, const double *a, const double *b2, int ll, const double *ei) {
+  const cplx ebot = ei[0], etop = ei[1];
+  const cplx emid = 0.5 * (etop + ebot);
+  const cplx ea = e - etop, eb = e - ebot;
+  const cplx det = ea * eb;
+  const cplx zoff = csqrt(det);
+  cplx Qt = (e - emid - zoff) * 0.5;
+  if (cimag(Qt) > 0.0) Qt = (e - emid + zoff) * 0.5;
+  for (int l = ll - 1; l >= 1; l--) Qt = b2[l - 1] / (e - a[l - 1] - Qt);
+  return -cimag(Qt) / PI_RP;
+}
+
+/* ---- density (density_of_states.f90:248-372) for one (atom, direction) -----------------------------------------
+ * a, b2: (lld,18) = recursion%a(:, :, ia, mdir), recursion%b2(:, :, ia, mdir); dw_l, cshi: (18) potential
+ * parameters of the atom; tdens: (18,nv). */
+void orc_density(const double *a, const double *b2, int lld, const double *ene, int nv, const double *dw_l,
+                 const double *cshi, double *tdens) {
+  double aa[lld + 2], sqbb[lld + 2], edge[NB], width[NB];
+  for (int nl = 0; nl < NB; nl++) {
+    double am1, bm1;
+    int ifail;
+    for (int l = 1; l <= lld; l++) {
+      aa[l] = a[(l - 1) + (size_t)lld * nl];
+      sqbb[l] = sqrt(b2[(l - 1) + (size_t)lld * nl]);
+    }
+    bpopt(lld, aa, sqbb, lld - 1, &am1, &bm1, &ifail);
+    if (nl == 0 || nl == 9) bm1 = 1.01 * bm1;
+    edge[nl] = am1 - 2.0 * bm1;
+    width[nl] = 4.0 * bm1;
+  }
+  for (int eidx = 0; eidx < nv; eidx++)
+    for (int nl = 0; nl < NB; nl++) {
+      const double e_shift = ene[eidx] / dw_l[nl] - 1.00 * cshi[nl];
+      const double be[2] = {edge[nl], edge[nl] + width[nl]};
+      const double dens = orc_bprldos(e_shift, a + (size_t)lld * nl, b2 + (size_t)lld * nl, lld, be);
+      tdens[nl + (size_t)NB * eidx] = 0.0 + 1.0 * dens / dw_l[nl];
+    }
+}
+
+/* ---- sgreen (green.f90:628-705): g0(18,18,nv,na) from the scalar-recursion DOS ---------------------------------
+ * a, b2: (lld,18,na,nmdir_alloc=3) like recursion%a; dw_l, cshi: (18,na). */
+void orc_sgreen(const double *a, const double *b2, int lld, int na, int nmdir, const double *ene, int nv,
+                const double *dw_l, const double *cshi, cplx *g0) {
+  const cplx impi = PI_RP;
+  const cplx gfac[2][3] = {{1.0, -I, 1.0}, {1.0, I, -1.0}};
+  const double lmask[3] = {1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0};
+  const int goff[4][3] = {{0, 0, 0}, {9, 9, 0}, {9, 9, 9}, {0, 0, 9}};
+  const cplx dfac = I * impi / 2.0;
+  double *doso = malloc(sizeof(double) * NB * nv);
+  memset(g0, 0, sizeof(cplx) * BLK * (size_t)nv * na);
+  for (int ia = 0; ia < na; ia++)
+    for (int mdir = 0; mdir < nmdir; mdir++) {
+      const size_t off = (size_t)lld * NB * (ia + (size_t)na * mdir);
+      cplx *g = g0 + (size_t)BLK * nv * ia;
+      orc_density(a + off, b2 + off, lld, ene, nv, dw_l + (size_t)NB * ia, cshi + (size_t)NB * ia, doso);
+      if (nmdir == 1) {
+        for (int ie = 0; ie < nv; ie++)
+          for (int j = 0; j < NB; j++) g[j + NB * j + (size_t)BLK * ie] = -I * doso[j + (size_t)NB * ie] * impi;
+      } else {
+        for (int ie = 0; ie < nv; ie++)
+          for (int j = 0; j < 9; j++) {
+            cplx *gb = g + (size_t)BLK * ie;
+            const double up = doso[j + (size_t)NB * ie], dn = doso[j + 9 + (size_t)NB * ie];
+            gb[j + NB * j] = gb[j + NB * j] - (up + dn) * dfac * lmask[mdir];
+            gb[(j + 9) + NB * (j + 9)] = gb[(j + 9) + NB * (j + 9)] - (up + dn) * dfac * lmask[mdir];
+            gb[(j + goff[0][mdir]) + NB * (j + goff[1][mdir])] -= (up - dn) * gfac[0][mdir] * dfac;
+            gb[(j + goff[2][mdir]) + NB * (j + goff[3][mdir])] -= (up - dn) * gfac[1][mdir] * dfac;
+          }
+      }
+    }
+  free(doso);
+}
+
+/* ---- calculate_gamma_nm (conductivity.f90:158-227): gamma: (nv, M, M) complex ---------------------------------- */
+void orc_gamma_nm(const double *ene, int nv, int M, double energy_min, double energy_max, cplx *gamma) {
+  const double a = (energy_max - energy_min) / (2 - 0.3), b = (energy_max + energy_min) / 2;
+  double *gk = malloc(sizeof(double) * M), *wt = malloc(sizeof(double) * M);
+  double *T = malloc(sizeof(double) * (size_t)nv * M);
+  cplx *cn = malloc(sizeof(cplx) * (size_t)nv * M), *cm = malloc(sizeof(cplx) * (size_t)nv * M);
+  orc_lorentz_kernel(M, 6.0, gk);
+  for (int n = 0; n < M; n++) wt[n] = 1.0;
+  wt[0] = 0.5;
+  for (int i = 0; i < nv; i++) {
+    const double w = (ene[i] - b) / a, ac = acos(w), sq = sqrt(1.0 - w * w);
+    for (int n = 1; n <= M; n++) {
+      cn[i + (size_t)nv * (n - 1)] = (w - I * (double)(n - 1) * sq) * cexp(I * (double)(n - 1) * ac);
+      cm[i + (size_t)nv * (n - 1)] = (w + I * (double)(n - 1) * sq) * cexp(-I * (double)(n - 1) * ac);
+    }
+    T[i] = 1.0;
+    if (M > 1) T[i + (size_t)nv] = w;
+    for (int n = 3; n <= M; n++) T[i + (size_t)nv * (n - 1)] = 2.0 * w * T[i + (size_t)nv * (n - 2)] - T[i + (size_t)nv * (n - 3)];
+  }
+  for (int n = 0; n < M; n++)
+    for (int m = 0; m < M; m++)
+      for (int i = 0; i < nv; i++) {
+        const double w = (ene[i] - b) / a;
+        cplx g = cn[i + (size_t)nv * n] * T[i + (size_t)nv * m] + cm[i + (size_t)nv * m] * T[i + (size_t)nv * n];
+        g = g / ((1.0 - w * w) * (1.0 - w * w));
+        g = g * gk[n] * gk[m] * wt[n] * wt[m];
+        gamma[i + (size_t)nv * (n + (size_t)M * m)] = g;
+      }
+  free(gk); free(wt); free(T); free(cn); free(cm);
+}
+
+/* ---- calculate_conductivity_tensor, integrand part (conductivity.f90:228-306) ----------------------------------
+ * mu_nm: (18,18,M,M,nloop); integrand: (18,nv) = diagonal integrand(l2,l2,i) summed over the loop index;
+ * integrand_at: (18,nv,nloop) per-type (filled for per_type only; may be NULL). */
+void orc_conductivity_integrand(const cplx *mu_nm, int M, int nloop, const double *ene, int nv, double energy_min,
+                                double energy_max, int per_type, cplx *integrand, cplx *integrand_at) {
+  const double de = energy_max - energy_min;
+  const double factor = 16 / (PI_RP * (de * de));
+  cplx *gamma = malloc(sizeof(cplx) * (size_t)nv * M * M);
+  orc_gamma_nm(ene, nv, M, energy_min, energy_max, gamma);
+  memset(integrand, 0, sizeof(cplx) * NB * (size_t)nv);
+  if (integrand_at) memset(integrand_at, 0, sizeof(cplx) * NB * (size_t)nv * nloop);
+  for (int t = 0; t < nloop; t++) {
+#pragma omp parallel for schedule(dynamic)
+    for (int i = 0; i < nv; i++)
+      for (int n = 0; n < M; n++)
+        for (int m = 0; m < M; m++)
+          for (int l2 = 0; l2 < NB; l2++) {
+            const cplx term = factor * gamma[i + (size_t)nv * (n + (size_t)M * m)] *
+                              mu_nm[(l2 + NB * l2) + (size_t)BLK * (n + (size_t)M * (m + (size_t)M * t))];
+            integrand[l2 + (size_t)NB * i] += term;
+            if (per_type && integrand_at) integrand_at[l2 + (size_t)NB * (i + (size_t)nv * t)] += term;
+          }
+  }
+  free(gamma);
+}
