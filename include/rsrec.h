@@ -94,6 +94,50 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
 int rsrec_ham_vec_matmul(rsrec_handle h, const rsrec_cplx *psi_in, rsrec_cplx *psi_out, double a_scale, double b_shift);
 int rsrec_velo_vec_matmul(rsrec_handle h, int slot, const rsrec_cplx *psi_in, rsrec_cplx *psi_out);
 
+/* ---- consumers either side of the recursion: the reference's green / density_of_states /
+ * conductivity back ends that read a_b, b2_b, a, b2, mu_n, mu_nm_stochastic.  Same array shapes as the reference. ---- */
+
+/* bpopt (recursion.f90:3540-3581, with emami 3589-3706) for `nchains` independent chains: a, rb (ll,nchains);
+ * ainf, rbinf, ifail (nchains; ifail may be NULL).  Bit-identical to the reference's non-contracted arithmetic. */
+int rsrec_bpopt(rsrec_handle h, int nchains, int ll, const double *a, const double *rb, double *ainf, double *rbinf,
+                int *ifail);
+
+/* get_terminf / get_cinf (recursion.f90:2092-2138 / 2030-2086): a_b, b_b (18,18,ll,na) with b_b = B (after zsqr) as
+ * block_green passes them; a_inf, b_inf (18,18,na) real; a_inf0, b_inf0 (na), may be NULL. */
+int rsrec_get_terminf(rsrec_handle h, const rsrec_cplx *a_b, const rsrec_cplx *b_b, int na, int ll, double *a_inf,
+                      double *b_inf, double *a_inf0, double *b_inf0);
+
+/* bgreen (green.f90:1191-1339) for one unit: a_b, b_b (18,18,ll); e (nv); channels ie_start..ie_start+ie_len-1
+ * (1-based) of g_out (18,18,nv) are computed, the others are zero; a_inf, b_inf (18,18) real; eta complex. */
+int rsrec_bgreen(rsrec_handle h, const rsrec_cplx *a_b, const rsrec_cplx *b_b, int ll, const double *e, int nv,
+                 int ie_start, int ie_len, const double *a_inf, const double *b_inf, double eta_re, double eta_im,
+                 int sym_term, rsrec_cplx *g_out);
+
+/* block_green (green.f90:588-621): get_terminf + bgreen(eta = 0, all channels) for na units; g0 (18,18,nv,na). */
+int rsrec_block_green(rsrec_handle h, const rsrec_cplx *a_b, const rsrec_cplx *b_b, int na, int ll, const double *e,
+                      int nv, int sym_term, rsrec_cplx *g0);
+
+/* chebyshev_green (green.f90:1030-1108): mu_n (18,18,2*lld+2,na) -> mu_ng (same shape, Jackson-weighted; may be
+ * NULL) and g0 (18,18,nv,na); energy_min/max are energy%energy_min/max. */
+int rsrec_chebyshev_green(rsrec_handle h, const rsrec_cplx *mu_n, int na, int lld, const double *ene, int nv,
+                          double energy_min, double energy_max, rsrec_cplx *mu_ng, rsrec_cplx *g0);
+
+/* dos%density with bprldos (density_of_states.f90:248-407) for every (atom, direction): a, b2 (lld,18,na,nmdir) =
+ * recursion%a/b2(:, :, :, 1:nmdir); dw_l, cshi (18,na); tdens (18,nv,na,nmdir). */
+int rsrec_density(rsrec_handle h, const double *a, const double *b2, int lld, int na, int nmdir, const double *ene,
+                  int nv, const double *dw_l, const double *cshi, double *tdens);
+
+/* sgreen (green.f90:628-705): g0 (18,18,nv,na) from the scalar-recursion coefficients; nmdir 1 or 3. */
+int rsrec_sgreen(rsrec_handle h, const double *a, const double *b2, int lld, int na, int nmdir, const double *ene,
+                 int nv, const double *dw_l, const double *cshi, rsrec_cplx *g0);
+
+/* calculate_gamma_nm + the energy integrand of calculate_conductivity_tensor (conductivity.f90:158-306):
+ * mu_nm (18,18,M,M,nloop) = mu_nm_stochastic; integrand (18,nv) = integrand(l2,l2,:) summed over the loop index;
+ * integrand_at (18,nv,nloop) per type when per_type != 0 (zeros otherwise; may be NULL). */
+int rsrec_conductivity_integrand(rsrec_handle h, const rsrec_cplx *mu_nm, int M, int nloop, const double *ene, int nv,
+                                 double energy_min, double energy_max, int per_type, rsrec_cplx *integrand,
+                                 rsrec_cplx *integrand_at);
+
 /* ---- device-resident stepping (what bench.py times as `value`; the calls above are the `e2e` path) ----
  * begin: upload start vectors, compute mu(1), mu(2) on the device.  run_steps: enqueue n chebyshev_recur_ll steps on
  * the handle's stream without host synchronisation.  end: wait, download mu_n(18,18,2*lld+2,nvec). */

@@ -15,6 +15,8 @@ SYMBOLS = [
     "rsrec_velo_vec_matmul", "rsrec_cheb_begin_random", "rsrec_cheb_begin_sites", "rsrec_cheb_run_steps",
     "rsrec_cheb_end", "rsrec_synchronize", "rsrec_stream", "rsrec_launch_count", "rsrec_set_kernel_family",
     "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read",
+    "rsrec_bpopt", "rsrec_get_terminf", "rsrec_bgreen", "rsrec_block_green", "rsrec_chebyshev_green", "rsrec_density",
+    "rsrec_sgreen", "rsrec_conductivity_integrand",
 ]
 
 
@@ -66,6 +68,14 @@ def load():
     L.rsrec_d2h_bytes.restype = C.c_longlong
     L.rsrec_profile.argtypes = [vp, i]
     L.rsrec_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i)]
+    L.rsrec_bpopt.argtypes = [vp, i, i, vp, vp, vp, vp, vp]
+    L.rsrec_get_terminf.argtypes = [vp, vp, vp, i, i, vp, vp, vp, vp]
+    L.rsrec_bgreen.argtypes = [vp, vp, vp, i, vp, i, i, i, vp, vp, d, d, i, vp]
+    L.rsrec_block_green.argtypes = [vp, vp, vp, i, i, vp, i, i, vp]
+    L.rsrec_chebyshev_green.argtypes = [vp, vp, i, i, vp, i, d, d, vp, vp]
+    L.rsrec_density.argtypes = [vp, vp, vp, i, i, i, vp, i, vp, vp, vp]
+    L.rsrec_sgreen.argtypes = [vp, vp, vp, i, i, i, vp, i, vp, vp, vp]
+    L.rsrec_conductivity_integrand.argtypes = [vp, vp, i, i, vp, i, d, d, i, vp, vp]
     _lib = L
     return L
 

@@ -9,6 +9,7 @@
 #include "eig18.cuh"
 #include "kernels_dmma.cuh"
 #include "kernels_kubo.cuh"
+#include "kernels_post.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -61,6 +62,7 @@ struct rsrec_handle_s {
   // work vectors and small matrices
   std::vector<DevBuf> vecs;
   DevBuf part, A, B, Bi, B2, mu, ahist, b2hist, scratch;
+  DevBuf post[12];  // work arrays of the post-recursion consumers (terminator, Green functions, Kubo back end)
   int32_t *d_si = nullptr, *d_sj = nullptr;
   double *d_as = nullptr, *d_bs = nullptr;
   int units_cap = 0;
@@ -81,6 +83,7 @@ struct rsrec_handle_s {
   } cheb;
 };
 typedef rsrec_handle_s H;
+static int post_configure();
 
 // ------------------------------------------------------------------------------------------------------------
 static int dev_alloc(DevBuf &b, size_t n, bool zero) {
@@ -628,7 +631,7 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
   if (const char *f = getenv("RSREC_SQRT_METHOD")) h->sqrt_method = atoi(f);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  if (dmma_configure() != 0 || kubo_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
+  if (dmma_configure() != 0 || kubo_configure() != 0 || post_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
   *out = h;
   return RSREC_OK;
 }
@@ -641,6 +644,7 @@ int rsrec_destroy(rsrec_handle h) {
   DevBuf *bufs[] = {&h->Hmain, &h->Hh, &h->Hho_neg, &h->Hx, &h->Hscalar, &h->Hva, &h->Hvb, &h->Hvoa_neg, &h->Hvob_neg,
                     &h->part, &h->A, &h->B, &h->Bi, &h->B2, &h->mu, &h->ahist, &h->b2hist, &h->scratch};
   for (auto b : bufs) dev_free(*b);
+  for (auto &b : h->post) dev_free(b);
   dmma_free_tiles(h->tiles);
   if (h->d_nbr) cudaFree(h->d_nbr);
   if (h->d_cls) cudaFree(h->d_cls);
@@ -969,6 +973,303 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
   }
   return RSREC_OK;
 }
+
+}  // extern "C"
+
+// ============================================================================================================
+// Consumers either side of the hot path: terminator, block / Chebyshev Green functions,
+// scalar continued fraction, Kubo-Bastin integrand.  d_* functions work on device arrays (so that the fused entry
+// points can chain them behind a recursion without a host round trip); the rsrec_* wrappers marshal host arrays.
+static int post_configure() {
+  const int smem = (2 + BG_WARPS) * BG_MAT * (int)sizeof(double2);
+  return cudaFuncSetAttribute(k_bgreen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess ? 0 : -1;
+}
+static int to_dev(H *h, DevBuf &b, const void *src, size_t ndoubles) {
+  TRY(dev_alloc(b, std::max<size_t>(ndoubles, 1), false));
+  if (ndoubles) CUDA_TRY(cudaMemcpyAsync(b.p, src, ndoubles * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  h->h2d_bytes += (long long)(ndoubles * sizeof(double));
+  return RSREC_OK;
+}
+static int to_host(H *h, void *dst, const double *src, size_t ndoubles) {
+  if (ndoubles) CUDA_TRY(cudaMemcpyAsync(dst, src, ndoubles * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  h->d2h_bytes += (long long)(ndoubles * sizeof(double));
+  return RSREC_OK;
+}
+static int grid_for(size_t n, int threads, int cap) { return (int)std::max<size_t>(1, std::min<size_t>((n + threads - 1) / threads, (size_t)cap)); }
+
+// get_terminf (recursion.f90:2092-2138) = get_cinf (324 bpopt chains per unit over the real parts) + fix-ups
+static int d_terminf(H *h, const double *d_ab, const double *d_bb, int na, int ll, double *d_ainf, double *d_binf,
+                     double *d_a0, double *d_b0) {
+  const ChainLayout lay{BLKC, 2, 2LL * BLKC * ll, 2LL * BLKC};
+  const int nch = BLKC * na;
+  k_bpopt<<<(nch + 63) / 64, 64, 0, h->st>>>(d_ab, d_bb, lay, ll, nch, d_ainf, d_binf, nullptr);
+  k_terminf_fix<<<na, BLKC, 0, h->st>>>(d_ainf, d_binf, d_a0, d_b0);
+  h->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return RSREC_OK;
+}
+// bgreen (green.f90:1191-1339) for na units sharing the mesh; a_inf, b_inf (18,18,na); g (18,18,nv,na) zeroed here
+static int d_bgreen(H *h, const double *d_ab, const double *d_bb, int ll, int na, const double *d_ene, int nv, int ie0,
+                    int ie_len, const double *d_ainf, const double *d_binf, double eta_re, double eta_im, int sym_term,
+                    double *d_g) {
+  CUDA_TRY(cudaMemsetAsync(d_g, 0, (size_t)na * nv * BLKD * sizeof(double), h->st));
+  if (ie_len <= 0) return RSREC_OK;
+  const int smem = (2 + BG_WARPS) * BG_MAT * (int)sizeof(double2);
+  k_bgreen<<<dim3((ie_len + BG_WARPS - 1) / BG_WARPS, na), BG_WARPS * 32, smem, h->st>>>(
+      (const double2 *)d_ab, (const double2 *)d_bb, ll, d_ene, nv, ie0, ie_len, d_ainf, d_binf, eta_re, eta_im, sym_term,
+      (double2 *)d_g);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return RSREC_OK;
+}
+// jackson_kernel / lorentz_kernel (math.f90:1641-1677): `real(ll)` is default (single) real in the reference
+static void host_jackson_kernel(int n, std::vector<double> &k) {
+  k.resize(n);
+  const float bign = (float)n;
+  for (int ll = 1; ll <= n; ll++) {
+    const double theta = PI_RP * ((float)ll - 1.0f) / (bign + 1.0f);
+    k[ll - 1] = (double)(bign - ((float)ll - 1.0f) + 1.0f) * std::cos(theta) + std::sin(theta) / std::tan(PI_RP / (bign + 1.0f));
+    k[ll - 1] = k[ll - 1] / (bign + 1.0f);
+  }
+}
+static void host_lorentz_kernel(int n, double lambda, std::vector<double> &k) {
+  k.resize(n);
+  for (int ll = 1; ll <= n; ll++) {
+    const float q = ((float)ll - 1.0f) / (float)n;
+    const double theta = lambda * (double)(1.0f - q);
+    k[ll - 1] = std::sinh(theta) / std::sinh(lambda);
+  }
+}
+// chebyshev_green (green.f90:1030-1108): d_mu (18,18,nk,na) -> d_mug (weighted moments), d_g0 (18,18,nv,na)
+static int d_cheb_green(H *h, const double *d_mu, int na, int lld, const double *d_ene, int nv, double emin, double emax,
+                        double *d_mug, double *d_g0) {
+  const int nk = 2 * lld + 2;
+  const double a = (emax - emin) / (2 - 0.3), b = (emax + emin) / 2;
+  std::vector<double> kern;
+  host_jackson_kernel(nk, kern);
+  TRY(to_dev(h, h->post[10], kern.data(), nk));
+  const size_t total = (size_t)na * nk * BLKC;
+  k_cheb_weight<<<grid_for(total, 256, h->sms * 8), 256, 0, h->st>>>((const double2 *)d_mu, h->post[10].p, nk, total, (double2 *)d_mug);
+  k_cheb_green<<<dim3((nv + CG_EB - 1) / CG_EB, na), CG_THREADS, 0, h->st>>>((const double2 *)d_mug, nk, d_ene, nv, a, b, (double2 *)d_g0);
+  h->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->st));  // `kern` goes out of scope
+  return RSREC_OK;
+}
+// density for nch = na*nmdir chains-of-18 (density_of_states.f90:248-372): d_a, d_b2 (lld,18,na,nmdir) -> d_td (18,nv,na,nmdir)
+static int d_density(H *h, const double *d_a, const double *d_b2, int lld, int na, int nmdir, const double *d_ene, int nv,
+                     const double *d_dw, const double *d_cs, double *d_td) {
+  const int nch = na * nmdir, nchain = NB * nch;
+  const size_t n = (size_t)lld * nchain;
+  TRY(dev_alloc(h->post[8], n + 2 * (size_t)nchain, false));
+  double *sq = h->post[8].p, *am1 = sq + n, *bm1 = am1 + nchain;
+  k_sqrt_array<<<grid_for(n, 256, h->sms * 8), 256, 0, h->st>>>(d_b2, sq, n);
+  const ChainLayout lay{(long long)nchain, (long long)lld, 0, 1};
+  k_bpopt<<<(nchain + 63) / 64, 64, 0, h->st>>>(d_a, sq, lay, lld, nchain, am1, bm1, nullptr);
+  const size_t total = (size_t)NB * nv * nch;
+  k_density<<<grid_for(total, 256, h->sms * 16), 256, 0, h->st>>>(d_a, d_b2, lld, nch, na, am1, bm1, d_ene, nv, d_dw, d_cs, d_td);
+  h->launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return RSREC_OK;
+}
+// calculate_gamma_nm + the integrand of calculate_conductivity_tensor (conductivity.f90:158-306).
+// d_mu: (18,18,M,M,nloop) device moments; outputs on the host.
+static int d_cond_integrand(H *h, const double *d_mu, int M, int nloop, const double *ene, int nv, double emin, double emax,
+                            int per_type, cplx *integrand, cplx *integrand_at) {
+  const double a = (emax - emin) / (2 - 0.3), b = (emax + emin) / 2, de = emax - emin;
+  const double factor = 16 / (PI_RP * (de * de));
+  std::vector<double> sk;
+  host_lorentz_kernel(M, 6.0, sk);
+  sk[0] *= 0.5;  // weights(1) = 0.5
+  const int nchunk = std::max(1, std::min(M, (2 * h->sms) / std::max(1, ((nv + CD_THREADS - 1) / CD_THREADS) * nloop)));
+  const size_t nvM = (size_t)nv * M;
+  TRY(to_dev(h, h->post[0], ene, nv));
+  TRY(to_dev(h, h->post[1], sk.data(), M));
+  TRY(dev_alloc(h->post[2], 2 * nvM, false));  // CN
+  TRY(dev_alloc(h->post[3], 2 * nvM, false));  // CM
+  TRY(dev_alloc(h->post[4], nvM + nv, false)); // TS, inv
+  TRY(dev_alloc(h->post[5], 2 * (size_t)nloop * M * M * NB, false));             // D
+  TRY(dev_alloc(h->post[6], 2 * (size_t)nloop * nchunk * NB * nv, false));      // partials
+  TRY(dev_alloc(h->post[7], 2 * (size_t)NB * nv * (1 + nloop), false));          // integrand, integrand_at
+  double *TS = h->post[4].p, *inv = TS + nvM;
+  double *d_int = h->post[7].p, *d_at = d_int + 2 * (size_t)NB * nv;
+  k_cond_tables<<<(nv + 127) / 128, 128, 0, h->st>>>(h->post[0].p, nv, M, a, b, h->post[1].p, (double2 *)h->post[2].p, (double2 *)h->post[3].p, TS, inv);
+  const size_t nblocks = (size_t)nloop * M * M;
+  k_cond_diag<<<grid_for(nblocks * NB, 256, h->sms * 16), 256, 0, h->st>>>((const double2 *)d_mu, M, nblocks, (double2 *)h->post[5].p);
+  k_cond_contract<<<dim3((nv + CD_THREADS - 1) / CD_THREADS, nchunk, nloop), CD_THREADS, 0, h->st>>>(
+      (const double2 *)h->post[2].p, (const double2 *)h->post[3].p, TS, (const double2 *)h->post[5].p, nv, M, nchunk, (double2 *)h->post[6].p);
+  k_cond_finish<<<(NB * nv + 127) / 128, 128, 0, h->st>>>((const double2 *)h->post[6].p, inv, nv, nchunk, nloop, factor, (double2 *)d_int,
+                                                         per_type ? (double2 *)d_at : nullptr);
+  h->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  TRY(to_host(h, integrand, d_int, 2 * (size_t)NB * nv));
+  if (integrand_at) {
+    if (per_type) TRY(to_host(h, integrand_at, d_at, 2 * (size_t)NB * nv * nloop));
+    else memset(integrand_at, 0, sizeof(cplx) * (size_t)NB * nv * nloop);
+  }
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+extern "C" {
+
+int rsrec_bpopt(rsrec_handle h, int nchains, int ll, const double *a, const double *rb, double *ainf, double *rbinf, int *ifail) {
+  if (!h || nchains < 0 || ll < 2 || !a || !rb || !ainf || !rbinf) return fail(RSREC_EINVAL, "rsrec_bpopt: bad argument (need ll >= 2)");
+  if (nchains == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t n = (size_t)ll * nchains;
+  TRY(to_dev(h, h->post[0], a, n));
+  TRY(to_dev(h, h->post[1], rb, n));
+  TRY(dev_alloc(h->post[2], 3 * (size_t)nchains, false));
+  double *d_ai = h->post[2].p, *d_bi = d_ai + nchains;
+  int *d_if = (int *)(d_bi + nchains);
+  const ChainLayout lay{(long long)nchains, (long long)ll, 0, 1};
+  k_bpopt<<<(nchains + 63) / 64, 64, 0, h->st>>>(h->post[0].p, h->post[1].p, lay, ll, nchains, d_ai, d_bi, d_if);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  TRY(to_host(h, ainf, d_ai, nchains));
+  TRY(to_host(h, rbinf, d_bi, nchains));
+  if (ifail) { CUDA_TRY(cudaMemcpyAsync(ifail, d_if, nchains * sizeof(int), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += nchains * 4; }
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_get_terminf(rsrec_handle h, const cplx *a_b, const cplx *b_b, int na, int ll, double *a_inf, double *b_inf,
+                      double *a_inf0, double *b_inf0) {
+  if (!h || na < 0 || ll < 2 || !a_b || !b_b || !a_inf || !b_inf) return fail(RSREC_EINVAL, "rsrec_get_terminf: bad argument (need ll >= 2)");
+  if (na == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t n = (size_t)na * ll * BLKD;
+  TRY(to_dev(h, h->post[0], a_b, n));
+  TRY(to_dev(h, h->post[1], b_b, n));
+  TRY(dev_alloc(h->post[2], 2 * (size_t)na * (BLKC + 1), false));
+  double *d_ai = h->post[2].p, *d_bi = d_ai + (size_t)na * BLKC, *d_a0 = d_bi + (size_t)na * BLKC, *d_b0 = d_a0 + na;
+  TRY(d_terminf(h, h->post[0].p, h->post[1].p, na, ll, d_ai, d_bi, d_a0, d_b0));
+  TRY(to_host(h, a_inf, d_ai, (size_t)na * BLKC));
+  TRY(to_host(h, b_inf, d_bi, (size_t)na * BLKC));
+  if (a_inf0) TRY(to_host(h, a_inf0, d_a0, na));
+  if (b_inf0) TRY(to_host(h, b_inf0, d_b0, na));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_bgreen(rsrec_handle h, const cplx *a_b, const cplx *b_b, int ll, const double *e, int nv, int ie_start, int ie_len,
+                 const double *a_inf, const double *b_inf, double eta_re, double eta_im, int sym_term, cplx *g_out) {
+  if (!h || ll < 1 || nv < 0 || !a_b || !b_b || !e || !a_inf || !b_inf || !g_out || ie_start < 1 || ie_len < 0 || ie_start - 1 + ie_len > nv)
+    return fail(RSREC_EINVAL, "rsrec_bgreen: bad argument");
+  if (nv == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(to_dev(h, h->post[0], a_b, (size_t)ll * BLKD));
+  TRY(to_dev(h, h->post[1], b_b, (size_t)ll * BLKD));
+  TRY(to_dev(h, h->post[2], a_inf, BLKC));
+  TRY(to_dev(h, h->post[3], b_inf, BLKC));
+  TRY(to_dev(h, h->post[4], e, nv));
+  TRY(dev_alloc(h->post[5], (size_t)nv * BLKD, false));
+  TRY(d_bgreen(h, h->post[0].p, h->post[1].p, ll, 1, h->post[4].p, nv, ie_start - 1, ie_len, h->post[2].p, h->post[3].p, eta_re, eta_im, sym_term, h->post[5].p));
+  TRY(to_host(h, g_out, h->post[5].p, (size_t)nv * BLKD));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_block_green(rsrec_handle h, const cplx *a_b, const cplx *b_b, int na, int ll, const double *e, int nv, int sym_term, cplx *g0) {
+  if (!h || na < 0 || ll < 2 || nv < 0 || !a_b || !b_b || !e || !g0) return fail(RSREC_EINVAL, "rsrec_block_green: bad argument (need ll >= 2)");
+  if (na == 0 || nv == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t n = (size_t)na * ll * BLKD;
+  TRY(to_dev(h, h->post[0], a_b, n));
+  TRY(to_dev(h, h->post[1], b_b, n));
+  TRY(dev_alloc(h->post[2], 2 * (size_t)na * (BLKC + 1), false));
+  TRY(to_dev(h, h->post[4], e, nv));
+  TRY(dev_alloc(h->post[5], (size_t)na * nv * BLKD, false));
+  double *d_ai = h->post[2].p, *d_bi = d_ai + (size_t)na * BLKC, *d_a0 = d_bi + (size_t)na * BLKC, *d_b0 = d_a0 + na;
+  TRY(d_terminf(h, h->post[0].p, h->post[1].p, na, ll, d_ai, d_bi, d_a0, d_b0));
+  TRY(d_bgreen(h, h->post[0].p, h->post[1].p, ll, na, h->post[4].p, nv, 0, nv, d_ai, d_bi, 0.0, 0.0, sym_term, h->post[5].p));
+  TRY(to_host(h, g0, h->post[5].p, (size_t)na * nv * BLKD));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_chebyshev_green(rsrec_handle h, const cplx *mu_n, int na, int lld, const double *ene, int nv, double energy_min,
+                          double energy_max, cplx *mu_ng, cplx *g0) {
+  if (!h || na < 0 || lld < 0 || nv < 0 || !mu_n || !ene || !g0 || energy_max == energy_min) return fail(RSREC_EINVAL, "rsrec_chebyshev_green: bad argument");
+  if (na == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t n = (size_t)na * (2 * lld + 2) * BLKD;
+  TRY(to_dev(h, h->post[0], mu_n, n));
+  TRY(dev_alloc(h->post[1], n, false));
+  TRY(to_dev(h, h->post[4], ene, nv));
+  TRY(dev_alloc(h->post[5], std::max<size_t>(1, (size_t)na * nv * BLKD), false));
+  if (nv == 0) {  // only the weighted moments
+    std::vector<double> kern;
+    host_jackson_kernel(2 * lld + 2, kern);
+    TRY(to_dev(h, h->post[10], kern.data(), kern.size()));
+    k_cheb_weight<<<grid_for(n / 2, 256, h->sms * 8), 256, 0, h->st>>>((const double2 *)h->post[0].p, h->post[10].p, 2 * lld + 2, n / 2, (double2 *)h->post[1].p);
+    h->launches++;
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+  } else {
+    TRY(d_cheb_green(h, h->post[0].p, na, lld, h->post[4].p, nv, energy_min, energy_max, h->post[1].p, h->post[5].p));
+  }
+  if (mu_ng) TRY(to_host(h, mu_ng, h->post[1].p, n));
+  TRY(to_host(h, g0, h->post[5].p, (size_t)na * nv * BLKD));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_density(rsrec_handle h, const double *a, const double *b2, int lld, int na, int nmdir, const double *ene, int nv,
+                  const double *dw_l, const double *cshi, double *tdens) {
+  if (!h || lld < 2 || na < 0 || nmdir < 1 || nv < 0 || !a || !b2 || !ene || !dw_l || !cshi || !tdens) return fail(RSREC_EINVAL, "rsrec_density: bad argument (need lld >= 2)");
+  if (na == 0 || nv == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t n = (size_t)lld * NB * na * nmdir;
+  TRY(to_dev(h, h->post[0], a, n));
+  TRY(to_dev(h, h->post[1], b2, n));
+  TRY(to_dev(h, h->post[2], dw_l, (size_t)NB * na));
+  TRY(to_dev(h, h->post[3], cshi, (size_t)NB * na));
+  TRY(to_dev(h, h->post[4], ene, nv));
+  TRY(dev_alloc(h->post[5], (size_t)NB * nv * na * nmdir, false));
+  TRY(d_density(h, h->post[0].p, h->post[1].p, lld, na, nmdir, h->post[4].p, nv, h->post[2].p, h->post[3].p, h->post[5].p));
+  TRY(to_host(h, tdens, h->post[5].p, (size_t)NB * nv * na * nmdir));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_sgreen(rsrec_handle h, const double *a, const double *b2, int lld, int na, int nmdir, const double *ene, int nv,
+                 const double *dw_l, const double *cshi, cplx *g0) {
+  if (!h || lld < 2 || na < 0 || (nmdir != 1 && nmdir != 3) || nv < 0 || !a || !b2 || !ene || !dw_l || !cshi || !g0)
+    return fail(RSREC_EINVAL, "rsrec_sgreen: bad argument (need lld >= 2, nmdir 1 or 3)");
+  if (na == 0 || nv == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t n = (size_t)lld * NB * na * nmdir;  // the first nmdir direction slabs of recursion%a(lld,18,na,3)
+  TRY(to_dev(h, h->post[0], a, n));
+  TRY(to_dev(h, h->post[1], b2, n));
+  TRY(to_dev(h, h->post[2], dw_l, (size_t)NB * na));
+  TRY(to_dev(h, h->post[3], cshi, (size_t)NB * na));
+  TRY(to_dev(h, h->post[4], ene, nv));
+  TRY(dev_alloc(h->post[5], (size_t)NB * nv * na * nmdir, false));
+  TRY(dev_alloc(h->post[6], (size_t)na * nv * BLKD, false));
+  TRY(d_density(h, h->post[0].p, h->post[1].p, lld, na, nmdir, h->post[4].p, nv, h->post[2].p, h->post[3].p, h->post[5].p));
+  CUDA_TRY(cudaMemsetAsync(h->post[6].p, 0, (size_t)na * nv * BLKD * sizeof(double), h->st));
+  const size_t total = (size_t)(nmdir == 1 ? NB : 9) * nv * na;
+  k_sgreen_assemble<<<grid_for(total, 256, h->sms * 8), 256, 0, h->st>>>(h->post[5].p, nv, na, nmdir, (double2 *)h->post[6].p);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  TRY(to_host(h, g0, h->post[6].p, (size_t)na * nv * BLKD));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_conductivity_integrand(rsrec_handle h, const cplx *mu_nm, int M, int nloop, const double *ene, int nv, double energy_min,
+                                 double energy_max, int per_type, cplx *integrand, cplx *integrand_at) {
+  if (!h || M < 1 || nloop < 1 || nv < 1 || !mu_nm || !ene || !integrand || energy_max == energy_min)
+    return fail(RSREC_EINVAL, "rsrec_conductivity_integrand: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(to_dev(h, h->post[9], mu_nm, (size_t)nloop * M * M * BLKD));
+  return d_cond_integrand(h, h->post[9].p, M, nloop, ene, nv, energy_min, energy_max, per_type, integrand, integrand_at);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 int rsrec_synchronize(rsrec_handle h) {
   if (!h) return fail(RSREC_EINVAL, "null handle");

@@ -1,0 +1,153 @@
+"""Host-side mirrors of the reference types that consume the recursion results:
+`green` (green.f90), `dos` (density_of_states.f90) and `conductivity` (conductivity.f90), on top of the C ABI.
+
+Same procedure names and result members as the reference; everything numerical runs in librsrec.so on the GPU.
+
+    g = Green(recursion)                 # green(dos_obj) -> recursion, energy, control
+    g.block_green()   -> g.g0 (18,18,nv,nrec_local)     green.f90:588-621   (needs recursion.zsqr() first, like run_dos)
+    g.chebyshev_green() -> g.g0, recursion.mu_ng        green.f90:1030-1108
+    g.sgreen()        -> g.g0                           green.f90:628-705
+    g.bgreen(ia, ie_start, ie_len, a_inf, b_inf, eta)   green.f90:1191-1339
+    Dos(recursion).density(ia, mdir) -> tdens (18,nv)   density_of_states.f90:248-372
+    Conductivity(recursion).calculate_conductivity_tensor() -> integrand (18,nv), integrand_at   conductivity.f90:228-306
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+NB = 18
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a, dt):
+    return np.asfortranarray(a, dtype=dt)
+
+
+class _Consumer:
+    def __init__(self, recursion):
+        self.recursion = recursion
+        self.en = recursion.en
+        self.control = recursion.control
+        self._L, self._h = recursion._L, recursion._h
+        if self.en.ene is None:
+            self.en.e_mesh()
+
+    @property
+    def ene(self):
+        return np.ascontiguousarray(self.en.ene, dtype=np.float64)
+
+
+class Green(_Consumer):
+    def __init__(self, recursion, sym_term: bool = False):
+        super().__init__(recursion)
+        self.sym_term = sym_term          # control%sym_term (green.f90:1240)
+        self.g0 = None
+
+    def get_terminf(self):
+        """recursion%get_terminf (recursion.f90:2092-2138) on the recursion's a_b / b2_b (= B after zsqr)."""
+        a_b, b_b = _f(self.recursion.a_b, np.complex128), _f(self.recursion.b2_b, np.complex128)
+        ll, na = a_b.shape[2], a_b.shape[3]
+        a_inf = np.zeros((NB, NB, na), order="F"); b_inf = np.zeros((NB, NB, na), order="F")
+        a0 = np.zeros(na); b0 = np.zeros(na)
+        _lib.check(self._L.rsrec_get_terminf(self._h, _p(a_b), _p(b_b), na, ll, _p(a_inf), _p(b_inf), _p(a0), _p(b0)))
+        return a_inf, b_inf, a0, b0
+
+    def bgreen(self, ia, ie_start, ie_len, a_inf, b_inf, eta=0.0):
+        """one unit `ia` (1-based local index); returns g_out (18,18,nv)."""
+        a_b = _f(self.recursion.a_b[..., ia - 1], np.complex128)
+        b_b = _f(self.recursion.b2_b[..., ia - 1], np.complex128)
+        ene = self.ene
+        g = np.zeros((NB, NB, len(ene)), np.complex128, order="F")
+        ai, bi = _f(a_inf, np.float64), _f(b_inf, np.float64)
+        eta = complex(eta)
+        _lib.check(self._L.rsrec_bgreen(self._h, _p(a_b), _p(b_b), a_b.shape[2], _p(ene), len(ene), ie_start, ie_len,
+                                        _p(ai), _p(bi), eta.real, eta.imag, int(self.sym_term), _p(g)))
+        return g
+
+    def block_green(self):
+        a_b, b_b = _f(self.recursion.a_b, np.complex128), _f(self.recursion.b2_b, np.complex128)
+        ll, na = a_b.shape[2], a_b.shape[3]
+        ene = self.ene
+        self.g0 = np.zeros((NB, NB, len(ene), na), np.complex128, order="F")
+        _lib.check(self._L.rsrec_block_green(self._h, _p(a_b), _p(b_b), na, ll, _p(ene), len(ene), int(self.sym_term),
+                                             _p(self.g0)))
+        return self.g0
+
+    def chebyshev_green(self):
+        mu = _f(self.recursion.mu_n, np.complex128)
+        nk, na = mu.shape[2], mu.shape[3]
+        ene = self.ene
+        self.recursion.mu_ng = np.zeros_like(mu, order="F")
+        self.g0 = np.zeros((NB, NB, len(ene), na), np.complex128, order="F")
+        _lib.check(self._L.rsrec_chebyshev_green(self._h, _p(mu), na, (nk - 2) // 2, _p(ene), len(ene),
+                                                 self.en.energy_min, self.en.energy_max, _p(self.recursion.mu_ng),
+                                                 _p(self.g0)))
+        return self.g0
+
+    def sgreen(self, dw_l, cshi, nmdir: int = 1):
+        """dw_l, cshi (18,na): potential parameters sqrt(Delta) and the band-centre shift of each atom
+        (density_of_states.f90:300-304)."""
+        a, b2 = _f(self.recursion.a, np.float64), _f(self.recursion.b2, np.float64)
+        lld, na = a.shape[0], a.shape[2]
+        ene = self.ene
+        dw, cs = _f(dw_l, np.float64), _f(cshi, np.float64)
+        self.g0 = np.zeros((NB, NB, len(ene), na), np.complex128, order="F")
+        _lib.check(self._L.rsrec_sgreen(self._h, _p(a), _p(b2), lld, na, nmdir, _p(ene), len(ene), _p(dw), _p(cs),
+                                        _p(self.g0)))
+        return self.g0
+
+
+class Dos(_Consumer):
+    def density_all(self, dw_l, cshi, nmdir: int = 1):
+        """tdens (18,nv,na,nmdir) for every atom and direction in one launch set."""
+        a, b2 = _f(self.recursion.a, np.float64), _f(self.recursion.b2, np.float64)
+        lld, na = a.shape[0], a.shape[2]
+        ene = self.ene
+        dw, cs = _f(dw_l, np.float64), _f(cshi, np.float64)
+        td = np.zeros((NB, len(ene), na, nmdir), order="F")
+        _lib.check(self._L.rsrec_density(self._h, _p(a), _p(b2), lld, na, nmdir, _p(ene), len(ene), _p(dw), _p(cs),
+                                         _p(td)))
+        return td
+
+    def density(self, ia, mdir, dw_l, cshi):
+        """dos%density(tdens, ia, mdir): one atom (1-based local index), one direction; dw_l, cshi (18)."""
+        a = _f(self.recursion.a[:, :, ia - 1:ia, mdir - 1:mdir], np.float64)
+        b2 = _f(self.recursion.b2[:, :, ia - 1:ia, mdir - 1:mdir], np.float64)
+        ene = self.ene
+        dw, cs = _f(np.reshape(dw_l, (NB, 1)), np.float64), _f(np.reshape(cshi, (NB, 1)), np.float64)
+        td = np.zeros((NB, len(ene)), order="F")
+        _lib.check(self._L.rsrec_density(self._h, _p(a), _p(b2), a.shape[0], 1, 1, _p(ene), len(ene), _p(dw), _p(cs),
+                                         _p(td)))
+        return td
+
+    def bpopt(self, a, rb):
+        """batched bpopt: a, rb (ll,nchains) -> ainf, rbinf, ifail (nchains)."""
+        a, rb = _f(a, np.float64), _f(rb, np.float64)
+        if a.ndim == 1:
+            a, rb = a.reshape(-1, 1, order="F"), rb.reshape(-1, 1, order="F")
+        n = a.shape[1]
+        ainf, rbinf, ifail = np.zeros(n), np.zeros(n), np.zeros(n, np.int32)
+        _lib.check(self._L.rsrec_bpopt(self._h, n, a.shape[0], _p(a), _p(rb), _p(ainf), _p(rbinf), _p(ifail)))
+        return ainf, rbinf, ifail
+
+
+class Conductivity(_Consumer):
+    def calculate_conductivity_tensor(self):
+        """Gamma_nm contracted with the diagonal of mu_nm_stochastic: the energy integrand of
+        conductivity.f90:267-290 (the Simpson integration and file output stay with the host program)."""
+        mu = _f(self.recursion.mu_nm_stochastic, np.complex128)
+        M, nloop = mu.shape[2], mu.shape[4]
+        ene = self.ene
+        per_type = self.control.cond_calctype == "per_type"
+        self.integrand = np.zeros((NB, len(ene)), np.complex128, order="F")
+        self.integrand_at = np.zeros((NB, len(ene), nloop), np.complex128, order="F")
+        _lib.check(self._L.rsrec_conductivity_integrand(self._h, _p(mu), M, nloop, _p(ene), len(ene), self.en.energy_min,
+                                                        self.en.energy_max, int(per_type), _p(self.integrand),
+                                                        _p(self.integrand_at)))
+        return self.integrand, self.integrand_at

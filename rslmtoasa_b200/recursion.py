@@ -41,6 +41,18 @@ class Energy:
     """`&energy energy_min, energy_max` (reference energy.f90); defines the Chebyshev scale a and shift b."""
     energy_min: float = -1.5
     energy_max: float = 1.5
+    channels_ldos: int = 2500
+    fermi: float = 0.0
+    ene: object = None
+
+    def e_mesh(self):
+        """energy%e_mesh (energy.f90:175-208): channels_ldos+10 points from energy_min with a step that hits fermi."""
+        if self.channels_ldos % 2 != 0:
+            self.channels_ldos -= 1
+        edel = (self.energy_max - self.energy_min) / self.channels_ldos
+        edel = (self.fermi - self.energy_min) / np.rint((self.fermi - self.energy_min) / edel)
+        self.ene = self.energy_min + edel * np.arange(self.channels_ldos + 10, dtype=np.float64)
+        return self.ene
 
     def scale_shift(self):
         # recursion.f90:3078-3079

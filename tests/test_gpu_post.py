@@ -1,0 +1,193 @@
+"""Parity of the device-side consumers of the recursion results against the CPU oracle, through
+the C ABI: terminator (bit-exact: it is branchy integer-like work on doubles), block / Chebyshev Green functions,
+scalar continued-fraction DOS, Kubo-Bastin integrand (floating point, tolerances below, relative to the largest entry).
+"""
+import numpy as np
+import pytest
+
+from tests.cases import case, relerr, EMIN, EMAX
+
+pytestmark = pytest.mark.gpu
+
+TOL_G = 1e-10      # Green functions: 20 levels of 18x18 inversions; measured ~1e-13
+TOL_SUM = 1e-12    # plain weighted sums (chebyshev_green, conductivity integrand)
+
+
+def _rec(lat, ham, **kw):
+    from rslmtoasa_b200 import Recursion, Control, Energy
+    ctl = Control(**{k: v for k, v in kw.items() if k in ("lld", "cond_ll", "cond_calctype", "random_vec_num")})
+    en = Energy(EMIN, EMAX, channels_ldos=kw.get("channels", 160), fermi=kw.get("fermi", 0.05))
+    extra = {k: v for k, v in kw.items() if k in ("ijpair", "atlist", "phases")}
+    return Recursion(ham, lat, ctl, en, **extra)
+
+
+@pytest.fixture(scope="module")
+def block_rec():
+    """recur_b + zsqr on the GPU for 4 units of the layered fcc case, lld = 9."""
+    lat, ham = case("surface")
+    rec = _rec(lat, ham, lld=9)
+    rec.recur_b()
+    rec.zsqr()
+    return rec
+
+
+def test_e_mesh_is_the_reference_rule(oracle_mod):
+    from rslmtoasa_b200 import Energy
+    en = Energy(-1.2, 1.0, channels_ldos=161, fermi=0.05)
+    assert np.array_equal(en.e_mesh(), oracle_mod.e_mesh(-1.2, 1.0, 161, 0.05)) and en.channels_ldos == 160
+
+
+def test_bpopt_bit_exact(oracle_mod, block_rec):
+    from rslmtoasa_b200 import Dos
+    rng = np.random.default_rng(11)
+    ll, n = 14, 200
+    a = 0.1 + 0.3 * rng.normal(size=(ll, n))
+    rb = 0.3 + 0.1 * rng.normal(size=(ll, n))          # some negative / tiny entries on purpose
+    a[:, 0], rb[:, 0] = 0.3, 0.25                        # constant chain
+    a[:, 1], rb[:, 1] = 0.0, 0.0                         # dead chain (off-diagonal block entries look like this)
+    ainf, rbinf, ifail = Dos(block_rec).bpopt(a, rb)
+    for c in range(n):
+        oa, ob, of = oracle_mod.bpopt(a[:, c], rb[:, c])
+        assert (ainf[c] == oa or (np.isnan(ainf[c]) and np.isnan(oa))) and (rbinf[c] == ob or np.isnan(ob)), c
+        assert ifail[c] == of
+
+
+def test_get_terminf_bit_exact(oracle_mod, block_rec):
+    from rslmtoasa_b200 import Green
+    a_inf, b_inf, a0, b0 = Green(block_rec).get_terminf()
+    oa, ob, oa0, ob0 = oracle_mod.get_terminf(block_rec.a_b, block_rec.b2_b)
+    assert np.array_equal(a_inf, oa) and np.array_equal(b_inf, ob)
+    assert np.array_equal(a0, oa0) and np.array_equal(b0, ob0)
+
+
+@pytest.mark.parametrize("sym_term", [False, True])
+@pytest.mark.parametrize("eta", [0.0, 0.02j])
+def test_bgreen(oracle_mod, block_rec, sym_term, eta):
+    from rslmtoasa_b200 import Green
+    g = Green(block_rec, sym_term=sym_term)
+    a_inf, b_inf, _, _ = g.get_terminf()
+    ene = g.ene
+    for ia in (1, 3):
+        got = g.bgreen(ia, 1, len(ene), a_inf[..., ia - 1], b_inf[..., ia - 1], eta)
+        ref = oracle_mod.bgreen(block_rec.a_b[..., ia - 1], block_rec.b2_b[..., ia - 1], ene, a_inf[..., ia - 1],
+                                b_inf[..., ia - 1], eta, sym_term)
+        assert relerr(got, ref) < TOL_G
+
+
+def test_bgreen_channel_window(oracle_mod, block_rec):
+    from rslmtoasa_b200 import Green
+    g = Green(block_rec)
+    a_inf, b_inf, _, _ = g.get_terminf()
+    full = g.bgreen(2, 1, len(g.ene), a_inf[..., 1], b_inf[..., 1])
+    one = g.bgreen(2, 40, 3, a_inf[..., 1], b_inf[..., 1])
+    assert np.array_equal(one[:, :, 39:42], full[:, :, 39:42])
+    assert not one[:, :, :39].any() and not one[:, :, 42:].any()
+    empty = g.bgreen(2, 5, 0, a_inf[..., 1], b_inf[..., 1])
+    assert not empty.any()
+
+
+@pytest.mark.parametrize("sym_term", [False, True])
+def test_block_green(oracle_mod, block_rec, sym_term):
+    from rslmtoasa_b200 import Green
+    g = Green(block_rec, sym_term=sym_term)
+    g0 = g.block_green()
+    ref = oracle_mod.block_green(block_rec.a_b, block_rec.b2_b, g.ene, sym_term)
+    assert g0.shape == ref.shape == (18, 18, 170, 4)
+    assert relerr(g0, ref) < TOL_G
+    d = np.arange(18)
+    assert (-g0[d, d].imag.sum(0)).min() > -1e-8          # Herglotz: non-negative LDOS
+
+
+def test_block_green_odd_sizes(oracle_mod):
+    """mesh lengths that do not fill the last CTA, a single unit, the shortest chain the terminator accepts"""
+    from rslmtoasa_b200 import Green
+    lat, ham = case("tiny")
+    for lld, channels in ((2, 2), (3, 14), (5, 36)):
+        rec = _rec(lat, ham, lld=lld, channels=channels, fermi=-0.3)
+        rec.recur_b()
+        rec.zsqr()
+        g = Green(rec)
+        g0 = g.block_green()
+        ref = oracle_mod.block_green(rec.a_b, rec.b2_b, g.ene)
+        both_nan = np.isnan(g0) & np.isnan(ref)
+        assert relerr(np.where(both_nan, 0, g0), np.where(both_nan, 0, ref)) < TOL_G
+
+
+@pytest.mark.parametrize("name,lld", [("bulk", 12), ("pbc", 30)])
+def test_chebyshev_green(oracle_mod, name, lld):
+    from rslmtoasa_b200 import Green
+    lat, ham = case(name)
+    rec = _rec(lat, ham, lld=lld, channels=211)
+    rec.chebyshev_recur()
+    g = Green(rec)
+    g0 = g.chebyshev_green()
+    mu_ng, ref = oracle_mod.chebyshev_green(rec.mu_n, g.ene, EMIN, EMAX)
+    assert relerr(g0, ref) < TOL_SUM
+    assert relerr(rec.mu_ng, mu_ng) < 1e-15
+
+
+def _scalar_rec():
+    from rslmtoasa_b200 import synthetic as S
+    lat, _ = case("bulk")
+    lat.irec = np.array([1, 2, 5], dtype=np.int32)
+    ham1 = S.make_hamiltonian(lat, seed=20260101, spin_orbit=False)
+    rec = _rec(lat, ham1, lld=10)
+    rec.recur()
+    return rec
+
+
+def test_density_and_sgreen(oracle_mod):
+    from rslmtoasa_b200 import Green, Dos
+    rec = _scalar_rec()
+    rng = np.random.default_rng(8)
+    dw = 1.0 + 0.05 * rng.normal(size=(18, 3))
+    cs = 0.02 * rng.normal(size=(18, 3))
+    dos = Dos(rec)
+    ene = dos.ene
+    for ia in (1, 3):
+        td = dos.density(ia, 1, dw[:, ia - 1], cs[:, ia - 1])
+        ref = oracle_mod.density(rec.a[:, :, ia - 1, 0], rec.b2[:, :, ia - 1, 0], ene, dw[:, ia - 1], cs[:, ia - 1])
+        assert relerr(td, ref) < 1e-13
+    g0 = Green(rec).sgreen(dw, cs, 1)
+    assert relerr(g0, oracle_mod.sgreen(rec.a, rec.b2, 1, ene, dw, cs)) < 1e-13
+    # three quantisation directions (non-collinear scalar path, green.f90:688-699)
+    rec.a[..., 1], rec.b2[..., 1] = rec.a[..., 0] * 1.01, rec.b2[..., 0]
+    rec.a[..., 2], rec.b2[..., 2] = rec.a[..., 0] * 0.99, rec.b2[..., 0]
+    g3 = Green(rec).sgreen(dw, cs, 3)
+    assert relerr(g3, oracle_mod.sgreen(rec.a, rec.b2, 3, ene, dw, cs)) < 1e-13
+    td_all = dos.density_all(dw, cs, 3)
+    assert td_all.shape == (18, len(ene), 3, 3)
+    assert relerr(td_all[:, :, 1, 2], oracle_mod.density(rec.a[:, :, 1, 2], rec.b2[:, :, 1, 2], ene, dw[:, 1], cs[:, 1])) < 1e-13
+
+
+@pytest.mark.parametrize("calctype,M", [("per_type", 7), ("random_vec", 24)])
+def test_conductivity_integrand(oracle_mod, calctype, M):
+    from rslmtoasa_b200 import Conductivity
+    lat, ham = case("pbc")
+    rng = np.random.default_rng(5)
+    kw = dict(cond_ll=M, cond_calctype=calctype, channels=60, fermi=0.0)
+    if calctype == "per_type":
+        rec = _rec(lat, ham, atlist=np.array([1, 2], np.int32), **kw)
+    else:
+        rec = _rec(lat, ham, phases=rng.random((lat.kk, 3)), random_vec_num=3, **kw)
+    rec.compute_moments_stochastic()
+    cond = Conductivity(rec)
+    integ, integ_at = cond.calculate_conductivity_tensor()
+    ri, rat = oracle_mod.conductivity_integrand(rec.mu_nm_stochastic, cond.ene, EMIN, EMAX, calctype == "per_type")
+    # the 10 extra mesh points of e_mesh lie beyond |w| = 1 on this coarse mesh: acos -> NaN on both sides
+    nan = np.isnan(ri)
+    assert np.array_equal(np.isnan(integ), nan) and 0 < nan.sum() < nan.size / 2
+    assert relerr(np.nan_to_num(integ), np.nan_to_num(ri)) < TOL_SUM
+    assert relerr(np.nan_to_num(integ_at), np.nan_to_num(rat)) < TOL_SUM
+    if calctype == "random_vec":
+        assert not np.nan_to_num(integ_at).any()
+
+
+def test_post_argument_errors(block_rec):
+    from rslmtoasa_b200 import Green, RsrecError
+    g = Green(block_rec)
+    a_inf, b_inf, _, _ = g.get_terminf()
+    with pytest.raises(RsrecError):
+        g.bgreen(1, 0, 3, a_inf[..., 0], b_inf[..., 0])          # channels are 1-based
+    with pytest.raises(RsrecError):
+        g.bgreen(1, 169, 3, a_inf[..., 0], b_inf[..., 0])        # window runs past the mesh
