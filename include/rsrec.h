@@ -138,6 +138,25 @@ int rsrec_conductivity_integrand(rsrec_handle h, const rsrec_cplx *mu_nm, int M,
                                  double energy_min, double energy_max, int per_type, rsrec_cplx *integrand,
                                  rsrec_cplx *integrand_at);
 
+/* ---- fused entry points: a recursion and its consumer with the coefficients staying on the device ---- */
+
+/* run_recursion + run_dos of the block path (self.f90:799-856): recur_b -> zsqr -> get_terminf -> bgreen(eta=0).
+ * a_b, b2_b (18,18,lld,nunits), b2_b = B^2 as recur_b leaves it (either may be NULL); g0 (18,18,nv,nunits). */
+int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, const double *ene, int nv,
+                        int sym_term, rsrec_cplx *a_b, rsrec_cplx *b2_b, rsrec_cplx *g0);
+
+/* chebyshev_recur (recursion.f90:3057-3130) + chebyshev_green (green.f90:1030-1108); mu_n, mu_ng may be NULL. */
+int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, double energy_min,
+                           double energy_max, const double *ene, int nv, rsrec_cplx *mu_n, rsrec_cplx *mu_ng,
+                           rsrec_cplx *g0);
+
+/* compute_moments_stochastic + calculate_gamma_nm + integrand of calculate_conductivity_tensor: only the diagonals
+ * mu_nm(l,l,n,m,i) the integrand consumes are kept, on the device; mu_nm (18,18,M,M,nstart) is downloaded only when
+ * non-NULL.  start_kind 0 = per_type (integrand_at filled), 1 = random_vec. */
+int rsrec_kubo_conductivity(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites,
+                            const double *phases, int M, double energy_min, double energy_max, const double *ene,
+                            int nv, rsrec_cplx *mu_nm, rsrec_cplx *integrand, rsrec_cplx *integrand_at);
+
 /* ---- device-resident stepping (what bench.py times as `value`; the calls above are the `e2e` path) ----
  * begin: upload start vectors, compute mu(1), mu(2) on the device.  run_steps: enqueue n chebyshev_recur_ll steps on
  * the handle's stream without host synchronisation.  end: wait, download mu_n(18,18,2*lld+2,nvec). */

@@ -16,7 +16,8 @@ SYMBOLS = [
     "rsrec_cheb_end", "rsrec_synchronize", "rsrec_stream", "rsrec_launch_count", "rsrec_set_kernel_family",
     "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read",
     "rsrec_bpopt", "rsrec_get_terminf", "rsrec_bgreen", "rsrec_block_green", "rsrec_chebyshev_green", "rsrec_density",
-    "rsrec_sgreen", "rsrec_conductivity_integrand",
+    "rsrec_sgreen", "rsrec_conductivity_integrand", "rsrec_recur_b_green", "rsrec_cheb_recur_green",
+    "rsrec_kubo_conductivity",
 ]
 
 
@@ -76,6 +77,9 @@ def load():
     L.rsrec_density.argtypes = [vp, vp, vp, i, i, i, vp, i, vp, vp, vp]
     L.rsrec_sgreen.argtypes = [vp, vp, vp, i, i, i, vp, i, vp, vp, vp]
     L.rsrec_conductivity_integrand.argtypes = [vp, vp, i, i, vp, i, d, d, i, vp, vp]
+    L.rsrec_recur_b_green.argtypes = [vp, i, vp, i, vp, i, i, vp, vp, vp]
+    L.rsrec_cheb_recur_green.argtypes = [vp, i, vp, i, d, d, vp, i, vp, vp, vp]
+    L.rsrec_kubo_conductivity.argtypes = [vp, i, i, vp, vp, i, d, d, vp, i, vp, vp, vp]
     _lib = L
     return L
 

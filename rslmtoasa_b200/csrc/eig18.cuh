@@ -15,6 +15,22 @@ struct Eig18Smem {
   double tot;
 };
 
+// Sum of one value per thread over the 324-thread CTA in a fixed order (run-to-run reproducible, unlike atomics):
+// 32 strided partial sums, then a shuffle tree in warp 0.  Uses s.Tr as scratch; result also left in s.tot.
+__device__ __forceinline__ double eig18_block_sum(Eig18Smem &s, double v) {
+  const int tid = threadIdx.x;
+  s.Tr[tid] = v;
+  __syncthreads();
+  if (tid < 32) {
+    double a = 0.0;
+    for (int k = tid; k < BLKC; k += 32) a += s.Tr[k];
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (tid == 0) s.tot = a;
+  }
+  __syncthreads();
+  return s.tot;
+}
+
 // A (Hermitian, upper triangle trusted like zheev 'U') -> eigenvalues s.ev, eigenvectors s.V (columns).
 __device__ void eig18_jacobi(Eig18Smem &s) {
   const int tid = threadIdx.x, r = tid % NB, c = tid / NB;
@@ -26,10 +42,8 @@ __device__ void eig18_jacobi(Eig18Smem &s) {
   __syncthreads();
   s.Ar[tid] = ar; s.Ai[tid] = ai;
   s.Vr[tid] = (r == c) ? 1.0 : 0.0; s.Vi[tid] = 0.0;
-  if (tid == 0) s.tot = 0.0;
   __syncthreads();
-  atomicAdd(&s.tot, ar * ar + ai * ai);
-  __syncthreads();
+  eig18_block_sum(s, ar * ar + ai * ai);
   // |a_ij|^2 <= 1e-40 ||A||_F^2: off-diagonal elements perturb eigenvalues at second order (~1e-40 ||A||),
   // far below double precision; Jacobi converges quadratically so this saves about one sweep over 1e-64.
   const double thresh = 1e-40 * s.tot;
@@ -107,11 +121,8 @@ __device__ bool sqrt18_newton_schulz(Eig18Smem &s, double *B, double *Bi) {
   double ar = s.Ar[tid], ai = s.Ai[tid];
   if (r > c) { ar = s.Ar[c + NB * r]; ai = -s.Ai[c + NB * r]; }  // trust the upper triangle like zheev('U')
   if (r == c) ai = 0.0;
-  if (tid == 0) s.tot = 0.0;
   __syncthreads();
-  atomicAdd(&s.tot, ar * ar + ai * ai);
-  __syncthreads();
-  const double scale = sqrt(s.tot);
+  const double scale = sqrt(eig18_block_sum(s, ar * ar + ai * ai));
   if (!(scale > 0.0) || !(scale < 1e300)) return false;
   __syncthreads();
   // Y in (Ar,Ai), Z in (Vr,Vi)

@@ -84,6 +84,7 @@ struct rsrec_handle_s {
 };
 typedef rsrec_handle_s H;
 static int post_configure();
+static int grid_for(size_t n, int threads, int cap);
 
 // ------------------------------------------------------------------------------------------------------------
 static int dev_alloc(DevBuf &b, size_t n, bool zero) {
@@ -519,8 +520,8 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     }
     CUDA_TRY(cudaGetLastError());
   }
-  CUDA_TRY(cudaMemcpyAsync(a_host, h->ahist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double));
-  CUDA_TRY(cudaMemcpyAsync(b2_host, h->b2hist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double));
+  if (a_host) { CUDA_TRY(cudaMemcpyAsync(a_host, h->ahist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double)); }
+  if (b2_host) { CUDA_TRY(cudaMemcpyAsync(b2_host, h->b2hist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double)); }
   CUDA_TRY(cudaStreamSynchronize(h->st));
   return RSREC_OK;
 }
@@ -893,9 +894,11 @@ int rsrec_velo_vec_matmul(rsrec_handle h, int slot, const cplx *psi_in, cplx *ps
 
 // compute_moments_stochastic (recursion.f90:1105-1230): left vectors T_m|r> are stored (like the reference's
 // left_vec), the right chain v_a T_n v_b |r> is contracted against all of them after every step.
-int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
-                       int M, double a, double b, cplx *mu_nm) {
-  if (!h || nstart < 0 || M < 1 || !mu_nm || a == 0.0) return fail(RSREC_EINVAL, "rsrec_kubo_moments: bad argument");
+// mu_nm (host, may be null): every start's moments are downloaded; d_diag (device, may be null): D[t][n][m][l2], the
+// diagonals calculate_conductivity_tensor consumes, are kept on the device instead.
+static int kubo_moments_impl(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
+                             int M, double a, double b, cplx *mu_nm, double *d_diag) {
+  if (!h || nstart < 0 || M < 1 || (!mu_nm && !d_diag) || a == 0.0) return fail(RSREC_EINVAL, "rsrec_kubo_moments: bad argument");
   if (start_kind == 0 ? !start_sites : !phases) return fail(RSREC_EINVAL, "rsrec_kubo_moments: missing start data");
   if (!h->have_op[0] || !h->have_op[1]) return fail(RSREC_EINVAL, "rsrec_set_operator must be called for slots 'a' and 'b'");
   if (nstart == 0) return RSREC_OK;
@@ -968,10 +971,21 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
         TRY(launch_reduce(h, M, nctas, 0, h->mu.p + (size_t)n * BLKD, nullptr, (size_t)M * BLKD, nullptr, nullptr));
       }
     }
-    CUDA_TRY(cudaMemcpyAsync(mu_nm + (size_t)s * M * M * BLKC, h->mu.p, (size_t)M * M * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)M * M * BLKD * sizeof(double));
+    if (d_diag) {
+      k_cond_diag<<<grid_for((size_t)M * M * NB, 256, h->sms * 16), 256, 0, h->st>>>((const double2 *)h->mu.p, M, (size_t)M * M,
+                                                                                  (double2 *)d_diag + (size_t)s * M * M * NB);
+      h->launches++;
+    }
+    if (mu_nm) { CUDA_TRY(cudaMemcpyAsync(mu_nm + (size_t)s * M * M * BLKC, h->mu.p, (size_t)M * M * BLKD * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)M * M * BLKD * sizeof(double)); }
     CUDA_TRY(cudaStreamSynchronize(h->st));
   }
   return RSREC_OK;
+}
+
+int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
+                       int M, double a, double b, cplx *mu_nm) {
+  if (!mu_nm) return fail(RSREC_EINVAL, "rsrec_kubo_moments: bad argument");
+  return kubo_moments_impl(h, nstart, start_kind, start_sites, phases, M, a, b, mu_nm, nullptr);
 }
 
 }  // extern "C"
@@ -1074,8 +1088,9 @@ static int d_density(H *h, const double *d_a, const double *d_b2, int lld, int n
 }
 // calculate_gamma_nm + the integrand of calculate_conductivity_tensor (conductivity.f90:158-306).
 // d_mu: (18,18,M,M,nloop) device moments; outputs on the host.
-static int d_cond_integrand(H *h, const double *d_mu, int M, int nloop, const double *ene, int nv, double emin, double emax,
-                            int per_type, cplx *integrand, cplx *integrand_at) {
+// d_mu: (18,18,M,M,nloop) device moments, or null when d_diag_in already holds D[t][n][m][l2].
+static int d_cond_integrand(H *h, const double *d_mu, const double *d_diag_in, int M, int nloop, const double *ene, int nv,
+                            double emin, double emax, int per_type, cplx *integrand, cplx *integrand_at) {
   const double a = (emax - emin) / (2 - 0.3), b = (emax + emin) / 2, de = emax - emin;
   const double factor = 16 / (PI_RP * (de * de));
   std::vector<double> sk;
@@ -1088,16 +1103,17 @@ static int d_cond_integrand(H *h, const double *d_mu, int M, int nloop, const do
   TRY(dev_alloc(h->post[2], 2 * nvM, false));  // CN
   TRY(dev_alloc(h->post[3], 2 * nvM, false));  // CM
   TRY(dev_alloc(h->post[4], nvM + nv, false)); // TS, inv
-  TRY(dev_alloc(h->post[5], 2 * (size_t)nloop * M * M * NB, false));             // D
+  if (d_mu) TRY(dev_alloc(h->post[5], 2 * (size_t)nloop * M * M * NB, false));   // D
+  const double *d_D = d_mu ? h->post[5].p : d_diag_in;
   TRY(dev_alloc(h->post[6], 2 * (size_t)nloop * nchunk * NB * nv, false));      // partials
   TRY(dev_alloc(h->post[7], 2 * (size_t)NB * nv * (1 + nloop), false));          // integrand, integrand_at
   double *TS = h->post[4].p, *inv = TS + nvM;
   double *d_int = h->post[7].p, *d_at = d_int + 2 * (size_t)NB * nv;
   k_cond_tables<<<(nv + 127) / 128, 128, 0, h->st>>>(h->post[0].p, nv, M, a, b, h->post[1].p, (double2 *)h->post[2].p, (double2 *)h->post[3].p, TS, inv);
   const size_t nblocks = (size_t)nloop * M * M;
-  k_cond_diag<<<grid_for(nblocks * NB, 256, h->sms * 16), 256, 0, h->st>>>((const double2 *)d_mu, M, nblocks, (double2 *)h->post[5].p);
+  if (d_mu) k_cond_diag<<<grid_for(nblocks * NB, 256, h->sms * 16), 256, 0, h->st>>>((const double2 *)d_mu, M, nblocks, (double2 *)h->post[5].p);
   k_cond_contract<<<dim3((nv + CD_THREADS - 1) / CD_THREADS, nchunk, nloop), CD_THREADS, 0, h->st>>>(
-      (const double2 *)h->post[2].p, (const double2 *)h->post[3].p, TS, (const double2 *)h->post[5].p, nv, M, nchunk, (double2 *)h->post[6].p);
+      (const double2 *)h->post[2].p, (const double2 *)h->post[3].p, TS, (const double2 *)d_D, nv, M, nchunk, (double2 *)h->post[6].p);
   k_cond_finish<<<(NB * nv + 127) / 128, 128, 0, h->st>>>((const double2 *)h->post[6].p, inv, nv, nchunk, nloop, factor, (double2 *)d_int,
                                                          per_type ? (double2 *)d_at : nullptr);
   h->launches += 4;
@@ -1264,7 +1280,86 @@ int rsrec_conductivity_integrand(rsrec_handle h, const cplx *mu_nm, int M, int n
     return fail(RSREC_EINVAL, "rsrec_conductivity_integrand: bad argument");
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(to_dev(h, h->post[9], mu_nm, (size_t)nloop * M * M * BLKD));
-  return d_cond_integrand(h, h->post[9].p, M, nloop, ene, nv, energy_min, energy_max, per_type, integrand, integrand_at);
+  return d_cond_integrand(h, h->post[9].p, nullptr, M, nloop, ene, nv, energy_min, energy_max, per_type, integrand, integrand_at);
+}
+
+// ---- fused entry points: recursion + its consumer without a host round trip of the coefficients -----------------
+// run_recursion + run_dos of the block path (self.f90:799-856): recur_b -> zsqr -> get_terminf -> bgreen.
+// a_b, b2_b (18,18,lld,nunits; b2_b = B^2 as recur_b leaves it; either may be NULL), g0 (18,18,nv,nunits).
+int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, const double *ene, int nv, int sym_term,
+                        cplx *a_b, cplx *b2_b, cplx *g0) {
+  if (!h || nunits < 0 || lld < 2 || nv < 1 || !ene || !g0 || (nunits > 0 && !site_i)) return fail(RSREC_EINVAL, "rsrec_recur_b_green: bad argument (need lld >= 2)");
+  if (nunits == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  TRY(to_dev(h, h->post[4], ene, nv));
+  const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
+  const size_t hs = (size_t)lld * BLKD;
+  for (int u0 = 0; u0 < nunits; u0 += ub) {
+    const int n = std::min(ub, nunits - u0);
+    TRY(upload_units(h, n, site_i + u0, nullptr, nullptr, nullptr));
+    TRY(plan_build(h, n, site_i + u0, nullptr));
+    TRY(lanczos_batch(h, n, lld, false, a_b ? (double *)(a_b + (size_t)u0 * lld * BLKC) : nullptr,
+                      b2_b ? (double *)(b2_b + (size_t)u0 * lld * BLKC) : nullptr));
+    // zsqr on the device copy of the B^2 history, then the terminator and the continued fraction
+    TRY(dev_alloc(h->post[1], (size_t)n * hs, false));
+    CUDA_TRY(cudaMemcpyAsync(h->post[1].p, h->b2hist.p, (size_t)n * hs * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    k_zsqr<<<(unsigned)((size_t)n * lld), BLKC, 0, h->st>>>(h->post[1].p);
+    h->launches++;
+    TRY(dev_alloc(h->post[2], 2 * (size_t)n * (BLKC + 1), false));
+    TRY(dev_alloc(h->post[5], (size_t)n * nv * BLKD, false));
+    double *d_ai = h->post[2].p, *d_bi = d_ai + (size_t)n * BLKC, *d_a0 = d_bi + (size_t)n * BLKC, *d_b0 = d_a0 + n;
+    TRY(d_terminf(h, h->ahist.p, h->post[1].p, n, lld, d_ai, d_bi, d_a0, d_b0));
+    TRY(d_bgreen(h, h->ahist.p, h->post[1].p, lld, n, h->post[4].p, nv, 0, nv, d_ai, d_bi, 0.0, 0.0, sym_term, h->post[5].p));
+    TRY(to_host(h, g0 + (size_t)u0 * nv * BLKC, h->post[5].p, (size_t)n * nv * BLKD));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+  }
+  return RSREC_OK;
+}
+
+// chebyshev_recur + chebyshev_green (recursion.f90:3057-3130 + green.f90:1030-1108): mu_n, mu_ng may be NULL.
+int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, double energy_min, double energy_max,
+                           const double *ene, int nv, cplx *mu_n, cplx *mu_ng, cplx *g0) {
+  if (!h || nunits < 0 || lld < 0 || nv < 1 || !ene || !g0 || energy_max == energy_min || (nunits > 0 && !site_i))
+    return fail(RSREC_EINVAL, "rsrec_cheb_recur_green: bad argument");
+  if (nunits == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  TRY(to_dev(h, h->post[4], ene, nv));
+  const double a = (energy_max - energy_min) / (2 - 0.3), b = (energy_max + energy_min) / 2;  // recursion.f90:3078-3079
+  const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
+  const size_t ms = (size_t)(2 * lld + 2) * BLKD;
+  std::vector<cplx> mu_tmp;
+  int rc_all = RSREC_OK;
+  for (int u0 = 0; u0 < nunits; u0 += ub) {
+    const int n = std::min(ub, nunits - u0);
+    TRY(rsrec_cheb_begin_sites(h, n, site_i + u0, nullptr, nullptr, nullptr, lld, a, b));
+    TRY(cheb_steps(h, lld));
+    cplx *mu_out = mu_n ? mu_n + (size_t)u0 * (2 * lld + 2) * BLKC : nullptr;
+    if (!mu_out) { mu_tmp.resize((size_t)n * (2 * lld + 2) * BLKC); mu_out = mu_tmp.data(); }  // the divergence guard reads them
+    int rc = cheb_finish(h, mu_out);
+    if (rc == RSREC_EDIVERGED) rc_all = rc; else TRY(rc);
+    TRY(dev_alloc(h->post[1], (size_t)n * ms, false));
+    TRY(dev_alloc(h->post[5], (size_t)n * nv * BLKD, false));
+    TRY(d_cheb_green(h, h->mu.p, n, lld, h->post[4].p, nv, energy_min, energy_max, h->post[1].p, h->post[5].p));
+    if (mu_ng) TRY(to_host(h, mu_ng + (size_t)u0 * (2 * lld + 2) * BLKC, h->post[1].p, (size_t)n * ms));
+    TRY(to_host(h, g0 + (size_t)u0 * nv * BLKC, h->post[5].p, (size_t)n * nv * BLKD));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+  }
+  return rc_all;
+}
+
+// compute_moments_stochastic + calculate_gamma_nm + the integrand of calculate_conductivity_tensor: only the 18
+// diagonals of every mu_nm block are kept (on the device); mu_nm (18,18,M,M,nstart) is downloaded only if non-NULL.
+int rsrec_kubo_conductivity(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites, const double *phases, int M,
+                            double energy_min, double energy_max, const double *ene, int nv, cplx *mu_nm, cplx *integrand,
+                            cplx *integrand_at) {
+  if (!h || nstart < 1 || M < 1 || nv < 1 || !ene || !integrand || energy_max == energy_min) return fail(RSREC_EINVAL, "rsrec_kubo_conductivity: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const double a = (energy_max - energy_min) / (2 - 0.3), b = (energy_max + energy_min) / 2;
+  TRY(dev_alloc(h->post[11], 2 * (size_t)nstart * M * M * NB, false));
+  TRY(kubo_moments_impl(h, nstart, start_kind, start_sites, phases, M, a, b, mu_nm, h->post[11].p));
+  return d_cond_integrand(h, nullptr, h->post[11].p, M, nstart, ene, nv, energy_min, energy_max, start_kind == 0, integrand, integrand_at);
 }
 
 }  // extern "C"

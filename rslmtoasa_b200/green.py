@@ -90,6 +90,42 @@ class Green(_Consumer):
                                                  _p(self.g0)))
         return self.g0
 
+    # -- fused: recursion + Green function without a host round trip of the coefficients ------------------------
+    def recur_b_green(self):
+        """run_recursion + run_dos of the block path (self.f90:799-856) in one call: fills recursion.a_b, b2_b (= B^2,
+        as recur_b leaves it), recursion.a, b2 and self.g0."""
+        rec = self.recursion
+        s, e = rec._local_units(len(rec.lattice.irec))
+        sites = np.ascontiguousarray(rec.lattice.irec[s - 1:e], dtype=np.int32)
+        lld, n = self.control.lld, len(sites)
+        ene = self.ene
+        rec.a_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        rec.b2_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        self.g0 = np.zeros((NB, NB, len(ene), n), np.complex128, order="F")
+        _lib.check(self._L.rsrec_recur_b_green(self._h, n, _p(sites), lld, _p(ene), len(ene), int(self.sym_term),
+                                               _p(rec.a_b), _p(rec.b2_b), _p(self.g0)))
+        d = np.arange(NB)
+        rec.a = np.zeros((lld, NB, n, 3), order="F"); rec.b2 = np.zeros((lld, NB, n, 3), order="F")
+        rec.a[:, :, :, 0] = np.real(rec.a_b[d, d]).transpose(1, 0, 2)
+        rec.b2[:, :, :, 0] = np.real(rec.b2_b[d, d]).transpose(1, 0, 2)
+        return self.g0
+
+    def chebyshev_recur_green(self, keep_moments: bool = True):
+        """chebyshev_recur + chebyshev_green in one call."""
+        rec = self.recursion
+        s, e = rec._local_units(len(rec.lattice.irec))
+        sites = np.ascontiguousarray(rec.lattice.irec[s - 1:e], dtype=np.int32)
+        lld, n = self.control.lld, len(sites)
+        ene = self.ene
+        if keep_moments:
+            rec.mu_n = np.zeros((NB, NB, 2 * lld + 2, n), np.complex128, order="F")
+            rec.mu_ng = np.zeros((NB, NB, 2 * lld + 2, n), np.complex128, order="F")
+        self.g0 = np.zeros((NB, NB, len(ene), n), np.complex128, order="F")
+        _lib.check(self._L.rsrec_cheb_recur_green(self._h, n, _p(sites), lld, self.en.energy_min, self.en.energy_max,
+                                                  _p(ene), len(ene), _p(rec.mu_n) if keep_moments else None,
+                                                  _p(rec.mu_ng) if keep_moments else None, _p(self.g0)))
+        return self.g0
+
     def sgreen(self, dw_l, cshi, nmdir: int = 1):
         """dw_l, cshi (18,na): potential parameters sqrt(Delta) and the band-centre shift of each atom
         (density_of_states.f90:300-304)."""
@@ -150,4 +186,27 @@ class Conductivity(_Consumer):
         _lib.check(self._L.rsrec_conductivity_integrand(self._h, _p(mu), M, nloop, _p(ene), len(ene), self.en.energy_min,
                                                         self.en.energy_max, int(per_type), _p(self.integrand),
                                                         _p(self.integrand_at)))
+        return self.integrand, self.integrand_at
+
+    def compute_conductivity(self, keep_moments: bool = False):
+        """compute_moments_stochastic + calculate_conductivity_tensor's integrand in one call; only the diagonals of
+        mu_nm_stochastic the integrand consumes are kept (on the device) unless keep_moments is set."""
+        rec = self.recursion
+        M = self.control.cond_ll
+        ene = self.ene
+        per_type = self.control.cond_calctype == "per_type"
+        if per_type:
+            sites = np.ascontiguousarray(rec.atlist, dtype=np.int32)
+            nstart, ph = len(sites), None
+        else:
+            ph = _f(rec.phases, np.float64)
+            nstart, sites = ph.shape[1], None
+        mu = np.zeros((NB, NB, M, M, nstart), np.complex128, order="F") if keep_moments else None
+        self.integrand = np.zeros((NB, len(ene)), np.complex128, order="F")
+        self.integrand_at = np.zeros((NB, len(ene), nstart), np.complex128, order="F")
+        _lib.check(self._L.rsrec_kubo_conductivity(self._h, nstart, 0 if per_type else 1, _p(sites), _p(ph), M,
+                                                   self.en.energy_min, self.en.energy_max, _p(ene), len(ene), _p(mu),
+                                                   _p(self.integrand), _p(self.integrand_at)))
+        if keep_moments:
+            rec.mu_nm_stochastic = mu
         return self.integrand, self.integrand_at

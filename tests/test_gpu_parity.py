@@ -270,3 +270,19 @@ def test_linearity_of_ham_vec_matmul_at_config4_size():
     hx, hy, hxy = rec.ham_vec_matmul(x, 1.0, 0.0), rec.ham_vec_matmul(y, 1.0, 0.0), rec.ham_vec_matmul(x + c * y, 1.0, 0.0)
     assert relerr(hxy, hx + c * hy) < 1e-13
     assert abs(np.vdot(x, hy) - np.vdot(hx, y)) / abs(np.vdot(x, hy)) < 1e-12
+
+
+@pytest.mark.parametrize("family", [0, 1])
+def test_results_are_bitwise_reproducible(family):
+    """every reduction runs in a fixed order (no atomics on the data path): same handle or a fresh one, same bits"""
+    lat, ham = case("impurity_hoh")
+    outs = []
+    for fresh in range(2):
+        rec = _rec(lat, ham, lld=7)
+        rec.set_kernel_family(family)
+        for rep in range(2):
+            rec.recur_b()
+            rec.chebyshev_recur()
+            outs.append((rec.a_b.copy(), rec.b2_b.copy(), rec.mu_n.copy()))
+    for o in outs[1:]:
+        assert all(np.array_equal(x, y) for x, y in zip(o, outs[0]))

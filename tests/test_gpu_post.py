@@ -183,6 +183,60 @@ def test_conductivity_integrand(oracle_mod, calctype, M):
         assert not np.nan_to_num(integ_at).any()
 
 
+def test_fused_recur_b_green_is_the_staged_pipeline(oracle_mod):
+    """recur_b -> zsqr -> block_green through host arrays == the fused device-resident call, bit for bit"""
+    from rslmtoasa_b200 import Green
+    for name in ("surface", "impurity_hoh"):
+        lat, ham = case(name)
+        rec = _rec(lat, ham, lld=8)
+        rec.recur_b()
+        a_b, b2_b = rec.a_b.copy(), rec.b2_b.copy()
+        rec.zsqr()
+        staged = Green(rec).block_green().copy()
+        rec2 = _rec(lat, ham, lld=8)
+        g0 = Green(rec2).recur_b_green()
+        assert np.array_equal(rec2.a_b, a_b) and np.array_equal(rec2.b2_b, b2_b)
+        assert np.array_equal(g0, staged)
+        orc = oracle_mod.Oracle(lat, ham)
+        oa, ob2 = orc.lanczos_block(lat.irec, 8)
+        assert relerr(g0, oracle_mod.block_green(oa, orc.zsqr(ob2), Green(rec2).ene)) < 1e-8   # end to end vs the oracle
+
+
+def test_fused_cheb_recur_green(oracle_mod):
+    from rslmtoasa_b200 import Green
+    lat, ham = case("surface")
+    rec = _rec(lat, ham, lld=10, channels=100)
+    rec.chebyshev_recur()
+    staged = Green(rec).chebyshev_green().copy()
+    rec2 = _rec(lat, ham, lld=10, channels=100)
+    g = Green(rec2)
+    g0 = g.chebyshev_recur_green()
+    assert np.array_equal(rec2.mu_n, rec.mu_n) and np.array_equal(rec2.mu_ng, rec.mu_ng)
+    assert np.array_equal(g0, staged, equal_nan=True) and not np.isnan(g0[:, :, :100]).any()   # mesh tail has |w| > 1
+    assert np.array_equal(g.chebyshev_recur_green(keep_moments=False), staged, equal_nan=True)
+
+
+@pytest.mark.parametrize("calctype", ["per_type", "random_vec"])
+def test_fused_kubo_conductivity(oracle_mod, calctype):
+    from rslmtoasa_b200 import Conductivity
+    lat, ham = case("pbc")
+    kw = dict(cond_ll=9, cond_calctype=calctype, channels=60, fermi=0.0)
+    if calctype == "per_type":
+        rec = _rec(lat, ham, atlist=np.array([2, 1], np.int32), **kw)
+    else:
+        rec = _rec(lat, ham, phases=np.random.default_rng(6).random((lat.kk, 2)), random_vec_num=2, **kw)
+    rec.compute_moments_stochastic()
+    staged, staged_at = (x.copy() for x in Conductivity(rec).calculate_conductivity_tensor())
+    c = Conductivity(rec)
+    integ, integ_at = c.compute_conductivity(keep_moments=True)
+    assert np.array_equal(integ, staged, equal_nan=True) and np.array_equal(integ_at, staged_at, equal_nan=True)
+    assert np.array_equal(c.recursion.mu_nm_stochastic, rec.mu_nm_stochastic)
+    integ2, _ = c.compute_conductivity(keep_moments=False)
+    assert np.array_equal(integ2, staged, equal_nan=True)
+    ri, _ = oracle_mod.conductivity_integrand(rec.mu_nm_stochastic, c.ene, EMIN, EMAX, calctype == "per_type")
+    assert relerr(np.nan_to_num(integ), np.nan_to_num(ri)) < TOL_SUM
+
+
 def test_post_argument_errors(block_rec):
     from rslmtoasa_b200 import Green, RsrecError
     g = Green(block_rec)

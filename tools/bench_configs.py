@@ -11,7 +11,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from rslmtoasa_b200 import Recursion, Control, Energy, synthetic as S  # noqa: E402
+from rslmtoasa_b200 import Recursion, Control, Energy, Green, Dos, Conductivity, synthetic as S  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 EMIN, EMAX = -2.0, 2.0
@@ -75,6 +75,72 @@ def run(name, lat, ham, lld, what, cpu=True, **kw):
     rec.close()
 
 
+def run_post(name, lat, ham, lld, what, channels=2500, cpu=True, **kw):
+    """the consumers either side of the recursion at the reference's mesh size
+    (channels_ldos + 10 energies), host arrays in / host arrays out, CPU oracle beside it."""
+    ctl = Control(lld=lld, **{k: v for k, v in kw.items() if k in ("cond_ll", "cond_calctype")})
+    en = Energy(EMIN, EMAX, channels_ldos=channels, fermi=0.0)
+    rec = Recursion(ham, lat, ctl, en, **{k: v for k, v in kw.items() if k in ("atlist", "phases")})
+    out = {"config": name, "kk": lat.kk, "units": int(len(lat.irec)), "lld": lld, "what": what, "nv": channels + 10}
+    l0 = rec.launch_count
+    if what == "block_green":
+        rec.recur_b(); rec.zsqr()
+        g = Green(rec)
+        t = timed(g.block_green)
+        if cpu:
+            t0 = time.perf_counter(); ref = O.block_green(rec.a_b, rec.b2_b, g.ene); tc = time.perf_counter() - t0
+            out["relerr_g0"] = relerr(g.g0, ref)
+        out["work"] = "%d energies x %d levels x %d units: 18x18 complex LU inverse + 2 products each" % (channels + 10, lld - 1, len(lat.irec))
+    elif what == "chebyshev_green":
+        rec.chebyshev_recur()
+        g = Green(rec)
+        t = timed(g.chebyshev_green)
+        if cpu:
+            t0 = time.perf_counter(); _, ref = O.chebyshev_green(rec.mu_n, g.ene, EMIN, EMAX); tc = time.perf_counter() - t0
+            out["relerr_g0"] = relerr(g.g0, ref)
+    elif what == "sgreen":
+        rec.recur()
+        g = Green(rec)
+        na = len(lat.irec)
+        dw, cs = np.ones((18, na)), np.zeros((18, na))
+        t = timed(lambda: g.sgreen(dw, cs, 1))
+        if cpu:
+            t0 = time.perf_counter(); ref = O.sgreen(rec.a, rec.b2, 1, g.ene, dw, cs); tc = time.perf_counter() - t0
+            out["relerr_g0"] = relerr(g.g0, ref)
+    elif what == "conductivity":
+        M = kw["cond_ll"]
+        rng = np.random.default_rng(1)
+        nloop = kw.get("nloop", 1)
+        mu = np.asfortranarray((rng.normal(size=(18, 18, M, M, nloop)) + 1j * rng.normal(size=(18, 18, M, M, nloop))) * 1e-3)
+        rec.mu_nm_stochastic = mu
+        c = Conductivity(rec)
+        t = timed(c.calculate_conductivity_tensor, reps=2)
+        out["M"] = M
+        if cpu:
+            t0 = time.perf_counter(); ri, _ = O.conductivity_integrand(mu, c.ene, EMIN, EMAX, True); tc = time.perf_counter() - t0
+            ok = ~np.isnan(ri)
+            out["relerr_integrand"] = relerr(c.integrand[ok], ri[ok])
+    out.update({"gpu_seconds": t, "launches_per_call": (rec.launch_count - l0) // 4 if what != "conductivity" else (rec.launch_count - l0) // 3})
+    if cpu:
+        out.update({"cpu_seconds": tc, "cpu_threads": O.lib().orc_get_max_threads(), "speedup": tc / t})
+    print(json.dumps(out), flush=True)
+    rec.close()
+
+
+def main_post():
+    lat = S.sphere_cluster("bcc", 80.0)
+    run_post("1 bulk bccFe run_dos block_green", lat, S.make_hamiltonian(lat, seed=20260101), 21, "block_green")
+    run_post("1 bulk bccFe chebyshev_green lld=100", lat, S.make_hamiltonian(lat, seed=20260101), 100, "chebyshev_green")
+    run_post("1 bulk bccFe sgreen (scalar)", lat, S.make_hamiltonian(lat, seed=20260101, spin_orbit=False), 21, "sgreen")
+    lat = S.sphere_cluster("fcc", 100.0, ntype=7, type_rule="layer")
+    lat.irec = np.array([1, 2, 3, 14, 15, 20], dtype=np.int32)
+    run_post("2 surface fcc 6 units block_green", lat, S.make_hamiltonian(lat, seed=20260102), 21, "block_green")
+    lat = S.periodic_bcc(4, 4, 3)
+    ham = S.make_hamiltonian(lat, seed=20260104, velocity=True)
+    run_post("4 conductivity integrand cond_ll=100", lat, ham, 21, "conductivity", cond_ll=100, cond_calctype="per_type", atlist=[1])
+    run_post("4 conductivity integrand cond_ll=300", lat, ham, 21, "conductivity", cond_ll=300, cond_calctype="per_type", atlist=[1])
+
+
 def main():
     quick = "--quick" in sys.argv
     # config 1: bulk bcc Fe, rc = 80 -> kk = 5984, 1 type, 1 unit, lld = 21, block Lanczos (hoh F/T) + Chebyshev lld=100
@@ -103,4 +169,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--post" in sys.argv:
+        main_post()
+    else:
+        main()
