@@ -94,6 +94,18 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
 int rsrec_ham_vec_matmul(rsrec_handle h, const rsrec_cplx *psi_in, rsrec_cplx *psi_out, double a_scale, double b_shift);
 int rsrec_velo_vec_matmul(rsrec_handle h, int slot, const rsrec_cplx *psi_in, rsrec_cplx *psi_out);
 
+/* create_ll_map (recursion.f90:3277-3303) with the start mask of chebyshev_recur (izeroll(site,1) = 1, 3086-3087):
+ * izeroll (0:kk, lld+1) int32, column ll+1 = sites reachable within ll applications of H (what izero holds after
+ * ll hops; the library itself never materialises the masks -- inactive sites hold exact zeros). */
+int rsrec_create_ll_map(rsrec_handle h, int site, int lld, int32_t *izeroll);
+
+/* chebyshev_orbital_mod, moment part (recursion.f90:2901-3008): mu_n_orb (18,18,lld) = sum over start_sites of
+ * L_r^H T_{n-1}(H~)|r> with |L_r> = i (Y H~ X - X H~ Y)|r>; cr (3,kk) = lattice%cr, alat = lattice%alat.  The
+ * reference loops over all kk sites and divides by kk; the Jackson weighting / trace integration (3012-3048) stay
+ * with the caller. */
+int rsrec_orbital_moments(rsrec_handle h, int nstart, const int32_t *start_sites, const double *cr, double alat,
+                          int lld, double a_scale, double b_shift, rsrec_cplx *mu_n_orb);
+
 /* ---- consumers either side of the recursion: the reference's green / density_of_states /
  * conductivity back ends that read a_b, b2_b, a, b2, mu_n, mu_nm_stochastic.  Same array shapes as the reference. ---- */
 

@@ -168,3 +168,47 @@ def kubo_moments(lat, ham, W, M, a, b):
         for m in range(M):
             mu[:, :, nn_, m] = left[m].conj().T @ right[nn_]
     return mu
+
+
+def ll_map(lat, site, lld):
+    """create_ll_map (`recursion.f90:3277-3303`) via powers of the adjacency pattern: column ll+1 marks the sites
+    that gather from a site marked in column ll (or are marked already)."""
+    kk = lat.kk
+    A = np.zeros((kk, kk), dtype=bool)
+    for i in range(1, kk + 1):
+        for j in range(2, lat.nn[i - 1, 0] + 1):
+            nb = lat.nn[i - 1, j - 1]
+            if nb != 0:
+                A[i - 1, nb - 1] = True
+    m = np.zeros((kk + 1, lld + 1), dtype=np.int32)
+    m[site, 0] = 1
+    for ll in range(lld):
+        cur = m[1:, ll].astype(bool)
+        m[1:, ll + 1] = (cur | (A @ cur)).astype(np.int32)
+    return m
+
+
+def orbital_moments(lat, ham, start_sites, cr, alat, lld, a, b):
+    """chebyshev_orbital_mod's moments (`recursion.f90:2901-3008`): mu_n = sum_r L_r^H T_{n-1}(H~) |r>,
+    |L_r> = i (Y H0~ X - X H0~ Y)|r>, H0 = the non-hoh operator (ham_vec_matmul), H = the full one."""
+    H = dense_hamiltonian(lat, ham)
+    n = H.shape[0]
+    Ht = (H - b * np.eye(n)) / a
+    if ham.hoh:
+        H0 = _assemble(lat, ham.ee, ham.hall, onsite_extra=ham.lsham)
+        H0t = (H0 - b * np.eye(n)) / a
+    else:
+        H0t = Ht
+    X = np.kron(np.diag(cr[0] * alat), np.eye(NB))
+    Y = np.kron(np.diag(cr[1] * alat), np.eye(NB))
+    mu = np.zeros((NB, NB, lld), dtype=np.complex128)
+    for r in start_sites:
+        W = start_block(lat, r)
+        left = 1j * (Y @ H0t @ X @ W - X @ H0t @ Y @ W)
+        t0, t1 = W, Ht @ W
+        for k in range(lld):
+            cur = t0 if k == 0 else t1
+            mu[:, :, k] += left.conj().T @ cur
+            if k >= 1:
+                t0, t1 = t1, 2.0 * (Ht @ t1) - t0
+    return mu

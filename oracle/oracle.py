@@ -51,6 +51,8 @@ def lib():
         _lib.orc_velo_vec_matmul.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp]
         _lib.orc_heev18.argtypes = [c_vp, c_vp]
         _lib.orc_last_irnum.argtypes = [c_vp]
+        _lib.orc_create_ll_map.argtypes = [c_vp, C.c_int, c_vp]
+        _lib.orc_orbital_moments.argtypes = [c_vp, C.c_int, c_vp, c_vp, C.c_double, C.c_int, C.c_double, C.c_double, c_vp]
         _lib.orc_last_irnum.restype = C.c_int
     return _lib
 
@@ -141,6 +143,21 @@ class Oracle:
             n, kind, s = ph.shape[1], 1, None
         mu = np.zeros((18, 18, cond_ll, cond_ll, n), np.complex128, order="F")
         rc = lib().orc_kubo_moments(self.h, n, kind, _p(s), _p(ph), cond_ll, a, b, _p(mu))
+        assert rc == 0
+        return mu
+
+    def create_ll_map(self, site, lld):
+        """izeroll (kk+1, lld+1) with column 1 = the start mask of chebyshev_recur (recursion.f90:3086-3091)."""
+        m = np.zeros((self.lat.kk + 1, lld + 1), np.int32, order="F")
+        m[site, 0] = 1
+        lib().orc_create_ll_map(self.h, lld, _p(m))
+        return m
+
+    def orbital_moments(self, start_sites, cr, alat, lld, a, b):
+        s = np.ascontiguousarray(start_sites, dtype=np.int32)
+        crf = np.asfortranarray(cr, dtype=np.float64)
+        mu = np.zeros((18, 18, lld), np.complex128, order="F")
+        rc = lib().orc_orbital_moments(self.h, len(s), _p(s), _p(crf), float(alat), lld, a, b, _p(mu))
         assert rc == 0
         return mu
 

@@ -809,3 +809,84 @@ int orc_kubo_moments(orc_ctx *c, int nstart, int start_kind, const int32_t *star
   free(psiref); free(w0); free(w1); free(w2); free(v0); free(v1); free(v2); free(right); free(left);
   return 0;
 }
+
+/* ===================== create_ll_map (recursion.f90:3277-3303) ===================== */
+/* izeroll: (0:kk, lld+1) int32, column-major; column 1 must hold the start mask (chebyshev_recur sets
+ * izeroll(j,1) = 1, 3086-3087). */
+void orc_create_ll_map(const orc_ctx *c, int lld, int32_t *izeroll) {
+  const int kk = c->kk;
+  const size_t ld = (size_t)kk + 1;
+  int32_t *idumll = (int32_t *)calloc(ld, sizeof(int32_t));
+  for (int ll = 1; ll <= lld; ll++) {
+    memset(idumll, 0, ld * sizeof(int32_t));
+    for (int i = 1; i <= kk; i++) {
+      idumll[i] = izeroll[i + ld * (ll - 1)];
+      const int nr = NN(c, i, 1);
+      if (nr >= 2)
+        for (int j = 2; j <= nr; j++) {
+          const int nnmap = NN(c, i, j);
+          if (nnmap != 0 && izeroll[nnmap + ld * (ll - 1)] != 0) idumll[i] = 1;
+        }
+    }
+    memcpy(izeroll + ld * ll, idumll, ld * sizeof(int32_t));
+  }
+  free(idumll);
+}
+
+/* ===================== chebyshev_orbital_mod, moment part (recursion.f90:2901-3008) ===================== */
+/* The reference loops `random` over ALL kk start sites and never zeroes mu_n_orb; here the start sites are an argument
+ * and mu_n_orb(18,18,lld) is the plain sum over them (the caller divides by kk, 3010).  The left vector
+ * i (Y H~ X - X H~ Y)|r> is built with ham_vec_matmul (the non-hoh routine, 2957/2973) even when hoh is set; the
+ * Chebyshev chain uses ham_hoh_vec_matmul when hoh (2984-2996).  cr: (3,kk) lattice%cr. */
+static void ham_apply_nohoh(orc_ctx *c, const cplx *in, cplx *out, double a, double b) {
+  const int hoh = c->hoh;
+  c->hoh = 0;
+  ham_apply(c, in, out, a, b);
+  c->hoh = hoh;
+}
+int orc_orbital_moments(orc_ctx *c, int nstart, const int32_t *start_sites, const double *cr, double alat, int lld,
+                        double a, double b, cplx *mu_n_orb) {
+  const int kk = c->kk;
+  const size_t n = (size_t)BLK * kk;
+  cplx *psiref = (cplx *)calloc(n, sizeof(cplx)), *w0 = (cplx *)calloc(n, sizeof(cplx));
+  cplx *l1 = (cplx *)calloc(n, sizeof(cplx)), *l2 = (cplx *)calloc(n, sizeof(cplx)), *left = (cplx *)calloc(n, sizeof(cplx));
+  cplx *v0 = (cplx *)calloc(n, sizeof(cplx)), *v1 = (cplx *)calloc(n, sizeof(cplx)), *v2 = (cplx *)calloc(n, sizeof(cplx));
+  memset(mu_n_orb, 0, sizeof(cplx) * (size_t)BLK * lld);
+  for (int s = 0; s < nstart; s++) {
+    const int r = start_sites[s];
+    memset(v0, 0, n * sizeof(cplx)); memset(v1, 0, n * sizeof(cplx)); memset(v2, 0, n * sizeof(cplx));
+    zero_blocks(psiref, kk);
+    for (int i = 0; i <= kk; i++) c->izero[i] = (i > 0); /* this%izero(:) = 1 */
+    for (int m = 0; m < NB; m++) SBLK(psiref, r)[m + NB * m] = 1.0;
+    for (int k = 1; k <= kk; k++)
+      for (int e = 0; e < BLK; e++) SBLK(l1, k)[e] = cr[0 + 3 * (k - 1)] * SBLK(psiref, k)[e] * alat;
+    ham_apply_nohoh(c, l1, w0, a, b);
+    for (int k = 1; k <= kk; k++)
+      for (int e = 0; e < BLK; e++) SBLK(l1, k)[e] = cr[1 + 3 * (k - 1)] * SBLK(w0, k)[e] * alat;
+    for (int k = 1; k <= kk; k++)
+      for (int e = 0; e < BLK; e++) SBLK(l2, k)[e] = cr[1 + 3 * (k - 1)] * SBLK(psiref, k)[e] * alat;
+    ham_apply_nohoh(c, l2, w0, a, b);
+    for (int k = 1; k <= kk; k++)
+      for (int e = 0; e < BLK; e++) SBLK(l2, k)[e] = cr[0 + 3 * (k - 1)] * SBLK(w0, k)[e] * alat;
+    for (size_t e = 0; e < n; e++) left[e] = I * (l1[e] - l2[e]);
+    for (int nn_ = 1; nn_ <= lld; nn_++) {
+      if (nn_ == 1) {
+        memcpy(v1, psiref, n * sizeof(cplx));
+      } else if (nn_ == 2) {
+        memcpy(v0, v1, n * sizeof(cplx));
+        ham_apply(c, v0, v1, a, b);
+        memcpy(c->izero, c->idum, sizeof(int32_t) * (kk + 1));
+      } else {
+        ham_apply(c, v1, v2, a, b);
+        memcpy(c->izero, c->idum, sizeof(int32_t) * (kk + 1));
+        for (size_t k = 0; k < n; k++) { v2[k] = 2 * v2[k] - v0[k]; v0[k] = v1[k]; v1[k] = v2[k]; v2[k] = 0.0; }
+      }
+      cplx dum[BLK];
+      for (int k = 0; k < BLK; k++) dum[k] = 0.0;
+      for (int k = 1; k <= kk; k++) gemm_cn(dum, SBLK(left, k), SBLK(v1, k));
+      for (int k = 0; k < BLK; k++) mu_n_orb[k + (size_t)BLK * (nn_ - 1)] += dum[k];
+    }
+  }
+  free(psiref); free(w0); free(l1); free(l2); free(left); free(v0); free(v1); free(v2);
+  return 0;
+}

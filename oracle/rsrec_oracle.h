@@ -64,6 +64,12 @@ void orc_ham_vec_matmul(orc_ctx *c, const orc_cplx *psi_in, orc_cplx *psi_out, d
 void orc_velo_vec_matmul(orc_ctx *c, int slot, const orc_cplx *psi_in, orc_cplx *psi_out, int32_t *izero);
 /* Hermitian 18x18 eigen-decomposition used in place of LAPACK zheev (cyclic Jacobi). u: in = matrix, out = vectors */
 int orc_heev18(orc_cplx *u, double *ev);
+/* create_ll_map (recursion.f90:3277-3303): izeroll (0:kk, lld+1) int32 column-major, column 1 = start mask on entry */
+void orc_create_ll_map(const orc_ctx *c, int lld, int32_t *izeroll);
+/* chebyshev_orbital_mod, moment part (recursion.f90:2901-3008): mu_n_orb(18,18,lld) summed over the start sites;
+ * cr (3,kk), alat as lattice%cr, lattice%alat */
+int orc_orbital_moments(orc_ctx *c, int nstart, const int32_t *start_sites, const double *cr, double alat, int lld,
+                        double a, double b, orc_cplx *mu_n_orb);
 /* number of active sites after the last hop (this%irnum) */
 int orc_last_irnum(const orc_ctx *c);
 

@@ -17,7 +17,7 @@ SYMBOLS = [
     "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read",
     "rsrec_bpopt", "rsrec_get_terminf", "rsrec_bgreen", "rsrec_block_green", "rsrec_chebyshev_green", "rsrec_density",
     "rsrec_sgreen", "rsrec_conductivity_integrand", "rsrec_recur_b_green", "rsrec_cheb_recur_green",
-    "rsrec_kubo_conductivity",
+    "rsrec_kubo_conductivity", "rsrec_create_ll_map", "rsrec_orbital_moments",
 ]
 
 
@@ -80,6 +80,8 @@ def load():
     L.rsrec_recur_b_green.argtypes = [vp, i, vp, i, vp, i, i, vp, vp, vp]
     L.rsrec_cheb_recur_green.argtypes = [vp, i, vp, i, d, d, vp, i, vp, vp, vp]
     L.rsrec_kubo_conductivity.argtypes = [vp, i, i, vp, vp, i, d, d, vp, i, vp, vp, vp]
+    L.rsrec_create_ll_map.argtypes = [vp, i, i, vp]
+    L.rsrec_orbital_moments.argtypes = [vp, i, vp, vp, d, i, d, d, vp]
     _lib = L
     return L
 

@@ -492,3 +492,41 @@ __global__ void k_cond_finish(const double2 *part, const double *inv, int nv, in
   }
   integrand[l2 + (size_t)NB * i] = tot;
 }
+
+// ---- create_ll_map (recursion.f90:3277-3303): one reachability level ------------------------------------------
+// prev/next: izeroll(0:kk, ll) / izeroll(0:kk, ll+1); nbr [ng][kk] 0-based with kk = "no neighbour", row 0 = self.
+__global__ void k_ll_map_step(const int32_t *__restrict__ nbr, int ng, int kk, const int32_t *__restrict__ prev,
+                              int32_t *__restrict__ next) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kk; i += gridDim.x * blockDim.x) {
+    int v = prev[i + 1];
+    for (int j = 1; j < ng && !v; j++) {
+      const int nb = nbr[(size_t)j * kk + i];
+      if (nb < kk && prev[nb + 1] != 0) v = 1;
+    }
+    next[i + 1] = v;
+    if (i == 0) next[0] = 0;
+  }
+}
+
+// ---- chebyshev_orbital_mod helpers (recursion.f90:2949-2979): RI36 block vectors ---------------------------------
+// out_k = (pos[comp + 3 k] * in_k) * alat
+__global__ void k_scale_by_pos(const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ pos,
+                               int comp, double alat, int kk) {
+  const size_t total = (size_t)kk * BLKD;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    out[t] = __dmul_rn(__dmul_rn(pos[comp + 3 * (t / BLKD)], in[t]), alat);
+}
+// out = i (x - y):  (re, im) -> (-(xi - yi), xr - yr); RI36 column = 18 reals then 18 imaginaries
+__global__ void k_i_times_diff(const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ out, int kk) {
+  const size_t total = (size_t)kk * BLKC;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t col = t / NB, r = t % NB, o = col * COLD + r;
+    const double dr = x[o] - y[o], di = x[o + NB] - y[o + NB];
+    out[o] = -di;
+    out[o + NB] = dr;
+  }
+}
+__global__ void k_add_block(double *dst, const double *src) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < BLKD) dst[t] += src[t];
+}

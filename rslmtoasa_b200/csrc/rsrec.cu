@@ -269,7 +269,7 @@ static int unit_batch(H *h, int nunits, int nvec) {
 }
 
 // ---- operator application: out = epilogue( H src ) for a unit batch ---------------------------------------
-enum OpKind { OP_HAM = 0, OP_SCALAR = 1, OP_VELO_A = 2, OP_VELO_B = 3 };
+enum OpKind { OP_HAM = 0, OP_SCALAR = 1, OP_VELO_A = 2, OP_VELO_B = 3, OP_HAM_NOHOH = 4 /* ham_vec_matmul even when hoh */ };
 
 // Active-region plan for site-started recursions.  level(site) = number of operator applications after which the
 // site can be non-zero (start sites: 0); a tile is processed by the k-th application iff its smallest level <= k.
@@ -371,9 +371,9 @@ static int apply_op(H *h, OpKind op, const double *in, double *out, const double
   p.kk = h->kk; p.nslot_h = h->nslot; p.ngather = h->ncols; p.vstride = vstride(h);
   p.nbr = h->d_nbr; p.cls = h->d_cls; p.in = in; p.prev = prev; p.out = out; p.a = a; p.b = b; p.epi = epi; p.part = part;
   p.out2 = h->out2;
-  const bool hoh = h->hoh && op != OP_SCALAR;
+  const bool hoh = h->hoh && op != OP_SCALAR && op != OP_HAM_NOHOH;
   if (!hoh) {
-    const double *Hs = op == OP_HAM ? h->Hmain.p : op == OP_SCALAR ? h->Hscalar.p : op == OP_VELO_A ? h->Hva.p : h->Hvb.p;
+    const double *Hs = (op == OP_HAM || op == OP_HAM_NOHOH) ? h->Hmain.p : op == OP_SCALAR ? h->Hscalar.p : op == OP_VELO_A ? h->Hva.p : h->Hvb.p;
     p.g[0] = GatherTerm{Hs, in, 0};
     p.ngterms = 1;
     return launch_apply(h, p, nunits, nctas);
@@ -1365,6 +1365,89 @@ int rsrec_kubo_conductivity(rsrec_handle h, int nstart, int start_kind, const in
 }  // extern "C"
 
 extern "C" {
+
+// create_ll_map (recursion.f90:3277-3303) for the start mask of chebyshev_recur (izeroll(site,1) = 1, 3086-3087):
+// izeroll (0:kk, lld+1) int32 column-major.
+int rsrec_create_ll_map(rsrec_handle h, int site, int lld, int32_t *izeroll) {
+  if (!h || !izeroll || lld < 0 || site < 1 || site > h->kk) return fail(RSREC_EINVAL, "rsrec_create_ll_map: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  const size_t ld = (size_t)h->kk + 1, n = ld * (lld + 1);
+  TRY(dev_alloc(h->post[0], (n + 1) / 2, false));
+  int32_t *m = (int32_t *)h->post[0].p;
+  CUDA_TRY(cudaMemsetAsync(m, 0, n * sizeof(int32_t), h->st));
+  const int32_t one = 1;
+  CUDA_TRY(cudaMemcpyAsync(m + site, &one, sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+  for (int ll = 0; ll < lld; ll++) {
+    k_ll_map_step<<<grid_for(h->kk, 256, h->sms * 8), 256, 0, h->st>>>(h->d_nbr, h->ncols, h->kk, m + ld * ll, m + ld * (ll + 1));
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(izeroll, m, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->st));
+  h->d2h_bytes += (long long)(n * sizeof(int32_t));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+// chebyshev_orbital_mod, moment part (recursion.f90:2901-3008): mu_n_orb (18,18,lld) = sum over the given start sites
+// of  L_r^H T_{n-1}(H~)|r>,  |L_r> = i (Y H~ X - X H~ Y)|r>  (the reference loops over all kk sites and divides by kk;
+// the Jackson weighting and the trace integration stay with the caller).  cr (3,kk) = lattice%cr, alat = lattice%alat.
+int rsrec_orbital_moments(rsrec_handle h, int nstart, const int32_t *start_sites, const double *cr, double alat, int lld,
+                          double a, double b, cplx *mu_n_orb) {
+  if (!h || nstart < 0 || lld < 1 || !cr || !mu_n_orb || a == 0.0 || (nstart > 0 && !start_sites)) return fail(RSREC_EINVAL, "rsrec_orbital_moments: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  h->plan.on = false;  // this%izero(:) = 1: every site active
+  const int nctas = nctas_for(h, 1), kk = h->kk;
+  double *psiref, *tmp, *l1, *l2, *w0, *left, *v0, *v1;
+  TRY(get_vec(h, 0, 1, &psiref)); TRY(get_vec(h, 1, 1, &tmp)); TRY(get_vec(h, 2, 1, &l1)); TRY(get_vec(h, 3, 1, &l2));
+  TRY(get_vec(h, 4, 1, &w0)); TRY(get_vec(h, 5, 1, &left)); TRY(get_vec(h, 6, 1, &v0)); TRY(get_vec(h, 7, 1, &v1));
+  double *vs[] = {psiref, tmp, l1, l2, w0, left, v0, v1};
+  for (double *v : vs) TRY(zero_vec(h, v, 1));  // also the null-site block of every vector
+  TRY(to_dev(h, h->post[0], cr, (size_t)3 * kk));
+  TRY(dev_alloc(h->part, part_doubles(h, 1, nctas), false));
+  TRY(dev_alloc(h->mu, (size_t)(lld + 1) * BLKD, false));
+  CUDA_TRY(cudaMemsetAsync(h->mu.p, 0, (size_t)(lld + 1) * BLKD * sizeof(double), h->st));
+  double *acc = h->mu.p, *one = h->mu.p + (size_t)lld * BLKD;
+  const int g = grid_for((size_t)kk * BLKC, 256, h->sms * 8);
+  for (int s = 0; s < nstart; s++) {
+    TRY(zero_vec(h, psiref, 1));
+    TRY(upload_units(h, 1, start_sites + s, nullptr, nullptr, nullptr));
+    k_init_site_start<<<1, 32, 0, h->st>>>(psiref, vstride(h), h->d_si, h->d_sj, h->d_as, h->d_bs, 1);
+    // Y H~ X |r>
+    k_scale_by_pos<<<g, 256, 0, h->st>>>(psiref, l1, h->post[0].p, 0, alat, kk);
+    h->launches += 2;
+    TRY(apply_op(h, OP_HAM_NOHOH, l1, w0, nullptr, tmp, EPI_HAM, a, b, 1, nctas, nullptr));
+    k_scale_by_pos<<<g, 256, 0, h->st>>>(w0, l1, h->post[0].p, 1, alat, kk);
+    // X H~ Y |r>
+    k_scale_by_pos<<<g, 256, 0, h->st>>>(psiref, l2, h->post[0].p, 1, alat, kk);
+    h->launches += 2;
+    TRY(apply_op(h, OP_HAM_NOHOH, l2, w0, nullptr, tmp, EPI_HAM, a, b, 1, nctas, nullptr));
+    k_scale_by_pos<<<g, 256, 0, h->st>>>(w0, l2, h->post[0].p, 0, alat, kk);
+    k_i_times_diff<<<g, 256, 0, h->st>>>(l1, l2, left, kk);
+    h->launches += 2;
+    double *c0 = v0, *c1 = v1, *cur = psiref;
+    for (int n = 0; n < lld; n++) {
+      if (n == 1) {
+        TRY(apply_op(h, OP_HAM, psiref, c1, nullptr, tmp, EPI_HAM, a, b, 1, nctas, nullptr));
+        CUDA_TRY(cudaMemcpyAsync(c0, psiref, vstride(h) * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+        cur = c1;
+      } else if (n > 1) {  // c0 <- 2 H~ c1 - c0, then swap
+        TRY(apply_op(h, OP_HAM, c1, c0, c0, tmp, EPI_CHEB_NOGRAM, a, b, 1, nctas, nullptr));
+        std::swap(c0, c1);
+        cur = c1;
+      }
+      TRY(launch_gram(h, left, cur, 1, nctas, h->part.p));
+      TRY(launch_reduce(h, 1, nctas, 0, one, nullptr, BLKD, nullptr, nullptr));
+      k_add_block<<<(BLKD + 255) / 256, 256, 0, h->st>>>(acc + (size_t)n * BLKD, one);
+      h->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  TRY(to_host(h, mu_n_orb, acc, (size_t)lld * BLKD));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
 
 int rsrec_synchronize(rsrec_handle h) {
   if (!h) return fail(RSREC_EINVAL, "null handle");

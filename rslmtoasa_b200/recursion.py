@@ -235,6 +235,24 @@ class Recursion:
             _lib.check(self._L.rsrec_kubo_moments(self._h, ph.shape[1], 1, None, _p(ph), M, a, b, _p(mu)))
         self.mu_nm_stochastic = mu
 
+    # -- reachability map and the experimental orbital-moment KPM -----------------------------------------------
+    def create_ll_map(self, site: int):
+        """create_ll_map (3277-3303) for the start mask izeroll(site,1) = 1: -> self.izeroll (kk+1, lld+1) int32."""
+        m = np.zeros((self.lattice.kk + 1, self.control.lld + 1), np.int32, order="F")
+        _lib.check(self._L.rsrec_create_ll_map(self._h, int(site), self.control.lld, _p(m)))
+        self.izeroll = m
+        return m
+
+    def chebyshev_orbital_mod(self, start_sites, cr, alat):
+        """moment part of chebyshev_orbital_mod (2901-3008) for the given start sites: mu_n_orb (18,18,lld), un-normalised."""
+        s = np.ascontiguousarray(start_sites, dtype=np.int32)
+        crf = np.asfortranarray(cr, dtype=np.float64)
+        a, b = self.en.scale_shift()
+        mu = np.zeros((NB, NB, self.control.lld), np.complex128, order="F")
+        _lib.check(self._L.rsrec_orbital_moments(self._h, len(s), _p(s), _p(crf), float(alat), self.control.lld, a, b, _p(mu)))
+        self.mu_n_orb = mu
+        return mu
+
     # -- single operator applications -------------------------------------------------------------------------
     def ham_vec_matmul(self, psi_in, a, b):
         pin = _fc(psi_in)

@@ -286,3 +286,27 @@ def test_results_are_bitwise_reproducible(family):
             outs.append((rec.a_b.copy(), rec.b2_b.copy(), rec.mu_n.copy()))
     for o in outs[1:]:
         assert all(np.array_equal(x, y) for x, y in zip(o, outs[0]))
+
+
+@pytest.mark.parametrize("name", ["bulk", "tiny", "pbc", "impurity"])
+def test_create_ll_map_bit_exact(oracle_mod, name):
+    lat, ham = case(name)
+    rec = _rec(lat, ham, lld=6)
+    orc = oracle_mod.Oracle(lat, ham)
+    for site in (1, lat.kk):
+        assert np.array_equal(rec.create_ll_map(site), orc.create_ll_map(site, 6))
+
+
+@pytest.mark.parametrize("family", [0, 1])
+@pytest.mark.parametrize("name", ["bulk", "bulk_hoh", "impurity"])
+def test_chebyshev_orbital_mod(oracle_mod, name, family):
+    lat, ham = case(name)
+    rec = _rec(lat, ham, lld=7)
+    rec.set_kernel_family(family)
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    cr = 0.5 * lat.cr.astype(np.float64)
+    starts = [1, 4, lat.kk]
+    mu = rec.chebyshev_orbital_mod(starts, cr, 5.42)
+    ref = oracle_mod.Oracle(lat, ham).orbital_moments(starts, cr, 5.42, 7, a, b)
+    assert relerr(mu, ref) < TOL_MU
+    assert np.array_equal(mu, rec.chebyshev_orbital_mod(starts, cr, 5.42))       # reproducible

@@ -189,3 +189,22 @@ def test_golden_vectors(oracle_mod):
     lat, ham = case("pbc")
     mk = oracle_mod.Oracle(lat, ham).kubo_moments(4, a, b, start_sites=[1])
     assert relerr(mk, g["pbc_kubo"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["bulk", "tiny", "pbc"])
+def test_create_ll_map_vs_adjacency_powers(oracle_mod, name):
+    lat, ham = case(name)
+    orc = oracle_mod.Oracle(lat, ham)
+    m = orc.create_ll_map(2, 6)
+    assert np.array_equal(m, D.ll_map(lat, 2, 6))
+    assert m[0].sum() == 0 and (np.diff(m.sum(0)) >= 0).all()          # index 0 stays 0; the region only grows
+
+
+@pytest.mark.parametrize("name", ["bulk", "bulk_hoh", "impurity"])
+def test_orbital_moments_vs_dense(oracle_mod, name):
+    lat, ham = case(name)
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    cr = 0.5 * lat.cr.astype(np.float64)
+    mu = oracle_mod.Oracle(lat, ham).orbital_moments([1, 4], cr, 5.42, 7, a, b)
+    dm = D.orbital_moments(lat, ham, [1, 4], cr, 5.42, 7, a, b)
+    assert relerr(mu, dm) < 1e-11
