@@ -21,6 +21,11 @@ module rsrec_c_mod
    public :: rsrec_create, rsrec_destroy, rsrec_set_lattice, rsrec_set_hamiltonian, rsrec_set_operator
    public :: rsrec_lanczos_block, rsrec_lanczos_scalar, rsrec_zsqr, rsrec_cheb_moments, rsrec_cheb_moments_random
    public :: rsrec_kubo_moments, rsrec_ham_vec_matmul, rsrec_velo_vec_matmul, rsrec_last_error_f, rsrec_check
+   public :: rsrec_create_ll_map, rsrec_orbital_moments
+   ! consumers of the recursion results (green.f90, density_of_states.f90, conductivity.f90) and fused drivers
+   public :: rsrec_bpopt, rsrec_get_terminf, rsrec_bgreen, rsrec_block_green, rsrec_chebyshev_green, rsrec_density
+   public :: rsrec_sgreen, rsrec_conductivity_integrand, rsrec_recur_b_green, rsrec_cheb_recur_green
+   public :: rsrec_kubo_conductivity
 
    interface
       function rsrec_last_error() bind(C, name='rsrec_last_error') result(msg)
@@ -147,6 +152,156 @@ module rsrec_c_mod
          integer(c_int), value :: slot
          complex(c_double_complex), intent(in) :: psi_in(18, 18, *)
          complex(c_double_complex), intent(out) :: psi_out(18, 18, *)
+         integer(c_int) :: rc
+      end function
+      ! create_ll_map: recursion.f90:3277-3303 (start mask izeroll(site,1) = 1); izeroll(0:kk, lld+1)
+      function rsrec_create_ll_map(h, site, lld, izeroll) bind(C, name='rsrec_create_ll_map') result(rc)
+         import :: c_ptr, c_int, c_int32_t
+         type(c_ptr), value :: h
+         integer(c_int), value :: site, lld
+         integer(c_int32_t), intent(out) :: izeroll(*)
+         integer(c_int) :: rc
+      end function
+
+      ! chebyshev_orbital_mod (moment part): recursion.f90:2901-3008
+      function rsrec_orbital_moments(h, nstart, start_sites, cr, alat, lld, a_scale, b_shift, mu_n_orb) &
+         bind(C, name='rsrec_orbital_moments') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nstart, lld
+         integer(c_int32_t), intent(in) :: start_sites(*)
+         real(c_double), intent(in) :: cr(3, *)
+         real(c_double), value :: alat, a_scale, b_shift
+         complex(c_double_complex), intent(out) :: mu_n_orb(18, 18, *)
+         integer(c_int) :: rc
+      end function
+
+      ! bpopt (+ emami): recursion.f90:3540-3706, batched over chains; a, rb (ll, nchains)
+      function rsrec_bpopt(h, nchains, ll, a, rb, ainf, rbinf, ifail) bind(C, name='rsrec_bpopt') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: nchains, ll
+         real(c_double), intent(in) :: a(ll, *), rb(ll, *)
+         real(c_double), intent(out) :: ainf(*), rbinf(*)
+         integer(c_int), intent(out) :: ifail(*)
+         integer(c_int) :: rc
+      end function
+
+      ! get_terminf: recursion.f90:2092-2138
+      function rsrec_get_terminf(h, a_b, b_b, na, ll, a_inf, b_inf, a_inf0, b_inf0) &
+         bind(C, name='rsrec_get_terminf') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: na, ll
+         complex(c_double_complex), intent(in) :: a_b(18, 18, ll, *), b_b(18, 18, ll, *)
+         real(c_double), intent(out) :: a_inf(18, 18, *), b_inf(18, 18, *), a_inf0(*), b_inf0(*)
+         integer(c_int) :: rc
+      end function
+
+      ! bgreen: green.f90:1191-1339 (one unit; eta passed as two reals)
+      function rsrec_bgreen(h, a_b, b_b, ll, e, nv, ie_start, ie_len, a_inf, b_inf, eta_re, eta_im, sym_term, g_out) &
+         bind(C, name='rsrec_bgreen') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: ll, nv, ie_start, ie_len, sym_term
+         complex(c_double_complex), intent(in) :: a_b(18, 18, *), b_b(18, 18, *)
+         real(c_double), intent(in) :: e(*), a_inf(18, 18), b_inf(18, 18)
+         real(c_double), value :: eta_re, eta_im
+         complex(c_double_complex), intent(out) :: g_out(18, 18, *)
+         integer(c_int) :: rc
+      end function
+
+      ! block_green: green.f90:588-621
+      function rsrec_block_green(h, a_b, b_b, na, ll, e, nv, sym_term, g0) bind(C, name='rsrec_block_green') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: na, ll, nv, sym_term
+         complex(c_double_complex), intent(in) :: a_b(18, 18, ll, *), b_b(18, 18, ll, *)
+         real(c_double), intent(in) :: e(*)
+         complex(c_double_complex), intent(out) :: g0(18, 18, nv, *)
+         integer(c_int) :: rc
+      end function
+
+      ! chebyshev_green: green.f90:1030-1108
+      function rsrec_chebyshev_green(h, mu_n, na, lld, ene, nv, energy_min, energy_max, mu_ng, g0) &
+         bind(C, name='rsrec_chebyshev_green') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: na, lld, nv
+         complex(c_double_complex), intent(in) :: mu_n(18, 18, 2*lld + 2, *)
+         real(c_double), intent(in) :: ene(*)
+         real(c_double), value :: energy_min, energy_max
+         complex(c_double_complex), intent(out) :: mu_ng(18, 18, 2*lld + 2, *), g0(18, 18, nv, *)
+         integer(c_int) :: rc
+      end function
+
+      ! dos%density + bprldos: density_of_states.f90:248-407, all (atom, direction) pairs at once
+      function rsrec_density(h, a, b2, lld, na, nmdir, ene, nv, dw_l, cshi, tdens) bind(C, name='rsrec_density') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: lld, na, nmdir, nv
+         real(c_double), intent(in) :: a(lld, 18, na, *), b2(lld, 18, na, *), ene(*), dw_l(18, *), cshi(18, *)
+         real(c_double), intent(out) :: tdens(18, nv, na, *)
+         integer(c_int) :: rc
+      end function
+
+      ! sgreen: green.f90:628-705
+      function rsrec_sgreen(h, a, b2, lld, na, nmdir, ene, nv, dw_l, cshi, g0) bind(C, name='rsrec_sgreen') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: lld, na, nmdir, nv
+         real(c_double), intent(in) :: a(lld, 18, na, *), b2(lld, 18, na, *), ene(*), dw_l(18, *), cshi(18, *)
+         complex(c_double_complex), intent(out) :: g0(18, 18, nv, *)
+         integer(c_int) :: rc
+      end function
+
+      ! calculate_gamma_nm + integrand of calculate_conductivity_tensor: conductivity.f90:158-306
+      function rsrec_conductivity_integrand(h, mu_nm, M, nloop, ene, nv, energy_min, energy_max, per_type, &
+                                            integrand, integrand_at) bind(C, name='rsrec_conductivity_integrand') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: M, nloop, nv, per_type
+         complex(c_double_complex), intent(in) :: mu_nm(18, 18, M, M, *)
+         real(c_double), intent(in) :: ene(*)
+         real(c_double), value :: energy_min, energy_max
+         complex(c_double_complex), intent(out) :: integrand(18, *), integrand_at(18, nv, *)
+         integer(c_int) :: rc
+      end function
+
+      ! fused: recur_b -> zsqr -> get_terminf -> bgreen (self%run_recursion + self%run_dos, self.f90:799-856)
+      function rsrec_recur_b_green(h, nunits, site_i, lld, ene, nv, sym_term, a_b, b2_b, g0) &
+         bind(C, name='rsrec_recur_b_green') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nunits, lld, nv, sym_term
+         integer(c_int32_t), intent(in) :: site_i(*)
+         real(c_double), intent(in) :: ene(*)
+         complex(c_double_complex), intent(out) :: a_b(18, 18, lld, *), b2_b(18, 18, lld, *), g0(18, 18, nv, *)
+         integer(c_int) :: rc
+      end function
+
+      ! fused: chebyshev_recur -> chebyshev_green
+      function rsrec_cheb_recur_green(h, nunits, site_i, lld, energy_min, energy_max, ene, nv, mu_n, mu_ng, g0) &
+         bind(C, name='rsrec_cheb_recur_green') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nunits, lld, nv
+         integer(c_int32_t), intent(in) :: site_i(*)
+         real(c_double), value :: energy_min, energy_max
+         real(c_double), intent(in) :: ene(*)
+         complex(c_double_complex), intent(out) :: mu_n(18, 18, 2*lld + 2, *), mu_ng(18, 18, 2*lld + 2, *), g0(18, 18, nv, *)
+         integer(c_int) :: rc
+      end function
+
+      ! fused: compute_moments_stochastic -> calculate_gamma_nm -> integrand (mu_nm may be c_null_ptr)
+      function rsrec_kubo_conductivity(h, nstart, start_kind, start_sites, phases, M, energy_min, energy_max, ene, nv, &
+                                       mu_nm, integrand, integrand_at) bind(C, name='rsrec_kubo_conductivity') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h, start_sites, phases, mu_nm
+         integer(c_int), value :: nstart, start_kind, M, nv
+         real(c_double), value :: energy_min, energy_max
+         real(c_double), intent(in) :: ene(*)
+         complex(c_double_complex), intent(out) :: integrand(18, *), integrand_at(18, nv, *)
          integer(c_int) :: rc
       end function
    end interface

@@ -43,8 +43,17 @@ struct hamiltonian {  // hamiltonian.f90:52-66
 struct control {  // control.f90:356-384
   int lld = 16, cond_ll = 200;
 };
-struct energy {
-  double energy_min = -1.5, energy_max = 1.5;
+struct energy {  // energy.f90: energy_min/max, channels_ldos, fermi and the mesh e_mesh builds (175-208)
+  double energy_min = -1.5, energy_max = 1.5, fermi = 0.0;
+  int channels_ldos = 2500;
+  std::vector<double> ene;
+  void e_mesh() {
+    if (channels_ldos % 2 != 0) channels_ldos -= 1;
+    double edel = (energy_max - energy_min) / channels_ldos;
+    edel = (fermi - energy_min) / std::nearbyint((fermi - energy_min) / edel);
+    ene.resize(channels_ldos + 10);
+    for (int i = 0; i < channels_ldos + 10; i++) ene[i] = energy_min + edel * i;
+  }
 };
 struct mpi_vars {  // mpi.f90:32-58 (get_mpi_variables)
   int start_atom = 1, end_atom = 0, atoms_per_process = 0;
@@ -129,6 +138,10 @@ class recursion {
   double scale() const { return (en_.energy_max - en_.energy_min) / (2 - 0.3); }  // recursion.f90:3078
   double shift() const { return (en_.energy_max + en_.energy_min) / 2; }          // recursion.f90:3079
   rsrec_handle handle() const { return h_; }
+  const control &ctl() const { return ctl_; }
+  const energy &en() const { return en_; }
+  int nunits_local() const { return (int)local_sites().size(); }
+  std::vector<int32_t> sites_local() const { return local_sites(); }
 
  private:
   static const rsrec_cplx *p(const std::vector<cplx> &v) { return v.empty() ? nullptr : reinterpret_cast<const rsrec_cplx *>(v.data()); }
@@ -176,6 +189,42 @@ class recursion {
   energy en_;
   int rank_, np_;
   rsrec_handle h_ = nullptr;
+};
+
+// Mirror of the reference's `type green` (green.f90) for the procedures that consume the recursion results.
+class green {
+ public:
+  std::vector<cplx> g0;  // (18,18,nv,nunits)
+  bool sym_term = false;  // control%sym_term
+  green(recursion &r, energy &e) : rec_(r), en_(e) {
+    if (en_.ene.empty()) en_.e_mesh();
+  }
+  void block_green() {  // green.f90:588-621 (after recursion%zsqr, like self%run_dos)
+    const int lld = rec_.ctl().lld, nv = (int)en_.ene.size(), na = (int)(rec_.a_b.size() / ((size_t)324 * lld));
+    g0.assign((size_t)324 * nv * na, 0.0);
+    check(rsrec_block_green(rec_.handle(), cp(rec_.a_b), cp(rec_.b2_b), na, lld, en_.ene.data(), nv, sym_term, mp(g0)));
+  }
+  void chebyshev_green(std::vector<cplx> *mu_ng = nullptr) {  // green.f90:1030-1108
+    const int lld = rec_.ctl().lld, nv = (int)en_.ene.size(), na = (int)(rec_.mu_n.size() / ((size_t)324 * (2 * lld + 2)));
+    g0.assign((size_t)324 * nv * na, 0.0);
+    if (mu_ng) mu_ng->assign(rec_.mu_n.size(), 0.0);
+    check(rsrec_chebyshev_green(rec_.handle(), cp(rec_.mu_n), na, lld, en_.ene.data(), nv, en_.energy_min, en_.energy_max,
+                                mu_ng ? mp(*mu_ng) : nullptr, mp(g0)));
+  }
+  void recur_b_green() {  // fused self%run_recursion + self%run_dos (block path)
+    const auto sites = rec_.sites_local();
+    const int n = (int)sites.size(), lld = rec_.ctl().lld, nv = (int)en_.ene.size();
+    rec_.a_b.assign((size_t)324 * lld * n, 0.0);
+    rec_.b2_b.assign((size_t)324 * lld * n, 0.0);
+    g0.assign((size_t)324 * nv * n, 0.0);
+    check(rsrec_recur_b_green(rec_.handle(), n, sites.data(), lld, en_.ene.data(), nv, sym_term, mp(rec_.a_b), mp(rec_.b2_b), mp(g0)));
+  }
+
+ private:
+  static const rsrec_cplx *cp(const std::vector<cplx> &v) { return reinterpret_cast<const rsrec_cplx *>(v.data()); }
+  static rsrec_cplx *mp(std::vector<cplx> &v) { return reinterpret_cast<rsrec_cplx *>(v.data()); }
+  recursion &rec_;
+  energy &en_;
 };
 
 }  // namespace rsrec

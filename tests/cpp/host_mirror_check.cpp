@@ -31,13 +31,25 @@ int main(int argc, char **argv) {
   auto emm = rd<double>(f);
   rsrec::energy en; en.energy_min = emm[0]; en.energy_max = emm[1];
   auto ref_a = rd<rsrec::cplx>(f), ref_b2 = rd<rsrec::cplx>(f), ref_mu = rd<rsrec::cplx>(f), ref_aij = rd<rsrec::cplx>(f);
+  auto mesh = rd<double>(f);   // channels_ldos, fermi
+  auto ref_g0 = rd<rsrec::cplx>(f), ref_gk = rd<rsrec::cplx>(f);
+  en.channels_ldos = (int)mesh[0]; en.fermi = mesh[1];
   fclose(f);
   try {
     rsrec::recursion rec(ham, lat, ctl, en);
     rec.recur_b();
     printf("recur_b a_b %.3e b2_b %.3e\n", relerr(rec.a_b, ref_a), relerr(rec.b2_b, ref_b2));
+    rsrec::green gr(rec, en);
+    rec.zsqr();
+    gr.block_green();
+    printf("block_green g0 %.3e\n", relerr(gr.g0, ref_g0));
+    const auto staged = gr.g0;
+    gr.recur_b_green();
+    printf("recur_b_green g0 %.3e\n", relerr(gr.g0, staged));
     rec.chebyshev_recur();
     printf("chebyshev_recur mu_n %.3e\n", relerr(rec.mu_n, ref_mu));
+    gr.chebyshev_green();
+    printf("chebyshev_green g0 %.3e\n", relerr(gr.g0, ref_gk));
     rec.recur_b_ij();
     printf("recur_b_ij a_b %.3e\n", relerr(rec.a_b, ref_aij));
     rsrec::energy bad; bad.energy_min = -0.05; bad.energy_max = 0.05;

@@ -110,3 +110,19 @@ def test_synthetic_lattices_match_survey_sizes():
     for m in range(1, 15):                                    # reciprocity of the neighbour table
         j = lat.nn[:, m] - 1
         assert (lat.nn[j, opp[m]] - 1 == np.arange(lat.kk)).all()
+
+
+def test_fortran_module_binds_every_data_path_symbol():
+    """fortran/rsrec_c_mod.f90 is the ISO_C_BINDING layer the north star asks for: one interface per C entry point.
+    (Bench/diagnostic helpers -- stepping sessions, counters, profiling, kernel-family switch -- are Python-only.)"""
+    hdr = open(os.path.join(ROOT, "include", "rsrec.h")).read()
+    declared = set(re.findall(r"\b(rsrec_[a-z0-9_]+)\s*\(", hdr))
+    f90 = open(os.path.join(ROOT, "fortran", "rsrec_c_mod.f90")).read()
+    bound = set(re.findall(r"name='(rsrec_[a-z0-9_]+)'", f90))
+    helpers = {"rsrec_version", "rsrec_compiled_arch", "rsrec_cheb_begin_random", "rsrec_cheb_begin_sites",
+               "rsrec_cheb_run_steps", "rsrec_cheb_end", "rsrec_synchronize", "rsrec_stream", "rsrec_launch_count",
+               "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read", "rsrec_set_kernel_family"}
+    assert bound <= declared
+    assert declared - bound == helpers
+    for name in bound:       # every interface is exported from the module
+        assert re.search(r"public ::[^\n]*\b%s\b" % name, f90) or name == "rsrec_last_error", name

@@ -54,15 +54,21 @@ def test_cpp_host_mirror_matches_oracle(tmp_path, oracle_mod):
         _w(f, ham.ee, np.complex128); _w(f, ham.lsham, np.complex128); _w(f, ham.hall, np.complex128)
         _w(f, [EMIN, EMAX], np.float64)
         _w(f, a_b, np.complex128); _w(f, b2_b, np.complex128); _w(f, mu, np.complex128); _w(f, aij, np.complex128)
+        _w(f, [70, 0.05], np.float64)
+        ene = oracle_mod.e_mesh(EMIN, EMAX, 70, 0.05)              # the C++ mirror builds the same mesh (energy.f90:175-208)
+        _w(f, oracle_mod.block_green(a_b, orc.zsqr(b2_b), ene), np.complex128)
+        _w(f, oracle_mod.chebyshev_green(mu, ene, EMIN, EMAX)[1], np.complex128)   # NaN tail (|w| > 1) is skipped by the C++ max
     out = subprocess.run([_build(tmp_path), path], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     vals = {}
     for line in out.stdout.splitlines():
         t = line.split()
-        if t[0] in ("recur_b", "chebyshev_recur", "recur_b_ij"):
+        if t[0] in ("recur_b", "chebyshev_recur", "recur_b_ij", "block_green", "recur_b_green", "chebyshev_green"):
             for k, v in zip(t[1::2], t[2::2]):
                 vals[t[0] + "." + k] = float(v)
     assert vals["recur_b.a_b"] < 1e-10 and vals["recur_b.b2_b"] < 1e-10
     assert vals["chebyshev_recur.mu_n"] < 1e-9
     assert vals["recur_b_ij.a_b"] < 1e-10
+    assert vals["block_green.g0"] < 1e-8 and vals["recur_b_green.g0"] == 0.0
+    assert vals["chebyshev_green.g0"] < 1e-9
     assert "fatal -2" in out.stdout and "did not converge" in out.stdout
