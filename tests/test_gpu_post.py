@@ -245,3 +245,40 @@ def test_post_argument_errors(block_rec):
         g.bgreen(1, 0, 3, a_inf[..., 0], b_inf[..., 0])          # channels are 1-based
     with pytest.raises(RsrecError):
         g.bgreen(1, 169, 3, a_inf[..., 0], b_inf[..., 0])        # window runs past the mesh
+
+
+def test_gpu_against_committed_golden_vectors():
+    """the CUDA path against tests/golden/*.npz: hot-path coefficients recomputed on the GPU, then every consumer fed
+    with the COMMITTED coefficients so that each stage is compared on identical inputs"""
+    import os
+    from rslmtoasa_b200 import Green, Dos, Conductivity
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    g, p = np.load(os.path.join(here, "oracle_golden.npz")), np.load(os.path.join(here, "post_golden.npz"))
+    lat, ham = case("impurity_hoh")
+    rec = _rec(lat, ham, lld=6)
+    rec.en.ene = p["ene"]
+    rec.recur_b()
+    assert relerr(rec.a_b, g["imp_a_b"]) < 1e-10 and relerr(rec.b2_b, g["imp_b2_b"]) < 1e-10
+    rec.chebyshev_recur()
+    assert relerr(rec.mu_n, g["imp_mu"]) < 1e-9
+    rec.a_b, rec.b2_b = g["imp_a_b"], g["imp_b2_b"].copy()
+    rec.zsqr()
+    assert relerr(rec.b2_b, p["b_b"]) < 1e-12
+    rec.b2_b = p["b_b"]
+    gr = Green(rec)
+    a_inf, b_inf, a0, b0 = gr.get_terminf()
+    assert np.array_equal(a_inf, p["a_inf"]) and np.array_equal(b_inf, p["b_inf"])
+    assert np.array_equal(a0, p["a_inf0"]) and np.array_equal(b0, p["b_inf0"])
+    assert relerr(gr.block_green(), p["g0_block"]) < TOL_G
+    gr.sym_term = True
+    assert relerr(gr.block_green(), p["g0_block_sym"]) < TOL_G
+    rec.mu_n = g["imp_mu"]
+    assert relerr(gr.chebyshev_green(), p["g0_cheb"]) < TOL_SUM and relerr(rec.mu_ng, p["mu_ng"]) < 1e-15
+    rec.a = np.zeros((8, 18, 1, 3), order="F"); rec.b2 = np.ones((8, 18, 1, 3), order="F")
+    rec.a[..., 0], rec.b2[..., 0] = g["bulk_sa"], g["bulk_sb"]
+    assert relerr(Dos(rec).density(1, 1, p["dw"][:, 0], p["cs"][:, 0]), p["tdens"]) < 1e-13
+    rec.mu_nm_stochastic = g["pbc_kubo"]
+    rec.control.cond_calctype = "per_type"
+    integ, integ_at = Conductivity(rec).calculate_conductivity_tensor()
+    assert relerr(np.nan_to_num(integ), np.nan_to_num(p["integrand"])) < TOL_SUM
+    assert relerr(np.nan_to_num(integ_at), np.nan_to_num(p["integrand_at"])) < TOL_SUM

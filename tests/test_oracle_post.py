@@ -187,3 +187,23 @@ def test_gamma_nm_and_integrand_vs_numpy(oracle_mod):
     assert relerr(integ, ri) < 1e-12 and relerr(integ_at, rat) < 1e-12
     integ2, at2 = oracle_mod.conductivity_integrand(mu, ene, EMIN, EMAX, False)
     assert np.array_equal(integ2, integ) and not at2.any()
+
+
+def test_post_golden_vectors(oracle_mod):
+    """committed oracle outputs computed from the committed coefficient fixtures (tests/golden/make_golden_post.py)"""
+    import os
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    g, p = np.load(os.path.join(here, "oracle_golden.npz")), np.load(os.path.join(here, "post_golden.npz"))
+    ene = p["ene"]
+    b_b = oracle_mod.Oracle.zsqr(None, g["imp_b2_b"])
+    assert relerr(b_b, p["b_b"]) < 1e-12
+    a_inf, b_inf, a0, b0 = oracle_mod.get_terminf(g["imp_a_b"], p["b_b"])
+    assert np.array_equal(a_inf, p["a_inf"]) and np.array_equal(b_inf, p["b_inf"]) and np.array_equal(a0, p["a_inf0"])
+    assert relerr(oracle_mod.block_green(g["imp_a_b"], p["b_b"], ene), p["g0_block"]) < 1e-12
+    assert relerr(oracle_mod.block_green(g["imp_a_b"], p["b_b"], ene, True), p["g0_block_sym"]) < 1e-12
+    mu_ng, g0 = oracle_mod.chebyshev_green(g["imp_mu"], ene, EMIN, EMAX)
+    assert relerr(mu_ng, p["mu_ng"]) < 1e-14 and relerr(g0, p["g0_cheb"]) < 1e-13
+    td = oracle_mod.density(g["bulk_sa"][..., 0], g["bulk_sb"][..., 0], ene, p["dw"][:, 0], p["cs"][:, 0])
+    assert relerr(td, p["tdens"]) < 1e-13
+    integ, integ_at = oracle_mod.conductivity_integrand(g["pbc_kubo"], ene, EMIN, EMAX, True)
+    assert relerr(np.nan_to_num(integ), np.nan_to_num(p["integrand"])) < 1e-13
