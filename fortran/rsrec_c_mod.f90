@@ -21,7 +21,7 @@ module rsrec_c_mod
    public :: rsrec_create, rsrec_destroy, rsrec_set_lattice, rsrec_set_hamiltonian, rsrec_set_operator
    public :: rsrec_lanczos_block, rsrec_lanczos_scalar, rsrec_zsqr, rsrec_cheb_moments, rsrec_cheb_moments_random
    public :: rsrec_kubo_moments, rsrec_ham_vec_matmul, rsrec_velo_vec_matmul, rsrec_last_error_f, rsrec_check
-   public :: rsrec_create_ll_map, rsrec_orbital_moments
+   public :: rsrec_create_ll_map, rsrec_orbital_moments, rsrec_build_nn
    ! consumers of the recursion results (green.f90, density_of_states.f90, conductivity.f90) and fused drivers
    public :: rsrec_bpopt, rsrec_get_terminf, rsrec_bgreen, rsrec_block_green, rsrec_chebyshev_green, rsrec_density
    public :: rsrec_sgreen, rsrec_conductivity_integrand, rsrec_recur_b_green, rsrec_cheb_recur_green
@@ -154,6 +154,20 @@ module rsrec_c_mod
          complex(c_double_complex), intent(out) :: psi_out(18, 18, *)
          integer(c_int) :: rc
       end function
+      ! lattice%nncal + lattice%remd (lattice.f90:3035-3123, 2823-2907) on the device; call once with ncols = 0 and
+      ! nn = c_null_ptr to query nm, allocate lattice%nn(kk, nm+1), call again (replaces lattice.f90:1851-1868)
+      function rsrec_build_nn(device_ordinal, kk, crd, no, ntot, iu, ct, pbc, nrep, a, alat, ncols, nn, nm) &
+         bind(C, name='rsrec_build_nn') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double
+         integer(c_int), value :: device_ordinal, kk, ntot, ncols
+         real(c_double), intent(in) :: crd(3, *), a(3, 3)
+         integer(c_int32_t), intent(in) :: no(*), iu(*), pbc(3), nrep(3)
+         real(c_double), value :: ct, alat
+         type(c_ptr), value :: nn
+         integer(c_int), intent(out) :: nm
+         integer(c_int) :: rc
+      end function
+
       ! create_ll_map: recursion.f90:3277-3303 (start mask izeroll(site,1) = 1); izeroll(0:kk, lld+1)
       function rsrec_create_ll_map(h, site, lld, izeroll) bind(C, name='rsrec_create_ll_map') result(rc)
          import :: c_ptr, c_int, c_int32_t

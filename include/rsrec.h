@@ -106,6 +106,15 @@ int rsrec_create_ll_map(rsrec_handle h, int site, int lld, int32_t *izeroll);
 int rsrec_orbital_moments(rsrec_handle h, int nstart, const int32_t *start_sites, const double *cr, double alat,
                           int lld, double a_scale, double b_shift, rsrec_cplx *mu_n_orb);
 
+/* ---- neighbour table on the device: lattice%nncal + lattice%remd (lattice.f90:3035-3123,
+ * 2823-2907) with a cell grid instead of the O(kk^2) pair loop; identical table (integers, bit-exact).
+ * crd (3,kk) = cr*alat; no (kk) = lattice%num (bravais type of each site); iu (ntot) = representative site of each
+ * bravais type; ct = lattice%ct(1); pbc[3] = b1,b2,b3 flags (NULL = open cluster), nrep[3] = n1,n2,n3, a (3,3) =
+ * lattice%a, alat.  nn (kk, ncols) out, ncols >= *nm_out + 1 like lattice%nn (call with nn = NULL to query nm). */
+int rsrec_build_nn(int device_ordinal, int kk, const double *crd, const int32_t *no, int ntot, const int32_t *iu,
+                   double ct, const int32_t *pbc, const int32_t *nrep, const double *a, double alat, int ncols,
+                   int32_t *nn, int *nm_out);
+
 /* ---- consumers either side of the recursion: the reference's green / density_of_states /
  * conductivity back ends that read a_b, b2_b, a, b2, mu_n, mu_nm_stochastic.  Same array shapes as the reference. ---- */
 

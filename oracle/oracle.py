@@ -20,7 +20,7 @@ c_vp = C.c_void_p
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("rsrec_oracle.c", "rsrec_oracle_post.c", "rsrec_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("rsrec_oracle.c", "rsrec_oracle_post.c", "rsrec_oracle_lattice.c", "rsrec_oracle.h")]
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "librsrec_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -338,3 +338,28 @@ def conductivity_integrand(mu_nm, ene, energy_min, energy_max, per_type):
     _post().orc_conductivity_integrand(_p(mu), M, nloop, _p(ene), nv, energy_min, energy_max, int(per_type), _p(integ),
                                        _p(integ_at))
     return integ, integ_at
+
+
+# ---- neighbour-table construction (rsrec_oracle_lattice.c) ----------------------------------------
+def build_nn(crd, no, iu, ct, pbc=None, nrep=(1, 1, 1), a=None, alat=1.0, ncols=None):
+    """lattice%nncal + lattice%remd.  crd (3,kk) = cr*alat; no (kk) bravais type; iu (ntot) representative sites;
+    pbc: None (open cluster) or 3 flags with nrep = (n1,n2,n3) and a (3,3) = lattice%a.  -> nn (kk, nm+1), nm."""
+    L = lib()
+    L.orc_build_nn.argtypes = [C.c_int, c_vp, c_vp, C.c_int, c_vp, C.c_double, C.c_int, c_vp, c_vp, c_vp, C.c_double,
+                               C.c_int, c_vp, c_vp]
+    crd = np.asfortranarray(crd, dtype=np.float64)
+    kk = crd.shape[1]
+    no = np.ascontiguousarray(no, dtype=np.int32); iu = np.ascontiguousarray(iu, dtype=np.int32)
+    b = np.ascontiguousarray(pbc if pbc is not None else (0, 0, 0), dtype=np.int32)
+    nr = np.ascontiguousarray(nrep, dtype=np.int32)
+    av = np.asfortranarray(a if a is not None else np.eye(3), dtype=np.float64)
+    nm = C.c_int(0)
+    cols = ncols or 1
+    while True:
+        nn = np.zeros((kk, cols), np.int32, order="F")
+        rc = L.orc_build_nn(kk, _p(crd), _p(no), len(iu), _p(iu), float(ct), int(pbc is not None), _p(b), _p(nr), _p(av),
+                            float(alat), cols, _p(nn), C.byref(nm))
+        if rc == -1 and ncols is None:
+            cols = nm.value + 1
+            continue
+        return nn, nm.value, rc

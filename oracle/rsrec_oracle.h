@@ -102,6 +102,10 @@ void orc_gamma_nm(const double *ene, int nv, int M, double energy_min, double en
 void orc_conductivity_integrand(const orc_cplx *mu_nm, int M, int nloop, const double *ene, int nv, double energy_min,
                                 double energy_max, int per_type, orc_cplx *integrand, orc_cplx *integrand_at);
 
+/* ---- neighbour table, rsrec_oracle_lattice.c: nncal + remd (lattice.f90:3035-3123, 2823-2907) ---- */
+int orc_build_nn(int kk, const double *crd, const int32_t *no, int ntot, const int32_t *iu, double ct, int use_pbc,
+                 const int *b, const int *nrep, const double *a, double alat, int ncols, int32_t *nn, int *nm_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
 #include "kernels_dmma.cuh"
 #include "kernels_kubo.cuh"
 #include "kernels_post.cuh"
+#include "kernels_lattice.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1446,6 +1447,101 @@ int rsrec_orbital_moments(rsrec_handle h, int nstart, const int32_t *start_sites
   }
   TRY(to_host(h, mu_n_orb, acc, (size_t)lld * BLKD));
   CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+// lattice%nncal + lattice%remd on the device (lattice.f90:3035-3123, 2823-2907); handle-free because the handle's
+// sizes (ncols) are only known once the table exists.  See kernels_lattice.cuh for the algorithm.
+int rsrec_build_nn(int device, int kk, const double *crd, const int32_t *no, int ntot, const int32_t *iu, double ct,
+                   const int32_t *pbc, const int32_t *nrep, const double *a, double alat, int ncols, int32_t *nn, int *nm_out) {
+  if (kk < 1 || !crd || !no || ntot < 1 || !iu || !(ct > 0.0) || !nm_out) return fail(RSREC_EINVAL, "rsrec_build_nn: bad argument");
+  for (int t = 0; t < ntot; t++) if (iu[t] < 1 || iu[t] > kk) return fail(RSREC_EINVAL, "rsrec_build_nn: representative site out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(RSREC_ECUDA, "no CUDA device available (this library has no CPU path)"); }
+  if (device < 0 || device >= ndev) return fail(RSREC_EINVAL, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  LatPbc P;
+  memset(&P, 0, sizeof(P));
+  P.use = pbc && (pbc[0] || pbc[1] || pbc[2]);
+  P.alat = alat;
+  for (int l = 0; l < 3; l++) { P.b[l] = P.use ? (pbc[l] != 0) : 0; P.n[l] = nrep ? nrep[l] : 1; }
+  if (P.use && !a) return fail(RSREC_EINVAL, "rsrec_build_nn: lattice vectors are required with periodic boundaries");
+  for (int e = 0; e < 9; e++) P.a[e] = a ? a[e] : 0.0;
+  // bounding box of the sites (host, O(kk)); ghosts and the grid live in the box padded by ct
+  double lo[3] = {crd[0], crd[1], crd[2]}, hi[3] = {crd[0], crd[1], crd[2]};
+  for (int i = 1; i < kk; i++)
+    for (int l = 0; l < 3; l++) { lo[l] = std::min(lo[l], crd[l + 3 * (size_t)i]); hi[l] = std::max(hi[l], crd[l + 3 * (size_t)i]); }
+  LatGrid G;
+  double cs = ct * (1.0 + 1e-9), vol = 1.0;
+  for (int l = 0; l < 3; l++) vol *= (hi[l] - lo[l] + 2.0 * ct);
+  const double max_cells = 3.2e7;
+  if (vol / (cs * cs * cs) > max_cells) cs = std::cbrt(vol / max_cells);
+  G.inv_cs = 1.0 / cs;
+  size_t ncells = 1;
+  for (int l = 0; l < 3; l++) { G.org[l] = lo[l] - ct; G.dim[l] = (int)std::floor((hi[l] - lo[l] + 2.0 * ct) / cs) + 1; ncells *= (size_t)G.dim[l]; }
+  struct Bufs {
+    double *crd = nullptr, *gpos = nullptr, *set = nullptr;
+    int32_t *no = nullptr, *iu = nullptr, *gidx = nullptr, *cell_pts = nullptr, *rows = nullptr, *nn = nullptr;
+    int *ctr = nullptr, *cell_cnt = nullptr, *cell_start = nullptr, *cnt = nullptr;
+    ~Bufs() { void *p[] = {crd, gpos, set, no, iu, gidx, cell_pts, rows, nn, ctr, cell_cnt, cell_start, cnt}; for (void *q : p) if (q) cudaFree(q); }
+  } B;
+  cudaStream_t st = nullptr;  // default stream: this is a set-up call
+  CUDA_TRY(cudaMalloc(&B.crd, sizeof(double) * 3 * (size_t)kk));
+  CUDA_TRY(cudaMalloc(&B.no, sizeof(int32_t) * (size_t)kk));
+  CUDA_TRY(cudaMalloc(&B.iu, sizeof(int32_t) * (size_t)ntot));
+  CUDA_TRY(cudaMalloc(&B.ctr, sizeof(int) * 4));
+  CUDA_TRY(cudaMalloc(&B.cnt, sizeof(int) * (size_t)kk));
+  CUDA_TRY(cudaMemcpy(B.crd, crd, sizeof(double) * 3 * (size_t)kk, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(B.no, no, sizeof(int32_t) * (size_t)kk, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(B.iu, iu, sizeof(int32_t) * (size_t)ntot, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(B.ctr, 0, sizeof(int) * 4));
+  const int tb = 128, gb = (kk + tb - 1) / tb;
+  int hctr[4] = {0, 0, 0, 0};
+  if (P.use) {  // 1. ghost images: count, allocate, write
+    k_lat_ghosts<<<gb, tb, 0, st>>>(B.crd, kk, P, G, lo[0] - ct, lo[1] - ct, lo[2] - ct, hi[0] + ct, hi[1] + ct, hi[2] + ct, B.ctr, nullptr, nullptr);
+    CUDA_TRY(cudaMemcpy(hctr, B.ctr, sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  const int ng = hctr[0], npts = kk + ng;
+  if (ng > 0) {
+    CUDA_TRY(cudaMalloc(&B.gidx, sizeof(int32_t) * (size_t)ng));
+    CUDA_TRY(cudaMalloc(&B.gpos, sizeof(double) * 3 * (size_t)ng));
+    CUDA_TRY(cudaMemset(B.ctr, 0, sizeof(int)));
+    k_lat_ghosts<<<gb, tb, 0, st>>>(B.crd, kk, P, G, lo[0] - ct, lo[1] - ct, lo[2] - ct, hi[0] + ct, hi[1] + ct, hi[2] + ct, B.ctr, B.gidx, B.gpos);
+  }
+  // 2. counting sort of all points into the cell grid
+  CUDA_TRY(cudaMalloc(&B.cell_cnt, sizeof(int) * ncells));
+  CUDA_TRY(cudaMalloc(&B.cell_start, sizeof(int) * (ncells + 1)));
+  CUDA_TRY(cudaMalloc(&B.cell_pts, sizeof(int32_t) * (size_t)npts));
+  CUDA_TRY(cudaMemset(B.cell_cnt, 0, sizeof(int) * ncells));
+  const int gp = (npts + tb - 1) / tb;
+  k_lat_cell_count<<<gp, tb, 0, st>>>(B.crd, B.gpos, kk, npts, G, B.cell_cnt);
+  k_lat_scan<<<1, 1024, 0, st>>>(B.cell_cnt, B.cell_start, (int)ncells);
+  CUDA_TRY(cudaMemset(B.cell_cnt, 0, sizeof(int) * ncells));
+  k_lat_cell_fill<<<gp, tb, 0, st>>>(B.crd, B.gpos, kk, npts, G, B.cell_start, B.cell_cnt, B.cell_pts);
+  // 3. nncal: count (upper bound), allocate the rows, fill (exact)
+  k_lat_nncal<<<gb, tb, 0, st>>>(B.crd, B.gpos, B.gidx, kk, P, G, B.cell_start, B.cell_pts, ct, B.cnt, B.ctr + 1, nullptr, 0);
+  CUDA_TRY(cudaMemcpy(hctr, B.ctr, sizeof(int) * 4, cudaMemcpyDeviceToHost));
+  const int rowcap = std::max(1, hctr[1] - 1);
+  CUDA_TRY(cudaMalloc(&B.rows, sizeof(int32_t) * (size_t)kk * rowcap));
+  k_lat_nncal<<<gb, tb, 0, st>>>(B.crd, B.gpos, B.gidx, kk, P, G, B.cell_start, B.cell_pts, ct, B.cnt, B.ctr + 2, B.rows, rowcap);
+  CUDA_TRY(cudaMemcpy(hctr, B.ctr, sizeof(int) * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaGetLastError());
+  const int nnmax = std::max(hctr[2], 1);  // NM = NNMAX (nn(:,1) counts the site itself)
+  *nm_out = nnmax;
+  if (!nn || ncols < nnmax + 1) return fail(RSREC_EINVAL, "rsrec_build_nn: nn needs nm+1 = " + std::to_string(nnmax + 1) + " columns (lattice.f90:1856)");
+  // 4. remd
+  const int nmcols = nnmax + 2;
+  CUDA_TRY(cudaMalloc(&B.set, sizeof(double) * 3 * (size_t)ntot * nmcols));
+  CUDA_TRY(cudaMemset(B.set, 0, sizeof(double) * 3 * (size_t)ntot * nmcols));
+  CUDA_TRY(cudaMalloc(&B.nn, sizeof(int32_t) * (size_t)kk * ncols));
+  CUDA_TRY(cudaMemset(B.nn, 0, sizeof(int32_t) * (size_t)kk * ncols));
+  k_lat_set<<<ntot, 64, 0, st>>>(B.crd, kk, P, B.iu, ntot, B.cnt, B.rows, nmcols, B.set);
+  k_lat_remd<<<gb, tb, 0, st>>>(B.crd, kk, P, B.no, B.iu, ntot, B.cnt, B.rows, nmcols, B.set, ncols, B.nn, B.ctr + 3);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(hctr, B.ctr, sizeof(int) * 4, cudaMemcpyDeviceToHost));
+  if (hctr[3] == 2) return fail(RSREC_EINVAL, "rsrec_build_nn: VECTOR NOT FOUND (a site has a neighbour vector its type's representative lacks; lattice.f90:2896)");
+  if (hctr[3] == 3) return fail(RSREC_EINVAL, "rsrec_build_nn: TYPE NO NOT FOUND (lattice.f90:2860)");
+  CUDA_TRY(cudaMemcpy(nn, B.nn, sizeof(int32_t) * (size_t)kk * ncols, cudaMemcpyDeviceToHost));
   return RSREC_OK;
 }
 
