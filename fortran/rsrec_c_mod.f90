@@ -21,7 +21,7 @@ module rsrec_c_mod
    public :: rsrec_create, rsrec_destroy, rsrec_set_lattice, rsrec_set_hamiltonian, rsrec_set_operator
    public :: rsrec_lanczos_block, rsrec_lanczos_scalar, rsrec_zsqr, rsrec_cheb_moments, rsrec_cheb_moments_random
    public :: rsrec_kubo_moments, rsrec_ham_vec_matmul, rsrec_velo_vec_matmul, rsrec_last_error_f, rsrec_check
-   public :: rsrec_create_ll_map, rsrec_orbital_moments, rsrec_build_nn
+   public :: rsrec_create_ll_map, rsrec_orbital_moments, rsrec_build_nn, rsrec_build_hamiltonian
    ! consumers of the recursion results (green.f90, density_of_states.f90, conductivity.f90) and fused drivers
    public :: rsrec_bpopt, rsrec_get_terminf, rsrec_bgreen, rsrec_block_green, rsrec_chebyshev_green, rsrec_density
    public :: rsrec_sgreen, rsrec_conductivity_integrand, rsrec_recur_b_green, rsrec_cheb_recur_green
@@ -165,6 +165,19 @@ module rsrec_c_mod
          real(c_double), value :: ct, alat
          type(c_ptr), value :: nn
          integer(c_int), intent(out) :: nm
+         integer(c_int) :: rc
+      end function
+
+      ! device-side build_bulkham / build_locham (hamiltonian.f90:1553-1667 with ham0m_nc 2225-2303, hcpx); optional
+      ! downloads are passed as c_loc(array) or c_null_ptr
+      function rsrec_build_hamiltonian(h, hhh, jt, it, pot, mom, lsham, hoh, ee, eeo, hall, hallo, enim, obarm) &
+         bind(C, name='rsrec_build_hamiltonian') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double, c_double_complex
+         type(c_ptr), value :: h, ee, eeo, hall, hallo, enim, obarm
+         real(c_double), intent(in) :: hhh(9, 9, *), mom(3, *)
+         integer(c_int32_t), intent(in) :: jt(*), it(*)
+         complex(c_double_complex), intent(in) :: pot(9, 12, *), lsham(18, 18, *)
+         integer(c_int), value :: hoh
          integer(c_int) :: rc
       end function
 

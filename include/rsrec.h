@@ -106,6 +106,22 @@ int rsrec_create_ll_map(rsrec_handle h, int site, int lld, int32_t *izeroll);
 int rsrec_orbital_moments(rsrec_handle h, int nstart, const int32_t *start_sites, const double *cr, double alat,
                           int lld, double a_scale, double b_shift, rsrec_cplx *mu_n_orb);
 
+/* ---- device-side assembly of the block sets: build_bulkham / build_locham with chbar_nc's
+ * orbital part, ham0m_nc, hcpx, build_obarm, build_enim (hamiltonian.f90:1481-1667, 2225-2369; math.f90:1508-1577).
+ * Replaces rsrec_set_hamiltonian: the sets the recursion kernels read are produced on the device from
+ *   hhh  (9,9,nslot,ncls) real : hhh(ilm,jlm) = real(sbar(jlm,ilm,m,num(ia))) as hmfind returns it, for slot m of class c
+ *                                (classes: atom types 1..ntype through atlist, then local sites 1..nmax);
+ *   jt   (nslot,ncls) int32    : type iz of the atom in slot m (slot 1 = the atom itself), 0 = no neighbour -> zero block;
+ *   it   (ncls) int32          : type of the class's own atom;
+ *   pot  (9,12,ntype) complex  : wx0, wx1, cx0, cx1, cex0, cex1, obx0, obx1, cx(:,1), cx(:,2), cex(:,1), cex(:,2)
+ *                                of symbolic_atoms(type)%potential (potential.f90:56-65);
+ *   mom  (3,ntype), lsham (18,18,ntype) (build_lsham stays on the host: constants).
+ * Optional downloads (NULL to skip) in the reference's shapes: ee, eeo (18,18,nslot,ntype), hall, hallo
+ * (18,18,nslot,nmax), enim, obarm (18,18,ntype) for the host modules that still read them. */
+int rsrec_build_hamiltonian(rsrec_handle h, const double *hhh, const int32_t *jt, const int32_t *it,
+                            const rsrec_cplx *pot, const double *mom, const rsrec_cplx *lsham, int hoh, rsrec_cplx *ee,
+                            rsrec_cplx *eeo, rsrec_cplx *hall, rsrec_cplx *hallo, rsrec_cplx *enim, rsrec_cplx *obarm);
+
 /* ---- neighbour table on the device: lattice%nncal + lattice%remd (lattice.f90:3035-3123,
  * 2823-2907) with a cell grid instead of the O(kk^2) pair loop; identical table (integers, bit-exact).
  * crd (3,kk) = cr*alat; no (kk) = lattice%num (bravais type of each site); iu (ntot) = representative site of each

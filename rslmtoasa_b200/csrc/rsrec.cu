@@ -11,6 +11,7 @@
 #include "kernels_kubo.cuh"
 #include "kernels_post.cuh"
 #include "kernels_lattice.cuh"
+#include "kernels_ham.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -59,6 +60,11 @@ struct rsrec_handle_s {
   // device operator data
   int32_t *d_nbr = nullptr, *d_cls = nullptr;
   DevBuf Hmain, Hh, Hho_neg, Hx, Hscalar, Hva, Hvb, Hvoa_neg, Hvob_neg;
+  // complex block sets in the reference's layout, classes = types then local sites: ee|hall, eeo|hallo, lsham, enim,
+  // obarm.  Filled from the host arrays (rsrec_set_hamiltonian) or assembled on the device (rsrec_build_hamiltonian).
+  DevBuf cBLK, cBLKO, cLS, cENIM, cOBARM, cV[2], cVO[2];
+  int32_t *d_cls_type = nullptr;
+  bool ham_on_device = false;  // cBLK.. are current (device-side assembly): do not re-stage from the host copies
   DmmaTiles tiles;
   // work vectors and small matrices
   std::vector<DevBuf> vecs;
@@ -181,60 +187,68 @@ static int ensure_ready(H *h) {
       for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj[fill[a]++] = i; }
   }
 
-  auto src_block = [&](const std::vector<cplx> &ty, const std::vector<cplx> &loc, int c, int m) -> const cplx * {
-    if (c < h->ntype) return ty.data() + (size_t)BLKC * (m + (size_t)nslot * c);
-    return loc.data() + (size_t)BLKC * (m + (size_t)nslot * (c - h->ntype));
+  // class -> atom type (for the per-type on-site terms lsham / enim)
+  std::vector<int32_t> cls_type(ncls);
+  for (int c = 0; c < ncls; c++) cls_type[c] = c < h->ntype ? c : h->iz[c - h->ntype] - 1;
+  if (!h->d_cls_type) CUDA_TRY(cudaMalloc(&h->d_cls_type, ncls * sizeof(int32_t)));
+  CUDA_TRY(cudaMemcpy(h->d_cls_type, cls_type.data(), ncls * sizeof(int32_t), cudaMemcpyHostToDevice));
+  const size_t nblk = (size_t)ncls * nslot, ntb = (size_t)h->ntype * nslot;
+  const size_t setn = nblk * HBLK;
+  if (!h->ham_on_device) {  // stage the reference's arrays: ee followed by hall = blocks of classes 0..ncls-1
+    auto stage = [&](DevBuf &dst, const std::vector<cplx> &ty, const std::vector<cplx> &loc) -> int {
+      std::vector<double> st(nblk * BLKD, 0.0);
+      if (!ty.empty()) memcpy(st.data(), ty.data(), ntb * BLKD * sizeof(double));
+      if (!loc.empty()) memcpy(st.data() + ntb * BLKD, loc.data(), (nblk - ntb) * BLKD * sizeof(double));
+      return upload(dst, st);
+    };
+    TRY(stage(h->cBLK, h->ee, h->hall));
+    std::vector<double> ls((const double *)h->lsham.data(), (const double *)h->lsham.data() + (size_t)h->ntype * BLKD);
+    TRY(upload(h->cLS, ls));
+    if (h->hoh) {
+      TRY(stage(h->cBLKO, h->eeo, h->hallo));
+      std::vector<double> en((const double *)h->enim.data(), (const double *)h->enim.data() + (size_t)h->ntype * BLKD);
+      TRY(upload(h->cENIM, en));
+    }
+  }
+  // HR36 packing on the device (hamiltonian.f90:1553-1667 exports): locham = H_on + lsham summed before the product
+  // (1582, 1608); scalar recursion: only the two 9x9 spin-diagonal sub-blocks act, no lsham (recursion.f90:3337-3342)
+  const dim3 pg(nslot, ncls);
+  auto pack = [&](DevBuf &dst, const double *src, int ncls_src, const double *add, double scale, int spin_diag, int skip_on) -> int {
+    TRY(dev_alloc(dst, setn, false));
+    k_pack_hr36<<<pg, BLKC, 0, h->st>>>((const double2 *)src, ncls_src, (const double2 *)add, h->d_cls_type, nslot, scale, spin_diag, skip_on, 0, dst.p);
+    h->launches++;
+    return RSREC_OK;
   };
-  auto cls_type = [&](int c) { return c < h->ntype ? c : h->iz[c - h->ntype] - 1; };
-  const size_t setn = (size_t)ncls * nslot * HBLK;
-  std::vector<double> hm(setn, 0.0), hs(setn, 0.0);
-  for (int c = 0; c < ncls; c++)
-    for (int m = 0; m < nslot; m++) {
-      const cplx *b = src_block(h->ee, h->hall, c, m);
-      double *d = hm.data() + ((size_t)c * nslot + m) * HBLK;
-      pack_block(b, d, 1.0);
-      if (m == 0) add_block(h->lsham.data() + (size_t)BLKC * cls_type(c), d);  // locham = H_on + lsham (1582, 1608)
-      // scalar recursion: only the two 9x9 spin-diagonal sub-blocks act, no lsham (recursion.f90:3337-3342)
-      cplx sd[BLKC];
-      for (int k = 0; k < NB; k++)
-        for (int r = 0; r < NB; r++) {
-          const bool keep = (r < 9) == (k < 9);
-          sd[r + NB * k].re = keep ? b[r + NB * k].re : 0.0;
-          sd[r + NB * k].im = keep ? b[r + NB * k].im : 0.0;
-        }
-      pack_block(sd, hs.data() + ((size_t)c * nslot + m) * HBLK, 1.0);
-    }
-  TRY(upload(h->Hmain, hm));
-  TRY(upload(h->Hscalar, hs));
+  TRY(pack(h->Hmain, h->cBLK.p, ncls, h->cLS.p, 1.0, 0, 0));
+  TRY(pack(h->Hscalar, h->cBLK.p, ncls, nullptr, 1.0, 1, 0));
   if (h->hoh) {
-    std::vector<double> hh(setn, 0.0), ho(setn, 0.0), hx((size_t)ncls * HBLK, 0.0);
-    for (int c = 0; c < ncls; c++) {
-      for (int m = 0; m < nslot; m++) {
-        pack_block(src_block(h->ee, h->hall, c, m), hh.data() + ((size_t)c * nslot + m) * HBLK, 1.0);
-        pack_block(src_block(h->eeo, h->hallo, c, m), ho.data() + ((size_t)c * nslot + m) * HBLK, -1.0);
-      }
-      pack_block(h->enim.data() + (size_t)BLKC * cls_type(c), hx.data() + (size_t)c * HBLK, 1.0);
-      add_block(h->lsham.data() + (size_t)BLKC * cls_type(c), hx.data() + (size_t)c * HBLK);
-    }
-    TRY(upload(h->Hh, hh));
-    TRY(upload(h->Hho_neg, ho));
-    TRY(upload(h->Hx, hx));
+    TRY(pack(h->Hh, h->cBLK.p, ncls, nullptr, 1.0, 0, 0));
+    TRY(pack(h->Hho_neg, h->cBLKO.p, ncls, nullptr, -1.0, 0, 0));
+    TRY(dev_alloc(h->Hx, (size_t)ncls * HBLK, false));  // enim + lsham of the class's type
+    k_pack_hr36<<<dim3(1, ncls), BLKC, 0, h->st>>>((const double2 *)h->cENIM.p, ncls, (const double2 *)h->cLS.p, h->d_cls_type, 1, 1.0, 0, 0, 1, h->Hx.p);
+    h->launches++;
   }
   // velocity operators are type-indexed; the reference skips the site-indexed region entirely
   // (loops start at nmax+1, recursion.f90:603-634): local classes keep zero blocks.
   for (int s = 0; s < 2; s++) {
     if (!h->have_op[s]) continue;
     const std::vector<cplx> &v = s == 0 ? h->v_a : h->v_b, &vo = s == 0 ? h->vo_a : h->vo_b;
-    std::vector<double> hv(setn, 0.0), hvo(setn, 0.0);
-    for (int c = 0; c < h->ntype; c++)
-      for (int m = 0; m < nslot; m++) {
-        pack_block(v.data() + (size_t)BLKC * (m + (size_t)nslot * c), hv.data() + ((size_t)c * nslot + m) * HBLK, 1.0);
-        if (h->hoh && !vo.empty() && m > 0)  // on-site vo term is commented out in the reference (761)
-          pack_block(vo.data() + (size_t)BLKC * (m + (size_t)nslot * c), hvo.data() + ((size_t)c * nslot + m) * HBLK, -1.0);
+    std::vector<double> sv((const double *)v.data(), (const double *)v.data() + ntb * BLKD);
+    TRY(upload(h->cV[s], sv));
+    TRY(pack(s == 0 ? h->Hva : h->Hvb, h->cV[s].p, h->ntype, nullptr, 1.0, 0, 0));
+    if (h->hoh) {
+      if (!vo.empty()) {  // on-site vo term is commented out in the reference (761): slot 0 stays zero
+        std::vector<double> svo((const double *)vo.data(), (const double *)vo.data() + ntb * BLKD);
+        TRY(upload(h->cVO[s], svo));
+        TRY(pack(s == 0 ? h->Hvoa_neg : h->Hvob_neg, h->cVO[s].p, h->ntype, nullptr, -1.0, 0, 1));
+      } else {
+        TRY(dev_alloc(s == 0 ? h->Hvoa_neg : h->Hvob_neg, setn, false));
+        CUDA_TRY(cudaMemsetAsync((s == 0 ? h->Hvoa_neg : h->Hvob_neg).p, 0, setn * sizeof(double), h->st));
       }
-    TRY(upload(s == 0 ? h->Hva : h->Hvb, hv));
-    if (h->hoh) TRY(upload(s == 0 ? h->Hvoa_neg : h->Hvob_neg, hvo));
+    }
   }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->st));
   if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
   h->h2d_bytes += g_upload_bytes + (long long)h->tiles.ntiles * (DM_S + 1 + (long long)ng * DM_S) * 4;
   h->dirty = false;
@@ -633,7 +647,7 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
   if (const char *f = getenv("RSREC_SQRT_METHOD")) h->sqrt_method = atoi(f);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  if (dmma_configure() != 0 || kubo_configure() != 0 || post_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
+  if (dmma_configure() != 0 || kubo_configure() != 0 || post_configure() != 0 || ham_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
   *out = h;
   return RSREC_OK;
 }
@@ -650,6 +664,8 @@ int rsrec_destroy(rsrec_handle h) {
   dmma_free_tiles(h->tiles);
   if (h->d_nbr) cudaFree(h->d_nbr);
   if (h->d_cls) cudaFree(h->d_cls);
+  if (h->d_cls_type) cudaFree(h->d_cls_type);
+  { DevBuf *cb[] = {&h->cBLK, &h->cBLKO, &h->cLS, &h->cENIM, &h->cOBARM, &h->cV[0], &h->cV[1], &h->cVO[0], &h->cVO[1]}; for (auto b : cb) dev_free(*b); }
   if (h->plan.d_order) cudaFree(h->plan.d_order);
   if (h->plan.d_counts) cudaFree(h->plan.d_counts);
   if (h->d_si) { cudaFree(h->d_si); cudaFree(h->d_sj); cudaFree(h->d_as); cudaFree(h->d_bs); }
@@ -689,7 +705,7 @@ int rsrec_set_hamiltonian(rsrec_handle h, const cplx *ee, const cplx *eeo, const
     if (h->nmax > 0) h->hallo.assign(hallo, hallo + nl); else h->hallo.clear();
   }
   h->hoh = hoh ? 1 : 0;
-  h->have_ham = true; h->dirty = true;
+  h->have_ham = true; h->dirty = true; h->ham_on_device = false;
   return RSREC_OK;
 }
 
@@ -1542,6 +1558,55 @@ int rsrec_build_nn(int device, int kk, const double *crd, const int32_t *no, int
   if (hctr[3] == 2) return fail(RSREC_EINVAL, "rsrec_build_nn: VECTOR NOT FOUND (a site has a neighbour vector its type's representative lacks; lattice.f90:2896)");
   if (hctr[3] == 3) return fail(RSREC_EINVAL, "rsrec_build_nn: TYPE NO NOT FOUND (lattice.f90:2860)");
   CUDA_TRY(cudaMemcpy(nn, B.nn, sizeof(int32_t) * (size_t)kk * ncols, cudaMemcpyDeviceToHost));
+  return RSREC_OK;
+}
+
+// Device-side assembly of the block sets: what build_bulkham / build_locham (+ chbar_nc's orbital
+// part, ham0m_nc, hcpx, build_obarm, build_enim) compute on the host, from the structure-constant blocks and the
+// potential parameters, straight into the device-resident sets the recursion kernels read.
+int rsrec_build_hamiltonian(rsrec_handle h, const double *hhh, const int32_t *jt, const int32_t *it, const cplx *pot,
+                            const double *mom, const cplx *lsham, int hoh, cplx *ee, cplx *eeo, cplx *hall, cplx *hallo,
+                            cplx *enim, cplx *obarm) {
+  if (!h || !hhh || !jt || !it || !pot || !mom || !lsham) return fail(RSREC_EINVAL, "rsrec_build_hamiltonian: null argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const int ncls = h->ncls, nslot = h->nslot, ntype = h->ntype;
+  for (int c = 0; c < ncls; c++) {
+    if (it[c] < 1 || it[c] > ntype) return fail(RSREC_EINVAL, "rsrec_build_hamiltonian: it out of range");
+    for (int m = 0; m < nslot; m++)
+      if (jt[m + nslot * c] < 0 || jt[m + nslot * c] > ntype) return fail(RSREC_EINVAL, "rsrec_build_hamiltonian: jt out of range");
+  }
+  const size_t nblk = (size_t)ncls * nslot;
+  TRY(to_dev(h, h->post[0], hhh, 81 * nblk));
+  TRY(dev_alloc(h->post[1], (nblk + ncls + 1) / 2 + 1, false));
+  int32_t *d_jt = (int32_t *)h->post[1].p, *d_it = d_jt + nblk;
+  CUDA_TRY(cudaMemcpyAsync(d_jt, jt, nblk * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(d_it, it, ncls * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+  h->h2d_bytes += (long long)((nblk + ncls) * sizeof(int32_t));
+  TRY(to_dev(h, h->post[2], pot, (size_t)2 * 9 * POT_NPAR * ntype));
+  TRY(to_dev(h, h->post[3], mom, (size_t)3 * ntype));
+  TRY(to_dev(h, h->cLS, lsham, (size_t)ntype * BLKD));
+  TRY(dev_alloc(h->cBLK, nblk * BLKD, false));
+  TRY(dev_alloc(h->cBLKO, nblk * BLKD, false));
+  TRY(dev_alloc(h->cENIM, (size_t)ntype * BLKD, false));
+  TRY(dev_alloc(h->cOBARM, (size_t)ntype * BLKD, false));
+  k_ham_blocks<<<dim3(nslot, ncls), 96, 0, h->st>>>(h->post[0].p, d_jt, d_it, (const double2 *)h->post[2].p, h->post[3].p, hoh ? 1 : 0, nslot, (double2 *)h->cBLK.p);
+  k_ham_onsite18<<<dim3(ntype, 2), 96, 0, h->st>>>((const double2 *)h->post[2].p, h->post[3].p, (double2 *)h->cOBARM.p, (double2 *)h->cENIM.p);
+  h->launches += 2;
+  if (hoh) {
+    k_ham_times_o<<<dim3(nslot, ncls), BLKC, 0, h->st>>>((const double2 *)h->cBLK.p, (const double2 *)h->cOBARM.p, d_jt, nslot, (double2 *)h->cBLKO.p);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  const size_t ntb = (size_t)ntype * nslot;
+  if (ee) TRY(to_host(h, ee, h->cBLK.p, ntb * BLKD));
+  if (hall && h->nmax > 0) TRY(to_host(h, hall, h->cBLK.p + ntb * BLKD, (nblk - ntb) * BLKD));
+  if (hoh && eeo) TRY(to_host(h, eeo, h->cBLKO.p, ntb * BLKD));
+  if (hoh && hallo && h->nmax > 0) TRY(to_host(h, hallo, h->cBLKO.p + ntb * BLKD, (nblk - ntb) * BLKD));
+  if (enim) TRY(to_host(h, enim, h->cENIM.p, (size_t)ntype * BLKD));
+  if (obarm) TRY(to_host(h, obarm, h->cOBARM.p, (size_t)ntype * BLKD));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  h->hoh = hoh ? 1 : 0;
+  h->have_ham = true; h->dirty = true; h->ham_on_device = true;
   return RSREC_OK;
 }
 

@@ -99,6 +99,35 @@ class Recursion:
                 v, vo = _fc(getattr(ham, "v_" + slot)), _fc(getattr(ham, "vo_" + slot, None))
                 _lib.check(L.rsrec_set_operator(self._h, ord(slot), _p(v), _p(vo)))
 
+    def build_hamiltonian(self, hhh, jt, it, pot, mom, lsham, hoh=False, download=True):
+        """Device-side build_bulkham / build_locham (hamiltonian.f90:1553-1667): assembles the block sets on the GPU
+        from structure-constant blocks and potential parameters (see include/rsrec.h).  `pot` is a dict with the
+        (9,ntype) arrays wx0 wx1 cx0 cx1 cex0 cex1 obx0 obx1 and the (9,2,ntype) arrays cx, cex.  With download=True the
+        reference's arrays come back as a dict (ee, eeo, hall, hallo, enim, obarm)."""
+        lat = self.lattice
+        nt, ns, nl = lat.ntype, lat.nslot, lat.nmax
+        packed = np.zeros((9, 12, nt), np.complex128, order="F")
+        for k, name in enumerate(("wx0", "wx1", "cx0", "cx1", "cex0", "cex1", "obx0", "obx1")):
+            packed[:, k, :] = pot[name]
+        packed[:, 8, :], packed[:, 9, :] = pot["cx"][:, 0, :], pot["cx"][:, 1, :]
+        packed[:, 10, :], packed[:, 11, :] = pot["cex"][:, 0, :], pot["cex"][:, 1, :]
+        hhh = np.asfortranarray(hhh, dtype=np.float64)
+        jt = np.asfortranarray(jt, dtype=np.int32)
+        it = np.ascontiguousarray(it, dtype=np.int32)
+        mom = np.asfortranarray(mom, dtype=np.float64)
+        ls = _fc(lsham)
+        out = {}
+        if download:
+            out = {"ee": np.zeros((NB, NB, ns, nt), np.complex128, order="F"),
+                   "eeo": np.zeros((NB, NB, ns, nt), np.complex128, order="F") if hoh else None,
+                   "hall": np.zeros((NB, NB, ns, nl), np.complex128, order="F") if nl else None,
+                   "hallo": np.zeros((NB, NB, ns, nl), np.complex128, order="F") if (nl and hoh) else None,
+                   "enim": np.zeros((NB, NB, nt), np.complex128, order="F"),
+                   "obarm": np.zeros((NB, NB, nt), np.complex128, order="F")}
+        _lib.check(self._L.rsrec_build_hamiltonian(self._h, _p(hhh), _p(jt), _p(it), _p(packed), _p(mom), _p(ls), int(hoh),
+                                                   *[_p(out.get(k)) for k in ("ee", "eeo", "hall", "hallo", "enim", "obarm")]))
+        return out
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._L.rsrec_destroy(self._h)
