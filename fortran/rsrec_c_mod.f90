@@ -22,6 +22,7 @@ module rsrec_c_mod
    public :: rsrec_lanczos_block, rsrec_lanczos_scalar, rsrec_zsqr, rsrec_cheb_moments, rsrec_cheb_moments_random
    public :: rsrec_kubo_moments, rsrec_ham_vec_matmul, rsrec_velo_vec_matmul, rsrec_last_error_f, rsrec_check
    public :: rsrec_create_ll_map, rsrec_orbital_moments, rsrec_build_nn, rsrec_build_hamiltonian
+   public :: rsrec_rotate_to_local_axis, rsrec_rotate_from_local_axis, rsrec_lanczos_block_local_axis
    ! consumers of the recursion results (green.f90, density_of_states.f90, conductivity.f90) and fused drivers
    public :: rsrec_bpopt, rsrec_get_terminf, rsrec_bgreen, rsrec_block_green, rsrec_chebyshev_green, rsrec_density
    public :: rsrec_sgreen, rsrec_conductivity_integrand, rsrec_recur_b_green, rsrec_cheb_recur_green
@@ -178,6 +179,32 @@ module rsrec_c_mod
          integer(c_int32_t), intent(in) :: jt(*), it(*)
          complex(c_double_complex), intent(in) :: pot(9, 12, *), lsham(18, 18, *)
          integer(c_int), value :: hoh
+         integer(c_int) :: rc
+      end function
+
+      ! hamiltonian%rotate_to_local_axis / rotate_from_local_axis: hamiltonian.f90:2442-2484
+      function rsrec_rotate_to_local_axis(h, m_loc) bind(C, name='rsrec_rotate_to_local_axis') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(in) :: m_loc(3)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_rotate_from_local_axis(h) bind(C, name='rsrec_rotate_from_local_axis') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int) :: rc
+      end function
+
+      ! recur_b with hamiltonian%local_axis (recursion.f90:1826-1832); mom(3, nunits)
+      function rsrec_lanczos_block_local_axis(h, nunits, site_i, mom, lld, a_b, b2_b) &
+         bind(C, name='rsrec_lanczos_block_local_axis') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nunits, lld
+         integer(c_int32_t), intent(in) :: site_i(*)
+         real(c_double), intent(in) :: mom(3, *)
+         complex(c_double_complex), intent(out) :: a_b(18, 18, lld, *), b2_b(18, 18, lld, *)
          integer(c_int) :: rc
       end function
 

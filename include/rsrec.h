@@ -122,6 +122,17 @@ int rsrec_build_hamiltonian(rsrec_handle h, const double *hhh, const int32_t *jt
                             const rsrec_cplx *pot, const double *mom, const rsrec_cplx *lsham, int hoh, rsrec_cplx *ee,
                             rsrec_cplx *eeo, rsrec_cplx *hall, rsrec_cplx *hallo, rsrec_cplx *enim, rsrec_cplx *obarm);
 
+/* hamiltonian%rotate_to_local_axis / rotate_from_local_axis (hamiltonian.f90:2442-2484; rotmag_loc, ROTMAT, DSs, car2sph
+ * of math.f90:1981-2192): the device-resident sets ee, hall (and eeo, hallo, enim when hoh) become R^H X R with R the
+ * rotation that takes m_loc to the z axis, always starting from the sets as built (the reference's *_glob copies); lsham
+ * is not rotated, like the reference.  No host round trip: the rotated sets exist only on the device. */
+int rsrec_rotate_to_local_axis(rsrec_handle h, const double *m_loc /* (3) */);
+int rsrec_rotate_from_local_axis(rsrec_handle h);
+/* recur_b with hamiltonian%local_axis set (recursion.f90:1826-1832): unit u runs on the sets rotated to mom(:,u)
+ * (mom (3,nunits) = symbolic_atoms(i)%potential%mom); the sets stay rotated to the last unit's axis, like the reference. */
+int rsrec_lanczos_block_local_axis(rsrec_handle h, int nunits, const int32_t *site_i, const double *mom, int lld,
+                                   rsrec_cplx *a_b, rsrec_cplx *b2_b);
+
 /* ---- neighbour table on the device: lattice%nncal + lattice%remd (lattice.f90:3035-3123,
  * 2823-2907) with a cell grid instead of the O(kk^2) pair loop; identical table (integers, bit-exact).
  * crd (3,kk) = cr*alat; no (kk) = lattice%num (bravais type of each site); iu (ntot) = representative site of each

@@ -158,3 +158,79 @@ def pauli_block(it, jt, onsite, hhh, pot, mom, hoh):
             b[:, l, :, l] += c0 * np.eye(2) + c1 * msi
     b = b.reshape(18, 18)
     return np.kron(np.eye(2), VC) @ b @ np.kron(np.eye(2), V)
+
+
+# ---- local-axis rotation: rotmag_loc / ROTMAT / DSs / car2sph (math.f90:1981-2192) -------------------------------------
+def _factint(n):
+    if n < 0:
+        return 0
+    f = 1
+    for i in range(1, n + 1):
+        f *= i
+    return f
+
+
+def _binom(x, y):
+    if y < 0 or y > x:
+        return 0
+    return _factint(x) // (_factint(y) * _factint(x - y))
+
+
+def _nint(x):
+    return int(np.floor(x + 0.5)) if x >= 0 else -int(np.floor(-x + 0.5))
+
+
+def dss(J, M, Mp, beta):
+    """Wigner small-d element as the reference sums it (math.f90:2107-2125)"""
+    smin = max(0, _nint(-Mp - M))
+    smax = min(_nint(J - Mp), _nint(J - M))
+    out = 0.0
+    for s in range(smin, smax + 1):
+        ds = s * 1.0
+        dst = _binom(_nint(J + M), _nint(J - Mp - ds)) * _binom(_nint(J - M), s) * (-1.0) ** _nint(J - Mp - ds)
+        out = out + dst * np.cos(0.5 * beta) ** (2 * ds + Mp + M) * np.sin(0.5 * beta) ** (2 * J - 2 * ds - Mp - M)
+    return out * np.sqrt(1.0 * _factint(_nint(J + Mp)) * _factint(_nint(J - Mp)) / (_factint(_nint(J - M)) * _factint(_nint(J + M))))
+
+
+def rotmat(a, b, g):
+    """ROTMAT (math.f90:2055-2105): 18x18 = orbital D-matrices (l = 0,1,2) x spin-1/2 D-matrix"""
+    sm = np.zeros((2, 2), complex)
+    sm[0, 0] = dss(0.5, 0.5, 0.5, b) * np.exp(-I * (0.5 * a + 0.5 * g))
+    sm[0, 1] = dss(0.5, 0.5, -0.5, b) * np.exp(-I * (0.5 * a - 0.5 * g))
+    sm[1, 0] = dss(0.5, -0.5, 0.5, b) * np.exp(-I * (-0.5 * a + 0.5 * g))
+    sm[1, 1] = dss(0.5, -0.5, -0.5, b) * np.exp(-I * (-0.5 * a - 0.5 * g))
+    m9 = np.zeros((9, 9), complex)
+    for J in range(3):
+        S = J * J + 1 + J
+        for M in range(-J, J + 1):
+            for Mp in range(-J, J + 1):
+                m9[S + M - 1, S + Mp - 1] = dss(J * 1.0, M * 1.0, Mp * 1.0, b) * np.exp(-I * (M * a + Mp * g))
+    mat = np.zeros((18, 18), complex)
+    for M in range(9):
+        for Mp in range(9):
+            mat[Mp, M] = m9[Mp, M] * sm[0, 0]
+            mat[Mp, M + 9] = m9[Mp, M] * sm[0, 1]
+            mat[Mp + 9, M] = m9[Mp, M] * sm[1, 0]
+            mat[Mp + 9, M + 9] = m9[Mp, M] * sm[1, 1]
+    return mat
+
+
+def car2sph(c):
+    """(theta, phi, r2) with the reference's conventions: theta = atan2(y,x) (0 when x=y=0), phi = acos(z / r^2)"""
+    x, y, z = c
+    d2, r2 = x * x + y * y, x * x + y * y + z * z
+    theta = 0.0 if d2 == 0.0 else np.arctan2(y, x)
+    return theta, np.arccos(z / r2), r2
+
+
+def local_axis_rmat(mom):
+    alfa, beta, _ = car2sph(mom)
+    return rotmat(alfa, beta, 0.0)
+
+
+def rotmag_loc(mat_in, mom):
+    """MATout(:,:,j) = R^H (MATin(:,:,j) R) for every 18x18 block of mat_in (any trailing shape)"""
+    r = local_axis_rmat(mom)
+    flat = mat_in.reshape(18, 18, -1, order="F")
+    out = np.stack([r.conj().T @ (flat[:, :, j] @ r) for j in range(flat.shape[2])], axis=2)
+    return np.asfortranarray(out.reshape(mat_in.shape, order="F"))

@@ -18,7 +18,8 @@ SYMBOLS = [
     "rsrec_bpopt", "rsrec_get_terminf", "rsrec_bgreen", "rsrec_block_green", "rsrec_chebyshev_green", "rsrec_density",
     "rsrec_sgreen", "rsrec_conductivity_integrand", "rsrec_recur_b_green", "rsrec_cheb_recur_green",
     "rsrec_kubo_conductivity", "rsrec_create_ll_map", "rsrec_orbital_moments",
-    "rsrec_build_nn", "rsrec_build_hamiltonian",
+    "rsrec_build_nn", "rsrec_build_hamiltonian", "rsrec_rotate_to_local_axis", "rsrec_rotate_from_local_axis",
+    "rsrec_lanczos_block_local_axis",
 ]
 
 
@@ -85,6 +86,9 @@ def load():
     L.rsrec_orbital_moments.argtypes = [vp, i, vp, vp, d, i, d, d, vp]
     L.rsrec_build_nn.argtypes = [i, i, vp, vp, i, vp, d, vp, vp, vp, d, i, vp, C.POINTER(i)]
     L.rsrec_build_hamiltonian.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
+    L.rsrec_rotate_to_local_axis.argtypes = [vp, vp]
+    L.rsrec_rotate_from_local_axis.argtypes = [vp]
+    L.rsrec_lanczos_block_local_axis.argtypes = [vp, i, vp, vp, i, vp, vp]
     _lib = L
     return L
 

@@ -165,3 +165,24 @@ k_pack_hr36(const double2 *__restrict__ src, int ncls_src, const double2 *__rest
   d[(r + NB) * COLD + k] = v.y;
   d[(r + NB) * COLD + NB + k] = v.x;
 }
+
+// rotmag_loc (math.f90:1981-2053): out(:,:,j) = R^H (in(:,:,j) R) for every 18x18 block; R = ROTMAT(alfa, beta, 0)
+__global__ void __launch_bounds__(BLKC)
+k_rotmag(const double2 *__restrict__ in, const double2 *__restrict__ R, double2 *__restrict__ out) {
+  __shared__ double2 A[BLKC], Rm[BLKC], T[BLKC];
+  const int t = threadIdx.x, r = t % NB, k = t / NB;
+  const size_t off = (size_t)BLKC * blockIdx.x;
+  A[t] = in[off + t];
+  Rm[t] = R[t];
+  __syncthreads();
+  double2 s = make_double2(0.0, 0.0);
+  for (int l = 0; l < NB; l++) s = c_add(s, c_mul(A[r + NB * l], Rm[l + NB * k]));   // h * Ux
+  T[t] = s;
+  __syncthreads();
+  s = make_double2(0.0, 0.0);
+  for (int l = 0; l < NB; l++) {                                                      // Ux' * (h * Ux)
+    const double2 u = Rm[l + NB * r];
+    s = c_add(s, c_mul(make_double2(u.x, -u.y), T[l + NB * k]));
+  }
+  out[off + t] = s;
+}

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -56,13 +57,15 @@ struct rsrec_handle_s {
   // host copies of the reference arrays (small) so that device sets can be (re)built in any call order
   std::vector<int32_t> nn, iz;
   std::vector<cplx> ee, eeo, hall, hallo, lsham, enim, v_a, v_b, vo_a, vo_b;
-  bool have_lat = false, have_ham = false, have_op[2] = {false, false}, dirty = true;
+  bool have_lat = false, have_ham = false, have_op[2] = {false, false}, dirty = true /* lattice tables */, dirty_ham = true /* block sets */;
   // device operator data
   int32_t *d_nbr = nullptr, *d_cls = nullptr;
   DevBuf Hmain, Hh, Hho_neg, Hx, Hscalar, Hva, Hvb, Hvoa_neg, Hvob_neg;
   // complex block sets in the reference's layout, classes = types then local sites: ee|hall, eeo|hallo, lsham, enim,
   // obarm.  Filled from the host arrays (rsrec_set_hamiltonian) or assembled on the device (rsrec_build_hamiltonian).
   DevBuf cBLK, cBLKO, cLS, cENIM, cOBARM, cV[2], cVO[2];
+  DevBuf gBLK, gBLKO, gENIM;  // the reference's *_glob copies (hamiltonian.f90:70-80) while rotated to a local axis
+  bool have_glob = false;
   int32_t *d_cls_type = nullptr;
   bool ham_on_device = false;  // cBLK.. are current (device-side assembly): do not re-stage from the host copies
   DmmaTiles tiles;
@@ -153,9 +156,10 @@ static int upload(DevBuf &b, const std::vector<double> &host) {
 static int ensure_ready(H *h) {
   if (!h->have_lat) return fail(RSREC_EINVAL, "rsrec_set_lattice has not been called");
   if (!h->have_ham) return fail(RSREC_EINVAL, "rsrec_set_hamiltonian has not been called");
-  if (!h->dirty) return RSREC_OK;
+  if (!h->dirty && !h->dirty_ham) return RSREC_OK;
   g_upload_bytes = 0;
   const int kk = h->kk, nslot = h->nslot, ncls = h->ncls, ng = h->ncols;
+  if (h->dirty) {
   // neighbour table [slot][site], slot 0 = self, missing -> kk
   std::vector<int32_t> nbr((size_t)ng * kk), cls(kk);
   for (int i = 0; i < kk; i++) {
@@ -186,6 +190,12 @@ static int ensure_ready(H *h) {
     for (int j = 1; j < ng; j++)
       for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj[fill[a]++] = i; }
   }
+
+  if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
+  h->h2d_bytes += (long long)h->tiles.ntiles * (DM_S + 1 + (long long)ng * DM_S) * 4;
+  h->dirty = false;
+  h->dirty_ham = true;
+  }  // lattice tables
 
   // class -> atom type (for the per-type on-site terms lsham / enim)
   std::vector<int32_t> cls_type(ncls);
@@ -249,9 +259,8 @@ static int ensure_ready(H *h) {
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->st));
-  if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
-  h->h2d_bytes += g_upload_bytes + (long long)h->tiles.ntiles * (DM_S + 1 + (long long)ng * DM_S) * 4;
-  h->dirty = false;
+  h->h2d_bytes += g_upload_bytes;
+  h->dirty_ham = false;
   return RSREC_OK;
 }
 
@@ -665,7 +674,7 @@ int rsrec_destroy(rsrec_handle h) {
   if (h->d_nbr) cudaFree(h->d_nbr);
   if (h->d_cls) cudaFree(h->d_cls);
   if (h->d_cls_type) cudaFree(h->d_cls_type);
-  { DevBuf *cb[] = {&h->cBLK, &h->cBLKO, &h->cLS, &h->cENIM, &h->cOBARM, &h->cV[0], &h->cV[1], &h->cVO[0], &h->cVO[1]}; for (auto b : cb) dev_free(*b); }
+  { DevBuf *cb[] = {&h->cBLK, &h->cBLKO, &h->cLS, &h->cENIM, &h->cOBARM, &h->cV[0], &h->cV[1], &h->cVO[0], &h->cVO[1], &h->gBLK, &h->gBLKO, &h->gENIM}; for (auto b : cb) dev_free(*b); }
   if (h->plan.d_order) cudaFree(h->plan.d_order);
   if (h->plan.d_counts) cudaFree(h->plan.d_counts);
   if (h->d_si) { cudaFree(h->d_si); cudaFree(h->d_sj); cudaFree(h->d_as); cudaFree(h->d_bs); }
@@ -705,7 +714,7 @@ int rsrec_set_hamiltonian(rsrec_handle h, const cplx *ee, const cplx *eeo, const
     if (h->nmax > 0) h->hallo.assign(hallo, hallo + nl); else h->hallo.clear();
   }
   h->hoh = hoh ? 1 : 0;
-  h->have_ham = true; h->dirty = true; h->ham_on_device = false;
+  h->have_ham = true; h->dirty_ham = true; h->ham_on_device = false; h->have_glob = false;
   return RSREC_OK;
 }
 
@@ -715,7 +724,7 @@ int rsrec_set_operator(rsrec_handle h, int slot, const cplx *v_op, const cplx *v
   const int s = slot == 'a' ? 0 : 1;
   (s == 0 ? h->v_a : h->v_b).assign(v_op, v_op + nt);
   if (vo_op) (s == 0 ? h->vo_a : h->vo_b).assign(vo_op, vo_op + nt); else (s == 0 ? h->vo_a : h->vo_b).clear();
-  h->have_op[s] = true; h->dirty = true;
+  h->have_op[s] = true; h->dirty_ham = true;
   return RSREC_OK;
 }
 
@@ -1606,7 +1615,112 @@ int rsrec_build_hamiltonian(rsrec_handle h, const double *hhh, const int32_t *jt
   if (obarm) TRY(to_host(h, obarm, h->cOBARM.p, (size_t)ntype * BLKD));
   CUDA_TRY(cudaStreamSynchronize(h->st));
   h->hoh = hoh ? 1 : 0;
-  h->have_ham = true; h->dirty = true; h->ham_on_device = true;
+  h->have_ham = true; h->dirty_ham = true; h->ham_on_device = true; h->have_glob = false;
+  return RSREC_OK;
+}
+
+// ---- local spin axis (hamiltonian%rotate_to_local_axis / rotate_from_local_axis, hamiltonian.f90:2442-2484) -----------
+// ROTMAT / DSs / car2sph of math.f90:2055-2192, evaluated on the host (an 18x18 matrix of closed-form entries)
+static long long factint(int n) { if (n < 0) return 0; long long f = 1; for (int i = 1; i <= n; i++) f *= i; return f; }
+static long long binom_ll(int x, int y) { if (y < 0 || y > x) return 0; return factint(x) / (factint(y) * factint(x - y)); }
+static int nint_d(double x) { return (int)std::lround(x); }
+static double wigner_dss(double J, double M, double Mp, double beta) {
+  const int smin = std::max(0, nint_d(-Mp - M)), smax = std::min(nint_d(J - Mp), nint_d(J - M));
+  double d = 0.0;
+  for (int s = smin; s <= smax; s++) {
+    const double ds = s * 1.0;
+    const double dst = (double)binom_ll(nint_d(J + M), nint_d(J - Mp - ds)) * (double)binom_ll(nint_d(J - M), s) *
+                       std::pow(-1.0, nint_d(J - Mp - ds));
+    d += dst * std::pow(std::cos(0.5 * beta), 2 * ds + Mp + M) * std::pow(std::sin(0.5 * beta), 2 * J - 2 * ds - Mp - M);
+  }
+  return d * std::sqrt(1.0 * factint(nint_d(J + Mp)) * factint(nint_d(J - Mp)) / ((double)factint(nint_d(J - M)) * factint(nint_d(J + M))));
+}
+static void host_rotmat(const double mom[3], std::vector<std::complex<double>> &R) {
+  typedef std::complex<double> cd;
+  const double X = mom[0], Y = mom[1], Z = mom[2], D2 = X * X + Y * Y, R2 = X * X + Y * Y + Z * Z;
+  const double alfa = D2 == 0.0 ? 0.0 : std::atan2(Y, X), beta = std::acos(Z / R2), gama = 0.0;  // car2sph (sic: z / r^2)
+  const cd IM(0.0, 1.0);
+  cd SM[2][2];
+  SM[0][0] = wigner_dss(0.5, 0.5, 0.5, beta) * std::exp(-IM * (0.5 * alfa + 0.5 * gama));
+  SM[0][1] = wigner_dss(0.5, 0.5, -0.5, beta) * std::exp(-IM * (0.5 * alfa - 0.5 * gama));
+  SM[1][0] = wigner_dss(0.5, -0.5, 0.5, beta) * std::exp(-IM * (-0.5 * alfa + 0.5 * gama));
+  SM[1][1] = wigner_dss(0.5, -0.5, -0.5, beta) * std::exp(-IM * (-0.5 * alfa - 0.5 * gama));
+  cd M9[9][9];
+  for (auto &row : M9) for (auto &e : row) e = 0.0;
+  for (int J = 0; J <= 2; J++) {
+    const int S = J * J + 1 + J;
+    for (int M = -J; M <= J; M++)
+      for (int Mp = -J; Mp <= J; Mp++)
+        M9[S + M - 1][S + Mp - 1] = wigner_dss(J * 1.0, M * 1.0, Mp * 1.0, beta) * std::exp(-IM * ((double)M * alfa + (double)Mp * gama));
+  }
+  R.assign(BLKC, cd(0.0, 0.0));
+  for (int M = 0; M < 9; M++)
+    for (int Mp = 0; Mp < 9; Mp++) {
+      R[Mp + NB * M] = M9[Mp][M] * SM[0][0];
+      R[Mp + NB * (M + 9)] = M9[Mp][M] * SM[0][1];
+      R[(Mp + 9) + NB * M] = M9[Mp][M] * SM[1][0];
+      R[(Mp + 9) + NB * (M + 9)] = M9[Mp][M] * SM[1][1];
+    }
+}
+static int rotate_sets(H *h, const double m_loc[3]) {
+  TRY(ensure_ready(h));  // the current sets are staged on the device
+  const size_t nb = (size_t)h->ncls * h->nslot;
+  if (!h->have_glob) {  // *_glob = the sets as built (hamiltonian.f90:1609-1612, 1661-1664)
+    TRY(dev_alloc(h->gBLK, nb * BLKD, false));
+    CUDA_TRY(cudaMemcpyAsync(h->gBLK.p, h->cBLK.p, nb * BLKD * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    if (h->hoh) {
+      TRY(dev_alloc(h->gBLKO, nb * BLKD, false));
+      TRY(dev_alloc(h->gENIM, (size_t)h->ntype * BLKD, false));
+      CUDA_TRY(cudaMemcpyAsync(h->gBLKO.p, h->cBLKO.p, nb * BLKD * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+      CUDA_TRY(cudaMemcpyAsync(h->gENIM.p, h->cENIM.p, (size_t)h->ntype * BLKD * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    }
+    h->have_glob = true;
+  }
+  std::vector<std::complex<double>> R;
+  host_rotmat(m_loc, R);
+  TRY(to_dev(h, h->post[10], R.data(), BLKD));
+  k_rotmag<<<(unsigned)nb, BLKC, 0, h->st>>>((const double2 *)h->gBLK.p, (const double2 *)h->post[10].p, (double2 *)h->cBLK.p);
+  h->launches++;
+  if (h->hoh) {
+    k_rotmag<<<(unsigned)nb, BLKC, 0, h->st>>>((const double2 *)h->gBLKO.p, (const double2 *)h->post[10].p, (double2 *)h->cBLKO.p);
+    k_rotmag<<<(unsigned)h->ntype, BLKC, 0, h->st>>>((const double2 *)h->gENIM.p, (const double2 *)h->post[10].p, (double2 *)h->cENIM.p);
+    h->launches += 2;
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->st));  // R goes out of scope
+  h->ham_on_device = true;  // the rotated sets live only on the device
+  h->dirty_ham = true;      // repack (lsham is NOT rotated, like the reference)
+  return RSREC_OK;
+}
+
+int rsrec_rotate_to_local_axis(rsrec_handle h, const double *m_loc) {
+  if (!h || !m_loc) return fail(RSREC_EINVAL, "rsrec_rotate_to_local_axis: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  return rotate_sets(h, m_loc);
+}
+int rsrec_rotate_from_local_axis(rsrec_handle h) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  if (!h->have_glob) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t nb = (size_t)h->ncls * h->nslot;
+  CUDA_TRY(cudaMemcpyAsync(h->cBLK.p, h->gBLK.p, nb * BLKD * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  if (h->hoh) {
+    CUDA_TRY(cudaMemcpyAsync(h->cBLKO.p, h->gBLKO.p, nb * BLKD * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CUDA_TRY(cudaMemcpyAsync(h->cENIM.p, h->gENIM.p, (size_t)h->ntype * BLKD * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  }
+  h->dirty_ham = true;
+  return RSREC_OK;
+}
+// recur_b with hamiltonian%local_axis (recursion.f90:1826-1832): unit u runs on the sets rotated to mom(:,u); like the
+// reference the sets stay rotated to the last unit's axis on return (rsrec_rotate_from_local_axis restores them).
+int rsrec_lanczos_block_local_axis(rsrec_handle h, int nunits, const int32_t *site_i, const double *mom, int lld, cplx *a_b,
+                                   cplx *b2_b) {
+  if (!h || nunits < 0 || !a_b || !b2_b || lld < 1 || (nunits > 0 && (!site_i || !mom))) return fail(RSREC_EINVAL, "rsrec_lanczos_block_local_axis: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  for (int u = 0; u < nunits; u++) {
+    TRY(rotate_sets(h, mom + 3 * (size_t)u));
+    TRY(rsrec_lanczos_block(h, 1, site_i + u, nullptr, nullptr, nullptr, lld, a_b + (size_t)u * lld * BLKC, b2_b + (size_t)u * lld * BLKC));
+  }
   return RSREC_OK;
 }
 

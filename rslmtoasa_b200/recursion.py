@@ -128,6 +128,24 @@ class Recursion:
                                                    *[_p(out.get(k)) for k in ("ee", "eeo", "hall", "hallo", "enim", "obarm")]))
         return out
 
+    def rotate_to_local_axis(self, m_loc):
+        """hamiltonian%rotate_to_local_axis (hamiltonian.f90:2442-2463) on the device-resident sets."""
+        m = np.ascontiguousarray(m_loc, dtype=np.float64)
+        _lib.check(self._L.rsrec_rotate_to_local_axis(self._h, _p(m)))
+
+    def rotate_from_local_axis(self):
+        _lib.check(self._L.rsrec_rotate_from_local_axis(self._h))
+
+    def recur_b_local_axis(self, mom):
+        """recur_b with hamiltonian%local_axis (recursion.f90:1826-1832): mom (3, nrec) = the moments of the recursion atoms."""
+        s, e = self._local_units(len(self.lattice.irec))
+        sites = np.ascontiguousarray(self.lattice.irec[s - 1:e], dtype=np.int32)
+        mm = np.asfortranarray(np.asarray(mom, dtype=np.float64)[:, s - 1:e])
+        lld, n = self.control.lld, len(sites)
+        self.a_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        self.b2_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        _lib.check(self._L.rsrec_lanczos_block_local_axis(self._h, n, _p(sites), _p(mm), lld, _p(self.a_b), _p(self.b2_b)))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._L.rsrec_destroy(self._h)

@@ -85,3 +85,38 @@ def test_recursion_on_device_built_blocks(oracle_mod, hoh):
     orc = oracle_mod.Oracle(lat, ham3)
     oa, ob = orc.lanczos_block(lat.irec, 7)
     assert relerr(a1, oa) < 1e-10 and relerr(b1, ob) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["surface", "impurity_hoh"])
+def test_recur_b_local_axis(oracle_mod, name):
+    """per-unit rotation of the block sets on the device (rotmag_loc) == the oracle run on numpy-rotated host arrays"""
+    import copy
+    from rslmtoasa_b200 import Recursion, Control, Energy
+    lat, ham = case(name)
+    if name == "impurity_hoh":
+        lat.irec = np.array([1, 3], dtype=np.int32)
+    rng = np.random.default_rng(9)
+    mom = rng.normal(size=(3, len(lat.irec))); mom /= np.linalg.norm(mom, axis=0)
+    mom[:, 0] = [0.0, 0.0, 1.0]                               # identity rotation for the first unit
+    rec = Recursion(ham, lat, Control(lld=6), Energy(EMIN, EMAX))
+    rec.recur_b()
+    plain = rec.a_b.copy()
+    rec.recur_b_local_axis(mom)
+    assert relerr(rec.a_b[..., 0], plain[..., 0]) < 1e-13     # m = z: nothing changes
+    for u, site in enumerate(lat.irec):
+        h2 = copy.copy(ham)
+        h2.ee = HO.rotmag_loc(ham.ee, mom[:, u])
+        if lat.nmax:
+            h2.hall = HO.rotmag_loc(ham.hall, mom[:, u])
+        if ham.hoh:
+            h2.eeo, h2.enim = HO.rotmag_loc(ham.eeo, mom[:, u]), HO.rotmag_loc(ham.enim, mom[:, u])
+            if lat.nmax:
+                h2.hallo = HO.rotmag_loc(ham.hallo, mom[:, u])
+        oa, ob = oracle_mod.Oracle(lat, h2).lanczos_block([site], 6)
+        assert relerr(rec.a_b[..., u], oa[..., 0]) < 1e-10 and relerr(rec.b2_b[..., u], ob[..., 0]) < 1e-10
+    # the sets stay rotated to the last unit's axis (like the reference) until rotate_from_local_axis
+    rec.recur_b()
+    assert relerr(rec.a_b[..., -1], plain[..., -1]) > 1e-6
+    rec.rotate_from_local_axis()
+    rec.recur_b()
+    assert np.array_equal(rec.a_b, plain)

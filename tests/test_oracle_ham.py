@@ -69,3 +69,46 @@ def test_hermiticity_of_reciprocal_pairs():
     b01 = HO.spin_block(np.stack([HO.hcpx_cart2sph(h01[:, :, k]) for k in range(4)], axis=2))
     b10 = HO.spin_block(np.stack([HO.hcpx_cart2sph(h10[:, :, k]) for k in range(4)], axis=2))
     assert np.abs(b10 - b01.conj().T).max() < 1e-13
+
+
+def _spherical_L():
+    """L_z, L_x, L_y in the basis (00)(1-1)(10)(11)(2-2)..(22) from the ladder-operator definitions (independent of the
+    reference's tables)"""
+    lz = np.zeros((9, 9)); lp = np.zeros((9, 9))
+    for l in range(3):
+        s = l * l + l
+        for m in range(-l, l + 1):
+            lz[s + m, s + m] = m
+            if m < l:
+                lp[s + m + 1, s + m] = np.sqrt(l * (l + 1) - m * (m + 1))
+    lm = lp.T
+    return 0.5 * (lp + lm), -0.5j * (lp - lm), lz
+
+
+def test_local_axis_rotation_is_the_rotation_that_takes_m_to_z():
+    rng = np.random.default_rng(5)
+    assert np.allclose(HO.local_axis_rmat(np.array([0.0, 0.0, 1.0])), np.eye(18))
+    lx, ly, lz = _spherical_L()
+    for _ in range(4):
+        m = rng.normal(size=3); m /= np.linalg.norm(m)
+        r = HO.local_axis_rmat(m)
+        assert np.allclose(r.conj().T @ r, np.eye(18), atol=1e-13)                  # unitary
+        # spin: R^H (m.sigma) R = sigma_z ; orbital: R^H (m.L) R = L_z  (the moment direction becomes the z axis)
+        ms = np.kron(sum(m[k] * HO.SIG[k] for k in range(3)), np.eye(9))
+        assert np.allclose(r.conj().T @ ms @ r, np.kron(HO.SIG[2], np.eye(9)), atol=1e-12)
+        ml = np.kron(np.eye(2), m[0] * lx + m[1] * ly + m[2] * lz)
+        assert np.allclose(r.conj().T @ ml @ r, np.kron(np.eye(2), lz), atol=1e-12)
+
+
+def test_rotated_blocks_of_a_ferromagnet_are_spin_diagonal():
+    """all moments along m: after rotate_to_local_axis(m) the exchange part is sigma_z, so no spin mixing remains in
+    blocks built from rotation-invariant orbital parts (s-like structure constants)"""
+    hhh, jt, it, pot, mom = random_inputs(ntype=1, nslot=3, nloc=0)
+    hhh[:] = 0.0
+    hhh[0, 0] = 0.3                                    # s-s hopping only: orbital part invariant under rotation
+    for k in ("cx0", "cx1", "cex0", "cex1"):
+        pot[k][1:] = 0.0
+    blk, _, _, _ = HO.build_blocks(hhh, jt, it, pot, mom, False)
+    rot = HO.rotmag_loc(blk, mom[:, 0])
+    assert np.abs(blk[0, 9]).max() > 1e-3                                           # spin mixing in the global frame
+    assert np.abs(rot[:9, 9:]).max() < 1e-13 and np.abs(rot[9:, :9]).max() < 1e-13  # gone in the local frame
