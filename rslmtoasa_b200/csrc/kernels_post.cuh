@@ -135,6 +135,27 @@ __global__ void k_bpopt(const double *A, const double *RB, ChainLayout lay, int 
   if (ifail_o) ifail_o[ch] = ifail;
 }
 
+// the 18 diagonal chains of each unit only: chain c = (i, unit), results written to element (i,i) of a_inf/b_inf
+__global__ void k_bpopt_diag(const double *A, const double *RB, ChainLayout lay, int ll, int nchains, double *ainf_o,
+                             double *rbinf_o) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= nchains) return;
+  const long long off = (ch / lay.inner) * lay.outer_stride + (ch % lay.inner) * lay.inner_stride;
+  BpoptChain c;
+  c.a = A + off; c.rb = RB + off; c.ls = lay.lstride; c.n = ll - 1;
+  c.ainf = __ldg(c.a + (long long)(c.n - 1) * c.ls);
+  double bmax = 0.0, bmin = 0.0;
+  for (int jiter = 1;; jiter++) {
+    dev_emami(c, bmax, bmin);
+    const double s = __dadd_rn(bmax, bmin);
+    c.ainf = __dadd_rn(c.ainf, s);
+    if (fabs(s) <= 1.0e-05 || jiter > 300) break;
+  }
+  const int i = ch % NB, unit = ch / NB;
+  ainf_o[(size_t)unit * BLKC + i * (NB + 1)] = c.ainf;
+  rbinf_o[(size_t)unit * BLKC + i * (NB + 1)] = __ddiv_rn(__dsub_rn(bmax, bmin), 2.0);
+}
+
 // get_terminf's fix-ups (recursion.f90:2110-2136): a_inf, b_inf (18,18,na) in place; a_inf0, b_inf0 (na)
 __global__ void k_terminf_fix(double *a_inf, double *b_inf, double *a_inf0, double *b_inf0) {
   double *ai = a_inf + (size_t)blockIdx.x * BLKC, *bi = b_inf + (size_t)blockIdx.x * BLKC;
@@ -160,12 +181,15 @@ __global__ void k_terminf_fix(double *a_inf, double *b_inf, double *a_inf0, doub
 
 // ---- block continued fraction (bgreen) ------------------------------------------------------------------------
 #define BG_WARPS 8
+#ifndef BG_MINB
+#define BG_MINB 2
+#endif
 #define BG_LD 19  // padded column stride (complex) so that the 16-byte column accesses of 8 lanes hit 8 bank groups
 #define BG_MAT (NB * BG_LD)
 
 // a_b, b_b: (18,18,ll,na) complex, b_b = B (after zsqr); g: (18,18,nv,na).  Channels ie0..ie0+ie_len-1 (0-based) are
 // written, the rest of g is left untouched (the caller zeroes it, like bgreen's g_out = 0).
-__global__ void __launch_bounds__(BG_WARPS * 32)
+__global__ void __launch_bounds__(BG_WARPS * 32, BG_MINB)
 k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int ll, const double *__restrict__ ene,
          int nv, int ie0, int ie_len, const double *__restrict__ a_inf, const double *__restrict__ b_inf, double eta_re,
          double eta_im, int sym_term, double2 *__restrict__ g) {

@@ -1039,9 +1039,16 @@ static int grid_for(size_t n, int threads, int cap) { return (int)std::max<size_
 
 // get_terminf (recursion.f90:2092-2138) = get_cinf (324 bpopt chains per unit over the real parts) + fix-ups
 static int d_terminf(H *h, const double *d_ab, const double *d_bb, int na, int ll, double *d_ainf, double *d_binf,
-                     double *d_a0, double *d_b0) {
+                     double *d_a0, double *d_b0, bool diag_only = false) {
+  // diag_only: bgreen reads only a_inf(i,i), b_inf(i,i) (green.f90:1243-1262) and a_inf0/b_inf0 average the diagonal, so
+  // the callers that do not hand a_inf/b_inf back (block_green, the fused driver) run 18 chains per unit instead of 324
   const ChainLayout lay{BLKC, 2, 2LL * BLKC * ll, 2LL * BLKC};
   const int nch = BLKC * na;
+  if (diag_only) {
+    CUDA_TRY(cudaMemsetAsync(d_ainf, 0, 2 * (size_t)nch * sizeof(double), h->st));  // a_inf and b_inf are adjacent
+    const ChainLayout dl{NB, 2LL * (NB + 1), 2LL * BLKC * ll, 2LL * BLKC};
+    k_bpopt_diag<<<(NB * na + 63) / 64, 64, 0, h->st>>>(d_ab, d_bb, dl, ll, NB * na, d_ainf, d_binf);
+  } else
   k_bpopt<<<(nch + 63) / 64, 64, 0, h->st>>>(d_ab, d_bb, lay, ll, nch, d_ainf, d_binf, nullptr);
   k_terminf_fix<<<na, BLKC, 0, h->st>>>(d_ainf, d_binf, d_a0, d_b0);
   h->launches += 2;
@@ -1224,7 +1231,7 @@ int rsrec_block_green(rsrec_handle h, const cplx *a_b, const cplx *b_b, int na, 
   TRY(to_dev(h, h->post[4], e, nv));
   TRY(dev_alloc(h->post[5], (size_t)na * nv * BLKD, false));
   double *d_ai = h->post[2].p, *d_bi = d_ai + (size_t)na * BLKC, *d_a0 = d_bi + (size_t)na * BLKC, *d_b0 = d_a0 + na;
-  TRY(d_terminf(h, h->post[0].p, h->post[1].p, na, ll, d_ai, d_bi, d_a0, d_b0));
+  TRY(d_terminf(h, h->post[0].p, h->post[1].p, na, ll, d_ai, d_bi, d_a0, d_b0, true));
   TRY(d_bgreen(h, h->post[0].p, h->post[1].p, ll, na, h->post[4].p, nv, 0, nv, d_ai, d_bi, 0.0, 0.0, sym_term, h->post[5].p));
   TRY(to_host(h, g0, h->post[5].p, (size_t)na * nv * BLKD));
   CUDA_TRY(cudaStreamSynchronize(h->st));
@@ -1335,7 +1342,7 @@ int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int l
     TRY(dev_alloc(h->post[2], 2 * (size_t)n * (BLKC + 1), false));
     TRY(dev_alloc(h->post[5], (size_t)n * nv * BLKD, false));
     double *d_ai = h->post[2].p, *d_bi = d_ai + (size_t)n * BLKC, *d_a0 = d_bi + (size_t)n * BLKC, *d_b0 = d_a0 + n;
-    TRY(d_terminf(h, h->ahist.p, h->post[1].p, n, lld, d_ai, d_bi, d_a0, d_b0));
+    TRY(d_terminf(h, h->ahist.p, h->post[1].p, n, lld, d_ai, d_bi, d_a0, d_b0, true));
     TRY(d_bgreen(h, h->ahist.p, h->post[1].p, lld, n, h->post[4].p, nv, 0, nv, d_ai, d_bi, 0.0, 0.0, sym_term, h->post[5].p));
     TRY(to_host(h, g0 + (size_t)u0 * nv * BLKC, h->post[5].p, (size_t)n * nv * BLKD));
     CUDA_TRY(cudaStreamSynchronize(h->st));
