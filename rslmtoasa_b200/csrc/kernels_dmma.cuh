@@ -294,7 +294,7 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
 // grid = (ctas, nunits); partials in complex column-major (i + 18 j) like the host arrays.
 __global__ void __launch_bounds__(GR_THREADS, 1)
 k_gram_dmma(const double *__restrict__ X, const double *__restrict__ Y, int two, int kk, size_t xstride, size_t ystride,
-            double *part) {
+            double *part, const int32_t *__restrict__ border, const int32_t *__restrict__ bcnt, int nblocks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *sbase = reinterpret_cast<double *>(smem_raw);
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)GR_WARPS * 2 * GR_STAGE_D * 8);
@@ -331,17 +331,23 @@ k_gram_dmma(const double *__restrict__ X, const double *__restrict__ Y, int two,
 
   const int stride = gridDim.x * GR_WARPS;
   const int s0 = blockIdx.x * GR_WARPS + warp;
+  // border/bcnt (optional): the contiguous 8-site blocks that can be non-zero at this step (active-region plan);
+  // positions past kk in the last block map to the null site kk, whose block is always zero
+  const int nact = border ? bcnt[unit] * DM_S : kk;
+  const int32_t *bo = border ? border + (size_t)unit * nblocks : nullptr;
+  auto site_of = [&](int idx) { return bo ? min(bo[idx >> 3] * DM_S + (idx & 7), kk) : idx; };
   // prologue: up to two sites in flight
   for (int pf = 0; pf < 2; pf++) {
-    const int site = s0 + pf * stride;
-    if (site < kk && lane == 0) {
+    const int idx = s0 + pf * stride;
+    const int site = idx < nact ? site_of(idx) : 0;
+    if (idx < nact && lane == 0) {
       mbar_expect_tx(&wbar[pf], GR_STAGE_D * 8);
       bulk_g2s(wsm + (size_t)pf * GR_STAGE_D, Xu + (size_t)site * BLKD, BLKD * 8, &wbar[pf]);
       bulk_g2s(wsm + (size_t)pf * GR_STAGE_D + BLKD, Yu + (size_t)site * BLKD, BLKD * 8, &wbar[pf]);
     }
   }
   int itn = 0;
-  for (int site = s0; site < kk; site += stride, itn++) {
+  for (int idx = s0; idx < nact; idx += stride, itn++) {
     const int slot = itn & 1;
     mbar_wait(&wbar[slot], (itn >> 1) & 1);
     const double *sm = wsm + (size_t)slot * GR_STAGE_D;
@@ -366,8 +372,9 @@ k_gram_dmma(const double *__restrict__ X, const double *__restrict__ Y, int two,
       }
     }
     __syncwarp();
-    const int nsite = site + 2 * stride;
-    if (nsite < kk && lane == 0) {
+    const int nidx = idx + 2 * stride;
+    const int nsite = nidx < nact ? site_of(nidx) : 0;
+    if (nidx < nact && lane == 0) {
       mbar_expect_tx(&wbar[slot], GR_STAGE_D * 8);
       bulk_g2s(wsm + (size_t)slot * GR_STAGE_D, Xu + (size_t)nsite * BLKD, BLKD * 8, &wbar[slot]);
       bulk_g2s(wsm + (size_t)slot * GR_STAGE_D + BLKD, Yu + (size_t)nsite * BLKD, BLKD * 8, &wbar[slot]);
@@ -437,7 +444,8 @@ __device__ __forceinline__ void rmul_product(const double *xs, const double *ts,
 
 template <int MODE, int XN>
 __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const double *hpsi, int kk, double *tiles,
-                                              const double *tmat, uint64_t *full, uint64_t *empty, int warp, int lane) {
+                                              const double *tmat, uint64_t *full, uint64_t *empty, int warp, int lane,
+                                              const int32_t *bo, int nact) {
   const int g = lane >> 2, q = lane & 3;
   const int mt[3] = {2 * warp, 2 * warp + 1, 16 + (warp >> 2)};
   const int w4 = warp & 3;
@@ -455,12 +463,11 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
   for (int nt = 0; nt < 5; nt++) boff[nt] = min(nt * 8 + g, 35) * COLD + q;
 #pragma unroll
   for (int x = 0; x < 2; x++) xoff[x] = min(xn[x] * 8 + g, 35) * COLD + q;
-  const int ntiles = (kk + DM_S - 1) / DM_S;
   uint32_t it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+  for (int ti = blockIdx.x; ti < nact; ti += gridDim.x, it++) {
     const int slot = it & 1;
     const double *sm = tiles + (size_t)slot * 2 * RM_TILE_D;
-    const int site0 = tile * DM_S;
+    const int site0 = (bo ? bo[ti] : ti) * DM_S;
     // output element (row n = (s,k), column c') -> RI36 offset
     auto gofs = [&](int i, int c) { return (size_t)(site0 + rows[i]) * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
     auto valid = [&](int i, int c) { return c < 2 * NB && site0 + rows[i] < kk; };
@@ -542,7 +549,7 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
 template <int MODE>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const double *m0, const double *m1, size_t mstride,
-            int kk, size_t vstride) {
+            int kk, size_t vstride, const int32_t *__restrict__ border, const int32_t *__restrict__ bcnt, int nblocks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);                       // [2 slots][2 tiles]
   double *tmat = tiles + 2 * 2 * RM_TILE_D;                                   // [2][36x36]: T[c'][j'] = Mhat[j'][c']
@@ -568,14 +575,16 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
     tmat[e] = v;
   }
   __syncthreads();
-  const int ntiles = (kk + DM_S - 1) / DM_S;
+  // border/bcnt (optional): contiguous 8-site blocks that can be non-zero at this step (active-region plan)
+  const int nact = border ? bcnt[unit] : (kk + DM_S - 1) / DM_S;
+  const int32_t *bo = border ? border + (size_t)unit * nblocks : nullptr;
   if (warp == DM_CONSUMERS) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      for (int ti = blockIdx.x; ti < nact; ti += gridDim.x, it++) {
         const int slot = it & 1;
         mbar_wait(&empty[slot], ((it >> 1) & 1) ^ 1);
-        const int site0 = tile * DM_S, ns = min(DM_S, kk - site0);
+        const int site0 = (bo ? bo[ti] : ti) * DM_S, ns = min(DM_S, kk - site0);
         const uint32_t bytes = (uint32_t)ns * BLKD * 8;
         double *sm = tiles + (size_t)slot * 2 * RM_TILE_D;
         if (MODE == RM_ORTHO) {
@@ -592,9 +601,9 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
     return;
   }
   if (warp == 3 || warp == 6)
-    rmul_consumer<MODE, 2>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane);
+    rmul_consumer<MODE, 2>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane, bo, nact);
   else
-    rmul_consumer<MODE, 1>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane);
+    rmul_consumer<MODE, 1>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane, bo, nact);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -715,22 +724,24 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
 }
 
 static int dmma_launch_gram(const double *X, size_t xstride, const double *Y, size_t ystride, int two, int kk,
-                            int nunits, int ctas, double *part, cudaStream_t st, long long *launches) {
+                            int nunits, int ctas, double *part, cudaStream_t st, long long *launches,
+                            const int32_t *border = nullptr, const int32_t *bcnt = nullptr, int nblocks = 0) {
   dim3 grid(ctas, nunits);
-  k_gram_dmma<<<grid, GR_THREADS, GR_SMEM_BYTES, st>>>(X, Y, two, kk, xstride, ystride, part);
+  k_gram_dmma<<<grid, GR_THREADS, GR_SMEM_BYTES, st>>>(X, Y, two, kk, xstride, ystride, part, border, bcnt, nblocks);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
 static int dmma_launch_rmul(int mode, double *psi, double *pmn, const double *hpsi, const double *m0, const double *m1,
                             size_t mstride, int kk, size_t vstride, int nunits, int sms, cudaStream_t st,
-                            long long *launches) {
+                            long long *launches, const int32_t *border = nullptr, const int32_t *bcnt = nullptr,
+                            int nblocks = 0) {
   const int ntiles = (kk + DM_S - 1) / DM_S;
   dim3 grid(std::max(1, std::min(ntiles, (sms + nunits - 1) / nunits)), nunits);
   if (mode == RM_ORTHO)
-    k_rmul_dmma<RM_ORTHO><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride);
+    k_rmul_dmma<RM_ORTHO><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride, border, bcnt, nblocks);
   else
-    k_rmul_dmma<RM_ROTATE><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride);
+    k_rmul_dmma<RM_ROTATE><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride, border, bcnt, nblocks);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

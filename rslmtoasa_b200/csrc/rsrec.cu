@@ -83,6 +83,10 @@ struct rsrec_handle_s {
     int level = 0, maxlevel = 0, nunits = 0;
     int32_t *d_order = nullptr, *d_counts = nullptr;
     size_t order_cap = 0, counts_cap = 0;
+    // the same levels for contiguous 8-site blocks (what the site-ordered Gram / right-multiplication kernels walk)
+    int32_t *d_border = nullptr, *d_bcounts = nullptr;
+    size_t border_cap = 0, bcounts_cap = 0;
+    int nblocks = 0;
   } plan;
   // Chebyshev stepping session
   struct {
@@ -143,9 +147,13 @@ static void pack_block(const cplx *src, double *dst, double scale) {
 }
 
 static long long g_upload_bytes = 0;  // folded into the handle's h2d counter by ensure_ready
+static cudaStream_t g_upload_stream = nullptr;
+// Stream-ordered on the handle's stream: a synchronous cudaMemcpy from pageable memory returns once the data is in the
+// driver's staging buffer, NOT when it has reached the device, and the handle's stream is non-blocking -- a kernel
+// launched on it right afterwards could read the destination before the DMA lands.
 static int upload(DevBuf &b, const std::vector<double> &host) {
   TRY(dev_alloc(b, host.size(), false));
-  CUDA_TRY(cudaMemcpy(b.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpyAsync(b.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, g_upload_stream));
   g_upload_bytes += (long long)(host.size() * sizeof(double));
   return RSREC_OK;
 }
@@ -158,6 +166,7 @@ static int ensure_ready(H *h) {
   if (!h->have_ham) return fail(RSREC_EINVAL, "rsrec_set_hamiltonian has not been called");
   if (!h->dirty && !h->dirty_ham) return RSREC_OK;
   g_upload_bytes = 0;
+  g_upload_stream = h->st;
   const int kk = h->kk, nslot = h->nslot, ncls = h->ncls, ng = h->ncols;
   if (h->dirty) {
   // neighbour table [slot][site], slot 0 = self, missing -> kk
@@ -177,8 +186,8 @@ static int ensure_ready(H *h) {
   }
   if (!h->d_nbr) CUDA_TRY(cudaMalloc(&h->d_nbr, nbr.size() * sizeof(int32_t)));
   if (!h->d_cls) CUDA_TRY(cudaMalloc(&h->d_cls, cls.size() * sizeof(int32_t)));
-  CUDA_TRY(cudaMemcpy(h->d_nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->d_cls, cls.data(), cls.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpyAsync(h->d_nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(h->d_cls, cls.data(), cls.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
   h->h2d_bytes += (long long)((nbr.size() + cls.size()) * sizeof(int32_t));
   {  // reverse adjacency (CSR): radj[a] = sites i that gather from a (i != a), for the breadth-first reach levels
     h->radj_off.assign(kk + 1, 0);
@@ -193,6 +202,7 @@ static int ensure_ready(H *h) {
 
   if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
   h->h2d_bytes += (long long)h->tiles.ntiles * (DM_S + 1 + (long long)ng * DM_S) * 4;
+  CUDA_TRY(cudaDeviceSynchronize());  // the tile tables went through the legacy stream: make sure they have landed
   h->dirty = false;
   h->dirty_ham = true;
   }  // lattice tables
@@ -201,7 +211,7 @@ static int ensure_ready(H *h) {
   std::vector<int32_t> cls_type(ncls);
   for (int c = 0; c < ncls; c++) cls_type[c] = c < h->ntype ? c : h->iz[c - h->ntype] - 1;
   if (!h->d_cls_type) CUDA_TRY(cudaMalloc(&h->d_cls_type, ncls * sizeof(int32_t)));
-  CUDA_TRY(cudaMemcpy(h->d_cls_type, cls_type.data(), ncls * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpyAsync(h->d_cls_type, cls_type.data(), ncls * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
   const size_t nblk = (size_t)ncls * nslot, ntb = (size_t)h->ntype * nslot;
   const size_t setn = nblk * HBLK;
   if (!h->ham_on_device) {  // stage the reference's arrays: ee followed by hall = blocks of classes 0..ncls-1
@@ -304,7 +314,9 @@ static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *si
   if (h->family != 1 || (size_t)nunits * h->kk > (size_t)64 << 20) return RSREC_OK;
   const int kk = h->kk, nt = h->tiles.ntiles;
   std::vector<int32_t> order((size_t)nunits * nt), level(kk), tl(nt), frontier, next;
-  std::vector<std::vector<int32_t>> cum(nunits);
+  std::vector<std::vector<int32_t>> cum(nunits), bcum(nunits);
+  const int nb = (kk + DM_S - 1) / DM_S;
+  std::vector<int32_t> border((size_t)nunits * nb), bl(nb);
   int maxlevel = 0;
   for (int u = 0; u < nunits; u++) {
     std::fill(level.begin(), level.end(), INT32_MAX);
@@ -336,11 +348,33 @@ static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *si
     std::vector<int32_t> pos(c.begin(), c.end() - 1);
     int32_t *o = order.data() + (size_t)u * nt;
     for (int t = 0; t < nt; t++) if (tl[t] != INT32_MAX) o[pos[tl[t]]++] = t;
+    // contiguous blocks of 8 sites, same counting sort
+    for (int b = 0; b < nb; b++) {
+      int m = INT32_MAX;
+      for (int k = 0; k < DM_S && b * DM_S + k < kk; k++) m = std::min(m, level[b * DM_S + k]);
+      bl[b] = m;
+    }
+    std::vector<int32_t> bc(ml + 2, 0);
+    for (int b = 0; b < nb; b++) if (bl[b] != INT32_MAX) bc[bl[b] + 1]++;
+    for (int L = 0; L <= ml; L++) bc[L + 1] += bc[L];
+    bcum[u].assign(bc.begin() + 1, bc.end());
+    std::vector<int32_t> bpos(bc.begin(), bc.end() - 1);
+    int32_t *bo = border.data() + (size_t)u * nb;
+    for (int b = 0; b < nb; b++) if (bl[b] != INT32_MAX) bo[bpos[bl[b]]++] = b;
   }
-  std::vector<int32_t> counts((size_t)(maxlevel + 1) * nunits);
+  std::vector<int32_t> counts((size_t)(maxlevel + 1) * nunits), bcounts((size_t)(maxlevel + 1) * nunits);
   for (int L = 0; L <= maxlevel; L++)
-    for (int u = 0; u < nunits; u++) counts[(size_t)L * nunits + u] = cum[u][std::min<size_t>(L, cum[u].size() - 1)];
+    for (int u = 0; u < nunits; u++) {
+      counts[(size_t)L * nunits + u] = cum[u][std::min<size_t>(L, cum[u].size() - 1)];
+      bcounts[(size_t)L * nunits + u] = bcum[u][std::min<size_t>(L, bcum[u].size() - 1)];
+    }
   auto &pl = h->plan;
+  if (pl.border_cap < border.size()) { if (pl.d_border) cudaFree(pl.d_border); CUDA_TRY(cudaMalloc(&pl.d_border, border.size() * 4)); pl.border_cap = border.size(); }
+  if (pl.bcounts_cap < bcounts.size()) { if (pl.d_bcounts) cudaFree(pl.d_bcounts); CUDA_TRY(cudaMalloc(&pl.d_bcounts, bcounts.size() * 4)); pl.bcounts_cap = bcounts.size(); }
+  CUDA_TRY(cudaMemcpyAsync(pl.d_border, border.data(), border.size() * 4, cudaMemcpyHostToDevice, h->st));
+  CUDA_TRY(cudaMemcpyAsync(pl.d_bcounts, bcounts.data(), bcounts.size() * 4, cudaMemcpyHostToDevice, h->st));
+  h->h2d_bytes += (long long)((border.size() + bcounts.size()) * 4);
+  pl.nblocks = nb;
   if (pl.order_cap < order.size()) { if (pl.d_order) cudaFree(pl.d_order); CUDA_TRY(cudaMalloc(&pl.d_order, order.size() * 4)); pl.order_cap = order.size(); }
   if (pl.counts_cap < counts.size()) { if (pl.d_counts) cudaFree(pl.d_counts); CUDA_TRY(cudaMalloc(&pl.d_counts, counts.size() * 4)); pl.counts_cap = counts.size(); }
   CUDA_TRY(cudaMemcpyAsync(pl.d_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice, h->st));
@@ -351,6 +385,16 @@ static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *si
   return RSREC_OK;
 }
 
+// the active contiguous-block list at the plan's current level (null when no plan is active)
+static void plan_blocks(const H *h, int nunits, const int32_t **border, const int32_t **bcnt, int *nblocks) {
+  *border = nullptr; *bcnt = nullptr; *nblocks = 0;
+  static const bool off = getenv("RSREC_NO_BLOCK_PLAN") != nullptr;  // A/B switch for measurements
+  if (!off && h->plan.on && h->plan.nunits == nunits && h->family == 1) {
+    *border = h->plan.d_border;
+    *bcnt = h->plan.d_bcounts + (size_t)h->plan.level * nunits;
+    *nblocks = h->plan.nblocks;
+  }
+}
 static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas);
 static int launch_apply(H *h, ApplyParams &p, int nunits, int nctas) {
   if (!h->profile) return launch_apply_inner(h, p, nunits, nctas);
@@ -426,7 +470,9 @@ static int launch_gram_strided(H *h, const double *X, size_t xs, const double *Y
   if (h->family == 1) {
     // many units in one launch (Kubo contraction): fewer CTAs per unit, the grid is filled by the unit dimension
     const int ctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms + nunits - 1) / nunits));
-    if (dmma_launch_gram(Y, ys, X, xs, 0, h->kk, nunits, ctas, part, h->st, &h->launches) != 0)
+    const int32_t *bo, *bc; int nbk;
+    plan_blocks(h, nunits, &bo, &bc, &nbk);
+    if (dmma_launch_gram(Y, ys, X, xs, 0, h->kk, nunits, ctas, part, h->st, &h->launches, bo, bc, nbk) != 0)
       return fail(RSREC_ECUDA, std::string("k_gram_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->last_parts = ctas;
     return RSREC_OK;
@@ -521,7 +567,9 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     // pmn -= psi A ; B2 = sum pmn^H pmn
     dim3 grid(nctas, nunits);
     if (h->family == 1) {
-      if (dmma_launch_rmul(RM_ORTHO, psi, pmn, nullptr, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches) != 0)
+      const int32_t *bo, *bc; int nbk;
+      plan_blocks(h, nunits, &bo, &bc, &nbk);
+      if (dmma_launch_rmul(RM_ORTHO, psi, pmn, nullptr, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches, bo, bc, nbk) != 0)
         return fail(RSREC_ECUDA, std::string("k_rmul_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       TRY(launch_gram(h, pmn, pmn, nunits, nctas, h->part.p));
     } else {
@@ -536,7 +584,9 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     h->launches++;
     // psi = pmn B^-1 ; pmn = psi_old B
     if (h->family == 1) {
-      if (dmma_launch_rmul(RM_ROTATE, psi, pmn, nullptr, h->Bi.p, h->B.p, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches) != 0)
+      const int32_t *bo, *bc; int nbk;
+      plan_blocks(h, nunits, &bo, &bc, &nbk);
+      if (dmma_launch_rmul(RM_ROTATE, psi, pmn, nullptr, h->Bi.p, h->B.p, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches, bo, bc, nbk) != 0)
         return fail(RSREC_ECUDA, std::string("k_rmul_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     } else {
       k_lz_rotate_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->B.p, h->Bi.p, BLKD, h->kk, vstride(h));
@@ -593,7 +643,9 @@ static int cheb_steps(H *h, int nsteps) {
     if (h->family == 1) {
       TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB_NOGRAM, c.a, c.b, c.nunits, c.nctas, nullptr));
       const int gctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms + c.nunits - 1) / c.nunits));
-      if (dmma_launch_gram(p1, vstride(h), p0, vstride(h), 1, h->kk, c.nunits, gctas, h->part.p, h->st, &h->launches) != 0)
+      const int32_t *bo, *bc; int nbk;
+      plan_blocks(h, c.nunits, &bo, &bc, &nbk);
+      if (dmma_launch_gram(p1, vstride(h), p0, vstride(h), 1, h->kk, c.nunits, gctas, h->part.p, h->st, &h->launches, bo, bc, nbk) != 0)
         return fail(RSREC_ECUDA, std::string("k_gram_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       h->last_parts = gctas;
     } else {
@@ -677,6 +729,8 @@ int rsrec_destroy(rsrec_handle h) {
   { DevBuf *cb[] = {&h->cBLK, &h->cBLKO, &h->cLS, &h->cENIM, &h->cOBARM, &h->cV[0], &h->cV[1], &h->cVO[0], &h->cVO[1], &h->gBLK, &h->gBLKO, &h->gENIM}; for (auto b : cb) dev_free(*b); }
   if (h->plan.d_order) cudaFree(h->plan.d_order);
   if (h->plan.d_counts) cudaFree(h->plan.d_counts);
+  if (h->plan.d_border) cudaFree(h->plan.d_border);
+  if (h->plan.d_bcounts) cudaFree(h->plan.d_bcounts);
   if (h->d_si) { cudaFree(h->d_si); cudaFree(h->d_sj); cudaFree(h->d_as); cudaFree(h->d_bs); }
   for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   cudaStreamDestroy(h->st);

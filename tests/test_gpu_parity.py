@@ -310,3 +310,21 @@ def test_chebyshev_orbital_mod(oracle_mod, name, family):
     ref = oracle_mod.Oracle(lat, ham).orbital_moments(starts, cr, 5.42, 7, a, b)
     assert relerr(mu, ref) < TOL_MU
     assert np.array_equal(mu, rec.chebyshev_orbital_mod(starts, cr, 5.42))       # reproducible
+
+
+def test_fresh_handles_give_identical_kubo_moments():
+    """every handle uploads and packs the block sets again: the set-up path must be stream-ordered with the kernels
+    (a synchronous cudaMemcpy from pageable memory returns before the DMA lands), so 12 fresh handles agree bit for bit"""
+    from rslmtoasa_b200 import synthetic as S
+    lat, ham = case("pbc_hoh")
+    ph = S.random_phases(lat.kk, 2)
+    first = None
+    for it in range(12):
+        rec = _rec(lat, ham, cond_ll=6, cond_calctype="random_vec", phases=ph)
+        if it % 3 == 1:
+            rec.recur_b()
+        rec.compute_moments_stochastic()
+        if first is None:
+            first = rec.mu_nm_stochastic.copy()
+        assert np.array_equal(rec.mu_nm_stochastic, first)
+        rec.close()
