@@ -126,3 +126,16 @@ def test_fortran_module_binds_every_data_path_symbol():
     assert declared - bound == helpers
     for name in bound:       # every interface is exported from the module
         assert re.search(r"public ::[^\n]*\b%s\b" % name, f90) or name == "rsrec_last_error", name
+
+
+def test_header_is_valid_c_and_cxx(tmp_path):
+    """include/rsrec.h is the boundary a C or Fortran host binds: it must compile as plain C11 and as C++17"""
+    import shutil
+    import subprocess
+    src_c = tmp_path / "use_c.c"
+    src_c.write_text('#include "rsrec.h"\nint main(void) { rsrec_handle h = 0; double _Complex z = 0; (void)z; return rsrec_destroy(h) + 0 * rsrec_version(); }\n')
+    src_cc = tmp_path / "use_cc.cpp"
+    src_cc.write_text('#include "rsrec.hpp"\nint main() { rsrec::energy e; e.e_mesh(); return (int)e.ene.size() == 2510 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call([shutil.which("gcc") or "/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", inc, "-c", str(src_c), "-o", str(tmp_path / "c.o")])
+    subprocess.check_call([shutil.which("g++") or "/usr/bin/g++", "-std=c++17", "-Wall", "-I", inc, "-c", str(src_cc), "-o", str(tmp_path / "cc.o")])

@@ -328,3 +328,40 @@ def test_fresh_handles_give_identical_kubo_moments():
             first = rec.mu_nm_stochastic.copy()
         assert np.array_equal(rec.mu_nm_stochastic, first)
         rec.close()
+
+
+def test_edge_sizes_and_empty_inputs(oracle_mod):
+    """lld = 1 (no step at all), lld = 2, zero units, a single-site 'cluster', units on the last site"""
+    from rslmtoasa_b200 import Recursion, Control, Energy, synthetic as S
+    lat, ham = case("tiny")
+    orc = oracle_mod.Oracle(lat, ham)
+    for lld in (1, 2):
+        rec = _rec(lat, ham, lld=lld)
+        rec.recur_b()
+        a_b, b2_b = orc.lanczos_block(lat.irec, lld)
+        assert rec.a_b.shape == (18, 18, lld, len(lat.irec))
+        assert relerr(rec.b2_b, b2_b) < TOL_AB and np.abs(rec.a_b - a_b).max() < 1e-12
+    rec = _rec(lat, ham, lld=0)
+    rec.chebyshev_recur()                                    # lld = 0: only mu(1), mu(2)
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    mu, _ = orc.cheb_moments(lat.irec, 0, a, b)
+    assert rec.mu_n.shape == (18, 18, 2, len(lat.irec)) and relerr(rec.mu_n, mu) < TOL_MU
+    # no units on this rank (more ranks than units): empty results, no launch
+    rec = _rec(lat, ham, lld=4, rank=3, numprocs=4)
+    n0 = rec.launch_count
+    rec.recur_b(); rec.chebyshev_recur()
+    assert rec.a_b.shape[-1] == 0 and rec.mu_n.shape[-1] == 0 and rec.launch_count == n0
+    # the last site of the cluster as the recursion site (edge of the site range, mostly missing neighbours)
+    lat.irec = np.array([lat.kk], dtype=np.int32)
+    rec = _rec(lat, ham, lld=5)
+    rec.recur_b()
+    a_b, b2_b = orc.lanczos_block(lat.irec, 5)
+    assert relerr(rec.a_b, a_b) < TOL_AB and relerr(rec.b2_b, b2_b) < TOL_AB
+    # one-site lattice: H reduces to the on-site block; A_1 = H_on + lsham, B_2^2 = 0
+    one = S.sphere_cluster("bcc", 0.1)
+    assert one.kk == 1
+    h1 = S.make_hamiltonian(one, seed=3)
+    rec = _rec(one, h1, lld=2)
+    rec.recur_b()
+    assert relerr(rec.a_b[:, :, 0, 0], h1.ee[:, :, 0, 0] + h1.lsham[:, :, 0]) < 1e-14
+    assert np.abs(rec.b2_b[:, :, 1, 0]).max() < 1e-25

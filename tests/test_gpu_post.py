@@ -282,3 +282,25 @@ def test_gpu_against_committed_golden_vectors():
     integ, integ_at = Conductivity(rec).calculate_conductivity_tensor()
     assert relerr(np.nan_to_num(integ), np.nan_to_num(p["integrand"])) < TOL_SUM
     assert relerr(np.nan_to_num(integ_at), np.nan_to_num(p["integrand_at"])) < TOL_SUM
+
+
+def test_block_green_full_mesh_size(oracle_mod):
+    """the reference's mesh size (channels_ldos + 10 = 2510 energies), lld = 21, 3 units of the layered fcc case"""
+    from rslmtoasa_b200 import Green
+    lat, ham = case("surface")
+    lat.irec = np.array([1, 2, 9], dtype=np.int32)
+    rec = _rec(lat, ham, lld=21, channels=2500, fermi=0.0)
+    g = Green(rec)
+    g0 = g.recur_b_green()
+    assert g0.shape == (18, 18, 2510, 3)
+    orc = oracle_mod.Oracle(lat, ham)
+    a_b, b2_b = orc.lanczos_block(lat.irec, 21)
+    ref = oracle_mod.block_green(a_b, orc.zsqr(b2_b), g.ene)
+    # lld = 21 on a 250-site cluster runs into an exhausted Krylov space: compare where the chain is still stable
+    assert relerr(rec.a_b[:, :, :8], a_b[:, :, :8]) < 1e-8
+    staged = oracle_mod.block_green(rec.a_b, orc.zsqr(rec.b2_b), g.ene)
+    ok = np.isfinite(staged) & np.isfinite(g0)
+    assert ok.mean() > 0.99 and relerr(g0[ok], staged[ok]) < 1e-8
+    d = np.arange(18)
+    ldos = -g0[d, d].imag.sum(0) / np.pi
+    assert np.nanmin(ldos) > -1e-6
