@@ -737,7 +737,7 @@ static int dmma_launch_rmul(int mode, double *psi, double *pmn, const double *hp
                             long long *launches, const int32_t *border = nullptr, const int32_t *bcnt = nullptr,
                             int nblocks = 0) {
   const int ntiles = (kk + DM_S - 1) / DM_S;
-  dim3 grid(std::max(1, std::min(ntiles, (sms + nunits - 1) / nunits)), nunits);
+  dim3 grid(std::max(1, std::min(ntiles, sms / nunits)), nunits);
   if (mode == RM_ORTHO)
     k_rmul_dmma<RM_ORTHO><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride, border, bcnt, nblocks);
   else

@@ -469,7 +469,7 @@ static int launch_gram_strided(H *h, const double *X, size_t xs, const double *Y
                                double *part) {
   if (h->family == 1) {
     // many units in one launch (Kubo contraction): fewer CTAs per unit, the grid is filled by the unit dimension
-    const int ctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms + nunits - 1) / nunits));
+    const int ctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / nunits));
     const int32_t *bo, *bc; int nbk;
     plan_blocks(h, nunits, &bo, &bc, &nbk);
     if (dmma_launch_gram(Y, ys, X, xs, 0, h->kk, nunits, ctas, part, h->st, &h->launches, bo, bc, nbk) != 0)
@@ -490,7 +490,7 @@ static int launch_gram(H *h, const double *X, const double *Y, int nunits, int n
 }
 static size_t part_doubles(const H *h, int nunits, int nctas) {
   const int simt = std::max(1, std::min(nctas, (6 * h->sms + nunits - 1) / nunits));
-  const int dm = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms + nunits - 1) / nunits));
+  const int dm = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / nunits));
   return (size_t)nunits * std::max(std::max(simt, dm), std::min(nctas, nctas_for(h, nunits))) * 2 * BLKD;
 }
 static int launch_reduce(H *h, int nunits, int /*nctas*/, int mode, double *d0, double *d1, size_t dstride,
@@ -642,7 +642,7 @@ static int cheb_steps(H *h, int nsteps) {
     // psi2 = 2 (H psi1 - b psi1)/a - psi0, written over psi0; D1 = sum psi1^H psi1, D2 = sum psi2^H psi1
     if (h->family == 1) {
       TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB_NOGRAM, c.a, c.b, c.nunits, c.nctas, nullptr));
-      const int gctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms + c.nunits - 1) / c.nunits));
+      const int gctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / c.nunits));
       const int32_t *bo, *bc; int nbk;
       plan_blocks(h, c.nunits, &bo, &bc, &nbk);
       if (dmma_launch_gram(p1, vstride(h), p0, vstride(h), 1, h->kk, c.nunits, gctas, h->part.p, h->st, &h->launches, bo, bc, nbk) != 0)
