@@ -8,6 +8,8 @@
 ! unchanged, so self.f90 / green.f90 / density_of_states.f90 / conductivity.f90 compile and run
 ! untouched.  `this%gpu` is one new component of the type: `type(c_ptr) :: gpu = c_null_ptr`.
 ! Work vectors (psi_b, pmn_b, hpsi, ...) are no longer allocated on the host.
+! Procedures here: gpu_export, recur_b, recur_b_ij, recur, zsqr, chebyshev_recur, chebyshev_recur_ij,
+! compute_moments_stochastic (the consumers' bodies are in green_gpu_shim.f90).  NOT compiled in the build container.
 !------------------------------------------------------------------------------
 module recursion_gpu_shim
    use, intrinsic :: iso_c_binding
@@ -87,10 +89,129 @@ contains
                        __FILE__, __LINE__)
    end subroutine
 
-   ! recur_b_ij / chebyshev_recur_ij: build the unit list exactly as the reference's loops do --
-   ! slot ij_loc*4-4+reci, signs (1,1),(1,-1),(1,i),(1,-i)/sqrt(2), a single (1,1) unit when i == j --
-   ! and call rsrec_lanczos_block / rsrec_cheb_moments once; recur -> rsrec_lanczos_scalar;
-   ! compute_moments_stochastic -> rsrec_set_operator('a'/'b') + rsrec_kubo_moments with the random
-   ! numbers drawn on the host (random_number) and passed as `phases`.  See rslmtoasa_b200/recursion.py
-   ! (`_pair_units`, `recur`, `compute_moments_stochastic`) for the executable statement of the same logic.
+   !> unit list of recur_b_ij / chebyshev_recur_ij (recursion.f90:1666-1707, 2390-2440): result slot ij_loc*4-4+reci,
+   !> signs (1,1),(1,-1),(1,i),(1,-i)/sqrt(2); a pair with i == j keeps only reci = 1 with signs (1,1)
+   subroutine pair_units(this, n, si, sj, asg, bsg, slots)
+      use recursion_mod, only: recursion
+      use math_mod, only: one_over_sqrt_two
+      class(recursion), intent(in) :: this
+      integer, intent(out) :: n
+      integer(c_int32_t), allocatable, intent(out) :: si(:), sj(:)
+      complex(c_double_complex), allocatable, intent(out) :: asg(:), bsg(:)
+      integer, allocatable, intent(out) :: slots(:)
+      integer :: ij, ij_loc, i, j, reci, nmax_units
+      complex(c_double_complex), parameter :: bs(4) = [(1.0d0, 0.0d0), (-1.0d0, 0.0d0), (0.0d0, 1.0d0), (0.0d0, -1.0d0)]
+      nmax_units = 4*max(end_atom - start_atom + 1, 0)
+      allocate (si(nmax_units), sj(nmax_units), asg(nmax_units), bsg(nmax_units), slots(nmax_units))
+      n = 0
+      do ij = start_atom, end_atom
+         ij_loc = g2l_map(ij)
+         i = this%lattice%ijpair(ij, 1)
+         j = this%lattice%ijpair(ij, 2)
+         do reci = 1, 4
+            if (i == j .and. reci > 1) cycle
+            n = n + 1
+            si(n) = i; sj(n) = j; slots(n) = ij_loc*4 - 4 + reci
+            if (i == j) then
+               asg(n) = (1.0d0, 0.0d0); bsg(n) = (1.0d0, 0.0d0)
+            else
+               asg(n) = (1.0d0, 0.0d0)*one_over_sqrt_two; bsg(n) = bs(reci)*one_over_sqrt_two
+            end if
+         end do
+      end do
+   end subroutine
+
+   subroutine recur_b_ij(this)
+      use recursion_mod, only: recursion
+      class(recursion), intent(inout), target :: this
+      integer :: n, u, lld
+      integer(c_int32_t), allocatable :: si(:), sj(:)
+      complex(c_double_complex), allocatable :: asg(:), bsg(:), a_u(:, :, :, :), b_u(:, :, :, :)
+      integer, allocatable :: slots(:)
+      call get_mpi_variables(rank, this%lattice%njij)
+      call gpu_export(this)
+      call pair_units(this, n, si, sj, asg, bsg, slots)
+      lld = this%lattice%control%lld
+      allocate (a_u(18, 18, lld, max(n, 1)), b_u(18, 18, lld, max(n, 1)))
+      call rsrec_check(rsrec_lanczos_block(this%gpu, int(n, c_int), si, sj, asg, bsg, int(lld, c_int), a_u, b_u), &
+                       __FILE__, __LINE__)
+      do u = 1, n
+         this%a_b(:, :, :, slots(u)) = a_u(:, :, :, u)
+         this%b2_b(:, :, :, slots(u)) = b_u(:, :, :, u)
+      end do
+   end subroutine
+
+   subroutine chebyshev_recur_ij(this)
+      use recursion_mod, only: recursion
+      class(recursion), intent(inout), target :: this
+      integer :: n, u, lld
+      real(c_double) :: a, b
+      integer(c_int32_t), allocatable :: si(:), sj(:)
+      complex(c_double_complex), allocatable :: asg(:), bsg(:), mu_u(:, :, :, :)
+      integer, allocatable :: slots(:)
+      a = (this%en%energy_max - this%en%energy_min)/(2 - 0.3)
+      b = (this%en%energy_max + this%en%energy_min)/2
+      call get_mpi_variables(rank, this%lattice%njij)
+      call gpu_export(this)
+      call pair_units(this, n, si, sj, asg, bsg, slots)
+      lld = this%lattice%control%lld
+      allocate (mu_u(18, 18, 2*lld + 2, max(n, 1)))
+      call rsrec_check(rsrec_cheb_moments(this%gpu, int(n, c_int), si, sj, asg, bsg, int(lld, c_int), a, b, mu_u), &
+                       __FILE__, __LINE__)
+      do u = 1, n
+         this%mu_n(:, :, :, slots(u)) = mu_u(:, :, :, u)
+      end do
+   end subroutine
+
+   !> scalar recursion (nsp = 1), recursion.f90:3485-3532: the 18 start orbitals of a site run as one block vector
+   subroutine recur(this)
+      use recursion_mod, only: recursion
+      class(recursion), intent(inout), target :: this
+      integer :: nloc, lld
+      integer(c_int32_t), allocatable :: sites(:)
+      real(c_double), allocatable :: a_u(:, :, :), b_u(:, :, :)
+      call get_mpi_variables(rank, this%lattice%nrec)
+      call gpu_export(this)
+      nloc = end_atom - start_atom + 1
+      lld = this%lattice%control%lld
+      allocate (sites(nloc), a_u(lld, 18, nloc), b_u(lld, 18, nloc))
+      sites = this%lattice%irec(start_atom:end_atom)
+      call rsrec_check(rsrec_lanczos_scalar(this%gpu, int(nloc, c_int), sites, int(lld, c_int), a_u, b_u), __FILE__, __LINE__)
+      this%a(1:lld, :, 1:nloc, 1) = a_u
+      this%b2(1:lld, :, 1:nloc, 1) = b_u
+   end subroutine
+
+   !> compute_moments_stochastic (recursion.f90:979-1234).  The uniform numbers of the random-phase start vectors are
+   !> drawn here with random_number (the reference calls random_seed() without arguments, 1106) and handed to the engine.
+   subroutine compute_moments_stochastic(this)
+      use recursion_mod, only: recursion
+      class(recursion), intent(inout), target :: this
+      integer :: loop_over, m
+      real(c_double) :: a, b
+      integer(c_int32_t), allocatable, target :: sites(:)
+      real(c_double), allocatable, target :: phases(:, :)
+      a = (this%en%energy_max - this%en%energy_min)/(2 - 0.3)
+      b = (this%en%energy_max + this%en%energy_min)/2
+      m = this%control%cond_ll
+      call gpu_export(this)
+      call rsrec_check(rsrec_set_operator(this%gpu, int(iachar('a'), c_int), c_loc(this%hamiltonian%v_a), &
+                                          c_loc(this%hamiltonian%vo_a)), __FILE__, __LINE__)
+      call rsrec_check(rsrec_set_operator(this%gpu, int(iachar('b'), c_int), c_loc(this%hamiltonian%v_b), &
+                                          c_loc(this%hamiltonian%vo_b)), __FILE__, __LINE__)
+      select case (this%control%cond_calctype)
+      case ('per_type')
+         loop_over = this%lattice%ntype
+         allocate (sites(loop_over))
+         sites = this%lattice%atlist(1:loop_over)
+         call rsrec_check(rsrec_kubo_moments(this%gpu, int(loop_over, c_int), 0_c_int, c_loc(sites), c_null_ptr, &
+                                             int(m, c_int), a, b, this%mu_nm_stochastic), __FILE__, __LINE__)
+      case ('random_vec')
+         loop_over = this%control%random_vec_num
+         allocate (phases(this%lattice%kk, loop_over))
+         call random_seed()
+         call random_number(phases)
+         call rsrec_check(rsrec_kubo_moments(this%gpu, int(loop_over, c_int), 1_c_int, c_null_ptr, c_loc(phases), &
+                                             int(m, c_int), a, b, this%mu_nm_stochastic), __FILE__, __LINE__)
+      end select
+   end subroutine
 end module recursion_gpu_shim

@@ -141,6 +141,39 @@ def main_post():
     run_post("4 conductivity integrand cond_ll=300", lat, ham, 21, "conductivity", cond_ll=300, cond_calctype="per_type", atlist=[1])
 
 
+def run_scf_step(name, lat, ham, lld=21, channels=2500):
+    """what self%run_recursion + self%run_dos do every SCF iteration on the block path (self.f90:799-856):
+    recur_b -> zsqr -> get_terminf -> bgreen on the full mesh, host arrays in / g0 out; fused GPU call vs CPU oracle."""
+    rec = Recursion(ham, lat, Control(lld=lld), Energy(EMIN, EMAX, channels_ldos=channels, fermi=0.0))
+    g = Green(rec)
+    t = timed(g.recur_b_green, reps=5)
+    orc = O.Oracle(lat, ham)
+    t0 = time.perf_counter()
+    a_b, b2_b = orc.lanczos_block(lat.irec, lld)
+    t1 = time.perf_counter()
+    ref = O.block_green(a_b, orc.zsqr(b2_b), g.ene)
+    tc = time.perf_counter() - t0
+    ok = np.isfinite(ref) & np.isfinite(g.g0)
+    out = {"config": name, "what": "scf_step: recur_b + zsqr + terminator + bgreen (fused, device-resident coefficients)",
+           "kk": lat.kk, "units": int(len(lat.irec)), "lld": lld, "nv": channels + 10, "hoh": bool(ham.hoh),
+           "gpu_seconds": t, "cpu_seconds": tc, "cpu_recursion_seconds": t1 - t0, "cpu_threads": O.lib().orc_get_max_threads(),
+           "speedup": tc / t, "relerr_a_b": relerr(rec.a_b, a_b), "relerr_g0": relerr(g.g0[ok], ref[ok]),
+           "d2h_bytes_g0": int(g.g0.nbytes)}
+    print(json.dumps(out), flush=True)
+    rec.close()
+
+
+def main_scf():
+    lat = S.sphere_cluster("bcc", 80.0)
+    run_scf_step("1 bulk bccFe", lat, S.make_hamiltonian(lat, seed=20260101))
+    run_scf_step("1 bulk bccFe hoh", lat, S.make_hamiltonian(lat, seed=20260101, hoh=True))
+    lat = S.sphere_cluster("fcc", 100.0, ntype=7, type_rule="layer")
+    lat.irec = np.array([1, 2, 3, 14, 15, 20], dtype=np.int32)
+    run_scf_step("2 surface fcc 6 units", lat, S.make_hamiltonian(lat, seed=20260102))
+    lat = S.sphere_cluster("bcc", 60.0, ntype=3, nmax=15, type_rule="b2")
+    run_scf_step("3 impurity B2 nmax=15", lat, S.make_hamiltonian(lat, seed=20260103))
+
+
 def main():
     quick = "--quick" in sys.argv
     # config 1: bulk bcc Fe, rc = 80 -> kk = 5984, 1 type, 1 unit, lld = 21, block Lanczos (hoh F/T) + Chebyshev lld=100
@@ -171,5 +204,7 @@ def main():
 if __name__ == "__main__":
     if "--post" in sys.argv:
         main_post()
+    elif "--scf" in sys.argv:
+        main_scf()
     else:
         main()
