@@ -97,6 +97,8 @@ class ClockSampler:
 def workload(cells):
     nx, ny, nz = cells
     lat = S.periodic_bcc(nx, ny, nz)
+    if not os.environ.get("RSREC_BENCH_NO_POSITIONS"):   # lattice%cr: orders the work for L2 locality, results unchanged
+        lat.cr = S.periodic_bcc_positions(nx, ny, nz)
     ham = S.make_hamiltonian(lat, seed=SEED_H, spin_orbit=True)
     return lat, ham
 

@@ -22,6 +22,7 @@ module rsrec_c_mod
    public :: rsrec_lanczos_block, rsrec_lanczos_scalar, rsrec_zsqr, rsrec_cheb_moments, rsrec_cheb_moments_random
    public :: rsrec_kubo_moments, rsrec_ham_vec_matmul, rsrec_velo_vec_matmul, rsrec_last_error_f, rsrec_check
    public :: rsrec_create_ll_map, rsrec_orbital_moments, rsrec_build_nn, rsrec_build_hamiltonian
+   public :: rsrec_set_positions
    public :: rsrec_rotate_to_local_axis, rsrec_rotate_from_local_axis, rsrec_lanczos_block_local_axis
    ! consumers of the recursion results (green.f90, density_of_states.f90, conductivity.f90) and fused drivers
    public :: rsrec_bpopt, rsrec_get_terminf, rsrec_bgreen, rsrec_block_green, rsrec_chebyshev_green, rsrec_density
@@ -53,6 +54,14 @@ module rsrec_c_mod
          import :: c_ptr, c_int, c_int32_t
          type(c_ptr), value :: h
          integer(c_int32_t), intent(in) :: nn(*), iz(*)
+         integer(c_int) :: rc
+      end function
+
+      ! optional lattice%cr(3, kk): orders the work for L2 locality only (results unchanged)
+      function rsrec_set_positions(h, cr) bind(C, name='rsrec_set_positions') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(in) :: cr(3, *)
          integer(c_int) :: rc
       end function
 

@@ -49,6 +49,11 @@ int rsrec_destroy(rsrec_handle h);
  * chbar_nc may zero entries of nn (hamiltonian.f90:2350-2352). */
 int rsrec_set_lattice(rsrec_handle h, const int32_t *nn, const int32_t *iz);
 
+/* Optional: lattice%cr (3,kk) (lattice.f90:239).  Coordinates never enter the arithmetic; they only order the work
+ * (8-site tiles along a Morton curve) so that gathers of concurrently running CTAs hit L2.  Results are bit-identical
+ * with or without this call; NULL clears.  Call before the first recursion (it re-sorts the tile tables). */
+int rsrec_set_positions(rsrec_handle h, const double *cr);
+
 /* hamiltonian%{ee,eeo}(18,18,nslot,ntype), {hall,hallo}(18,18,nslot,nmax), {lsham,enim}(18,18,ntype), hoh
  * (hamiltonian.f90:52-66,294-301).  Called once per SCF iteration after build_bulkham/build_locham
  * (self.f90:777-797).  eeo/hallo/enim may be NULL when hoh==0; hall/hallo may be NULL when nmax==0. */

@@ -19,7 +19,7 @@ SYMBOLS = [
     "rsrec_sgreen", "rsrec_conductivity_integrand", "rsrec_recur_b_green", "rsrec_cheb_recur_green",
     "rsrec_kubo_conductivity", "rsrec_create_ll_map", "rsrec_orbital_moments",
     "rsrec_build_nn", "rsrec_build_hamiltonian", "rsrec_rotate_to_local_axis", "rsrec_rotate_from_local_axis",
-    "rsrec_lanczos_block_local_axis",
+    "rsrec_lanczos_block_local_axis", "rsrec_set_positions",
 ]
 
 
@@ -89,6 +89,7 @@ def load():
     L.rsrec_rotate_to_local_axis.argtypes = [vp, vp]
     L.rsrec_rotate_from_local_axis.argtypes = [vp]
     L.rsrec_lanczos_block_local_axis.argtypes = [vp, i, vp, vp, i, vp, vp]
+    L.rsrec_set_positions.argtypes = [vp, vp]
     _lib = L
     return L
 

@@ -635,8 +635,20 @@ static void dmma_free_tiles(DmmaTiles &t) {
 
 // Tiles = up to 8 sites of one Hamiltonian class, ordered by their first site so that consecutive CTAs touch
 // neighbouring parts of the vector (L2 reuse of the gathered blocks).  nbr: [ng][kk], cls: [kk].
+// pos (optional, 3 x kk = lattice%cr): tiles are then ordered along a Morton (Z-order) curve through their first site,
+// so that the 148 persistent CTAs, which walk the list side by side, gather from a compact region of the vector: at
+// 10^6 sites in storage order the three z-planes a tile row touches (3 x 104 MB) exceed the 126 MB L2 and every psi
+// block was fetched from DRAM 2.6 times.
+static uint32_t morton_spread10(uint32_t v) {  // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
 static int dmma_build_tiles(DmmaTiles &t, const std::vector<int32_t> &nbr, const std::vector<int32_t> &cls, int kk, int ng,
-                            int ncls) {
+                            int ncls, const double *pos = nullptr) {
   dmma_free_tiles(t);
   std::vector<std::vector<int32_t>> by_cls(ncls);
   for (int i = 0; i < kk; i++) by_cls[cls[i]].push_back(i);
@@ -649,7 +661,27 @@ static int dmma_build_tiles(DmmaTiles &t, const std::vector<int32_t> &nbr, const
       for (int k = 0; k < DM_S; k++) x.s[k] = (o + k < by_cls[c].size()) ? by_cls[c][o + k] : kk;
       tiles.push_back(x);
     }
-  std::sort(tiles.begin(), tiles.end(), [](const T &a, const T &b) { return a.s[0] < b.s[0]; });
+  if (pos) {
+    double lo[3], hi[3];
+    for (int l = 0; l < 3; l++) lo[l] = hi[l] = pos[l];
+    for (int i = 1; i < kk; i++)
+      for (int l = 0; l < 3; l++) { lo[l] = std::min(lo[l], pos[l + 3 * (size_t)i]); hi[l] = std::max(hi[l], pos[l + 3 * (size_t)i]); }
+    const double ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), std::max(hi[2] - lo[2], 1e-300));
+    std::vector<uint32_t> key(tiles.size());
+    std::vector<size_t> perm(tiles.size());
+    for (size_t i = 0; i < tiles.size(); i++) {
+      uint32_t q[3];
+      for (int l = 0; l < 3; l++) q[l] = (uint32_t)std::min(1023.0, std::floor((pos[l + 3 * (size_t)tiles[i].s[0]] - lo[l]) / ext * 1024.0));
+      key[i] = morton_spread10(q[0]) | (morton_spread10(q[1]) << 1) | (morton_spread10(q[2]) << 2);
+      perm[i] = i;
+    }
+    std::sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return key[a] != key[b] ? key[a] < key[b] : tiles[a].s[0] < tiles[b].s[0]; });
+    std::vector<T> sorted(tiles.size());
+    for (size_t i = 0; i < tiles.size(); i++) sorted[i] = tiles[perm[i]];
+    tiles.swap(sorted);
+  } else {
+    std::sort(tiles.begin(), tiles.end(), [](const T &a, const T &b) { return a.s[0] < b.s[0]; });
+  }
   const int nt = (int)tiles.size();
   std::vector<int32_t> hs((size_t)nt * DM_S), hc(nt), hn((size_t)nt * ng * DM_S);
   for (int i = 0; i < nt; i++) {

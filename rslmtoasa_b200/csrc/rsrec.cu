@@ -56,6 +56,7 @@ struct rsrec_handle_s {
   size_t prof_used = 0;
   // host copies of the reference arrays (small) so that device sets can be (re)built in any call order
   std::vector<int32_t> nn, iz;
+  std::vector<double> pos;  // optional lattice%cr (3,kk): only used to order the work (L2 locality), never in arithmetic
   std::vector<cplx> ee, eeo, hall, hallo, lsham, enim, v_a, v_b, vo_a, vo_b;
   bool have_lat = false, have_ham = false, have_op[2] = {false, false}, dirty = true /* lattice tables */, dirty_ham = true /* block sets */;
   // device operator data
@@ -200,7 +201,7 @@ static int ensure_ready(H *h) {
       for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj[fill[a]++] = i; }
   }
 
-  if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
+  if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls, h->pos.empty() ? nullptr : h->pos.data()) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
   h->h2d_bytes += (long long)h->tiles.ntiles * (DM_S + 1 + (long long)ng * DM_S) * 4;
   CUDA_TRY(cudaDeviceSynchronize());  // the tile tables went through the legacy stream: make sure they have landed
   h->dirty = false;
@@ -1782,6 +1783,15 @@ int rsrec_lanczos_block_local_axis(rsrec_handle h, int nunits, const int32_t *si
     TRY(rotate_sets(h, mom + 3 * (size_t)u));
     TRY(rsrec_lanczos_block(h, 1, site_i + u, nullptr, nullptr, nullptr, lld, a_b + (size_t)u * lld * BLKC, b2_b + (size_t)u * lld * BLKC));
   }
+  return RSREC_OK;
+}
+
+// Optional: lattice%cr (3,kk).  Coordinates never enter the arithmetic; they only order the 8-site tiles along a
+// space-filling curve so that the gathers of concurrently running CTAs hit L2 (results are bit-identical either way).
+int rsrec_set_positions(rsrec_handle h, const double *cr) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  if (cr) h->pos.assign(cr, cr + (size_t)3 * h->kk); else h->pos.clear();
+  h->dirty = true;
   return RSREC_OK;
 }
 

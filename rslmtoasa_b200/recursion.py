@@ -92,6 +92,9 @@ class Recursion:
         nn = np.asfortranarray(lat.nn, dtype=np.int32)
         iz = np.ascontiguousarray(lat.iz, dtype=np.int32)
         _lib.check(L.rsrec_set_lattice(self._h, _p(nn), _p(iz)))
+        if getattr(lat, "cr", None) is not None:      # lattice%cr: work ordering only (L2 locality)
+            cr = np.asfortranarray(lat.cr, dtype=np.float64)
+            _lib.check(L.rsrec_set_positions(self._h, _p(cr)))
         arrs = [_fc(getattr(ham, k, None)) for k in ("ee", "eeo", "hall", "hallo", "lsham", "enim")]
         _lib.check(L.rsrec_set_hamiltonian(self._h, *[_p(x) for x in arrs], int(bool(ham.hoh))))
         if getattr(ham, "v_a", None) is not None:

@@ -140,6 +140,16 @@ def sphere_cluster(kind: str = "bcc", r2: float = 8.0, ntype: int = 1, nmax: int
                    irec=np.array([1], dtype=np.int32), cr=pts.T.copy(), disp=disp)
 
 
+def periodic_bcc_positions(nx: int, ny: int, nz: int) -> np.ndarray:
+    """(3, kk) coordinates in units of a/2 of periodic_bcc's sites (the reference's lattice%cr up to the factor alat/2)."""
+    idx = np.arange(nx * ny * nz, dtype=np.int64)
+    cell = np.stack([idx % nx, (idx // nx) % ny, idx // (nx * ny)]).astype(np.float64) * 2.0
+    cr = np.empty((3, 2 * nx * ny * nz), dtype=np.float64, order="F")
+    cr[:, 0::2] = cell
+    cr[:, 1::2] = cell + 1.0
+    return cr
+
+
 def periodic_bcc(nx: int, ny: int, nz: int, ntype: int = 1) -> Lattice:
     """bcc with periodic boundaries, nx*ny*nz cubic cells x 2 atoms, generated analytically (O(kk)).
 

@@ -365,3 +365,20 @@ def test_edge_sizes_and_empty_inputs(oracle_mod):
     rec.recur_b()
     assert relerr(rec.a_b[:, :, 0, 0], h1.ee[:, :, 0, 0] + h1.lsham[:, :, 0]) < 1e-14
     assert np.abs(rec.b2_b[:, :, 1, 0]).max() < 1e-25
+
+
+def test_positions_only_reorder_the_work():
+    """rsrec_set_positions (lattice%cr) sorts the tiles along a Morton curve for L2 locality: bit-identical results"""
+    from rslmtoasa_b200 import synthetic as S
+    lat = S.periodic_bcc(6, 5, 4)
+    ham = S.make_hamiltonian(lat, seed=20260104)
+    ph = S.random_phases(lat.kk, 2)
+    outs = []
+    for with_pos in (False, True):
+        lat.cr = S.periodic_bcc_positions(6, 5, 4) if with_pos else None
+        rec = _rec(lat, ham, lld=6, phases=ph)
+        rec.chebyshev_recur_random()
+        mu = rec.mu_n.copy()
+        rec.recur_b()
+        outs.append((mu, rec.a_b.copy(), rec.b2_b.copy()))
+    assert all(np.array_equal(x, y) for x, y in zip(*outs))
