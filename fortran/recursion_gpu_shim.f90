@@ -31,6 +31,7 @@ contains
                                        int(this%lattice%ntype, c_int), int(this%lattice%nmax, c_int)), __FILE__, __LINE__)
       end if
       call rsrec_check(rsrec_set_lattice(this%gpu, this%lattice%nn, this%lattice%iz), __FILE__, __LINE__)
+      call rsrec_check(rsrec_set_positions(this%gpu, this%lattice%cr), __FILE__, __LINE__)   ! work ordering only
       call rsrec_check(rsrec_set_hamiltonian(this%gpu, c_loc(this%hamiltonian%ee), c_loc(this%hamiltonian%eeo), &
                                              c_loc(this%hamiltonian%hall), c_loc(this%hamiltonian%hallo), &
                                              c_loc(this%hamiltonian%lsham), c_loc(this%hamiltonian%enim), &

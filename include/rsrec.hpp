@@ -30,6 +30,7 @@ struct lattice {  // lattice.f90:144-309 (members on the hot path)
   std::vector<int32_t> iz;      // (kk)
   std::vector<int32_t> irec;    // (nrec) recursion sites
   std::vector<int32_t> ijpair;  // (njij, 2) column-major
+  std::vector<double> cr;       // optional (3, kk) coordinates: work ordering only
   int nslot() const {
     int m = 0;
     for (int i = 0; i < kk; i++) m = nn[i] > m ? nn[i] : m;
@@ -91,6 +92,7 @@ class recursion {
 
   void upload() {
     check(rsrec_set_lattice(h_, lat_.nn.data(), lat_.iz.data()));
+    if (!lat_.cr.empty()) check(rsrec_set_positions(h_, lat_.cr.data()));
     check(rsrec_set_hamiltonian(h_, p(ham_.ee), p(ham_.eeo), p(ham_.hall), p(ham_.hallo), p(ham_.lsham), p(ham_.enim),
                                 ham_.hoh));
     if (!ham_.v_a.empty()) {
