@@ -309,7 +309,7 @@ k_gram_dmma(const double *__restrict__ X, const double *__restrict__ Y, int two,
 
   // fragment source offsets (doubles, relative to the stage base: X block at 0, Y block at BLKD)
   const int nmt = two ? 5 : 3;
-  int aoff[5], boff[5], bneg_from[5];  // B operand: k' >= bneg_from -> negate (never: 99)
+  int aoff[5], boff[5];
   bool bswap[5];
 #pragma unroll
   for (int mt = 0; mt < 5; mt++) {
@@ -608,9 +608,8 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
 
 // ---- host side ------------------------------------------------------------------------------------------------
 static int dmma_configure() {
-  cudaError_t e;
 #define DM_ATTR(K) \
-  if ((e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES)) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES) != cudaSuccess) return -3;
   DM_ATTR((k_apply_dmma<EPI_STORE, false>))
   DM_ATTR((k_apply_dmma<EPI_STORE, true>))
   DM_ATTR((k_apply_dmma<EPI_HAM, false>))
@@ -620,9 +619,9 @@ static int dmma_configure() {
   DM_ATTR((k_apply_dmma<EPI_HOP, false>))
   DM_ATTR((k_apply_dmma<EPI_HOP, true>))
 #undef DM_ATTR
-  if ((e = cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES)) != cudaSuccess) return -3;
-  if ((e = cudaFuncSetAttribute(k_rmul_dmma<RM_ORTHO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES)) != cudaSuccess) return -3;
-  if ((e = cudaFuncSetAttribute(k_rmul_dmma<RM_ROTATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES)) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_rmul_dmma<RM_ORTHO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_rmul_dmma<RM_ROTATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES) != cudaSuccess) return -3;
   return 0;
 }
 

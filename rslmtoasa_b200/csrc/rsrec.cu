@@ -131,43 +131,25 @@ static int zero_vec(H *h, double *v, int nunits) {
   return RSREC_OK;
 }
 
-// host complex col-major block (r + 18 k) -> HR36 real embedding [[Hr,-Hi],[Hi,Hr]] (36x36 row-major), scaled
-static void add_block(const cplx *src, double *dst, double scale = 1.0) {
-  for (int k = 0; k < NB; k++)
-    for (int r = 0; r < NB; r++) {
-      const double re = scale * src[r + NB * k].re, im = scale * src[r + NB * k].im;
-      dst[r * COLD + k] += re;
-      dst[r * COLD + NB + k] -= im;
-      dst[(r + NB) * COLD + k] += im;
-      dst[(r + NB) * COLD + NB + k] += re;
-    }
-}
-static void pack_block(const cplx *src, double *dst, double scale) {
-  for (int e = 0; e < HBLK; e++) dst[e] = 0.0;
-  add_block(src, dst, scale);
-}
-
-static long long g_upload_bytes = 0;  // folded into the handle's h2d counter by ensure_ready
-static cudaStream_t g_upload_stream = nullptr;
 // Stream-ordered on the handle's stream: a synchronous cudaMemcpy from pageable memory returns once the data is in the
 // driver's staging buffer, NOT when it has reached the device, and the handle's stream is non-blocking -- a kernel
 // launched on it right afterwards could read the destination before the DMA lands.
-static int upload(DevBuf &b, const std::vector<double> &host) {
-  TRY(dev_alloc(b, host.size(), false));
-  CUDA_TRY(cudaMemcpyAsync(b.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, g_upload_stream));
-  g_upload_bytes += (long long)(host.size() * sizeof(double));
-  return RSREC_OK;
-}
+static int upload(rsrec_handle_s *h, DevBuf &b, const std::vector<double> &host);
 
 // Build the device operator sets from the host copies (the "device-resident CSR-of-blocks" export of the
 // hamiltonian builder and the device index array of the lattice): classes 0..ntype-1 = bulk types (ee),
 // ntype..ntype+nmax-1 = site-indexed local region (hall) -- hamiltonian.f90:1553-1667, lattice.f90:1856-1860.
+static int upload(H *h, DevBuf &b, const std::vector<double> &host) {
+  TRY(dev_alloc(b, host.size(), false));
+  CUDA_TRY(cudaMemcpyAsync(b.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  h->h2d_bytes += (long long)(host.size() * sizeof(double));
+  return RSREC_OK;
+}
+
 static int ensure_ready(H *h) {
   if (!h->have_lat) return fail(RSREC_EINVAL, "rsrec_set_lattice has not been called");
   if (!h->have_ham) return fail(RSREC_EINVAL, "rsrec_set_hamiltonian has not been called");
   if (!h->dirty && !h->dirty_ham) return RSREC_OK;
-  g_upload_bytes = 0;
-  g_upload_stream = h->st;
   const int kk = h->kk, nslot = h->nslot, ncls = h->ncls, ng = h->ncols;
   if (h->dirty) {
   // neighbour table [slot][site], slot 0 = self, missing -> kk
@@ -220,15 +202,15 @@ static int ensure_ready(H *h) {
       std::vector<double> st(nblk * BLKD, 0.0);
       if (!ty.empty()) memcpy(st.data(), ty.data(), ntb * BLKD * sizeof(double));
       if (!loc.empty()) memcpy(st.data() + ntb * BLKD, loc.data(), (nblk - ntb) * BLKD * sizeof(double));
-      return upload(dst, st);
+      return upload(h, dst, st);
     };
     TRY(stage(h->cBLK, h->ee, h->hall));
     std::vector<double> ls((const double *)h->lsham.data(), (const double *)h->lsham.data() + (size_t)h->ntype * BLKD);
-    TRY(upload(h->cLS, ls));
+    TRY(upload(h, h->cLS, ls));
     if (h->hoh) {
       TRY(stage(h->cBLKO, h->eeo, h->hallo));
       std::vector<double> en((const double *)h->enim.data(), (const double *)h->enim.data() + (size_t)h->ntype * BLKD);
-      TRY(upload(h->cENIM, en));
+      TRY(upload(h, h->cENIM, en));
     }
   }
   // HR36 packing on the device (hamiltonian.f90:1553-1667 exports): locham = H_on + lsham summed before the product
@@ -255,12 +237,12 @@ static int ensure_ready(H *h) {
     if (!h->have_op[s]) continue;
     const std::vector<cplx> &v = s == 0 ? h->v_a : h->v_b, &vo = s == 0 ? h->vo_a : h->vo_b;
     std::vector<double> sv((const double *)v.data(), (const double *)v.data() + ntb * BLKD);
-    TRY(upload(h->cV[s], sv));
+    TRY(upload(h, h->cV[s], sv));
     TRY(pack(s == 0 ? h->Hva : h->Hvb, h->cV[s].p, h->ntype, nullptr, 1.0, 0, 0));
     if (h->hoh) {
       if (!vo.empty()) {  // on-site vo term is commented out in the reference (761): slot 0 stays zero
         std::vector<double> svo((const double *)vo.data(), (const double *)vo.data() + ntb * BLKD);
-        TRY(upload(h->cVO[s], svo));
+        TRY(upload(h, h->cVO[s], svo));
         TRY(pack(s == 0 ? h->Hvoa_neg : h->Hvob_neg, h->cVO[s].p, h->ntype, nullptr, -1.0, 0, 1));
       } else {
         TRY(dev_alloc(s == 0 ? h->Hvoa_neg : h->Hvob_neg, setn, false));
@@ -270,7 +252,6 @@ static int ensure_ready(H *h) {
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->st));
-  h->h2d_bytes += g_upload_bytes;
   h->dirty_ham = false;
   return RSREC_OK;
 }
@@ -709,7 +690,11 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
   if (const char *f = getenv("RSREC_SQRT_METHOD")) h->sqrt_method = atoi(f);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  if (dmma_configure() != 0 || kubo_configure() != 0 || post_configure() != 0 || ham_configure() != 0) return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
+  if (dmma_configure() != 0 || kubo_configure() != 0 || post_configure() != 0 || ham_configure() != 0) {
+    cudaStreamDestroy(h->st);
+    delete h;
+    return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
+  }
   *out = h;
   return RSREC_OK;
 }
