@@ -186,6 +186,7 @@ __global__ void k_terminf_fix(double *a_inf, double *b_inf, double *a_inf0, doub
 #endif
 #define BG_LD 19  // padded column stride (complex) so that the 16-byte column accesses of 8 lanes hit 8 bank groups
 #define BG_MAT (NB * BG_LD)
+#define BG_WSTRIDE (BG_MAT + NB)  // per-warp shared memory: Q plus the 18 pivot reciprocals
 
 // a_b, b_b: (18,18,ll,na) complex, b_b = B (after zsqr); g: (18,18,nv,na).  Channels ie0..ie0+ie_len-1 (0-based) are
 // written, the rest of g is left untouched (the caller zeroes it, like bgreen's g_out = 0).
@@ -194,7 +195,8 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
          int nv, int ie0, int ie_len, const double *__restrict__ a_inf, const double *__restrict__ b_inf, double eta_re,
          double eta_im, int sym_term, double2 *__restrict__ g) {
   extern __shared__ double2 bg_smem[];
-  double2 *sA = bg_smem, *sB = bg_smem + BG_MAT, *Q = bg_smem + 2 * BG_MAT + (threadIdx.x >> 5) * BG_MAT;
+  double2 *sA = bg_smem, *sB = bg_smem + BG_MAT, *Q = bg_smem + 2 * BG_MAT + (threadIdx.x >> 5) * BG_WSTRIDE;
+  double2 *dinv = Q + BG_MAT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, unit = blockIdx.y;
   const int iel = blockIdx.x * BG_WARPS + warp;
   const bool live = iel < ie_len;
@@ -255,7 +257,12 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
       if (act && p != k) { const double2 t = q[k]; q[k] = q[p]; q[p] = t; }
       __syncwarp();
       if (lane == k) {
-        const double2 r = c_div(make_double2(1.0, 0.0), q[k]);
+        // 1/u_kk = conj(u)/|u|^2: one division; kept for the back substitution (x_i /= u_ii becomes a product).
+        // Divisions are the longest dependent operations of the level, 36 of them were on its critical path.
+        const double2 u = q[k];
+        const double inv = 1.0 / (u.x * u.x + u.y * u.y);
+        const double2 r = make_double2(u.x * inv, -u.y * inv);
+        dinv[k] = r;
         for (int i = k + 1; i < NB; i++) q[i] = c_mul(q[i], r);
       }
       __syncwarp();
@@ -279,7 +286,7 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
     for (int i = NB - 1; i >= 0; i--) {
 #pragma unroll
       for (int k = i + 1; k < NB; k++) x[i] = c_sub(x[i], c_mul(Q[k * BG_LD + i], x[k]));
-      x[i] = c_div(x[i], Q[i * BG_LD + i]);
+      x[i] = c_mul(x[i], dinv[i]);
     }
     __syncwarp();  // all lanes have read the factors
     if (act) {

@@ -1061,7 +1061,7 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
 // scalar continued fraction, Kubo-Bastin integrand.  d_* functions work on device arrays (so that the fused entry
 // points can chain them behind a recursion without a host round trip); the rsrec_* wrappers marshal host arrays.
 static int post_configure() {
-  const int smem = (2 + BG_WARPS) * BG_MAT * (int)sizeof(double2);
+  const int smem = (2 * BG_MAT + BG_WARPS * BG_WSTRIDE) * (int)sizeof(double2);
   return cudaFuncSetAttribute(k_bgreen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess ? 0 : -1;
 }
 static int to_dev(H *h, DevBuf &b, const void *src, size_t ndoubles) {
@@ -1101,7 +1101,7 @@ static int d_bgreen(H *h, const double *d_ab, const double *d_bb, int ll, int na
                     double *d_g) {
   CUDA_TRY(cudaMemsetAsync(d_g, 0, (size_t)na * nv * BLKD * sizeof(double), h->st));
   if (ie_len <= 0) return RSREC_OK;
-  const int smem = (2 + BG_WARPS) * BG_MAT * (int)sizeof(double2);
+  const int smem = (2 * BG_MAT + BG_WARPS * BG_WSTRIDE) * (int)sizeof(double2);
   k_bgreen<<<dim3((ie_len + BG_WARPS - 1) / BG_WARPS, na), BG_WARPS * 32, smem, h->st>>>(
       (const double2 *)d_ab, (const double2 *)d_bb, ll, d_ene, nv, ie0, ie_len, d_ainf, d_binf, eta_re, eta_im, sym_term,
       (double2 *)d_g);
