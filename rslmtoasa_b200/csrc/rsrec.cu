@@ -336,9 +336,13 @@ static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *si
       for (int k = 0; k < DM_S && b * DM_S + k < kk; k++) m = std::min(m, level[b * DM_S + k]);
       bl[b] = m;
     }
-    std::vector<int32_t> bc(ml + 2, 0);
+    // a contiguous block can lie deeper than every class tile (tiles collect far-apart sites of one class): its own maximum
+    int mlb = 0;
+    for (int b = 0; b < nb; b++) if (bl[b] != INT32_MAX) mlb = std::max(mlb, bl[b]);
+    maxlevel = std::max(maxlevel, mlb);
+    std::vector<int32_t> bc(mlb + 2, 0);
     for (int b = 0; b < nb; b++) if (bl[b] != INT32_MAX) bc[bl[b] + 1]++;
-    for (int L = 0; L <= ml; L++) bc[L + 1] += bc[L];
+    for (int L = 0; L <= mlb; L++) bc[L + 1] += bc[L];
     bcum[u].assign(bc.begin() + 1, bc.end());
     std::vector<int32_t> bpos(bc.begin(), bc.end() - 1);
     int32_t *bo = border.data() + (size_t)u * nb;

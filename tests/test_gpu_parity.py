@@ -382,3 +382,48 @@ def test_positions_only_reorder_the_work():
         rec.recur_b()
         outs.append((mu, rec.a_b.copy(), rec.b2_b.copy()))
     assert all(np.array_equal(x, y) for x, y in zip(*outs))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_lattices_and_holes(oracle_mod, seed):
+    """fuzz: random cluster radius / typing / local region / hoh, neighbour entries zeroed at random inside the slot
+    lists (what chbar_nc does when hmfind fails, hamiltonian.f90:2350-2352), random recursion sites and pair units"""
+    from rslmtoasa_b200 import synthetic as S
+    rng = np.random.default_rng(1000 + seed)
+    kind = ["bcc", "fcc"][seed % 2]
+    ntype = int(rng.integers(1, 4))
+    nmax = int(rng.integers(0, 6))
+    lat = S.sphere_cluster(kind, float(rng.uniform(2.0, 7.0)), ntype=ntype, nmax=nmax,
+                           type_rule="layer" if ntype > 1 else "single")
+    ham = S.make_hamiltonian(lat, seed=seed, hoh=bool(seed & 2))
+    nn = lat.nn.copy(order="F")
+    holes = rng.random(nn.shape) < 0.08
+    holes[:, 0] = False
+    nn[holes] = 0
+    lat.nn = nn
+    nrec = int(rng.integers(1, 4))
+    lat.irec = rng.choice(np.arange(1, lat.kk + 1), size=min(nrec, lat.kk), replace=False).astype(np.int32)
+    lld = int(rng.integers(3, 8))
+    family = seed % 2
+    rec = _rec(lat, ham, lld=lld)
+    rec.set_kernel_family(family)
+    orc = oracle_mod.Oracle(lat, ham)
+    rec.recur_b()
+    a_b, b2_b = orc.lanczos_block(lat.irec, lld)
+    # holes make H non-Hermitian: B^2 can leave the PSD cone late in the chain on both sides alike; compare the stable part
+    ok = np.isfinite(a_b).all(axis=(0, 1, 3)) & np.isfinite(rec.a_b).all(axis=(0, 1, 3))
+    n_ok = int(np.argmin(ok)) if not ok.all() else lld
+    assert n_ok >= 2
+    assert relerr(rec.a_b[:, :, :n_ok], a_b[:, :, :n_ok]) < 1e-8 and relerr(rec.b2_b[:, :, :n_ok], b2_b[:, :, :n_ok]) < 1e-8
+    rec.chebyshev_recur()
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    mu, _ = orc.cheb_moments(lat.irec, lld, a, b)
+    assert relerr(rec.mu_n, mu) < TOL_MU
+    if lat.kk >= 3:
+        i, j = (int(v) for v in rng.choice(np.arange(1, lat.kk + 1), size=2, replace=False))
+        rec2 = _rec(lat, ham, lld=lld, ijpair=np.array([[i, j]], dtype=np.int32))
+        rec2.set_kernel_family(family)
+        rec2.chebyshev_recur_ij()
+        s = 1 / np.sqrt(2)
+        mu2, _ = orc.cheb_moments([i] * 4, lld, a, b, site_j=[j] * 4, asign=[s] * 4, bsign=[s, -s, 1j * s, -1j * s])
+        assert relerr(rec2.mu_n, mu2) < TOL_MU
