@@ -71,3 +71,27 @@ def test_million_site_periodic_table_properties():
         assert (back == 1).all()                                 # reciprocity
     with pytest.raises(Exception):
         build_nn(crd[:, :1000], np.ones(1000, np.int32), [1000], 1.1 * ALAT)     # edge representative -> VECTOR NOT FOUND
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_point_clouds_bit_exact(oracle_mod, seed):
+    """fuzz: arbitrary coordinates (no lattice), every site its own bravais type so that remd maps trivially; random
+    cut-off; open, partially periodic and fully periodic boxes (skewed cell for odd seeds)"""
+    from rslmtoasa_b200.lattice import build_nn
+    rng = np.random.default_rng(50 + seed)
+    n = int(rng.integers(40, 400))
+    box = rng.uniform(4.0, 9.0, size=3)
+    a = np.diag(box)
+    if seed % 2:
+        a[0, 1], a[0, 2], a[1, 2] = rng.uniform(-1.0, 1.0, size=3)       # columns = cell vectors a1, a2, a3
+    frac = rng.random((3, n))
+    crd = a @ frac
+    no = np.arange(1, n + 1, dtype=np.int32)
+    iu = np.arange(1, n + 1, dtype=np.int32)
+    ct = float(rng.uniform(0.8, 2.2))
+    pbc = [None, (1, 1, 1), (1, 0, 1), (0, 1, 0), (1, 1, 1), None][seed]
+    kw = {} if pbc is None else dict(pbc=pbc, nrep=(1, 1, 1), a=a, alat=1.0)
+    nn, nm = build_nn(crd, no, iu, ct, **kw)
+    ref, rnm, rc = oracle_mod.build_nn(crd, no, iu, ct, **kw)
+    assert rc == 0 and nm == rnm and np.array_equal(nn, ref)
+    assert (nn[:, 0] >= 1).all()

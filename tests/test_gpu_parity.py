@@ -427,3 +427,48 @@ def test_randomised_lattices_and_holes(oracle_mod, seed):
         s = 1 / np.sqrt(2)
         mu2, _ = orc.cheb_moments([i] * 4, lld, a, b, site_j=[j] * 4, asign=[s] * 4, bsign=[s, -s, 1j * s, -1j * s])
         assert relerr(rec2.mu_n, mu2) < TOL_MU
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_kubo_and_scalar(oracle_mod, seed):
+    """fuzz: Kubo-Bastin moments (per_type and random vectors, odd cond_ll, local region present so that the velocity
+    operators skip sites 1..nmax like the reference) and the scalar recursion on random open clusters with holes"""
+    from rslmtoasa_b200 import synthetic as S
+    rng = np.random.default_rng(2000 + seed)
+    kind = ["bcc", "fcc"][seed % 2]
+    ntype, nmax = int(rng.integers(1, 3)), int(rng.integers(0, 4))
+    lat = S.sphere_cluster(kind, float(rng.uniform(2.0, 5.0)), ntype=ntype, nmax=nmax,
+                           type_rule="layer" if ntype > 1 else "single")
+    hoh = bool(seed & 1) and nmax == 0                       # velo_hoh uses the type-indexed sets only
+    ham = S.make_hamiltonian(lat, seed=seed, hoh=hoh, velocity=True)
+    if hoh:
+        ham.vo_a = np.asfortranarray(0.3j * ham.eeo); ham.vo_b = np.asfortranarray(-0.2 * ham.eeo)
+    nn = lat.nn.copy(order="F")
+    holes = rng.random(nn.shape) < 0.05
+    holes[:, 0] = False
+    nn[holes] = 0
+    lat.nn = nn
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    M = int(rng.integers(1, 8))
+    orc = oracle_mod.Oracle(lat, ham)
+    family = (seed // 2) % 2
+    if seed % 3 == 0:
+        sites = rng.choice(np.arange(nmax + 1, lat.kk + 1), size=2, replace=False).astype(np.int32)
+        rec = _rec(lat, ham, cond_ll=M, cond_calctype="per_type", atlist=sites)
+        ref = orc.kubo_moments(M, a, b, start_sites=sites)
+    else:
+        ph = np.asfortranarray(rng.random((lat.kk, 2)))
+        rec = _rec(lat, ham, cond_ll=M, cond_calctype="random_vec", phases=ph)
+        ref = orc.kubo_moments(M, a, b, phases=ph)
+    rec.set_kernel_family(family)
+    rec.compute_moments_stochastic()
+    assert relerr(rec.mu_nm_stochastic, ref) < TOL_MU
+    # scalar recursion on the spin-diagonal part
+    ham1 = S.make_hamiltonian(lat, seed=seed, spin_orbit=False)
+    lat.irec = rng.choice(np.arange(1, lat.kk + 1), size=2, replace=False).astype(np.int32)
+    lld = int(rng.integers(2, 7))
+    rec = _rec(lat, ham1, lld=lld)
+    rec.set_kernel_family(family)
+    rec.recur()
+    sa, sb = oracle_mod.Oracle(lat, ham1).lanczos_scalar(lat.irec, lld)
+    assert relerr(rec.a[..., 0], sa) < 1e-8 and relerr(rec.b2[..., 0], sb) < 1e-8

@@ -304,3 +304,52 @@ def test_block_green_full_mesh_size(oracle_mod):
     d = np.arange(18)
     ldos = -g0[d, d].imag.sum(0) / np.pi
     assert np.nanmin(ldos) > -1e-6
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_randomised_consumers(oracle_mod, block_rec, seed):
+    """fuzz: random Hermitian A_l / positive definite B_l chains, random moments, random scalar chains and mesh sizes"""
+    from rslmtoasa_b200 import Green, Dos, Conductivity, Energy
+    rng = np.random.default_rng(300 + seed)
+    ll, na = int(rng.integers(2, 12)), int(rng.integers(1, 4))
+    channels = int(rng.integers(2, 90)) * 2
+
+    def herm(scale):
+        m = rng.normal(size=(18, 18)) + 1j * rng.normal(size=(18, 18))
+        return scale * (m + m.conj().T) / 2
+
+    a_b = np.zeros((18, 18, ll, na), complex, order="F"); b_b = np.zeros_like(a_b)
+    for u in range(na):
+        for l in range(ll):
+            a_b[:, :, l, u] = herm(0.1) + np.diag(rng.uniform(-0.3, 0.3, 18))
+            h = herm(0.05)
+            b_b[:, :, l, u] = h @ h + 0.3 * np.eye(18)                 # Hermitian positive definite, like zsqr's output
+    rec = block_rec
+    saved = (rec.a_b, rec.b2_b, rec.en)
+    try:
+        rec.en = Energy(-1.5, 1.5, channels_ldos=channels, fermi=float(rng.uniform(-0.5, 0.5)))
+        rec.en.e_mesh()
+        rec.a_b, rec.b2_b = a_b, b_b
+        for sym in (False, True):
+            g = Green(rec, sym_term=sym)
+            assert relerr(g.block_green(), oracle_mod.block_green(a_b, b_b, g.ene, sym)) < TOL_G
+        a_inf, b_inf, a0, b0 = g.get_terminf()
+        oa, ob, oa0, ob0 = oracle_mod.get_terminf(a_b, b_b)
+        assert np.array_equal(a_inf, oa, equal_nan=True) and np.array_equal(b_inf, ob, equal_nan=True)
+        lld = int(rng.integers(0, 9))
+        mu = np.asfortranarray(rng.normal(size=(18, 18, 2 * lld + 2, na)) + 1j * rng.normal(size=(18, 18, 2 * lld + 2, na)))
+        rec.mu_n = mu
+        g0 = Green(rec).chebyshev_green()
+        mu_ng, ref = oracle_mod.chebyshev_green(mu, g.ene, -1.5, 1.5)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(g0), ok) and relerr(g0[ok], ref[ok]) < TOL_SUM
+        lls = int(rng.integers(2, 15))
+        a = np.asfortranarray(rng.uniform(-0.3, 0.3, size=(lls, 18, na, 3)))
+        b2 = np.asfortranarray(rng.uniform(0.02, 0.2, size=(lls, 18, na, 3)))
+        rec.a, rec.b2 = a, b2
+        dw = 1.0 + 0.05 * rng.normal(size=(18, na)); cs = 0.02 * rng.normal(size=(18, na))
+        for nmdir in (1, 3):
+            got = Green(rec).sgreen(dw, cs, nmdir)
+            assert relerr(got, oracle_mod.sgreen(a, b2, nmdir, g.ene, dw, cs)) < 1e-12
+    finally:
+        rec.a_b, rec.b2_b, rec.en = saved
