@@ -281,6 +281,7 @@ static int unit_batch(H *h, int nunits, int nvec) {
   double avail = 0.9 * (double)(fr + held);
   size_t per = vstride(h) * sizeof(double) * nvec;
   int nb = (int)std::max(1.0, std::floor(avail / (double)per));
+  if (const char *f = getenv("RSREC_UNIT_BATCH")) nb = std::max(1, std::min(nb, atoi(f)));  // tests: force small batches
   return std::min(nunits, nb);
 }
 

@@ -472,3 +472,35 @@ def test_randomised_kubo_and_scalar(oracle_mod, seed):
     rec.recur()
     sa, sb = oracle_mod.Oracle(lat, ham1).lanczos_scalar(lat.irec, lld)
     assert relerr(rec.a[..., 0], sa) < 1e-8 and relerr(rec.b2[..., 0], sb) < 1e-8
+
+
+def test_unit_batching_when_memory_is_short(oracle_mod, monkeypatch):
+    """units that do not fit in device memory together are processed in batches (RSREC_UNIT_BATCH forces it here):
+    every driver gives the unbatched result (the reduction grids differ, so to rounding)"""
+    lat, ham = case("surface")                       # 4 recursion sites
+    pairs = np.array([[1, 2], [5, 5], [2, 9]], dtype=np.int32)
+    ref = _rec(lat, ham, lld=6, ijpair=pairs)
+    ref.recur_b(); a0, b0 = ref.a_b.copy(), ref.b2_b.copy()
+    ref.chebyshev_recur(); m0 = ref.mu_n.copy()
+    ref.recur_b_ij(); aij0 = ref.a_b.copy()
+    for nb in ("1", "3"):
+        monkeypatch.setenv("RSREC_UNIT_BATCH", nb)
+        rec = _rec(lat, ham, lld=6, ijpair=pairs)
+        rec.recur_b()
+        assert relerr(rec.a_b, a0) < 1e-12 and relerr(rec.b2_b, b0) < 1e-12
+        rec.chebyshev_recur()
+        assert relerr(rec.mu_n, m0) < 1e-12
+        rec.recur_b_ij()
+        assert relerr(rec.a_b, aij0) < 1e-12
+        from rslmtoasa_b200 import Green
+        g = Green(rec)
+        rec2 = _rec(lat, ham, lld=6)
+        g2 = Green(rec2)
+        monkeypatch.delenv("RSREC_UNIT_BATCH")
+        want = g2.recur_b_green().copy()
+        monkeypatch.setenv("RSREC_UNIT_BATCH", nb)
+        rec3 = _rec(lat, ham, lld=6)
+        got = Green(rec3).recur_b_green()
+        ok = np.isfinite(want)
+        assert relerr(got[ok], want[ok]) < 1e-9
+    monkeypatch.delenv("RSREC_UNIT_BATCH")
