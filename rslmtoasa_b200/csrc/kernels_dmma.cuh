@@ -27,7 +27,23 @@
 #define DM_CONSUMERS 8
 #define DM_THREADS (32 * (DM_CONSUMERS + 1))
 #define DM_MAXST 48
+#ifndef DM_APPLY_S
+#define DM_APPLY_S 4  // default geometry of the SpMV kernel (8: one CTA per SM, 4: two half-tile CTAs per SM)
+#endif
 #define DM_SMEM_BYTES (DM_STAGES * DM_STAGE_D * 8 + 64)
+// The SpMV kernel comes in two geometries (template parameter S = sites per CTA pass):
+//   S = 8: one CTA per SM, 8 consumer warps on a whole tile, 4-stage ring of 51.8 kB stages;
+//   S = 4: two CTAs per SM, each with 4 consumer warps on HALF a tile (one warp per SM sub-partition), 3-stage ring of
+//          31.1 kB stages.  The two warps of a sub-partition then belong to different CTAs and drift out of phase, so
+//          stage boundaries and epilogues of one overlap the DMMAs of the other.
+template <int S> struct ApGeom {
+  static constexpr int kConsumers = S;
+  static constexpr int kStages = S == 8 ? 4 : 3;
+  static constexpr int kStageD = HBLK + S * BLKD;
+  static constexpr int kThreads = 32 * (S + 1);
+  static constexpr int kSmem = kStages * kStageD * 8 + 64;
+  static constexpr int kMinBlocks = S == 8 ? 1 : 2;
+};
 
 struct DmmaTiles {
   int ntiles = 0, ng = 0, kk = 0;
@@ -83,7 +99,7 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 
 // One consumer warp of k_apply_dmma.  XN = number of units this warp owns in its shared m-tile (compile time so that
 // no DMMA is ever issued predicated-off: a predicated-off DMMA still occupies the tensor pipe).
-template <int EPI, bool ADDEND, int XN>
+template <int EPI, bool ADDEND, int XN, int S>
 __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaStages &st,
                                               const int32_t *__restrict__ tile_sites, double *stages, uint64_t *full,
                                               uint64_t *empty, int ntiles, int nunits,
@@ -92,9 +108,11 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
   const int g = lane >> 2, q = lane & 3;
   const int nst = st.n;
   const double inv_a = 1.0 / p.a;  // the epilogue multiplies by 1/a (<= 1 ulp from the reference's division)
-  const int mt0 = 2 * warp, mt1 = 2 * warp + 1, mt2 = 16 + (warp >> 2);
+  constexpr int STG = ApGeom<S>::kStages, STGD = ApGeom<S>::kStageD;
+  // S = 8: 18 m-tiles, warps share m-tiles 16/17;  S = 4: 9 m-tiles, the four warps share m-tile 8
+  const int mt0 = 2 * warp, mt1 = 2 * warp + 1, mt2 = S == 8 ? 16 + (warp >> 2) : 8;
   const int w4 = warp & 3;
-  const int xn0 = (warp == 6) ? 2 : (warp == 7) ? 4 : w4;  // first extra n-tile
+  const int xn0 = (S == 8 && warp == 6) ? 2 : (S == 8 && warp == 7) ? 4 : w4;  // first extra n-tile
   const int xn1 = xn0 + 1;                                  // second one (XN == 2 only)
   int aoff[3], boff[5], xoff[2];
   aoff[0] = HBLK + (mt0 * 8 + g) * COLD + q;
@@ -108,9 +126,10 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
   uint32_t it = 0;
   for (int u = 0; u < nunits; u++) {
     const size_t uo = (size_t)u * p.vstride;
-    const int n_u = cnt ? cnt[u] : ntiles;
+    const int n_u = (cnt ? cnt[u] : ntiles) * (DM_S / S);  // in passes of S sites
     for (int ti = blockIdx.x; ti < n_u; ti += gridDim.x) {
-      const int tile = order ? order[(size_t)u * ntiles + ti] : ti;
+      const int tpos = S == 8 ? ti : ti >> 1, half = S == 8 ? 0 : (ti & 1) * S;
+      const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
       double acc[2][5][2], xacc[XN][2];
 #pragma unroll
       for (int i = 0; i < 2; i++)
@@ -124,13 +143,13 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         const int n = (i == 0 ? mt0 : i == 1 ? mt1 : mt2) * 8 + g;
-        const int site = tile_sites[tile * DM_S + n / NB];
+        const int site = tile_sites[tile * DM_S + half + n / NB];
         gval[i] = site < p.kk;
         goff[i] = uo + (size_t)site * BLKD + (n % NB) * COLD + 2 * q;
       }
       double2 pv[2][5], xpv[XN];  // prefetched `prev` (psi0) fragments
       for (int j = 0; j < nst; j++, it++) {
-        const int slot = it % DM_STAGES;
+        const int slot = it % STG;
         if ((EPI == EPI_CHEB_NOGRAM || EPI == EPI_HOP) && j == nst - 1) {
           // issue the epilogue's global loads now; they land while the last stage is being computed
 #pragma unroll
@@ -146,8 +165,8 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
                                                     : make_double2(0.0, 0.0);
           }
         }
-        mbar_wait(&full[slot], (it / DM_STAGES) & 1);
-        const double *sm = stages + (size_t)slot * DM_STAGE_D;
+        mbar_wait(&full[slot], (it / STG) & 1);
+        const double *sm = stages + (size_t)slot * STGD;
         // fragments of k-step ks+1 are loaded before the DMMAs of k-step ks are issued (register double buffering)
         double b[2][5], a[2][3], xb[2][XN];
 #pragma unroll
@@ -181,8 +200,8 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
         }
       }
       // ===== epilogue from the accumulator fragments; the last stage (self blocks of `in`) is still held =====
-      const int lslot = (it - 1) % DM_STAGES;
-      const double *sm = stages + (size_t)lslot * DM_STAGE_D;
+      const int lslot = (it - 1) % STG;
+      const double *sm = stages + (size_t)lslot * STGD;
       auto finish = [&](double v0, double v1, int n, int nt, size_t go, double2 prev) {
         if (ADDEND) {
           const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go));
@@ -218,8 +237,8 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
 }
 
 // ---- fused gather-SpMV + epilogue ---------------------------------------------------------------------------
-template <int EPI, bool ADDEND>
-__global__ void __launch_bounds__(DM_THREADS, 1)
+template <int EPI, bool ADDEND, int S>
+__global__ void __launch_bounds__(ApGeom<S>::kThreads, ApGeom<S>::kMinBlocks)
 k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_sites, const int32_t *__restrict__ tile_cls,
              const int32_t *__restrict__ tile_nbr, int ntiles, int nunits, const int32_t *__restrict__ order,
              const int32_t *__restrict__ cnt) {
@@ -228,28 +247,30 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
   // (recursion.f90:1629-1636): unreached tiles hold exact zeros and are skipped.
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stages = reinterpret_cast<double *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)DM_STAGES * DM_STAGE_D * 8);
-  uint64_t *empty = full + DM_STAGES;
+  constexpr int STG = ApGeom<S>::kStages, STGD = ApGeom<S>::kStageD, NCONS = ApGeom<S>::kConsumers;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STG * STGD * 8);
+  uint64_t *empty = full + STG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < DM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], DM_CONSUMERS); }
+    for (int s = 0; s < STG; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const int nst = st.n, ng = p.ngather;
 
-  if (warp == DM_CONSUMERS) {
+  if (warp == NCONS) {
     // ===== producer warp: TMA bulk copies =====
     // The (site index, class) of the next stage is fetched from global memory while the warp waits for the ring slot
     // of the current one, so the index-load latency is off the critical path of the pipeline.
     int cu = 0, ci = blockIdx.x, cj = 0;  // cursor: unit, position in the unit's tile list, stage
-    auto count = [&](int u) { return cnt ? cnt[u] : ntiles; };
+    auto count = [&](int u) { return (cnt ? cnt[u] : ntiles) * (DM_S / S); };  // passes of S sites
     auto settle = [&](int &u, int &i) { while (u < nunits && i >= count(u)) { u++; i = blockIdx.x; } };
     auto fetch = [&](int u, int i, int j, int &site, int &cls) {
-      const int tile = order ? order[(size_t)u * ntiles + i] : i;
+      const int tpos = S == 8 ? i : i >> 1, half = S == 8 ? 0 : (i & 1) * S;
+      const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
       cls = tile_cls[tile];
       const int m = st.slot[j];
-      site = (lane < DM_S) ? ((m == 0) ? tile_sites[tile * DM_S + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + lane]) : 0;
+      site = (lane < S) ? ((m == 0) ? tile_sites[tile * DM_S + half + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + half + lane]) : 0;
     };
     settle(cu, ci);
     int site = 0, cls = 0;
@@ -258,14 +279,14 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
       int nu = cu, ni = ci, nj = cj + 1, nsite = 0, ncls = 0;
       if (nj == nst) { nj = 0; ni += gridDim.x; settle(nu, ni); }
       if (nu < nunits) fetch(nu, ni, nj, nsite, ncls);
-      const int slot = it % DM_STAGES;
-      mbar_wait(&empty[slot], ((it / DM_STAGES) & 1) ^ 1);
-      double *sm = stages + (size_t)slot * DM_STAGE_D;
-      if (lane == 0) mbar_expect_tx(&full[slot], DM_STAGE_D * 8);
+      const int slot = it % STG;
+      mbar_wait(&empty[slot], ((it / STG) & 1) ^ 1);
+      double *sm = stages + (size_t)slot * STGD;
+      if (lane == 0) mbar_expect_tx(&full[slot], STGD * 8);
       __syncwarp();
-      if (lane < DM_S) {
+      if (lane < S) {
         bulk_g2s(sm + HBLK + lane * BLKD, st.src[cj] + (size_t)cu * p.vstride + (size_t)site * BLKD, BLKD * 8, &full[slot]);
-      } else if (lane == DM_S) {
+      } else if (lane == S) {
         bulk_g2s(sm, st.H[cj] + (size_t)cls * st.hstride[cj], HBLK * 8, &full[slot]);
       }
       cu = nu; ci = ni; cj = nj; site = nsite; cls = ncls;
@@ -278,10 +299,10 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
   // shared m-tiles 16/17, so the sub-partitions carry 22/22/23/23 units and the two warps of a sub-partition stay
   // within one unit of each other (both keep the tensor pipe fed).
   //   m-tile 16: w0:n0  w1:n1  w2:n2  w3:n3,n4        m-tile 17: w4:n0  w5:n1  w6:n2,n3  w7:n4
-  if (warp == 3 || warp == 6)
-    dmma_consumer<EPI, ADDEND, 2>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+  if (warp == 3 || (S == 8 && warp == 6))
+    dmma_consumer<EPI, ADDEND, 2, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
   else
-    dmma_consumer<EPI, ADDEND, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+    dmma_consumer<EPI, ADDEND, 1, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
 }
 
 // ---- Gram reductions on the tensor pipe -------------------------------------------------------------------------
@@ -608,16 +629,17 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
 
 // ---- host side ------------------------------------------------------------------------------------------------
 static int dmma_configure() {
-#define DM_ATTR(K) \
-  if (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES) != cudaSuccess) return -3;
-  DM_ATTR((k_apply_dmma<EPI_STORE, false>))
-  DM_ATTR((k_apply_dmma<EPI_STORE, true>))
-  DM_ATTR((k_apply_dmma<EPI_HAM, false>))
-  DM_ATTR((k_apply_dmma<EPI_HAM, true>))
-  DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, false>))
-  DM_ATTR((k_apply_dmma<EPI_CHEB_NOGRAM, true>))
-  DM_ATTR((k_apply_dmma<EPI_HOP, false>))
-  DM_ATTR((k_apply_dmma<EPI_HOP, true>))
+#define DM_ATTR(E, A) \
+  if (cudaFuncSetAttribute(k_apply_dmma<E, A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<8>::kSmem) != cudaSuccess) return -3; \
+  if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3;
+  DM_ATTR(EPI_STORE, false)
+  DM_ATTR(EPI_STORE, true)
+  DM_ATTR(EPI_HAM, false)
+  DM_ATTR(EPI_HAM, true)
+  DM_ATTR(EPI_CHEB_NOGRAM, false)
+  DM_ATTR(EPI_CHEB_NOGRAM, true)
+  DM_ATTR(EPI_HOP, false)
+  DM_ATTR(EPI_HOP, true)
 #undef DM_ATTR
   if (cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES) != cudaSuccess) return -3;
   if (cudaFuncSetAttribute(k_rmul_dmma<RM_ORTHO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES) != cudaSuccess) return -3;
@@ -738,9 +760,17 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
     sg.H[sg.n] = p.Hx; sg.src[sg.n] = p.srcx; sg.hstride[sg.n] = HBLK; sg.slot[sg.n] = 0;
     sg.n++;
   }
-  const int grid = dmma_grid(t, sms);
-#define DM_LAUNCH(E, A) \
-  k_apply_dmma<E, A><<<grid, DM_THREADS, DM_SMEM_BYTES, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr, t.ntiles, nunits, order, cnt)
+  static const int geom = getenv("RSREC_APPLY_S") ? atoi(getenv("RSREC_APPLY_S")) : DM_APPLY_S;
+  const int grid = geom == 4 ? std::max(1, std::min(2 * t.ntiles, 2 * sms)) : dmma_grid(t, sms);
+#define DM_LAUNCH(E, A)                                                                                                   \
+  do {                                                                                                                    \
+    if (geom == 4)                                                                                                        \
+      k_apply_dmma<E, A, 4><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmem, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,       \
+                                                                              t.ntiles, nunits, order, cnt);             \
+    else                                                                                                                  \
+      k_apply_dmma<E, A, 8><<<grid, ApGeom<8>::kThreads, ApGeom<8>::kSmem, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,       \
+                                                                              t.ntiles, nunits, order, cnt);             \
+  } while (0)
   const bool ad = p.addend != nullptr;
   switch (p.epi) {
     case EPI_STORE: if (ad) DM_LAUNCH(EPI_STORE, true); else DM_LAUNCH(EPI_STORE, false); break;
