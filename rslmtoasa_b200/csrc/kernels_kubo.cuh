@@ -192,3 +192,159 @@ static int kubo_launch(const double *left, size_t lstride, int M, const double *
   (*launches) += 2;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
+
+// ---- diagonal-only contraction ------------------------------------------------------------------------------------------
+// calculate_conductivity_tensor consumes only mu_nm(l,l,n,m) (conductivity.f90:276-279): 18 of the 324 entries of every
+// moment block.  When the caller does not ask for mu_nm_stochastic itself (rsrec_kubo_conductivity), the contraction is
+//   D(l; m, n) = sum_{site,k} conj(L_m(k,l)) R_n(k,l)
+// i.e. one real GEMM per orbital column l with K = 36*kk:  C_l[m][(n, re|im)] = A_l[m][(site,k')] B_l[(site,k')][(n,c)],
+// A = column l of the left blocks, B = column l of the right blocks and of their J-rotation -- 18x fewer flops than the
+// full blocks.  CTA tile: 16 left x 16 right vectors; a pipeline stage = the 9-column half (2592 B, contiguous in RI36)
+// of those 32 site blocks (83 kB), two stages; 72 (column, m-tile, n-tile) units per stage = 9 per consumer warp:
+// warp w owns all 8 units of column w of the half and one unit of column 8.  Work item = (left block, right block,
+// site chunk); partial tiles are summed in fixed order by k_kdiag_reduce.  The kernel is L2-bandwidth bound
+// (0.5 flop per byte and pair), not tensor bound.
+#define KD_MB 16
+#define KD_NR 16
+#define KD_HALF_D 324                                   // doubles in 9 columns of a site block
+#define KD_STAGE_D ((KD_MB + KD_NR) * KD_HALF_D)        // 10368 doubles = 82944 B
+#define KD_STAGES 2
+#define KD_CONSUMERS 8
+#define KD_THREADS (32 * (KD_CONSUMERS + 1))
+#define KD_SMEM_BYTES (KD_STAGES * KD_STAGE_D * 8 + 64)
+#define KD_TILE_D (NB * KD_MB * 2 * KD_NR)              // doubles per partial tile: [l][m][ncol] = 9216
+
+__global__ void __launch_bounds__(KD_THREADS, 1)
+k_kubo_diag(const double *__restrict__ left, size_t lstride, int nmb, const double *__restrict__ right, size_t rstride,
+            int nnb, int kk, int nchunk, double *__restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stages = reinterpret_cast<double *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)KD_STAGES * KD_STAGE_D * 8);
+  uint64_t *empty = full + KD_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < KD_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], KD_CONSUMERS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nitems = nmb * nnb * nchunk;
+  if (warp == KD_CONSUMERS) {  // producer: 32 lanes = the 32 vectors of the tile
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int c = item % nchunk, nb = (item / nchunk) % nnb, mb = item / (nchunk * nnb);
+      const int s0 = (int)((long long)kk * c / nchunk), s1 = (int)((long long)kk * (c + 1) / nchunk);
+      const double *src = lane < KD_MB ? left + (size_t)(mb * KD_MB + lane) * lstride
+                                       : right + (size_t)(nb * KD_NR + lane - KD_MB) * rstride;
+      for (int site = s0; site < s1; site++)
+        for (int half = 0; half < 2; half++, it++) {
+          const int slot = it % KD_STAGES;
+          mbar_wait(&empty[slot], ((it / KD_STAGES) & 1) ^ 1);
+          double *sm = stages + (size_t)slot * KD_STAGE_D;
+          if (lane == 0) mbar_expect_tx(&full[slot], KD_STAGE_D * 8);
+          __syncwarp();
+          bulk_g2s(sm + lane * KD_HALF_D, src + (size_t)site * BLKD + half * KD_HALF_D, KD_HALF_D * 8, &full[slot]);
+        }
+    }
+    return;
+  }
+  const int g = lane >> 2, q = lane & 3;
+  // unit lists: column `warp` of the half with (mt, nt) = (0..1, 0..3); plus column 8 with (mt, nt) = (warp/4, warp%4)
+  const int xmt = warp >> 2, xnt = warp & 3;
+  // A fragment: left vector mt*8+g, column lc of the half, k' = 4ks+q  -> sm[(mt*8+g)*324 + lc*36 + 4ks + q]
+  // B fragment: right vector (nt&1)*8+g; nt >= 2 is the J-rotated copy: k'<18 -> x[k'+18], k'>=18 -> -x[k'-18]
+  auto bfrag = [&](const double *col, int nt, int ks) -> double {
+    const double *x = col + (size_t)(KD_MB + (nt & 1) * 8 + g) * KD_HALF_D;
+    const int k = 4 * ks + q;
+    if (nt < 2) return x[k];
+    return k < NB ? x[k + NB] : -x[k - NB];
+  };
+  uint32_t it = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int c = item % nchunk;
+    const int s0 = (int)((long long)kk * c / nchunk), s1 = (int)((long long)kk * (c + 1) / nchunk);
+    double acc[2][8][2], xacc[2][2];  // [half][mt*4+nt][e], [half][e]
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) acc[h][u][0] = acc[h][u][1] = 0.0;
+      xacc[h][0] = xacc[h][1] = 0.0;
+    }
+    for (int site = s0; site < s1; site++) {
+#pragma unroll
+      for (int half = 0; half < 2; half++, it++) {
+        const int slot = it % KD_STAGES;
+        mbar_wait(&full[slot], (it / KD_STAGES) & 1);
+        const double *sm = stages + (size_t)slot * KD_STAGE_D;
+        const double *colw = sm + warp * COLD, *col8 = sm + 8 * COLD;
+#pragma unroll
+        for (int ks = 0; ks < 9; ks++) {
+          const double a0 = colw[(size_t)g * KD_HALF_D + 4 * ks + q], a1 = colw[(size_t)(8 + g) * KD_HALF_D + 4 * ks + q];
+          double b[4];
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) b[nt] = bfrag(colw, nt, ks);
+          const double xa = col8[(size_t)(xmt * 8 + g) * KD_HALF_D + 4 * ks + q], xb = bfrag(col8, xnt, ks);
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            dmma(acc[half][nt][0], acc[half][nt][1], a0, b[nt]);
+            dmma(acc[half][4 + nt][0], acc[half][4 + nt][1], a1, b[nt]);
+          }
+          dmma(xacc[half][0], xacc[half][1], xa, xb);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+      }
+    }
+    // partial tile: part[item][l][m][ncol], ncol < 16: Re for right vector ncol, ncol >= 16: Im for right vector ncol-16
+    double *pp = part + (size_t)item * KD_TILE_D;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int l = h * 9 + warp, m = (u >> 2) * 8 + g, ncol = (u & 3) * 8 + 2 * q;
+        *reinterpret_cast<double2 *>(pp + ((size_t)l * KD_MB + m) * (2 * KD_NR) + ncol) = make_double2(acc[h][u][0], acc[h][u][1]);
+      }
+      const int l = h * 9 + 8, m = xmt * 8 + g, ncol = xnt * 8 + 2 * q;
+      *reinterpret_cast<double2 *>(pp + ((size_t)l * KD_MB + m) * (2 * KD_NR) + ncol) = make_double2(xacc[h][0], xacc[h][1]);
+    }
+  }
+}
+
+// D[(n0 + n) * M + m][l] (complex, the layout of k_cond_diag for one start vector) = sum over the site chunks, fixed order
+__global__ void k_kdiag_reduce(const double *__restrict__ part, int nmb, int nnb, int nchunk, int M, int n0, double2 *__restrict__ D) {
+  const size_t total = (size_t)nmb * nnb * NB * KD_MB * KD_NR;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int nl = (int)(t % KD_NR), ml = (int)((t / KD_NR) % KD_MB), l = (int)((t / (KD_NR * KD_MB)) % NB);
+    const int nb = (int)((t / ((size_t)KD_NR * KD_MB * NB)) % nnb), mb = (int)(t / ((size_t)KD_NR * KD_MB * NB * nnb));
+    const int m = mb * KD_MB + ml, n = n0 + nb * KD_NR + nl;
+    if (m >= M || n >= M) continue;
+    double re = 0.0, im = 0.0;
+    for (int c = 0; c < nchunk; c++) {
+      const double *pp = part + ((size_t)((mb * nnb + nb) * nchunk + c)) * KD_TILE_D + ((size_t)l * KD_MB + ml) * (2 * KD_NR);
+      re += pp[nl];
+      im += pp[KD_NR + nl];
+    }
+    D[((size_t)n * M + m) * NB + l] = make_double2(re, im);
+  }
+}
+
+static int kdiag_configure() {
+  return cudaFuncSetAttribute(k_kubo_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM_BYTES) == cudaSuccess ? 0 : -3;
+}
+// site chunks per (left block, right block) pair so that the work items fill the SMs in whole waves
+static int kdiag_chunks(int nmb, int nnb, int kk, int sms) {
+  const int pairs = nmb * nnb;
+  int nchunk = std::max(1, (4 * sms + pairs - 1) / pairs);
+  return std::min(nchunk, std::max(1, kk / 64));
+}
+static size_t kdiag_part_doubles(int nmb, int nnb, int nchunk) { return (size_t)nmb * nnb * nchunk * KD_TILE_D; }
+// contracts the right vectors n0 .. n0 + 16*nnb - 1 (padding vectors must be zero) against all left vectors
+static int kdiag_launch(const double *left, size_t lstride, int M, const double *right, size_t rstride, int nnb, int kk, int n0,
+                        double *part, double2 *D, int sms, cudaStream_t st, long long *launches) {
+  const int nmb = (M + KD_MB - 1) / KD_MB, nchunk = kdiag_chunks(nmb, nnb, kk, sms);
+  const int nitems = nmb * nnb * nchunk;
+  k_kubo_diag<<<std::min(nitems, sms), KD_THREADS, KD_SMEM_BYTES, st>>>(left, lstride, nmb, right, rstride, nnb, kk, nchunk, part);
+  const size_t total = (size_t)nmb * nnb * NB * KD_MB * KD_NR;
+  k_kdiag_reduce<<<(unsigned)std::min<size_t>((total + 255) / 256, 4096), 256, 0, st>>>(part, nmb, nnb, nchunk, M, n0, D);
+  (*launches) += 2;
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

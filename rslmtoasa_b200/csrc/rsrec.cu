@@ -695,7 +695,7 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
   if (const char *f = getenv("RSREC_SQRT_METHOD")) h->sqrt_method = atoi(f);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  if (dmma_configure() != 0 || kubo_configure() != 0 || post_configure() != 0 || ham_configure() != 0) {
+  if (dmma_configure() != 0 || kubo_configure() != 0 || kdiag_configure() != 0 || post_configure() != 0 || ham_configure() != 0) {
     cudaStreamDestroy(h->st);
     delete h;
     return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
@@ -976,8 +976,17 @@ static int kubo_moments_impl(rsrec_handle h, int nstart, int start_kind, const i
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
   const bool gemm = h->family == 1;  // tensor pipeline: batched GEMM contraction (kernels_kubo.cuh)
-  const int M4 = gemm ? (M + KB_MB - 1) / KB_MB * KB_MB : M;
-  if (unit_batch(h, 1, M4 + 6 + (gemm ? KB_NR : 0)) < 1) return fail(RSREC_ENOMEM, "left-vector storage does not fit in device memory");
+  // only the diagonals mu(l,l,n,m) are wanted: column-wise contraction, 18x fewer flops (k_kubo_diag)
+  static const bool no_diag = getenv("RSREC_NO_KUBO_DIAG") != nullptr;
+  const bool diag_only = gemm && !mu_nm && d_diag && !no_diag;
+  const int M4 = diag_only ? (M + KD_MB - 1) / KD_MB * KD_MB : gemm ? (M + KB_MB - 1) / KB_MB * KB_MB : M;
+  // right vectors kept per contraction: 4 for the full-block GEMM; for the diagonal kernel as many 16-blocks as fit
+  int nring = gemm ? KB_NR : 0;
+  if (diag_only) {
+    const int fit = unit_batch(h, 1 << 20, 1) - (M4 + 6);
+    nring = std::max(KD_NR, std::min((M + KD_NR - 1) / KD_NR * KD_NR, fit / KD_NR * KD_NR));
+  }
+  if (unit_batch(h, 1, M4 + 6 + nring) < 1) return fail(RSREC_ENOMEM, "left-vector storage does not fit in device memory");
   h->plan.on = false;
   const int nctas = nctas_for(h, 1);
   // vecs: 0 psiref, 1 tmp(hoh), 2 v0, 3 v1, 4 right, 5 spare, 6 left[m] (batched), 7 ring of KB_NR right vectors
@@ -989,10 +998,13 @@ static int kubo_moments_impl(rsrec_handle h, int nstart, int start_kind, const i
   TRY(get_vec(h, 6, M4, &leftbuf));
   for (int m = 0; m < M; m++) left[m] = leftbuf + (size_t)m * vstride(h);
   if (gemm) {
-    TRY(get_vec(h, 7, KB_NR, &ring));
-    TRY(zero_vec(h, ring, KB_NR));
+    TRY(get_vec(h, 7, nring, &ring));
+    TRY(zero_vec(h, ring, nring));
     if (M4 > M) TRY(zero_vec(h, leftbuf + (size_t)M * vstride(h), M4 - M));  // padding rows of the last left block
-    TRY(dev_alloc(h->part, kubo_part_doubles(M4 / KB_MB, h->kk, h->sms), false));
+    if (diag_only)
+      TRY(dev_alloc(h->part, kdiag_part_doubles(M4 / KD_MB, nring / KD_NR, kdiag_chunks(M4 / KD_MB, nring / KD_NR, h->kk, h->sms)), false));
+    else
+      TRY(dev_alloc(h->part, kubo_part_doubles(M4 / KB_MB, h->kk, h->sms), false));
   } else {
     TRY(dev_alloc(h->part, part_doubles(h, M, nctas), false));
   }
@@ -1029,7 +1041,18 @@ static int kubo_moments_impl(rsrec_handle h, int nstart, int start_kind, const i
         cur = c1;
       }
       // mu_nm_stochastic(:,:,n,m,i) = sum_k left_vec(:,:,k,m)^H right_vec(:,:,k) for all m (1220-1228)
-      if (gemm) {
+      if (diag_only) {
+        // right vectors are collected nring at a time; only the diagonals mu(l,l,n,m) are contracted
+        TRY(apply_op(h, OP_VELO_A, cur, ring + (size_t)(n % nring) * vstride(h), nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas, nullptr));
+        if (n % nring == nring - 1 || n == M - 1) {
+          const int n0 = n - n % nring, filled = n - n0 + 1, nnb = (filled + KD_NR - 1) / KD_NR;
+          if (filled < nnb * KD_NR)  // stale vectors of the previous batch in the last 16-block: zero them
+            TRY(zero_vec(h, ring + (size_t)filled * vstride(h), nnb * KD_NR - filled));
+          if (kdiag_launch(leftbuf, vstride(h), M, ring, vstride(h), nnb, h->kk, n0, h->part.p,
+                           (double2 *)d_diag + (size_t)s * M * M * NB, h->sms, h->st, &h->launches) != 0)
+            return fail(RSREC_ECUDA, std::string("k_kubo_diag launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        }
+      } else if (gemm) {
         // right vectors are collected KB_NR at a time, then contracted against every left vector in one GEMM
         TRY(apply_op(h, OP_VELO_A, cur, ring + (size_t)(n % KB_NR) * vstride(h), nullptr, tmp, EPI_STORE, 1.0, 0.0, 1, nctas, nullptr));
         if (n % KB_NR == KB_NR - 1 || n == M - 1) {
@@ -1042,7 +1065,7 @@ static int kubo_moments_impl(rsrec_handle h, int nstart, int start_kind, const i
         TRY(launch_reduce(h, M, nctas, 0, h->mu.p + (size_t)n * BLKD, nullptr, (size_t)M * BLKD, nullptr, nullptr));
       }
     }
-    if (d_diag) {
+    if (d_diag && !diag_only) {
       k_cond_diag<<<grid_for((size_t)M * M * NB, 256, h->sms * 16), 256, 0, h->st>>>((const double2 *)h->mu.p, M, (size_t)M * M,
                                                                                   (double2 *)d_diag + (size_t)s * M * M * NB);
       h->launches++;
