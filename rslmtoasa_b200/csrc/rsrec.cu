@@ -79,6 +79,7 @@ struct rsrec_handle_s {
   int units_cap = 0;
   // active-region plan (the reference's izero/irlist): tiles reachable per step from the units' start sites
   std::vector<int32_t> radj_off, radj;  // reverse adjacency of the neighbour table (who gathers from site a)
+  std::vector<int32_t> nbr_host;        // [ncols][kk] 0-based neighbour table as uploaded
   struct {
     bool on = false;
     int level = 0, maxlevel = 0, nunits = 0;
@@ -172,18 +173,10 @@ static int ensure_ready(H *h) {
   CUDA_TRY(cudaMemcpyAsync(h->d_nbr, nbr.data(), nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
   CUDA_TRY(cudaMemcpyAsync(h->d_cls, cls.data(), cls.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
   h->h2d_bytes += (long long)((nbr.size() + cls.size()) * sizeof(int32_t));
-  {  // reverse adjacency (CSR): radj[a] = sites i that gather from a (i != a), for the breadth-first reach levels
-    h->radj_off.assign(kk + 1, 0);
-    for (int j = 1; j < ng; j++)
-      for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj_off[a + 1]++; }
-    for (int a = 0; a < kk; a++) h->radj_off[a + 1] += h->radj_off[a];
-    h->radj.resize(h->radj_off[kk]);
-    std::vector<int32_t> fill(h->radj_off.begin(), h->radj_off.end() - 1);
-    for (int j = 1; j < ng; j++)
-      for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj[fill[a]++] = i; }
-  }
-
-  if (dmma_build_tiles(h->tiles, nbr, cls, kk, ng, ncls, h->pos.empty() ? nullptr : h->pos.data()) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
+  h->nbr_host.swap(nbr);  // kept for the active-region planner (reverse adjacency is built on first use)
+  h->radj_off.clear(); h->radj.clear();
+  const std::vector<int32_t> &nbr_c = h->nbr_host;
+  if (dmma_build_tiles(h->tiles, nbr_c, cls, kk, ng, ncls, h->pos.empty() ? nullptr : h->pos.data()) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
   h->h2d_bytes += (long long)h->tiles.ntiles * (DM_S + 1 + (long long)ng * DM_S) * 4;
   CUDA_TRY(cudaDeviceSynchronize());  // the tile tables went through the legacy stream: make sure they have landed
   h->dirty = false;
@@ -296,6 +289,18 @@ static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *si
   h->plan.on = false;
   if (h->family != 1 || (size_t)nunits * h->kk > (size_t)64 << 20) return RSREC_OK;
   const int kk = h->kk, nt = h->tiles.ntiles;
+  if (h->radj_off.empty()) {  // reverse adjacency (CSR): radj[a] = sites i that gather from a (i != a), built on first use
+    const int ng = h->ncols;
+    const std::vector<int32_t> &nbr = h->nbr_host;
+    h->radj_off.assign(kk + 1, 0);
+    for (int j = 1; j < ng; j++)
+      for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj_off[a + 1]++; }
+    for (int a = 0; a < kk; a++) h->radj_off[a + 1] += h->radj_off[a];
+    h->radj.resize(h->radj_off[kk]);
+    std::vector<int32_t> fill(h->radj_off.begin(), h->radj_off.end() - 1);
+    for (int j = 1; j < ng; j++)
+      for (int i = 0; i < kk; i++) { const int a = nbr[(size_t)j * kk + i]; if (a < kk) h->radj[fill[a]++] = i; }
+  }
   std::vector<int32_t> order((size_t)nunits * nt), level(kk), tl(nt), frontier, next;
   std::vector<std::vector<int32_t>> cum(nunits), bcum(nunits);
   const int nb = (kk + DM_S - 1) / DM_S;
