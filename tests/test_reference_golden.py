@@ -1,0 +1,43 @@
+"""The oracle against the REFERENCE'S OWN GOLDEN VALUES: `tests/scf/references/Example_bulk_bccFe_*/ref.json` of
+rslmtoasa/rslmtoasa (totaldos.out rows 500 / 1000 / 1500, written by the Fortran program with 5 decimals).
+
+oracle/ref_bccfe.py restates the reference's pipeline for that regression case from the input files up (cluster, neighbour
+table, screened structure constants, potential parameters, L.S, Hamiltonian blocks) and the C oracle does the recursion
+(hop_b / hop_b_hoh / crecal_b or the Chebyshev moments), zsqr, terminator + block continued fraction or chebyshev_green.
+All twelve fixtures of the case are reproduced to every printed digit -- this is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import ref_bccfe as R
+
+NAMES = sorted(n for n in R.GOLDEN if "nsp4" not in n)     # nsp = 4 runs the same recursion as nsp = 2 (same fixtures)
+
+
+def _check(ene, dos, g, tol=6e-6):
+    for row, (e_ref, d_ref) in g["rows"].items():
+        assert abs((ene[row - 1] - g["fermi"]) - e_ref) < 6e-6            # the mesh (energy%e_mesh) hits the same points
+        assert abs(dos[row - 1] - d_ref) < tol, (row, dos[row - 1], d_ref)
+
+
+def test_cluster_and_structure_constants_of_the_case(oracle_mod):
+    lat, ham, ene, g = R.case_inputs(oracle_mod, "Example_bulk_bccFe_nsp2_block")
+    assert lat.kk == 5984 and lat.nn.shape == (5984, 16) and (lat.nn[0, 1:15] > 0).all()      # kk = 5984
+    assert len(ene) == 2510
+    h_on = ham.ee[:, :, 0, 0]
+    assert np.abs(h_on - h_on.conj().T).max() < 1e-14
+    # cubic symmetry of the on-site block: p orbitals degenerate, d split into t2g / eg
+    d = np.real(np.diag(h_on))[:9]
+    assert np.ptp(d[1:4]) < 1e-12 and abs(d[4] - d[8]) < 1e-12 and abs(d[5] - d[7]) < 1e-12
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_reference_golden(oracle_mod, name):
+    ene, dos = R.oracle_total_dos(oracle_mod, name)
+    g = R.case_inputs(oracle_mod, name)[3]
+    _check(ene, dos, g)
+
+
+def test_nsp4_fixtures_equal_nsp2():
+    for n, g in R.GOLDEN.items():
+        if "nsp4" in n:
+            assert g["rows"] == R.GOLDEN[n.replace("nsp4", "nsp2")]["rows"]
