@@ -7,8 +7,9 @@
     build_bulkham / build_locham   hamiltonian.f90:1553-1616 / 1618-1667 (spin-block composition, eeo = ee*obarm)
     build_obarm / build_enim   hamiltonian.f90:1481-1508 / 1510-1551
 
-PARITY UNPINNED by reference fixtures (the reference dumps ee to fort.131/132 only when run).  Pinned by
-`pauli_block` below -- an independent statement of the same physics, block = P_i(l) S(l,l') P_j(l') with
+PARITY PINNED by the reference's bccFe golden fixtures: oracle/ref_bccfe.py feeds the reference's Fe potential and
+screened structure constants through build_blocks (nsp 1/2/4, hoh on/off) and the resulting DOS matches every stored
+totaldos.out value (tests/test_reference_golden.py).  Pinned further by `pauli_block` below -- an independent statement of the same physics, block = P_i(l) S(l,l') P_j(l') with
 P = w0 + w1 (m.sigma) as 2x2 spin matrices -- and by invariants in tests/test_oracle_ham.py.
 
 Inputs (all per CLASS c = atom type 1..ntype followed by local site 1..nmax, like the device library):

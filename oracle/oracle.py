@@ -1,7 +1,8 @@
 """ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE -- never imported by the product package).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
-PARITY UNPINNED by reference fixtures (see rsrec_oracle.h); pinned by oracle/dense_check.py.
+PARITY PINNED by the reference's bccFe golden fixtures (oracle/ref_bccfe.py, tests/test_reference_golden.py) and by
+oracle/dense_check*.py for what those do not reach -- see rsrec_oracle.h.
 """
 from __future__ import annotations
 

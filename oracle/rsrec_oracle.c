@@ -1,7 +1,8 @@
 /*
  * rsrec_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).  See rsrec_oracle.h.
  *
- * PARITY UNPINNED by reference fixtures (none exist at this boundary); pinned by oracle/dense_check.py.
+ * PARITY PINNED by the reference's bccFe golden fixtures (recur_b, hop_b(_hoh), chebyshev_recur, zsqr; see
+ * rsrec_oracle.h) and, for the routines those do not reach, by oracle/dense_check.py.
  *
  * Restates, with the reference's own pass structure, masks and per-site 18x18x18 complex products:
  *   hop_b            recursion.f90:1560-1648        hop_b_hoh          recursion.f90:1411-1552

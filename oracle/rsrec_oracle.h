@@ -5,10 +5,14 @@
  * (`source/recursion.f90`).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library; the product (librsrec.so) never does.
  *
- * PARITY UNPINNED at the a_n/b_n/mu_n boundary: the reference stores no golden coefficient or moment
- * vectors (only end-to-end etot/DOS values that need the whole Fortran program) and cannot be compiled in
- * this image (no Fortran compiler).  The oracle is pinned instead by an independent dense numpy restatement
- * (oracle/dense_check.py) and by mathematical invariants (tests/test_oracle.py).
+ * PARITY PINNED by the reference's own golden fixtures for the SCF chain: oracle/ref_bccfe.py rebuilds the reference's
+ * bccFe regression case (tests/scf/references/Example_bulk_bccFe_<case>/ref.json, 12 cases: nsp 1/2/4, hoh on/off, block
+ * and Chebyshev recursion, lld 16/21, two energy windows) from its input files and reproduces every stored
+ * totaldos.out value to all printed digits through this oracle (tests/test_reference_golden.py) and through the
+ * CUDA library (tests/test_gpu_reference_golden.py).  Routines no reference fixture reaches (scalar recursion,
+ * recur_b_ij, Kubo-Bastin moments, site-indexed `hall` region, orbital moments) are pinned by the independent dense
+ * numpy restatement (oracle/dense_check*.py) and by invariants (tests/test_oracle*.py).  The reference itself cannot
+ * be compiled here (no Fortran compiler), so there is no oracle/_ref.
  *
  * All arrays are Fortran column-major exactly as the reference holds them; site / type indices are 1-based.
  */

@@ -4,7 +4,9 @@
  *   lattice%nncal              lattice.f90:3035-3123   (O(kk^2) pair loop, cut-off test of `mapa`, 2956-2973)
  *   lattice%f_wrap_coord_diff  lattice.f90:2975-3018   (minimum image over the 27 supercell shifts)
  *   lattice%remd               lattice.f90:2823-2907   (slots reordered to the representative atom's vector set)
- * PARITY UNPINNED by reference fixtures; pinned by tests/test_oracle_lattice.py (numpy restatement + invariants).
+ * PARITY: the table it builds for the reference's bccFe cluster feeds the golden-value reproduction of
+ * tests/test_reference_golden.py (see rsrec_oracle.h); otherwise pinned by tests/test_oracle_lattice.py (numpy
+ * restatement + invariants).
  * Compiled with -ffp-contract=off (distance tests are branch decisions).
  */
 #include "rsrec_oracle.h"

@@ -2,8 +2,10 @@
  * rsrec_oracle_post.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE) for the consumers either side of the
  * recursion hot path.  See rsrec_oracle.h.
  *
- * PARITY UNPINNED by reference fixtures (the reference pins only end-to-end etot/DOS files and cannot be compiled
- * here); pinned by the independent numpy restatement in oracle/dense_check.py and by invariants in tests/.
+ * PARITY PINNED by the reference's bccFe golden fixtures for bpopt/emami/get_terminf, bgreen/block_green and
+ * chebyshev_green/jackson_kernel (the totaldos.out values of tests/scf/references are -Im Tr g0/pi of exactly these;
+ * see rsrec_oracle.h and tests/test_reference_golden.py); the scalar density/sgreen and the Kubo-Bastin contraction,
+ * which no reference fixture reaches, are pinned by the numpy restatement in oracle/dense_check_post.py.
  *
  * Restates, statement for statement:
  *   emami               recursion.f90:3589-3706      bpopt               recursion.f90:3540-3581

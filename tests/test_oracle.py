@@ -1,6 +1,7 @@
 """CPU tests of the oracle: pinned against the independent dense restatement and against invariants.
 
-The reference stores no golden a_n/b_n/mu_n vectors ("parity unpinned"), so the oracle is pinned by
+The reference stores no golden a_n/b_n/mu_n vectors; its end-to-end golden DOS values pin the oracle in
+tests/test_reference_golden.py.  Here, at the coefficient boundary, the oracle is pinned by
 (1) oracle/dense_check.py -- dense-matrix algebra with numpy/LAPACK, no masks or neighbour loops -- and
 (2) mathematical invariants of the recursions, and (3) committed golden vectors generated from the oracle
 (tests/golden, guards against regressions of the oracle itself).

@@ -41,3 +41,21 @@ def test_nsp4_fixtures_equal_nsp2():
     for n, g in R.GOLDEN.items():
         if "nsp4" in n:
             assert g["rows"] == R.GOLDEN[n.replace("nsp4", "nsp2")]["rows"]
+
+
+def test_embedded_golden_table_is_the_reference_fixture_file():
+    """oracle/ref_bccfe.py:GOLDEN == tests/golden/reference_bccfe_ref.json (copied from the reference tree by
+    tests/golden/make_reference_golden.py), including the settings of every case"""
+    import json
+    import os
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_bccfe_ref.json")))["cases"]
+    assert set(ref) == set(R.GOLDEN)
+    for name, g in R.GOLDEN.items():
+        nml = ref[name]["namelists"]
+        assert nml["control"] == {"nsp": g["nsp"], "recur": g["recur"], "lld": g["lld"]}
+        assert nml["hamiltonian"]["hoh"] == g["hoh"] and nml["self"]["nstep"] == 1
+        assert ("energy" in nml) == ("window" in g)
+        if "window" in g:
+            assert (nml["energy"]["energy_min"], nml["energy"]["energy_max"]) == g["window"]
+        for row, (e, d) in g["rows"].items():
+            assert ref[name]["totaldos.out"][str(row)] == {"1": e, "2": d}
