@@ -28,6 +28,9 @@ module rsrec_c_mod
    public :: rsrec_bpopt, rsrec_get_terminf, rsrec_bgreen, rsrec_block_green, rsrec_chebyshev_green, rsrec_density
    public :: rsrec_sgreen, rsrec_conductivity_integrand, rsrec_recur_b_green, rsrec_cheb_recur_green
    public :: rsrec_kubo_conductivity
+   ! consumers of g0 in the SCF loop (bands.f90)
+   public :: rsrec_bands_set_g0, rsrec_bands_get_g0, rsrec_bands_g0_shape, rsrec_bands_dos, rsrec_bands_fermi
+   public :: rsrec_bands_magnetic_moments, rsrec_bands_moments, rsrec_bands_band_energy
 
    interface
       function rsrec_last_error() bind(C, name='rsrec_last_error') result(msg)
@@ -367,6 +370,88 @@ module rsrec_c_mod
          complex(c_double_complex), intent(out) :: integrand(18, *), integrand_at(18, nv, *)
          integer(c_int) :: rc
       end function
+      ! ---- type bands (bands.f90): g0 stays on the device after every Green-function call ----
+      function rsrec_bands_set_g0(h, g0, nunits, nv) bind(C, name='rsrec_bands_set_g0') result(rc)
+         import :: c_ptr, c_int, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nunits, nv
+         complex(c_double_complex), intent(in) :: g0(18, 18, nv, *)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_bands_get_g0(h, g0) bind(C, name='rsrec_bands_get_g0') result(rc)
+         import :: c_ptr, c_int, c_double_complex
+         type(c_ptr), value :: h
+         complex(c_double_complex), intent(out) :: g0(18, 18, *)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_bands_g0_shape(h, nunits, nv) bind(C, name='rsrec_bands_g0_shape') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int), intent(out) :: nunits, nv
+         integer(c_int) :: rc
+      end function
+
+      ! DOS loops of calculate_fermi (bands.f90:260-273); dosia, dosial may be c_null_ptr
+      function rsrec_bands_dos(h, dtot, dosia, dosial) bind(C, name='rsrec_bands_dos') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h, dosia, dosial
+         real(c_double), intent(out) :: dtot(*)
+         integer(c_int) :: rc
+      end function
+
+      ! Fermi level of calculate_fermi (bands.f90:322-342 with `fermi`, 366-402)
+      function rsrec_bands_fermi(h, dtot, nv, edel, energy_min, qqv, fix_fermi, fermi, nv1, e1, ifail) &
+         bind(C, name='rsrec_bands_fermi') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(in) :: dtot(*)
+         integer(c_int), value :: nv, fix_fermi
+         real(c_double), value :: edel, energy_min, qqv
+         real(c_double), intent(inout) :: fermi
+         integer(c_int), intent(inout) :: nv1
+         real(c_double), intent(out) :: e1
+         integer(c_int), intent(out) :: ifail
+         integer(c_int) :: rc
+      end function
+
+      ! calculate_magnetic_moments (bands.f90:791-855): mom0 = mx,my,mz; mom1 = potential%mom1, (3,nunits)
+      function rsrec_bands_magnetic_moments(h, ene, edel, fermi, nv1, e1, mom0, mom1) &
+         bind(C, name='rsrec_bands_magnetic_moments') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(in) :: ene(*)
+         real(c_double), value :: edel, fermi, e1
+         integer(c_int), value :: nv1
+         real(c_double), intent(out) :: mom0(3, *), mom1(3, *)
+         integer(c_int) :: rc
+      end function
+
+      ! calculate_moments + calculate_orbital_moments (bands.f90:409-524, 1075-1156): occ(3,6,nunits) = sgef,pmef,smef
+      function rsrec_bands_moments(h, channels_ldos, ene, edel, fermi, nv1, e1, mom, occ, lmom) &
+         bind(C, name='rsrec_bands_moments') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         integer(c_int), value :: channels_ldos, nv1
+         real(c_double), intent(in) :: ene(*), mom(3, *)
+         real(c_double), value :: edel, fermi, e1
+         real(c_double), intent(out) :: occ(3, 6, *), lmom(3, *)
+         integer(c_int) :: rc
+      end function
+
+      ! calculate_band_energy (bands.f90:354-359)
+      function rsrec_bands_band_energy(h, dtot, nv, ene, edel, fermi, nv1, e1, eband) &
+         bind(C, name='rsrec_bands_band_energy') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(in) :: dtot(*), ene(*)
+         integer(c_int), value :: nv, nv1
+         real(c_double), value :: edel, fermi, e1
+         real(c_double), intent(out) :: eband
+         integer(c_int) :: rc
+      end function
+
    end interface
 
 contains

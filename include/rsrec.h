@@ -194,11 +194,12 @@ int rsrec_conductivity_integrand(rsrec_handle h, const rsrec_cplx *mu_nm, int M,
 /* ---- fused entry points: a recursion and its consumer with the coefficients staying on the device ---- */
 
 /* run_recursion + run_dos of the block path (self.f90:799-856): recur_b -> zsqr -> get_terminf -> bgreen(eta=0).
- * a_b, b2_b (18,18,lld,nunits), b2_b = B^2 as recur_b leaves it (either may be NULL); g0 (18,18,nv,nunits). */
+ * a_b, b2_b (18,18,lld,nunits), b2_b = B^2 as recur_b leaves it (either may be NULL); g0 (18,18,nv,nunits), may be
+ * NULL: g0 then only stays on the device for the rsrec_bands_* consumers below. */
 int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, const double *ene, int nv,
                         int sym_term, rsrec_cplx *a_b, rsrec_cplx *b2_b, rsrec_cplx *g0);
 
-/* chebyshev_recur (recursion.f90:3057-3130) + chebyshev_green (green.f90:1030-1108); mu_n, mu_ng may be NULL. */
+/* chebyshev_recur (recursion.f90:3057-3130) + chebyshev_green (green.f90:1030-1108); mu_n, mu_ng, g0 may be NULL. */
 int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, double energy_min,
                            double energy_max, const double *ene, int nv, rsrec_cplx *mu_n, rsrec_cplx *mu_ng,
                            rsrec_cplx *g0);
@@ -209,6 +210,42 @@ int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, in
 int rsrec_kubo_conductivity(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites,
                             const double *phases, int M, double energy_min, double energy_max, const double *ene,
                             int nv, rsrec_cplx *mu_nm, rsrec_cplx *integrand, rsrec_cplx *integrand_at);
+
+/* ---- `type bands` (bands.f90): what the SCF loop takes from g0 -- total DOS, Fermi level, band moments, charges ----
+ * Every Green-function entry point above (block_green, chebyshev_green, sgreen and the fused ones) leaves its
+ * g0 (18,18,nv,nunits) on the device; these calls consume that copy, so a fused call with g0 = NULL followed by them
+ * moves only O(nv) + O(nunits) numbers to the host.  rsrec_bands_set_g0 uploads a g0 computed elsewhere. */
+int rsrec_bands_set_g0(rsrec_handle h, const rsrec_cplx *g0, int nunits, int nv);
+int rsrec_bands_get_g0(rsrec_handle h, rsrec_cplx *g0);
+int rsrec_bands_g0_shape(rsrec_handle h, int *nunits, int *nv);
+
+/* DOS part of calculate_fermi (bands.f90:260-273): dtot (nv) summed over this handle's units in the reference's
+ * order (bit-exact; the caller all-reduces it across ranks like bands.f90:276), dosia (nv,nunits) and dosial
+ * (18,nv,nunits) (either may be NULL). */
+int rsrec_bands_dos(rsrec_handle h, double *dtot, double *dosia, double *dosial);
+
+/* Fermi level of calculate_fermi (bands.f90:322-342) from the all-reduced dtot (nv = channels_ldos + 10):
+ * fix_fermi == 0: the two `fermi` scans (366-402), fermi in/out = en%fermi, nv1 in/out = en%ik1 / bands%nv1, e1 out =
+ * bands%e1, ifail (may be NULL) = 1 when the valence charge qqv is not reached; fix_fermi != 0: nv1 and e1 of the
+ * fixed level (338-341), dtot unused. */
+int rsrec_bands_fermi(rsrec_handle h, const double *dtot, int nv, double edel, double energy_min, double qqv,
+                      int fix_fermi, double *fermi, int *nv1, double *e1, int *ifail);
+
+/* calculate_magnetic_moments (bands.f90:791-855) with calculate_projected_dos (1158-1181): mom0 (3,nunits) = mx,my,mz
+ * and mom1 (3,nunits) = potential%mom1, the Simpson integrals (simpson_m, math.f90:1579-1598) of order 0 and 1 of
+ * dx,dy,dz up to the Fermi level; ene (nv) = en%ene.  The normalisation to mtot/mom is the caller's (scalar). */
+int rsrec_bands_magnetic_moments(rsrec_handle h, const double *ene, double edel, double fermi, int nv1, double e1,
+                                 double *mom0, double *mom1);
+
+/* calculate_moments (bands.f90:409-524) with calculate_orbital_moments (1075-1156): mom (3,nunits) = potential%mom;
+ * occ (3,6,nunits) = sgef, pmef, smef of channel i = l + 3(isp-1) (from which the caller forms ql and gravity_center,
+ * 492-495); lmom (3,nunits) = potential%lmom. */
+int rsrec_bands_moments(rsrec_handle h, int channels_ldos, const double *ene, double edel, double fermi, int nv1,
+                        double e1, const double *mom, double *occ, double *lmom);
+
+/* calculate_band_energy (bands.f90:354-359): eband = simpson_m(order 1) of the all-reduced dtot. */
+int rsrec_bands_band_energy(rsrec_handle h, const double *dtot, int nv, const double *ene, double edel, double fermi,
+                            int nv1, double e1, double *eband);
 
 /* ---- device-resident stepping (what bench.py times as `value`; the calls above are the `e2e` path) ----
  * begin: upload start vectors, compute mu(1), mu(2) on the device.  run_steps: enqueue n chebyshev_recur_ll steps on

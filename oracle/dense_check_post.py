@@ -141,3 +141,42 @@ def conductivity_integrand(mu_nm, ene, emin, emax):
     mud = mu_nm[d, d]                                                  # (18, M, M, nloop)
     at = factor * np.einsum("enm,lnmt->let", g, mud)
     return at.sum(-1), at
+
+
+# ---- `type bands`: independent numpy statement (vectorised; Pauli-matrix form instead of the element-wise loops) ------
+def bands_projections(g0, mom):
+    """g0 (18,18,nv,nu), mom (3,nu) -> dict of energy-resolved quantities:
+    dos (nv,nu), spin (3,nv,nu) = -Im Tr(sigma_d g0)/pi, dspd (6,nv,nu), lorb (3,nv,nu) = Im Tr(L_d g0)"""
+    from .oracle import l_spherical
+    g = np.asarray(g0).reshape(9, 2, 9, 2, g0.shape[2], g0.shape[3], order="F")   # axes (o, s, o', s', e, u): row = o + 9 s
+    sig = np.array([[[0, 1], [1, 0]], [[0, -1j], [1j, 0]], [[1, 0], [0, -1]]], complex)
+    one = np.eye(2)
+    # orbital-diagonal 2x2 spin blocks G_o[s, s']
+    go = np.einsum("osotev->ostev", g)
+    dos = -np.imag(np.einsum("ossev->ev", go)) / np.pi
+    # Tr_spin(sigma_d G): the reference's expressions are aimag of the combinations below (no conjugations)
+    spin = np.stack([-np.imag(np.einsum("st,otsev->ev", sig[d], go)) / np.pi for d in range(3)])
+    lsl = [slice(0, 1), slice(1, 4), slice(4, 9)]
+    nv, nu = g0.shape[2], g0.shape[3]
+    dspd = np.zeros((6, nv, nu))
+    for isp in range(2):
+        sgn = 1.0 - 2.0 * isp
+        for l in range(3):
+            G = go[lsl[l]]
+            n = np.imag(np.einsum("ossev->ev", G))
+            s = [np.imag(np.einsum("st,otsev->ev", sig[d], G)) for d in range(3)]
+            dspd[l + 3 * isp] = (-n - sgn * (mom[0][None, :] * s[0] + mom[1][None, :] * s[1] + mom[2][None, :] * s[2])) * 0.5 / np.pi
+    L = l_spherical()
+    lorb = np.stack([np.imag(np.einsum("ik,ksisev->ev", L[:, :, d], g)) for d in range(3)])
+    return {"dos": dos, "spin": spin, "dspd": dspd, "lorb": lorb}
+
+
+def simpson_to_fermi(y, ene, edel, fermi, nv1, e1, nexp):
+    """simpson_m in closed vector form: composite Simpson over points 1..nv1 plus the partial last panel"""
+    f = y * ene ** nexp
+    w = np.zeros(nv1)
+    w[0:nv1 - 2:2] += 1.0; w[1:nv1 - 1:2] += 4.0; w[2:nv1:2] += 1.0
+    val = edel / 3.0 * np.tensordot(w, f[:nv1], axes=(0, 0))
+    if e1 != fermi:
+        val = val + (fermi - e1) * (f[nv1 - 1] + 4.0 * f[nv1] + f[nv1 + 1]) / 6.0
+    return val

@@ -364,3 +364,85 @@ def build_nn(crd, no, iu, ct, pbc=None, nrep=(1, 1, 1), a=None, alat=1.0, ncols=
             cols = nm.value + 1
             continue
         return nn, nm.value, rc
+
+
+# ---- `type bands` (bands.f90; rsrec_oracle_bands.c) -------------------------------------------------------------------
+def _bands():
+    L = lib()
+    if not getattr(L, "_bands_ready", False):
+        d, i = C.c_double, C.c_int
+        L.orc_bands_dos.argtypes = [c_vp, i, i, c_vp, c_vp, c_vp]
+        L.orc_bands_fermi.argtypes = [c_vp, i, d, d, d, i, C.POINTER(d), C.POINTER(i), C.POINTER(d), C.POINTER(i)]
+        L.orc_simpson_m.argtypes = [d, d, i, c_vp, d, i, c_vp]
+        L.orc_simpson_m.restype = d
+        L.orc_bands_magnetic_moments.argtypes = [c_vp, i, i, c_vp, d, d, i, d, c_vp, c_vp]
+        L.orc_bands_moments.argtypes = [c_vp, i, i, i, c_vp, c_vp, c_vp, d, d, i, d, c_vp, c_vp]
+        L._bands_ready = True
+    return L
+
+
+def e_mesh_full(energy_min, energy_max, channels_ldos, fermi):
+    """energy%e_mesh (energy.f90:175-208) -> dict(ene, edel, nv1, channels_ldos)"""
+    if channels_ldos % 2 == 0:
+        nv1 = channels_ldos + 1
+    else:
+        nv1 = channels_ldos
+        channels_ldos -= 1
+    edel = (energy_max - energy_min) / channels_ldos
+    r = (fermi - energy_min) / edel
+    edel = (fermi - energy_min) / (np.sign(r) * np.floor(abs(r) + 0.5))
+    return {"ene": energy_min + edel * np.arange(channels_ldos + 10, dtype=np.float64), "edel": float(edel), "nv1": nv1,
+            "channels_ldos": channels_ldos}
+
+
+def l_spherical():
+    """hcpx(L_x), hcpx(L_y), hcpx(L_z) as calculate_orbital_moments forms them (bands.f90:1094-1101) -> (9,9,3)"""
+    from . import ham_oracle as HO
+    from .ref_bccfe import _L_matrices
+    return np.asfortranarray(np.stack([HO.hcpx_cart2sph(m) for m in _L_matrices()], axis=2))
+
+
+def bands_dos(g0):
+    L = _bands()
+    g0 = _f(g0, np.complex128)
+    nv, nu = g0.shape[2], g0.shape[3]
+    dtot = np.zeros(nv); dosia = np.zeros((nv, nu), order="F"); dosial = np.zeros((18, nv, nu), order="F")
+    L.orc_bands_dos(_p(g0), nv, nu, _p(dtot), _p(dosia), _p(dosial))
+    return dtot, dosia, dosial
+
+
+def bands_fermi(dtot, edel, energy_min, qqv, fermi, ik1, fix_fermi=False):
+    """-> fermi, nv1, e1, ifail"""
+    L = _bands()
+    dtot = np.ascontiguousarray(dtot, dtype=np.float64)
+    f, n, e, fl = C.c_double(fermi), C.c_int(ik1), C.c_double(0.0), C.c_int(0)
+    L.orc_bands_fermi(_p(dtot), len(dtot), float(edel), float(energy_min), float(qqv), int(fix_fermi), C.byref(f), C.byref(n),
+                      C.byref(e), C.byref(fl))
+    return f.value, n.value, e.value, fl.value
+
+
+def simpson_m(h, ef, npts, y, ea, nexp, ene):
+    L = _bands()
+    y = np.ascontiguousarray(y, dtype=np.float64); ene = np.ascontiguousarray(ene, dtype=np.float64)
+    return L.orc_simpson_m(float(h), float(ef), int(npts), _p(y), float(ea), int(nexp), _p(ene))
+
+
+def bands_magnetic_moments(g0, ene, edel, fermi, nv1, e1):
+    L = _bands()
+    g0 = _f(g0, np.complex128); ene = np.ascontiguousarray(ene, dtype=np.float64)
+    nv, nu = g0.shape[2], g0.shape[3]
+    m0 = np.zeros((3, nu), order="F"); m1 = np.zeros((3, nu), order="F")
+    L.orc_bands_magnetic_moments(_p(g0), nv, nu, _p(ene), float(edel), float(fermi), int(nv1), float(e1), _p(m0), _p(m1))
+    return m0, m1
+
+
+def bands_moments(g0, channels_ldos, mom, ene, edel, fermi, nv1, e1):
+    """-> occ (3,6,nunits) = sgef, pmef, smef; lmom (3,nunits)"""
+    L = _bands()
+    g0 = _f(g0, np.complex128); ene = np.ascontiguousarray(ene, dtype=np.float64)
+    nv, nu = g0.shape[2], g0.shape[3]
+    mom = _f(mom, np.float64); lsph = l_spherical()
+    occ = np.zeros((3, 6, nu), order="F"); lmom = np.zeros((3, nu), order="F")
+    L.orc_bands_moments(_p(g0), nv, int(channels_ldos), nu, _p(mom), _p(lsph), _p(ene), float(edel), float(fermi), int(nv1),
+                        float(e1), _p(occ), _p(lmom))
+    return occ, lmom

@@ -295,4 +295,6 @@ def oracle_total_dos(oracle_mod, name):
         a, b = oracle_mod.cheb_scale(g["energy_min"], g["energy_max"])
         mu, _ = orc.cheb_moments(lat.irec, g["lld"], a, b)
         _, g0 = oracle_mod.chebyshev_green(mu, ene, g["energy_min"], g["energy_max"])
-    return ene, total_dos(g0)
+    dtot = oracle_mod.bands_dos(g0)[0]                  # calculate_fermi's DOS loop (rsrec_oracle_bands.c) writes totaldos.out
+    assert np.allclose(dtot, total_dos(g0), rtol=0, atol=1e-12)
+    return ene, dtot

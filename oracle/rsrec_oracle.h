@@ -110,6 +110,17 @@ void orc_conductivity_integrand(const orc_cplx *mu_nm, int M, int nloop, const d
 int orc_build_nn(int kk, const double *crd, const int32_t *no, int ntot, const int32_t *iu, double ct, int use_pbc,
                  const int *b, const int *nrep, const double *a, double alat, int ncols, int32_t *nn, int *nm_out);
 
+/* ---- `type bands` (bands.f90), rsrec_oracle_bands.c: g0 (18,18,nv,nunits) -> DOS, Fermi level, band moments ---- */
+void orc_bands_dos(const orc_cplx *g0, int nv, int nunits, double *dtot, double *dosia, double *dosial);
+void orc_fermi(double *ef, double h, int *ik1, double ainf, int npts, const double *y, int *ifail, double qqv, double *e1);
+void orc_bands_fermi(const double *dtot, int nv, double edel, double energy_min, double qqv, int fix_fermi, double *fermi,
+                     int *nv1, double *e1, int *ifail);
+double orc_simpson_m(double h, double ef, int npts, const double *y, double ea, int nexp, const double *ene);
+void orc_bands_magnetic_moments(const orc_cplx *g0, int nv, int nunits, const double *ene, double edel, double fermi, int nv1,
+                                double e1, double *mom0, double *mom1);
+void orc_bands_moments(const orc_cplx *g0, int nv, int channels_ldos, int nunits, const double *mom, const orc_cplx *lsph,
+                       const double *ene, double edel, double fermi, int nv1, double e1, double *occ, double *lmom);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,8 @@ SYMBOLS = [
     "rsrec_kubo_conductivity", "rsrec_create_ll_map", "rsrec_orbital_moments",
     "rsrec_build_nn", "rsrec_build_hamiltonian", "rsrec_rotate_to_local_axis", "rsrec_rotate_from_local_axis",
     "rsrec_lanczos_block_local_axis", "rsrec_set_positions",
+    "rsrec_bands_set_g0", "rsrec_bands_get_g0", "rsrec_bands_g0_shape", "rsrec_bands_dos", "rsrec_bands_fermi",
+    "rsrec_bands_magnetic_moments", "rsrec_bands_moments", "rsrec_bands_band_energy",
 ]
 
 
@@ -89,6 +91,14 @@ def load():
     L.rsrec_rotate_to_local_axis.argtypes = [vp, vp]
     L.rsrec_rotate_from_local_axis.argtypes = [vp]
     L.rsrec_lanczos_block_local_axis.argtypes = [vp, i, vp, vp, i, vp, vp]
+    L.rsrec_bands_set_g0.argtypes = [vp, vp, i, i]
+    L.rsrec_bands_get_g0.argtypes = [vp, vp]
+    L.rsrec_bands_g0_shape.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    L.rsrec_bands_dos.argtypes = [vp, vp, vp, vp]
+    L.rsrec_bands_fermi.argtypes = [vp, vp, i, d, d, d, i, C.POINTER(d), C.POINTER(i), C.POINTER(d), C.POINTER(i)]
+    L.rsrec_bands_magnetic_moments.argtypes = [vp, vp, d, d, i, d, vp, vp]
+    L.rsrec_bands_moments.argtypes = [vp, i, vp, d, d, i, d, vp, vp, vp]
+    L.rsrec_bands_band_energy.argtypes = [vp, vp, i, vp, d, d, i, d, vp]
     L.rsrec_set_positions.argtypes = [vp, vp]
     _lib = L
     return L

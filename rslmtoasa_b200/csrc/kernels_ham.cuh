@@ -14,8 +14,8 @@
 
 __constant__ double2 c_hcpx_v[81], c_hcpx_vc[81];  // col-major 9x9: element (i,j) at i + 9 j
 
-static int ham_configure() {
-  double2 v[81], vc[81];
+// V / V^H of hcpx (math.f90:1525-1558), col-major 9x9, on the host
+static void hcpx_host_matrices(double2 *v, double2 *vc) {
   for (int e = 0; e < 81; e++) v[e] = vc[e] = make_double2(0.0, 0.0);
   const double c = 1.0 / sqrt(2.0);
   auto S = [](double2 *m, int i, int j, double re, double im) { m[(i - 1) + 9 * (j - 1)] = make_double2(re, im); };
@@ -28,6 +28,11 @@ static int ham_configure() {
   S(v, 7, 6, c, 0); S(v, 7, 8, -c, 0); S(v, 8, 5, c, 0); S(v, 8, 9, c, 0); S(v, 9, 7, 1, 0);
   S(vc, 5, 5, 0, -c); S(vc, 9, 5, 0, c); S(vc, 6, 6, 0, -c); S(vc, 8, 6, 0, -c);
   S(vc, 6, 7, c, 0); S(vc, 8, 7, -c, 0); S(vc, 5, 8, c, 0); S(vc, 9, 8, c, 0); S(vc, 7, 9, 1, 0);
+}
+
+static int ham_configure() {
+  double2 v[81], vc[81];
+  hcpx_host_matrices(v, vc);
   if (cudaMemcpyToSymbol(c_hcpx_v, v, sizeof(v)) != cudaSuccess) return -1;
   if (cudaMemcpyToSymbol(c_hcpx_vc, vc, sizeof(vc)) != cudaSuccess) return -1;
   return 0;

@@ -12,6 +12,7 @@
 #include "kernels_post.cuh"
 #include "kernels_lattice.cuh"
 #include "kernels_ham.cuh"
+#include "kernels_bands.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -74,6 +75,9 @@ struct rsrec_handle_s {
   std::vector<DevBuf> vecs;
   DevBuf part, A, B, Bi, B2, mu, ahist, b2hist, scratch;
   DevBuf post[12];  // work arrays of the post-recursion consumers (terminator, Green functions, Kubo back end)
+  // on-site Green function of the last Green-function call, kept for the `bands` consumers (bands.f90)
+  DevBuf g0all, bands_y, bands_out;
+  int g0_units = 0, g0_nv = 0;
   int32_t *d_si = nullptr, *d_sj = nullptr;
   double *d_as = nullptr, *d_bs = nullptr;
   int units_cap = 0;
@@ -700,7 +704,7 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
   if (const char *f = getenv("RSREC_SQRT_METHOD")) h->sqrt_method = atoi(f);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  if (dmma_configure() != 0 || kubo_configure() != 0 || kdiag_configure() != 0 || post_configure() != 0 || ham_configure() != 0) {
+  if (dmma_configure() != 0 || kubo_configure() != 0 || kdiag_configure() != 0 || post_configure() != 0 || ham_configure() != 0 || bands_configure() != 0) {
     cudaStreamDestroy(h->st);
     delete h;
     return fail(RSREC_ECUDA, "cannot reserve shared memory for the DMMA kernels");
@@ -718,6 +722,7 @@ int rsrec_destroy(rsrec_handle h) {
                     &h->part, &h->A, &h->B, &h->Bi, &h->B2, &h->mu, &h->ahist, &h->b2hist, &h->scratch};
   for (auto b : bufs) dev_free(*b);
   for (auto &b : h->post) dev_free(b);
+  dev_free(h->g0all); dev_free(h->bands_y); dev_free(h->bands_out);
   dmma_free_tiles(h->tiles);
   if (h->d_nbr) cudaFree(h->d_nbr);
   if (h->d_cls) cudaFree(h->d_cls);
@@ -1109,6 +1114,18 @@ static int to_host(H *h, void *dst, const double *src, size_t ndoubles) {
   return RSREC_OK;
 }
 static int grid_for(size_t n, int threads, int cap) { return (int)std::max<size_t>(1, std::min<size_t>((n + threads - 1) / threads, (size_t)cap)); }
+// g0 (18,18,nv,na) stays on the device for the bands consumers
+static int g0_reserve(H *h, int na, int nv) {
+  h->g0_units = 0; h->g0_nv = 0;
+  TRY(dev_alloc(h->g0all, std::max<size_t>(1, (size_t)na * nv * BLKD), false));
+  h->g0_units = na; h->g0_nv = nv;
+  return RSREC_OK;
+}
+static int g0_keep(H *h, const double *d_src, int na, int nv) {
+  TRY(g0_reserve(h, na, nv));
+  CUDA_TRY(cudaMemcpyAsync(h->g0all.p, d_src, (size_t)na * nv * BLKD * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  return RSREC_OK;
+}
 
 // get_terminf (recursion.f90:2092-2138) = get_cinf (324 bpopt chains per unit over the real parts) + fix-ups
 static int d_terminf(H *h, const double *d_ab, const double *d_bb, int na, int ll, double *d_ainf, double *d_binf,
@@ -1306,6 +1323,7 @@ int rsrec_block_green(rsrec_handle h, const cplx *a_b, const cplx *b_b, int na, 
   double *d_ai = h->post[2].p, *d_bi = d_ai + (size_t)na * BLKC, *d_a0 = d_bi + (size_t)na * BLKC, *d_b0 = d_a0 + na;
   TRY(d_terminf(h, h->post[0].p, h->post[1].p, na, ll, d_ai, d_bi, d_a0, d_b0, true));
   TRY(d_bgreen(h, h->post[0].p, h->post[1].p, ll, na, h->post[4].p, nv, 0, nv, d_ai, d_bi, 0.0, 0.0, sym_term, h->post[5].p));
+  TRY(g0_keep(h, h->post[5].p, na, nv));
   TRY(to_host(h, g0, h->post[5].p, (size_t)na * nv * BLKD));
   CUDA_TRY(cudaStreamSynchronize(h->st));
   return RSREC_OK;
@@ -1332,6 +1350,7 @@ int rsrec_chebyshev_green(rsrec_handle h, const cplx *mu_n, int na, int lld, con
     TRY(d_cheb_green(h, h->post[0].p, na, lld, h->post[4].p, nv, energy_min, energy_max, h->post[1].p, h->post[5].p));
   }
   if (mu_ng) TRY(to_host(h, mu_ng, h->post[1].p, n));
+  if (nv > 0) TRY(g0_keep(h, h->post[5].p, na, nv));
   TRY(to_host(h, g0, h->post[5].p, (size_t)na * nv * BLKD));
   CUDA_TRY(cudaStreamSynchronize(h->st));
   return RSREC_OK;
@@ -1375,6 +1394,7 @@ int rsrec_sgreen(rsrec_handle h, const double *a, const double *b2, int lld, int
   k_sgreen_assemble<<<grid_for(total, 256, h->sms * 8), 256, 0, h->st>>>(h->post[5].p, nv, na, nmdir, (double2 *)h->post[6].p);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
+  TRY(g0_keep(h, h->post[6].p, na, nv));
   TRY(to_host(h, g0, h->post[6].p, (size_t)na * nv * BLKD));
   CUDA_TRY(cudaStreamSynchronize(h->st));
   return RSREC_OK;
@@ -1394,10 +1414,11 @@ int rsrec_conductivity_integrand(rsrec_handle h, const cplx *mu_nm, int M, int n
 // a_b, b2_b (18,18,lld,nunits; b2_b = B^2 as recur_b leaves it; either may be NULL), g0 (18,18,nv,nunits).
 int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, const double *ene, int nv, int sym_term,
                         cplx *a_b, cplx *b2_b, cplx *g0) {
-  if (!h || nunits < 0 || lld < 2 || nv < 1 || !ene || !g0 || (nunits > 0 && !site_i)) return fail(RSREC_EINVAL, "rsrec_recur_b_green: bad argument (need lld >= 2)");
+  if (!h || nunits < 0 || lld < 2 || nv < 1 || !ene || (nunits > 0 && !site_i)) return fail(RSREC_EINVAL, "rsrec_recur_b_green: bad argument (need lld >= 2)");
   if (nunits == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
+  TRY(g0_reserve(h, nunits, nv));
   TRY(to_dev(h, h->post[4], ene, nv));
   const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
   const size_t hs = (size_t)lld * BLKD;
@@ -1413,11 +1434,11 @@ int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int l
     k_zsqr<<<(unsigned)((size_t)n * lld), BLKC, 0, h->st>>>(h->post[1].p);
     h->launches++;
     TRY(dev_alloc(h->post[2], 2 * (size_t)n * (BLKC + 1), false));
-    TRY(dev_alloc(h->post[5], (size_t)n * nv * BLKD, false));
+    double *d_g0 = h->g0all.p + (size_t)u0 * nv * BLKD;
     double *d_ai = h->post[2].p, *d_bi = d_ai + (size_t)n * BLKC, *d_a0 = d_bi + (size_t)n * BLKC, *d_b0 = d_a0 + n;
     TRY(d_terminf(h, h->ahist.p, h->post[1].p, n, lld, d_ai, d_bi, d_a0, d_b0, true));
-    TRY(d_bgreen(h, h->ahist.p, h->post[1].p, lld, n, h->post[4].p, nv, 0, nv, d_ai, d_bi, 0.0, 0.0, sym_term, h->post[5].p));
-    TRY(to_host(h, g0 + (size_t)u0 * nv * BLKC, h->post[5].p, (size_t)n * nv * BLKD));
+    TRY(d_bgreen(h, h->ahist.p, h->post[1].p, lld, n, h->post[4].p, nv, 0, nv, d_ai, d_bi, 0.0, 0.0, sym_term, d_g0));
+    if (g0) TRY(to_host(h, g0 + (size_t)u0 * nv * BLKC, d_g0, (size_t)n * nv * BLKD));
     CUDA_TRY(cudaStreamSynchronize(h->st));
   }
   return RSREC_OK;
@@ -1426,11 +1447,12 @@ int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int l
 // chebyshev_recur + chebyshev_green (recursion.f90:3057-3130 + green.f90:1030-1108): mu_n, mu_ng may be NULL.
 int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, double energy_min, double energy_max,
                            const double *ene, int nv, cplx *mu_n, cplx *mu_ng, cplx *g0) {
-  if (!h || nunits < 0 || lld < 0 || nv < 1 || !ene || !g0 || energy_max == energy_min || (nunits > 0 && !site_i))
+  if (!h || nunits < 0 || lld < 0 || nv < 1 || !ene || energy_max == energy_min || (nunits > 0 && !site_i))
     return fail(RSREC_EINVAL, "rsrec_cheb_recur_green: bad argument");
   if (nunits == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
+  TRY(g0_reserve(h, nunits, nv));
   TRY(to_dev(h, h->post[4], ene, nv));
   const double a = (energy_max - energy_min) / (2 - 0.3), b = (energy_max + energy_min) / 2;  // recursion.f90:3078-3079
   const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
@@ -1446,10 +1468,10 @@ int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, in
     int rc = cheb_finish(h, mu_out);
     if (rc == RSREC_EDIVERGED) rc_all = rc; else TRY(rc);
     TRY(dev_alloc(h->post[1], (size_t)n * ms, false));
-    TRY(dev_alloc(h->post[5], (size_t)n * nv * BLKD, false));
-    TRY(d_cheb_green(h, h->mu.p, n, lld, h->post[4].p, nv, energy_min, energy_max, h->post[1].p, h->post[5].p));
+    double *d_g0 = h->g0all.p + (size_t)u0 * nv * BLKD;
+    TRY(d_cheb_green(h, h->mu.p, n, lld, h->post[4].p, nv, energy_min, energy_max, h->post[1].p, d_g0));
     if (mu_ng) TRY(to_host(h, mu_ng + (size_t)u0 * (2 * lld + 2) * BLKC, h->post[1].p, (size_t)n * ms));
-    TRY(to_host(h, g0 + (size_t)u0 * nv * BLKC, h->post[5].p, (size_t)n * nv * BLKD));
+    if (g0) TRY(to_host(h, g0 + (size_t)u0 * nv * BLKC, d_g0, (size_t)n * nv * BLKD));
     CUDA_TRY(cudaStreamSynchronize(h->st));
   }
   return rc_all;
@@ -1842,5 +1864,148 @@ int rsrec_profile_read(rsrec_handle h, double *total_ms, int *nlaunches) {
   return RSREC_OK;
 }
 long long rsrec_launch_count(rsrec_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"
+
+// ---- `type bands` (bands.f90): the consumers of g0 in the SCF loop, on the device-resident g0 ----------------------
+static int bands_need_g0(H *h, const char *who) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  if (h->g0_units <= 0 || h->g0_nv <= 0) return fail(RSREC_EINVAL, std::string(who) + ": no on-site Green function on the device (call a Green-function entry point or rsrec_bands_set_g0 first)");
+  return RSREC_OK;
+}
+// simpson_m over nint integrands x nord powers of the energy (d_y: (nv,nint)) -> host out (nord,nint)
+static int bands_simpson(H *h, const double *d_y, int nv, int nint, int nord, int ord0, const double *ene, double edel, double fermi,
+                         int nv1, double e1, double *out) {
+  if (nv1 < 1 || nv1 + 2 > nv) return fail(RSREC_EINVAL, "bands: need 1 <= nv1 and nv1 + 2 <= nv (simpson_m reads Y(NPTS+2))");
+  TRY(to_dev(h, h->post[4], ene, nv));
+  const int n = nint * nord;
+  TRY(dev_alloc(h->bands_out, std::max(n, 4), false));
+  k_bands_simpson<<<(n * 32 + 127) / 128, 128, 0, h->st>>>(d_y, nv, nint, nord, ord0, h->post[4].p, edel, fermi, nv1, e1, h->bands_out.p);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  TRY(to_host(h, out, h->bands_out.p, n));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+extern "C" {
+
+int rsrec_bands_set_g0(rsrec_handle h, const cplx *g0, int nunits, int nv) {
+  if (!h || !g0 || nunits < 1 || nv < 1) return fail(RSREC_EINVAL, "rsrec_bands_set_g0: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(g0_reserve(h, nunits, nv));
+  CUDA_TRY(cudaMemcpyAsync(h->g0all.p, g0, (size_t)nunits * nv * BLKD * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  h->h2d_bytes += (long long)((size_t)nunits * nv * BLKD * sizeof(double));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_bands_g0_shape(rsrec_handle h, int *nunits, int *nv) {
+  if (!h || !nunits || !nv) return fail(RSREC_EINVAL, "rsrec_bands_g0_shape: bad argument");
+  *nunits = h->g0_units; *nv = h->g0_nv;
+  return RSREC_OK;
+}
+
+int rsrec_bands_get_g0(rsrec_handle h, cplx *g0) {
+  TRY(bands_need_g0(h, "rsrec_bands_get_g0"));
+  if (!g0) return fail(RSREC_EINVAL, "rsrec_bands_get_g0: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(to_host(h, g0, h->g0all.p, (size_t)h->g0_units * h->g0_nv * BLKD));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_bands_dos(rsrec_handle h, double *dtot, double *dosia, double *dosial) {
+  TRY(bands_need_g0(h, "rsrec_bands_dos"));
+  if (!dtot) return fail(RSREC_EINVAL, "rsrec_bands_dos: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const int nv = h->g0_nv, nu = h->g0_units;
+  const size_t n1 = (size_t)nv * nu;
+  TRY(dev_alloc(h->bands_y, nv + n1 * 19, false));
+  double *d_dtot = h->bands_y.p, *d_ia = d_dtot + nv, *d_ial = d_ia + n1;
+  k_bands_dtot<<<(nv + 127) / 128, 128, 0, h->st>>>((const double2 *)h->g0all.p, nv, nu, d_dtot);
+  h->launches++;
+  if (dosia || dosial) {
+    k_bands_ldos<<<(unsigned)((n1 + 127) / 128), 128, 0, h->st>>>((const double2 *)h->g0all.p, nv, nu, dosia ? d_ia : nullptr, dosial ? d_ial : nullptr);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  TRY(to_host(h, dtot, d_dtot, nv));
+  if (dosia) TRY(to_host(h, dosia, d_ia, n1));
+  if (dosial) TRY(to_host(h, dosial, d_ial, n1 * 18));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+int rsrec_bands_fermi(rsrec_handle h, const double *dtot, int nv, double edel, double energy_min, double qqv, int fix_fermi,
+                      double *fermi, int *nv1, double *e1, int *ifail) {
+  if (!h || !fermi || !nv1 || !e1 || nv < 3 || edel == 0.0 || (!fix_fermi && !dtot)) return fail(RSREC_EINVAL, "rsrec_bands_fermi: bad argument");
+  if (ifail) *ifail = 0;
+  if (fix_fermi) {  // bands.f90:338-341
+    const int ik1 = (int)std::llround((*fermi - energy_min) / edel);  // nint
+    *nv1 = ik1;
+    *e1 = energy_min + (ik1 - 1) * edel;
+    return RSREC_OK;
+  }
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(to_dev(h, h->post[4], dtot, nv));
+  TRY(dev_alloc(h->bands_out, 4, false));
+  k_bands_fermi<<<1, 32, 0, h->st>>>(h->post[4].p, nv, edel, energy_min, qqv, *fermi, *nv1, h->bands_out.p);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  double res[4];
+  TRY(to_host(h, res, h->bands_out.p, 4));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  *fermi = res[0]; *e1 = res[1]; *nv1 = (int)res[2];
+  if (ifail) *ifail = (int)res[3];
+  return RSREC_OK;
+}
+
+int rsrec_bands_magnetic_moments(rsrec_handle h, const double *ene, double edel, double fermi, int nv1, double e1, double *mom0,
+                                 double *mom1) {
+  TRY(bands_need_g0(h, "rsrec_bands_magnetic_moments"));
+  if (!ene || !mom0 || !mom1) return fail(RSREC_EINVAL, "rsrec_bands_magnetic_moments: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const int nv = h->g0_nv, nu = h->g0_units;
+  const size_t n = (size_t)nv * nu * 3;
+  TRY(dev_alloc(h->bands_y, n, false));
+  k_bands_spin<<<(unsigned)((n + 127) / 128), 128, 0, h->st>>>((const double2 *)h->g0all.p, nv, nu, h->bands_y.p);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  std::vector<double> out((size_t)6 * nu);  // (order 0..1, direction, unit)
+  TRY(bands_simpson(h, h->bands_y.p, nv, 3 * nu, 2, 0, ene, edel, fermi, nv1, e1, out.data()));
+  for (int i = 0; i < 3 * nu; i++) { mom0[i] = out[2 * i]; mom1[i] = out[2 * i + 1]; }
+  return RSREC_OK;
+}
+
+int rsrec_bands_moments(rsrec_handle h, int channels_ldos, const double *ene, double edel, double fermi, int nv1, double e1,
+                        const double *mom, double *occ, double *lmom) {
+  TRY(bands_need_g0(h, "rsrec_bands_moments"));
+  if (!ene || !mom || !occ || !lmom || channels_ldos < 0 || channels_ldos > h->g0_nv) return fail(RSREC_EINVAL, "rsrec_bands_moments: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const int nv = h->g0_nv, nu = h->g0_units;
+  const size_t n = (size_t)nv * nu * 9;
+  TRY(dev_alloc(h->bands_y, n, false));
+  TRY(to_dev(h, h->post[3], mom, (size_t)3 * nu));
+  k_bands_dspd<<<(unsigned)((n + 127) / 128), 128, 0, h->st>>>((const double2 *)h->g0all.p, nv, channels_ldos, nu, h->post[3].p, h->bands_y.p);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  std::vector<double> out((size_t)27 * nu);  // (order 0..2, q 0..8, unit)
+  TRY(bands_simpson(h, h->bands_y.p, nv, 9 * nu, 3, 0, ene, edel, fermi, nv1, e1, out.data()));
+  for (int u = 0; u < nu; u++) {
+    for (int q = 0; q < 6; q++)
+      for (int k = 0; k < 3; k++) occ[k + 3 * (q + 6 * u)] = out[k + 3 * (q + 9 * (size_t)u)];
+    for (int d = 0; d < 3; d++) lmom[d + 3 * u] = -(out[3 * (6 + d + 9 * (size_t)u)] / PI_RP);  // bands.f90:1144-1146
+  }
+  return RSREC_OK;
+}
+
+int rsrec_bands_band_energy(rsrec_handle h, const double *dtot, int nv, const double *ene, double edel, double fermi, int nv1,
+                            double e1, double *eband) {
+  if (!h || !dtot || !ene || !eband || nv < 3) return fail(RSREC_EINVAL, "rsrec_bands_band_energy: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(to_dev(h, h->bands_y, dtot, nv));
+  return bands_simpson(h, h->bands_y.p, nv, 1, 1, 1, ene, edel, fermi, nv1, e1, eband);
+}
 
 }  // extern "C"

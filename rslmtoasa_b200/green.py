@@ -91,9 +91,10 @@ class Green(_Consumer):
         return self.g0
 
     # -- fused: recursion + Green function without a host round trip of the coefficients ------------------------
-    def recur_b_green(self):
+    def recur_b_green(self, download_g0: bool = True):
         """run_recursion + run_dos of the block path (self.f90:799-856) in one call: fills recursion.a_b, b2_b (= B^2,
-        as recur_b leaves it), recursion.a, b2 and self.g0."""
+        as recur_b leaves it), recursion.a, b2 and self.g0.  download_g0 = False leaves g0 on the device only (for
+        `Bands`)."""
         rec = self.recursion
         s, e = rec._local_units(len(rec.lattice.irec))
         sites = np.ascontiguousarray(rec.lattice.irec[s - 1:e], dtype=np.int32)
@@ -101,7 +102,7 @@ class Green(_Consumer):
         ene = self.ene
         rec.a_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
         rec.b2_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
-        self.g0 = np.zeros((NB, NB, len(ene), n), np.complex128, order="F")
+        self.g0 = np.zeros((NB, NB, len(ene), n), np.complex128, order="F") if download_g0 else None
         _lib.check(self._L.rsrec_recur_b_green(self._h, n, _p(sites), lld, _p(ene), len(ene), int(self.sym_term),
                                                _p(rec.a_b), _p(rec.b2_b), _p(self.g0)))
         d = np.arange(NB)
@@ -110,7 +111,7 @@ class Green(_Consumer):
         rec.b2[:, :, :, 0] = np.real(rec.b2_b[d, d]).transpose(1, 0, 2)
         return self.g0
 
-    def chebyshev_recur_green(self, keep_moments: bool = True):
+    def chebyshev_recur_green(self, keep_moments: bool = True, download_g0: bool = True):
         """chebyshev_recur + chebyshev_green in one call."""
         rec = self.recursion
         s, e = rec._local_units(len(rec.lattice.irec))
@@ -120,7 +121,7 @@ class Green(_Consumer):
         if keep_moments:
             rec.mu_n = np.zeros((NB, NB, 2 * lld + 2, n), np.complex128, order="F")
             rec.mu_ng = np.zeros((NB, NB, 2 * lld + 2, n), np.complex128, order="F")
-        self.g0 = np.zeros((NB, NB, len(ene), n), np.complex128, order="F")
+        self.g0 = np.zeros((NB, NB, len(ene), n), np.complex128, order="F") if download_g0 else None
         _lib.check(self._L.rsrec_cheb_recur_green(self._h, n, _p(sites), lld, self.en.energy_min, self.en.energy_max,
                                                   _p(ene), len(ene), _p(rec.mu_n) if keep_moments else None,
                                                   _p(rec.mu_ng) if keep_moments else None, _p(self.g0)))

@@ -44,13 +44,24 @@ class Energy:
     channels_ldos: int = 2500
     fermi: float = 0.0
     ene: object = None
+    edel: float = 0.0
+    nv1: int = 0
+    ik1: int = 0
+    fix_fermi: bool = False
 
     def e_mesh(self):
-        """energy%e_mesh (energy.f90:175-208): channels_ldos+10 points from energy_min with a step that hits fermi."""
-        if self.channels_ldos % 2 != 0:
+        """energy%e_mesh (energy.f90:175-208): channels_ldos+10 points from energy_min with a step that hits fermi;
+        nv1 = ik1 = the odd channel count."""
+        if self.channels_ldos % 2 == 0:
+            self.nv1 = self.channels_ldos + 1
+        else:
+            self.nv1 = self.channels_ldos
             self.channels_ldos -= 1
+        self.ik1 = self.nv1
         edel = (self.energy_max - self.energy_min) / self.channels_ldos
-        edel = (self.fermi - self.energy_min) / np.rint((self.fermi - self.energy_min) / edel)
+        r = (self.fermi - self.energy_min) / edel
+        edel = (self.fermi - self.energy_min) / (np.sign(r) * np.floor(abs(r) + 0.5))  # nint
+        self.edel = float(edel)
         self.ene = self.energy_min + edel * np.arange(self.channels_ldos + 10, dtype=np.float64)
         return self.ene
 
