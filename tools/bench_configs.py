@@ -153,12 +153,33 @@ def run_scf_step(name, lat, ham, lld=21, channels=2500):
     t1 = time.perf_counter()
     ref = O.block_green(a_b, orc.zsqr(b2_b), g.ene)
     tc = time.perf_counter() - t0
-    ok = np.isfinite(ref) & np.isfinite(g.g0)
+    g0_gpu = g.g0
+    ok = np.isfinite(ref) & np.isfinite(g0_gpu)
+    # the same step with g0 left on the device and the `bands` consumers (Fermi level, moments, band energy) run there
+    from rslmtoasa_b200.bands import Bands
+    nu = len(lat.irec)
+
+    def with_bands():
+        g.recur_b_green(download_g0=False)
+        rec.en.fermi = 0.0
+        b = Bands(g, qqv=6.0 * nu)
+        b.calculate_fermi(); b.calculate_magnetic_moments(); b.calculate_moments(); b.calculate_band_energy()
+        return b
+    tb = timed(with_bands, reps=5)
+    b = with_bands()
+    t2 = time.perf_counter()
+    dtot = O.bands_dos(ref)[0]
+    ef, nv1, e1, _ = O.bands_fermi(dtot, rec.en.edel, rec.en.energy_min, 6.0 * nu, 0.0, rec.en.ik1)
+    occ, _ = O.bands_moments(ref, rec.en.channels_ldos, b.mom, g.ene, rec.en.edel, ef, nv1, e1)
+    O.bands_magnetic_moments(ref, g.ene, rec.en.edel, ef, nv1, e1)
+    tcb = time.perf_counter() - t2
     out = {"config": name, "what": "scf_step: recur_b + zsqr + terminator + bgreen (fused, device-resident coefficients)",
+           "gpu_seconds_with_bands_g0_resident": tb, "cpu_bands_seconds": tcb, "err_fermi": abs(rec.en.fermi - ef),
+           "err_charges": float(np.abs(b.occ - occ).max()),
            "kk": lat.kk, "units": int(len(lat.irec)), "lld": lld, "nv": channels + 10, "hoh": bool(ham.hoh),
            "gpu_seconds": t, "cpu_seconds": tc, "cpu_recursion_seconds": t1 - t0, "cpu_threads": O.lib().orc_get_max_threads(),
-           "speedup": tc / t, "relerr_a_b": relerr(rec.a_b, a_b), "relerr_g0": relerr(g.g0[ok], ref[ok]),
-           "d2h_bytes_g0": int(g.g0.nbytes)}
+           "speedup": tc / t, "relerr_a_b": relerr(rec.a_b, a_b), "relerr_g0": relerr(g0_gpu[ok], ref[ok]),
+           "d2h_bytes_g0": int(g0_gpu.nbytes)}
     print(json.dumps(out), flush=True)
     rec.close()
 
