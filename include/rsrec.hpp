@@ -47,11 +47,16 @@ struct control {  // control.f90:356-384
 struct energy {  // energy.f90: energy_min/max, channels_ldos, fermi and the mesh e_mesh builds (175-208)
   double energy_min = -1.5, energy_max = 1.5, fermi = 0.0;
   int channels_ldos = 2500;
+  double edel = 0.0;
+  int nv1 = 0, ik1 = 0;
+  bool fix_fermi = false;
   std::vector<double> ene;
   void e_mesh() {
-    if (channels_ldos % 2 != 0) channels_ldos -= 1;
-    double edel = (energy_max - energy_min) / channels_ldos;
-    edel = (fermi - energy_min) / std::nearbyint((fermi - energy_min) / edel);
+    if (channels_ldos % 2 == 0) nv1 = channels_ldos + 1;
+    else { nv1 = channels_ldos; channels_ldos -= 1; }
+    ik1 = nv1;
+    edel = (energy_max - energy_min) / channels_ldos;
+    edel = (fermi - energy_min) / std::round((fermi - energy_min) / edel);  // nint
     ene.resize(channels_ldos + 10);
     for (int i = 0; i < channels_ldos + 10; i++) ene[i] = energy_min + edel * i;
   }
@@ -213,20 +218,81 @@ class green {
     check(rsrec_chebyshev_green(rec_.handle(), cp(rec_.mu_n), na, lld, en_.ene.data(), nv, en_.energy_min, en_.energy_max,
                                 mu_ng ? mp(*mu_ng) : nullptr, mp(g0)));
   }
-  void recur_b_green() {  // fused self%run_recursion + self%run_dos (block path)
+  // fused self%run_recursion + self%run_dos (block path); download_g0 = false leaves g0 on the device only (for `bands`)
+  void recur_b_green(bool download_g0 = true) {
     const auto sites = rec_.sites_local();
     const int n = (int)sites.size(), lld = rec_.ctl().lld, nv = (int)en_.ene.size();
     rec_.a_b.assign((size_t)324 * lld * n, 0.0);
     rec_.b2_b.assign((size_t)324 * lld * n, 0.0);
-    g0.assign((size_t)324 * nv * n, 0.0);
-    check(rsrec_recur_b_green(rec_.handle(), n, sites.data(), lld, en_.ene.data(), nv, sym_term, mp(rec_.a_b), mp(rec_.b2_b), mp(g0)));
+    g0.assign(download_g0 ? (size_t)324 * nv * n : 0, 0.0);
+    check(rsrec_recur_b_green(rec_.handle(), n, sites.data(), lld, en_.ene.data(), nv, sym_term, mp(rec_.a_b), mp(rec_.b2_b),
+                              download_g0 ? mp(g0) : nullptr));
   }
+  recursion &rec() { return rec_; }
+  energy &en() { return en_; }
 
  private:
   static const rsrec_cplx *cp(const std::vector<cplx> &v) { return reinterpret_cast<const rsrec_cplx *>(v.data()); }
   static rsrec_cplx *mp(std::vector<cplx> &v) { return reinterpret_cast<rsrec_cplx *>(v.data()); }
   recursion &rec_;
   energy &en_;
+};
+
+// `type bands` (bands.f90): consumes the g0 the last Green-function call left on the device
+class bands {
+ public:
+  double qqv = 0.0, e1 = 0.0, eband = 0.0;
+  int nv1 = 0, ifail = 0, nsp = 2;
+  std::vector<double> dtot;             // (nv)
+  std::vector<double> mom0, mom1, mom;  // (3,nunits): mx,my,mz; potential%mom1; unit vectors potential%mom
+  std::vector<double> occ, lmom;        // (3,6,nunits) = sgef,pmef,smef per (l, spin); (3,nunits)
+  bands(green &g, double valence) : qqv(valence), gr_(g) {}
+  void calculate_fermi() {  // bands.f90:227-347 (single rank: no all-reduce of dtot)
+    int nu = 0, nv = 0;
+    check(rsrec_bands_g0_shape(h(), &nu, &nv));
+    dtot.assign(nv, 0.0);
+    check(rsrec_bands_dos(h(), dtot.data(), nullptr, nullptr));
+    energy &en = gr_.en();
+    double fermi = en.fermi, e1_new = 0.0;
+    int n1 = en.ik1;
+    check(rsrec_bands_fermi(h(), dtot.data(), nv, en.edel, en.energy_min, qqv, en.fix_fermi, &fermi, &n1, &e1_new, &ifail));
+    if (ifail == 0) { en.fermi = fermi; nv1 = n1; e1 = e1_new; }
+  }
+  void calculate_magnetic_moments() {  // bands.f90:791-855
+    const int nu = units();
+    mom0.assign(3 * (size_t)nu, 0.0); mom1.assign(3 * (size_t)nu, 0.0); mom.assign(3 * (size_t)nu, 0.0);
+    energy &en = gr_.en();
+    check(rsrec_bands_magnetic_moments(h(), en.ene.data(), en.edel, en.fermi, nv1, e1, mom0.data(), mom1.data()));
+    for (int u = 0; u < nu; u++) {
+      const double *m = &mom0[3 * (size_t)u];
+      const double mtot = std::sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) + 1.0e-15;
+      for (int d = 0; d < 3; d++) mom[3 * (size_t)u + d] = nsp < 3 ? (d == 2 ? 1.0 : 0.0) : m[d] / mtot;
+    }
+  }
+  void calculate_moments() {  // bands.f90:409-524 with calculate_orbital_moments 1075-1156
+    const int nu = units();
+    if (mom.size() != 3 * (size_t)nu) { mom.assign(3 * (size_t)nu, 0.0); for (int u = 0; u < nu; u++) mom[3 * (size_t)u + 2] = 1.0; }
+    occ.assign(18 * (size_t)nu, 0.0); lmom.assign(3 * (size_t)nu, 0.0);
+    energy &en = gr_.en();
+    check(rsrec_bands_moments(h(), en.channels_ldos, en.ene.data(), en.edel, en.fermi, nv1, e1, mom.data(), occ.data(), lmom.data()));
+  }
+  // potential%ql(q, l, isp) of unit u (q = 1..3, l = 0..2, isp = 1..2), bands.f90:493-495
+  double ql(int q, int l, int isp, int u) const {
+    const double *o = &occ[3 * ((size_t)(l + 3 * (isp - 1)) + 6 * (size_t)u)];
+    if (q == 1) return o[0];
+    if (q == 2) return 0.0;
+    const double cg = o[1] / o[0];
+    return o[2] - 2.0 * cg * o[1] + cg * cg * o[0];
+  }
+  void calculate_band_energy() {  // bands.f90:354-359
+    energy &en = gr_.en();
+    check(rsrec_bands_band_energy(h(), dtot.data(), (int)dtot.size(), en.ene.data(), en.edel, en.fermi, nv1, e1, &eband));
+  }
+
+ private:
+  rsrec_handle h() { return gr_.rec().handle(); }
+  int units() { int nu = 0, nv = 0; check(rsrec_bands_g0_shape(h(), &nu, &nv)); return nu; }
+  green &gr_;
 };
 
 }  // namespace rsrec

@@ -18,6 +18,12 @@ static double relerr(const std::vector<rsrec::cplx> &x, const std::vector<rsrec:
   for (size_t i = 0; i < x.size(); i++) { e = std::max(e, std::abs(x[i] - r[i])); m = std::max(m, std::abs(r[i])); }
   return e / m;
 }
+static double relerr_d(const std::vector<double> &x, const std::vector<double> &r) {
+  double e = 0, m = 0;
+  if (x.size() != r.size()) return 1e300;
+  for (size_t i = 0; i < x.size(); i++) { e = std::max(e, std::abs(x[i] - r[i])); m = std::max(m, std::abs(r[i])); }
+  return e / m;
+}
 int main(int argc, char **argv) {
   FILE *f = fopen(argv[1], "rb");
   if (!f) return 2;
@@ -34,6 +40,8 @@ int main(int argc, char **argv) {
   auto mesh = rd<double>(f);   // channels_ldos, fermi
   auto ref_g0 = rd<rsrec::cplx>(f), ref_gk = rd<rsrec::cplx>(f);
   en.channels_ldos = (int)mesh[0]; en.fermi = mesh[1];
+  auto bsc = rd<double>(f);   // qqv, fermi, nv1, e1, eband
+  auto ref_occ = rd<double>(f), ref_m0 = rd<double>(f), ref_lmom = rd<double>(f);
   fclose(f);
   try {
     rsrec::recursion rec(ham, lat, ctl, en);
@@ -46,6 +54,15 @@ int main(int argc, char **argv) {
     const auto staged = gr.g0;
     gr.recur_b_green();
     printf("recur_b_green g0 %.3e\n", relerr(gr.g0, staged));
+    {  // bands on the device-resident g0 of the fused call (never downloaded)
+      gr.recur_b_green(false);
+      rsrec::bands bd(gr, bsc[0]);
+      bd.calculate_fermi(); bd.calculate_magnetic_moments(); bd.calculate_moments(); bd.calculate_band_energy();
+      printf("bands fermi %.3e nv1 %.1f eband %.3e occ %.3e mom0 %.3e lmom %.3e\n", std::abs(en.fermi - bsc[1]),
+             std::abs((double)bd.nv1 - bsc[2]), std::abs(bd.eband - bsc[4]) / std::abs(bsc[4]), relerr_d(bd.occ, ref_occ),
+             relerr_d(bd.mom0, ref_m0), relerr_d(bd.lmom, ref_lmom));
+      en.fermi = mesh[1];
+    }
     rec.chebyshev_recur();
     printf("chebyshev_recur mu_n %.3e\n", relerr(rec.mu_n, ref_mu));
     gr.chebyshev_green();

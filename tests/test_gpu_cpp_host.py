@@ -58,12 +58,25 @@ def test_cpp_host_mirror_matches_oracle(tmp_path, oracle_mod):
         ene = oracle_mod.e_mesh(EMIN, EMAX, 70, 0.05)              # the C++ mirror builds the same mesh (energy.f90:175-208)
         _w(f, oracle_mod.block_green(a_b, orc.zsqr(b2_b), ene), np.complex128)
         _w(f, oracle_mod.chebyshev_green(mu, ene, EMIN, EMAX)[1], np.complex128)   # NaN tail (|w| > 1) is skipped by the C++ max
+        # bands on the block g0: valence, then the oracle's fermi, nv1, e1, eband, occ(3,6,n), mom0(3,n), lmom(3,n)
+        g0 = oracle_mod.block_green(a_b, orc.zsqr(b2_b), ene)
+        m = oracle_mod.e_mesh_full(EMIN, EMAX, 70, 0.05)
+        dtot = oracle_mod.bands_dos(g0)[0]
+        qqv = 0.4 * oracle_mod.simpson_m(m["edel"], ene[m["nv1"] - 1], m["nv1"], dtot, ene[m["nv1"] - 1], 0, ene)
+        ef, nv1, e1, ifail = oracle_mod.bands_fermi(dtot, m["edel"], EMIN, qqv, 0.05, m["nv1"])
+        assert ifail == 0
+        nu = g0.shape[3]
+        mom = np.tile(np.array([0.0, 0.0, 1.0])[:, None], (1, nu))
+        occ, lmom = oracle_mod.bands_moments(g0, m["channels_ldos"], mom, ene, m["edel"], ef, nv1, e1)
+        m0, _ = oracle_mod.bands_magnetic_moments(g0, ene, m["edel"], ef, nv1, e1)
+        _w(f, [qqv, ef, nv1, e1, oracle_mod.simpson_m(m["edel"], ef, nv1, dtot, e1, 1, ene)], np.float64)
+        _w(f, occ, np.float64); _w(f, m0, np.float64); _w(f, lmom, np.float64)
     out = subprocess.run([_build(tmp_path), path], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     vals = {}
     for line in out.stdout.splitlines():
         t = line.split()
-        if t[0] in ("recur_b", "chebyshev_recur", "recur_b_ij", "block_green", "recur_b_green", "chebyshev_green"):
+        if t[0] in ("recur_b", "chebyshev_recur", "recur_b_ij", "block_green", "recur_b_green", "chebyshev_green", "bands"):
             for k, v in zip(t[1::2], t[2::2]):
                 vals[t[0] + "." + k] = float(v)
     assert vals["recur_b.a_b"] < 1e-10 and vals["recur_b.b2_b"] < 1e-10
@@ -71,4 +84,6 @@ def test_cpp_host_mirror_matches_oracle(tmp_path, oracle_mod):
     assert vals["recur_b_ij.a_b"] < 1e-10
     assert vals["block_green.g0"] < 1e-8 and vals["recur_b_green.g0"] == 0.0
     assert vals["chebyshev_green.g0"] < 1e-9
+    assert vals["bands.fermi"] < 1e-10 and vals["bands.nv1"] == 0.0 and vals["bands.eband"] < 1e-10
+    assert vals["bands.occ"] < 1e-10 and vals["bands.mom0"] < 1e-10 and vals["bands.lmom"] < 1e-10
     assert "fatal -2" in out.stdout and "did not converge" in out.stdout

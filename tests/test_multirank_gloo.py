@@ -57,3 +57,50 @@ def test_sharded_units_and_collectives(tmp_path, oracle_mod, world):
         g = np.load(os.path.join(str(tmp_path), f"r{r}.npz"))
         assert relerr(g["mu_sum"], mu.sum(axis=-1)) < 1e-13        # every rank holds the full sum
         assert relerr(g["a_all"], a_b) < 1e-13                      # gather reproduces the 1-rank result
+
+
+def _bands_worker(rank, world, port, out_dir):
+    """the N>1 flow of `Bands` (rslmtoasa_b200/bands.py): per-rank dtot -> all-reduce -> Fermi scan on every rank ->
+    per-unit moments -> all-gather; the per-rank compute is played by the oracle"""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from rslmtoasa_b200 import parallel as P
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g0, m, qqv = _bands_case(O)
+    nu = g0.shape[3]
+    lo, hi = P.shard_range(nu, rank, world)
+    loc = np.asfortranarray(g0[..., lo:hi])
+    dtot = O.bands_dos(loc)[0] if hi > lo else np.zeros(g0.shape[2])
+    dtot = P.allreduce_sum(dtot)
+    ef, nv1, e1, ifail = O.bands_fermi(dtot, m["edel"], -1.2, qqv, 0.05, m["nv1"])
+    mom = np.asfortranarray(np.tile(np.array([0.0, 0.0, 1.0])[:, None], (1, hi - lo)))
+    occ = O.bands_moments(loc, m["channels_ldos"], mom, m["ene"], m["edel"], ef, nv1, e1)[0] if hi > lo else np.zeros((3, 6, 0), order="F")
+    occ_all = P.allgather_units(occ, nu)
+    np.savez(os.path.join(out_dir, f"b{rank}.npz"), dtot=dtot, ef=ef, nv1=nv1, occ=occ_all)
+    dist.destroy_process_group()
+
+
+def _bands_case(O):
+    m = O.e_mesh_full(-1.2, 0.9, 120, 0.05)
+    nv, nu = len(m["ene"]), 5
+    rng = np.random.default_rng(3)
+    g0 = rng.standard_normal((18, 18, nv, nu)) + 1j * rng.standard_normal((18, 18, nv, nu))
+    g0[np.arange(18), np.arange(18)] -= 3j
+    return np.asfortranarray(g0), m, 20.0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_bands_flow_over_ranks(tmp_path, oracle_mod, world):
+    mp.spawn(_bands_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    g0, m, qqv = _bands_case(oracle_mod)
+    dtot = oracle_mod.bands_dos(g0)[0]
+    ef, nv1, e1, ifail = oracle_mod.bands_fermi(dtot, m["edel"], -1.2, qqv, 0.05, m["nv1"])
+    assert ifail == 0
+    mom = np.tile(np.array([0.0, 0.0, 1.0])[:, None], (1, g0.shape[3]))
+    occ = oracle_mod.bands_moments(g0, m["channels_ldos"], mom, m["ene"], m["edel"], ef, nv1, e1)[0]
+    for r in range(world):
+        g = np.load(os.path.join(str(tmp_path), f"b{r}.npz"))
+        assert np.allclose(g["dtot"], dtot, rtol=1e-13, atol=1e-13)      # sum order differs across ranks: rounding only
+        assert int(g["nv1"]) == nv1 and abs(float(g["ef"]) - ef) < 1e-12
+        assert np.allclose(g["occ"], occ, rtol=1e-10, atol=1e-12)
