@@ -77,8 +77,44 @@ contains
                                                     integrand, integrand_at), __FILE__, __LINE__)
    end subroutine
 
+   !> green%calculate_intersite_gf (green.f90:425-469): the four Green functions of every pair come from the
+   !> device-resident g0 (staged flow: recur_b_ij / chebyshev_recur_ij filled a_b / mu_n with four slots per pair, then
+   !> block_green / chebyshev_green over the 4*njij units), and are combined to gij, gji and their spin components there
+   subroutine calculate_intersite_gf(this)
+      use green_mod, only: green
+      class(green), intent(inout), target :: this
+      integer(c_int32_t) :: pi(atoms_per_process), pj(atoms_per_process)
+      complex(c_double_complex), allocatable, target :: gspin(:, :, :, :, :)
+      integer :: ia, ia_glob, nv
+      nv = this%en%channels_ldos + 10
+      do ia_glob = start_atom, end_atom
+         ia = g2l_map(ia_glob)
+         pi(ia) = int(this%lattice%ijpair(ia_glob, 1), c_int32_t)
+         pj(ia) = int(this%lattice%ijpair(ia_glob, 2), c_int32_t)
+      end do
+      if (this%control%recur == 'block') then
+         call this%recursion%zsqr()
+         call rsrec_check(rsrec_block_green(this%recursion%gpu, this%recursion%a_b, this%recursion%b2_b, &
+                                            int(4*atoms_per_process, c_int), int(this%control%lld, c_int), this%en%ene, &
+                                            int(nv, c_int), merge(1_c_int, 0_c_int, this%control%sym_term), this%g0), &
+                          __FILE__, __LINE__)   ! g0 sized (18,18,nv,4*njij_loc) here; only its device copy is consumed
+      else
+         call rsrec_check(rsrec_chebyshev_green(this%recursion%gpu, this%recursion%mu_n, int(4*atoms_per_process, c_int), &
+                                                int(this%control%lld, c_int), this%en%ene, int(nv, c_int), &
+                                                this%en%energy_min, this%en%energy_max, this%recursion%mu_ng, this%g0), &
+                          __FILE__, __LINE__)
+      end if
+      allocate (gspin(9, 9, nv, atoms_per_process, 8))
+      call rsrec_check(rsrec_intersite_gf(this%recursion%gpu, int(atoms_per_process, c_int), pi, pj, 0_c_int, this%gij, &
+                                          this%gji, c_loc(gspin)), __FILE__, __LINE__)
+      this%ginmag = gspin(:, :, :, :, 1); this%gix = gspin(:, :, :, :, 2); this%giy = gspin(:, :, :, :, 3)
+      this%giz = gspin(:, :, :, :, 4); this%gjnmag = gspin(:, :, :, :, 5); this%gjx = gspin(:, :, :, :, 6)
+      this%gjy = gspin(:, :, :, :, 7); this%gjz = gspin(:, :, :, :, 8)
+   end subroutine
+
    ! Fused drivers (no host round trip of a_b/b2_b, mu_n or mu_nm_stochastic): self%run_recursion + self%run_dos of the
    ! block path -> rsrec_recur_b_green; chebyshev_recur + chebyshev_green -> rsrec_cheb_recur_green;
-   ! compute_moments_stochastic + calculate_conductivity_tensor -> rsrec_kubo_conductivity.  See
+   ! compute_moments_stochastic + calculate_conductivity_tensor -> rsrec_kubo_conductivity; recur_b_ij / chebyshev_recur_ij
+   ! + calculate_intersite_gf -> rsrec_recur_b_ij_green / rsrec_cheb_recur_ij_green (g0 = c_null_ptr) + rsrec_intersite_gf.  See
    ! rslmtoasa_b200/green.py (recur_b_green, chebyshev_recur_green, compute_conductivity) for the executable statement.
 end module green_gpu_shim

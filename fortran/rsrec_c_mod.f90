@@ -31,6 +31,8 @@ module rsrec_c_mod
    ! consumers of g0 in the SCF loop (bands.f90)
    public :: rsrec_bands_set_g0, rsrec_bands_get_g0, rsrec_bands_g0_shape, rsrec_bands_dos, rsrec_bands_fermi
    public :: rsrec_bands_magnetic_moments, rsrec_bands_moments, rsrec_bands_band_energy
+   ! exchange path: pair-unit fused drivers and calculate_intersite_gf
+   public :: rsrec_recur_b_ij_green, rsrec_cheb_recur_ij_green, rsrec_intersite_gf
 
    interface
       function rsrec_last_error() bind(C, name='rsrec_last_error') result(msg)
@@ -449,6 +451,42 @@ module rsrec_c_mod
          integer(c_int), value :: nv, nv1
          real(c_double), value :: edel, fermi, e1
          real(c_double), intent(out) :: eband
+         integer(c_int) :: rc
+      end function
+
+      ! fused: recur_b_ij -> zsqr -> block_green_ij (a_b, b2_b, g0 may be c_null_ptr)
+      function rsrec_recur_b_ij_green(h, nunits, site_i, site_j, asign, bsign, lld, ene, nv, sym_term, a_b, b2_b, g0) &
+         bind(C, name='rsrec_recur_b_ij_green') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double, c_double_complex
+         type(c_ptr), value :: h, a_b, b2_b, g0
+         integer(c_int), value :: nunits, lld, nv, sym_term
+         integer(c_int32_t), intent(in) :: site_i(*), site_j(*)
+         complex(c_double_complex), intent(in) :: asign(*), bsign(*)
+         real(c_double), intent(in) :: ene(*)
+         integer(c_int) :: rc
+      end function
+
+      ! fused: chebyshev_recur_ij -> chebyshev_green_ij (mu_n, mu_ng, g0 may be c_null_ptr)
+      function rsrec_cheb_recur_ij_green(h, nunits, site_i, site_j, asign, bsign, lld, energy_min, energy_max, ene, nv, &
+                                         mu_n, mu_ng, g0) bind(C, name='rsrec_cheb_recur_ij_green') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double, c_double_complex
+         type(c_ptr), value :: h, mu_n, mu_ng, g0
+         integer(c_int), value :: nunits, lld, nv
+         integer(c_int32_t), intent(in) :: site_i(*), site_j(*)
+         complex(c_double_complex), intent(in) :: asign(*), bsign(*)
+         real(c_double), value :: energy_min, energy_max
+         real(c_double), intent(in) :: ene(*)
+         integer(c_int) :: rc
+      end function
+
+      ! calculate_intersite_gf (green.f90:425-469) on the device-resident g0 of the pair units; gspin may be c_null_ptr
+      function rsrec_intersite_gf(h, njij, pair_i, pair_j, compact, gij, gji, gspin) &
+         bind(C, name='rsrec_intersite_gf') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double_complex
+         type(c_ptr), value :: h, gspin
+         integer(c_int), value :: njij, compact
+         integer(c_int32_t), intent(in) :: pair_i(*), pair_j(*)
+         complex(c_double_complex), intent(out) :: gij(18, 18, *), gji(18, 18, *)
          integer(c_int) :: rc
       end function
 

@@ -204,6 +204,25 @@ int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, in
                            double energy_max, const double *ene, int nv, rsrec_cplx *mu_n, rsrec_cplx *mu_ng,
                            rsrec_cplx *g0);
 
+/* The same two fused drivers for pair start vectors (the exchange path): recur_b_ij (recursion.f90:1655-1737) + zsqr +
+ * block_green_ij (green.f90:356-384), and chebyshev_recur_ij (2376-2487) + chebyshev_green_ij (892-952).  Units as in
+ * rsrec_lanczos_block / rsrec_cheb_moments (site_i, site_j, asign, bsign). */
+int rsrec_recur_b_ij_green(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j,
+                           const rsrec_cplx *asign, const rsrec_cplx *bsign, int lld, const double *ene, int nv,
+                           int sym_term, rsrec_cplx *a_b, rsrec_cplx *b2_b, rsrec_cplx *g0);
+int rsrec_cheb_recur_ij_green(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j,
+                              const rsrec_cplx *asign, const rsrec_cplx *bsign, int lld, double energy_min,
+                              double energy_max, const double *ene, int nv, rsrec_cplx *mu_n, rsrec_cplx *mu_ng,
+                              rsrec_cplx *g0);
+
+/* calculate_intersite_gf (green.f90:425-469) on the g0 the last Green-function call left on the device for the pair
+ * units: gij, gji (18,18,nv,njij) = ((g1 - g2) +- (g3 - g4)/i)/2 (g1 alone when i == j), and their spin
+ * decomposition gspin (9,9,nv,njij,8) = Ginmag, Gix, Giy, Giz, Gjnmag, Gjx, Gjy, Gjz (may be NULL).
+ * compact != 0: the units are packed (one unit for an i == j pair, four otherwise -- what the drivers above are given);
+ * compact == 0: four slots per pair as in recursion%a_b(:,:,:,4*njij) (slots 2-4 of an i == j pair are ignored). */
+int rsrec_intersite_gf(rsrec_handle h, int njij, const int32_t *pair_i, const int32_t *pair_j, int compact,
+                       rsrec_cplx *gij, rsrec_cplx *gji, rsrec_cplx *gspin);
+
 /* compute_moments_stochastic + calculate_gamma_nm + integrand of calculate_conductivity_tensor: only the diagonals
  * mu_nm(l,l,n,m,i) the integrand consumes are kept, on the device; mu_nm (18,18,M,M,nstart) is downloaded only when
  * non-NULL.  start_kind 0 = per_type (integrand_at filled), 1 = random_vec. */

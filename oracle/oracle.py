@@ -446,3 +446,19 @@ def bands_moments(g0, channels_ldos, mom, ene, edel, fermi, nv1, e1):
     L.orc_bands_moments(_p(g0), nv, int(channels_ldos), nu, _p(mom), _p(lsph), _p(ene), float(edel), float(fermi), int(nv1),
                         float(e1), _p(occ), _p(lmom))
     return occ, lmom
+
+
+def intersite_gf(g0, pairs):
+    """calculate_intersite_gf (green.f90:425-469): g0 (18,18,nv,4*njij) in the four-slot layout, pairs (njij,2)
+    -> gij, gji (18,18,nv,njij), gspin (9,9,nv,njij,8) = Ginmag, Gix, Giy, Giz, Gjnmag, Gjx, Gjy, Gjz"""
+    L = lib()
+    L.orc_intersite_gf.argtypes = [c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]
+    g0 = _f(g0, np.complex128)
+    pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+    nv, njij = g0.shape[2], len(pairs)
+    assert g0.shape[3] == 4 * njij
+    pi, pj = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+    gij = np.zeros((18, 18, nv, njij), np.complex128, order="F"); gji = np.zeros_like(gij, order="F")
+    gs = np.zeros((9, 9, nv, njij, 8), np.complex128, order="F")
+    L.orc_intersite_gf(_p(g0), nv, njij, _p(pi), _p(pj), _p(gij), _p(gji), _p(gs))
+    return gij, gji, gs

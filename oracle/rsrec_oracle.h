@@ -106,6 +106,10 @@ void orc_gamma_nm(const double *ene, int nv, int M, double energy_min, double en
 void orc_conductivity_integrand(const orc_cplx *mu_nm, int M, int nloop, const double *ene, int nv, double energy_min,
                                 double energy_max, int per_type, orc_cplx *integrand, orc_cplx *integrand_at);
 
+/* calculate_intersite_gf (green.f90:425-469): g0 (18,18,nv,4*njij) -> gij, gji (18,18,nv,njij), gspin (9,9,nv,njij,8) */
+void orc_intersite_gf(const orc_cplx *g0, int nv, int njij, const int32_t *pair_i, const int32_t *pair_j, orc_cplx *gij,
+                      orc_cplx *gji, orc_cplx *gspin);
+
 /* ---- neighbour table, rsrec_oracle_lattice.c: nncal + remd (lattice.f90:3035-3123, 2823-2907) ---- */
 int orc_build_nn(int kk, const double *crd, const int32_t *no, int ntot, const int32_t *iu, double ct, int use_pbc,
                  const int *b, const int *nrep, const double *a, double alat, int ncols, int32_t *nn, int *nm_out);

@@ -12,6 +12,7 @@
  *   get_cinf            recursion.f90:2030-2086      get_terminf         recursion.f90:2092-2138
  *   bgreen              green.f90:1191-1339          block_green         green.f90:588-621
  *   chebyshev_green     green.f90:1030-1108          jackson_kernel      math.f90:1641-1655
+ *   calculate_intersite_gf  green.f90:425-469 (block_green_ij 356-384 / chebyshev_green_ij 892-952 = the per-unit routines above)
  *   density / bprldos   density_of_states.f90:248-372 / 378-407          sgreen   green.f90:628-705
  *   calculate_gamma_nm / calculate_conductivity_tensor (integrand)  conductivity.f90:158-306, lorentz_kernel math.f90:1663-1677
  * LAPACK zgetrf/zgetri of bgreen are restated as LU with partial pivoting (izamax's |re|+|im| pivot rule) followed
@@ -465,4 +466,42 @@ void orc_conductivity_integrand(const cplx *mu_nm, int M, int nloop, const doubl
           }
   }
   free(gamma);
+}
+
+/* calculate_intersite_gf (green.f90:425-469) for njij pairs: g0 (18,18,nv,4*njij) holds the four on-site-like Green
+ * functions of each pair in its four slots (slot 1 only when i == j); gij, gji (18,18,nv,njij); gspin (9,9,nv,njij,8) =
+ * Ginmag, Gix, Giy, Giz, Gjnmag, Gjx, Gjy, Gjz */
+void orc_intersite_gf(const orc_cplx *g0, int nv, int njij, const int32_t *pair_i, const int32_t *pair_j, orc_cplx *gij,
+                      orc_cplx *gji, orc_cplx *gspin) {
+  const size_t blk = (size_t)324 * nv, sblk = (size_t)81 * nv * njij;
+  for (int ia = 0; ia < njij; ia++) {
+    const orc_cplx *g1 = g0 + blk * (4 * (size_t)ia), *g2 = g1 + blk, *g3 = g2 + blk, *g4 = g3 + blk;
+    orc_cplx *ij = gij + blk * ia, *ji = gji + blk * ia;
+    for (size_t e = 0; e < blk; e++) {
+      if (pair_i[ia] == pair_j[ia]) {
+        ij[e] = g1[e];
+        ji[e] = g1[e];
+      } else {
+        ij[e] = g1[e] - g2[e] + (1.0 / I * g3[e] - 1.0 / I * g4[e]);
+        ji[e] = g1[e] - g2[e] - (1.0 / I * g3[e] - 1.0 / I * g4[e]);
+        ij[e] = ij[e] * 0.5;
+        ji[e] = ji[e] * 0.5;
+      }
+    }
+    for (int w = 0; w < 2; w++) {
+      const orc_cplx *g = w ? ji : ij;
+      orc_cplx *nm = gspin + sblk * (4 * w) + (size_t)81 * nv * ia, *gx = nm + sblk, *gy = gx + sblk, *gz = gy + sblk;
+      for (int ie = 0; ie < nv; ie++)
+        for (int i = 0; i < 9; i++)
+          for (int j = 0; j < 9; j++) {
+            const orc_cplx uu = g[j + 18 * i + (size_t)324 * ie], dd = g[j + 9 + 18 * (i + 9) + (size_t)324 * ie];
+            const orc_cplx ud = g[j + 18 * (i + 9) + (size_t)324 * ie], du = g[j + 9 + 18 * i + (size_t)324 * ie];
+            const size_t o = j + 9 * i + (size_t)81 * ie;
+            nm[o] = (uu + dd) * 0.5;
+            gz[o] = 0.5 * (uu - dd);
+            gy[o] = 0.5 * (I * ud - I * du);
+            gx[o] = 0.5 * (ud + du);
+          }
+    }
+  }
 }

@@ -561,3 +561,44 @@ __global__ void k_add_block(double *dst, const double *src) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < BLKD) dst[t] += src[t];
 }
+
+// ---- calculate_intersite_gf (green.f90:425-469) ---------------------------------------------------------------------
+// meta[2p] = first unit of pair p in g0 (18,18,nv,nunits), meta[2p+1] = 1 when i == j (only that unit is used).
+// gij = ((g1 - g2) + (1/i g3 - 1/i g4)) / 2, gji = ((g1 - g2) - (1/i g3 - 1/i g4)) / 2
+__global__ void k_intersite_combine(const double2 *__restrict__ g0, int nv, int njij, const int32_t *__restrict__ meta,
+                                    double2 *__restrict__ gij, double2 *__restrict__ gji) {
+  const size_t total = (size_t)njij * nv * BLKC;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(t % BLKC), ie = (int)((t / BLKC) % nv), p = (int)(t / ((size_t)BLKC * nv));
+    const int u = meta[2 * p];
+    const double2 g1 = g0[((size_t)u * nv + ie) * BLKC + e];
+    if (meta[2 * p + 1]) { gij[t] = g1; gji[t] = g1; continue; }
+    const double2 g2 = g0[((size_t)(u + 1) * nv + ie) * BLKC + e], g3 = g0[((size_t)(u + 2) * nv + ie) * BLKC + e],
+                  g4 = g0[((size_t)(u + 3) * nv + ie) * BLKC + e];
+    const double2 d = c_sub(g1, g2);
+    const double2 m3 = make_double2(g3.y, -g3.x), m4 = make_double2(g4.y, -g4.x);  // (1/i) g = -i g
+    const double2 tt = c_sub(m3, m4);
+    gij[t] = c_scale(c_add(d, tt), 0.5);
+    gji[t] = c_scale(c_sub(d, tt), 0.5);
+  }
+}
+// gspin (9,9,nv,njij,8): Ginmag, Gix, Giy, Giz, Gjnmag, Gjx, Gjy, Gjz (green.f90:452-465)
+__global__ void k_intersite_pauli(const double2 *__restrict__ gij, const double2 *__restrict__ gji, int nv, int njij,
+                                  double2 *__restrict__ gspin) {
+  const size_t nblk = (size_t)njij * nv, total = nblk * 81;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(t % 81), j = e % 9, i = e / 9;
+    const size_t blk = t / 81;
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      const double2 *g = (w ? gji : gij) + blk * BLKC;
+      const double2 uu = g[j + 18 * i], dd = g[j + 9 + 18 * (i + 9)], ud = g[j + 18 * (i + 9)], du = g[j + 9 + 18 * i];
+      double2 *o = gspin + (size_t)(4 * w) * total + t;
+      o[0] = c_scale(c_add(uu, dd), 0.5);
+      o[total] = c_scale(c_add(ud, du), 0.5);                                        // x
+      const double2 iud = make_double2(-ud.y, ud.x), idu = make_double2(-du.y, du.x);  // i * g
+      o[2 * total] = c_scale(c_sub(iud, idu), 0.5);                                  // y
+      o[3 * total] = c_scale(c_sub(uu, dd), 0.5);                                    // z
+    }
+  }
+}

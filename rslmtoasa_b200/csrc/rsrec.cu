@@ -1412,8 +1412,8 @@ int rsrec_conductivity_integrand(rsrec_handle h, const cplx *mu_nm, int M, int n
 // ---- fused entry points: recursion + its consumer without a host round trip of the coefficients -----------------
 // run_recursion + run_dos of the block path (self.f90:799-856): recur_b -> zsqr -> get_terminf -> bgreen.
 // a_b, b2_b (18,18,lld,nunits; b2_b = B^2 as recur_b leaves it; either may be NULL), g0 (18,18,nv,nunits).
-int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, const double *ene, int nv, int sym_term,
-                        cplx *a_b, cplx *b2_b, cplx *g0) {
+static int recur_b_green_impl(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                             const cplx *bsign, int lld, const double *ene, int nv, int sym_term, cplx *a_b, cplx *b2_b, cplx *g0) {
   if (!h || nunits < 0 || lld < 2 || nv < 1 || !ene || (nunits > 0 && !site_i)) return fail(RSREC_EINVAL, "rsrec_recur_b_green: bad argument (need lld >= 2)");
   if (nunits == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
@@ -1424,8 +1424,8 @@ int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int l
   const size_t hs = (size_t)lld * BLKD;
   for (int u0 = 0; u0 < nunits; u0 += ub) {
     const int n = std::min(ub, nunits - u0);
-    TRY(upload_units(h, n, site_i + u0, nullptr, nullptr, nullptr));
-    TRY(plan_build(h, n, site_i + u0, nullptr));
+    TRY(upload_units(h, n, site_i + u0, site_j ? site_j + u0 : nullptr, asign ? asign + u0 : nullptr, bsign ? bsign + u0 : nullptr));
+    TRY(plan_build(h, n, site_i + u0, site_j ? site_j + u0 : nullptr));
     TRY(lanczos_batch(h, n, lld, false, a_b ? (double *)(a_b + (size_t)u0 * lld * BLKC) : nullptr,
                       b2_b ? (double *)(b2_b + (size_t)u0 * lld * BLKC) : nullptr));
     // zsqr on the device copy of the B^2 history, then the terminator and the continued fraction
@@ -1444,9 +1444,33 @@ int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int l
   return RSREC_OK;
 }
 
+int rsrec_recur_b_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, const double *ene, int nv, int sym_term,
+                        cplx *a_b, cplx *b2_b, cplx *g0) {
+  return recur_b_green_impl(h, nunits, site_i, nullptr, nullptr, nullptr, lld, ene, nv, sym_term, a_b, b2_b, g0);
+}
+// the same for pair start vectors (recur_b_ij, recursion.f90:1655-1737, + block_green_ij, green.f90:356-384)
+int rsrec_recur_b_ij_green(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                           const cplx *bsign, int lld, const double *ene, int nv, int sym_term, cplx *a_b, cplx *b2_b, cplx *g0) {
+  return recur_b_green_impl(h, nunits, site_i, site_j, asign, bsign, lld, ene, nv, sym_term, a_b, b2_b, g0);
+}
+
+static int cheb_recur_green_impl(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                                 const cplx *bsign, int lld, double energy_min, double energy_max, const double *ene, int nv,
+                                 cplx *mu_n, cplx *mu_ng, cplx *g0);
 // chebyshev_recur + chebyshev_green (recursion.f90:3057-3130 + green.f90:1030-1108): mu_n, mu_ng may be NULL.
 int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, int lld, double energy_min, double energy_max,
                            const double *ene, int nv, cplx *mu_n, cplx *mu_ng, cplx *g0) {
+  return cheb_recur_green_impl(h, nunits, site_i, nullptr, nullptr, nullptr, lld, energy_min, energy_max, ene, nv, mu_n, mu_ng, g0);
+}
+// chebyshev_recur_ij (recursion.f90:2376-2487) + chebyshev_green_ij (green.f90:892-952)
+int rsrec_cheb_recur_ij_green(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                              const cplx *bsign, int lld, double energy_min, double energy_max, const double *ene, int nv,
+                              cplx *mu_n, cplx *mu_ng, cplx *g0) {
+  return cheb_recur_green_impl(h, nunits, site_i, site_j, asign, bsign, lld, energy_min, energy_max, ene, nv, mu_n, mu_ng, g0);
+}
+static int cheb_recur_green_impl(rsrec_handle h, int nunits, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                                 const cplx *bsign, int lld, double energy_min, double energy_max, const double *ene, int nv,
+                                 cplx *mu_n, cplx *mu_ng, cplx *g0) {
   if (!h || nunits < 0 || lld < 0 || nv < 1 || !ene || energy_max == energy_min || (nunits > 0 && !site_i))
     return fail(RSREC_EINVAL, "rsrec_cheb_recur_green: bad argument");
   if (nunits == 0) return RSREC_OK;
@@ -1461,7 +1485,8 @@ int rsrec_cheb_recur_green(rsrec_handle h, int nunits, const int32_t *site_i, in
   int rc_all = RSREC_OK;
   for (int u0 = 0; u0 < nunits; u0 += ub) {
     const int n = std::min(ub, nunits - u0);
-    TRY(rsrec_cheb_begin_sites(h, n, site_i + u0, nullptr, nullptr, nullptr, lld, a, b));
+    TRY(rsrec_cheb_begin_sites(h, n, site_i + u0, site_j ? site_j + u0 : nullptr, asign ? asign + u0 : nullptr,
+                               bsign ? bsign + u0 : nullptr, lld, a, b));
     TRY(cheb_steps(h, lld));
     cplx *mu_out = mu_n ? mu_n + (size_t)u0 * (2 * lld + 2) * BLKC : nullptr;
     if (!mu_out) { mu_tmp.resize((size_t)n * (2 * lld + 2) * BLKC); mu_out = mu_tmp.data(); }  // the divergence guard reads them
@@ -1866,6 +1891,44 @@ int rsrec_profile_read(rsrec_handle h, double *total_ms, int *nlaunches) {
 long long rsrec_launch_count(rsrec_handle h) { return h ? h->launches : 0; }
 
 }  // extern "C"
+
+// ---- calculate_intersite_gf (green.f90:425-469) on the device-resident g0 of the pair units ----------------------
+extern "C" int rsrec_intersite_gf(rsrec_handle h, int njij, const int32_t *pair_i, const int32_t *pair_j, int compact, cplx *gij,
+                                  cplx *gji, cplx *gspin) {
+  if (!h || njij < 0 || !pair_i || !pair_j || !gij || !gji) return fail(RSREC_EINVAL, "rsrec_intersite_gf: bad argument");
+  if (njij == 0) return RSREC_OK;
+  std::vector<int32_t> meta(2 * (size_t)njij);  // first unit, same-site flag
+  int next = 0;
+  for (int p = 0; p < njij; p++) {
+    const int same = pair_i[p] == pair_j[p];
+    meta[2 * p] = compact ? next : 4 * p;
+    meta[2 * p + 1] = same;
+    next += compact ? (same ? 1 : 4) : 4;
+  }
+  if (h->g0_units != next || h->g0_nv < 1)
+    return fail(RSREC_EINVAL, "rsrec_intersite_gf: the device-resident g0 does not hold the units of these pairs (run a Green-function call on the pair units first)");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const int nv = h->g0_nv;
+  const size_t nblk = (size_t)njij * nv;
+  TRY(dev_alloc(h->post[5], 2 * nblk * BLKD, false));
+  TRY(dev_alloc(h->post[6], gspin ? 8 * nblk * 162 : 1, false));
+  TRY(dev_alloc(h->post[7], (2 * (size_t)njij + 1) / 2 + 1, false));
+  CUDA_TRY(cudaMemcpyAsync(h->post[7].p, meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->st));
+  double2 *d_gij = (double2 *)h->post[5].p, *d_gji = d_gij + nblk * BLKC;
+  k_intersite_combine<<<grid_for(nblk * BLKC, 256, h->sms * 16), 256, 0, h->st>>>((const double2 *)h->g0all.p, nv, njij,
+                                                                               (const int32_t *)h->post[7].p, d_gij, d_gji);
+  h->launches++;
+  if (gspin) {
+    k_intersite_pauli<<<grid_for(nblk * 81, 256, h->sms * 16), 256, 0, h->st>>>(d_gij, d_gji, nv, njij, (double2 *)h->post[6].p);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  TRY(to_host(h, gij, h->post[5].p, nblk * BLKD));
+  TRY(to_host(h, gji, h->post[5].p + nblk * BLKD, nblk * BLKD));
+  if (gspin) TRY(to_host(h, gspin, h->post[6].p, 8 * nblk * 162));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
 
 // ---- `type bands` (bands.f90): the consumers of g0 in the SCF loop, on the device-resident g0 ----------------------
 static int bands_need_g0(H *h, const char *who) {

@@ -127,6 +127,40 @@ class Green(_Consumer):
                                                   _p(rec.mu_ng) if keep_moments else None, _p(self.g0)))
         return self.g0
 
+    # -- exchange path: green%calculate_intersite_gf (green.f90:425-469) ------------------------------------------------
+    def calculate_intersite_gf(self, fused: bool = True):
+        """gij, gji (18,18,nv,njij_local) and their spin components Ginmag, Gix, Giy, Giz, Gjnmag, Gjx, Gjy, Gjz
+        (9,9,nv,njij_local) for this rank's pairs of `recursion.ijpair`, `control.recur` = 'block' | 'chebyshev'.
+        fused: the pair recursion (recur_b_ij / chebyshev_recur_ij) and the Green functions run in one call with g0 left on
+        the device; otherwise recursion.a_b / b2_b (after zsqr) or mu_n with four slots per pair are used, like the
+        reference does after run_recursion."""
+        rec = self.recursion
+        nloc, slots, (si, sj, asg, bsg) = rec._pair_units()
+        s0, _ = rec._local_units(len(rec.ijpair))
+        pairs = np.asarray(rec.ijpair[s0 - 1:s0 - 1 + nloc], dtype=np.int32).reshape(-1, 2)
+        pi, pj = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+        ene = self.ene
+        nv, lld = len(ene), self.control.lld
+        block = getattr(self.control, "recur", "block") == "block"
+        if fused:
+            n = len(si)
+            if block:
+                _lib.check(self._L.rsrec_recur_b_ij_green(self._h, n, _p(si), _p(sj), _p(asg), _p(bsg), lld, _p(ene), nv,
+                                                          int(self.sym_term), None, None, None))
+            else:
+                _lib.check(self._L.rsrec_cheb_recur_ij_green(self._h, n, _p(si), _p(sj), _p(asg), _p(bsg), lld,
+                                                             self.en.energy_min, self.en.energy_max, _p(ene), nv, None, None, None))
+        elif block:
+            self.block_green()
+        else:
+            self.chebyshev_green()
+        self.gij = np.zeros((NB, NB, nv, nloc), np.complex128, order="F")
+        self.gji = np.zeros((NB, NB, nv, nloc), np.complex128, order="F")
+        gs = np.zeros((9, 9, nv, nloc, 8), np.complex128, order="F")
+        _lib.check(self._L.rsrec_intersite_gf(self._h, nloc, _p(pi), _p(pj), int(fused), _p(self.gij), _p(self.gji), _p(gs)))
+        (self.ginmag, self.gix, self.giy, self.giz, self.gjnmag, self.gjx, self.gjy, self.gjz) = (gs[..., c] for c in range(8))
+        return self.gij, self.gji
+
     def sgreen(self, dw_l, cshi, nmdir: int = 1):
         """dw_l, cshi (18,na): potential parameters sqrt(Delta) and the band-centre shift of each atom
         (density_of_states.f90:300-304)."""

@@ -374,3 +374,62 @@ def test_kubo_diagonal_contraction_sizes(oracle_mod, M, nvec):
         ri, _ = oracle_mod.conductivity_integrand(mu, c.ene, EMIN, EMAX, False)
         assert np.array_equal(np.isnan(integ), np.isnan(ri))
         assert relerr(np.nan_to_num(integ), np.nan_to_num(ri)) < 1e-10
+
+
+# ---- exchange path: calculate_intersite_gf (green.f90:425-469) -----------------------------------------------------------
+PAIRS = np.array([[1, 2], [3, 3], [2, 9], [5, 1]], np.int32)
+
+
+def _oracle_intersite(oracle_mod, lat, ham, rec, recur, lld, ene):
+    orc = oracle_mod.Oracle(lat, ham)
+    _, slots, (si, sj, asg, bsg) = rec._pair_units()
+    n4 = 4 * len(PAIRS)
+    if recur == "block":
+        a_c, b_c = orc.lanczos_block(si, lld, site_j=sj, asign=asg, bsign=bsg)
+        g_c = oracle_mod.block_green(a_c, orc.zsqr(b_c), ene)
+    else:
+        a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+        mu_c, _ = orc.cheb_moments(si, lld, a, b, site_j=sj, asign=asg, bsign=bsg)
+        g_c = oracle_mod.chebyshev_green(mu_c, ene, EMIN, EMAX)[1]
+    g0 = np.zeros((18, 18, len(ene), n4), complex, order="F")
+    g0[..., slots] = g_c
+    return oracle_mod.intersite_gf(g0, PAIRS)
+
+
+@pytest.mark.parametrize("recur", ["block", "chebyshev"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_calculate_intersite_gf(oracle_mod, recur, fused):
+    from rslmtoasa_b200 import Green
+    lat, ham = case("bulk_hoh" if recur == "block" else "bulk")
+    lld = 8
+    rec = _rec(lat, ham, lld=lld, ijpair=PAIRS, channels=60)
+    rec.control.recur = recur
+    gr = Green(rec)
+    if not fused:                                  # the reference's staged flow: recursion results on the host, four slots per pair
+        if recur == "block":
+            rec.recur_b_ij(); rec.zsqr()
+        else:
+            rec.chebyshev_recur_ij()
+    gij, gji = gr.calculate_intersite_gf(fused=fused)
+    oij, oji, ogs = _oracle_intersite(oracle_mod, lat, ham, rec, recur, lld, gr.ene)
+    ok = np.isfinite(oij)                          # chebyshev: the mesh tail beyond |w| = 1 is NaN on both sides
+    assert ok.mean() > 0.7 and np.array_equal(np.isfinite(gij), ok)
+    tol = TOL_G if recur == "block" else TOL_SUM
+    assert relerr(gij[ok], oij[ok]) < tol and relerr(gji[ok], oji[ok]) < tol
+    mine = np.stack([gr.ginmag, gr.gix, gr.giy, gr.giz, gr.gjnmag, gr.gjx, gr.gjy, gr.gjz], axis=-1)
+    oks = np.isfinite(ogs)
+    assert relerr(mine[oks], ogs[oks]) < tol
+    # i == j pair: gij = gji = the on-site Green function of that site
+    assert np.array_equal(gij[..., 1][ok[..., 1]], gji[..., 1][ok[..., 1]])
+
+
+def test_intersite_gf_needs_matching_resident_g0(block_rec):
+    from rslmtoasa_b200 import Green, RsrecError
+    import ctypes as C
+    gr = Green(block_rec)
+    gr.block_green()                               # 4 on-site units, not pair units
+    z = np.zeros((18, 18, len(gr.ene), 3), complex, order="F")
+    pi = np.array([1, 2, 3], np.int32); pj = np.array([2, 3, 4], np.int32)
+    rc = block_rec._L.rsrec_intersite_gf(block_rec._h, 3, pi.ctypes.data_as(C.c_void_p), pj.ctypes.data_as(C.c_void_p), 1,
+                                         z.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), None)
+    assert rc == -1

@@ -207,3 +207,53 @@ def test_post_golden_vectors(oracle_mod):
     assert relerr(td, p["tdens"]) < 1e-13
     integ, integ_at = oracle_mod.conductivity_integrand(g["pbc_kubo"], ene, EMIN, EMAX, True)
     assert relerr(np.nan_to_num(integ), np.nan_to_num(p["integrand"])) < 1e-13
+
+
+def test_intersite_gf_is_the_off_diagonal_green_function(oracle_mod):
+    """calculate_intersite_gf (green.f90:425-469) pinned by physics: with the four pair start vectors (|i> + s|j>)/sqrt2,
+    s = 1, -1, i, -i, the combination ((g1 - g2) + (g3 - g4)/i)/2 is linear in the moments and must equal the Chebyshev
+    Green function of the OFF-DIAGONAL moments <i|T_n(H)|j> computed with dense matrices; gji likewise for <j|T_n|i>."""
+    from oracle import dense_check as D
+    from tests.cases import case, EMIN, EMAX
+    lat, ham = case("bulk")
+    orc = oracle_mod.Oracle(lat, ham)
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    lld, pairs = 6, np.array([[1, 2], [3, 3], [2, 9]], np.int32)
+    s = 1 / np.sqrt(2)
+    si, sj, asg, bsg, slots = [], [], [], [], []
+    for p, (i, j) in enumerate(pairs):
+        for r, sg in enumerate((1, -1, 1j, -1j)):
+            if i == j and r > 0:
+                continue
+            si.append(i); sj.append(j); slots.append(4 * p + r)
+            asg.append(1.0 if i == j else s); bsg.append(1.0 if i == j else s * sg)
+    mu_c, _ = orc.cheb_moments(si, lld, a, b, site_j=sj, asign=asg, bsign=bsg)
+    mu = np.zeros((18, 18, 2 * lld + 2, 4 * len(pairs)), complex, order="F")
+    mu[..., slots] = mu_c
+    ene = oracle_mod.e_mesh(-1.5, 1.5, 60, 0.0)[:60]
+    g0 = oracle_mod.chebyshev_green(mu, ene, EMIN, EMAX)[1]
+    gij, gji, gs = oracle_mod.intersite_gf(g0, pairs)
+    H = D.dense_hamiltonian(lat, ham)
+    Ht = (H - b * np.eye(H.shape[0])) / a
+    for p, (i, j) in enumerate(pairs):
+        Wi, Wj = D.start_block(lat, i), D.start_block(lat, j)
+        t0, t1 = Wj, Ht @ Wj
+        m_ij = np.zeros((18, 18, 2 * lld + 2, 1), complex, order="F")
+        m_ji = np.zeros_like(m_ij, order="F")
+        u0, u1 = Wi, Ht @ Wi
+        for k in range(2 * lld + 2):
+            m_ij[:, :, k, 0] = Wi.conj().T @ t0
+            m_ji[:, :, k, 0] = Wj.conj().T @ u0
+            t0, t1 = t1, 2.0 * (Ht @ t1) - t0
+            u0, u1 = u1, 2.0 * (Ht @ u1) - u0
+        want_ij = oracle_mod.chebyshev_green(m_ij, ene, EMIN, EMAX)[1][..., 0]
+        want_ji = oracle_mod.chebyshev_green(m_ji, ene, EMIN, EMAX)[1][..., 0]
+        scale = np.abs(want_ij).max()
+        assert np.abs(gij[..., p] - want_ij).max() < 1e-11 * scale, p
+        assert np.abs(gji[..., p] - want_ji).max() < 1e-11 * scale, p
+    # spin decomposition: G = Gnmag*1 + Gx*sx + Gy*sy + Gz*sz restores the 18x18 block (orbital part 9x9 each)
+    sig = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.array([[1, 0], [0, -1]])]
+    for w, g in enumerate((gij, gji)):
+        rebuilt = sum(np.einsum("st,jiep->sjtiep", sig[c], gs[..., 4 * w + c]) for c in range(4))
+        rebuilt = rebuilt.reshape(18, 18, g.shape[2], g.shape[3])
+        assert np.abs(rebuilt - g).max() < 1e-13 * np.abs(g).max()
