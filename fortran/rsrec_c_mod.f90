@@ -32,7 +32,7 @@ module rsrec_c_mod
    public :: rsrec_bands_set_g0, rsrec_bands_get_g0, rsrec_bands_g0_shape, rsrec_bands_dos, rsrec_bands_fermi
    public :: rsrec_bands_magnetic_moments, rsrec_bands_moments, rsrec_bands_band_energy
    ! exchange path: pair-unit fused drivers and calculate_intersite_gf
-   public :: rsrec_recur_b_ij_green, rsrec_cheb_recur_ij_green, rsrec_intersite_gf
+   public :: rsrec_recur_b_ij_green, rsrec_cheb_recur_ij_green, rsrec_intersite_gf, rsrec_conductivity_cumulative
 
    interface
       function rsrec_last_error() bind(C, name='rsrec_last_error') result(msg)
@@ -487,6 +487,18 @@ module rsrec_c_mod
          integer(c_int), value :: njij, compact
          integer(c_int32_t), intent(in) :: pair_i(*), pair_j(*)
          complex(c_double_complex), intent(out) :: gij(18, 18, *), gji(18, 18, *)
+         integer(c_int) :: rc
+      end function
+
+      ! tail of calculate_conductivity_tensor (conductivity.f90:300-372): sigma(2,19,nv,1+nat); integrand_at may be c_null_ptr
+      function rsrec_conductivity_cumulative(h, integrand, integrand_at, nv, nv1, nat, wstep, loop_over, sigma) &
+         bind(C, name='rsrec_conductivity_cumulative') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h, integrand_at
+         complex(c_double_complex), intent(in) :: integrand(18, *)
+         integer(c_int), value :: nv, nv1, nat, loop_over
+         real(c_double), value :: wstep
+         real(c_double), intent(out) :: sigma(2, 19, nv, *)
          integer(c_int) :: rc
       end function
 

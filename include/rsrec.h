@@ -191,6 +191,16 @@ int rsrec_conductivity_integrand(rsrec_handle h, const rsrec_cplx *mu_nm, int M,
                                  double energy_min, double energy_max, int per_type, rsrec_cplx *integrand,
                                  rsrec_cplx *integrand_at);
 
+/* Tail of calculate_conductivity_tensor (conductivity.f90:300-372): for every mesh energy i the T = 0 Fermi-weighted
+ * Simpson integral (simpson_f, math.f90:1600-1632, kBT = 1e-15, E_F = wscale(i)) of the integrand -- the sigma(E_F)
+ * curves written to cond_total*.out / <symbol>_cond*.out.  The reference's O(nv^2) loop (one exp per term) is a running
+ * sum: one pass per series, added in the reference's order (bit-identical).  integrand (18,nv), integrand_at
+ * (18,nv,nat) from rsrec_conductivity_integrand / rsrec_kubo_conductivity (nat = 0: no per-type output); nv1 = en%nv1;
+ * wstep = wscale(2) - wscale(1); sigma (2,19,nv,1+nat): (re|im, total then orbital l2 = 1..18, energy, summed | type);
+ * the summed block is divided by real(loop_over) as in the file output, the per-type blocks are not. */
+int rsrec_conductivity_cumulative(rsrec_handle h, const rsrec_cplx *integrand, const rsrec_cplx *integrand_at, int nv,
+                                  int nv1, int nat, double wstep, int loop_over, double *sigma);
+
 /* ---- fused entry points: a recursion and its consumer with the coefficients staying on the device ---- */
 
 /* run_recursion + run_dos of the block path (self.f90:799-856): recur_b -> zsqr -> get_terminf -> bgreen(eta=0).

@@ -462,3 +462,18 @@ def intersite_gf(g0, pairs):
     gs = np.zeros((9, 9, nv, njij, 8), np.complex128, order="F")
     L.orc_intersite_gf(_p(g0), nv, njij, _p(pi), _p(pj), _p(gij), _p(gji), _p(gs))
     return gij, gji, gs
+
+
+def conductivity_cumulative(integrand, integrand_at, nv1, wscale, loop_over):
+    """tail of calculate_conductivity_tensor (conductivity.f90:300-372), the literal O(nv^2) simpson_f loop:
+    integrand (18,nv), integrand_at (18,nv,nat) or None -> sigma (2,19,nv,1+nat)"""
+    L = lib()
+    L.orc_conductivity_cumulative.argtypes = [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]
+    integrand = _f(integrand, np.complex128)
+    nv = integrand.shape[1]
+    nat = 0 if integrand_at is None else integrand_at.shape[2]
+    iat = None if integrand_at is None else _f(integrand_at, np.complex128)
+    ws = np.ascontiguousarray(wscale, dtype=np.float64)
+    sigma = np.zeros((2, 19, nv, 1 + nat), order="F")
+    L.orc_conductivity_cumulative(_p(integrand), _p(iat) if nat else None, nv, int(nv1), nat, _p(ws), int(loop_over), _p(sigma))
+    return sigma

@@ -106,6 +106,9 @@ void orc_gamma_nm(const double *ene, int nv, int M, double energy_min, double en
 void orc_conductivity_integrand(const orc_cplx *mu_nm, int M, int nloop, const double *ene, int nv, double energy_min,
                                 double energy_max, int per_type, orc_cplx *integrand, orc_cplx *integrand_at);
 
+/* tail of calculate_conductivity_tensor (conductivity.f90:300-372), literal O(nv^2) simpson_f loop; sigma (2,19,nv,1+nat) */
+void orc_conductivity_cumulative(const orc_cplx *integrand, const orc_cplx *integrand_at, int nv, int nv1, int nat,
+                                 const double *wscale, int loop_over, double *sigma);
 /* calculate_intersite_gf (green.f90:425-469): g0 (18,18,nv,4*njij) -> gij, gji (18,18,nv,njij), gspin (9,9,nv,njij,8) */
 void orc_intersite_gf(const orc_cplx *g0, int nv, int njij, const int32_t *pair_i, const int32_t *pair_j, orc_cplx *gij,
                       orc_cplx *gji, orc_cplx *gspin);

@@ -505,3 +505,42 @@ void orc_intersite_gf(const orc_cplx *g0, int nv, int njij, const int32_t *pair_
     }
   }
 }
+
+/* fermifun (math.f90:994-1000) and simpson_f with fermi = .true. (math.f90:1600-1632), literal.  The reference declares
+ * Y, Ene with NPTS+10 elements while the caller's arrays hold NPTS+9 (conductivity.f90:312): the last panel reads one
+ * element past the end.  Here that element is y = 0 at the next mesh energy (its Fermi factor is 0 for every E_F on the
+ * mesh, so any finite stray value would not contribute either). */
+static double fermifun(double e, double ef, double kbt) { return 1.0 / (exp((e - ef) / kbt) + 1.0); }
+static double simpson_f_fermi(const double *ene, double ef, int npts, const double *y, int nv, double temp) {
+  const double kB = 0.633362019e-5;
+  const double h = ene[1] - ene[0], kbt = kB * temp + 1.0e-15;
+  double aint = 0.0;
+  for (int i = 2; i <= npts + 9; i += 2) {
+    const double yp = i + 1 <= nv ? y[i] : 0.0, ep = i + 1 <= nv ? ene[i] : ene[nv - 1] + h * (i + 1 - nv);
+    aint = aint + y[i - 2] * fermifun(ene[i - 2], ef, kbt) + 4.0 * y[i - 1] * fermifun(ene[i - 1], ef, kbt) + yp * fermifun(ep, ef, kbt);
+  }
+  return h * aint / 3.0;
+}
+/* tail of calculate_conductivity_tensor (conductivity.f90:300-372): integrand (18,nv) = integrand(l2,l2,:), integrand_at
+ * (18,nv,nat); wscale (nv); sigma (2,19,nv,1+nat) as written to the cond_*.out files (summed block / real(loop_over)) */
+void orc_conductivity_cumulative(const orc_cplx *integrand, const orc_cplx *integrand_at, int nv, int nv1, int nat,
+                                 const double *wscale, int loop_over, double *sigma) {
+  double *tr = (double *)malloc(sizeof(double) * 38 * (size_t)nv);  /* series-major copies: [2*s + c][nv] */
+  for (int g = 0; g <= nat; g++) {
+    const orc_cplx *src = g == 0 ? integrand : integrand_at + (size_t)18 * nv * (g - 1);
+    for (int i = 0; i < nv; i++) { tr[i] = 0.0; tr[nv + i] = 0.0; }
+    for (int l2 = 0; l2 < 18; l2++)
+      for (int i = 0; i < nv; i++) {
+        tr[i] = tr[i] + creal(src[l2 + 18 * (size_t)i]);
+        tr[nv + i] = tr[nv + i] + cimag(src[l2 + 18 * (size_t)i]);
+        tr[(size_t)(2 * (l2 + 1)) * nv + i] = creal(src[l2 + 18 * (size_t)i]);
+        tr[(size_t)(2 * (l2 + 1) + 1) * nv + i] = cimag(src[l2 + 18 * (size_t)i]);
+      }
+    const double div = g == 0 ? (double)(float)loop_over : 1.0;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int i = 0; i < nv; i++)
+      for (int sc = 0; sc < 38; sc++)
+        sigma[sc + 38 * ((size_t)i + (size_t)nv * g)] = simpson_f_fermi(wscale, wscale[i], nv1, tr + (size_t)sc * nv, nv, 0.0) / div;
+  }
+  free(tr);
+}

@@ -22,7 +22,7 @@ SYMBOLS = [
     "rsrec_lanczos_block_local_axis", "rsrec_set_positions",
     "rsrec_bands_set_g0", "rsrec_bands_get_g0", "rsrec_bands_g0_shape", "rsrec_bands_dos", "rsrec_bands_fermi",
     "rsrec_bands_magnetic_moments", "rsrec_bands_moments", "rsrec_bands_band_energy",
-    "rsrec_recur_b_ij_green", "rsrec_cheb_recur_ij_green", "rsrec_intersite_gf",
+    "rsrec_recur_b_ij_green", "rsrec_cheb_recur_ij_green", "rsrec_intersite_gf", "rsrec_conductivity_cumulative",
 ]
 
 
@@ -95,6 +95,7 @@ def load():
     L.rsrec_recur_b_ij_green.argtypes = [vp, i, vp, vp, vp, vp, i, vp, i, i, vp, vp, vp]
     L.rsrec_cheb_recur_ij_green.argtypes = [vp, i, vp, vp, vp, vp, i, d, d, vp, i, vp, vp, vp]
     L.rsrec_intersite_gf.argtypes = [vp, i, vp, vp, i, vp, vp, vp]
+    L.rsrec_conductivity_cumulative.argtypes = [vp, vp, vp, i, i, i, d, i, vp]
     L.rsrec_bands_set_g0.argtypes = [vp, vp, i, i]
     L.rsrec_bands_get_g0.argtypes = [vp, vp]
     L.rsrec_bands_g0_shape.argtypes = [vp, C.POINTER(i), C.POINTER(i)]

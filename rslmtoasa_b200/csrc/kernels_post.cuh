@@ -602,3 +602,56 @@ __global__ void k_intersite_pauli(const double2 *__restrict__ gij, const double2
     }
   }
 }
+
+// ---- tail of calculate_conductivity_tensor (conductivity.f90:300-372) ------------------------------------------------
+// For every mesh energy i the reference integrates each integrand series with simpson_f (math.f90:1600-1632) using the
+// Fermi function at T = 0 (kBT = 1e-15) and E_F = wscale(i): f = 1 below, 1/2 at, 0 above the point, so the O(nv^2)
+// loop with an exp per term is a running Simpson sum.  One thread per series walks the panels once, adding them in the
+// reference's order (bit-identical to the literal loop); the boundary panel(s) are evaluated with the reference's
+// grouping  (Y(I-1) f + 4 Y(I) f) + Y(I+1) f.  Series: s = 0 total, 1..18 orbital l2; component c = re / im;
+// block g = 0 the summed integrand, 1..nat the per-type ones.  The term Y(nv+1) the reference reads one past the end
+// of the arrays always carries f = 0 and is dropped.
+//   integrand (18,nv) complex, integrand_at (18,nv,nat) complex; out: ((19 series, 2 comps), nv, 1+nat), divided by
+//   `div` for g = 0 (real(loop_over)) and not for g > 0, as written to the cond_*.out files.
+__global__ void k_cond_cumulative(const double2 *__restrict__ integrand, const double2 *__restrict__ integrand_at, int nv, int npts9,
+                                  int nat, double h, double div, double *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nser = 38;
+  if (t >= nser * (1 + nat)) return;
+  const int g = t / nser, sc = t % nser, s = sc >> 1, c = sc & 1;
+  const double2 *src = g == 0 ? integrand : integrand_at + (size_t)(g - 1) * 18 * nv;
+  auto Y = [&](int j) {  // 1-based mesh index
+    if (j > nv) return 0.0;
+    if (s > 0) { const double2 v = __ldg(src + (s - 1) + 18 * (size_t)(j - 1)); return c ? v.y : v.x; }
+    double a = 0.0;
+    for (int l = 0; l < 18; l++) { const double2 v = __ldg(src + l + 18 * (size_t)(j - 1)); a = __dadd_rn(a, c ? v.y : v.x); }
+    return a;
+  };
+  double *o = out + ((size_t)g * nv) * nser + sc;  // out[(g*nv + (i-1))*38 + sc]
+  const double d = g == 0 ? div : 1.0;
+  // the literal loop multiplies EVERY point by its Fermi factor: a non-finite Y(j) above E_F gives NaN * 0 = NaN, so
+  // one non-finite sample makes every integral NaN
+  bool bad = false;
+  for (int j = 1; j <= min(nv, npts9 + 1); j++) bad |= !isfinite(Y(j));
+  if (bad) {
+    for (int i = 0; i < nv; i++) o[(size_t)i * nser] = nan("");
+    return;
+  }
+  auto fin = [&](double aint) { return __ddiv_rn(__ddiv_rn(__dmul_rn(h, aint), 3.0), d); };
+  double P = 0.0;    // the panels I = 2, 4, .. that lie fully below the Fermi point, added term by term like the reference
+  double ym = Y(1);  // Y(I-1) of the current panel
+  o[0] = fin(__dmul_rn(ym, 0.5));
+  for (int I = 2; I <= npts9; I += 2) {
+    const double y0 = Y(I), yp = Y(I + 1);
+    const double A = __dadd_rn(P, ym);
+    if (I <= nv) o[(size_t)(I - 1) * nser] = fin(__dadd_rn(A, __dmul_rn(__dmul_rn(4.0, y0), 0.5)));   // E_F at the even point I
+    const double F = __dadd_rn(A, __dmul_rn(4.0, y0));
+    if (I + 1 <= nv) {                                                                              // E_F at the odd point I+1
+      double B = __dadd_rn(F, __dmul_rn(yp, 0.5));
+      if (I + 2 <= npts9) B = __dadd_rn(B, __dmul_rn(yp, 0.5));
+      o[(size_t)I * nser] = fin(B);
+    }
+    P = __dadd_rn(F, yp);
+    ym = yp;
+  }
+}

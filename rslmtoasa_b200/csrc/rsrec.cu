@@ -1892,6 +1892,29 @@ long long rsrec_launch_count(rsrec_handle h) { return h ? h->launches : 0; }
 
 }  // extern "C"
 
+// tail of calculate_conductivity_tensor (conductivity.f90:300-372): the T = 0 Fermi-weighted Simpson integrals of the
+// integrand up to every mesh energy.  integrand (18,nv), integrand_at (18,nv,nat) (nat = 0: none);
+// sigma (2,19,nv,1+nat): (re|im, total|orbital l2, energy, summed|per type); the summed block is divided by loop_over.
+extern "C" int rsrec_conductivity_cumulative(rsrec_handle h, const cplx *integrand, const cplx *integrand_at, int nv, int nv1, int nat,
+                                             double wstep, int loop_over, double *sigma) {
+  if (!h || !integrand || nv < 3 || nv1 < 1 || nv1 + 9 > nv + 1 || nat < 0 || (nat > 0 && !integrand_at) || loop_over < 1 || !sigma)
+    return fail(RSREC_EINVAL, "rsrec_conductivity_cumulative: bad argument (need nv1 + 9 <= nv + 1)");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(to_dev(h, h->post[0], integrand, (size_t)36 * nv));
+  if (nat) TRY(to_dev(h, h->post[1], integrand_at, (size_t)36 * nv * nat));
+  const size_t nout = (size_t)38 * nv * (1 + nat);
+  TRY(dev_alloc(h->post[2], nout, false));
+  CUDA_TRY(cudaMemsetAsync(h->post[2].p, 0, nout * sizeof(double), h->st));
+  const int nthr = 38 * (1 + nat);
+  k_cond_cumulative<<<(nthr + 63) / 64, 64, 0, h->st>>>((const double2 *)h->post[0].p, nat ? (const double2 *)h->post[1].p : nullptr, nv,
+                                                       nv1 + 9, nat, wstep, (double)(float)loop_over, h->post[2].p);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  TRY(to_host(h, sigma, h->post[2].p, nout));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
 // ---- calculate_intersite_gf (green.f90:425-469) on the device-resident g0 of the pair units ----------------------
 extern "C" int rsrec_intersite_gf(rsrec_handle h, int njij, const int32_t *pair_i, const int32_t *pair_j, int compact, cplx *gij,
                                   cplx *gji, cplx *gspin) {

@@ -223,6 +223,23 @@ class Conductivity(_Consumer):
                                                         _p(self.integrand_at)))
         return self.integrand, self.integrand_at
 
+    def integrate_conductivity(self):
+        """tail of calculate_conductivity_tensor (conductivity.f90:300-372): sigma(E_F) for every mesh energy from
+        self.integrand / self.integrand_at -> self.sigma (2,19,nv,1+nat): (re|im, total|orbital, energy, summed|per type),
+        the numbers the reference writes to cond_total*.out and <symbol>_cond*.out."""
+        ene = self.ene
+        a, b = self.en.scale_shift()
+        ws = (ene - b) / a
+        per_type = self.control.cond_calctype == "per_type"
+        nat = self.integrand_at.shape[2] if per_type else 0
+        loop_over = self.integrand_at.shape[2]
+        integ = _f(self.integrand, np.complex128)
+        iat = _f(self.integrand_at, np.complex128) if nat else None
+        self.sigma = np.zeros((2, 19, len(ene), 1 + nat), order="F")
+        _lib.check(self._L.rsrec_conductivity_cumulative(self._h, _p(integ), _p(iat), len(ene), self.en.nv1, nat,
+                                                         float(ws[1] - ws[0]), loop_over, _p(self.sigma)))
+        return self.sigma
+
     def compute_conductivity(self, keep_moments: bool = False):
         """compute_moments_stochastic + calculate_conductivity_tensor's integrand in one call; only the diagonals of
         mu_nm_stochastic the integrand consumes are kept (on the device) unless keep_moments is set."""

@@ -433,3 +433,27 @@ def test_intersite_gf_needs_matching_resident_g0(block_rec):
     rc = block_rec._L.rsrec_intersite_gf(block_rec._h, 3, pi.ctypes.data_as(C.c_void_p), pj.ctypes.data_as(C.c_void_p), 1,
                                          z.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), None)
     assert rc == -1
+
+
+def test_conductivity_cumulative_bit_exact(oracle_mod, block_rec):
+    """tail of calculate_conductivity_tensor: the running-sum kernel == the literal O(nv^2) simpson_f loop, bit for bit"""
+    from rslmtoasa_b200 import Conductivity
+    cond = Conductivity(block_rec)
+    en = block_rec.en
+    nv = len(cond.ene)
+    rng = np.random.default_rng(17)
+    cond.integrand = np.asfortranarray(rng.standard_normal((18, nv)) + 1j * rng.standard_normal((18, nv)))
+    cond.integrand_at = np.asfortranarray(rng.standard_normal((18, nv, 3)) + 1j * rng.standard_normal((18, nv, 3)))
+    a, b = en.scale_shift()
+    ws = (cond.ene - b) / a
+    for calctype in ("per_type", "random_vec"):
+        block_rec.control.cond_calctype = calctype
+        sig = cond.integrate_conductivity()
+        ref = oracle_mod.conductivity_cumulative(cond.integrand, cond.integrand_at if calctype == "per_type" else None, en.nv1, ws, 3)
+        assert sig.shape == ref.shape and np.array_equal(sig, ref)
+    block_rec.control.cond_calctype = "per_type"
+    # a non-finite sample poisons every integral of its series in the literal loop (NaN * 0): same here
+    cond.integrand[4, 10] = np.nan
+    sig = cond.integrate_conductivity()
+    assert np.isnan(sig[0, 0, :, 0]).all() and np.isnan(sig[0, 5, :, 0]).all()          # real total, real orbital l2 = 5
+    assert np.isfinite(sig[1, :, :, 0]).all() and np.isfinite(sig[:, 3, :, 0]).all()      # imaginary parts, other orbitals

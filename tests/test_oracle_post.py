@@ -257,3 +257,35 @@ def test_intersite_gf_is_the_off_diagonal_green_function(oracle_mod):
         rebuilt = sum(np.einsum("st,jiep->sjtiep", sig[c], gs[..., 4 * w + c]) for c in range(4))
         rebuilt = rebuilt.reshape(18, 18, g.shape[2], g.shape[3])
         assert np.abs(rebuilt - g).max() < 1e-13 * np.abs(g).max()
+
+
+def test_conductivity_cumulative_is_a_running_simpson_sum(oracle_mod):
+    """the literal simpson_f loop of calculate_conductivity_tensor (one exp per term, O(nv^2)) against the closed form:
+    at T = 0 the Fermi factor is 1 below, 1/2 at and 0 above E_F, so sigma(i) = h/3 (sum_{j<i} W_j Y_j + W_i Y_i / 2) with
+    the composite Simpson weights W = 1,4,2,4,..."""
+    m = oracle_mod.e_mesh_full(-1.0, 1.0, 80, 0.1)
+    ene, nv, nv1 = m["ene"], len(m["ene"]), m["nv1"]
+    a, b = oracle_mod.cheb_scale(-1.0, 1.0)
+    ws = (ene - b) / a
+    rng = np.random.default_rng(5)
+    integ = np.asfortranarray(rng.standard_normal((18, nv)) + 1j * rng.standard_normal((18, nv)))
+    integ_at = np.asfortranarray(rng.standard_normal((18, nv, 2)) + 1j * rng.standard_normal((18, nv, 2)))
+    sig = oracle_mod.conductivity_cumulative(integ, integ_at, nv1, ws, 3)
+    W = np.ones(nv); W[1::2] = 4.0; W[2::2] = 2.0
+    h = ws[1] - ws[0]
+
+    def closed(y):
+        wy = W * y
+        return h / 3.0 * (np.concatenate([[0.0], np.cumsum(wy)[:-1]]) + 0.5 * wy)
+    for g, src, div in ((0, integ, 3.0), (1, integ_at[..., 0], 1.0), (2, integ_at[..., 1], 1.0)):
+        for c, part in ((0, src.real), (1, src.imag)):
+            assert np.allclose(sig[c, 0, :, g], closed(part.sum(axis=0)) / div, rtol=1e-12, atol=1e-13)
+            for l2 in (0, 7, 17):
+                assert np.allclose(sig[c, 1 + l2, :, g], closed(part[l2]) / div, rtol=1e-12, atol=1e-13)
+    # physical reading: for a smooth integrand sigma(E_F) is its integral from the bottom of the mesh up to E_F
+    y = np.exp(-ws ** 2)
+    smooth = np.asfortranarray(np.tile(y / 18.0, (18, 1)).astype(complex))
+    s2 = oracle_mod.conductivity_cumulative(smooth, None, nv1, ws, 1)
+    from math import erf, sqrt, pi
+    exact = np.array([sqrt(pi) / 2 * (erf(w) - erf(ws[0])) for w in ws])
+    assert np.abs(s2[0, 0, 2::2, 0] - exact[2::2]).max() < 1e-6       # odd (1-based) points close whole Simpson panels
