@@ -180,7 +180,11 @@ __global__ void k_terminf_fix(double *a_inf, double *b_inf, double *a_inf0, doub
 }
 
 // ---- block continued fraction (bgreen) ------------------------------------------------------------------------
+// Two geometries: 8 warps per CTA (128 registers, 16 warps per SM) and 9 warps per CTA (<= 113 registers, a little more
+// spilling, 18 warps per SM).  A chain is one warp's sequential work, so what counts is the number of ROUNDS the grid
+// needs: the standard mesh of one atom (2510 energies) is 1.06 rounds of 148 x 16 warps but 0.94 of 148 x 18.
 #define BG_WARPS 8
+#define BG_WARPS_WIDE 9
 #ifndef BG_MINB
 #define BG_MINB 2
 #endif
@@ -190,7 +194,8 @@ __global__ void k_terminf_fix(double *a_inf, double *b_inf, double *a_inf0, doub
 
 // a_b, b_b: (18,18,ll,na) complex, b_b = B (after zsqr); g: (18,18,nv,na).  Channels ie0..ie0+ie_len-1 (0-based) are
 // written, the rest of g is left untouched (the caller zeroes it, like bgreen's g_out = 0).
-__global__ void __launch_bounds__(BG_WARPS * 32, BG_MINB)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, BG_MINB)
 k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int ll, const double *__restrict__ ene,
          int nv, int ie0, int ie_len, const double *__restrict__ a_inf, const double *__restrict__ b_inf, double eta_re,
          double eta_im, int sym_term, double2 *__restrict__ g) {
@@ -198,7 +203,7 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
   double2 *sA = bg_smem, *sB = bg_smem + BG_MAT, *Q = bg_smem + 2 * BG_MAT + (threadIdx.x >> 5) * BG_WSTRIDE;
   double2 *dinv = Q + BG_MAT;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, unit = blockIdx.y;
-  const int iel = blockIdx.x * BG_WARPS + warp;
+  const int iel = blockIdx.x * NW + warp;
   const bool live = iel < ie_len;
   const int ei = ie0 + (live ? iel : ie_len - 1);
   const bool act = lane < NB;
@@ -227,7 +232,7 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
   const double2 P = en != 0.0 ? make_double2(en + eta_re, eta_im) : make_double2(en, 0.0);
   for (int l = ll - 1; l >= 1; l--) {
     __syncthreads();  // every warp is done with the previous level's B
-    for (int t = threadIdx.x; t < BLKC; t += BG_WARPS * 32) {
+    for (int t = threadIdx.x; t < BLKC; t += NW * 32) {
       sA[(t / NB) * BG_LD + t % NB] = au[(size_t)(l - 1) * BLKC + t];
       sB[(t / NB) * BG_LD + t % NB] = bu[(size_t)(l - 1) * BLKC + t];
     }

@@ -1098,9 +1098,11 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
 // Consumers either side of the hot path: terminator, block / Chebyshev Green functions,
 // scalar continued fraction, Kubo-Bastin integrand.  d_* functions work on device arrays (so that the fused entry
 // points can chain them behind a recursion without a host round trip); the rsrec_* wrappers marshal host arrays.
+static int bgreen_smem(int nw) { return (2 * BG_MAT + nw * BG_WSTRIDE) * (int)sizeof(double2); }
 static int post_configure() {
-  const int smem = (2 * BG_MAT + BG_WARPS * BG_WSTRIDE) * (int)sizeof(double2);
-  return cudaFuncSetAttribute(k_bgreen, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess ? 0 : -1;
+  if (cudaFuncSetAttribute(k_bgreen<BG_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bgreen_smem(BG_WARPS)) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_bgreen<BG_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bgreen_smem(BG_WARPS_WIDE)) != cudaSuccess) return -1;
+  return 0;
 }
 static int to_dev(H *h, DevBuf &b, const void *src, size_t ndoubles) {
   TRY(dev_alloc(b, std::max<size_t>(ndoubles, 1), false));
@@ -1151,10 +1153,18 @@ static int d_bgreen(H *h, const double *d_ab, const double *d_bb, int ll, int na
                     double *d_g) {
   CUDA_TRY(cudaMemsetAsync(d_g, 0, (size_t)na * nv * BLKD * sizeof(double), h->st));
   if (ie_len <= 0) return RSREC_OK;
-  const int smem = (2 * BG_MAT + BG_WARPS * BG_WSTRIDE) * (int)sizeof(double2);
-  k_bgreen<<<dim3((ie_len + BG_WARPS - 1) / BG_WARPS, na), BG_WARPS * 32, smem, h->st>>>(
-      (const double2 *)d_ab, (const double2 *)d_bb, ll, d_ene, nv, ie0, ie_len, d_ainf, d_binf, eta_re, eta_im, sym_term,
-      (double2 *)d_g);
+  // rounds of resident warps each geometry needs (2 CTAs per SM); the wide one pays 10-17 % per chain for its spills (measured)
+  auto rounds = [&](int nw) { return ((long long)((ie_len + nw - 1) / nw) * na + 2LL * h->sms - 1) / (2LL * h->sms); };
+  const char *force = getenv("RSREC_BGREEN_WARPS");
+  const bool wide = force ? atoi(force) == BG_WARPS_WIDE : 117 * rounds(BG_WARPS_WIDE) < 100 * rounds(BG_WARPS);
+  if (wide)
+    k_bgreen<BG_WARPS_WIDE><<<dim3((ie_len + BG_WARPS_WIDE - 1) / BG_WARPS_WIDE, na), BG_WARPS_WIDE * 32, bgreen_smem(BG_WARPS_WIDE), h->st>>>(
+        (const double2 *)d_ab, (const double2 *)d_bb, ll, d_ene, nv, ie0, ie_len, d_ainf, d_binf, eta_re, eta_im, sym_term,
+        (double2 *)d_g);
+  else
+    k_bgreen<BG_WARPS><<<dim3((ie_len + BG_WARPS - 1) / BG_WARPS, na), BG_WARPS * 32, bgreen_smem(BG_WARPS), h->st>>>(
+        (const double2 *)d_ab, (const double2 *)d_bb, ll, d_ene, nv, ie0, ie_len, d_ainf, d_binf, eta_re, eta_im, sym_term,
+        (double2 *)d_g);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return RSREC_OK;

@@ -19,5 +19,16 @@ else:
     ham = S.make_hamiltonian(lat, seed=20260102)
 rec = Recursion(ham, lat, Control(lld=21), Energy(-2.0, 2.0, channels_ldos=channels, fermi=0.0))
 g = Green(rec)
-g.recur_b_green()
-print("done", cfg, "launches", rec.launch_count, "g0", g.g0.shape)
+if "--bands" in sys.argv:      # the whole SCF iteration: g0 stays on the device, the `bands` consumers run there
+    from rslmtoasa_b200.bands import Bands
+    import time
+    for rep in range(2):
+        t0 = time.perf_counter()
+        g.recur_b_green(download_g0=False)
+        rec.en.fermi = 0.0
+        b = Bands(g, qqv=6.0 * len(lat.irec))
+        b.calculate_fermi(); b.calculate_magnetic_moments(); b.calculate_moments(); b.calculate_band_energy()
+        print("scf step", rep, time.perf_counter() - t0, "s  fermi", rec.en.fermi, "eband", b.eband)
+else:
+    g.recur_b_green()
+    print("done", cfg, "launches", rec.launch_count, "g0", g.g0.shape)
