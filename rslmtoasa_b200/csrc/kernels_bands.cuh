@@ -110,7 +110,13 @@ __device__ void bands_fermi_scan(double &ef, double h, int &ik1, double ainf, in
 
 // the two calls of calculate_fermi (bands.f90:327-334): res = {fermi, e1, nv1, ifail}
 __global__ void k_bands_fermi(const double *__restrict__ dtot, int npts, double h, double ainf, double qqv, double fermi_in, int ik1_in,
-                              double *__restrict__ res) {
+                              double *__restrict__ res, int use_smem) {
+  extern __shared__ double fm_smem[];
+  if (use_smem) {  // the scan is one thread's dependent chain: feed it from shared memory, not from L2
+    for (int i = threadIdx.x; i < npts; i += blockDim.x) fm_smem[i] = dtot[i];
+    __syncthreads();
+    dtot = fm_smem;
+  }
   if (blockIdx.x || threadIdx.x) return;
   double ef_mag = fermi_in, e1_mag = fermi_in, ef = fermi_in;
   int ik1_mag = 0, ik1 = ik1_in, ifail = 1;

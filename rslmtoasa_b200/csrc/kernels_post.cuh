@@ -51,16 +51,36 @@ struct BpoptChain {
   long long ls;
   int n;  // = ll - 1
   double ainf;
-  __device__ __forceinline__ double az(int i) const {
+  // optional per-thread copies in shared memory (element i of this thread at s?z[i * sstride]): the Sturm counts read
+  // every coefficient ~50 times per emami call, and from global memory each read is a dependent L1/L2 access
+  double *saz = nullptr, *sbz = nullptr;
+  int sstride = 0;
+  __device__ __forceinline__ double az_g(int i) const {
     const double d = __dsub_rn(__ldg(a + (long long)(i - 1) * ls), ainf);
     return i == n ? d : __dmul_rn(0.5, d);
   }
-  __device__ __forceinline__ double bz(int i) const {  // emami's B: B(1) = 0, B(n+1) = 0
+  __device__ __forceinline__ double bz_g(int i) const {  // emami's B: B(1) = 0, B(n+1) = 0
     if (i <= 1 || i > n) return 0.0;
     const double r = __ldg(rb + (long long)(i - 1) * ls);
     return i == n ? __dmul_rn(0.70710678118654746 /* 1/sqrt(2) as the reference's double expression */, r) : __dmul_rn(0.5, r);
   }
+  __device__ __forceinline__ void stage() {  // after every change of ainf
+    if (!saz) return;
+    for (int i = 1; i <= n + 1; i++) {
+      if (i <= n) saz[i * sstride] = az_g(i);
+      sbz[i * sstride] = bz_g(i);
+    }
+  }
+  __device__ __forceinline__ double az(int i) const { return saz ? saz[i * sstride] : az_g(i); }
+  __device__ __forceinline__ double bz(int i) const { return sbz ? sbz[i * sstride] : bz_g(i); }
+  // shared-memory carve-up for a CTA of nthreads: [2][n + 2][nthreads] doubles
+  __device__ __forceinline__ void attach(double *smem, int nthreads, int tid) {
+    saz = smem + tid;
+    sbz = smem + (size_t)(n + 2) * nthreads + tid;
+    sstride = nthreads;
+  }
 };
+static inline size_t bpopt_smem_bytes(int ll, int nthreads) { return (size_t)2 * (ll + 1) * nthreads * sizeof(double); }
 
 __device__ inline int sturm_count(const BpoptChain &c, double e) {
   const double relfeh = 1.8189894035458565e-12;  // 2^-39
@@ -114,16 +134,19 @@ __device__ inline void dev_emami(const BpoptChain &c, double &emax_o, double &em
 
 // bpopt (recursion.f90:3540-3581) for nchains independent chains
 __global__ void k_bpopt(const double *A, const double *RB, ChainLayout lay, int ll, int nchains, double *ainf_o,
-                        double *rbinf_o, int *ifail_o) {
+                        double *rbinf_o, int *ifail_o, int use_smem) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= nchains) return;
   const long long off = (ch / lay.inner) * lay.outer_stride + (ch % lay.inner) * lay.inner_stride;
+  extern __shared__ double bp_smem[];
   BpoptChain c;
   c.a = A + off; c.rb = RB + off; c.ls = lay.lstride; c.n = ll - 1;
   c.ainf = __ldg(c.a + (long long)(c.n - 1) * c.ls);  // AINF = A(N)
+  if (use_smem) c.attach(bp_smem, blockDim.x, threadIdx.x);
   double bmax = 0.0, bmin = 0.0;
   int ifail = 0;
   for (int jiter = 1;; jiter++) {
+    c.stage();
     dev_emami(c, bmax, bmin);
     const double s = __dadd_rn(bmax, bmin);
     c.ainf = __dadd_rn(c.ainf, s);
@@ -137,15 +160,18 @@ __global__ void k_bpopt(const double *A, const double *RB, ChainLayout lay, int 
 
 // the 18 diagonal chains of each unit only: chain c = (i, unit), results written to element (i,i) of a_inf/b_inf
 __global__ void k_bpopt_diag(const double *A, const double *RB, ChainLayout lay, int ll, int nchains, double *ainf_o,
-                             double *rbinf_o) {
+                             double *rbinf_o, int use_smem) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= nchains) return;
   const long long off = (ch / lay.inner) * lay.outer_stride + (ch % lay.inner) * lay.inner_stride;
+  extern __shared__ double bp_smem[];
   BpoptChain c;
   c.a = A + off; c.rb = RB + off; c.ls = lay.lstride; c.n = ll - 1;
   c.ainf = __ldg(c.a + (long long)(c.n - 1) * c.ls);
+  if (use_smem) c.attach(bp_smem, blockDim.x, threadIdx.x);
   double bmax = 0.0, bmin = 0.0;
   for (int jiter = 1;; jiter++) {
+    c.stage();
     dev_emami(c, bmax, bmin);
     const double s = __dadd_rn(bmax, bmin);
     c.ainf = __dadd_rn(c.ainf, s);
