@@ -243,7 +243,10 @@ int rsrec_kubo_conductivity(rsrec_handle h, int nstart, int start_kind, const in
 /* ---- `type bands` (bands.f90): what the SCF loop takes from g0 -- total DOS, Fermi level, band moments, charges ----
  * Every Green-function entry point above (block_green, chebyshev_green, sgreen and the fused ones) leaves its
  * g0 (18,18,nv,nunits) on the device; these calls consume that copy, so a fused call with g0 = NULL followed by them
- * moves only O(nv) + O(nunits) numbers to the host.  rsrec_bands_set_g0 uploads a g0 computed elsewhere. */
+ * moves only O(nv) + O(nunits) numbers to the host.  rsrec_bands_set_g0 uploads a g0 computed elsewhere.
+ * g0 is kept only while it leaves half of the free device memory to the recursion (or up to RSREC_G0_RESIDENT_MAX_MB
+ * when that environment variable is set); beyond that the Green-function calls stream it to the host per batch of
+ * units as before, refuse g0 = NULL with RSREC_ENOMEM, and the calls below report that no g0 is resident. */
 int rsrec_bands_set_g0(rsrec_handle h, const rsrec_cplx *g0, int nunits, int nv);
 int rsrec_bands_get_g0(rsrec_handle h, rsrec_cplx *g0);
 int rsrec_bands_g0_shape(rsrec_handle h, int *nunits, int *nv);

@@ -1124,7 +1124,17 @@ static int g0_reserve(H *h, int na, int nv) {
   h->g0_units = na; h->g0_nv = nv;
   return RSREC_OK;
 }
+// true when g0 of na units may stay resident: it must leave half of the free device memory to the recursion itself
+static bool g0_fits(H *h, int na, int nv) {
+  const size_t need = (size_t)na * nv * BLKD * sizeof(double);
+  if (const char *cap = getenv("RSREC_G0_RESIDENT_MAX_MB")) return need <= (size_t)atoll(cap) * 1048576;  // test hook / user cap
+  if (h->g0all.n * sizeof(double) >= need) return true;
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return false;
+  return need <= (fr + h->g0all.n * sizeof(double)) / 2;
+}
 static int g0_keep(H *h, const double *d_src, int na, int nv) {
+  if (!g0_fits(h, na, nv)) { h->g0_units = 0; h->g0_nv = 0; return RSREC_OK; }  // too large to keep: the host copy is the only one
   TRY(g0_reserve(h, na, nv));
   CUDA_TRY(cudaMemcpyAsync(h->g0all.p, d_src, (size_t)na * nv * BLKD * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   return RSREC_OK;
@@ -1435,7 +1445,9 @@ static int recur_b_green_impl(rsrec_handle h, int nunits, const int32_t *site_i,
   if (nunits == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
-  TRY(g0_reserve(h, nunits, nv));
+  const bool keep = g0_fits(h, nunits, nv);
+  if (!keep && !g0) return fail(RSREC_ENOMEM, "rsrec_recur_b_green: g0 of all units does not fit on the device; pass a host g0");
+  if (keep) TRY(g0_reserve(h, nunits, nv)); else { h->g0_units = 0; h->g0_nv = 0; }
   TRY(to_dev(h, h->post[4], ene, nv));
   const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
   const size_t hs = (size_t)lld * BLKD;
@@ -1451,7 +1463,8 @@ static int recur_b_green_impl(rsrec_handle h, int nunits, const int32_t *site_i,
     k_zsqr<<<(unsigned)((size_t)n * lld), BLKC, 0, h->st>>>(h->post[1].p);
     h->launches++;
     TRY(dev_alloc(h->post[2], 2 * (size_t)n * (BLKC + 1), false));
-    double *d_g0 = h->g0all.p + (size_t)u0 * nv * BLKD;
+    if (!keep) TRY(dev_alloc(h->post[5], (size_t)n * nv * BLKD, false));
+    double *d_g0 = keep ? h->g0all.p + (size_t)u0 * nv * BLKD : h->post[5].p;
     double *d_ai = h->post[2].p, *d_bi = d_ai + (size_t)n * BLKC, *d_a0 = d_bi + (size_t)n * BLKC, *d_b0 = d_a0 + n;
     TRY(d_terminf(h, h->ahist.p, h->post[1].p, n, lld, d_ai, d_bi, d_a0, d_b0, true));
     TRY(d_bgreen(h, h->ahist.p, h->post[1].p, lld, n, h->post[4].p, nv, 0, nv, d_ai, d_bi, 0.0, 0.0, sym_term, d_g0));
@@ -1493,7 +1506,9 @@ static int cheb_recur_green_impl(rsrec_handle h, int nunits, const int32_t *site
   if (nunits == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
-  TRY(g0_reserve(h, nunits, nv));
+  const bool keep = g0_fits(h, nunits, nv);
+  if (!keep && !g0) return fail(RSREC_ENOMEM, "rsrec_cheb_recur_green: g0 of all units does not fit on the device; pass a host g0");
+  if (keep) TRY(g0_reserve(h, nunits, nv)); else { h->g0_units = 0; h->g0_nv = 0; }
   TRY(to_dev(h, h->post[4], ene, nv));
   const double a = (energy_max - energy_min) / (2 - 0.3), b = (energy_max + energy_min) / 2;  // recursion.f90:3078-3079
   const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
@@ -1510,7 +1525,8 @@ static int cheb_recur_green_impl(rsrec_handle h, int nunits, const int32_t *site
     int rc = cheb_finish(h, mu_out);
     if (rc == RSREC_EDIVERGED) rc_all = rc; else TRY(rc);
     TRY(dev_alloc(h->post[1], (size_t)n * ms, false));
-    double *d_g0 = h->g0all.p + (size_t)u0 * nv * BLKD;
+    if (!keep) TRY(dev_alloc(h->post[5], (size_t)n * nv * BLKD, false));
+    double *d_g0 = keep ? h->g0all.p + (size_t)u0 * nv * BLKD : h->post[5].p;
     TRY(d_cheb_green(h, h->mu.p, n, lld, h->post[4].p, nv, energy_min, energy_max, h->post[1].p, d_g0));
     if (mu_ng) TRY(to_host(h, mu_ng + (size_t)u0 * (2 * lld + 2) * BLKC, h->post[1].p, (size_t)n * ms));
     if (g0) TRY(to_host(h, g0 + (size_t)u0 * nv * BLKC, d_g0, (size_t)n * nv * BLKD));

@@ -139,3 +139,24 @@ def test_scf_quantities_of_the_reference_bccfe_case(oracle_mod):
     m0, _ = oracle_mod.bands_magnetic_moments(g0, ene, en.edel, ef, nv1, e1)
     assert np.abs(b.mom0 - m0).max() < 1e-8
     assert 1.5 < b.mom0[2, 0] < 3.0 and abs(occ[0].sum() - 8.0) < 1e-6     # bcc Fe: ~2.2 mu_B, 8 electrons
+
+
+def test_g0_too_large_to_keep_falls_back_to_the_host_copy(oracle_mod, monkeypatch):
+    """g0 of all units stays on the device only if it leaves room for the recursion; otherwise the fused call streams it to
+    the host batch by batch as before (same values), refuses g0 = NULL, and the bands calls ask for rsrec_bands_set_g0"""
+    rec, lat, ham = _rec()
+    gr = Green(rec)
+    want = gr.recur_b_green().copy()
+    monkeypatch.setenv("RSREC_G0_RESIDENT_MAX_MB", "1")
+    got = gr.recur_b_green()
+    assert np.array_equal(got, want)
+    b = Bands(gr, qqv=1.0)
+    with pytest.raises(RsrecError):
+        b.calculate_fermi()
+    with pytest.raises(RsrecError):
+        gr.recur_b_green(download_g0=False)
+    monkeypatch.setenv("RSREC_G0_RESIDENT_MAX_MB", "100000")
+    b.set_g0(want)
+    b.qqv = 2.0
+    b.calculate_fermi()
+    assert np.array_equal(b.dtot, oracle_mod.bands_dos(want)[0])
