@@ -230,10 +230,12 @@ def build_pot(par):
             "cex1": half(cex, -1), "obx0": half(obx, 1), "obx1": half(obx, -1), "cx": cx[:, :, None], "cex": cex[:, :, None]}
 
 
-def build_case(oracle_mod, hoh=False, inp=INPUT, par=FE):
-    """-> (lattice, hamiltonian, ene) of the bccFe regression case in the containers the oracle / the GPU library take"""
+def build_case(oracle_mod, hoh=False, inp=INPUT, par=FE, cr=None):
+    """-> (lattice, hamiltonian, ene) of the bccFe regression case in the containers the oracle / the GPU library take
+    (cr: another cluster in units of alat, site 1 = the representative atom; default the bcc cut of `inp`)"""
     from rslmtoasa_b200.synthetic import Lattice, Hamiltonian
-    cr = bravais_cluster(inp["rc"])
+    if cr is None:
+        cr = bravais_cluster(inp["rc"])
     kk = cr.shape[1]
     crd = np.asfortranarray(cr * inp["alat"])
     nn, nm, rc = oracle_mod.build_nn(crd, np.ones(kk, np.int32), [1], inp["ct"])

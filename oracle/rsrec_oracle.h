@@ -9,8 +9,10 @@
  * bccFe regression case (tests/scf/references/Example_bulk_bccFe_<case>/ref.json, 12 cases: nsp 1/2/4, hoh on/off, block
  * and Chebyshev recursion, lld 16/21, two energy windows) from its input files and reproduces every stored
  * totaldos.out value to all printed digits through this oracle (tests/test_reference_golden.py) and through the
- * CUDA library (tests/test_gpu_reference_golden.py).  Routines no reference fixture reaches (scalar recursion,
- * recur_b_ij, Kubo-Bastin moments, site-indexed `hall` region, orbital moments) are pinned by the independent dense
+ * CUDA library (tests/test_gpu_reference_golden.py); oracle/ref_fccpt.py does the same for the Kubo-Bastin path with the
+ * stored Pt_cond.out curves of tests/postproc/references/Example_exchange_conductivity_fccPt{,_hoh} (kubo moments, velocity
+ * products, Gamma contraction, Fermi-weighted tail).  Routines no reference fixture reaches (scalar recursion,
+ * recur_b_ij, site-indexed `hall` region, orbital moments) are pinned by the independent dense
  * numpy restatement (oracle/dense_check*.py) and by invariants (tests/test_oracle*.py).  The reference itself cannot
  * be compiled here (no Fortran compiler), so there is no oracle/_ref.
  *

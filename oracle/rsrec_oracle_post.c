@@ -4,8 +4,9 @@
  *
  * PARITY PINNED by the reference's bccFe golden fixtures for bpopt/emami/get_terminf, bgreen/block_green and
  * chebyshev_green/jackson_kernel (the totaldos.out values of tests/scf/references are -Im Tr g0/pi of exactly these;
- * see rsrec_oracle.h and tests/test_reference_golden.py); the scalar density/sgreen and the Kubo-Bastin contraction,
- * which no reference fixture reaches, are pinned by the numpy restatement in oracle/dense_check_post.py.
+ * see rsrec_oracle.h and tests/test_reference_golden.py) and for calculate_gamma_nm / calculate_conductivity_tensor (the
+ * Pt_cond.out curves of tests/postproc/references/Example_exchange_conductivity_fccPt*, oracle/ref_fccpt.py); the scalar
+ * density/sgreen, which no reference fixture reaches, are pinned by the numpy restatement in oracle/dense_check_post.py.
  *
  * Restates, statement for statement:
  *   emami               recursion.f90:3589-3706      bpopt               recursion.f90:3540-3581

@@ -8,13 +8,19 @@ import json
 import os
 
 REF = "/root/reference/tests/scf"
-out = {"_source": "rslmtoasa/rslmtoasa tests/scf/references/Example_bulk_bccFe_*/ref.json + tests/scf/cases.json", "cases": {}}
+out = {"_source": "rslmtoasa/rslmtoasa tests/scf/references/Example_bulk_bccFe_*/ref.json + tests/scf/cases.json; tests/postproc/references/Example_exchange_conductivity_fccPt*/ref.json + tests/postproc/cases.json", "cases": {}}
 cases = {c["name"]: c for c in json.load(open(os.path.join(REF, "cases.json")))["cases"]}
 for d in sorted(glob.glob(os.path.join(REF, "references", "Example_bulk_bccFe_*"))):
     name = os.path.basename(d)
     ref = json.load(open(os.path.join(d, "ref.json")))
     out["cases"][name] = {"namelists": cases[name]["namelists"], "totaldos.out": ref["text"]["totaldos.out"],
                           "etot": ref["nml"]["Fe_out.nml"]["etot"]}
+# post-processing fixtures (conductivity): tests/postproc/references/Example_exchange_conductivity_fccPt*/ref.json
+PP = "/root/reference/tests/postproc"
+pcases = {c["name"]: c for c in json.load(open(os.path.join(PP, "cases.json")))["cases"]}
+for d in sorted(glob.glob(os.path.join(PP, "references", "Example_exchange_conductivity_fccPt*"))):
+    name = os.path.basename(d)
+    out["cases"][name] = {"namelists": pcases[name]["namelists"], "Pt_cond.out": json.load(open(os.path.join(d, "ref.json")))["text"]["Pt_cond.out"]}
 here = os.path.dirname(os.path.abspath(__file__))
 json.dump(out, open(os.path.join(here, "reference_bccfe_ref.json"), "w"), indent=1, sort_keys=True)
 print(len(out["cases"]), "cases")

@@ -60,3 +60,27 @@ def test_gpu_pipeline_from_coordinates_reproduces_reference_golden(oracle_mod):
     gr = Green(rec)
     g0 = gr.recur_b_green()
     _check(gr.ene, R.total_dos(g0), dict(g, fermi=inp["fermi"]))
+
+
+@pytest.mark.parametrize("hoh", [False, True])
+def test_gpu_reproduces_reference_conductivity_golden(oracle_mod, hoh):
+    """the reference's stored Pt_cond.out values (tests/postproc/references/Example_exchange_conductivity_fccPt{,_hoh}) from
+    the CUDA path: fused Kubo moments + Gamma contraction (rsrec_kubo_conductivity) + the sigma(E_F) tail
+    (rsrec_conductivity_cumulative), 8000 sites, cond_ll = 50"""
+    from oracle import ref_fccpt as P
+    from rslmtoasa_b200 import Recursion, Control, Energy, Conductivity
+    lat, ham, ene, mesh = P.kubo_inputs(oracle_mod, hoh)
+    inp = P.INPUT
+    en = Energy(inp["energy_min"], inp["energy_max"], channels_ldos=inp["channels_ldos"], fermi=inp["fermi"])
+    rec = Recursion(ham, lat, Control(lld=50, cond_ll=inp["cond_ll"], cond_calctype="per_type"), en, atlist=[1])
+    c = Conductivity(rec)
+    assert np.array_equal(c.ene, ene)
+    c.compute_conductivity()
+    sig = c.integrate_conductivity()
+    worst = P.check_rows(ene, sig[0, 0, :, 1], "Example_exchange_conductivity_fccPt" + ("_hoh" if hoh else ""))
+    assert worst < 1e-5
+    # the staged path (moments on the host, then the integrand) gives the same curve
+    rec.compute_moments_stochastic()
+    c.calculate_conductivity_tensor()
+    sig2 = c.integrate_conductivity()
+    assert np.allclose(sig2[0, 0, :, 1], sig[0, 0, :, 1], rtol=1e-9, atol=1e-12)

@@ -49,6 +49,11 @@ def test_embedded_golden_table_is_the_reference_fixture_file():
     import json
     import os
     ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_bccfe_ref.json")))["cases"]
+    from oracle import ref_fccpt as P
+    for name, rows in P.GOLDEN.items():               # the conductivity fixtures embedded in oracle/ref_fccpt.py
+        for row, (e, v) in rows.items():
+            assert ref[name]["Pt_cond.out"][str(row)] == {"1": e, "2": v}
+    ref = {k: v for k, v in ref.items() if "totaldos.out" in v}
     assert set(ref) == set(R.GOLDEN)
     for name, g in R.GOLDEN.items():
         nml = ref[name]["namelists"]
@@ -59,3 +64,18 @@ def test_embedded_golden_table_is_the_reference_fixture_file():
             assert (nml["energy"]["energy_min"], nml["energy"]["energy_max"]) == g["window"]
         for row, (e, d) in g["rows"].items():
             assert ref[name]["totaldos.out"][str(row)] == {"1": e, "2": d}
+
+
+@pytest.mark.parametrize("hoh", [False, True])
+def test_oracle_reproduces_reference_conductivity_golden(oracle_mod, hoh):
+    """tests/postproc/references/Example_exchange_conductivity_fccPt{,_hoh}/ref.json: Pt_cond.out rows 500/1000/1500 of
+    the reference's Kubo-Bastin post-processing (fcc Pt, 8000 sites, cond_ll = 50, spin-Hall operator pair) reproduced by
+    the oracle chain kubo moments -> Gamma contraction -> Fermi-weighted Simpson tail.  This pins compute_moments_stochastic
+    (with the hoh operator variants), the velocity products, calculate_gamma_nm and calculate_conductivity_tensor."""
+    import os
+    from oracle import ref_fccpt as P
+    if hoh and not os.environ.get("RSREC_SLOW_TESTS"):
+        pytest.skip("second 8000-site CPU Kubo run (~1.5 min); set RSREC_SLOW_TESTS=1 -- the GPU test covers both cases")
+    ene, re = P.oracle_conductivity(oracle_mod, hoh)
+    worst = P.check_rows(ene, re, "Example_exchange_conductivity_fccPt" + ("_hoh" if hoh else ""))
+    assert worst < 1e-5
