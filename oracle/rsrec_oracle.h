@@ -11,8 +11,9 @@
  * totaldos.out value to all printed digits through this oracle (tests/test_reference_golden.py) and through the
  * CUDA library (tests/test_gpu_reference_golden.py); oracle/ref_fccpt.py does the same for the Kubo-Bastin path with the
  * stored Pt_cond.out curves of tests/postproc/references/Example_exchange_conductivity_fccPt{,_hoh} (kubo moments, velocity
- * products, Gamma contraction, Fermi-weighted tail).  Routines no reference fixture reaches (scalar recursion,
- * recur_b_ij, site-indexed `hall` region, orbital moments) are pinned by the independent dense
+ * products, Gamma contraction, Fermi-weighted tail), and oracle/ref_exchange.py for the pair path (recur_b_ij,
+ * calculate_intersite_gf) with the stored J_ij of tests/postproc/references/Example_exchange_bccFe{,_hoh}.  Routines no
+ * reference fixture reaches (scalar recursion, site-indexed `hall` region, orbital moments, random-vector starts) are pinned by the independent dense
  * numpy restatement (oracle/dense_check*.py) and by invariants (tests/test_oracle*.py).  The reference itself cannot
  * be compiled here (no Fortran compiler), so there is no oracle/_ref.
  *

@@ -84,3 +84,22 @@ def test_gpu_reproduces_reference_conductivity_golden(oracle_mod, hoh):
     c.calculate_conductivity_tensor()
     sig2 = c.integrate_conductivity()
     assert np.allclose(sig2[0, 0, :, 1], sig[0, 0, :, 1], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("hoh", [False, True])
+def test_gpu_reproduces_reference_exchange_golden(oracle_mod, hoh):
+    """the reference's stored J_ij (tests/postproc/references/Example_exchange_bccFe{,_hoh}/ref.json) from the CUDA path: fused
+    pair recursion + Green functions (rsrec_recur_b_ij_green) + rsrec_intersite_gf on the device-resident g0"""
+    from oracle import ref_exchange as X
+    from rslmtoasa_b200 import Recursion, Control, Energy, Green
+    lat, ham, ene, mesh = X.case_inputs(oracle_mod, hoh)
+    inp = X.INPUT
+    en = Energy(inp["energy_min"], inp["energy_max"], channels_ldos=inp["channels_ldos"], fermi=inp["fermi"])
+    rec = Recursion(ham, lat, Control(lld=inp["lld"], recur="block"), en, ijpair=X.PAIRS)
+    gr = Green(rec)
+    assert np.array_equal(gr.ene, ene)
+    gr.calculate_intersite_gf(fused=True)
+    gs = np.stack([gr.ginmag, gr.gix, gr.giy, gr.giz, gr.gjnmag, gr.gjx, gr.gjy, gr.gjz], axis=-1)
+    jij = X.jij_from_spin_components(gs, ene, mesh["nv1"])
+    dist = np.linalg.norm(lat.cr[:, X.PAIRS[:, 1] - 1] - lat.cr[:, X.PAIRS[:, 0] - 1], axis=0)
+    assert X.check(jij, dist, "Example_exchange_bccFe" + ("_hoh" if hoh else "")) < 1.5e-6

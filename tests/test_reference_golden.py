@@ -53,6 +53,11 @@ def test_embedded_golden_table_is_the_reference_fixture_file():
     for name, rows in P.GOLDEN.items():               # the conductivity fixtures embedded in oracle/ref_fccpt.py
         for row, (e, v) in rows.items():
             assert ref[name]["Pt_cond.out"][str(row)] == {"1": e, "2": v}
+    from oracle import ref_exchange as X
+    for name, rows in X.GOLDEN.items():               # the exchange fixtures embedded in oracle/ref_exchange.py
+        for row, (j, dist) in rows.items():
+            assert ref[name]["jij.out"][str(row)] == {"6": j, "7": dist}
+        assert ref[name]["namelists"]["control"]["lld"] == X.INPUT["lld"]
     ref = {k: v for k, v in ref.items() if "totaldos.out" in v}
     assert set(ref) == set(R.GOLDEN)
     for name, g in R.GOLDEN.items():
@@ -79,3 +84,13 @@ def test_oracle_reproduces_reference_conductivity_golden(oracle_mod, hoh):
     ene, re = P.oracle_conductivity(oracle_mod, hoh)
     worst = P.check_rows(ene, re, "Example_exchange_conductivity_fccPt" + ("_hoh" if hoh else ""))
     assert worst < 1e-5
+
+
+@pytest.mark.parametrize("hoh", [False, True])
+def test_oracle_reproduces_reference_exchange_golden(oracle_mod, hoh):
+    """tests/postproc/references/Example_exchange_bccFe{,_hoh}/ref.json: J_ij of the nearest and next-nearest neighbour pair
+    (jij.out, f12.6) from the oracle chain recur_b_ij -> zsqr -> block_green_ij -> calculate_intersite_gf; pins the pair
+    recursion (four start-vector combinations) and the inter-site Green functions, with and without hoh."""
+    from oracle import ref_exchange as X
+    jij, dist = X.oracle_jij(oracle_mod, hoh)
+    assert X.check(jij, dist, "Example_exchange_bccFe" + ("_hoh" if hoh else "")) < 1.5e-6
