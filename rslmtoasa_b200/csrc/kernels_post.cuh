@@ -132,6 +132,110 @@ __device__ inline void dev_emami(const BpoptChain &c, double &emax_o, double &em
   emin_o = e;
 }
 
+// ---- warp-per-chain emami: the bisections are sequential chains of Sturm counts (20 dependent divisions each), so a
+// thread-per-chain kernel is pure latency.  A warp instead evaluates the 31 nodes of the next FIVE bisection levels at
+// once: node k (heap numbering, lane k-1) derives its trial energy from the bounds its ancestors WOULD have set (only
+// halvings, no counts needed), all lanes count in parallel, and the true path is then walked with shuffles using the
+// reference's branch and stop rules.  Every number on the true path is computed by the same operations as the serial
+// loop, so the result is bit-identical; ~22 serial counts become 5 rounds.
+// kind 0: first bisection (num == n -> emax = e ; num < n -> emin = e); kind 1: second (num == 0 -> emin ; else emax).
+__device__ inline bool emami_rounds(const BpoptChain &c, int kind, double &emax, double &emin, double &e_last, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const int n = c.n;
+  const double eps = 1.0e-6;
+  int istop = 1;
+  for (;;) {
+    // this lane's node: k = lane + 1 in 1..31 (lane 31 repeats node 31), depth d = floor(log2 k)
+    const int k = min(lane + 1, 31);
+    const int d = 31 - __clz(k);
+    double hi = emax, lo = emin, e = 0.0;
+    for (int lev = 0; lev <= d; lev++) {
+      e = __ddiv_rn(__dadd_rn(hi, lo), 2.0);
+      if (lev == d) break;
+      const int bit = (k >> (d - 1 - lev)) & 1;  // 1: the branch that moves emax down to e
+      if (bit) hi = e; else lo = e;
+    }
+    const int num = sturm_count(c, e);
+    // walk the true path
+    int node = 1;
+    for (int lev = 0; lev < 5; lev++) {
+      const double en = __shfl_sync(FULL, e, node - 1);
+      const int cnt = __shfl_sync(FULL, num, node - 1);
+      e_last = en;
+      if (istop > 50) return true;  // the reference's "goto 1000": caller returns (emax, emin) as they are
+      int bit;
+      if (kind == 0) { bit = cnt == n; if (cnt == n) emax = en; if (cnt < n) emin = en; }
+      else { bit = cnt > 0; if (cnt == 0) emin = en; if (cnt > 0) emax = en; }
+      const double dele = fabs(__ddiv_rn(__dsub_rn(emax, emin), __ddiv_rn(__dadd_rn(emax, emin), 2.0)));
+      if (dele <= eps) return false;
+      istop++;
+      node = 2 * node + bit;
+    }
+  }
+}
+
+__device__ inline void dev_emami_warp(const BpoptChain &c, double &emax_o, double &emin_o, int lane) {
+  const int n = c.n;
+  double emax0 = -1.0e6, emin0 = 1.0e6;
+  for (int i = 1; i <= n; i++) {
+    const double ai = c.az(i), b0 = fabs(c.bz(i)), b1 = fabs(c.bz(i + 1));
+    const double x1 = __dadd_rn(__dadd_rn(ai, b0), b1), x2 = __dsub_rn(__dsub_rn(ai, b0), b1);
+    if (emax0 <= x1) emax0 = x1;
+    if (emin0 > x2) emin0 = x2;
+  }
+  double emax = emax0, emin = emin0, e = 0.0;
+  if (emami_rounds(c, 0, emax, emin, e, lane)) { emax_o = emax; emin_o = emin; return; }
+  const double e1 = e;
+  emax = e1; emin = emin0;
+  if (emami_rounds(c, 1, emax, emin, e, lane)) { emax_o = emax; emin_o = emin; return; }
+  emax_o = e1;
+  emin_o = e;
+}
+
+// bpopt for nchains chains, one WARP per chain; diag != 0: chain = (orbital i, unit), results go to element (i,i) of the
+// (18,18,unit) arrays (the 18 diagonal chains block_green consumes); shared memory: 2 (ll + 1) doubles per warp
+__global__ void k_bpopt_warp(const double *A, const double *RB, ChainLayout lay, int ll, int nchains, double *ainf_o,
+                             double *rbinf_o, int *ifail_o, int diag) {
+  extern __shared__ double bp_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int ch = blockIdx.x * wpb + wib;
+  if (ch >= nchains) return;
+  const long long off = (ch / lay.inner) * lay.outer_stride + (ch % lay.inner) * lay.inner_stride;
+  BpoptChain c;
+  c.a = A + off; c.rb = RB + off; c.ls = lay.lstride; c.n = ll - 1;
+  c.ainf = __ldg(c.a + (long long)(c.n - 1) * c.ls);
+  c.saz = bp_smem + (size_t)wib * 2 * (ll + 1);
+  c.sbz = c.saz + (ll + 1);
+  c.sstride = 1;
+  double bmax = 0.0, bmin = 0.0;
+  int ifail = 0;
+  for (int jiter = 1;; jiter++) {
+    for (int i = 1 + lane; i <= c.n + 1; i += 32) {
+      if (i <= c.n) c.saz[i] = c.az_g(i);
+      c.sbz[i] = c.bz_g(i);
+    }
+    __syncwarp();
+    dev_emami_warp(c, bmax, bmin, lane);
+    __syncwarp();
+    const double s = __dadd_rn(bmax, bmin);
+    c.ainf = __dadd_rn(c.ainf, s);
+    if (fabs(s) <= 1.0e-05) break;
+    if (jiter > 300) { ifail = 1; break; }
+  }
+  if (lane == 0) {
+    const double rbinf = __ddiv_rn(__dsub_rn(bmax, bmin), 2.0);
+    if (diag) {
+      const int i = ch % NB, unit = ch / NB;
+      ainf_o[(size_t)unit * BLKC + i * (NB + 1)] = c.ainf;
+      rbinf_o[(size_t)unit * BLKC + i * (NB + 1)] = rbinf;
+    } else {
+      ainf_o[ch] = c.ainf;
+      rbinf_o[ch] = rbinf;
+      if (ifail_o) ifail_o[ch] = ifail;
+    }
+  }
+}
+
 // bpopt (recursion.f90:3540-3581) for nchains independent chains
 __global__ void k_bpopt(const double *A, const double *RB, ChainLayout lay, int ll, int nchains, double *ainf_o,
                         double *rbinf_o, int *ifail_o, int use_smem) {

@@ -1098,7 +1098,26 @@ int rsrec_kubo_moments(rsrec_handle h, int nstart, int start_kind, const int32_t
 // Consumers either side of the hot path: terminator, block / Chebyshev Green functions,
 // scalar continued fraction, Kubo-Bastin integrand.  d_* functions work on device arrays (so that the fused entry
 // points can chain them behind a recursion without a host round trip); the rsrec_* wrappers marshal host arrays.
+// Terminator launcher: one warp per chain while the chains fit a few waves of resident warps (the bisections run five
+// levels per round there), one thread per chain beyond that.
+static void launch_bpopt(H *h, const double *A, const double *RB, ChainLayout lay, int ll, int nchains, double *ainf, double *rbinf,
+                         int *ifail, int diag);
 #define BPOPT_SMEM_MAX (48 * 1024)  // beyond this (ll > ~45) the chains are read from global memory as before
+static void launch_bpopt(H *h, const double *A, const double *RB, ChainLayout lay, int ll, int nchains, double *ainf, double *rbinf,
+                         int *ifail, int diag) {
+  const size_t wsm = (size_t)4 * 2 * (ll + 1) * sizeof(double);  // 4 warps per CTA
+  const char *force = getenv("RSREC_BPOPT_KERNEL");              // "thread" | "warp" (A/B switch)
+  const bool warp = force ? force[0] == 'w' : (nchains <= 4 * 32 * h->sms && wsm <= BPOPT_SMEM_MAX);
+  if (warp) {
+    k_bpopt_warp<<<(nchains + 3) / 4, 128, wsm, h->st>>>(A, RB, lay, ll, nchains, ainf, rbinf, ifail, diag);
+  } else if (diag) {
+    const size_t sm = bpopt_smem_bytes(ll, 32);
+    k_bpopt_diag<<<(nchains + 31) / 32, 32, sm <= BPOPT_SMEM_MAX ? sm : 0, h->st>>>(A, RB, lay, ll, nchains, ainf, rbinf, sm <= BPOPT_SMEM_MAX);
+  } else {
+    const size_t sm = bpopt_smem_bytes(ll, 64);
+    k_bpopt<<<(nchains + 63) / 64, 64, sm <= BPOPT_SMEM_MAX ? sm : 0, h->st>>>(A, RB, lay, ll, nchains, ainf, rbinf, ifail, sm <= BPOPT_SMEM_MAX);
+  }
+}
 static int bgreen_smem(int nw) { return (2 * BG_MAT + nw * BG_WSTRIDE) * (int)sizeof(double2); }
 static int post_configure() {
   if (cudaFuncSetAttribute(k_bgreen<BG_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bgreen_smem(BG_WARPS)) != cudaSuccess) return -1;
@@ -1150,12 +1169,9 @@ static int d_terminf(H *h, const double *d_ab, const double *d_bb, int na, int l
   if (diag_only) {
     CUDA_TRY(cudaMemsetAsync(d_ainf, 0, 2 * (size_t)nch * sizeof(double), h->st));  // a_inf and b_inf are adjacent
     const ChainLayout dl{NB, 2LL * (NB + 1), 2LL * BLKC * ll, 2LL * BLKC};
-    // 18 chains per unit: small CTAs so that the few chains spread over many SMs
-    const size_t sm = bpopt_smem_bytes(ll, 32);
-    k_bpopt_diag<<<(NB * na + 31) / 32, 32, sm <= BPOPT_SMEM_MAX ? sm : 0, h->st>>>(d_ab, d_bb, dl, ll, NB * na, d_ainf, d_binf, sm <= BPOPT_SMEM_MAX);
+    launch_bpopt(h, d_ab, d_bb, dl, ll, NB * na, d_ainf, d_binf, nullptr, 1);
   } else {
-    const size_t sm = bpopt_smem_bytes(ll, 64);
-    k_bpopt<<<(nch + 63) / 64, 64, sm <= BPOPT_SMEM_MAX ? sm : 0, h->st>>>(d_ab, d_bb, lay, ll, nch, d_ainf, d_binf, nullptr, sm <= BPOPT_SMEM_MAX);
+    launch_bpopt(h, d_ab, d_bb, lay, ll, nch, d_ainf, d_binf, nullptr, 0);
   }
   k_terminf_fix<<<na, BLKC, 0, h->st>>>(d_ainf, d_binf, d_a0, d_b0);
   h->launches += 2;
@@ -1227,8 +1243,7 @@ static int d_density(H *h, const double *d_a, const double *d_b2, int lld, int n
   double *sq = h->post[8].p, *am1 = sq + n, *bm1 = am1 + nchain;
   k_sqrt_array<<<grid_for(n, 256, h->sms * 8), 256, 0, h->st>>>(d_b2, sq, n);
   const ChainLayout lay{(long long)nchain, (long long)lld, 0, 1};
-  const size_t bsm = bpopt_smem_bytes(lld, 64);
-  k_bpopt<<<(nchain + 63) / 64, 64, bsm <= BPOPT_SMEM_MAX ? bsm : 0, h->st>>>(d_a, sq, lay, lld, nchain, am1, bm1, nullptr, bsm <= BPOPT_SMEM_MAX);
+  launch_bpopt(h, d_a, sq, lay, lld, nchain, am1, bm1, nullptr, 0);
   const size_t total = (size_t)NB * nv * nch;
   k_density<<<grid_for(total, 256, h->sms * 16), 256, 0, h->st>>>(d_a, d_b2, lld, nch, na, am1, bm1, d_ene, nv, d_dw, d_cs, d_td);
   h->launches += 3;
@@ -1289,8 +1304,7 @@ int rsrec_bpopt(rsrec_handle h, int nchains, int ll, const double *a, const doub
   double *d_ai = h->post[2].p, *d_bi = d_ai + nchains;
   int *d_if = (int *)(d_bi + nchains);
   const ChainLayout lay{(long long)nchains, (long long)ll, 0, 1};
-  const size_t bsm = bpopt_smem_bytes(ll, 64);
-  k_bpopt<<<(nchains + 63) / 64, 64, bsm <= BPOPT_SMEM_MAX ? bsm : 0, h->st>>>(h->post[0].p, h->post[1].p, lay, ll, nchains, d_ai, d_bi, d_if, bsm <= BPOPT_SMEM_MAX);
+  launch_bpopt(h, h->post[0].p, h->post[1].p, lay, ll, nchains, d_ai, d_bi, d_if, 0);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   TRY(to_host(h, ainf, d_ai, nchains));

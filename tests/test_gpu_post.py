@@ -37,8 +37,11 @@ def test_e_mesh_is_the_reference_rule(oracle_mod):
     assert np.array_equal(en.e_mesh(), oracle_mod.e_mesh(-1.2, 1.0, 161, 0.05)) and en.channels_ldos == 160
 
 
-def test_bpopt_bit_exact(oracle_mod, block_rec):
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
+def test_bpopt_bit_exact(oracle_mod, block_rec, kernel, monkeypatch):
+    """both terminator kernels: one warp per chain (31 speculative bisection nodes per round) and one thread per chain"""
     from rslmtoasa_b200 import Dos
+    monkeypatch.setenv("RSREC_BPOPT_KERNEL", kernel)
     rng = np.random.default_rng(11)
     ll, n = 14, 200
     a = 0.1 + 0.3 * rng.normal(size=(ll, n))
