@@ -40,7 +40,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    saved_fd = os.dup(1); os.dup2(2, 1)        # NCCL's start-up banner goes to stderr, stdout stays JSON lines only
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier(); torch.cuda.synchronize(dev)
+    finally:
+        sys.stdout.flush(); os.dup2(saved_fd, 1); os.close(saved_fd)
     # ---- config 2 (replicated unit batch) ----
     lat = S.sphere_cluster("fcc", 100.0, ntype=7, type_rule="layer")
     base = [1, 2, 3, 14, 15, 20]
@@ -56,6 +61,24 @@ def main():
         print(json.dumps({"config": "2 surface fcc, 24 recursion sites, recur_b lld=21", "n_gpus": world, "units_total": 24,
                           "units_per_gpu": len(lat.irec) // world, "seconds": t, "steps_per_s": 24 * 20 / t,
                           "checksum": float(np.abs(a_all).sum())}), flush=True)
+    # ---- the whole SCF iteration on the same 24 units: recursion -> terminator -> Green function (g0 stays on each GPU)
+    #      -> dtot all-reduced -> Fermi level -> charges / moments per unit, gathered ----
+    from rslmtoasa_b200 import Green
+    from rslmtoasa_b200.bands import Bands
+    rec.en.channels_ldos, rec.en.fermi, rec.en.ene = 2500, 0.0, None
+    g = Green(rec)
+
+    def run_scf():
+        g.recur_b_green(download_g0=False)
+        rec.en.fermi = 0.0
+        b = Bands(g, qqv=6.0 * len(lat.irec), device=dev)
+        b.calculate_fermi(); b.calculate_magnetic_moments(); b.calculate_moments(); b.calculate_band_energy()
+        return b.en.fermi, b.eband, b.gather(b.occ)
+    t, (ef, eb, occ) = timed(run_scf, dev)
+    if rank == 0:
+        print(json.dumps({"config": "2 surface fcc, 24 recursion sites, whole SCF iteration (recur_b + green nv=2510 + bands)",
+                          "n_gpus": world, "units_per_gpu": len(lat.irec) // world, "seconds": t, "fermi": ef, "eband": eb,
+                          "checksum_occ": float(np.abs(occ).sum()), "occ_shape": list(occ.shape)}), flush=True)
     rec.close()
     # ---- config 4 ----
     lat = S.periodic_bcc(10, 20, 20)
