@@ -139,3 +139,25 @@ def test_header_is_valid_c_and_cxx(tmp_path):
     inc = os.path.join(ROOT, "include")
     subprocess.check_call([shutil.which("gcc") or "/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", inc, "-c", str(src_c), "-o", str(tmp_path / "c.o")])
     subprocess.check_call([shutil.which("g++") or "/usr/bin/g++", "-std=c++17", "-Wall", "-I", inc, "-c", str(src_cc), "-o", str(tmp_path / "cc.o")])
+
+
+def test_committed_bench_lines_keep_the_driver_contract():
+    """the JSON lines bench.py printed on the B200 (profiles/r01d_bench_n*_1M.json) carry every key the driver reads"""
+    import glob
+    import json
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01d_bench_n*_1M.json")))
+    assert files
+    for f in files:
+        d = json.loads(open(f).read())
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert k in d, (f, k)
+        assert d["dtype"] == "f64" and d["scaling"] == "weak" and d["vs_baseline"] is None and "workload" in d["config"]
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert d["e2e"]["value"] < d["value"] and d["e2e"]["h2d_bytes_per_step"] > 0
+        r = d["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if d["n_gpus"] == 1:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
