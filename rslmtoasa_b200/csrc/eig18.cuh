@@ -204,7 +204,8 @@ __device__ __forceinline__ void eig18_func(const Eig18Smem &s, const double *f, 
 // crecal_b "B_n+1": take the reduced B^2 of unit blockIdx.x (k_reduce_parts), record it in the history slot, then
 // B = U sqrt(L) U^H and B^-1 = U L^-1/2 U^H.  diag != 0: scalar Lanczos, everything diagonal & real.
 __global__ void __launch_bounds__(BLKC) k_lz_eig(const double *b2, size_t b2stride, double *b2_hist_slot, size_t hstride,
-                                                 double *Bmat, double *Bimat, size_t bstride, int diag, int method) {
+                                                 double *Bmat, double *Bimat, size_t bstride, int diag, int method,
+                                                 double *b_hist_slot = nullptr) {
   __shared__ Eig18Smem s;
   __shared__ double f1[NB], f2[NB];
   const int tid = threadIdx.x, unit = blockIdx.x, r = tid % NB, c = tid / NB;
@@ -213,14 +214,19 @@ __global__ void __launch_bounds__(BLKC) k_lz_eig(const double *b2, size_t b2stri
   b2_hist_slot[(size_t)unit * hstride + 2 * tid] = mr;
   b2_hist_slot[(size_t)unit * hstride + 2 * tid + 1] = mi;
   double *B = Bmat + (size_t)unit * bstride, *Bi = Bimat + (size_t)unit * bstride;
+  double *bh = b_hist_slot ? b_hist_slot + (size_t)unit * hstride : nullptr;  // B of this level for the Green function
   if (diag) {
     const double sq = sqrt(mr);
     B[2 * tid] = (r == c) ? sq : 0.0; B[2 * tid + 1] = 0.0;
     Bi[2 * tid] = (r == c) ? 1.0 / sq : 0.0; Bi[2 * tid + 1] = 0.0;
+    if (bh) { bh[2 * tid] = B[2 * tid]; bh[2 * tid + 1] = 0.0; }
     return;
   }
   s.Ar[tid] = mr; s.Ai[tid] = mi;
-  if (method == 1 && sqrt18_newton_schulz(s, B, Bi)) return;
+  if (method == 1 && sqrt18_newton_schulz(s, B, Bi)) {
+    if (bh) { bh[2 * tid] = B[2 * tid]; bh[2 * tid + 1] = B[2 * tid + 1]; }
+    return;
+  }
   __syncthreads();
   s.Ar[tid] = mr; s.Ai[tid] = mi;  // fallback / method 0: eigen-decomposition like the reference's zheev path
   eig18_jacobi(s);
@@ -228,6 +234,7 @@ __global__ void __launch_bounds__(BLKC) k_lz_eig(const double *b2, size_t b2stri
   __syncthreads();
   eig18_func(s, f1, B);
   eig18_func(s, f2, Bi);
+  if (bh) { bh[2 * tid] = B[2 * tid]; bh[2 * tid + 1] = B[2 * tid + 1]; }
 }
 
 // zsqr: in-place square root of a batch of Hermitian PSD 18x18 matrices (complex col-major)
@@ -236,7 +243,13 @@ __global__ void __launch_bounds__(BLKC) k_zsqr(double *mats) {
   __shared__ double f1[NB];
   const int tid = threadIdx.x;
   double *m = mats + (size_t)blockIdx.x * BLKD;
-  s.Ar[tid] = m[2 * tid]; s.Ai[tid] = m[2 * tid + 1];
+  __shared__ double inv_scratch[BLKD];
+  const double mr = m[2 * tid], mi = m[2 * tid + 1];
+  s.Ar[tid] = mr; s.Ai[tid] = mi;
+  // same routine, same input bits as k_lz_eig saw for this level: the staged zsqr returns exactly the B the recursion used
+  if (sqrt18_newton_schulz(s, m, inv_scratch)) return;
+  __syncthreads();
+  s.Ar[tid] = mr; s.Ai[tid] = mi;
   eig18_jacobi(s);
   if (tid < NB) f1[tid] = sqrt(s.ev[tid]);
   __syncthreads();

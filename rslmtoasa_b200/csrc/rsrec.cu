@@ -73,7 +73,7 @@ struct rsrec_handle_s {
   DmmaTiles tiles;
   // work vectors and small matrices
   std::vector<DevBuf> vecs;
-  DevBuf part, A, B, Bi, B2, mu, ahist, b2hist, scratch;
+  DevBuf part, A, B, Bi, B2, mu, ahist, b2hist, bhist /* B = (B^2)^1/2 per level, what zsqr would return */, scratch;
   DevBuf post[12];  // work arrays of the post-recursion consumers (terminator, Green functions, Kubo back end)
   // on-site Green function of the last Green-function call, kept for the `bands` consumers (bands.f90)
   DevBuf g0all, bands_y, bands_out;
@@ -538,15 +538,18 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   const size_t hs = (size_t)lld * BLKD;  // history stride per unit (doubles)
   TRY(dev_alloc(h->ahist, (size_t)nunits * hs, false));
   TRY(dev_alloc(h->b2hist, (size_t)nunits * hs, false));
+  TRY(dev_alloc(h->bhist, (size_t)nunits * hs, false));
   TRY(zero_vec(h, psi, nunits));
   TRY(zero_vec(h, pmn, nunits));
   if (hpsi) TRY(zero_vec(h, hpsi, nunits));  // tiles the active-region plan skips must read as zeros
   if (tmp) TRY(zero_vec(h, tmp, nunits));
   CUDA_TRY(cudaMemsetAsync(h->ahist.p, 0, (size_t)nunits * hs * sizeof(double), h->st));
   CUDA_TRY(cudaMemsetAsync(h->b2hist.p, 0, (size_t)nunits * hs * sizeof(double), h->st));
+  CUDA_TRY(cudaMemsetAsync(h->bhist.p, 0, (size_t)nunits * hs * sizeof(double), h->st));
   k_init_site_start<<<nunits, 32, 0, h->st>>>(psi, vstride(h), h->d_si, h->d_sj, h->d_as, h->d_bs, nunits);
   k_set_identity<<<nunits, 64, 0, h->st>>>(h->b2hist.p, hs, nunits);  // b2temp_b(:,:,1) = I
-  h->launches += 2;
+  k_set_identity<<<nunits, 64, 0, h->st>>>(h->bhist.p, hs, nunits);   // and its square root
+  h->launches += 3;
   for (int ll = 0; ll < lld - 1; ll++) {
     // hop_b / hop_b_hoh: pmn = H psi - pmn ; A = sum psi^H H psi
     if (h->family == 1) {  // tensor-pipe SpMV: hpsi = H psi, pmn = hpsi - pmn; A = sum psi^H hpsi on the tensor pipe too
@@ -576,7 +579,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     // B2 -> history slot ll+1, B, B^-1
     TRY(launch_reduce(h, nunits, nctas, 0, h->B2.p, nullptr, BLKD, nullptr, nullptr));
     k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->B2.p, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
-                                         BLKD, diag ? 1 : 0, h->sqrt_method);
+                                         BLKD, diag ? 1 : 0, h->sqrt_method, h->bhist.p + (size_t)(ll + 1) * BLKD);
     h->launches++;
     // psi = pmn B^-1 ; pmn = psi_old B
     if (h->family == 1) {
@@ -719,7 +722,7 @@ int rsrec_destroy(rsrec_handle h) {
   cudaStreamSynchronize(h->st);
   for (auto &v : h->vecs) dev_free(v);
   DevBuf *bufs[] = {&h->Hmain, &h->Hh, &h->Hho_neg, &h->Hx, &h->Hscalar, &h->Hva, &h->Hvb, &h->Hvoa_neg, &h->Hvob_neg,
-                    &h->part, &h->A, &h->B, &h->Bi, &h->B2, &h->mu, &h->ahist, &h->b2hist, &h->scratch};
+                    &h->part, &h->A, &h->B, &h->Bi, &h->B2, &h->mu, &h->ahist, &h->b2hist, &h->bhist, &h->scratch};
   for (auto b : bufs) dev_free(*b);
   for (auto &b : h->post) dev_free(b);
   dev_free(h->g0all); dev_free(h->bands_y); dev_free(h->bands_out);
@@ -1471,11 +1474,10 @@ static int recur_b_green_impl(rsrec_handle h, int nunits, const int32_t *site_i,
     TRY(plan_build(h, n, site_i + u0, site_j ? site_j + u0 : nullptr));
     TRY(lanczos_batch(h, n, lld, false, a_b ? (double *)(a_b + (size_t)u0 * lld * BLKC) : nullptr,
                       b2_b ? (double *)(b2_b + (size_t)u0 * lld * BLKC) : nullptr));
-    // zsqr on the device copy of the B^2 history, then the terminator and the continued fraction
+    // zsqr is free here: crecal_b already formed B = (B^2)^1/2 at every level (k_lz_eig keeps it in bhist); then the
+    // terminator and the continued fraction
     TRY(dev_alloc(h->post[1], (size_t)n * hs, false));
-    CUDA_TRY(cudaMemcpyAsync(h->post[1].p, h->b2hist.p, (size_t)n * hs * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-    k_zsqr<<<(unsigned)((size_t)n * lld), BLKC, 0, h->st>>>(h->post[1].p);
-    h->launches++;
+    CUDA_TRY(cudaMemcpyAsync(h->post[1].p, h->bhist.p, (size_t)n * hs * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
     TRY(dev_alloc(h->post[2], 2 * (size_t)n * (BLKC + 1), false));
     if (!keep) TRY(dev_alloc(h->post[5], (size_t)n * nv * BLKD, false));
     double *d_g0 = keep ? h->g0all.p + (size_t)u0 * nv * BLKD : h->post[5].p;
