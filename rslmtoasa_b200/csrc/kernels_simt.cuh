@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) k_gram_simt(const double *X, con
 // mode 2: diagonal projection (scalar Lanczos): keep Re(diag) only
 // grid = (ceil(2*648 / warps_per_block), nunits)
 __global__ void k_reduce_parts(const double *part, int nctas, int mode, double *dst0, double *dst1, size_t dstride,
-                               const double *mu0, const double *mu1) {
+                               const double *mu0, const double *mu1, double *hist0 = nullptr, size_t hstride = 0) {
   const int unit = blockIdx.y, lane = threadIdx.x & 31;
   const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (e >= 2 * BLKD) return;
@@ -158,6 +158,7 @@ __global__ void k_reduce_parts(const double *part, int nctas, int mode, double *
       if (i != j || im) s = 0.0;
     }
     d[(size_t)unit * dstride + idx] = s;
+    if (hist0 && which == 0) hist0[(size_t)unit * hstride + idx] = s;  // the history slot of the same block (atemp_b)
   }
 }
 

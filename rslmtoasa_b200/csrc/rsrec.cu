@@ -490,8 +490,8 @@ static size_t part_doubles(const H *h, int nunits, int nctas) {
   return (size_t)nunits * std::max(std::max(simt, dm), std::min(nctas, nctas_for(h, nunits))) * 2 * BLKD;
 }
 static int launch_reduce(H *h, int nunits, int /*nctas*/, int mode, double *d0, double *d1, size_t dstride,
-                         const double *m0, const double *m1) {
-  k_reduce_parts<<<dim3((2 * BLKD + 7) / 8, nunits), 256, 0, h->st>>>(h->part.p, h->last_parts, mode, d0, d1, dstride, m0, m1);
+                         const double *m0, const double *m1, double *hist0 = nullptr, size_t hstride = 0) {
+  k_reduce_parts<<<dim3((2 * BLKD + 7) / 8, nunits), 256, 0, h->st>>>(h->part.p, h->last_parts, mode, d0, d1, dstride, m0, m1, hist0, hstride);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return RSREC_OK;
@@ -560,9 +560,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     } else {
       TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, h->part.p));
     }
-    TRY(launch_reduce(h, nunits, nctas, diag ? 2 : 0, h->A.p, nullptr, BLKD, nullptr, nullptr));
-    CUDA_TRY(cudaMemcpy2DAsync(h->ahist.p + (size_t)ll * BLKD, hs * sizeof(double), h->A.p, BLKD * sizeof(double),
-                               BLKD * sizeof(double), nunits, cudaMemcpyDeviceToDevice, h->st));
+    TRY(launch_reduce(h, nunits, nctas, diag ? 2 : 0, h->A.p, nullptr, BLKD, nullptr, nullptr, h->ahist.p + (size_t)ll * BLKD, hs));
     // pmn -= psi A ; B2 = sum pmn^H pmn
     dim3 grid(nctas, nunits);
     if (h->family == 1) {
