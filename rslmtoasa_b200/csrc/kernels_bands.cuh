@@ -82,15 +82,16 @@ __global__ void k_bands_ldos(const double2 *__restrict__ g0, int nv, int nunits,
   if (dosia) dosia[blk] = d;
 }
 
-// res: ef, e1, ik1 (as double), ifail (as double).  y = dtot(1..npts)
-__device__ void bands_fermi_scan(double &ef, double h, int &ik1, double ainf, int npts, const double *y, int &ifail, double qqv, double &e1) {
+// `fermi` (bands.f90:366-402).  pan[j] = H*(Y(I-1) + 4 Y(I) + Y(I+1))/3 of panel I = 2 j + 2 (precomputed by all threads
+// with the reference's operations); the scan itself is a serial add-and-compare.  y = dtot(1..npts) is only needed for
+// nothing else, so the caller passes the panel values.
+__device__ void bands_fermi_scan(double &ef, double h, int &ik1, double ainf, int npts, const double *pan, int &ifail, double qqv, double &e1) {
   ifail = 1;
   double aint = 0.0, aint0 = 0.0;
   int i;
   bool hit = false;
   for (i = 2; i <= npts - 1; i += 2) {
-    const double s = __dadd_rn(__dadd_rn(y[i - 2], __dmul_rn(4.0, y[i - 1])), y[i]);
-    aint = __dadd_rn(aint, __ddiv_rn(__dmul_rn(h, s), 3.0));
+    aint = __dadd_rn(aint, pan[(i >> 1) - 1]);
     if (aint >= qqv) { hit = true; break; }
     aint0 = aint;
   }
@@ -108,20 +109,22 @@ __device__ void bands_fermi_scan(double &ef, double h, int &ik1, double ainf, in
   }
 }
 
-// the two calls of calculate_fermi (bands.f90:327-334): res = {fermi, e1, nv1, ifail}
+// the two calls of calculate_fermi (bands.f90:327-334): res = {fermi, e1, nv1, ifail}; pan: npts/2 doubles of scratch
+// (shared memory when it fits, else global)
 __global__ void k_bands_fermi(const double *__restrict__ dtot, int npts, double h, double ainf, double qqv, double fermi_in, int ik1_in,
-                              double *__restrict__ res, int use_smem) {
+                              double *__restrict__ res, double *__restrict__ pan_global) {
   extern __shared__ double fm_smem[];
-  if (use_smem) {  // the scan is one thread's dependent chain: feed it from shared memory, not from L2
-    for (int i = threadIdx.x; i < npts; i += blockDim.x) fm_smem[i] = dtot[i];
-    __syncthreads();
-    dtot = fm_smem;
+  double *pan = pan_global ? pan_global : fm_smem;
+  for (int i = 2 + 2 * threadIdx.x; i <= npts - 1; i += 2 * blockDim.x) {
+    const double s = __dadd_rn(__dadd_rn(dtot[i - 2], __dmul_rn(4.0, dtot[i - 1])), dtot[i]);
+    pan[(i >> 1) - 1] = __ddiv_rn(__dmul_rn(h, s), 3.0);
   }
+  __syncthreads();
   if (blockIdx.x || threadIdx.x) return;
   double ef_mag = fermi_in, e1_mag = fermi_in, ef = fermi_in;
   int ik1_mag = 0, ik1 = ik1_in, ifail = 1;
-  bands_fermi_scan(ef_mag, h, ik1_mag, ainf, npts, dtot, ifail, qqv, e1_mag);
-  bands_fermi_scan(ef, h, ik1, ainf, npts, dtot, ifail, qqv, e1_mag);
+  bands_fermi_scan(ef_mag, h, ik1_mag, ainf, npts, pan, ifail, qqv, e1_mag);
+  bands_fermi_scan(ef, h, ik1, ainf, npts, pan, ifail, qqv, e1_mag);
   res[0] = ef; res[1] = e1_mag; res[2] = (double)ik1; res[3] = (double)ifail;
 }
 

@@ -2083,9 +2083,10 @@ int rsrec_bands_fermi(rsrec_handle h, const double *dtot, int nv, double edel, d
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(to_dev(h, h->post[4], dtot, nv));
   TRY(dev_alloc(h->bands_out, 4, false));
-  const size_t fsm = (size_t)nv * sizeof(double);
-  k_bands_fermi<<<1, 256, fsm <= 48 * 1024 ? fsm : 0, h->st>>>(h->post[4].p, nv, edel, energy_min, qqv, *fermi, *nv1, h->bands_out.p,
-                                                          fsm <= 48 * 1024);
+  const size_t fsm = (size_t)(nv / 2 + 1) * sizeof(double);  // one value per Simpson panel
+  double *pan_g = nullptr;
+  if (fsm > 48 * 1024) { TRY(dev_alloc(h->bands_y, nv / 2 + 1, false)); pan_g = h->bands_y.p; }
+  k_bands_fermi<<<1, 256, pan_g ? 0 : fsm, h->st>>>(h->post[4].p, nv, edel, energy_min, qqv, *fermi, *nv1, h->bands_out.p, pan_g);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   double res[4];
