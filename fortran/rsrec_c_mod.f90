@@ -33,6 +33,7 @@ module rsrec_c_mod
    public :: rsrec_bands_magnetic_moments, rsrec_bands_moments, rsrec_bands_band_energy
    ! exchange path: pair-unit fused drivers and calculate_intersite_gf
    public :: rsrec_recur_b_ij_green, rsrec_cheb_recur_ij_green, rsrec_intersite_gf, rsrec_conductivity_cumulative
+   public :: rsrec_spin_diag_launch_count
 
    interface
       function rsrec_last_error() bind(C, name='rsrec_last_error') result(msg)
@@ -500,6 +501,12 @@ module rsrec_c_mod
          real(c_double), value :: wstep
          real(c_double), intent(out) :: sigma(2, 19, nv, *)
          integer(c_int) :: rc
+      end function
+
+      function rsrec_spin_diag_launch_count(h) bind(C, name='rsrec_spin_diag_launch_count') result(n)
+         import :: c_ptr, c_long_long
+         type(c_ptr), value :: h
+         integer(c_long_long) :: n
       end function
 
    end interface

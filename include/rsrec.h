@@ -292,6 +292,9 @@ int rsrec_synchronize(rsrec_handle h);
 void *rsrec_stream(rsrec_handle h);
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */
 long long rsrec_launch_count(rsrec_handle h);
+/* how many of the SpMV launches ran the spin-diagonal two-block kernel (collinear hopping blocks; RSREC_NO_SPIN_DIAG=1
+ * in the environment disables it) */
+long long rsrec_spin_diag_launch_count(rsrec_handle h);
 /* host<->device bytes this handle has moved so far (uploads of lattice/Hamiltonian/start data, downloads of results) */
 long long rsrec_h2d_bytes(rsrec_handle h);
 long long rsrec_d2h_bytes(rsrec_handle h);

@@ -22,7 +22,7 @@ SYMBOLS = [
     "rsrec_lanczos_block_local_axis", "rsrec_set_positions",
     "rsrec_bands_set_g0", "rsrec_bands_get_g0", "rsrec_bands_g0_shape", "rsrec_bands_dos", "rsrec_bands_fermi",
     "rsrec_bands_magnetic_moments", "rsrec_bands_moments", "rsrec_bands_band_energy",
-    "rsrec_recur_b_ij_green", "rsrec_cheb_recur_ij_green", "rsrec_intersite_gf", "rsrec_conductivity_cumulative",
+    "rsrec_recur_b_ij_green", "rsrec_cheb_recur_ij_green", "rsrec_intersite_gf", "rsrec_conductivity_cumulative", "rsrec_spin_diag_launch_count",
 ]
 
 
@@ -67,6 +67,8 @@ def load():
     L.rsrec_stream.restype = vp
     L.rsrec_launch_count.argtypes = [vp]
     L.rsrec_launch_count.restype = C.c_longlong
+    L.rsrec_spin_diag_launch_count.argtypes = [vp]
+    L.rsrec_spin_diag_launch_count.restype = C.c_longlong
     L.rsrec_set_kernel_family.argtypes = [vp, i]
     L.rsrec_h2d_bytes.argtypes = [vp]
     L.rsrec_h2d_bytes.restype = C.c_longlong

@@ -19,6 +19,7 @@
 #pragma once
 #include "common.cuh"
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #define DM_S 8                               // sites per tile
@@ -58,6 +59,7 @@ struct DmmaStages {  // stage list of one tile, in execution order (self stage l
   const double *src[DM_MAXST];
   int hstride[DM_MAXST];  // doubles between classes
   int slot[DM_MAXST];     // neighbour slot, 0 = self
+  unsigned char sd[DM_MAXST];  // 1: every block of this stage is spin-diagonal (only the two 9x9 spin blocks are non-zero)
   int n;
 };
 
@@ -303,6 +305,244 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
     dmma_consumer<EPI, ADDEND, 2, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
   else
     dmma_consumer<EPI, ADDEND, 1, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+}
+
+// ---- spin-diagonal variant of the SpMV (S = 4 geometry) -----------------------------------------------------------------
+// In a collinear calculation the hopping blocks ee(:,:,m,type) are spin-diagonal -- only l.s on the on-site block couples
+// the spins -- so the 36x36 real embedding of such a block is two independent 18x18 products.  Stages flagged `sd` run
+// per spin with K = 18 (5 k-steps, the two padding columns point at a column of the OTHER spin, where the block is exactly
+// zero) instead of K = 36 (9 k-steps); the on-site stage stays full.  To let both kinds of stage add into the same
+// accumulators the output rows are grouped by spin, 24 per spin (3 n-tiles, 18 used):
+//   up:   rho 0..8 = Re rows 0..8, rho 9 pad, rho 10..18 = Im rows 18..26, rho 19..23 pad
+//   down: rho 24 pad, 25..33 = Re rows 9..17, rho 34 pad, 35..43 = Im rows 27..35, rho 44..47 pad
+// (the pads are placed so that every accumulator pair (rho, rho+1) of two valid rows is an aligned double2 in RI36).
+// A spin-diagonal stage issues 2 x 3 x 5 = 30 DMMAs per m-tile instead of 5 x 9 = 45; the full stage 6 x 9 = 54.
+// The blocks themselves are the ordinary HR36 ones: only the fragment addresses differ.
+__device__ __forceinline__ int sd_row(int rho) {  // accumulator row -> RI36 row, -1 = padding
+  if (rho < 24) {
+    if (rho < 9) return rho;
+    if (rho == 9) return -1;
+    return rho < 19 ? 18 + (rho - 10) : -1;
+  }
+  const int r = rho - 24;
+  if (r == 0 || r == 10) return -1;
+  if (r < 10) return 9 + (r - 1);
+  return r < 20 ? 27 + (r - 11) : -1;
+}
+__device__ __forceinline__ int sd_kcol(int spin, int kappa) {  // k index of a spin-diagonal stage -> RI36 row of psi / column of H
+  if (kappa < 9) return 9 * spin + kappa;
+  if (kappa < 18) return 18 + 9 * spin + (kappa - 9);
+  return 9 * (1 - spin);  // padding: a column of the other spin (H is exactly zero there)
+}
+
+// XN shared-m-tile units of this warp, all of spin XSPIN: warp 0: n-tiles 0,1  warp 1: 2  warp 2: 3,4  warp 3: 5
+template <int EPI, bool ADDEND, int XN, int XSPIN>
+__device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const DmmaStages &st,
+                                                 const int32_t *__restrict__ tile_sites, double *stages, uint64_t *full,
+                                                 uint64_t *empty, int ntiles, int nunits,
+                                                 const int32_t *__restrict__ order, const int32_t *__restrict__ cnt,
+                                                 int warp, int lane) {
+  constexpr int S = 4;
+  const int g = lane >> 2, q = lane & 3;
+  const int nst = st.n;
+  const double inv_a = 1.0 / p.a;
+  constexpr int STG = ApGeom<S>::kStages, STGD = ApGeom<S>::kStageD;
+  const int mt0 = 2 * warp, mt1 = 2 * warp + 1, mt2 = 8;
+  const int xn0 = XSPIN * 3 + (warp & 1 ? 2 : 0);  // warp 0: 0,1  warp 1: 2  warp 2: 3,4  warp 3: 5
+  int arow[3];                                     // psi column (m-tile row) base offsets
+  arow[0] = HBLK + (mt0 * 8 + g) * COLD;
+  arow[1] = HBLK + (mt1 * 8 + g) * COLD;
+  arow[2] = HBLK + (mt2 * 8 + g) * COLD;
+  int brow[6], xrow[XN];                           // H row base offsets of this lane's B fragments (pads read row 0)
+#pragma unroll
+  for (int nt = 0; nt < 6; nt++) brow[nt] = max(sd_row(nt * 8 + g), 0) * COLD;
+#pragma unroll
+  for (int x = 0; x < XN; x++) xrow[x] = max(sd_row((xn0 + x) * 8 + g), 0) * COLD;
+  int kc[2][5];                                    // k columns of the spin-diagonal stages
+#pragma unroll
+  for (int sp = 0; sp < 2; sp++)
+#pragma unroll
+    for (int ks = 0; ks < 5; ks++) kc[sp][ks] = sd_kcol(sp, 4 * ks + q);
+  // epilogue rows of this lane's accumulator pairs: RI36 offsets (or -1)
+  int er0[6], er1[6];
+#pragma unroll
+  for (int nt = 0; nt < 6; nt++) { er0[nt] = sd_row(nt * 8 + 2 * q); er1[nt] = sd_row(nt * 8 + 2 * q + 1); }
+
+  uint32_t it = 0;
+  for (int u = 0; u < nunits; u++) {
+    const size_t uo = (size_t)u * p.vstride;
+    const int n_u = (cnt ? cnt[u] : ntiles) * (DM_S / S);
+    for (int ti = blockIdx.x; ti < n_u; ti += gridDim.x) {
+      const int tpos = ti >> 1, half = (ti & 1) * S;
+      const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
+      double acc[2][6][2], xacc[XN][2];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int nt = 0; nt < 6; nt++) acc[i][nt][0] = acc[i][nt][1] = 0.0;
+#pragma unroll
+      for (int x = 0; x < XN; x++) xacc[x][0] = xacc[x][1] = 0.0;
+      size_t gbase[3];
+      bool gval[3];
+      int ncol[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const int n = (i == 0 ? mt0 : i == 1 ? mt1 : mt2) * 8 + g;
+        const int site = tile_sites[tile * DM_S + half + n / NB];
+        gval[i] = site < p.kk;
+        gbase[i] = uo + (size_t)site * BLKD + (n % NB) * COLD;
+        ncol[i] = n;
+      }
+      for (int j = 0; j < nst; j++, it++) {
+        const int slot = it % STG;
+        mbar_wait(&full[slot], (it / STG) & 1);
+        const double *sm = stages + (size_t)slot * STGD;
+        if (st.sd[j]) {
+#pragma unroll
+          for (int sp = 0; sp < 2; sp++) {
+#pragma unroll
+            for (int ks = 0; ks < 5; ks++) {
+              const int k = kc[sp][ks];
+              const double a0 = sm[arow[0] + k], a1 = sm[arow[1] + k];
+#pragma unroll
+              for (int t3 = 0; t3 < 3; t3++) {
+                const int nt = 3 * sp + t3;
+                const double b = sm[brow[nt] + k];
+                dmma(acc[0][nt][0], acc[0][nt][1], a0, b);
+                dmma(acc[1][nt][0], acc[1][nt][1], a1, b);
+              }
+              if (sp == XSPIN) {
+                const double a2 = sm[arow[2] + k];
+#pragma unroll
+                for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], a2, sm[xrow[x] + k]);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 9; ks++) {
+            const int k = 4 * ks + q;
+            const double a0 = sm[arow[0] + k], a1 = sm[arow[1] + k], a2 = sm[arow[2] + k];
+#pragma unroll
+            for (int nt = 0; nt < 6; nt++) {
+              const double b = sm[brow[nt] + k];
+              dmma(acc[0][nt][0], acc[0][nt][1], a0, b);
+              dmma(acc[1][nt][0], acc[1][nt][1], a1, b);
+            }
+#pragma unroll
+            for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], a2, sm[xrow[x] + k]);
+          }
+        }
+        if (j < nst - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+      }
+      // ===== epilogue: the last stage (self blocks of `in`) is still held =====
+      const int lslot = (it - 1) % STG;
+      const double *sm = stages + (size_t)lslot * STGD;
+      auto fin1 = [&](double v, int n, int r, size_t gb) {  // one row
+        const size_t go = gb + r;
+        if (ADDEND) v += __ldg(p.addend + go);
+        if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
+          v = (v - p.b * sm[HBLK + n * COLD + r]) * inv_a;
+          if (EPI == EPI_CHEB_NOGRAM) v = 2.0 * v - __ldg(p.prev + go);
+        }
+        if (EPI == EPI_HOP) { p.out2[go] = v; v -= p.prev[go]; }
+        p.out[go] = v;
+      };
+      auto fin2 = [&](double v0, double v1, int n, int r, size_t gb) {  // two adjacent rows, r even
+        const size_t go = gb + r;
+        if (ADDEND) { const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go)); v0 += ad.x; v1 += ad.y; }
+        if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
+          const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + r);
+          v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
+          if (EPI == EPI_CHEB_NOGRAM) {
+            const double2 pv = __ldg(reinterpret_cast<const double2 *>(p.prev + go));
+            v0 = 2.0 * v0 - pv.x; v1 = 2.0 * v1 - pv.y;
+          }
+        }
+        if (EPI == EPI_HOP) {
+          *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
+          const double2 pv = *reinterpret_cast<const double2 *>(p.prev + go);
+          v0 -= pv.x; v1 -= pv.y;
+        }
+        *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
+      };
+      auto finish = [&](double v0, double v1, int n, int nt, size_t gb) {
+        const int r0 = er0[nt], r1 = er1[nt];
+        if (r0 >= 0 && r1 >= 0) fin2(v0, v1, n, r0, gb);
+        else if (r0 >= 0) fin1(v0, n, r0, gb);
+        else if (r1 >= 0) fin1(v1, n, r1, gb);
+      };
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int nt = 0; nt < 6; nt++)
+          if (gval[i]) finish(acc[i][nt][0], acc[i][nt][1], ncol[i], nt, gbase[i]);
+#pragma unroll
+      for (int x = 0; x < XN; x++)
+        if (gval[2]) finish(xacc[x][0], xacc[x][1], ncol[2], xn0 + x, gbase[2]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[lslot]);
+    }
+  }
+}
+
+template <int EPI, bool ADDEND>
+__global__ void __launch_bounds__(ApGeom<4>::kThreads, ApGeom<4>::kMinBlocks)
+k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_sites, const int32_t *__restrict__ tile_cls,
+                const int32_t *__restrict__ tile_nbr, int ntiles, int nunits, const int32_t *__restrict__ order,
+                const int32_t *__restrict__ cnt) {
+  constexpr int S = 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stages = reinterpret_cast<double *>(smem_raw);
+  constexpr int STG = ApGeom<S>::kStages, STGD = ApGeom<S>::kStageD, NCONS = ApGeom<S>::kConsumers;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STG * STGD * 8);
+  uint64_t *empty = full + STG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STG; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nst = st.n, ng = p.ngather;
+  if (warp == NCONS) {  // producer warp: identical to k_apply_dmma<.., 4>
+    int cu = 0, ci = blockIdx.x, cj = 0;
+    auto count = [&](int u) { return (cnt ? cnt[u] : ntiles) * (DM_S / S); };
+    auto settle = [&](int &u, int &i) { while (u < nunits && i >= count(u)) { u++; i = blockIdx.x; } };
+    auto fetch = [&](int u, int i, int j, int &site, int &cls) {
+      const int tpos = i >> 1, half = (i & 1) * S;
+      const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
+      cls = tile_cls[tile];
+      const int m = st.slot[j];
+      site = (lane < S) ? ((m == 0) ? tile_sites[tile * DM_S + half + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + half + lane]) : 0;
+    };
+    settle(cu, ci);
+    int site = 0, cls = 0;
+    if (cu < nunits) fetch(cu, ci, cj, site, cls);
+    for (uint32_t it = 0; cu < nunits; it++) {
+      int nu = cu, ni = ci, nj = cj + 1, nsite = 0, ncls = 0;
+      if (nj == nst) { nj = 0; ni += gridDim.x; settle(nu, ni); }
+      if (nu < nunits) fetch(nu, ni, nj, nsite, ncls);
+      const int slot = it % STG;
+      mbar_wait(&empty[slot], ((it / STG) & 1) ^ 1);
+      double *sm = stages + (size_t)slot * STGD;
+      if (lane == 0) mbar_expect_tx(&full[slot], STGD * 8);
+      __syncwarp();
+      if (lane < S) {
+        bulk_g2s(sm + HBLK + lane * BLKD, st.src[cj] + (size_t)cu * p.vstride + (size_t)site * BLKD, BLKD * 8, &full[slot]);
+      } else if (lane == S) {
+        bulk_g2s(sm, st.H[cj] + (size_t)cls * st.hstride[cj], HBLK * 8, &full[slot]);
+      }
+      cu = nu; ci = ni; cj = nj; site = nsite; cls = ncls;
+    }
+    return;
+  }
+  if (warp == 0) dmma_consumer_sd<EPI, ADDEND, 2, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+  else if (warp == 1) dmma_consumer_sd<EPI, ADDEND, 1, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+  else if (warp == 2) dmma_consumer_sd<EPI, ADDEND, 2, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+  else dmma_consumer_sd<EPI, ADDEND, 1, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
 }
 
 // ---- Gram reductions on the tensor pipe -------------------------------------------------------------------------
@@ -631,7 +871,8 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
 static int dmma_configure() {
 #define DM_ATTR(E, A) \
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<8>::kSmem) != cudaSuccess) return -3; \
-  if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3; \
+  if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3;
   DM_ATTR(EPI_STORE, false)
   DM_ATTR(EPI_STORE, true)
   DM_ATTR(EPI_HAM, false)
@@ -741,9 +982,13 @@ static bool dmma_supported(const ApplyParams &p) {
 static int dmma_grid(const DmmaTiles &t, int sms) { return std::max(1, std::min(t.ntiles, sms)); }
 static int dmma_gram_ctas(int kk, int sms) { return std::max(1, std::min(sms, (kk + GR_WARPS - 1) / GR_WARPS)); }
 
+// sdflags(H set, slot) -> true when every block of that slot is spin-diagonal (nullptr: never)
+typedef bool (*SdLookup)(const void *ctx, const double *Hset, int slot);
 static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, cudaStream_t st, long long *launches,
-                             const int32_t *order = nullptr, const int32_t *cnt = nullptr) {
+                             const int32_t *order = nullptr, const int32_t *cnt = nullptr, SdLookup sdl = nullptr,
+                             const void *sdctx = nullptr, long long *sd_launches = nullptr) {
   DmmaStages sg;
+  memset(&sg, 0, sizeof(sg));
   sg.n = 0;
   // neighbour slots of every term first, then the on-site slots, then the on-site extra term (self stage last)
   for (int pass = 0; pass < 2; pass++)
@@ -754,17 +999,27 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
         sg.src[sg.n] = p.g[tm].src;
         sg.hstride[sg.n] = p.nslot_h * HBLK;
         sg.slot[sg.n] = m;
+        sg.sd[sg.n] = sdl && sdl(sdctx, p.g[tm].H, m);
         sg.n++;
       }
   if (p.Hx) {
     sg.H[sg.n] = p.Hx; sg.src[sg.n] = p.srcx; sg.hstride[sg.n] = HBLK; sg.slot[sg.n] = 0;
+    sg.sd[sg.n] = sdl && sdl(sdctx, p.Hx, 0);
     sg.n++;
   }
+  int nsd = 0;
+  for (int j = 0; j < sg.n; j++) nsd += sg.sd[j];
   static const int geom = getenv("RSREC_APPLY_S") ? atoi(getenv("RSREC_APPLY_S")) : DM_APPLY_S;
   const int grid = geom == 4 ? std::max(1, std::min(2 * t.ntiles, 2 * sms)) : dmma_grid(t, sms);
+  // the spin-grouped accumulator layout costs 6 instead of 5 n-tiles on full stages: worth it when most stages are spin-diagonal
+  const bool use_sd = geom == 4 && 2 * nsd > sg.n;
+  if (use_sd && sd_launches) (*sd_launches)++;
 #define DM_LAUNCH(E, A)                                                                                                   \
   do {                                                                                                                    \
-    if (geom == 4)                                                                                                        \
+    if (use_sd)                                                                                                           \
+      k_apply_dmma_sd<E, A><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmem, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,       \
+                                                                              t.ntiles, nunits, order, cnt);             \
+    else if (geom == 4)                                                                                                   \
       k_apply_dmma<E, A, 4><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmem, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,       \
                                                                               t.ntiles, nunits, order, cnt);             \
     else                                                                                                                  \

@@ -171,6 +171,14 @@ k_pack_hr36(const double2 *__restrict__ src, int ncls_src, const double2 *__rest
   d[(r + NB) * COLD + NB + k] = v.x;
 }
 
+// flags[m] |= 1 when any block of slot m has a non-zero element between the two spins (src: (18,18,nslot,ncls) complex)
+__global__ void __launch_bounds__(BLKC)
+k_sd_scan(const double2 *__restrict__ src, int nslot, int *__restrict__ flags) {
+  const int m = blockIdx.x, c = blockIdx.y, t = threadIdx.x, r = t % NB, k = t / NB;
+  const double2 v = src[(size_t)BLKC * (m + (size_t)nslot * c) + t];
+  if (((r < 9) != (k < 9)) && (v.x != 0.0 || v.y != 0.0)) atomicOr(&flags[m], 1);
+}
+
 // rotmag_loc (math.f90:1981-2053): out(:,:,j) = R^H (in(:,:,j) R) for every 18x18 block; R = ROTMAT(alfa, beta, 0)
 __global__ void __launch_bounds__(BLKC)
 k_rotmag(const double2 *__restrict__ in, const double2 *__restrict__ R, double2 *__restrict__ out) {

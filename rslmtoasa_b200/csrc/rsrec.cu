@@ -19,6 +19,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -48,6 +49,7 @@ struct rsrec_handle_s {
   int sms = 148;
   cudaStream_t st = nullptr;
   long long launches = 0;
+  long long sd_launches = 0;  // SpMV launches that took the spin-diagonal two-block kernel
   int last_parts = 0;  // partial-sum slots per unit written by the last fused apply
   double *out2 = nullptr;  // second output of the next EPI_HOP application (hpsi)
   int sqrt_method = 1;     // B = (B^2)^1/2: 1 = Newton-Schulz with Jacobi fallback, 0 = Jacobi eigen-decomposition
@@ -74,6 +76,8 @@ struct rsrec_handle_s {
   // work vectors and small matrices
   std::vector<DevBuf> vecs;
   DevBuf part, A, B, Bi, B2, mu, ahist, b2hist, bhist /* B = (B^2)^1/2 per level, what zsqr would return */, scratch;
+  // per H set (key = device pointer of the packed set): slot -> 1 when every block of the slot is spin-diagonal
+  std::map<const double *, std::vector<unsigned char>> sdmap;
   DevBuf post[12];  // work arrays of the post-recursion consumers (terminator, Green functions, Kubo back end)
   // on-site Green function of the last Green-function call, kept for the `bands` consumers (bands.f90)
   DevBuf g0all, bands_y, bands_out;
@@ -248,6 +252,48 @@ static int ensure_ready(H *h) {
     }
   }
   CUDA_TRY(cudaGetLastError());
+  // spin-diagonal slots (collinear hopping blocks): the tensor SpMV runs them as two 18x18 products (k_apply_dmma_sd)
+  h->sdmap.clear();
+  if (!getenv("RSREC_NO_SPIN_DIAG")) {
+    // scan(src, classes) -> per-slot "mixes the spins" flags
+    const int nsl = nslot;
+    TRY(dev_alloc(h->scratch, std::max<size_t>(h->scratch.n, (size_t)8 * nsl), false));
+    int *d_fl = (int *)h->scratch.p;
+    CUDA_TRY(cudaMemsetAsync(d_fl, 0, (size_t)8 * nsl * sizeof(int), h->st));
+    auto scan = [&](int row, const double *src, int slots, int classes) {
+      if (src && classes > 0) k_sd_scan<<<dim3(slots, classes), BLKC, 0, h->st>>>((const double2 *)src, slots, d_fl + row * nsl);
+    };
+    scan(0, h->cBLK.p, nsl, ncls);
+    if (h->hoh) scan(1, h->cBLKO.p, nsl, ncls);
+    scan(2, h->cLS.p, 1, h->ntype);
+    if (h->hoh) scan(3, h->cENIM.p, 1, h->ntype);
+    for (int sx = 0; sx < 2; sx++) {
+      if (!h->have_op[sx]) continue;
+      scan(4 + sx, h->cV[sx].p, nsl, h->ntype);
+      if (h->hoh && !(sx == 0 ? h->vo_a : h->vo_b).empty()) scan(6 + sx, h->cVO[sx].p, nsl, h->ntype);
+    }
+    std::vector<int> fl((size_t)8 * nsl);
+    CUDA_TRY(cudaMemcpyAsync(fl.data(), d_fl, fl.size() * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    auto diag = [&](int row, bool extra_mix0) {
+      std::vector<unsigned char> v(nsl);
+      for (int m = 0; m < nsl; m++) v[m] = !(fl[(size_t)row * nsl + m] || (m == 0 && extra_mix0));
+      return v;
+    };
+    const bool ls_mix = fl[(size_t)2 * nsl] != 0;
+    h->sdmap[h->Hmain.p] = diag(0, ls_mix);                                   // on-site slot carries lsham
+    h->sdmap[h->Hscalar.p] = std::vector<unsigned char>(nsl, 1);              // masked to the spin blocks by construction
+    if (h->hoh) {
+      h->sdmap[h->Hh.p] = diag(0, false);
+      h->sdmap[h->Hho_neg.p] = diag(1, false);
+      h->sdmap[h->Hx.p] = std::vector<unsigned char>(1, !(fl[(size_t)3 * nsl] || ls_mix));
+    }
+    for (int sx = 0; sx < 2; sx++) {
+      if (!h->have_op[sx]) continue;
+      h->sdmap[(sx == 0 ? h->Hva : h->Hvb).p] = diag(4 + sx, false);
+      if (h->hoh) h->sdmap[(sx == 0 ? h->Hvoa_neg : h->Hvob_neg).p] = diag(6 + sx, false);   // all-zero set: diagonal too
+    }
+  }
   CUDA_TRY(cudaStreamSynchronize(h->st));
   h->dirty_ham = false;
   return RSREC_OK;
@@ -414,7 +460,12 @@ static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas) {
       order = h->plan.d_order;
       cnt = h->plan.d_counts + (size_t)h->plan.level * nunits;
     }
-    if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches, order, cnt) != 0)
+    auto sdl = [](const void *ctx, const double *Hset, int slot) -> bool {
+      const auto &mp = ((const H *)ctx)->sdmap;
+      auto itf = mp.find(Hset);
+      return itf != mp.end() && slot < (int)itf->second.size() && itf->second[slot];
+    };
+    if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches, order, cnt, sdl, h, &h->sd_launches) != 0)
       return fail(RSREC_ECUDA, std::string("k_apply_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->last_parts = 0;
     return RSREC_OK;
@@ -1936,6 +1987,7 @@ int rsrec_profile_read(rsrec_handle h, double *total_ms, int *nlaunches) {
   return RSREC_OK;
 }
 long long rsrec_launch_count(rsrec_handle h) { return h ? h->launches : 0; }
+long long rsrec_spin_diag_launch_count(rsrec_handle h) { return h ? h->sd_launches : 0; }
 
 }  // extern "C"
 

@@ -504,3 +504,48 @@ def test_unit_batching_when_memory_is_short(oracle_mod, monkeypatch):
         ok = np.isfinite(want)
         assert relerr(got[ok], want[ok]) < 1e-9
     monkeypatch.delenv("RSREC_UNIT_BATCH")
+
+
+# ---- spin-diagonal (collinear) hopping blocks: k_apply_dmma_sd ------------------------------------------------------------
+def _collinear(ham):
+    """zero the blocks between the two spins on every hopping slot (m >= 2); the on-site slot keeps its l.s-like coupling"""
+    import copy
+    h = copy.deepcopy(ham)
+    for name in ("ee", "eeo", "hall", "hallo", "v_a", "v_b", "vo_a", "vo_b"):
+        a = getattr(h, name, None)
+        if a is None or a.size == 0:
+            continue
+        a = np.array(a, order="F")
+        a[:9, 9:, 1:, ...] = 0.0
+        a[9:, :9, 1:, ...] = 0.0
+        setattr(h, name, a)
+    return h
+
+
+@pytest.mark.parametrize("name", ["bulk", "bulk_hoh", "impurity", "surface", "pbc_hoh"])
+def test_spin_diagonal_hoppings_take_the_two_block_kernel(oracle_mod, name, monkeypatch):
+    """collinear Hamiltonians (hopping blocks spin-diagonal, on-site block full) run the SpMV as two 18x18 products per
+    slot; results must agree with the oracle and, to rounding, with the full-block kernel (RSREC_NO_SPIN_DIAG=1)"""
+    from rslmtoasa_b200 import Recursion, Control, Energy
+    lat, ham = case(name)
+    ham = _collinear(ham)
+    lld = 7
+    orc = oracle_mod.Oracle(lat, ham)
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    a_o, b_o = orc.lanczos_block(lat.irec, lld)
+    mu_o, _ = orc.cheb_moments(lat.irec, lld, a, b)
+    res = {}
+    for mode in ("sd", "full"):
+        if mode == "full":
+            monkeypatch.setenv("RSREC_NO_SPIN_DIAG", "1")
+        rec = Recursion(ham, lat, Control(lld=lld), Energy(EMIN, EMAX))
+        n0 = rec.launch_count
+        rec.recur_b()
+        rec.chebyshev_recur()
+        res[mode] = (rec.a_b.copy(), rec.b2_b.copy(), rec.mu_n.copy())
+        nsd = rec._L.rsrec_spin_diag_launch_count(rec._h)
+        assert (nsd > 0) == (mode == "sd"), (mode, nsd)
+        assert relerr(rec.a_b, a_o) < 1e-10 and relerr(rec.b2_b, b_o) < 1e-10 and relerr(rec.mu_n, mu_o) < 1e-9
+        rec.close()
+    for x, y in zip(res["sd"], res["full"]):
+        assert relerr(x, y) < 1e-12
