@@ -393,8 +393,29 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
         gbase[i] = uo + (size_t)site * BLKD + (n % NB) * COLD;
         ncol[i] = n;
       }
+      double pv[2][6][2], xpv[XN][2];  // prefetched `prev` values of this lane's accumulator rows
+      auto fetch_prev = [&](double *dst, int nt, size_t gb) {
+        const int r0 = er0[nt], r1 = er1[nt];
+        dst[0] = dst[1] = 0.0;
+        if (r0 >= 0 && r1 >= 0) {
+          const double2 t2 = __ldg(reinterpret_cast<const double2 *>(p.prev + gb + r0));
+          dst[0] = t2.x; dst[1] = t2.y;
+        } else if (r0 >= 0) dst[0] = __ldg(p.prev + gb + r0);
+        else if (r1 >= 0) dst[1] = __ldg(p.prev + gb + r1);
+      };
       for (int j = 0; j < nst; j++, it++) {
         const int slot = it % STG;
+        if ((EPI == EPI_CHEB_NOGRAM || EPI == EPI_HOP) && j == nst - 1) {
+          // issue the epilogue's global loads now; they land while the last stage is being computed
+#pragma unroll
+          for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int nt = 0; nt < 6; nt++)
+              if (gval[i]) fetch_prev(pv[i][nt], nt, gbase[i]); else pv[i][nt][0] = pv[i][nt][1] = 0.0;
+#pragma unroll
+          for (int x = 0; x < XN; x++)
+            if (gval[2]) fetch_prev(xpv[x], xn0 + x, gbase[2]); else xpv[x][0] = xpv[x][1] = 0.0;
+        }
         mbar_wait(&full[slot], (it / STG) & 1);
         const double *sm = stages + (size_t)slot * STGD;
         if (st.sd[j]) {
@@ -441,48 +462,44 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
       // ===== epilogue: the last stage (self blocks of `in`) is still held =====
       const int lslot = (it - 1) % STG;
       const double *sm = stages + (size_t)lslot * STGD;
-      auto fin1 = [&](double v, int n, int r, size_t gb) {  // one row
+      auto fin1 = [&](double v, int n, int r, size_t gb, double pr) {  // one row
         const size_t go = gb + r;
         if (ADDEND) v += __ldg(p.addend + go);
         if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
           v = (v - p.b * sm[HBLK + n * COLD + r]) * inv_a;
-          if (EPI == EPI_CHEB_NOGRAM) v = 2.0 * v - __ldg(p.prev + go);
+          if (EPI == EPI_CHEB_NOGRAM) v = 2.0 * v - pr;
         }
-        if (EPI == EPI_HOP) { p.out2[go] = v; v -= p.prev[go]; }
+        if (EPI == EPI_HOP) { p.out2[go] = v; v -= pr; }
         p.out[go] = v;
       };
-      auto fin2 = [&](double v0, double v1, int n, int r, size_t gb) {  // two adjacent rows, r even
+      auto fin2 = [&](double v0, double v1, int n, int r, size_t gb, double pr0, double pr1) {  // two adjacent rows, r even
         const size_t go = gb + r;
         if (ADDEND) { const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go)); v0 += ad.x; v1 += ad.y; }
         if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
           const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + r);
           v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
-          if (EPI == EPI_CHEB_NOGRAM) {
-            const double2 pv = __ldg(reinterpret_cast<const double2 *>(p.prev + go));
-            v0 = 2.0 * v0 - pv.x; v1 = 2.0 * v1 - pv.y;
-          }
+          if (EPI == EPI_CHEB_NOGRAM) { v0 = 2.0 * v0 - pr0; v1 = 2.0 * v1 - pr1; }
         }
         if (EPI == EPI_HOP) {
           *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
-          const double2 pv = *reinterpret_cast<const double2 *>(p.prev + go);
-          v0 -= pv.x; v1 -= pv.y;
+          v0 -= pr0; v1 -= pr1;
         }
         *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
       };
-      auto finish = [&](double v0, double v1, int n, int nt, size_t gb) {
+      auto finish = [&](double v0, double v1, int n, int nt, size_t gb, const double *pr) {
         const int r0 = er0[nt], r1 = er1[nt];
-        if (r0 >= 0 && r1 >= 0) fin2(v0, v1, n, r0, gb);
-        else if (r0 >= 0) fin1(v0, n, r0, gb);
-        else if (r1 >= 0) fin1(v1, n, r1, gb);
+        if (r0 >= 0 && r1 >= 0) fin2(v0, v1, n, r0, gb, pr[0], pr[1]);
+        else if (r0 >= 0) fin1(v0, n, r0, gb, pr[0]);
+        else if (r1 >= 0) fin1(v1, n, r1, gb, pr[1]);
       };
 #pragma unroll
       for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int nt = 0; nt < 6; nt++)
-          if (gval[i]) finish(acc[i][nt][0], acc[i][nt][1], ncol[i], nt, gbase[i]);
+          if (gval[i]) finish(acc[i][nt][0], acc[i][nt][1], ncol[i], nt, gbase[i], pv[i][nt]);
 #pragma unroll
       for (int x = 0; x < XN; x++)
-        if (gval[2]) finish(xacc[x][0], xacc[x][1], ncol[2], xn0 + x, gbase[2]);
+        if (gval[2]) finish(xacc[x][0], xacc[x][1], ncol[2], xn0 + x, gbase[2], xpv[x]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[lslot]);
     }
@@ -507,10 +524,13 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
   }
   __syncthreads();
   const int nst = st.n, ng = p.ngather;
-  if (warp == NCONS) {  // producer warp: identical to k_apply_dmma<.., 4>
-    int cu = 0, ci = blockIdx.x, cj = 0;
+  if (warp == NCONS) {
+    // producer warp.  The spin-diagonal stages are short (30 instead of 45 DMMAs per m-tile), so the neighbour indices
+    // are fetched TWO stages ahead of the copy that needs them (one stage ahead, as in k_apply_dmma, their L2 latency
+    // paces the ring).
     auto count = [&](int u) { return (cnt ? cnt[u] : ntiles) * (DM_S / S); };
     auto settle = [&](int &u, int &i) { while (u < nunits && i >= count(u)) { u++; i = blockIdx.x; } };
+    auto advance = [&](int &u, int &i, int &j) { if (++j == nst) { j = 0; i += gridDim.x; settle(u, i); } };
     auto fetch = [&](int u, int i, int j, int &site, int &cls) {
       const int tpos = i >> 1, half = (i & 1) * S;
       const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
@@ -518,24 +538,26 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
       const int m = st.slot[j];
       site = (lane < S) ? ((m == 0) ? tile_sites[tile * DM_S + half + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + half + lane]) : 0;
     };
+    int cu = 0, ci = blockIdx.x, cj = 0;          // stage being copied
     settle(cu, ci);
-    int site = 0, cls = 0;
-    if (cu < nunits) fetch(cu, ci, cj, site, cls);
+    int u1 = cu, i1 = ci, j1 = cj;                // one stage ahead
+    int site0 = 0, cls0 = 0, site1 = 0, cls1 = 0;
+    if (cu < nunits) { fetch(cu, ci, cj, site0, cls0); advance(u1, i1, j1); if (u1 < nunits) fetch(u1, i1, j1, site1, cls1); }
     for (uint32_t it = 0; cu < nunits; it++) {
-      int nu = cu, ni = ci, nj = cj + 1, nsite = 0, ncls = 0;
-      if (nj == nst) { nj = 0; ni += gridDim.x; settle(nu, ni); }
-      if (nu < nunits) fetch(nu, ni, nj, nsite, ncls);
+      int u2 = u1, i2 = i1, j2 = j1, site2 = 0, cls2 = 0;  // two stages ahead
+      if (u2 < nunits) { advance(u2, i2, j2); if (u2 < nunits) fetch(u2, i2, j2, site2, cls2); }
       const int slot = it % STG;
       mbar_wait(&empty[slot], ((it / STG) & 1) ^ 1);
       double *sm = stages + (size_t)slot * STGD;
       if (lane == 0) mbar_expect_tx(&full[slot], STGD * 8);
       __syncwarp();
       if (lane < S) {
-        bulk_g2s(sm + HBLK + lane * BLKD, st.src[cj] + (size_t)cu * p.vstride + (size_t)site * BLKD, BLKD * 8, &full[slot]);
+        bulk_g2s(sm + HBLK + lane * BLKD, st.src[cj] + (size_t)cu * p.vstride + (size_t)site0 * BLKD, BLKD * 8, &full[slot]);
       } else if (lane == S) {
-        bulk_g2s(sm, st.H[cj] + (size_t)cls * st.hstride[cj], HBLK * 8, &full[slot]);
+        bulk_g2s(sm, st.H[cj] + (size_t)cls0 * st.hstride[cj], HBLK * 8, &full[slot]);
       }
-      cu = nu; ci = ni; cj = nj; site = nsite; cls = ncls;
+      cu = u1; ci = i1; cj = j1; site0 = site1; cls0 = cls1;
+      u1 = u2; i1 = i2; j1 = j2; site1 = site2; cls1 = cls2;
     }
     return;
   }

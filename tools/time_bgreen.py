@@ -14,8 +14,11 @@ if len(sys.argv) > 1:                      # A/B: load an alternative build of t
     _B.LIB = os.path.abspath(sys.argv[1])
 from rslmtoasa_b200 import Recursion, Control, Energy, Green, synthetic as S  # noqa: E402
 
-for name in ("bulk", "surface"):
-    if name == "bulk":
+for name in ("bccfe", "bulk", "surface"):
+    if name == "bccfe":      # the reference's collinear bccFe regression case: hopping blocks are spin-diagonal
+        from oracle import oracle as O, ref_bccfe as R
+        lat, ham, _, _ = R.case_inputs(O, "Example_bulk_bccFe_nsp2_block")
+    elif name == "bulk":
         lat = S.sphere_cluster("bcc", 80.0); ham = S.make_hamiltonian(lat, seed=20260101)
     else:
         lat = S.sphere_cluster("fcc", 100.0, ntype=7, type_rule="layer"); lat.irec = np.array([1, 2, 3, 14, 15, 20], dtype=np.int32)
@@ -32,5 +35,6 @@ for name in ("bulk", "surface"):
     best = 1e9
     for _ in range(7):
         t0 = time.perf_counter(); g.recur_b_green(download_g0=False); best = min(best, time.perf_counter() - t0)
-    print(f"{name}: fused recur_b + green, g0 resident {best * 1e3:.3f} ms", flush=True)
+    print(f"{name}: fused recur_b + green, g0 resident {best * 1e3:.3f} ms  (spin-diagonal SpMV launches: "
+          f"{rec._L.rsrec_spin_diag_launch_count(rec._h)})", flush=True)
     rec.close()
