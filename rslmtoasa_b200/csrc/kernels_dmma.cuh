@@ -418,40 +418,58 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
         }
         mbar_wait(&full[slot], (it / STG) & 1);
         const double *sm = stages + (size_t)slot * STGD;
+        // fragments of step t+1 are loaded before the DMMAs of step t are issued (register double buffering)
         if (st.sd[j]) {
+          double fa[2][3], fb[2][3], fx[2][XN];
+          auto load = [&](int t, int buf) {  // t = 5 * spin + k-step
+            const int sp = t / 5, k = kc[sp][t % 5];
+            fa[buf][0] = sm[arow[0] + k]; fa[buf][1] = sm[arow[1] + k];
 #pragma unroll
-          for (int sp = 0; sp < 2; sp++) {
+            for (int t3 = 0; t3 < 3; t3++) fb[buf][t3] = sm[brow[3 * sp + t3] + k];
+            if (sp == XSPIN) {
+              fa[buf][2] = sm[arow[2] + k];
 #pragma unroll
-            for (int ks = 0; ks < 5; ks++) {
-              const int k = kc[sp][ks];
-              const double a0 = sm[arow[0] + k], a1 = sm[arow[1] + k];
+              for (int x = 0; x < XN; x++) fx[buf][x] = sm[xrow[x] + k];
+            }
+          };
+          load(0, 0);
 #pragma unroll
-              for (int t3 = 0; t3 < 3; t3++) {
-                const int nt = 3 * sp + t3;
-                const double b = sm[brow[nt] + k];
-                dmma(acc[0][nt][0], acc[0][nt][1], a0, b);
-                dmma(acc[1][nt][0], acc[1][nt][1], a1, b);
-              }
-              if (sp == XSPIN) {
-                const double a2 = sm[arow[2] + k];
+          for (int t = 0; t < 10; t++) {
+            const int c = t & 1, sp = t / 5;
+            if (t < 9) load(t + 1, c ^ 1);
 #pragma unroll
-                for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], a2, sm[xrow[x] + k]);
-              }
+            for (int t3 = 0; t3 < 3; t3++) {
+              dmma(acc[0][3 * sp + t3][0], acc[0][3 * sp + t3][1], fa[c][0], fb[c][t3]);
+              dmma(acc[1][3 * sp + t3][0], acc[1][3 * sp + t3][1], fa[c][1], fb[c][t3]);
+            }
+            if (sp == XSPIN) {
+#pragma unroll
+              for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], fa[c][2], fx[c][x]);
             }
           }
         } else {
+          double fa[2][3], fb[2][6], fx[2][XN];
+          auto load = [&](int ks, int buf) {
+            const int k = 4 * ks + q;
+#pragma unroll
+            for (int i = 0; i < 3; i++) fa[buf][i] = sm[arow[i] + k];
+#pragma unroll
+            for (int nt = 0; nt < 6; nt++) fb[buf][nt] = sm[brow[nt] + k];
+#pragma unroll
+            for (int x = 0; x < XN; x++) fx[buf][x] = sm[xrow[x] + k];
+          };
+          load(0, 0);
 #pragma unroll
           for (int ks = 0; ks < 9; ks++) {
-            const int k = 4 * ks + q;
-            const double a0 = sm[arow[0] + k], a1 = sm[arow[1] + k], a2 = sm[arow[2] + k];
+            const int c = ks & 1;
+            if (ks < 8) load(ks + 1, c ^ 1);
 #pragma unroll
             for (int nt = 0; nt < 6; nt++) {
-              const double b = sm[brow[nt] + k];
-              dmma(acc[0][nt][0], acc[0][nt][1], a0, b);
-              dmma(acc[1][nt][0], acc[1][nt][1], a1, b);
+              dmma(acc[0][nt][0], acc[0][nt][1], fa[c][0], fb[c][nt]);
+              dmma(acc[1][nt][0], acc[1][nt][1], fa[c][1], fb[c][nt]);
             }
 #pragma unroll
-            for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], a2, sm[xrow[x] + k]);
+            for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], fa[c][2], fx[c][x]);
           }
         }
         if (j < nst - 1) {
