@@ -549,3 +549,18 @@ def test_spin_diagonal_hoppings_take_the_two_block_kernel(oracle_mod, name, monk
         rec.close()
     for x, y in zip(res["sd"], res["full"]):
         assert relerr(x, y) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["pbc", "pbc_hoh"])
+def test_spin_diagonal_velocity_sets_in_kubo_moments(oracle_mod, name):
+    """Kubo-Bastin moments with collinear blocks: the velocity products v*psi (and vo*, hoh) take the two-block kernel too"""
+    from rslmtoasa_b200 import Recursion, Control, Energy
+    lat, ham = case(name)
+    ham = _collinear(ham)
+    M = 6
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    mu_o = oracle_mod.Oracle(lat, ham).kubo_moments(M, a, b, start_sites=[1, 5])
+    rec = Recursion(ham, lat, Control(cond_ll=M, cond_calctype="per_type"), Energy(EMIN, EMAX), atlist=[1, 5])
+    rec.compute_moments_stochastic()
+    assert rec._L.rsrec_spin_diag_launch_count(rec._h) > 0
+    assert relerr(rec.mu_nm_stochastic, mu_o) < 1e-9
