@@ -320,7 +320,7 @@ __global__ void k_terminf_fix(double *a_inf, double *b_inf, double *a_inf0, doub
 #endif
 #define BG_LD 19  // padded column stride (complex) so that the 16-byte column accesses of 8 lanes hit 8 bank groups
 #define BG_MAT (NB * BG_LD)
-#define BG_WSTRIDE (BG_MAT + NB)  // per-warp shared memory: Q plus the 18 pivot reciprocals
+#define BG_WSTRIDE (BG_MAT + NB + 5)  // per-warp shared memory: Q, the 18 pivot reciprocals, the row permutation (18 ints)
 
 // a_b, b_b: (18,18,ll,na) complex, b_b = B (after zsqr); g: (18,18,nv,na).  Channels ie0..ie0+ie_len-1 (0-based) are
 // written, the rest of g is left untouched (the caller zeroes it, like bgreen's g_out = 0).
@@ -332,6 +332,7 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
   extern __shared__ double2 bg_smem[];
   double2 *sA = bg_smem, *sB = bg_smem + BG_MAT, *Q = bg_smem + 2 * BG_MAT + (threadIdx.x >> 5) * BG_WSTRIDE;
   double2 *dinv = Q + BG_MAT;
+  int *perm = reinterpret_cast<int *>(dinv + NB);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, unit = blockIdx.y;
   const int iel = blockIdx.x * NW + warp;
   const bool live = iel < ie_len;
@@ -376,8 +377,9 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
       }
     }
     __syncwarp();
-    // LU with partial pivoting (zgetrf semantics); `pos` tracks where the permutation sends unit vector e_j
-    int pos = j;
+    // LU with partial pivoting (zgetrf semantics); perm = the row permutation (P x)(i) = x(perm(i))
+    if (act) perm[j] = j;
+    __syncwarp();
     for (int k = 0; k < NB; k++) {
       int p = k;
       if (lane == k) {
@@ -388,7 +390,7 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
         }
       }
       p = __shfl_sync(0xffffffffu, p, k);
-      if (pos == k) pos = p; else if (pos == p) pos = k;
+      if (lane == 0 && p != k) { const int t = perm[k]; perm[k] = perm[p]; perm[p] = t; }
       if (act && p != k) { const double2 t = q[k]; q[k] = q[p]; q[p] = t; }
       __syncwarp();
       if (lane == k) {
@@ -408,10 +410,13 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
       }
       __syncwarp();
     }
-    // column j of the inverse: solve (P A) x = P e_j with the LU factors (registers, fully unrolled)
+    // Q_new(:,j) = B^H (M^-1 B(:,j)): the reference inverts M and multiplies twice (zgetrf, zgetri, two zgemm: green.f90:1317-1323); solving
+    // M x = B(:,j) with the factors gives the same column without forming M^-1 (one 18^3 product less per level; the
+    // results differ by rounding only, parity tolerance 1e-10).  x = P b_j, forward, backward (registers, fully unrolled)
+    const double2 *bc = sB + j * BG_LD;
     double2 x[NB];
 #pragma unroll
-    for (int i = 0; i < NB; i++) x[i] = make_double2(i == pos ? 1.0 : 0.0, 0.0);
+    for (int i = 0; i < NB; i++) x[i] = bc[perm[i]];
 #pragma unroll
     for (int i = 1; i < NB; i++) {
 #pragma unroll
@@ -424,22 +429,6 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
       x[i] = c_mul(x[i], dinv[i]);
     }
     __syncwarp();  // all lanes have read the factors
-    if (act) {
-#pragma unroll
-      for (int i = 0; i < NB; i++) q[i] = x[i];
-    }
-    __syncwarp();
-    // W(:,j) = Qinv B(:,j)  (registers), then Q(:,j) = B^H W(:,j)
-    const double2 *bc = sB + j * BG_LD;
-#pragma unroll
-    for (int i = 0; i < NB; i++) x[i] = make_double2(0.0, 0.0);
-    for (int k = 0; k < NB; k++) {
-      const double2 b = bc[k];
-      const double2 *qk = Q + k * BG_LD;
-#pragma unroll
-      for (int i = 0; i < NB; i++) x[i] = c_add(x[i], c_mul(qk[i], b));
-    }
-    __syncwarp();  // every lane is done reading Qinv
     if (act) {
       for (int i = 0; i < NB; i++) {
         const double2 *bi_ = sB + i * BG_LD;
