@@ -381,32 +381,34 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
     if (act) perm[j] = j;
     __syncwarp();
     for (int k = 0; k < NB; k++) {
-      int p = k;
-      if (lane == k) {
-        double best = fabs(q[k].x) + fabs(q[k].y);
-        for (int i = k + 1; i < NB; i++) {
-          const double v = fabs(q[i].x) + fabs(q[i].y);
-          if (v > best) { best = v; p = i; }
-        }
+      // pivot of column k (izamax rule: first largest |re| + |im| among rows k..17): lane i looks at row i, a shuffle
+      // tree keeps the larger value, the smaller row on ties -- the serial scan by lane k alone was 17 dependent steps
+      double2 *ck = Q + k * BG_LD;
+      const bool below = lane >= k && lane < NB;
+      const double2 mine = below ? ck[lane] : make_double2(0.0, 0.0);
+      double best = below ? fabs(mine.x) + fabs(mine.y) : -1.0;
+      int p = below ? lane : NB;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int op = __shfl_xor_sync(0xffffffffu, p, o);
+        if (ov > best || (ov == best && op < p)) { best = ov; p = op; }
       }
-      p = __shfl_sync(0xffffffffu, p, k);
       if (lane == 0 && p != k) { const int t = perm[k]; perm[k] = perm[p]; perm[p] = t; }
+      // 1/u_kk = conj(u)/|u|^2: one division; kept for the back substitution (x_i /= u_ii becomes a product).
+      // Every lane forms it (u = row p of column k before the swap), lane i scales its own multiplier l_ik.
+      const double2 u = ck[p];
+      const double inv = 1.0 / (u.x * u.x + u.y * u.y);
+      const double2 r = make_double2(u.x * inv, -u.y * inv);
+      __syncwarp();  // column k has been read by every lane
       if (act && p != k) { const double2 t = q[k]; q[k] = q[p]; q[p] = t; }
       __syncwarp();
-      if (lane == k) {
-        // 1/u_kk = conj(u)/|u|^2: one division; kept for the back substitution (x_i /= u_ii becomes a product).
-        // Divisions are the longest dependent operations of the level, 36 of them were on its critical path.
-        const double2 u = q[k];
-        const double inv = 1.0 / (u.x * u.x + u.y * u.y);
-        const double2 r = make_double2(u.x * inv, -u.y * inv);
-        dinv[k] = r;
-        for (int i = k + 1; i < NB; i++) q[i] = c_mul(q[i], r);
-      }
+      if (lane == k) dinv[k] = r;
+      if (lane > k && lane < NB) ck[lane] = c_mul(ck[lane], r);
       __syncwarp();
       if (act && j > k) {
-        const double2 u = q[k];
-        const double2 *lk = Q + k * BG_LD;
-        for (int i = k + 1; i < NB; i++) q[i] = c_sub(q[i], c_mul(lk[i], u));
+        const double2 uj = q[k];
+        for (int i = k + 1; i < NB; i++) q[i] = c_sub(q[i], c_mul(ck[i], uj));
       }
       __syncwarp();
     }
