@@ -23,6 +23,13 @@ __device__ __forceinline__ double2 c_mul(double2 a, double2 b) {
 __device__ __forceinline__ double2 c_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 c_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 c_scale(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+// x - a*b and s + conj(a)*b as four fused multiply-adds (the mul-then-add forms cost six FP64 instructions)
+__device__ __forceinline__ double2 c_fnma(double2 x, double2 a, double2 b) {
+  return make_double2(fma(a.y, b.y, fma(-a.x, b.x, x.x)), fma(-a.y, b.x, fma(-a.x, b.y, x.y)));
+}
+__device__ __forceinline__ double2 c_fma_conj(double2 s, double2 a, double2 b) {
+  return make_double2(fma(a.y, b.y, fma(a.x, b.x, s.x)), fma(-a.y, b.x, fma(a.x, b.y, s.y)));
+}
 // a / b with Smith's scaling (what the compilers' complex division does)
 __device__ __forceinline__ double2 c_div(double2 a, double2 b) {
   if (fabs(b.x) < fabs(b.y)) {
@@ -371,10 +378,9 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
     // Q <- P - A - Q   (own column)
     if (act) {
       const double2 *ac = sA + j * BG_LD;
-      for (int i = 0; i < NB; i++) {
-        const double2 p = i == j ? P : make_double2(0.0, 0.0);
-        q[i] = c_sub(c_sub(p, ac[i]), q[i]);
-      }
+      const double2 qjj = q[j];
+      for (int i = 0; i < NB; i++) q[i] = c_sub(c_sub(make_double2(0.0, 0.0), ac[i]), q[i]);
+      q[j] = c_sub(c_sub(P, ac[j]), qjj);
     }
     __syncwarp();
     // LU with partial pivoting (zgetrf semantics); perm = the row permutation (P x)(i) = x(perm(i))
@@ -408,7 +414,7 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
       __syncwarp();
       if (act && j > k) {
         const double2 uj = q[k];
-        for (int i = k + 1; i < NB; i++) q[i] = c_sub(q[i], c_mul(ck[i], uj));
+        for (int i = k + 1; i < NB; i++) q[i] = c_fnma(q[i], ck[i], uj);
       }
       __syncwarp();
     }
@@ -422,21 +428,22 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
 #pragma unroll
     for (int i = 1; i < NB; i++) {
 #pragma unroll
-      for (int k = 0; k < i; k++) x[i] = c_sub(x[i], c_mul(Q[k * BG_LD + i], x[k]));
+      for (int k = 0; k < i; k++) x[i] = c_fnma(x[i], Q[k * BG_LD + i], x[k]);
     }
 #pragma unroll
     for (int i = NB - 1; i >= 0; i--) {
 #pragma unroll
-      for (int k = i + 1; k < NB; k++) x[i] = c_sub(x[i], c_mul(Q[k * BG_LD + i], x[k]));
+      for (int k = i + 1; k < NB; k++) x[i] = c_fnma(x[i], Q[k * BG_LD + i], x[k]);
       x[i] = c_mul(x[i], dinv[i]);
     }
     __syncwarp();  // all lanes have read the factors
     if (act) {
+#pragma unroll
       for (int i = 0; i < NB; i++) {
         const double2 *bi_ = sB + i * BG_LD;
         double2 s = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int k = 0; k < NB; k++) s = c_add(s, c_mul(make_double2(bi_[k].x, -bi_[k].y), x[k]));
+        for (int k = 0; k < NB; k++) s = c_fma_conj(s, bi_[k], x[k]);
         q[i] = s;
       }
     }
