@@ -143,40 +143,85 @@ __device__ bool sqrt18_newton_schulz(Eig18Smem &s, double *B, double *Bi) {
   s.Ar[tid] = ar / scale; s.Ai[tid] = ai / scale;
   s.Vr[tid] = (r == c) ? 1.0 : 0.0; s.Vi[tid] = 0.0;
   __syncthreads();
+  // The products are register-tiled: 81 threads each own a 2x2 tile of the result (thread-per-element, the matrices in
+  // shared memory, is one shared-memory load per FMA pair and was bound by the shared-memory pipe of the one SM it runs
+  // on: 3.3 us per iteration).  Every element is still the same ascending-k chain of fused multiply-adds, so B and B^-1
+  // are bit-identical to the thread-per-element form.
+  const bool tiled = tid < 81;
+  const int r0 = 2 * (tid % 9), c0 = 2 * (tid / 9);
   bool ok = false;
-  int extra = 0;
   for (int it = 0; it < 120; it++) {
-    // P = Z Y
-    double pr = 0.0, pi = 0.0;
+    // P = Z Y, residual I - P, T = (3I - P)/2
+    bool bad = false, big = false;
+    if (tiled) {
+      double pr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, pi[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-    for (int k = 0; k < NB; k++) {
-      const double zr = s.Vr[r + NB * k], zi = s.Vi[r + NB * k], yr = s.Ar[k + NB * c], yi = s.Ai[k + NB * c];
-      pr = fma(zr, yr, pr); pr = fma(-zi, yi, pr);
-      pi = fma(zr, yi, pi); pi = fma(zi, yr, pi);
+      for (int k = 0; k < NB; k++) {
+        double zr[2], zi[2], yr[2], yi[2];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+          zr[a] = s.Vr[r0 + a + NB * k]; zi[a] = s.Vi[r0 + a + NB * k];
+          yr[a] = s.Ar[k + NB * (c0 + a)]; yi[a] = s.Ai[k + NB * (c0 + a)];
+        }
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            pr[a][b] = fma(zr[a], yr[b], pr[a][b]); pr[a][b] = fma(-zi[a], yi[b], pr[a][b]);
+            pi[a][b] = fma(zr[a], yi[b], pi[a][b]); pi[a][b] = fma(zi[a], yr[b], pi[a][b]);
+          }
+      }
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const bool dg = (r0 + a) == (c0 + b);
+          const double dr = (dg ? 1.0 : 0.0) - pr[a][b], di = -pi[a][b];  // residual I - Z Y
+          bad = bad || !(fabs(dr) < 1e300) || !(fabs(di) < 1e300);
+          big = big || fabs(dr) > 1e-13 || fabs(di) > 1e-13;
+          s.Tr[r0 + a + NB * (c0 + b)] = (dg ? 1.5 : 0.0) - 0.5 * pr[a][b];
+          s.Ti[r0 + a + NB * (c0 + b)] = -0.5 * pi[a][b];
+        }
     }
-    const double dr = ((r == c) ? 1.0 : 0.0) - pr, di = -pi;  // residual I - Z Y
-    const bool bad = !(fabs(dr) < 1e300) || !(fabs(di) < 1e300);
     if (__syncthreads_or(bad)) return false;
-    const int big = __syncthreads_or(fabs(dr) > 1e-13 || fabs(di) > 1e-13);
-    s.Tr[tid] = ((r == c) ? 1.5 : 0.0) - 0.5 * pr; s.Ti[tid] = -0.5 * pi;
-    __syncthreads();
+    const int anybig = __syncthreads_or(big);
     // Y <- Y T, Z <- T Z
-    double yr_ = 0.0, yi_ = 0.0, zr_ = 0.0, zi_ = 0.0;
+    double yr_[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, yi_[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    double zr_[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, zi_[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    if (tiled) {
 #pragma unroll
-    for (int k = 0; k < NB; k++) {
-      const double a1 = s.Ar[r + NB * k], a2 = s.Ai[r + NB * k], t1 = s.Tr[k + NB * c], t2 = s.Ti[k + NB * c];
-      yr_ = fma(a1, t1, yr_); yr_ = fma(-a2, t2, yr_);
-      yi_ = fma(a1, t2, yi_); yi_ = fma(a2, t1, yi_);
-      const double u1 = s.Tr[r + NB * k], u2 = s.Ti[r + NB * k], z1 = s.Vr[k + NB * c], z2 = s.Vi[k + NB * c];
-      zr_ = fma(u1, z1, zr_); zr_ = fma(-u2, z2, zr_);
-      zi_ = fma(u1, z2, zi_); zi_ = fma(u2, z1, zi_);
+      for (int k = 0; k < NB; k++) {
+        double a1[2], a2[2], t1[2], t2[2], u1[2], u2[2], z1[2], z2[2];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+          a1[a] = s.Ar[r0 + a + NB * k]; a2[a] = s.Ai[r0 + a + NB * k];
+          t1[a] = s.Tr[k + NB * (c0 + a)]; t2[a] = s.Ti[k + NB * (c0 + a)];
+          u1[a] = s.Tr[r0 + a + NB * k]; u2[a] = s.Ti[r0 + a + NB * k];
+          z1[a] = s.Vr[k + NB * (c0 + a)]; z2[a] = s.Vi[k + NB * (c0 + a)];
+        }
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            yr_[a][b] = fma(a1[a], t1[b], yr_[a][b]); yr_[a][b] = fma(-a2[a], t2[b], yr_[a][b]);
+            yi_[a][b] = fma(a1[a], t2[b], yi_[a][b]); yi_[a][b] = fma(a2[a], t1[b], yi_[a][b]);
+            zr_[a][b] = fma(u1[a], z1[b], zr_[a][b]); zr_[a][b] = fma(-u2[a], z2[b], zr_[a][b]);
+            zi_[a][b] = fma(u1[a], z2[b], zi_[a][b]); zi_[a][b] = fma(u2[a], z1[b], zi_[a][b]);
+          }
+      }
     }
     __syncthreads();
-    s.Ar[tid] = yr_; s.Ai[tid] = yi_; s.Vr[tid] = zr_; s.Vi[tid] = zi_;
-    __syncthreads();
-    if (!big) {  // residual below 1e-13 BEFORE this (quadratic) update: the iterate is at round-off now
-      if (++extra == 1) { ok = true; break; }
+    if (tiled) {
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int e = r0 + a + NB * (c0 + b);
+          s.Ar[e] = yr_[a][b]; s.Ai[e] = yi_[a][b]; s.Vr[e] = zr_[a][b]; s.Vi[e] = zi_[a][b];
+        }
     }
+    __syncthreads();
+    if (!anybig) { ok = true; break; }  // residual below 1e-13 BEFORE this (quadratic) update: the iterate is at round-off now
   }
   if (!ok) return false;
   const double sq = sqrt(scale);

@@ -27,6 +27,9 @@ __device__ __forceinline__ double2 c_scale(double2 a, double s) { return make_do
 __device__ __forceinline__ double2 c_fnma(double2 x, double2 a, double2 b) {
   return make_double2(fma(a.y, b.y, fma(-a.x, b.x, x.x)), fma(-a.y, b.x, fma(-a.x, b.y, x.y)));
 }
+__device__ __forceinline__ double2 c_fma(double2 s, double2 a, double2 b) {  // s + a*b
+  return make_double2(fma(-a.y, b.y, fma(a.x, b.x, s.x)), fma(a.y, b.x, fma(a.x, b.y, s.y)));
+}
 __device__ __forceinline__ double2 c_fma_conj(double2 s, double2 a, double2 b) {
   return make_double2(fma(a.y, b.y, fma(a.x, b.x, s.x)), fma(-a.y, b.x, fma(a.x, b.y, s.y)));
 }
@@ -498,7 +501,7 @@ k_cheb_green(const double2 *__restrict__ mg, int nk, const double *__restrict__ 
       for (int ii = 0; ii < nch; ii++) {
         const double2 m = mu[(size_t)(i0 + ii) * BLKC + tid];
 #pragma unroll
-        for (int e = 0; e < CG_EB; e++) acc[e] = c_add(acc[e], c_mul(m, f[ii][e]));
+        for (int e = 0; e < CG_EB; e++) acc[e] = c_fma(acc[e], m, f[ii][e]);
       }
     }
   }
@@ -630,7 +633,7 @@ k_cond_contract(const double2 *__restrict__ CN, const double2 *__restrict__ CM, 
       const double2 cm = CM[(size_t)m * nv + ic];
       const double2 G = make_double2(cn.x * tm + cm.x * tn, cn.y * tm + cm.y * tn);
 #pragma unroll
-      for (int l = 0; l < NB; l++) acc[l] = c_add(acc[l], c_mul(G, d[(size_t)m * NB + l]));
+      for (int l = 0; l < NB; l++) acc[l] = c_fma(acc[l], G, d[(size_t)m * NB + l]);
     }
   }
   if (i < nv) {
