@@ -389,6 +389,7 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
     // LU with partial pivoting (zgetrf semantics); perm = the row permutation (P x)(i) = x(perm(i))
     if (act) perm[j] = j;
     __syncwarp();
+#pragma unroll
     for (int k = 0; k < NB; k++) {
       // pivot of column k (izamax rule: first largest |re| + |im| among rows k..17): lane i looks at row i, a shuffle
       // tree keeps the larger value, the smaller row on ties -- the serial scan by lane k alone was 17 dependent steps
@@ -417,6 +418,7 @@ k_bgreen(const double2 *__restrict__ a_b, const double2 *__restrict__ b_b, int l
       __syncwarp();
       if (act && j > k) {
         const double2 uj = q[k];
+#pragma unroll
         for (int i = k + 1; i < NB; i++) q[i] = c_fnma(q[i], ck[i], uj);
       }
       __syncwarp();

@@ -147,7 +147,7 @@ def run_scf_step(name, lat, ham, lld=21, channels=2500):
     rec = Recursion(ham, lat, Control(lld=lld), Energy(EMIN, EMAX, channels_ldos=channels, fermi=0.0))
     g = Green(rec)
     # GPU timings first: the oracle's OpenMP threads keep spinning after a parallel region and steal the launching thread's core
-    t = timed(g.recur_b_green, reps=5)
+    t = timed(g.recur_b_green, reps=15)
     g0_gpu = g.g0
     a_b_gpu = rec.a_b.copy()
     # the same step with g0 left on the device and the `bands` consumers (Fermi level, moments, band energy) run there
@@ -160,7 +160,7 @@ def run_scf_step(name, lat, ham, lld=21, channels=2500):
         b = Bands(g, qqv=6.0 * nu)
         b.calculate_fermi(); b.calculate_magnetic_moments(); b.calculate_moments(); b.calculate_band_energy()
         return b
-    tb = timed(with_bands, reps=5)
+    tb = timed(with_bands, reps=15)
     b = with_bands()
     orc = O.Oracle(lat, ham)
     t0 = time.perf_counter()
