@@ -34,6 +34,12 @@ module rsrec_c_mod
    ! exchange path: pair-unit fused drivers and calculate_intersite_gf
    public :: rsrec_recur_b_ij_green, rsrec_cheb_recur_ij_green, rsrec_intersite_gf, rsrec_conductivity_cumulative
    public :: rsrec_spin_diag_launch_count
+   ! the exchange step of the unit-sharded path (NCCL inside the library) and the per-phase timers (g_timer labels)
+   public :: rsrec_comm_unique_id, rsrec_comm_init, rsrec_comm_destroy, rsrec_comm_info, rsrec_shard_range
+   public :: rsrec_allreduce, rsrec_allgather_units, rsrec_lanczos_block_sharded, rsrec_cheb_moments_random_sum
+   public :: rsrec_phase_timing, rsrec_phase_count, rsrec_phase_label, rsrec_phase_read, rsrec_host_phase_read
+   public :: rsrec_phase_label_f, RSREC_COMM_ID_BYTES
+   integer(c_int), parameter :: RSREC_COMM_ID_BYTES = 128
 
    interface
       function rsrec_last_error() bind(C, name='rsrec_last_error') result(msg)
@@ -509,6 +515,121 @@ module rsrec_c_mod
          integer(c_long_long) :: n
       end function
 
+      ! ---- exchange step: one process per GPU = one MPI rank of the reference (mpi.f90:32-58) ----
+      ! rank 0 creates the id, the host broadcasts its 128 bytes (call MPI_Bcast(id, 128, MPI_BYTE, 0, comm, ierr))
+      function rsrec_comm_unique_id(id128) bind(C, name='rsrec_comm_unique_id') result(rc)
+         import :: c_int, c_signed_char
+         integer(c_signed_char), intent(out) :: id128(*)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_comm_init(h, nranks, rank, id128) bind(C, name='rsrec_comm_init') result(rc)
+         import :: c_ptr, c_int, c_signed_char
+         type(c_ptr), value :: h
+         integer(c_int), value :: nranks, rank
+         integer(c_signed_char), intent(in) :: id128(*)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_comm_destroy(h) bind(C, name='rsrec_comm_destroy') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_comm_info(h, nranks, rank, nccl_version) bind(C, name='rsrec_comm_info') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int), intent(out) :: nranks, rank, nccl_version
+         integer(c_int) :: rc
+      end function
+
+      ! get_mpi_variables (mpi.f90:32-58): first..last = start_atom..end_atom of `rank`
+      function rsrec_shard_range(rank, nranks, nunits, first, last) bind(C, name='rsrec_shard_range') result(rc)
+         import :: c_int
+         integer(c_int), value :: rank, nranks, nunits
+         integer(c_int), intent(out) :: first, last
+         integer(c_int) :: rc
+      end function
+
+      ! MPI_ALLREDUCE(MPI_IN_PLACE, buf, count, .., MPI_SUM) (bands.f90:270-275): dtype 0 real(rp), 1 complex(rp), 2 integer;
+      ! buf = c_loc(array)
+      function rsrec_allreduce(h, buf, count, dtype) bind(C, name='rsrec_allreduce') result(rc)
+         import :: c_ptr, c_int, c_long_long
+         type(c_ptr), value :: h, buf
+         integer(c_long_long), value :: count
+         integer(c_int), value :: dtype
+         integer(c_int) :: rc
+      end function
+
+      ! the MPI_Allgather of per-unit results recursion.f90:1788-1799 leaves commented out; local, full = c_loc(array)
+      function rsrec_allgather_units(h, local, full, doubles_per_unit, nunits_total) &
+         bind(C, name='rsrec_allgather_units') result(rc)
+         import :: c_ptr, c_int, c_long_long
+         type(c_ptr), value :: h, local, full
+         integer(c_long_long), value :: doubles_per_unit
+         integer(c_int), value :: nunits_total
+         integer(c_int) :: rc
+      end function
+
+      ! recur_b / recur_b_ij over all units of the job, a_b/b2_b(18,18,lld,nunits_total) gathered on the device
+      function rsrec_lanczos_block_sharded(h, nunits_total, site_i, site_j, asign, bsign, lld, a_b, b2_b) &
+         bind(C, name='rsrec_lanczos_block_sharded') result(rc)
+         import :: c_ptr, c_int, c_int32_t, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nunits_total, lld
+         integer(c_int32_t), intent(in) :: site_i(*), site_j(*)
+         complex(c_double_complex), intent(in) :: asign(*), bsign(*)
+         complex(c_double_complex), intent(out) :: a_b(18, 18, lld, *), b2_b(18, 18, lld, *)
+         integer(c_int) :: rc
+      end function
+
+      ! stochastic-trace KPM moments summed over the job's random vectors: mu_sum(18,18,2*lld+2)
+      function rsrec_cheb_moments_random_sum(h, nvec_local, phases, lld, a_scale, b_shift, mu_sum) &
+         bind(C, name='rsrec_cheb_moments_random_sum') result(rc)
+         import :: c_ptr, c_int, c_double, c_double_complex
+         type(c_ptr), value :: h
+         integer(c_int), value :: nvec_local, lld
+         real(c_double), intent(in) :: phases(*)
+         real(c_double), value :: a_scale, b_shift
+         complex(c_double_complex), intent(out) :: mu_sum(18, 18, *)
+         integer(c_int) :: rc
+      end function
+
+      ! ---- per-phase device timing under the reference's g_timer labels (recursion.f90:1902-1970, 3104-3127) ----
+      function rsrec_phase_timing(h, enable) bind(C, name='rsrec_phase_timing') result(rc)
+         import :: c_ptr, c_int
+         type(c_ptr), value :: h
+         integer(c_int), value :: enable
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_phase_count() bind(C, name='rsrec_phase_count') result(n)
+         import :: c_int
+         integer(c_int) :: n
+      end function
+
+      function rsrec_phase_label(idx) bind(C, name='rsrec_phase_label') result(label)
+         import :: c_ptr, c_int
+         integer(c_int), value :: idx
+         type(c_ptr) :: label
+      end function
+
+      function rsrec_phase_read(h, ms, calls) bind(C, name='rsrec_phase_read') result(rc)
+         import :: c_ptr, c_int, c_double, c_long_long
+         type(c_ptr), value :: h
+         real(c_double), intent(out) :: ms(*)
+         integer(c_long_long), intent(out) :: calls(*)
+         integer(c_int) :: rc
+      end function
+
+      function rsrec_host_phase_read(h, seconds) bind(C, name='rsrec_host_phase_read') result(rc)
+         import :: c_ptr, c_int, c_double
+         type(c_ptr), value :: h
+         real(c_double), intent(out) :: seconds(*)
+         integer(c_int) :: rc
+      end function
+
    end interface
 
 contains
@@ -530,6 +651,26 @@ contains
       end do
       allocate (character(len=n) :: msg)
       if (n > 0) msg = transfer(p(1:n), msg)
+   end function
+
+   !> g_timer label of phase idx (0-based) as a Fortran string
+   function rsrec_phase_label_f(idx) result(label)
+      integer, intent(in) :: idx
+      character(len=:), allocatable :: label
+      character(kind=c_char), pointer :: p(:)
+      type(c_ptr) :: cp
+      integer :: n
+      cp = rsrec_phase_label(int(idx, c_int))
+      label = ''
+      if (.not. c_associated(cp)) return
+      call c_f_pointer(cp, p, [64])
+      n = 0
+      do while (n < 64)
+         if (p(n + 1) == c_null_char) exit
+         n = n + 1
+      end do
+      allocate (character(len=n) :: label)
+      if (n > 0) label = transfer(p(1:n), label)
    end function
 
    !> maps a non-zero status to the reference's fatal convention (logger.f90:186-193)

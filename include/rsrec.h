@@ -302,6 +302,53 @@ long long rsrec_d2h_bytes(rsrec_handle h);
  * (read synchronises, returns the summed duration and the number of launches, and resets the counters) */
 int rsrec_profile(rsrec_handle h, int enable);
 int rsrec_profile_read(rsrec_handle h, double *total_ms, int *nlaunches);
+/* Per-phase DEVICE timing under the reference's own g_timer labels (recursion.f90:1902-1970 crecal_b: 'H|PSI_n>',
+ * 'H|Psi_n-A_n|Psi_n-B_n|Psi_n-1', 'B_n+1', '<PSI|B_n+1|PSI>'; 3104-3127 / 2454-2478 chebyshev_recur(_ij):
+ * '<PSI_0|PSI_0>', '<PSI_0|PSI_1>', '<PSI_0|PSI_n>'), so the host's profile tree keeps its inner entries:
+ * rsrec_phase_timing(h,1) starts recording CUDA-event pairs around every phase on the handle's stream (0 stops and
+ * resets); rsrec_phase_read synchronises, fills ms[rsrec_phase_count()] / calls[..] (summed since the last read) and
+ * resets.  rsrec_phase_label(i) is the g_timer label of entry i. */
+int rsrec_phase_timing(rsrec_handle h, int enable);
+int rsrec_phase_count(void);
+const char *rsrec_phase_label(int idx);
+int rsrec_phase_read(rsrec_handle h, double *ms, long long *calls);
+/* host wall-clock seconds of the stages of the unit-sharded calls since the last read: seconds[5] = tables (lattice /
+ * Hamiltonian export), plan (active-region levels + unit upload), recursion, exchange (NCCL), download.  Stage boundaries
+ * synchronise the stream only while rsrec_phase_timing is on. */
+int rsrec_host_phase_read(rsrec_handle h, double *seconds);
+
+/* ---- the exchange step of the unit-sharded path ------------------------------------------------
+ * The reference shards independent units (recursion sites, pair vectors, random vectors) over MPI ranks with
+ * get_mpi_variables (mpi.f90:32-58) and sums afterwards with MPI_ALLREDUCE (bands.f90:270-275, self.f90:887).  One process
+ * per GPU: every rank creates its handle, rank 0 calls rsrec_comm_unique_id and broadcasts the 128 bytes with whatever the
+ * host already has (MPI_Bcast in the Fortran host), then every rank calls rsrec_comm_init.  NCCL (dlopen'ed libnccl.so.2)
+ * then runs on the handle's stream directly on the device-resident results.  With a communicator attached:
+ *   - rsrec_bands_dos all-reduces dtot on the device before returning it (bands.f90:276);
+ *   - rsrec_kubo_conductivity with random vectors (start_kind 1) all-reduces the integrand over the ranks' vector shards
+ *     (nstart = 0 is then legal on a rank that owns no vector);
+ *   - rsrec_cheb_moments_random_sum / rsrec_lanczos_block_sharded below exchange their results on the device.
+ * Without a communicator every call below degenerates to the single-rank result. */
+#define RSREC_COMM_ID_BYTES 128
+int rsrec_comm_unique_id(unsigned char *id128);
+int rsrec_comm_init(rsrec_handle h, int nranks, int rank, const unsigned char *id128);
+int rsrec_comm_destroy(rsrec_handle h);
+int rsrec_comm_info(rsrec_handle h, int *nranks, int *rank, int *nccl_version);
+/* get_mpi_variables (mpi.f90:32-58): 1-based inclusive start_atom..end_atom of `rank` for nunits units */
+int rsrec_shard_range(int rank, int nranks, int nunits, int *first, int *last);
+/* MPI_ALLREDUCE(MPI_IN_PLACE, buf, count, <type>, MPI_SUM) of a host array: dtype 0 real(rp), 1 complex(rp), 2 integer */
+int rsrec_allreduce(rsrec_handle h, void *buf, long long count, int dtype);
+/* all-gather of per-unit host results in global unit order (the MPI_Allgather recursion.f90:1788-1799 leaves commented
+ * out): local = this rank's block-rule shard, full = all nunits_total units, doubles_per_unit reals each */
+int rsrec_allgather_units(rsrec_handle h, const void *local, void *full, long long doubles_per_unit, int nunits_total);
+/* recur_b / recur_b_ij over ALL units of the job: each rank runs its shard, a_b/b2_b (18,18,lld,nunits_total) are
+ * gathered on the device and returned on every rank */
+int rsrec_lanczos_block_sharded(rsrec_handle h, int nunits_total, const int32_t *site_i, const int32_t *site_j,
+                                const rsrec_cplx *asign, const rsrec_cplx *bsign, int lld, rsrec_cplx *a_b, rsrec_cplx *b2_b);
+/* stochastic-trace KPM: moments of this rank's random vectors (phases (kk,nvec_local)) summed on the device, all-reduced,
+ * mu_sum (18,18,2*lld+2) = sum over all vectors of the job */
+int rsrec_cheb_moments_random_sum(rsrec_handle h, int nvec_local, const double *phases, int lld, double a_scale,
+                                  double b_shift, rsrec_cplx *mu_sum);
+
 /* select kernel family: 0 = SIMT reference kernels, 1 = DMMA (FP64 tensor core) pipeline (default) */
 int rsrec_set_kernel_family(rsrec_handle h, int family);
 

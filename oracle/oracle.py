@@ -21,7 +21,7 @@ c_vp = C.c_void_p
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("rsrec_oracle.c", "rsrec_oracle_post.c", "rsrec_oracle_lattice.c", "rsrec_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("rsrec_oracle.c", "rsrec_oracle_post.c", "rsrec_oracle_lattice.c", "rsrec_oracle_bands.c", "rsrec_oracle.h")]
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "librsrec_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -30,8 +30,7 @@ def build(force: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()   # no-op unless a source is newer than the .so
         _lib = C.CDLL(_LIB_PATH)
         _lib.orc_create.restype = c_vp
         _lib.orc_create.argtypes = [C.c_int] * 5 + [c_vp, c_vp]
@@ -47,6 +46,7 @@ def lib():
         _lib.orc_cheb_moments_random.argtypes = [c_vp, C.c_int, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
         _lib.orc_cheb_time_steps.argtypes = [c_vp, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
         _lib.orc_kubo_moments.argtypes = [c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, C.c_double, C.c_double, c_vp]
+        _lib.orc_kubo_moments_cols.argtypes = [c_vp, C.c_int, C.c_int, c_vp, c_vp, C.c_int, C.c_double, C.c_double, c_vp, C.c_int, c_vp]
         _lib.orc_zsqr.argtypes = [c_vp, C.c_int, C.c_int]
         _lib.orc_ham_vec_matmul.argtypes = [c_vp, c_vp, c_vp, C.c_double, C.c_double, c_vp]
         _lib.orc_velo_vec_matmul.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp]
@@ -144,6 +144,21 @@ class Oracle:
             n, kind, s = ph.shape[1], 1, None
         mu = np.zeros((18, 18, cond_ll, cond_ll, n), np.complex128, order="F")
         rc = lib().orc_kubo_moments(self.h, n, kind, _p(s), _p(ph), cond_ll, a, b, _p(mu))
+        assert rc == 0
+        return mu
+
+    def kubo_moments_cols(self, cond_ll, a, b, msel, start_sites=None, phases=None):
+        """compute_moments_stochastic restricted to the left indices `msel` (1-based): mu(18,18,cond_ll,len(msel),nstart).
+        Same chains as kubo_moments; for full-size lattices where all cond_ll^2 contractions take minutes on a CPU."""
+        if start_sites is not None:
+            s = np.ascontiguousarray(start_sites, dtype=np.int32)
+            n, kind, ph = len(s), 0, None
+        else:
+            ph = np.asfortranarray(phases, dtype=np.float64)
+            n, kind, s = ph.shape[1], 1, None
+        ms = np.ascontiguousarray(msel, dtype=np.int32)
+        mu = np.zeros((18, 18, cond_ll, len(ms), n), np.complex128, order="F")
+        rc = lib().orc_kubo_moments_cols(self.h, n, kind, _p(s), _p(ph), cond_ll, a, b, _p(ms), len(ms), _p(mu))
         assert rc == 0
         return mu
 

@@ -740,9 +740,11 @@ void orc_velo_vec_matmul(orc_ctx *c, int slot, const cplx *psi_in, cplx *psi_out
   memcpy(izero, c->idum, sizeof(int32_t) * (c->kk + 1));
 }
 
-/* compute_moments_stochastic: recursion.f90:1105-1230 */
-int orc_kubo_moments(orc_ctx *c, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
-                     int M, double a, double b, cplx *mu_nm) {
+/* compute_moments_stochastic: recursion.f90:1105-1230.  msel/nsel (test infrastructure for full-size lattices, where the
+ * M*M contractions take minutes on a CPU): when msel != NULL only the left indices m = msel[0..nsel-1] (1-based) are
+ * contracted and the result is packed as mu(18,18,M,nsel,nstart); the two Chebyshev chains are the same either way. */
+static int kubo_moments_impl(orc_ctx *c, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
+                             int M, double a, double b, const int32_t *msel, int nsel, cplx *mu_nm) {
   const int kk = c->kk;
   const size_t n = (size_t)BLK * kk;
   cplx *psiref = (cplx *)calloc(n, sizeof(cplx)), *w0 = (cplx *)calloc(n, sizeof(cplx));
@@ -797,18 +799,29 @@ int orc_kubo_moments(orc_ctx *c, int nstart, int start_kind, const int32_t *star
       }
       velo_apply(c, c->v_a, c->vo_a, v1, right);
       memcpy(c->izero, c->idum, sizeof(int32_t) * (kk + 1));
+      const int mcount = msel ? nsel : M;
 #pragma omp parallel for schedule(dynamic)
-      for (int m = 1; m <= M; m++) {
+      for (int mi = 1; mi <= mcount; mi++) {
+        const int m = msel ? msel[mi - 1] : mi;
         cplx dum[BLK];
         for (int k = 0; k < BLK; k++) dum[k] = 0.0;
         for (int k = 1; k <= kk; k++) gemm_cn(dum, SBLK(left + n * (size_t)(m - 1), k), SBLK(right, k));
         /* mu_nm_stochastic(:,:,n,m,i) */
-        memcpy(mu_nm + (size_t)BLK * ((size_t)(nn_ - 1) + (size_t)M * ((size_t)(m - 1) + (size_t)M * s)), dum, sizeof(dum));
+        memcpy(mu_nm + (size_t)BLK * ((size_t)(nn_ - 1) + (size_t)M * ((size_t)(mi - 1) + (size_t)mcount * s)), dum, sizeof(dum));
       }
     }
   }
   free(psiref); free(w0); free(w1); free(w2); free(v0); free(v1); free(v2); free(right); free(left);
   return 0;
+}
+int orc_kubo_moments(orc_ctx *c, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
+                     int M, double a, double b, cplx *mu_nm) {
+  return kubo_moments_impl(c, nstart, start_kind, start_sites, phases, M, a, b, NULL, 0, mu_nm);
+}
+int orc_kubo_moments_cols(orc_ctx *c, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
+                          int M, double a, double b, const int32_t *msel, int nsel, cplx *mu_sel) {
+  for (int i = 0; i < nsel; i++) if (msel[i] < 1 || msel[i] > M) return -2;
+  return kubo_moments_impl(c, nstart, start_kind, start_sites, phases, M, a, b, msel, nsel, mu_sel);
 }
 
 /* ===================== create_ll_map (recursion.f90:3277-3303) ===================== */

@@ -63,6 +63,9 @@ int orc_cheb_time_steps(orc_ctx *c, const double *phases, int nsteps, double a, 
  * 1 = random_vec (phases kk x nstart).  mu_nm: 18x18xMxMxnstart. */
 int orc_kubo_moments(orc_ctx *c, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
                      int cond_ll, double a, double b, orc_cplx *mu_nm);
+/* the same chains, contracted only against the left indices msel[0..nsel-1] (1-based): mu_sel(18,18,M,nsel,nstart) */
+int orc_kubo_moments_cols(orc_ctx *c, int nstart, int start_kind, const int32_t *start_sites, const double *phases,
+                          int M, double a, double b, const int32_t *msel, int nsel, orc_cplx *mu_sel);
 /* zsqr: recursion.f90:1980-2023, in place on b2_b(18,18,lld,na). */
 int orc_zsqr(orc_cplx *b2_b, int lld, int na);
 /* single operator applications (ham_vec_matmul 913-977, ham_hoh_vec_matmul 785-911, velo_* 587-783);

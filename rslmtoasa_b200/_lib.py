@@ -23,6 +23,9 @@ SYMBOLS = [
     "rsrec_bands_set_g0", "rsrec_bands_get_g0", "rsrec_bands_g0_shape", "rsrec_bands_dos", "rsrec_bands_fermi",
     "rsrec_bands_magnetic_moments", "rsrec_bands_moments", "rsrec_bands_band_energy",
     "rsrec_recur_b_ij_green", "rsrec_cheb_recur_ij_green", "rsrec_intersite_gf", "rsrec_conductivity_cumulative", "rsrec_spin_diag_launch_count",
+    "rsrec_phase_timing", "rsrec_phase_count", "rsrec_phase_label", "rsrec_phase_read", "rsrec_host_phase_read",
+    "rsrec_comm_unique_id", "rsrec_comm_init", "rsrec_comm_destroy", "rsrec_comm_info", "rsrec_shard_range",
+    "rsrec_allreduce", "rsrec_allgather_units", "rsrec_lanczos_block_sharded", "rsrec_cheb_moments_random_sum",
 ]
 
 
@@ -107,6 +110,20 @@ def load():
     L.rsrec_bands_moments.argtypes = [vp, i, vp, d, d, i, d, vp, vp, vp]
     L.rsrec_bands_band_energy.argtypes = [vp, vp, i, vp, d, d, i, d, vp]
     L.rsrec_set_positions.argtypes = [vp, vp]
+    L.rsrec_phase_timing.argtypes = [vp, i]
+    L.rsrec_phase_label.argtypes = [i]
+    L.rsrec_phase_label.restype = C.c_char_p
+    L.rsrec_phase_read.argtypes = [vp, vp, vp]
+    L.rsrec_host_phase_read.argtypes = [vp, vp]
+    L.rsrec_comm_unique_id.argtypes = [vp]
+    L.rsrec_comm_init.argtypes = [vp, i, i, vp]
+    L.rsrec_comm_destroy.argtypes = [vp]
+    L.rsrec_comm_info.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+    L.rsrec_shard_range.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+    L.rsrec_allreduce.argtypes = [vp, vp, C.c_longlong, i]
+    L.rsrec_allgather_units.argtypes = [vp, vp, vp, C.c_longlong, i]
+    L.rsrec_lanczos_block_sharded.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp]
+    L.rsrec_cheb_moments_random_sum.argtypes = [vp, i, vp, i, d, d, vp]
     _lib = L
     return L
 

@@ -282,3 +282,12 @@ __global__ void k_set_identity(double *m, size_t stride, int n) {  // complex co
     m[(size_t)u * stride + 2 * e + 1] = 0.0;
   }
 }
+
+// acc[e] += sum over units (in unit order: deterministic) of src[u * stride + e]
+__global__ void k_sum_units(const double *__restrict__ src, size_t stride, int nunits, double *__restrict__ acc) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < stride; e += (size_t)gridDim.x * blockDim.x) {
+    double s = acc[e];
+    for (int u = 0; u < nunits; u++) s += src[(size_t)u * stride + e];
+    acc[e] = s;
+  }
+}

@@ -13,8 +13,10 @@
 #include "kernels_lattice.cuh"
 #include "kernels_ham.cuh"
 #include "kernels_bands.cuh"
+#include "comm_nccl.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -46,6 +48,7 @@ struct DevBuf {
 struct rsrec_handle_s {
   int dev = 0, kk = 0, ncols = 0, nslot = 0, ntype = 0, nmax = 0, hoh = 0, ncls = 0;
   int family = 1;
+  bool fam_ok = true;  // every operator application of this handle fits the tensor pipeline's stage list (set by ensure_ready)
   int sms = 148;
   cudaStream_t st = nullptr;
   long long launches = 0;
@@ -57,6 +60,11 @@ struct rsrec_handle_s {
   bool profile = false;                    // record CUDA events around every gather-SpMV launch
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
+  // per-phase device timing under the reference's g_timer labels (recursion.f90:1902-1970, 3104-3127)
+  bool phase_on = false;
+  struct PhaseEv { int phase; cudaEvent_t a, b; };
+  std::vector<PhaseEv> phase_events;
+  size_t phase_used = 0;
   // host copies of the reference arrays (small) so that device sets can be (re)built in any call order
   std::vector<int32_t> nn, iz;
   std::vector<double> pos;  // optional lattice%cr (3,kk): only used to order the work (L2 locality), never in arithmetic
@@ -98,6 +106,13 @@ struct rsrec_handle_s {
     size_t border_cap = 0, bcounts_cap = 0;
     int nblocks = 0;
   } plan;
+  // host wall-clock seconds per stage of a sharded call (rsrec_host_phase_read): tables, plan, recursion, exchange, download
+  double hphase[5] = {0, 0, 0, 0, 0};
+  // NCCL communicator of the unit-sharded job (rsrec_comm_init); null = single rank
+  rs_ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  DevBuf comm_buf;  // staging for collectives on host arrays
+  DevBuf comm_res;  // device-resident results that are exchanged (gathered histories, summed moments)
   // Chebyshev stepping session
   struct {
     bool active = false;
@@ -107,7 +122,46 @@ struct rsrec_handle_s {
   } cheb;
 };
 typedef rsrec_handle_s H;
+// Effective kernel family of a call.  The tensor pipeline lists one stage per gathered slot (DM_MAXST of them); when an
+// operator of this handle needs more (very long neighbour lists), EVERY kernel of the call runs in family 0 -- mixing the
+// families inside one recursion is not supported (the SIMT SpMV has no hpsi output and does not advance the plan).
+static bool fam1(const H *h) { return h->family == 1 && h->fam_ok; }
+// The phases the reference times with g_timer inside crecal_b and chebyshev_recur, in its own words.
+enum Phase { PH_HPSI = 0, PH_ORTHO, PH_BNEXT, PH_ROTATE, PH_MOM0, PH_MOM1, PH_MOMN, PH_COUNT };
+static const char *const kPhaseLabel[PH_COUNT] = {"H|PSI_n>", "H|Psi_n-A_n|Psi_n-B_n|Psi_n-1", "B_n+1", "<PSI|B_n+1|PSI>",
+                                                   "<PSI_0|PSI_0>", "<PSI_0|PSI_1>", "<PSI_0|PSI_n>"};
+// Host wall-clock per stage of a call, for the strong-scaling breakdown: 0 tables (ensure_ready), 1 plan (active-region
+// BFS + unit upload), 2 recursion (enqueue + device time), 3 exchange (NCCL), 4 download.  The stage boundaries are stream
+// synchronisations only while phase timing is on (otherwise a stage's time is its enqueue time and the device time lands in
+// the first stage that synchronises).
+enum HostPhase { HP_TABLES = 0, HP_PLAN, HP_RECUR, HP_EXCHANGE, HP_DOWNLOAD, HP_COUNT };
+struct HostScope {
+  H *h; int k; std::chrono::steady_clock::time_point t0;
+  HostScope(H *h_, int k_) : h(h_), k(k_), t0(std::chrono::steady_clock::now()) {}
+  ~HostScope() {
+    if (h->phase_on) cudaStreamSynchronize(h->st);
+    h->hphase[k] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+// records a CUDA event pair around a phase on the handle's stream while phase timing is enabled (two event records per
+// phase; nothing otherwise)
+struct PhaseScope {
+  H *h; size_t idx = (size_t)-1;
+  PhaseScope(H *h_, int phase) : h(h_) {
+    if (!h->phase_on) return;
+    if (h->phase_used == h->phase_events.size()) {
+      rsrec_handle_s::PhaseEv e; e.phase = phase;
+      if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+      h->phase_events.push_back(e);
+    }
+    idx = h->phase_used++;
+    h->phase_events[idx].phase = phase;
+    cudaEventRecord(h->phase_events[idx].a, h->st);
+  }
+  ~PhaseScope() { if (idx != (size_t)-1) cudaEventRecord(h->phase_events[idx].b, h->st); }
+};
 static int post_configure();
+static int comm_allreduce_dev(rsrec_handle_s *h, double *d, size_t n);
 static int grid_for(size_t n, int threads, int cap);
 
 // ------------------------------------------------------------------------------------------------------------
@@ -158,6 +212,11 @@ static int upload(H *h, DevBuf &b, const std::vector<double> &host) {
 static int ensure_ready(H *h) {
   if (!h->have_lat) return fail(RSREC_EINVAL, "rsrec_set_lattice has not been called");
   if (!h->have_ham) return fail(RSREC_EINVAL, "rsrec_set_hamiltonian has not been called");
+  {  // longest stage list any operator of this handle builds: H (+ the on-site e_nu + l.s stage with hoh), v - vo.(ee.)
+    int maxst = h->ncols + (h->hoh ? 1 : 0);
+    if (h->hoh && (h->have_op[0] || h->have_op[1])) maxst = std::max(maxst, 2 * h->ncols - 1);
+    h->fam_ok = maxst <= DM_MAXST;
+  }
   if (!h->dirty && !h->dirty_ham) return RSREC_OK;
   const int kk = h->kk, nslot = h->nslot, ncls = h->ncls, ng = h->ncols;
   if (h->dirty) {
@@ -315,17 +374,35 @@ static int nctas_for(const H *h, int nunits) {
   return std::max(1, std::min(n, h->kk));
 }
 
-// largest unit batch whose `nvec` work vectors fit in free device memory (keeps 10% headroom)
-static int unit_batch(H *h, int nunits, int nvec) {
+// Device memory the work vectors may use: what is free plus what the vectors with index < nreuse already hold (get_vec
+// re-uses those in place); vectors with a higher index are leftovers of an earlier call with a larger working set (the
+// Kubo left-vector store, for instance) and are released first.  10% headroom.
+static double vec_memory(H *h, int nreuse) {
+  for (size_t i = nreuse; i < h->vecs.size(); i++) dev_free(h->vecs[i]);
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  size_t held = 0;
+  for (size_t i = 0; i < h->vecs.size() && (int)i < nreuse; i++) held += h->vecs[i].n * sizeof(double);
+  return 0.9 * (double)(fr + held);
+}
+// work vectors of one recursion call: psi, pmn / psi0, psi1 (+ hpsi on the tensor pipeline's Lanczos, + the hoh scratch)
+static int lanczos_nvec(const H *h, bool diag) { return 2 + (fam1(h) ? 1 : 0) + ((h->hoh && !diag) ? 1 : 0); }
+static int cheb_nvec(const H *h) { return 2 + (h->hoh ? 1 : 0); }
+// largest unit batch whose `nvec` work vectors (+ extra bytes per unit: histories, a non-resident g0) fit
+static int unit_batch(H *h, int nunits, int nvec, size_t extra_bytes_per_unit = 0) {
+  const double avail = vec_memory(h, 4);  // vecs[0..3] are the recursion drivers' own
+  const size_t per = vstride(h) * sizeof(double) * nvec + extra_bytes_per_unit;
+  int nb = (int)std::max(1.0, std::floor(avail / (double)per));
+  if (const char *f = getenv("RSREC_UNIT_BATCH")) nb = std::max(1, std::min(nb, atoi(f)));  // tests: force small batches
+  return std::min(nunits, nb);
+}
+// how many single block vectors fit next to everything else that is allocated (no clamping: 0 means none)
+static long long vectors_that_fit(H *h) {
   size_t fr = 0, tot = 0;
   cudaMemGetInfo(&fr, &tot);
   size_t held = 0;
   for (auto &v : h->vecs) held += v.n * sizeof(double);
-  double avail = 0.9 * (double)(fr + held);
-  size_t per = vstride(h) * sizeof(double) * nvec;
-  int nb = (int)std::max(1.0, std::floor(avail / (double)per));
-  if (const char *f = getenv("RSREC_UNIT_BATCH")) nb = std::max(1, std::min(nb, atoi(f)));  // tests: force small batches
-  return std::min(nunits, nb);
+  return (long long)std::floor(0.9 * (double)(fr + held) / (double)(vstride(h) * sizeof(double)));
 }
 
 // ---- operator application: out = epilogue( H src ) for a unit batch ---------------------------------------
@@ -337,7 +414,7 @@ enum OpKind { OP_HAM = 0, OP_SCALAR = 1, OP_VELO_A = 2, OP_VELO_B = 3, OP_HAM_NO
 // exact zeros, so results are unchanged.
 static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *site_j) {
   h->plan.on = false;
-  if (h->family != 1 || (size_t)nunits * h->kk > (size_t)64 << 20) return RSREC_OK;
+  if (!fam1(h) || (size_t)nunits * h->kk > (size_t)64 << 20) return RSREC_OK;
   const int kk = h->kk, nt = h->tiles.ntiles;
   if (h->radj_off.empty()) {  // reverse adjacency (CSR): radj[a] = sites i that gather from a (i != a), built on first use
     const int ng = h->ncols;
@@ -431,7 +508,7 @@ static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *si
 static void plan_blocks(const H *h, int nunits, const int32_t **border, const int32_t **bcnt, int *nblocks) {
   *border = nullptr; *bcnt = nullptr; *nblocks = 0;
   static const bool off = getenv("RSREC_NO_BLOCK_PLAN") != nullptr;  // A/B switch for measurements
-  if (!off && h->plan.on && h->plan.nunits == nunits && h->family == 1) {
+  if (!off && h->plan.on && h->plan.nunits == nunits && fam1(h)) {
     *border = h->plan.d_border;
     *bcnt = h->plan.d_bcounts + (size_t)h->plan.level * nunits;
     *nblocks = h->plan.nblocks;
@@ -453,7 +530,8 @@ static int launch_apply(H *h, ApplyParams &p, int nunits, int nctas) {
   return rc;
 }
 static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas) {
-  if (h->family == 1 && dmma_supported(p)) {
+  if (fam1(h)) {
+    if (!dmma_supported(p)) return fail(RSREC_EINVAL, "internal: operator application not supported by the tensor pipeline");
     const int32_t *order = nullptr, *cnt = nullptr;
     if (h->plan.on && h->plan.nunits == nunits) {  // this application reaches level+1
       h->plan.level = std::min(h->plan.level + 1, h->plan.maxlevel);
@@ -514,7 +592,7 @@ static int apply_op(H *h, OpKind op, const double *in, double *out, const double
 // part[unit][cta][0] = sum_sites X^H Y  (first factor conjugated); xs/ys: doubles between units (0 = shared vector)
 static int launch_gram_strided(H *h, const double *X, size_t xs, const double *Y, size_t ys, int nunits, int nctas,
                                double *part) {
-  if (h->family == 1) {
+  if (fam1(h)) {
     // many units in one launch (Kubo contraction): fewer CTAs per unit, the grid is filled by the unit dimension
     const int ctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / nunits));
     const int32_t *bo, *bc; int nbk;
@@ -580,7 +658,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   TRY(get_vec(h, 1, nunits, &pmn));
   if (h->hoh && !diag) TRY(get_vec(h, 2, nunits, &tmp));
   double *hpsi = nullptr;
-  if (h->family == 1) TRY(get_vec(h, 3, nunits, &hpsi));
+  if (fam1(h)) TRY(get_vec(h, 3, nunits, &hpsi));
   TRY(dev_alloc(h->part, part_doubles(h, nunits, nctas), false));
   TRY(dev_alloc(h->A, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->B, (size_t)nunits * BLKD, false));
@@ -601,9 +679,12 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   k_set_identity<<<nunits, 64, 0, h->st>>>(h->b2hist.p, hs, nunits);  // b2temp_b(:,:,1) = I
   k_set_identity<<<nunits, 64, 0, h->st>>>(h->bhist.p, hs, nunits);   // and its square root
   h->launches += 3;
+  const dim3 grid(nctas, nunits);
   for (int ll = 0; ll < lld - 1; ll++) {
     // hop_b / hop_b_hoh: pmn = H psi - pmn ; A = sum psi^H H psi
-    if (h->family == 1) {  // tensor-pipe SpMV: hpsi = H psi, pmn = hpsi - pmn; A = sum psi^H hpsi on the tensor pipe too
+    {
+    PhaseScope ph_(h, PH_HPSI);
+    if (fam1(h)) {  // tensor-pipe SpMV: hpsi = H psi, pmn = hpsi - pmn; A = sum psi^H hpsi on the tensor pipe too
       h->out2 = hpsi;
       TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, nullptr));
       h->out2 = nullptr;
@@ -612,9 +693,11 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
       TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, h->part.p));
     }
     TRY(launch_reduce(h, nunits, nctas, diag ? 2 : 0, h->A.p, nullptr, BLKD, nullptr, nullptr, h->ahist.p + (size_t)ll * BLKD, hs));
+    }
     // pmn -= psi A ; B2 = sum pmn^H pmn
-    dim3 grid(nctas, nunits);
-    if (h->family == 1) {
+    {
+    PhaseScope ph_(h, PH_ORTHO);
+    if (fam1(h)) {
       const int32_t *bo, *bc; int nbk;
       plan_blocks(h, nunits, &bo, &bc, &nbk);
       if (dmma_launch_rmul(RM_ORTHO, psi, pmn, nullptr, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches, bo, bc, nbk) != 0)
@@ -625,13 +708,19 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
       h->last_parts = nctas;
       h->launches++;
     }
+    }
     // B2 -> history slot ll+1, B, B^-1
+    {
+    PhaseScope ph_(h, PH_BNEXT);
     TRY(launch_reduce(h, nunits, nctas, 0, h->B2.p, nullptr, BLKD, nullptr, nullptr));
     k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->B2.p, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
                                          BLKD, diag ? 1 : 0, h->sqrt_method, h->bhist.p + (size_t)(ll + 1) * BLKD);
     h->launches++;
+    }
     // psi = pmn B^-1 ; pmn = psi_old B
-    if (h->family == 1) {
+    {
+    PhaseScope ph_(h, PH_ROTATE);
+    if (fam1(h)) {
       const int32_t *bo, *bc; int nbk;
       plan_blocks(h, nunits, &bo, &bc, &nbk);
       if (dmma_launch_rmul(RM_ROTATE, psi, pmn, nullptr, h->Bi.p, h->B.p, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches, bo, bc, nbk) != 0)
@@ -639,6 +728,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     } else {
       k_lz_rotate_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, h->B.p, h->Bi.p, BLKD, h->kk, vstride(h));
       h->launches++;
+    }
     }
     CUDA_TRY(cudaGetLastError());
   }
@@ -669,11 +759,17 @@ static int cheb_first_moments(H *h) {
   TRY(get_vec(h, 1, c.nunits, &p1));
   if (h->hoh) TRY(get_vec(h, 2, c.nunits, &tmp));
   const size_t ms = (size_t)(2 * c.lld + 2) * BLKD;
-  TRY(launch_gram(h, p0, p0, c.nunits, c.nctas, h->part.p));
-  TRY(launch_reduce(h, c.nunits, c.nctas, 0, h->mu.p, nullptr, ms, nullptr, nullptr));
-  TRY(apply_op(h, OP_HAM, p0, p1, nullptr, tmp, EPI_HAM, c.a, c.b, c.nunits, c.nctas, nullptr));
-  TRY(launch_gram(h, p0, p1, c.nunits, c.nctas, h->part.p));
-  TRY(launch_reduce(h, c.nunits, c.nctas, 0, h->mu.p + BLKD, nullptr, ms, nullptr, nullptr));
+  {
+    PhaseScope ph_(h, PH_MOM0);
+    TRY(launch_gram(h, p0, p0, c.nunits, c.nctas, h->part.p));
+    TRY(launch_reduce(h, c.nunits, c.nctas, 0, h->mu.p, nullptr, ms, nullptr, nullptr));
+  }
+  {
+    PhaseScope ph_(h, PH_MOM1);
+    TRY(apply_op(h, OP_HAM, p0, p1, nullptr, tmp, EPI_HAM, c.a, c.b, c.nunits, c.nctas, nullptr));
+    TRY(launch_gram(h, p0, p1, c.nunits, c.nctas, h->part.p));
+    TRY(launch_reduce(h, c.nunits, c.nctas, 0, h->mu.p + BLKD, nullptr, ms, nullptr, nullptr));
+  }
   c.active = true;
   return RSREC_OK;
 }
@@ -685,10 +781,11 @@ static int cheb_steps(H *h, int nsteps) {
   if (h->hoh) TRY(get_vec(h, 2, c.nunits, &tmp));
   const size_t ms = (size_t)(2 * c.lld + 2) * BLKD;
   for (int s = 0; s < nsteps; s++) {
+    PhaseScope ph_(h, PH_MOMN);
     const int ll = c.done + 1;
     double *p0 = h->vecs[c.i0].p, *p1 = h->vecs[c.i1].p;
     // psi2 = 2 (H psi1 - b psi1)/a - psi0, written over psi0; D1 = sum psi1^H psi1, D2 = sum psi2^H psi1
-    if (h->family == 1) {
+    if (fam1(h)) {
       TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB_NOGRAM, c.a, c.b, c.nunits, c.nctas, nullptr));
       const int gctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / c.nunits));
       const int32_t *bo, *bc; int nbk;
@@ -786,6 +883,9 @@ int rsrec_destroy(rsrec_handle h) {
   if (h->plan.d_bcounts) cudaFree(h->plan.d_bcounts);
   if (h->d_si) { cudaFree(h->d_si); cudaFree(h->d_sj); cudaFree(h->d_as); cudaFree(h->d_bs); }
   for (auto &ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto &ev : h->phase_events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  if (h->comm && nccl_api()->dl) nccl_api()->CommDestroy(h->comm);
+  dev_free(h->comm_buf); dev_free(h->comm_res);
   cudaStreamDestroy(h->st);
   delete h;
   return RSREC_OK;
@@ -840,12 +940,16 @@ int rsrec_lanczos_block(rsrec_handle h, int nunits, const int32_t *site_i, const
   if (!h || nunits < 0 || !a_b || !b2_b || lld < 1 || (nunits > 0 && !site_i)) return fail(RSREC_EINVAL, "rsrec_lanczos_block: bad argument");
   if (nunits == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
-  TRY(ensure_ready(h));
-  const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
+  { HostScope hs_(h, HP_TABLES); TRY(ensure_ready(h)); }
+  const int ub = unit_batch(h, nunits, lanczos_nvec(h, false), (size_t)3 * lld * BLKD * sizeof(double));
   for (int u0 = 0; u0 < nunits; u0 += ub) {
     const int n = std::min(ub, nunits - u0);
-    TRY(upload_units(h, n, site_i + u0, site_j ? site_j + u0 : nullptr, asign ? asign + u0 : nullptr, bsign ? bsign + u0 : nullptr));
-    TRY(plan_build(h, n, site_i + u0, site_j ? site_j + u0 : nullptr));
+    {
+      HostScope hs_(h, HP_PLAN);
+      TRY(upload_units(h, n, site_i + u0, site_j ? site_j + u0 : nullptr, asign ? asign + u0 : nullptr, bsign ? bsign + u0 : nullptr));
+      TRY(plan_build(h, n, site_i + u0, site_j ? site_j + u0 : nullptr));
+    }
+    HostScope hs_(h, HP_RECUR);
     TRY(lanczos_batch(h, n, lld, false, (double *)(a_b + (size_t)u0 * lld * BLKC), (double *)(b2_b + (size_t)u0 * lld * BLKC)));
   }
   return RSREC_OK;
@@ -858,7 +962,7 @@ int rsrec_lanczos_scalar(rsrec_handle h, int nunits, const int32_t *sites, int l
   TRY(ensure_ready(h));
   // The 18 independent scalar recursions of a site (one per start orbital, recursion.f90:3499-3520) are the 18
   // columns of one block vector with diagonal A and B: run them together and keep Re(diag).
-  const int ub = unit_batch(h, nunits, 2);
+  const int ub = unit_batch(h, nunits, lanczos_nvec(h, true), (size_t)3 * lld * BLKD * sizeof(double));
   std::vector<double> ah((size_t)ub * lld * BLKD), bh((size_t)ub * lld * BLKD);
   for (int u0 = 0; u0 < nunits; u0 += ub) {
     const int n = std::min(ub, nunits - u0);
@@ -896,7 +1000,7 @@ int rsrec_cheb_begin_sites(rsrec_handle h, int nunits, const int32_t *site_i, co
   if (!h || nunits < 1 || !site_i) return fail(RSREC_EINVAL, "rsrec_cheb_begin_sites: bad argument");
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
-  if (unit_batch(h, nunits, h->hoh ? 3 : 2) < nunits) return fail(RSREC_ENOMEM, "unit batch does not fit in device memory");
+  if (unit_batch(h, nunits, cheb_nvec(h)) < nunits) return fail(RSREC_ENOMEM, "unit batch does not fit in device memory");
   TRY(upload_units(h, nunits, site_i, site_j, asign, bsign));
   TRY(plan_build(h, nunits, site_i, site_j));
   TRY(cheb_begin_common(h, nunits, lld, a, b));
@@ -915,7 +1019,7 @@ int rsrec_cheb_begin_random(rsrec_handle h, int nvec, const double *phases, int 
   if (!h || nvec < 1 || !phases) return fail(RSREC_EINVAL, "rsrec_cheb_begin_random: bad argument");
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
-  if (unit_batch(h, nvec, h->hoh ? 3 : 2) < nvec) return fail(RSREC_ENOMEM, "vector batch does not fit in device memory");
+  if (unit_batch(h, nvec, cheb_nvec(h)) < nvec) return fail(RSREC_ENOMEM, "vector batch does not fit in device memory");
   h->plan.on = false;  // every site is active from the start
   TRY(cheb_begin_common(h, nvec, lld, a, b));
   double *p0, *p1;
@@ -949,7 +1053,7 @@ int rsrec_cheb_moments(rsrec_handle h, int nunits, const int32_t *site_i, const 
   if (nunits == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
-  const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
+  const int ub = unit_batch(h, nunits, cheb_nvec(h), (size_t)(2 * lld + 2) * BLKD * sizeof(double));
   int rc_all = RSREC_OK;
   for (int u0 = 0; u0 < nunits; u0 += ub) {
     const int n = std::min(ub, nunits - u0);
@@ -967,7 +1071,7 @@ int rsrec_cheb_moments_random(rsrec_handle h, int nvec, const double *phases, in
   if (nvec == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
-  const int ub = unit_batch(h, nvec, h->hoh ? 3 : 2);
+  const int ub = unit_batch(h, nvec, cheb_nvec(h), (size_t)(2 * lld + 2) * BLKD * sizeof(double));
   int rc_all = RSREC_OK;
   for (int u0 = 0; u0 < nvec; u0 += ub) {
     const int n = std::min(ub, nvec - u0);
@@ -1037,7 +1141,7 @@ static int kubo_moments_impl(rsrec_handle h, int nstart, int start_kind, const i
   if (nstart == 0) return RSREC_OK;
   CUDA_TRY(cudaSetDevice(h->dev));
   TRY(ensure_ready(h));
-  const bool gemm = h->family == 1;  // tensor pipeline: batched GEMM contraction (kernels_kubo.cuh)
+  const bool gemm = fam1(h);  // tensor pipeline: batched GEMM contraction (kernels_kubo.cuh)
   // only the diagonals mu(l,l,n,m) are wanted: column-wise contraction, 18x fewer flops (k_kubo_diag)
   static const bool no_diag = getenv("RSREC_NO_KUBO_DIAG") != nullptr;
   const bool diag_only = gemm && !mu_nm && d_diag && !no_diag;
@@ -1045,10 +1149,12 @@ static int kubo_moments_impl(rsrec_handle h, int nstart, int start_kind, const i
   // right vectors kept per contraction: 4 for the full-block GEMM; for the diagonal kernel as many 16-blocks as fit
   int nring = gemm ? KB_NR : 0;
   if (diag_only) {
-    const int fit = unit_batch(h, 1 << 20, 1) - (M4 + 6);
-    nring = std::max(KD_NR, std::min((M + KD_NR - 1) / KD_NR * KD_NR, fit / KD_NR * KD_NR));
+    const long long fit = vectors_that_fit(h) - (M4 + 6);
+    nring = (int)std::max<long long>(KD_NR, std::min<long long>((M + KD_NR - 1) / KD_NR * KD_NR, fit / KD_NR * KD_NR));
   }
-  if (unit_batch(h, 1, M4 + 6 + nring) < 1) return fail(RSREC_ENOMEM, "left-vector storage does not fit in device memory");
+  if (vectors_that_fit(h) < (long long)M4 + 6 + nring)
+    return fail(RSREC_ENOMEM, "rsrec_kubo_moments: the left-vector storage (cond_ll + " + std::to_string(6 + nring) + " block vectors of " +
+                                  std::to_string(vstride(h) * sizeof(double) >> 20) + " MiB) does not fit in device memory");
   h->plan.on = false;
   const int nctas = nctas_for(h, 1);
   // vecs: 0 psiref, 1 tmp(hoh), 2 v0, 3 v1, 4 right, 5 spare, 6 left[m] (batched), 7 ring of KB_NR right vectors
@@ -1306,7 +1412,7 @@ static int d_density(H *h, const double *d_a, const double *d_b2, int lld, int n
 // d_mu: (18,18,M,M,nloop) device moments; outputs on the host.
 // d_mu: (18,18,M,M,nloop) device moments, or null when d_diag_in already holds D[t][n][m][l2].
 static int d_cond_integrand(H *h, const double *d_mu, const double *d_diag_in, int M, int nloop, const double *ene, int nv,
-                            double emin, double emax, int per_type, cplx *integrand, cplx *integrand_at) {
+                            double emin, double emax, int per_type, cplx *integrand, cplx *integrand_at, bool reduce_ranks = false) {
   const double a = (emax - emin) / (2 - 0.3), b = (emax + emin) / 2, de = emax - emin;
   const double factor = 16 / (PI_RP * (de * de));
   std::vector<double> sk;
@@ -1334,6 +1440,9 @@ static int d_cond_integrand(H *h, const double *d_mu, const double *d_diag_in, i
                                                          per_type ? (double2 *)d_at : nullptr);
   h->launches += 4;
   CUDA_TRY(cudaGetLastError());
+  // random vectors sharded over ranks: the integrand is linear in the moments, so the sum over all vectors of the job is
+  // one all-reduce of 18 x nv complex numbers on the device
+  if (reduce_ranks) TRY(comm_allreduce_dev(h, d_int, 2 * (size_t)NB * nv));
   TRY(to_host(h, integrand, d_int, 2 * (size_t)NB * nv));
   if (integrand_at) {
     if (per_type) TRY(to_host(h, integrand_at, d_at, 2 * (size_t)NB * nv * nloop));
@@ -1515,7 +1624,7 @@ static int recur_b_green_impl(rsrec_handle h, int nunits, const int32_t *site_i,
   if (!keep && !g0) return fail(RSREC_ENOMEM, "rsrec_recur_b_green: g0 of all units does not fit on the device; pass a host g0");
   if (keep) TRY(g0_reserve(h, nunits, nv)); else { h->g0_units = 0; h->g0_nv = 0; }
   TRY(to_dev(h, h->post[4], ene, nv));
-  const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
+  const int ub = unit_batch(h, nunits, lanczos_nvec(h, false), (size_t)4 * lld * BLKD * sizeof(double) + (keep ? 0 : (size_t)nv * BLKD * sizeof(double)));
   const size_t hs = (size_t)lld * BLKD;
   for (int u0 = 0; u0 < nunits; u0 += ub) {
     const int n = std::min(ub, nunits - u0);
@@ -1576,7 +1685,7 @@ static int cheb_recur_green_impl(rsrec_handle h, int nunits, const int32_t *site
   if (keep) TRY(g0_reserve(h, nunits, nv)); else { h->g0_units = 0; h->g0_nv = 0; }
   TRY(to_dev(h, h->post[4], ene, nv));
   const double a = (energy_max - energy_min) / (2 - 0.3), b = (energy_max + energy_min) / 2;  // recursion.f90:3078-3079
-  const int ub = unit_batch(h, nunits, h->hoh ? 3 : 2);
+  const int ub = unit_batch(h, nunits, cheb_nvec(h), (size_t)2 * (2 * lld + 2) * BLKD * sizeof(double) + (keep ? 0 : (size_t)nv * BLKD * sizeof(double)));
   const size_t ms = (size_t)(2 * lld + 2) * BLKD;
   std::vector<cplx> mu_tmp;
   int rc_all = RSREC_OK;
@@ -1605,12 +1714,27 @@ static int cheb_recur_green_impl(rsrec_handle h, int nunits, const int32_t *site
 int rsrec_kubo_conductivity(rsrec_handle h, int nstart, int start_kind, const int32_t *start_sites, const double *phases, int M,
                             double energy_min, double energy_max, const double *ene, int nv, cplx *mu_nm, cplx *integrand,
                             cplx *integrand_at) {
-  if (!h || nstart < 1 || M < 1 || nv < 1 || !ene || !integrand || energy_max == energy_min) return fail(RSREC_EINVAL, "rsrec_kubo_conductivity: bad argument");
+  if (!h || nstart < 0 || (nstart == 0 && !(start_kind == 1 && h->comm)) || M < 1 || nv < 1 || !ene || !integrand || energy_max == energy_min)
+    return fail(RSREC_EINVAL, "rsrec_kubo_conductivity: bad argument");
   CUDA_TRY(cudaSetDevice(h->dev));
+  if (nstart == 0) {  // a rank without random vectors of its own still takes part in the exchange
+    const size_t n = 2 * (size_t)NB * nv;
+    TRY(dev_alloc(h->post[7], n, false));
+    CUDA_TRY(cudaMemsetAsync(h->post[7].p, 0, n * sizeof(double), h->st));
+    TRY(comm_allreduce_dev(h, h->post[7].p, n));
+    TRY(to_host(h, integrand, h->post[7].p, n));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    return RSREC_OK;
+  }
   const double a = (energy_max - energy_min) / (2 - 0.3), b = (energy_max + energy_min) / 2;
   TRY(dev_alloc(h->post[11], 2 * (size_t)nstart * M * M * NB, false));
-  TRY(kubo_moments_impl(h, nstart, start_kind, start_sites, phases, M, a, b, mu_nm, h->post[11].p));
-  return d_cond_integrand(h, nullptr, h->post[11].p, M, nstart, ene, nv, energy_min, energy_max, start_kind == 0, integrand, integrand_at);
+  {
+    HostScope hs_(h, HP_RECUR);
+    TRY(kubo_moments_impl(h, nstart, start_kind, start_sites, phases, M, a, b, mu_nm, h->post[11].p));
+  }
+  HostScope hs_(h, HP_EXCHANGE);  // Gamma contraction + all-reduce of the integrand + download
+  return d_cond_integrand(h, nullptr, h->post[11].p, M, nstart, ene, nv, energy_min, energy_max, start_kind == 0, integrand, integrand_at,
+                          start_kind == 1);
 }
 
 }  // extern "C"
@@ -1986,6 +2110,227 @@ int rsrec_profile_read(rsrec_handle h, double *total_ms, int *nlaunches) {
   h->prof_used = 0;
   return RSREC_OK;
 }
+
+// ---- the exchange step of the unit-sharded path: NCCL on the handle's stream ---------------------
+#define NCCL_TRY(x)                                                                                            \
+  do {                                                                                                         \
+    int r_ = (x);                                                                                              \
+    if (r_ != RS_NCCL_SUCCESS) return fail(RSREC_ECUDA, std::string(#x) + ": " + nccl_api()->GetErrorString(r_)); \
+  } while (0)
+
+}  // extern "C"
+// in-place sum of n doubles on the device over all ranks (no-op without a communicator)
+static int comm_allreduce_dev(H *h, double *d, size_t n) {
+  if (!h->comm || h->comm_size == 1 || n == 0) return RSREC_OK;
+  NCCL_TRY(nccl_api()->AllReduce(d, d, n, RS_NCCL_FLOAT64, RS_NCCL_SUM, h->comm, h->st));
+  return RSREC_OK;
+}
+// get_mpi_variables (mpi.f90:32-58): 0-based half-open unit range of a rank
+static void shard_of(int rank, int nranks, long long n, long long *lo, long long *hi) {
+  long long per = n / nranks, rem = n % nranks;
+  if (rank < rem) { per += 1; *lo = rank * per; } else { *lo = rank * per + rem; }
+  *hi = *lo + per;
+}
+// every rank's contiguous shard (block rule) of `full` [nunits][per_unit doubles] is broadcast from its owner: afterwards
+// all ranks hold all units.  `full` is a device buffer; the caller has placed its own shard at its offset.
+static int comm_allgather_units_dev(H *h, double *full, size_t per_unit, long long nunits) {
+  if (!h->comm || h->comm_size == 1) return RSREC_OK;
+  NcclApi *N = nccl_api();
+  NCCL_TRY(N->GroupStart());
+  for (int r = 0; r < h->comm_size; r++) {
+    long long lo, hi;
+    shard_of(r, h->comm_size, nunits, &lo, &hi);
+    if (hi > lo) NCCL_TRY(N->Broadcast(full + (size_t)lo * per_unit, full + (size_t)lo * per_unit, (size_t)(hi - lo) * per_unit, RS_NCCL_FLOAT64, r, h->comm, h->st));
+  }
+  NCCL_TRY(N->GroupEnd());
+  return RSREC_OK;
+}
+extern "C" {
+
+int rsrec_comm_unique_id(unsigned char *id128) {
+  if (!id128) return fail(RSREC_EINVAL, "rsrec_comm_unique_id: null argument");
+  NcclApi *N = nccl_api();
+  if (!N->dl) return fail(RSREC_ECUDA, N->err);
+  rs_ncclUniqueId id;
+  NCCL_TRY(N->GetUniqueId(&id));
+  memcpy(id128, id.internal, RS_NCCL_ID_BYTES);
+  return RSREC_OK;
+}
+
+int rsrec_comm_init(rsrec_handle h, int nranks, int rank, const unsigned char *id128) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks || !id128) return fail(RSREC_EINVAL, "rsrec_comm_init: bad argument");
+  NcclApi *N = nccl_api();
+  if (!N->dl) return fail(RSREC_ECUDA, N->err);
+  CUDA_TRY(cudaSetDevice(h->dev));
+  if (h->comm) { N->CommDestroy(h->comm); h->comm = nullptr; }
+  rs_ncclUniqueId id;
+  memcpy(id.internal, id128, RS_NCCL_ID_BYTES);
+  NCCL_TRY(N->CommInitRank(&h->comm, nranks, id, rank));
+  h->comm_rank = rank; h->comm_size = nranks;
+  return RSREC_OK;
+}
+
+int rsrec_comm_destroy(rsrec_handle h) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  if (h->comm) {
+    CUDA_TRY(cudaSetDevice(h->dev));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    nccl_api()->CommDestroy(h->comm);
+  }
+  h->comm = nullptr; h->comm_rank = 0; h->comm_size = 1;
+  return RSREC_OK;
+}
+
+int rsrec_comm_info(rsrec_handle h, int *nranks, int *rank, int *nccl_version) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  if (nranks) *nranks = h->comm ? h->comm_size : 1;
+  if (rank) *rank = h->comm ? h->comm_rank : 0;
+  if (nccl_version) { *nccl_version = 0; if (h->comm) nccl_api()->GetVersion(nccl_version); }
+  return RSREC_OK;
+}
+
+int rsrec_shard_range(int rank, int nranks, int nunits, int *first, int *last) {
+  if (nranks < 1 || rank < 0 || rank >= nranks || nunits < 0 || !first || !last) return fail(RSREC_EINVAL, "rsrec_shard_range: bad argument");
+  long long lo, hi;
+  shard_of(rank, nranks, nunits, &lo, &hi);
+  *first = (int)lo + 1; *last = (int)hi;  // 1-based inclusive like start_atom / end_atom
+  return RSREC_OK;
+}
+
+// MPI_ALLREDUCE(MPI_IN_PLACE, buf, count, .., MPI_SUM) of a HOST array (bands.f90:270-275): dtype 0 = real(rp),
+// 1 = complex(rp) (count complex numbers), 2 = integer(4).  Staged through the device, reduced over NVLink.
+int rsrec_allreduce(rsrec_handle h, void *buf, long long count, int dtype) {
+  if (!h || count < 0 || (count > 0 && !buf) || dtype < 0 || dtype > 2) return fail(RSREC_EINVAL, "rsrec_allreduce: bad argument");
+  if (!h->comm || h->comm_size == 1 || count == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t bytes = (size_t)count * (dtype == 0 ? 8 : dtype == 1 ? 16 : 4);
+  TRY(dev_alloc(h->comm_buf, (bytes + 7) / 8, false));
+  CUDA_TRY(cudaMemcpyAsync(h->comm_buf.p, buf, bytes, cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (long long)bytes;
+  if (dtype == 2) NCCL_TRY(nccl_api()->AllReduce(h->comm_buf.p, h->comm_buf.p, (size_t)count, RS_NCCL_INT32, RS_NCCL_SUM, h->comm, h->st));
+  else TRY(comm_allreduce_dev(h, h->comm_buf.p, bytes / 8));
+  CUDA_TRY(cudaMemcpyAsync(buf, h->comm_buf.p, bytes, cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)bytes;
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+// The MPI_Allgather of per-unit results the reference has commented out (recursion.f90:1788-1799): `local` holds this
+// rank's units (block rule of get_mpi_variables over nunits_total) with doubles_per_unit reals each; `full` receives all
+// units in global order on every rank.  HOST arrays.
+int rsrec_allgather_units(rsrec_handle h, const void *local, void *full, long long doubles_per_unit, int nunits_total) {
+  if (!h || !full || doubles_per_unit < 1 || nunits_total < 0) return fail(RSREC_EINVAL, "rsrec_allgather_units: bad argument");
+  long long lo, hi;
+  shard_of(h->comm ? h->comm_rank : 0, h->comm ? h->comm_size : 1, nunits_total, &lo, &hi);
+  if (hi > lo && !local) return fail(RSREC_EINVAL, "rsrec_allgather_units: local shard missing");
+  if (!h->comm || h->comm_size == 1) { if (local != full && hi > lo) memcpy(full, local, (size_t)(hi - lo) * doubles_per_unit * 8); return RSREC_OK; }
+  CUDA_TRY(cudaSetDevice(h->dev));
+  const size_t n = (size_t)nunits_total * doubles_per_unit;
+  TRY(dev_alloc(h->comm_buf, n, false));
+  if (hi > lo) { CUDA_TRY(cudaMemcpyAsync(h->comm_buf.p + (size_t)lo * doubles_per_unit, local, (size_t)(hi - lo) * doubles_per_unit * 8, cudaMemcpyHostToDevice, h->st)); h->h2d_bytes += (hi - lo) * doubles_per_unit * 8; }
+  TRY(comm_allgather_units_dev(h, h->comm_buf.p, (size_t)doubles_per_unit, nunits_total));
+  CUDA_TRY(cudaMemcpyAsync(full, h->comm_buf.p, n * 8, cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)(n * 8);
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+// recur_b for ALL nunits_total recursion sites of the job: this rank runs its block-rule shard, the coefficient histories
+// are gathered on the device over NCCL and every rank receives a_b, b2_b (18,18,lld,nunits_total).
+int rsrec_lanczos_block_sharded(rsrec_handle h, int nunits_total, const int32_t *site_i, const int32_t *site_j, const cplx *asign,
+                                const cplx *bsign, int lld, cplx *a_b, cplx *b2_b) {
+  if (!h || nunits_total < 0 || !a_b || !b2_b || lld < 1 || (nunits_total > 0 && !site_i)) return fail(RSREC_EINVAL, "rsrec_lanczos_block_sharded: bad argument");
+  if (nunits_total == 0) return RSREC_OK;
+  CUDA_TRY(cudaSetDevice(h->dev));
+  { HostScope hs_(h, HP_TABLES); TRY(ensure_ready(h)); }
+  long long lo, hi;
+  shard_of(h->comm ? h->comm_rank : 0, h->comm ? h->comm_size : 1, nunits_total, &lo, &hi);
+  const size_t hs = (size_t)lld * BLKD, nall = (size_t)nunits_total * hs;
+  TRY(dev_alloc(h->comm_res, 2 * nall, false));   // gathered a_b | b2_b histories
+  double *g_a = h->comm_res.p, *g_b = g_a + nall;
+  const int nloc = (int)(hi - lo);
+  const int ub = nloc > 0 ? unit_batch(h, nloc, lanczos_nvec(h, false), (size_t)3 * lld * BLKD * sizeof(double)) : 1;
+  for (int u0 = 0; u0 < nloc; u0 += ub) {
+    const int n = std::min(ub, nloc - u0);
+    const size_t g0 = (size_t)lo + u0;
+    {
+      HostScope hs_(h, HP_PLAN);
+      TRY(upload_units(h, n, site_i + g0, site_j ? site_j + g0 : nullptr, asign ? asign + g0 : nullptr, bsign ? bsign + g0 : nullptr));
+      TRY(plan_build(h, n, site_i + g0, site_j ? site_j + g0 : nullptr));
+    }
+    HostScope hs_(h, HP_RECUR);
+    TRY(lanczos_batch(h, n, lld, false, nullptr, nullptr));
+    CUDA_TRY(cudaMemcpyAsync(g_a + g0 * hs, h->ahist.p, (size_t)n * hs * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CUDA_TRY(cudaMemcpyAsync(g_b + g0 * hs, h->b2hist.p, (size_t)n * hs * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  }
+  {
+    HostScope hs_(h, HP_EXCHANGE);
+    TRY(comm_allgather_units_dev(h, g_a, hs, nunits_total));
+    TRY(comm_allgather_units_dev(h, g_b, hs, nunits_total));
+  }
+  HostScope hs_(h, HP_DOWNLOAD);
+  TRY(to_host(h, a_b, g_a, nall));
+  TRY(to_host(h, b2_b, g_b, nall));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  return RSREC_OK;
+}
+
+// Stochastic-trace KPM moments: the local random vectors (phases (kk,nvec_local), this rank's shard) are run, their
+// moments summed on the device, the sum all-reduced over the communicator, and mu_sum (18,18,2*lld+2) = the sum over ALL
+// vectors of the job comes back on every rank -- one download of 2*lld+2 blocks instead of nvec of them plus a host sum.
+int rsrec_cheb_moments_random_sum(rsrec_handle h, int nvec_local, const double *phases, int lld, double a, double b, cplx *mu_sum) {
+  if (!h || nvec_local < 0 || !mu_sum || lld < 0 || (nvec_local > 0 && !phases)) return fail(RSREC_EINVAL, "rsrec_cheb_moments_random_sum: bad argument");
+  CUDA_TRY(cudaSetDevice(h->dev));
+  TRY(ensure_ready(h));
+  const size_t ms = (size_t)(2 * lld + 2) * BLKD;
+  TRY(dev_alloc(h->comm_res, ms, false));
+  CUDA_TRY(cudaMemsetAsync(h->comm_res.p, 0, ms * sizeof(double), h->st));
+  const int ub = nvec_local > 0 ? unit_batch(h, nvec_local, cheb_nvec(h), ms * sizeof(double)) : 1;
+  for (int u0 = 0; u0 < nvec_local; u0 += ub) {
+    const int n = std::min(ub, nvec_local - u0);
+    TRY(rsrec_cheb_begin_random(h, n, phases + (size_t)u0 * h->kk, lld, a, b));
+    TRY(cheb_steps(h, lld));
+    h->cheb.active = false;
+    k_sum_units<<<grid_for(ms, 256, h->sms * 8), 256, 0, h->st>>>(h->mu.p, ms, n, h->comm_res.p);  // fixed unit order
+    h->launches++;
+  }
+  TRY(comm_allreduce_dev(h, h->comm_res.p, ms));
+  TRY(to_host(h, mu_sum, h->comm_res.p, ms));
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  // the reference's divergence guard (recursion.f90:2594) on the summed moments
+  const double *m = (const double *)mu_sum;
+  const double lim = 1000.0 * std::max(1, nvec_local) * (h->comm ? h->comm_size : 1);
+  for (int k = 3; k < 2 * lld + 2; k += 2) {
+    double sre = 0.0;
+    for (int e = 0; e < BLKC; e++) sre += m[(size_t)k * BLKD + 2 * e];
+    if (!(sre <= lim)) return fail(RSREC_EDIVERGED, "Chebyshev moments did not converge. Check energy limits energy_min and energy_max");
+  }
+  return RSREC_OK;
+}
+
+int rsrec_phase_timing(rsrec_handle h, int enable) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  h->phase_on = enable != 0;
+  h->phase_used = 0;
+  return RSREC_OK;
+}
+int rsrec_host_phase_read(rsrec_handle h, double *seconds) {
+  if (!h || !seconds) return fail(RSREC_EINVAL, "rsrec_host_phase_read: bad argument");
+  for (int k = 0; k < HP_COUNT; k++) { seconds[k] = h->hphase[k]; h->hphase[k] = 0.0; }
+  return RSREC_OK;
+}
+int rsrec_phase_count(void) { return PH_COUNT; }
+const char *rsrec_phase_label(int idx) { return (idx >= 0 && idx < PH_COUNT) ? kPhaseLabel[idx] : nullptr; }
+int rsrec_phase_read(rsrec_handle h, double *ms, long long *calls) {
+  if (!h || !ms || !calls) return fail(RSREC_EINVAL, "rsrec_phase_read: bad argument");
+  CUDA_TRY(cudaStreamSynchronize(h->st));
+  for (int p = 0; p < PH_COUNT; p++) { ms[p] = 0.0; calls[p] = 0; }
+  for (size_t i = 0; i < h->phase_used; i++) {
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->phase_events[i].a, h->phase_events[i].b));
+    ms[h->phase_events[i].phase] += t;
+    calls[h->phase_events[i].phase]++;
+  }
+  h->phase_used = 0;
+  return RSREC_OK;
+}
 long long rsrec_launch_count(rsrec_handle h) { return h ? h->launches : 0; }
 long long rsrec_spin_diag_launch_count(rsrec_handle h) { return h ? h->sd_launches : 0; }
 
@@ -2115,6 +2460,7 @@ int rsrec_bands_dos(rsrec_handle h, double *dtot, double *dosia, double *dosial)
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  TRY(comm_allreduce_dev(h, d_dtot, nv));  // MPI_ALLREDUCE of dtot over the unit shards (bands.f90:270-276), on the device
   TRY(to_host(h, dtot, d_dtot, nv));
   if (dosia) TRY(to_host(h, dosia, d_ia, n1));
   if (dosial) TRY(to_host(h, dosial, d_ial, n1 * 18));

@@ -251,12 +251,16 @@ class Conductivity(_Consumer):
             sites = np.ascontiguousarray(rec.atlist, dtype=np.int32)
             nstart, ph = len(sites), None
         else:
+            # random vectors are the units of this path: each rank runs its block-rule shard (mpi.f90:32-58) and the library
+            # all-reduces the integrand over the communicator attached with Recursion.comm_init
             ph = _f(rec.phases, np.float64)
+            s, e = rec._local_units(ph.shape[1])
+            ph = np.asfortranarray(ph[:, s - 1:e])
             nstart, sites = ph.shape[1], None
         mu = np.zeros((NB, NB, M, M, nstart), np.complex128, order="F") if keep_moments else None
         self.integrand = np.zeros((NB, len(ene)), np.complex128, order="F")
-        self.integrand_at = np.zeros((NB, len(ene), nstart), np.complex128, order="F")
-        _lib.check(self._L.rsrec_kubo_conductivity(self._h, nstart, 0 if per_type else 1, _p(sites), _p(ph), M,
+        self.integrand_at = np.zeros((NB, len(ene), max(nstart, 1)), np.complex128, order="F")
+        _lib.check(self._L.rsrec_kubo_conductivity(self._h, nstart, 0 if per_type else 1, _p(sites), _p(ph) if nstart else None, M,
                                                    self.en.energy_min, self.en.energy_max, _p(ene), len(ene), _p(mu),
                                                    _p(self.integrand), _p(self.integrand_at)))
         if keep_moments:

@@ -368,3 +368,90 @@ class Recursion:
 
     def synchronize(self):
         _lib.check(self._L.rsrec_synchronize(self._h))
+
+    # -- per-phase device timing under the reference's g_timer labels (recursion.f90:1902-1970, 3104-3127) ------
+    def phase_timing(self, enable: bool = True):
+        _lib.check(self._L.rsrec_phase_timing(self._h, int(enable)))
+
+    def phase_read(self) -> dict:
+        """-> {g_timer label: (milliseconds on the device, calls)} since the last read."""
+        n = self._L.rsrec_phase_count()
+        ms = np.zeros(n, np.float64)
+        calls = np.zeros(n, np.int64)
+        _lib.check(self._L.rsrec_phase_read(self._h, _p(ms), _p(calls)))
+        return {self._L.rsrec_phase_label(k).decode(): (float(ms[k]), int(calls[k])) for k in range(n) if calls[k]}
+
+    def host_phase_read(self) -> dict:
+        """host wall-clock seconds per stage of the sharded calls since the last read."""
+        sec = np.zeros(5, np.float64)
+        _lib.check(self._L.rsrec_host_phase_read(self._h, _p(sec)))
+        return dict(zip(("tables", "plan", "recursion", "exchange", "download"), (float(x) for x in sec)))
+
+    # -- the exchange step of the unit-sharded path: NCCL inside the library (SURVEY.md 8b/8e) -------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0 creates the NCCL id; the host broadcasts these 128 bytes (MPI_Bcast in the Fortran host)."""
+        buf = (C.c_ubyte * 128)()
+        _lib.check(_lib.load().rsrec_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        _lib.check(self._L.rsrec_comm_init(self._h, nranks, rank, buf))
+        self.rank, self.numprocs = rank, nranks
+
+    def comm_init_torch(self):
+        """bench/tests convenience: the 128-byte id travels over an existing torch.distributed group (any backend)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(world, rank, box[0])
+
+    def comm_destroy(self):
+        _lib.check(self._L.rsrec_comm_destroy(self._h))
+
+    def comm_info(self):
+        n, r, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        _lib.check(self._L.rsrec_comm_info(self._h, C.byref(n), C.byref(r), C.byref(v)))
+        return n.value, r.value, v.value
+
+    def allreduce(self, arr: np.ndarray) -> np.ndarray:
+        """MPI_ALLREDUCE(MPI_IN_PLACE, arr, SUM) of a host array (float64 / complex128 / int32), in place."""
+        kind = {np.dtype(np.float64): 0, np.dtype(np.complex128): 1, np.dtype(np.int32): 2}[arr.dtype]
+        assert arr.flags.f_contiguous or arr.flags.c_contiguous
+        _lib.check(self._L.rsrec_allreduce(self._h, _p(arr), arr.size, kind))
+        return arr
+
+    def allgather_units(self, local: np.ndarray, n_units: int) -> np.ndarray:
+        """per-unit results (last axis = local unit) of all ranks in global unit order (recursion.f90:1788-1799)."""
+        loc = np.asfortranarray(local)
+        full = np.zeros(loc.shape[:-1] + (n_units,), dtype=loc.dtype, order="F")
+        per = int(np.prod(loc.shape[:-1])) * (2 if loc.dtype == np.complex128 else 1)
+        _lib.check(self._L.rsrec_allgather_units(self._h, _p(loc) if loc.size else None, _p(full), per, n_units))
+        return full
+
+    def recur_b_sharded(self):
+        """recur_b over ALL lattice.irec: every rank runs its block-rule shard, a_b/b2_b (18,18,lld,nrec) are gathered on
+        the device over NCCL and returned on every rank."""
+        sites = np.ascontiguousarray(self.lattice.irec, dtype=np.int32)
+        lld, n = self.control.lld, len(sites)
+        self.a_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        self.b2_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        _lib.check(self._L.rsrec_lanczos_block_sharded(self._h, n, _p(sites), None, None, None, lld, _p(self.a_b), _p(self.b2_b)))
+
+    def chebyshev_recur_random_sum(self, phases=None, sharded: bool = True):
+        """stochastic-trace moments: sum over ALL random vectors of the job (this rank runs its shard of the columns of
+        `phases`; the sum over local vectors and over ranks happens on the device) -> mu_sum (18,18,2*lld+2)."""
+        ph = np.asfortranarray(self.phases if phases is None else phases, dtype=np.float64)
+        if sharded:
+            s, e = self._local_units(ph.shape[1])
+            loc = np.asfortranarray(ph[:, s - 1:e])
+        else:                       # `phases` already is this rank's shard (e.g. a pinned staging buffer)
+            loc = ph
+        lld = self.control.lld
+        a, b = self.en.scale_shift()
+        mu = np.zeros((NB, NB, 2 * lld + 2), np.complex128, order="F")
+        _lib.check(self._L.rsrec_cheb_moments_random_sum(self._h, loc.shape[1], _p(loc) if loc.shape[1] else None, lld, a, b, _p(mu)))
+        self.mu_sum = mu
+        return mu
