@@ -349,6 +349,10 @@ int rsrec_lanczos_block_sharded(rsrec_handle h, int nunits_total, const int32_t 
 int rsrec_cheb_moments_random_sum(rsrec_handle h, int nvec_local, const double *phases, int lld, double a_scale,
                                   double b_shift, rsrec_cplx *mu_sum);
 
+/* the 18x18 reductions of a step inside the SpMV kernel (tensor pipeline): lanczos (default 1: A = sum psi^H H psi of hop_b),
+ * cheb (default 0: D1, D2 of chebyshev_recur_ll; measured slower than the separate Gram kernel); -1 leaves a
+ * setting unchanged.  Results agree to rounding either way. */
+int rsrec_set_fusion(rsrec_handle h, int lanczos, int cheb);
 /* select kernel family: 0 = SIMT reference kernels, 1 = DMMA (FP64 tensor core) pipeline (default) */
 int rsrec_set_kernel_family(rsrec_handle h, int family);
 

@@ -14,7 +14,7 @@ SYMBOLS = [
     "rsrec_cheb_moments", "rsrec_cheb_moments_random", "rsrec_kubo_moments", "rsrec_ham_vec_matmul",
     "rsrec_velo_vec_matmul", "rsrec_cheb_begin_random", "rsrec_cheb_begin_sites", "rsrec_cheb_run_steps",
     "rsrec_cheb_end", "rsrec_synchronize", "rsrec_stream", "rsrec_launch_count", "rsrec_set_kernel_family",
-    "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read",
+    "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read", "rsrec_set_fusion",
     "rsrec_bpopt", "rsrec_get_terminf", "rsrec_bgreen", "rsrec_block_green", "rsrec_chebyshev_green", "rsrec_density",
     "rsrec_sgreen", "rsrec_conductivity_integrand", "rsrec_recur_b_green", "rsrec_cheb_recur_green",
     "rsrec_kubo_conductivity", "rsrec_create_ll_map", "rsrec_orbital_moments",
@@ -73,6 +73,7 @@ def load():
     L.rsrec_spin_diag_launch_count.argtypes = [vp]
     L.rsrec_spin_diag_launch_count.restype = C.c_longlong
     L.rsrec_set_kernel_family.argtypes = [vp, i]
+    L.rsrec_set_fusion.argtypes = [vp, i, i]
     L.rsrec_h2d_bytes.argtypes = [vp]
     L.rsrec_h2d_bytes.restype = C.c_longlong
     L.rsrec_d2h_bytes.argtypes = [vp]

@@ -22,7 +22,8 @@ enum Epilogue {
   EPI_HAM = 1,    // out = (acc - b*in)/a                      ham_vec_matmul, recursion.f90:974-976
   EPI_CHEB = 2,   // out = 2*((acc - b*in)/a) - prev; grams     chebyshev_recur_ll, recursion.f90:2557-2592
   EPI_CHEB_NOGRAM = 3,  // same without the two reductions      compute_moments_stochastic, recursion.f90:1164
-  EPI_HOP = 4     // out(pmn) = acc - pmn; A += in^H acc        hop_b, recursion.f90:1638-1647
+  EPI_HOP = 4,    // out(pmn) = acc - pmn; A += in^H acc        hop_b, recursion.f90:1638-1647
+  EPI_HOP_GRAM = 5  // tensor pipeline: EPI_HOP with A = sum in^H (H in) reduced inside the SpMV kernel (no hpsi vector)
 };
 
 struct GatherTerm {

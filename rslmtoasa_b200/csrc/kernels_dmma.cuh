@@ -43,8 +43,19 @@ template <int S> struct ApGeom {
   static constexpr int kStageD = HBLK + S * BLKD;
   static constexpr int kThreads = 32 * (S + 1);
   static constexpr int kSmem = kStages * kStageD * 8 + 64;
+  static constexpr int kSmemGram = kSmem + S * BLKD * 8;   // + the output tile of a pass (operand of the fused Gram products)
   static constexpr int kMinBlocks = S == 8 ? 1 : 2;
 };
+// Gram products fused into the SpMV kernel (S = 4 geometry): 0 none, 1 = A = sum IN^H OUT (EPI_HOP_GRAM), 2 = D1 = sum IN^H IN and
+// D2 = sum OUT^H IN (EPI_CHEB).
+template <int EPI> struct EpiTraits {
+  static constexpr int kGram = EPI == EPI_CHEB ? 2 : EPI == EPI_HOP_GRAM ? 1 : 0;
+  static constexpr bool kCheb = EPI == EPI_CHEB || EPI == EPI_CHEB_NOGRAM;
+  static constexpr bool kHop = EPI == EPI_HOP || EPI == EPI_HOP_GRAM;
+  static constexpr bool kPrev = kCheb || kHop;             // the epilogue reads `prev`
+  static constexpr bool kScale = EPI == EPI_HAM || kCheb;  // (acc - b in)/a
+};
+#define GR_SLOTS 7  // accumulator tiles a consumer warp owns in the fused Gram products
 
 struct DmmaTiles {
   int ntiles = 0, ng = 0, kk = 0;
@@ -99,6 +110,103 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
+
+// ---- Gram products fused into the SpMV kernel --------------------------------------------------------------------------------
+// After the epilogue of a pass the CTA holds, in shared memory and in RI36 layout, the S = 4 site blocks of `in` (the last
+// pipeline stage) and of the fresh output tile (gbuf).  The 18x18 reductions of the step are real DMMA products on those
+// columns, exactly as in k_gram_dmma (Re D(i,j) = <Ycol_i, Xcol_j>, Im D(i,j) = <Ycol_i, J Xcol_j>):
+//   GRAM 2 (chebyshev_recur_ll, recursion.f90:2566-2592): rows 0..17 = IN columns (D1 = IN^H IN), rows 18..35 = OUT columns
+//           (D2 = OUT^H IN); right operand IN.  5 x 5 accumulator tiles: warp w owns m-tile w (5 tiles) and tile (4, w);
+//           warp 0 also (4, 4).
+//   GRAM 1 (hop_b, recursion.f90:1643-1647): rows = IN columns, right operand OUT = H psi.  3 x 5 tiles: warp w < 3 owns
+//           (w, 0..3), warp 3 owns (0..2, 4).
+// Every tile belongs to exactly one warp of the CTA and is accumulated over all passes of the CTA in a fixed order, so the
+// per-CTA partials need no cross-warp reduction and the result is bitwise reproducible.
+template <int GRAM>
+__device__ __forceinline__ void gram_slot_tile(int w, int s, int &mt, int &nt, bool &valid) {
+  if (GRAM == 2) {
+    if (s < 5) { mt = w; nt = s; valid = true; }
+    else if (s == 5) { mt = 4; nt = w; valid = true; }
+    else { mt = 4; nt = 4; valid = (w == 0); }
+  } else {
+    if (w < 3) { mt = w; nt = s; valid = s < 4; }
+    else { mt = s; nt = 4; valid = s < 3; }
+  }
+}
+template <int GRAM, int S, int N>
+__device__ __forceinline__ void gram_run(const double *in_tile, const double *out_tile, int warp, int lane,
+                                         double (&gacc)[GR_SLOTS][2]) {
+  const int g = lane >> 2, q = lane & 3;
+  int aoff[N], boff[N];
+  bool aout[N], bswap[N];
+#pragma unroll
+  for (int s = 0; s < N; s++) {
+    int mt, nt; bool valid;
+    gram_slot_tile<GRAM>(warp, s, mt, nt, valid);
+    const int i = mt * 8 + g, j = nt * 8 + g;
+    // left operand column: GRAM 2: i < 18 -> IN col i, else OUT col i-18;  GRAM 1: IN col i
+    aout[s] = GRAM == 2 && i >= NB;
+    aoff[s] = min(aout[s] ? i - NB : i, NB - 1) * COLD;
+    bswap[s] = j >= NB;
+    boff[s] = min(bswap[s] ? j - NB : j, NB - 1) * COLD;
+  }
+#pragma unroll 1
+  for (int site = 0; site < S; site++) {
+    const double *xin = in_tile + site * BLKD, *xout = out_tile + site * BLKD;
+    const double *rt = GRAM == 2 ? xin : xout;  // right operand
+#pragma unroll
+    for (int ks = 0; ks < 9; ks++) {
+      const int k = 4 * ks + q;
+      const int kj = k < NB ? k + NB : k - NB;   // row of (J X): (J X)[k] = k < 18 ? X[k+18] : -X[k-18]
+      double a[N], b[N];
+#pragma unroll
+      for (int s = 0; s < N; s++) {
+        a[s] = (aout[s] ? xout : xin)[aoff[s] + k];
+        b[s] = rt[boff[s] + (bswap[s] ? kj : k)];
+        if (bswap[s] && k >= NB) b[s] = -b[s];
+      }
+#pragma unroll
+      for (int s = 0; s < N; s++) dmma(gacc[s][0], gacc[s][1], a[s], b[s]);
+    }
+  }
+}
+// the slot count is warp-uniform: branch once, so that no DMMA is ever issued predicated-off
+template <int GRAM, int S>
+__device__ __forceinline__ void gram_accumulate(const double *in_tile, const double *out_tile, int warp, int lane,
+                                                double (&gacc)[GR_SLOTS][2]) {
+  if (GRAM == 2) {
+    if (warp == 0) gram_run<GRAM, S, 7>(in_tile, out_tile, warp, lane, gacc);
+    else gram_run<GRAM, S, 6>(in_tile, out_tile, warp, lane, gacc);
+  } else {
+    if (warp < 3) gram_run<GRAM, S, 4>(in_tile, out_tile, warp, lane, gacc);
+    else gram_run<GRAM, S, 3>(in_tile, out_tile, warp, lane, gacc);
+  }
+}
+// per-CTA partials in the layout k_reduce_parts sums: [2][18 x 18 complex, column-major]
+template <int GRAM>
+__device__ __forceinline__ void gram_flush(double *pp, int warp, int lane, double (&gacc)[GR_SLOTS][2]) {
+  const int g = lane >> 2, q = lane & 3;
+  constexpr int NS = GRAM == 2 ? 7 : 4;
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    int mt, nt; bool valid;
+    gram_slot_tile<GRAM>(warp, s, mt, nt, valid);
+    if (valid) {
+      const int R = mt * 8 + g;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int C = nt * 8 + 2 * q + e;
+        if (R < 2 * NB && C < 2 * NB && (GRAM == 2 || R < NB))
+          pp[(R / NB) * BLKD + 2 * ((R % NB) + NB * (C % NB)) + (C / NB)] = gacc[s][e];
+      }
+    }
+    gacc[s][0] = gacc[s][1] = 0.0;
+  }
+  if (GRAM == 1)  // matrix 1 is not produced: the reduction still reads it
+    for (int e = warp * 32 + lane; e < BLKD; e += 32 * 4) pp[BLKD + e] = 0.0;
+}
+__device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
 // One consumer warp of k_apply_dmma.  XN = number of units this warp owns in its shared m-tile (compile time so that
 // no DMMA is ever issued predicated-off: a predicated-off DMMA still occupies the tensor pipe).
 template <int EPI, bool ADDEND, int XN, int S>
@@ -106,9 +214,14 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
                                               const int32_t *__restrict__ tile_sites, double *stages, uint64_t *full,
                                               uint64_t *empty, int ntiles, int nunits,
                                               const int32_t *__restrict__ order, const int32_t *__restrict__ cnt,
-                                              int warp, int lane) {
+                                              int warp, int lane, double *gbuf) {
+  typedef EpiTraits<EPI> ET;
+  constexpr int GRAM = S == 4 ? ET::kGram : 0;
   const int g = lane >> 2, q = lane & 3;
   const int nst = st.n;
+  double gacc[GR_SLOTS][2];  // fused Gram accumulators of this warp's tiles (GRAM != 0)
+#pragma unroll
+  for (int s = 0; s < GR_SLOTS; s++) gacc[s][0] = gacc[s][1] = 0.0;
   const double inv_a = 1.0 / p.a;  // the epilogue multiplies by 1/a (<= 1 ulp from the reference's division)
   constexpr int STG = ApGeom<S>::kStages, STGD = ApGeom<S>::kStageD;
   // S = 8: 18 m-tiles, warps share m-tiles 16/17;  S = 4: 9 m-tiles, the four warps share m-tile 8
@@ -152,7 +265,7 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
       double2 pv[2][5], xpv[XN];  // prefetched `prev` (psi0) fragments
       for (int j = 0; j < nst; j++, it++) {
         const int slot = it % STG;
-        if ((EPI == EPI_CHEB_NOGRAM || EPI == EPI_HOP) && j == nst - 1) {
+        if (ET::kPrev && j == nst - 1) {
           // issue the epilogue's global loads now; they land while the last stage is being computed
 #pragma unroll
           for (int i = 0; i < 2; i++)
@@ -204,37 +317,45 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
       // ===== epilogue from the accumulator fragments; the last stage (self blocks of `in`) is still held =====
       const int lslot = (it - 1) % STG;
       const double *sm = stages + (size_t)lslot * STGD;
-      auto finish = [&](double v0, double v1, int n, int nt, size_t go, double2 prev) {
+      if (GRAM) consumer_bar(32 * S);  // every warp is done reading the previous pass's output tile
+      auto finish = [&](double v0, double v1, int n, int nt, size_t go, double2 prev, bool valid) {
         if (ADDEND) {
-          const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go));
+          const double2 ad = valid ? __ldg(reinterpret_cast<const double2 *>(p.addend + go)) : make_double2(0.0, 0.0);
           v0 += ad.x; v1 += ad.y;
         }
-        if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
+        if (ET::kScale) {
           const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + nt * 8 + 2 * q);
           v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
-          if (EPI == EPI_CHEB_NOGRAM) { v0 = 2.0 * v0 - prev.x; v1 = 2.0 * v1 - prev.y; }
+          if (ET::kCheb) { v0 = 2.0 * v0 - prev.x; v1 = 2.0 * v1 - prev.y; }
         }
-        if (EPI == EPI_HOP) {  // hop_b: hpsi = H psi (kept for A = psi^H hpsi), pmn = hpsi - pmn (recursion.f90:1641)
-          *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
+        if (ET::kHop) {  // hop_b: hpsi = H psi (kept for A = psi^H hpsi), pmn = hpsi - pmn (recursion.f90:1641)
+          if (GRAM == 1) *reinterpret_cast<double2 *>(gbuf + n * COLD + nt * 8 + 2 * q) = make_double2(v0, v1);
+          else if (valid) *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
           v0 -= prev.x; v1 -= prev.y;
         }
-        *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
+        if (GRAM == 2) *reinterpret_cast<double2 *>(gbuf + n * COLD + nt * 8 + 2 * q) = make_double2(v0, v1);
+        if (valid) *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
       };
 #pragma unroll
       for (int i = 0; i < 2; i++) {
         const int n = (i == 0 ? mt0 : mt1) * 8 + g;
 #pragma unroll
         for (int nt = 0; nt < 5; nt++)
-          if (gval[i] && (nt < 4 || q < 2)) finish(acc[i][nt][0], acc[i][nt][1], n, nt, goff[i] + nt * 8, pv[i][nt]);
+          if ((GRAM || gval[i]) && (nt < 4 || q < 2)) finish(acc[i][nt][0], acc[i][nt][1], n, nt, goff[i] + nt * 8, pv[i][nt], gval[i]);
       }
 #pragma unroll
       for (int x = 0; x < XN; x++) {
         const int nt = x == 0 ? xn0 : xn1;
-        if (gval[2] && (nt < 4 || q < 2)) finish(xacc[x][0], xacc[x][1], mt2 * 8 + g, nt, goff[2] + nt * 8, xpv[x]);
+        if ((GRAM || gval[2]) && (nt < 4 || q < 2)) finish(xacc[x][0], xacc[x][1], mt2 * 8 + g, nt, goff[2] + nt * 8, xpv[x], gval[2]);
+      }
+      if (GRAM) {
+        consumer_bar(32 * S);  // the output tile is complete in shared memory
+        gram_accumulate<GRAM, S>(sm + HBLK, gbuf, warp, lane, gacc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[lslot]);
     }
+    if (GRAM) gram_flush<GRAM>(p.part + ((size_t)u * gridDim.x + blockIdx.x) * (2 * BLKD), warp, lane, gacc);
   }
 }
 
@@ -301,10 +422,11 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
   // shared m-tiles 16/17, so the sub-partitions carry 22/22/23/23 units and the two warps of a sub-partition stay
   // within one unit of each other (both keep the tensor pipe fed).
   //   m-tile 16: w0:n0  w1:n1  w2:n2  w3:n3,n4        m-tile 17: w4:n0  w5:n1  w6:n2,n3  w7:n4
+  double *gbuf = reinterpret_cast<double *>(smem_raw + ApGeom<S>::kSmem);  // output tile of a pass (Gram variants only)
   if (warp == 3 || (S == 8 && warp == 6))
-    dmma_consumer<EPI, ADDEND, 2, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+    dmma_consumer<EPI, ADDEND, 2, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
   else
-    dmma_consumer<EPI, ADDEND, 1, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+    dmma_consumer<EPI, ADDEND, 1, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
 }
 
 // ---- spin-diagonal variant of the SpMV (S = 4 geometry) -----------------------------------------------------------------
@@ -341,8 +463,13 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
                                                  const int32_t *__restrict__ tile_sites, double *stages, uint64_t *full,
                                                  uint64_t *empty, int ntiles, int nunits,
                                                  const int32_t *__restrict__ order, const int32_t *__restrict__ cnt,
-                                                 int warp, int lane) {
+                                                 int warp, int lane, double *gbuf) {
+  typedef EpiTraits<EPI> ET;
+  constexpr int GRAM = ET::kGram;
   constexpr int S = 4;
+  double gacc[GR_SLOTS][2];  // fused Gram accumulators of this warp's tiles (GRAM != 0)
+#pragma unroll
+  for (int s = 0; s < GR_SLOTS; s++) gacc[s][0] = gacc[s][1] = 0.0;
   const int g = lane >> 2, q = lane & 3;
   const int nst = st.n;
   const double inv_a = 1.0 / p.a;
@@ -405,7 +532,7 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
       };
       for (int j = 0; j < nst; j++, it++) {
         const int slot = it % STG;
-        if ((EPI == EPI_CHEB_NOGRAM || EPI == EPI_HOP) && j == nst - 1) {
+        if (ET::kPrev && j == nst - 1) {
           // issue the epilogue's global loads now; they land while the last stage is being computed
 #pragma unroll
           for (int i = 0; i < 2; i++)
@@ -480,47 +607,59 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
       // ===== epilogue: the last stage (self blocks of `in`) is still held =====
       const int lslot = (it - 1) % STG;
       const double *sm = stages + (size_t)lslot * STGD;
-      auto fin1 = [&](double v, int n, int r, size_t gb, double pr) {  // one row
+      if (GRAM) consumer_bar(32 * S);  // every warp is done reading the previous pass's output tile
+      auto fin1 = [&](double v, int n, int r, size_t gb, double pr, bool valid) {  // one row
         const size_t go = gb + r;
-        if (ADDEND) v += __ldg(p.addend + go);
-        if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
+        if (ADDEND && valid) v += __ldg(p.addend + go);
+        if (ET::kScale) {
           v = (v - p.b * sm[HBLK + n * COLD + r]) * inv_a;
-          if (EPI == EPI_CHEB_NOGRAM) v = 2.0 * v - pr;
+          if (ET::kCheb) v = 2.0 * v - pr;
         }
-        if (EPI == EPI_HOP) { p.out2[go] = v; v -= pr; }
-        p.out[go] = v;
+        if (ET::kHop) {
+          if (GRAM == 1) gbuf[n * COLD + r] = v; else if (valid) p.out2[go] = v;
+          v -= pr;
+        }
+        if (GRAM == 2) gbuf[n * COLD + r] = v;
+        if (valid) p.out[go] = v;
       };
-      auto fin2 = [&](double v0, double v1, int n, int r, size_t gb, double pr0, double pr1) {  // two adjacent rows, r even
+      auto fin2 = [&](double v0, double v1, int n, int r, size_t gb, double pr0, double pr1, bool valid) {  // two adjacent rows, r even
         const size_t go = gb + r;
-        if (ADDEND) { const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go)); v0 += ad.x; v1 += ad.y; }
-        if (EPI == EPI_HAM || EPI == EPI_CHEB_NOGRAM) {
+        if (ADDEND && valid) { const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go)); v0 += ad.x; v1 += ad.y; }
+        if (ET::kScale) {
           const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + r);
           v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
-          if (EPI == EPI_CHEB_NOGRAM) { v0 = 2.0 * v0 - pr0; v1 = 2.0 * v1 - pr1; }
+          if (ET::kCheb) { v0 = 2.0 * v0 - pr0; v1 = 2.0 * v1 - pr1; }
         }
-        if (EPI == EPI_HOP) {
-          *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
+        if (ET::kHop) {
+          if (GRAM == 1) *reinterpret_cast<double2 *>(gbuf + n * COLD + r) = make_double2(v0, v1);
+          else if (valid) *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
           v0 -= pr0; v1 -= pr1;
         }
-        *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
+        if (GRAM == 2) *reinterpret_cast<double2 *>(gbuf + n * COLD + r) = make_double2(v0, v1);
+        if (valid) *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
       };
-      auto finish = [&](double v0, double v1, int n, int nt, size_t gb, const double *pr) {
+      auto finish = [&](double v0, double v1, int n, int nt, size_t gb, const double *pr, bool valid) {
         const int r0 = er0[nt], r1 = er1[nt];
-        if (r0 >= 0 && r1 >= 0) fin2(v0, v1, n, r0, gb, pr[0], pr[1]);
-        else if (r0 >= 0) fin1(v0, n, r0, gb, pr[0]);
-        else if (r1 >= 0) fin1(v1, n, r1, gb, pr[1]);
+        if (r0 >= 0 && r1 >= 0) fin2(v0, v1, n, r0, gb, pr[0], pr[1], valid);
+        else if (r0 >= 0) fin1(v0, n, r0, gb, pr[0], valid);
+        else if (r1 >= 0) fin1(v1, n, r1, gb, pr[1], valid);
       };
 #pragma unroll
       for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int nt = 0; nt < 6; nt++)
-          if (gval[i]) finish(acc[i][nt][0], acc[i][nt][1], ncol[i], nt, gbase[i], pv[i][nt]);
+          if (GRAM || gval[i]) finish(acc[i][nt][0], acc[i][nt][1], ncol[i], nt, gbase[i], pv[i][nt], gval[i]);
 #pragma unroll
       for (int x = 0; x < XN; x++)
-        if (gval[2]) finish(xacc[x][0], xacc[x][1], ncol[2], xn0 + x, gbase[2], xpv[x]);
+        if (GRAM || gval[2]) finish(xacc[x][0], xacc[x][1], ncol[2], xn0 + x, gbase[2], xpv[x], gval[2]);
+      if (GRAM) {
+        consumer_bar(32 * S);  // the output tile is complete in shared memory
+        gram_accumulate<GRAM, S>(sm + HBLK, gbuf, warp, lane, gacc);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[lslot]);
     }
+    if (GRAM) gram_flush<GRAM>(p.part + ((size_t)u * gridDim.x + blockIdx.x) * (2 * BLKD), warp, lane, gacc);
   }
 }
 
@@ -579,10 +718,11 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
     }
     return;
   }
-  if (warp == 0) dmma_consumer_sd<EPI, ADDEND, 2, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
-  else if (warp == 1) dmma_consumer_sd<EPI, ADDEND, 1, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
-  else if (warp == 2) dmma_consumer_sd<EPI, ADDEND, 2, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
-  else dmma_consumer_sd<EPI, ADDEND, 1, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+  double *gbuf = reinterpret_cast<double *>(smem_raw + ApGeom<S>::kSmem);  // output tile of a pass (Gram variants only)
+  if (warp == 0) dmma_consumer_sd<EPI, ADDEND, 2, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
+  else if (warp == 1) dmma_consumer_sd<EPI, ADDEND, 1, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
+  else if (warp == 2) dmma_consumer_sd<EPI, ADDEND, 2, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
+  else dmma_consumer_sd<EPI, ADDEND, 1, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
 }
 
 // ---- Gram reductions on the tensor pipe -------------------------------------------------------------------------
@@ -913,6 +1053,9 @@ static int dmma_configure() {
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<8>::kSmem) != cudaSuccess) return -3; \
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3; \
   if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3;
+#define DM_ATTR_GRAM(E, A) \
+  if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmemGram) != cudaSuccess) return -3; \
+  if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmemGram) != cudaSuccess) return -3;
   DM_ATTR(EPI_STORE, false)
   DM_ATTR(EPI_STORE, true)
   DM_ATTR(EPI_HAM, false)
@@ -921,7 +1064,12 @@ static int dmma_configure() {
   DM_ATTR(EPI_CHEB_NOGRAM, true)
   DM_ATTR(EPI_HOP, false)
   DM_ATTR(EPI_HOP, true)
+  DM_ATTR_GRAM(EPI_CHEB, false)
+  DM_ATTR_GRAM(EPI_CHEB, true)
+  DM_ATTR_GRAM(EPI_HOP_GRAM, false)
+  DM_ATTR_GRAM(EPI_HOP_GRAM, true)
 #undef DM_ATTR
+#undef DM_ATTR_GRAM
   if (cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES) != cudaSuccess) return -3;
   if (cudaFuncSetAttribute(k_rmul_dmma<RM_ORTHO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES) != cudaSuccess) return -3;
   if (cudaFuncSetAttribute(k_rmul_dmma<RM_ROTATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES) != cudaSuccess) return -3;
@@ -1007,17 +1155,27 @@ static int dmma_build_tiles(DmmaTiles &t, const std::vector<int32_t> &nbr, const
 
 // The epilogues that read `in` need its self blocks in the last pipeline stage.
 static bool dmma_supported(const ApplyParams &p) {
-  // EPI_CHEB carries reductions: the caller runs EPI_CHEB_NOGRAM + k_gram_dmma instead; EPI_HOP needs out2 (hpsi)
-  if (p.epi == EPI_CHEB || (p.epi == EPI_HOP && !p.out2)) return false;
+  // the epilogues with fused Gram products (S = 4 geometry only) need the partial buffer; EPI_HOP needs out2 (hpsi)
+  if ((p.epi == EPI_CHEB || p.epi == EPI_HOP_GRAM) && !p.part) return false;
+  if (p.epi == EPI_HOP && !p.out2) return false;
   int nst = 0;
   for (int t = 0; t < p.ngterms; t++) nst += p.ngather - p.g[t].first_slot;
   if (p.Hx) nst++;
   if (nst < 1 || nst > DM_MAXST) return false;
-  if (p.epi == EPI_HAM || p.epi == EPI_CHEB_NOGRAM) {
+  // the epilogues that read `in` (and the fused Gram products) need its self blocks in the last pipeline stage
+  if (p.epi == EPI_HAM || p.epi == EPI_CHEB_NOGRAM || p.epi == EPI_CHEB || p.epi == EPI_HOP_GRAM) {
     if (p.Hx) return p.srcx == p.in;
     return p.ngterms == 1 && p.g[0].first_slot == 0 && p.g[0].src == p.in;
   }
   return true;
+}
+static int dmma_apply_geom() {
+  static const int geom = getenv("RSREC_APPLY_S") ? atoi(getenv("RSREC_APPLY_S")) : DM_APPLY_S;
+  return geom;
+}
+// CTAs of an SpMV launch = per-unit partial-sum slots the fused Gram variants write
+static int dmma_apply_grid(const DmmaTiles &t, int sms) {
+  return dmma_apply_geom() == 4 ? std::max(1, std::min(2 * t.ntiles, 2 * sms)) : std::max(1, std::min(t.ntiles, sms));
 }
 static int dmma_grid(const DmmaTiles &t, int sms) { return std::max(1, std::min(t.ntiles, sms)); }
 static int dmma_gram_ctas(int kk, int sms) { return std::max(1, std::min(sms, (kk + GR_WARPS - 1) / GR_WARPS)); }
@@ -1026,7 +1184,7 @@ static int dmma_gram_ctas(int kk, int sms) { return std::max(1, std::min(sms, (k
 typedef bool (*SdLookup)(const void *ctx, const double *Hset, int slot);
 static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, cudaStream_t st, long long *launches,
                              const int32_t *order = nullptr, const int32_t *cnt = nullptr, SdLookup sdl = nullptr,
-                             const void *sdctx = nullptr, long long *sd_launches = nullptr) {
+                             const void *sdctx = nullptr, long long *sd_launches = nullptr, int *nparts_out = nullptr) {
   DmmaStages sg;
   memset(&sg, 0, sizeof(sg));
   sg.n = 0;
@@ -1066,15 +1224,28 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
       k_apply_dmma<E, A, 8><<<grid, ApGeom<8>::kThreads, ApGeom<8>::kSmem, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,       \
                                                                               t.ntiles, nunits, order, cnt);             \
   } while (0)
+#define DM_LAUNCH_GRAM(E, A)                                                                                              \
+  do {                                                                                                                    \
+    if (use_sd)                                                                                                           \
+      k_apply_dmma_sd<E, A><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmemGram, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,   \
+                                                                                  t.ntiles, nunits, order, cnt);         \
+    else                                                                                                                  \
+      k_apply_dmma<E, A, 4><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmemGram, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,   \
+                                                                                  t.ntiles, nunits, order, cnt);         \
+  } while (0)
   const bool ad = p.addend != nullptr;
+  if (nparts_out) *nparts_out = grid;
   switch (p.epi) {
     case EPI_STORE: if (ad) DM_LAUNCH(EPI_STORE, true); else DM_LAUNCH(EPI_STORE, false); break;
     case EPI_HAM: if (ad) DM_LAUNCH(EPI_HAM, true); else DM_LAUNCH(EPI_HAM, false); break;
     case EPI_CHEB_NOGRAM: if (ad) DM_LAUNCH(EPI_CHEB_NOGRAM, true); else DM_LAUNCH(EPI_CHEB_NOGRAM, false); break;
     case EPI_HOP: if (ad) DM_LAUNCH(EPI_HOP, true); else DM_LAUNCH(EPI_HOP, false); break;
+    case EPI_CHEB: if (geom != 4) return -1; if (ad) DM_LAUNCH_GRAM(EPI_CHEB, true); else DM_LAUNCH_GRAM(EPI_CHEB, false); break;
+    case EPI_HOP_GRAM: if (geom != 4) return -1; if (ad) DM_LAUNCH_GRAM(EPI_HOP_GRAM, true); else DM_LAUNCH_GRAM(EPI_HOP_GRAM, false); break;
     default: return -1;
   }
 #undef DM_LAUNCH
+#undef DM_LAUNCH_GRAM
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -48,6 +48,7 @@ struct DevBuf {
 struct rsrec_handle_s {
   int dev = 0, kk = 0, ncols = 0, nslot = 0, ntype = 0, nmax = 0, hoh = 0, ncls = 0;
   int family = 1;
+  bool fuse_lanczos = true, fuse_cheb = false;  // Gram products inside the SpMV kernel (rsrec_set_fusion)
   bool fam_ok = true;  // every operator application of this handle fits the tensor pipeline's stage list (set by ensure_ready)
   int sms = 148;
   cudaStream_t st = nullptr;
@@ -386,7 +387,15 @@ static double vec_memory(H *h, int nreuse) {
   return 0.9 * (double)(fr + held);
 }
 // work vectors of one recursion call: psi, pmn / psi0, psi1 (+ hpsi on the tensor pipeline's Lanczos, + the hoh scratch)
-static int lanczos_nvec(const H *h, bool diag) { return 2 + (fam1(h) ? 1 : 0) + ((h->hoh && !diag) ? 1 : 0); }
+// The 18x18 reduction of a Lanczos step (A = sum psi^H H psi) runs inside the SpMV kernel (north star: SpMV + three-term
+// update + dot products in one pass): one launch and one block vector (hpsi) less, same speed within noise on configs 1-3
+// (DESIGN.md 4).  RSREC_NO_FUSED_GRAM=1 restores the separate k_gram_dmma launch (A/B switch), as does the S = 8 geometry.
+static bool fused_gram(const H *h) { return fam1(h) && h->fuse_lanczos && dmma_apply_geom() == 4; }
+// The same fusion for chebyshev_recur_ll (D1, D2 inside the SpMV kernel) exists but is OFF by default: both kernels are bound
+// by the FP64 tensor pipe, the stand-alone Gram kernel keeps it 96 % busy, and the fused form measured 27.8 ms per step
+// against 26.4 ms at 10^6 sites (profiles/r02b_*).  RSREC_FUSED_CHEB=1 turns it on.
+static bool fused_cheb(const H *h) { return fam1(h) && h->fuse_cheb && dmma_apply_geom() == 4; }
+static int lanczos_nvec(const H *h, bool diag) { return 2 + ((fam1(h) && !fused_gram(h)) ? 1 : 0) + ((h->hoh && !diag) ? 1 : 0); }
 static int cheb_nvec(const H *h) { return 2 + (h->hoh ? 1 : 0); }
 // largest unit batch whose `nvec` work vectors (+ extra bytes per unit: histories, a non-resident g0) fit
 static int unit_batch(H *h, int nunits, int nvec, size_t extra_bytes_per_unit = 0) {
@@ -543,9 +552,10 @@ static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas) {
       auto itf = mp.find(Hset);
       return itf != mp.end() && slot < (int)itf->second.size() && itf->second[slot];
     };
-    if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches, order, cnt, sdl, h, &h->sd_launches) != 0)
+    int nparts = 0;
+    if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches, order, cnt, sdl, h, &h->sd_launches, &nparts) != 0)
       return fail(RSREC_ECUDA, std::string("k_apply_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
-    h->last_parts = 0;
+    h->last_parts = (p.epi == EPI_CHEB || p.epi == EPI_HOP_GRAM) ? nparts : 0;  // one partial slot per CTA of the launch
     return RSREC_OK;
   }
   h->last_parts = nctas;
@@ -616,7 +626,8 @@ static int launch_gram(H *h, const double *X, const double *Y, int nunits, int n
 static size_t part_doubles(const H *h, int nunits, int nctas) {
   const int simt = std::max(1, std::min(nctas, (6 * h->sms + nunits - 1) / nunits));
   const int dm = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / nunits));
-  return (size_t)nunits * std::max(std::max(simt, dm), std::min(nctas, nctas_for(h, nunits))) * 2 * BLKD;
+  const int fused = h->tiles.ntiles > 0 ? dmma_apply_grid(h->tiles, h->sms) : 2 * h->sms;
+  return (size_t)nunits * std::max(std::max(std::max(simt, dm), fused), std::min(nctas, nctas_for(h, nunits))) * 2 * BLKD;
 }
 static int launch_reduce(H *h, int nunits, int /*nctas*/, int mode, double *d0, double *d1, size_t dstride,
                          const double *m0, const double *m1, double *hist0 = nullptr, size_t hstride = 0) {
@@ -658,7 +669,8 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   TRY(get_vec(h, 1, nunits, &pmn));
   if (h->hoh && !diag) TRY(get_vec(h, 2, nunits, &tmp));
   double *hpsi = nullptr;
-  if (fam1(h)) TRY(get_vec(h, 3, nunits, &hpsi));
+  const bool fused = fused_gram(h);
+  if (fam1(h) && !fused) TRY(get_vec(h, 3, nunits, &hpsi));
   TRY(dev_alloc(h->part, part_doubles(h, nunits, nctas), false));
   TRY(dev_alloc(h->A, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->B, (size_t)nunits * BLKD, false));
@@ -684,7 +696,9 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     // hop_b / hop_b_hoh: pmn = H psi - pmn ; A = sum psi^H H psi
     {
     PhaseScope ph_(h, PH_HPSI);
-    if (fam1(h)) {  // tensor-pipe SpMV: hpsi = H psi, pmn = hpsi - pmn; A = sum psi^H hpsi on the tensor pipe too
+    if (fused) {    // one kernel: pmn = H psi - pmn and the per-CTA partials of A = sum psi^H (H psi)
+      TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP_GRAM, 1.0, 0.0, nunits, nctas, h->part.p));
+    } else if (fam1(h)) {  // tensor-pipe SpMV: hpsi = H psi, pmn = hpsi - pmn; A = sum psi^H hpsi on the tensor pipe too
       h->out2 = hpsi;
       TRY(apply_op(h, diag ? OP_SCALAR : OP_HAM, psi, pmn, pmn, tmp, EPI_HOP, 1.0, 0.0, nunits, nctas, nullptr));
       h->out2 = nullptr;
@@ -785,7 +799,9 @@ static int cheb_steps(H *h, int nsteps) {
     const int ll = c.done + 1;
     double *p0 = h->vecs[c.i0].p, *p1 = h->vecs[c.i1].p;
     // psi2 = 2 (H psi1 - b psi1)/a - psi0, written over psi0; D1 = sum psi1^H psi1, D2 = sum psi2^H psi1
-    if (fam1(h)) {
+    if (fused_cheb(h)) {  // SpMV + three-term update + D1, D2 partials in one kernel
+      TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB, c.a, c.b, c.nunits, c.nctas, h->part.p));
+    } else if (fam1(h)) {
       TRY(apply_op(h, OP_HAM, p1, p0, p0, tmp, EPI_CHEB_NOGRAM, c.a, c.b, c.nunits, c.nctas, nullptr));
       const int gctas = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / c.nunits));
       const int32_t *bo, *bc; int nbk;
@@ -852,6 +868,8 @@ int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, in
   h->ncls = ntype + nmax; h->sms = prop.multiProcessorCount;
   if (const char *f = getenv("RSREC_KERNEL_FAMILY")) h->family = atoi(f);
   if (const char *f = getenv("RSREC_SQRT_METHOD")) h->sqrt_method = atoi(f);
+  if (getenv("RSREC_NO_FUSED_GRAM")) h->fuse_lanczos = false;
+  if (getenv("RSREC_FUSED_CHEB")) h->fuse_cheb = true;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
   if (dmma_configure() != 0 || kubo_configure() != 0 || kdiag_configure() != 0 || post_configure() != 0 || ham_configure() != 0 || bands_configure() != 0) {
     cudaStreamDestroy(h->st);
@@ -894,6 +912,13 @@ int rsrec_destroy(rsrec_handle h) {
 int rsrec_set_kernel_family(rsrec_handle h, int family) {
   if (!h || family < 0 || family > 1) return fail(RSREC_EINVAL, "bad kernel family");
   h->family = family;
+  return RSREC_OK;
+}
+
+int rsrec_set_fusion(rsrec_handle h, int lanczos, int cheb) {
+  if (!h) return fail(RSREC_EINVAL, "null handle");
+  if (lanczos >= 0) h->fuse_lanczos = lanczos != 0;
+  if (cheb >= 0) h->fuse_cheb = cheb != 0;
   return RSREC_OK;
 }
 

@@ -179,6 +179,10 @@ class Recursion:
     def set_kernel_family(self, family: int):
         _lib.check(self._L.rsrec_set_kernel_family(self._h, family))
 
+    def set_fusion(self, lanczos: int = -1, cheb: int = -1):
+        """Gram products inside the SpMV kernel: lanczos (default on), cheb (default off); -1 = unchanged."""
+        _lib.check(self._L.rsrec_set_fusion(self._h, lanczos, cheb))
+
     @property
     def launch_count(self) -> int:
         return int(self._L.rsrec_launch_count(self._h))

@@ -191,7 +191,8 @@ def test_fortran_module_binds_every_data_path_symbol():
     bound = set(re.findall(r"name='(rsrec_[a-z0-9_]+)'", f90))
     helpers = {"rsrec_version", "rsrec_compiled_arch", "rsrec_cheb_begin_random", "rsrec_cheb_begin_sites",
                "rsrec_cheb_run_steps", "rsrec_cheb_end", "rsrec_synchronize", "rsrec_stream", "rsrec_launch_count",
-               "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read", "rsrec_set_kernel_family"}
+               "rsrec_h2d_bytes", "rsrec_d2h_bytes", "rsrec_profile", "rsrec_profile_read", "rsrec_set_kernel_family",
+               "rsrec_set_fusion"}
     assert bound <= declared
     assert declared - bound == helpers
     for name in bound:       # every interface is exported from the module

@@ -368,7 +368,9 @@ def test_edge_sizes_and_empty_inputs(oracle_mod):
 
 
 def test_positions_only_reorder_the_work():
-    """rsrec_set_positions (lattice%cr) sorts the tiles along a Morton curve for L2 locality: bit-identical results"""
+    """rsrec_set_positions (lattice%cr) sorts the tiles along a Morton curve for L2 locality: the Chebyshev moments are
+    bit-identical (site-ordered reductions); the Lanczos A = sum psi^H H psi is reduced per CTA of the SpMV kernel in tile
+    order, so its rounding follows the tile order (1e-13)"""
     from rslmtoasa_b200 import synthetic as S
     lat = S.periodic_bcc(6, 5, 4)
     ham = S.make_hamiltonian(lat, seed=20260104)
@@ -381,7 +383,8 @@ def test_positions_only_reorder_the_work():
         mu = rec.mu_n.copy()
         rec.recur_b()
         outs.append((mu, rec.a_b.copy(), rec.b2_b.copy()))
-    assert all(np.array_equal(x, y) for x, y in zip(*outs))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert relerr(outs[1][1], outs[0][1]) < 1e-13 and relerr(outs[1][2], outs[0][2]) < 1e-13
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -564,3 +567,34 @@ def test_spin_diagonal_velocity_sets_in_kubo_moments(oracle_mod, name):
     rec.compute_moments_stochastic()
     assert rec._L.rsrec_spin_diag_launch_count(rec._h) > 0
     assert relerr(rec.mu_nm_stochastic, mu_o) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["bulk", "bulk_hoh", "surface", "impurity_hoh", "pbc"])
+def test_gram_products_inside_the_spmv_kernel(oracle_mod, name):
+    """the fused forms (SpMV + three-term update + the 18x18 reductions in one kernel) against the oracle and against the
+    separate-kernel forms: Lanczos fused is the default, Chebyshev fused is opt-in (rsrec_set_fusion)"""
+    from rslmtoasa_b200 import synthetic as S
+    lat, ham = case(name)
+    lld = 7
+    orc = oracle_mod.Oracle(lat, ham)
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    a_b, b2_b = orc.lanczos_block(lat.irec, lld)
+    mu, _ = orc.cheb_moments(lat.irec, lld, a, b)
+    res = {}
+    for fused in (0, 1):
+        rec = _rec(lat, ham, lld=lld)
+        rec.set_fusion(lanczos=fused, cheb=fused)
+        l0 = rec.launch_count
+        rec.recur_b()
+        nl = rec.launch_count - l0
+        ph = S.random_phases(lat.kk, 2)
+        res[fused] = (rec.a_b.copy(), rec.b2_b.copy(), nl)
+        assert relerr(rec.a_b, a_b) < TOL_AB and relerr(rec.b2_b, b2_b) < TOL_AB
+        rec.chebyshev_recur()
+        assert relerr(rec.mu_n, mu) < TOL_MU
+        rec.chebyshev_recur_random(ph)
+        ref, _ = orc.cheb_moments_random(ph, lld, a, b)
+        assert relerr(rec.mu_n, ref) < TOL_MU
+        rec.close()
+    assert res[1][2] < res[0][2]                      # one launch less per step
+    assert relerr(res[1][0], res[0][0]) < 1e-12 and relerr(res[1][1], res[0][1]) < 1e-12
