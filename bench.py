@@ -338,7 +338,7 @@ def bench_strong(comm_info, device, rank, world, barrier, max_over_ranks):
     con = Conductivity(rec)
     rec.phases = ph[:, :2]; con.compute_conductivity()      # warm-up
     rec.phases = ph
-    t1 = timed(con.compute_conductivity)
+    t1 = min(timed(con.compute_conductivity) for _ in range(2))
     ref_i = con.integrand.copy()
     ph1 = phases_of(rec, con.compute_conductivity)
     with stdout_to_stderr():

@@ -111,6 +111,18 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 }
 
 
+
+// ---- work list of an SpMV launch -------------------------------------------------------------------------------------------
+// All passes (S sites of one tile) of all units form ONE list, walked by the persistent CTAs with stride gridDim.x: pass w
+// belongs to unit u iff base_u <= w < base_u + n_u, n_u = (tiles of unit u reachable at this step) * (8 / S).  With several
+// units in a batch the CTAs therefore share the passes of every unit (a per-unit loop left all but n_u CTAs idle while a unit's
+// active region was small, and rounded the rounds up per unit).  Producer and consumers walk the list with the same cursor.
+struct PassCursor {
+  int w, u, base, n_u;
+  template <int S>
+  __device__ __forceinline__ static int count(const int32_t *__restrict__ cnt, int ntiles, int u) { return (cnt ? cnt[u] : ntiles) * (DM_S / S); }
+};
+
 // ---- Gram products fused into the SpMV kernel --------------------------------------------------------------------------------
 // After the epilogue of a pass the CTA holds, in shared memory and in RI36 layout, the S = 4 site blocks of `in` (the last
 // pipeline stage) and of the fresh output tile (gbuf).  The 18x18 reductions of the step are real DMMA products on those
@@ -239,10 +251,18 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
   xoff[1] = min(xn1 * 8 + g, 35) * COLD + q;
 
   uint32_t it = 0;
-  for (int u = 0; u < nunits; u++) {
-    const size_t uo = (size_t)u * p.vstride;
-    const int n_u = (cnt ? cnt[u] : ntiles) * (DM_S / S);  // in passes of S sites
-    for (int ti = blockIdx.x; ti < n_u; ti += gridDim.x) {
+  int u = 0, base = 0, n_u = nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0;
+  for (int w = blockIdx.x;; w += gridDim.x) {
+    // units left behind are complete for this CTA: flush their Gram partials (zeros where the CTA had no pass)
+    while (u < nunits && w >= base + n_u) {
+      if (GRAM) gram_flush<GRAM>(p.part + ((size_t)u * gridDim.x + blockIdx.x) * (2 * BLKD), warp, lane, gacc);
+      base += n_u; u++;
+      if (u < nunits) n_u = PassCursor::count<S>(cnt, ntiles, u);
+    }
+    if (u >= nunits) break;
+    {
+      const size_t uo = (size_t)u * p.vstride;
+      const int ti = w - base;
       const int tpos = S == 8 ? ti : ti >> 1, half = S == 8 ? 0 : (ti & 1) * S;
       const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
       double acc[2][5][2], xacc[XN][2];
@@ -355,7 +375,6 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[lslot]);
     }
-    if (GRAM) gram_flush<GRAM>(p.part + ((size_t)u * gridDim.x + blockIdx.x) * (2 * BLKD), warp, lane, gacc);
   }
 }
 
@@ -385,34 +404,42 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
     // ===== producer warp: TMA bulk copies =====
     // The (site index, class) of the next stage is fetched from global memory while the warp waits for the ring slot
     // of the current one, so the index-load latency is off the critical path of the pipeline.
-    int cu = 0, ci = blockIdx.x, cj = 0;  // cursor: unit, position in the unit's tile list, stage
-    auto count = [&](int u) { return (cnt ? cnt[u] : ntiles) * (DM_S / S); };  // passes of S sites
-    auto settle = [&](int &u, int &i) { while (u < nunits && i >= count(u)) { u++; i = blockIdx.x; } };
-    auto fetch = [&](int u, int i, int j, int &site, int &cls) {
+    // cursor over the flattened pass list (PassCursor) and the stage within the pass
+    auto settle = [&](PassCursor &c) {
+      while (c.u < nunits && c.w >= c.base + c.n_u) {
+        c.base += c.n_u; c.u++;
+        if (c.u < nunits) c.n_u = PassCursor::count<S>(cnt, ntiles, c.u);
+      }
+    };
+    auto fetch = [&](const PassCursor &c, int j, int &site, int &cls) {
+      const int i = c.w - c.base;
       const int tpos = S == 8 ? i : i >> 1, half = S == 8 ? 0 : (i & 1) * S;
-      const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
+      const int tile = order ? order[(size_t)c.u * ntiles + tpos] : tpos;
       cls = tile_cls[tile];
       const int m = st.slot[j];
       site = (lane < S) ? ((m == 0) ? tile_sites[tile * DM_S + half + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + half + lane]) : 0;
     };
-    settle(cu, ci);
+    PassCursor cur{(int)blockIdx.x, 0, 0, nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0};
+    int cj = 0;
+    settle(cur);
     int site = 0, cls = 0;
-    if (cu < nunits) fetch(cu, ci, cj, site, cls);
-    for (uint32_t it = 0; cu < nunits; it++) {
-      int nu = cu, ni = ci, nj = cj + 1, nsite = 0, ncls = 0;
-      if (nj == nst) { nj = 0; ni += gridDim.x; settle(nu, ni); }
-      if (nu < nunits) fetch(nu, ni, nj, nsite, ncls);
+    if (cur.u < nunits) fetch(cur, cj, site, cls);
+    for (uint32_t it = 0; cur.u < nunits; it++) {
+      PassCursor nxt = cur;
+      int nj = cj + 1, nsite = 0, ncls = 0;
+      if (nj == nst) { nj = 0; nxt.w += gridDim.x; settle(nxt); }
+      if (nxt.u < nunits) fetch(nxt, nj, nsite, ncls);
       const int slot = it % STG;
       mbar_wait(&empty[slot], ((it / STG) & 1) ^ 1);
       double *sm = stages + (size_t)slot * STGD;
       if (lane == 0) mbar_expect_tx(&full[slot], STGD * 8);
       __syncwarp();
       if (lane < S) {
-        bulk_g2s(sm + HBLK + lane * BLKD, st.src[cj] + (size_t)cu * p.vstride + (size_t)site * BLKD, BLKD * 8, &full[slot]);
+        bulk_g2s(sm + HBLK + lane * BLKD, st.src[cj] + (size_t)cur.u * p.vstride + (size_t)site * BLKD, BLKD * 8, &full[slot]);
       } else if (lane == S) {
         bulk_g2s(sm, st.H[cj] + (size_t)cls * st.hstride[cj], HBLK * 8, &full[slot]);
       }
-      cu = nu; ci = ni; cj = nj; site = nsite; cls = ncls;
+      cur = nxt; cj = nj; site = nsite; cls = ncls;
     }
     return;
   }
@@ -496,10 +523,17 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
   for (int nt = 0; nt < 6; nt++) { er0[nt] = sd_row(nt * 8 + 2 * q); er1[nt] = sd_row(nt * 8 + 2 * q + 1); }
 
   uint32_t it = 0;
-  for (int u = 0; u < nunits; u++) {
-    const size_t uo = (size_t)u * p.vstride;
-    const int n_u = (cnt ? cnt[u] : ntiles) * (DM_S / S);
-    for (int ti = blockIdx.x; ti < n_u; ti += gridDim.x) {
+  int u = 0, base = 0, n_u = nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0;
+  for (int w = blockIdx.x;; w += gridDim.x) {
+    while (u < nunits && w >= base + n_u) {
+      if (GRAM) gram_flush<GRAM>(p.part + ((size_t)u * gridDim.x + blockIdx.x) * (2 * BLKD), warp, lane, gacc);
+      base += n_u; u++;
+      if (u < nunits) n_u = PassCursor::count<S>(cnt, ntiles, u);
+    }
+    if (u >= nunits) break;
+    {
+      const size_t uo = (size_t)u * p.vstride;
+      const int ti = w - base;
       const int tpos = ti >> 1, half = (ti & 1) * S;
       const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
       double acc[2][6][2], xacc[XN][2];
@@ -659,7 +693,6 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[lslot]);
     }
-    if (GRAM) gram_flush<GRAM>(p.part + ((size_t)u * gridDim.x + blockIdx.x) * (2 * BLKD), warp, lane, gacc);
   }
 }
 
@@ -685,36 +718,44 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
     // producer warp.  The spin-diagonal stages are short (30 instead of 45 DMMAs per m-tile), so the neighbour indices
     // are fetched TWO stages ahead of the copy that needs them (one stage ahead, as in k_apply_dmma, their L2 latency
     // paces the ring).
-    auto count = [&](int u) { return (cnt ? cnt[u] : ntiles) * (DM_S / S); };
-    auto settle = [&](int &u, int &i) { while (u < nunits && i >= count(u)) { u++; i = blockIdx.x; } };
-    auto advance = [&](int &u, int &i, int &j) { if (++j == nst) { j = 0; i += gridDim.x; settle(u, i); } };
-    auto fetch = [&](int u, int i, int j, int &site, int &cls) {
+    auto settle = [&](PassCursor &c) {
+      while (c.u < nunits && c.w >= c.base + c.n_u) {
+        c.base += c.n_u; c.u++;
+        if (c.u < nunits) c.n_u = PassCursor::count<S>(cnt, ntiles, c.u);
+      }
+    };
+    auto advance = [&](PassCursor &c, int &j) { if (++j == nst) { j = 0; c.w += gridDim.x; settle(c); } };
+    auto fetch = [&](const PassCursor &c, int j, int &site, int &cls) {
+      const int i = c.w - c.base;
       const int tpos = i >> 1, half = (i & 1) * S;
-      const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
+      const int tile = order ? order[(size_t)c.u * ntiles + tpos] : tpos;
       cls = tile_cls[tile];
       const int m = st.slot[j];
       site = (lane < S) ? ((m == 0) ? tile_sites[tile * DM_S + half + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + half + lane]) : 0;
     };
-    int cu = 0, ci = blockIdx.x, cj = 0;          // stage being copied
-    settle(cu, ci);
-    int u1 = cu, i1 = ci, j1 = cj;                // one stage ahead
+    PassCursor c0{(int)blockIdx.x, 0, 0, nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0};  // stage being copied
+    int j0 = 0;
+    settle(c0);
+    PassCursor c1 = c0;                             // one stage ahead
+    int j1 = j0;
     int site0 = 0, cls0 = 0, site1 = 0, cls1 = 0;
-    if (cu < nunits) { fetch(cu, ci, cj, site0, cls0); advance(u1, i1, j1); if (u1 < nunits) fetch(u1, i1, j1, site1, cls1); }
-    for (uint32_t it = 0; cu < nunits; it++) {
-      int u2 = u1, i2 = i1, j2 = j1, site2 = 0, cls2 = 0;  // two stages ahead
-      if (u2 < nunits) { advance(u2, i2, j2); if (u2 < nunits) fetch(u2, i2, j2, site2, cls2); }
+    if (c0.u < nunits) { fetch(c0, j0, site0, cls0); advance(c1, j1); if (c1.u < nunits) fetch(c1, j1, site1, cls1); }
+    for (uint32_t it = 0; c0.u < nunits; it++) {
+      PassCursor c2 = c1;                           // two stages ahead
+      int j2 = j1, site2 = 0, cls2 = 0;
+      if (c2.u < nunits) { advance(c2, j2); if (c2.u < nunits) fetch(c2, j2, site2, cls2); }
       const int slot = it % STG;
       mbar_wait(&empty[slot], ((it / STG) & 1) ^ 1);
       double *sm = stages + (size_t)slot * STGD;
       if (lane == 0) mbar_expect_tx(&full[slot], STGD * 8);
       __syncwarp();
       if (lane < S) {
-        bulk_g2s(sm + HBLK + lane * BLKD, st.src[cj] + (size_t)cu * p.vstride + (size_t)site0 * BLKD, BLKD * 8, &full[slot]);
+        bulk_g2s(sm + HBLK + lane * BLKD, st.src[j0] + (size_t)c0.u * p.vstride + (size_t)site0 * BLKD, BLKD * 8, &full[slot]);
       } else if (lane == S) {
-        bulk_g2s(sm, st.H[cj] + (size_t)cls0 * st.hstride[cj], HBLK * 8, &full[slot]);
+        bulk_g2s(sm, st.H[j0] + (size_t)cls0 * st.hstride[j0], HBLK * 8, &full[slot]);
       }
-      cu = u1; ci = i1; cj = j1; site0 = site1; cls0 = cls1;
-      u1 = u2; i1 = i2; j1 = j2; site1 = site2; cls1 = cls2;
+      c0 = c1; j0 = j1; site0 = site1; cls0 = cls1;
+      c1 = c2; j1 = j2; site1 = site2; cls1 = cls2;
     }
     return;
   }
@@ -1174,8 +1215,9 @@ static int dmma_apply_geom() {
   return geom;
 }
 // CTAs of an SpMV launch = per-unit partial-sum slots the fused Gram variants write
-static int dmma_apply_grid(const DmmaTiles &t, int sms) {
-  return dmma_apply_geom() == 4 ? std::max(1, std::min(2 * t.ntiles, 2 * sms)) : std::max(1, std::min(t.ntiles, sms));
+static int dmma_apply_grid(const DmmaTiles &t, int sms, int nunits) {
+  const long long passes = (long long)t.ntiles * std::max(1, nunits) * (dmma_apply_geom() == 4 ? 2 : 1);
+  return (int)std::max<long long>(1, std::min<long long>(passes, dmma_apply_geom() == 4 ? 2 * sms : sms));
 }
 static int dmma_grid(const DmmaTiles &t, int sms) { return std::max(1, std::min(t.ntiles, sms)); }
 static int dmma_gram_ctas(int kk, int sms) { return std::max(1, std::min(sms, (kk + GR_WARPS - 1) / GR_WARPS)); }
@@ -1207,8 +1249,8 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
   }
   int nsd = 0;
   for (int j = 0; j < sg.n; j++) nsd += sg.sd[j];
-  static const int geom = getenv("RSREC_APPLY_S") ? atoi(getenv("RSREC_APPLY_S")) : DM_APPLY_S;
-  const int grid = geom == 4 ? std::max(1, std::min(2 * t.ntiles, 2 * sms)) : dmma_grid(t, sms);
+  const int geom = dmma_apply_geom();
+  const int grid = dmma_apply_grid(t, sms, nunits);
   // the spin-grouped accumulator layout costs 6 instead of 5 n-tiles on full stages: worth it when most stages are spin-diagonal
   const bool use_sd = geom == 4 && 2 * nsd > sg.n;
   if (use_sd && sd_launches) (*sd_launches)++;

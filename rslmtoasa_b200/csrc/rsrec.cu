@@ -626,7 +626,7 @@ static int launch_gram(H *h, const double *X, const double *Y, int nunits, int n
 static size_t part_doubles(const H *h, int nunits, int nctas) {
   const int simt = std::max(1, std::min(nctas, (6 * h->sms + nunits - 1) / nunits));
   const int dm = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / nunits));
-  const int fused = h->tiles.ntiles > 0 ? dmma_apply_grid(h->tiles, h->sms) : 2 * h->sms;
+  const int fused = h->tiles.ntiles > 0 ? dmma_apply_grid(h->tiles, h->sms, nunits) : 2 * h->sms;
   return (size_t)nunits * std::max(std::max(std::max(simt, dm), fused), std::min(nctas, nctas_for(h, nunits))) * 2 * BLKD;
 }
 static int launch_reduce(H *h, int nunits, int /*nctas*/, int mode, double *d0, double *d1, size_t dstride,
