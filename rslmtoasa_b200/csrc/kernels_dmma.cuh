@@ -60,7 +60,7 @@ template <int EPI> struct EpiTraits {
 struct DmmaTiles {
   int ntiles = 0, ng = 0, kk = 0;
   int32_t *d_sites = nullptr;  // [ntiles][8]      site ids (kk = null)
-  int32_t *d_cls = nullptr;    // [ntiles]
+  int32_t *d_cls = nullptr;    // [ntiles][2]   Hamiltonian class of each half tile (sites 0-3 / 4-7)
   int32_t *d_nbr = nullptr;    // [ntiles][ng][8]  neighbour site ids per slot
   std::vector<int32_t> h_sites;  // host copy of d_sites (for the active-region planner)
 };
@@ -415,7 +415,7 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
       const int i = c.w - c.base;
       const int tpos = S == 8 ? i : i >> 1, half = S == 8 ? 0 : (i & 1) * S;
       const int tile = order ? order[(size_t)c.u * ntiles + tpos] : tpos;
-      cls = tile_cls[tile];
+      cls = tile_cls[2 * tile + (half ? 1 : 0)];
       const int m = st.slot[j];
       site = (lane < S) ? ((m == 0) ? tile_sites[tile * DM_S + half + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + half + lane]) : 0;
     };
@@ -729,7 +729,7 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
       const int i = c.w - c.base;
       const int tpos = i >> 1, half = (i & 1) * S;
       const int tile = order ? order[(size_t)c.u * ntiles + tpos] : tpos;
-      cls = tile_cls[tile];
+      cls = tile_cls[2 * tile + (half ? 1 : 0)];
       const int m = st.slot[j];
       site = (lane < S) ? ((m == 0) ? tile_sites[tile * DM_S + half + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + half + lane]) : 0;
     };
@@ -1138,20 +1138,43 @@ static uint32_t morton_spread10(uint32_t v) {  // 10 bits -> every third bit
   v = (v | (v << 2)) & 0x09249249u;
   return v;
 }
+static int dmma_apply_geom();
 static int dmma_build_tiles(DmmaTiles &t, const std::vector<int32_t> &nbr, const std::vector<int32_t> &cls, int kk, int ng,
-                            int ncls, const double *pos = nullptr) {
+                            int ncls, int ncls_type, const double *pos = nullptr) {
   dmma_free_tiles(t);
   std::vector<std::vector<int32_t>> by_cls(ncls);
   for (int i = 0; i < kk; i++) by_cls[cls[i]].push_back(i);
-  struct T { int32_t s[DM_S]; int32_t c; };
+  // Type-indexed classes (c < ncls_type): 8 sites per tile, one H block per stage.  Site-indexed classes (hall: one class per
+  // site): a class has a single site, so a tile takes TWO of them, one per half (the S = 4 geometry loads the H block of a
+  // pass by the class of its half tile); with the S = 8 geometry a tile has one class and such a site has a tile of its own.
+  struct T { int32_t s[DM_S]; int32_t c[2]; };
   std::vector<T> tiles;
-  for (int c = 0; c < ncls; c++)
+  const bool halves = dmma_apply_geom() == 4;
+  T open_local; bool have_open = false;
+  for (int c = 0; c < ncls; c++) {
+    const bool local = c >= ncls_type;
+    if (local && halves) {
+      for (size_t o = 0; o < by_cls[c].size(); o++) {   // one site per local class (more only if the caller reuses a class)
+        if (!have_open) {
+          for (int k = 0; k < DM_S; k++) open_local.s[k] = kk;
+          open_local.s[0] = by_cls[c][o]; open_local.c[0] = open_local.c[1] = c;
+          have_open = true;
+        } else {
+          open_local.s[DM_S / 2] = by_cls[c][o]; open_local.c[1] = c;
+          tiles.push_back(open_local);
+          have_open = false;
+        }
+      }
+      continue;
+    }
     for (size_t o = 0; o < by_cls[c].size(); o += DM_S) {
       T x;
-      x.c = c;
+      x.c[0] = x.c[1] = c;
       for (int k = 0; k < DM_S; k++) x.s[k] = (o + k < by_cls[c].size()) ? by_cls[c][o + k] : kk;
       tiles.push_back(x);
     }
+  }
+  if (have_open) tiles.push_back(open_local);
   if (pos) {
     double lo[3], hi[3];
     for (int l = 0; l < 3; l++) lo[l] = hi[l] = pos[l];
@@ -1174,9 +1197,9 @@ static int dmma_build_tiles(DmmaTiles &t, const std::vector<int32_t> &nbr, const
     std::sort(tiles.begin(), tiles.end(), [](const T &a, const T &b) { return a.s[0] < b.s[0]; });
   }
   const int nt = (int)tiles.size();
-  std::vector<int32_t> hs((size_t)nt * DM_S), hc(nt), hn((size_t)nt * ng * DM_S);
+  std::vector<int32_t> hs((size_t)nt * DM_S), hc((size_t)2 * nt), hn((size_t)nt * ng * DM_S);
   for (int i = 0; i < nt; i++) {
-    hc[i] = tiles[i].c;
+    hc[2 * i] = tiles[i].c[0]; hc[2 * i + 1] = tiles[i].c[1];
     for (int k = 0; k < DM_S; k++) {
       const int s = tiles[i].s[k];
       hs[(size_t)i * DM_S + k] = s;

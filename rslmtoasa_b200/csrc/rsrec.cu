@@ -244,8 +244,8 @@ static int ensure_ready(H *h) {
   h->nbr_host.swap(nbr);  // kept for the active-region planner (reverse adjacency is built on first use)
   h->radj_off.clear(); h->radj.clear();
   const std::vector<int32_t> &nbr_c = h->nbr_host;
-  if (dmma_build_tiles(h->tiles, nbr_c, cls, kk, ng, ncls, h->pos.empty() ? nullptr : h->pos.data()) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
-  h->h2d_bytes += (long long)h->tiles.ntiles * (DM_S + 1 + (long long)ng * DM_S) * 4;
+  if (dmma_build_tiles(h->tiles, nbr_c, cls, kk, ng, ncls, h->ntype, h->pos.empty() ? nullptr : h->pos.data()) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
+  h->h2d_bytes += (long long)h->tiles.ntiles * (DM_S + 2 + (long long)ng * DM_S) * 4;
   CUDA_TRY(cudaDeviceSynchronize());  // the tile tables went through the legacy stream: make sure they have landed
   h->dirty = false;
   h->dirty_ham = true;

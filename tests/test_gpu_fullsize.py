@@ -143,3 +143,24 @@ def test_many_units_are_split_into_batches_that_fit(oracle_mod, monkeypatch):
     rec.recur_b()
     assert relerr(rec.a_b, one) < 1e-13
     rec.close()
+
+
+@pytest.mark.parametrize("hoh", [False, True])
+def test_large_site_indexed_region(oracle_mod, hoh):
+    """a local (hall) region of hundreds of sites: site-indexed sites are packed two per tile (one per half tile, each half
+    with the Hamiltonian class of its site) -- odd and even counts, region larger than the bulk remainder of a class"""
+    for nmax in (301, 64):
+        lat = S.sphere_cluster("bcc", 24.0, ntype=3, nmax=nmax, type_rule="b2")
+        assert lat.kk > 2 * nmax
+        lat.irec = np.array([1, nmax, nmax + 1], dtype=np.int32)     # starts inside, at the edge of, and outside the region
+        ham = S.make_hamiltonian(lat, seed=20260103 + nmax, hoh=hoh)
+        rec = _rec(lat, ham, lld=7)
+        rec.recur_b()
+        orc = oracle_mod.Oracle(lat, ham)
+        a_b, b2_b = orc.lanczos_block(lat.irec, 7)
+        assert relerr(rec.a_b, a_b) < TOL_AB and relerr(rec.b2_b, b2_b) < TOL_AB
+        rec.chebyshev_recur()
+        a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+        mu, _ = orc.cheb_moments(lat.irec, 7, a, b)
+        assert relerr(rec.mu_n, mu) < TOL_MU
+        rec.close()
