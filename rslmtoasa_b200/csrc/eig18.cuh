@@ -250,11 +250,26 @@ __device__ __forceinline__ void eig18_func(const Eig18Smem &s, const double *f, 
 // B = U sqrt(L) U^H and B^-1 = U L^-1/2 U^H.  diag != 0: scalar Lanczos, everything diagonal & real.
 __global__ void __launch_bounds__(BLKC) k_lz_eig(const double *b2, size_t b2stride, double *b2_hist_slot, size_t hstride,
                                                  double *Bmat, double *Bimat, size_t bstride, int diag, int method,
-                                                 double *b_hist_slot = nullptr) {
+                                                 double *b_hist_slot = nullptr, const double *part = nullptr, int nparts = 0) {
   __shared__ Eig18Smem s;
   __shared__ double f1[NB], f2[NB];
   const int tid = threadIdx.x, unit = blockIdx.x, r = tid % NB, c = tid / NB;
-  double mr = b2[(size_t)unit * b2stride + 2 * tid], mi = b2[(size_t)unit * b2stride + 2 * tid + 1];
+  double mr, mi;
+  if (part) {
+    // B^2 = fixed-order sum of the per-CTA partials of sum pmn^H pmn (matrix 0 of each slot): folds the k_reduce_parts launch
+    // that used to precede this kernel into its prologue (coalesced: thread = matrix element)
+    const double2 *pp = reinterpret_cast<const double2 *>(part + (size_t)unit * nparts * (2 * BLKD)) + tid;
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+    int cta = 0;
+    for (; cta + 4 <= nparts; cta += 4) {
+      const double2 v0 = pp[(size_t)cta * BLKD], v1 = pp[(size_t)(cta + 1) * BLKD], v2 = pp[(size_t)(cta + 2) * BLKD], v3 = pp[(size_t)(cta + 3) * BLKD];
+      a0.x += v0.x; a0.y += v0.y; a1.x += v1.x; a1.y += v1.y; a2.x += v2.x; a2.y += v2.y; a3.x += v3.x; a3.y += v3.y;
+    }
+    for (; cta < nparts; cta++) { const double2 v = pp[(size_t)cta * BLKD]; a0.x += v.x; a0.y += v.y; }
+    mr = (a0.x + a1.x) + (a2.x + a3.x); mi = (a0.y + a1.y) + (a2.y + a3.y);
+  } else {
+    mr = b2[(size_t)unit * b2stride + 2 * tid]; mi = b2[(size_t)unit * b2stride + 2 * tid + 1];
+  }
   if (diag) { if (r != c) mr = 0.0; mi = 0.0; }
   b2_hist_slot[(size_t)unit * hstride + 2 * tid] = mr;
   b2_hist_slot[(size_t)unit * hstride + 2 * tid + 1] = mi;

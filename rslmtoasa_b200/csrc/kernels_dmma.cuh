@@ -924,11 +924,47 @@ __device__ __forceinline__ void rmul_product(const double *xs, const double *ts,
   }
 }
 
+
+// B^2 = sum pmn^H pmn of crecal_b (recursion.f90:1929-1934) inside the ORTHO pass: the freshly orthogonalised tile is written back
+// into its shared-memory slot (RI36, in place of the addend it replaces) and its 3 x 5 accumulator tiles are spread over the 8
+// consumer warps (tile t = warp + 8 s).  NT = tiles of this warp (2, or 1 for warp 7); same operand forms as k_gram_dmma.
+template <int NT>
+__device__ __forceinline__ void rmul_gram(const double *x, int ns, int warp, int lane, double (&gacc)[2][2]) {
+  const int g = lane >> 2, q = lane & 3;
+  int aoff[NT], boff[NT];
+  bool bswap[NT];
+#pragma unroll
+  for (int s = 0; s < NT; s++) {
+    const int t = warp + 8 * s, i = (t / 5) * 8 + g, j = (t % 5) * 8 + g;
+    aoff[s] = min(i, NB - 1) * COLD;
+    bswap[s] = j >= NB;
+    boff[s] = min(bswap[s] ? j - NB : j, NB - 1) * COLD;
+  }
+#pragma unroll 1
+  for (int site = 0; site < ns; site++) {
+    const double *xs = x + site * BLKD;
+#pragma unroll
+    for (int ks = 0; ks < 9; ks++) {
+      const int k = 4 * ks + q, kj = k < NB ? k + NB : k - NB;
+      double a[NT], b[NT];
+#pragma unroll
+      for (int s = 0; s < NT; s++) {
+        a[s] = xs[aoff[s] + k];
+        b[s] = xs[boff[s] + (bswap[s] ? kj : k)];
+        if (bswap[s] && k >= NB) b[s] = -b[s];
+      }
+#pragma unroll
+      for (int s = 0; s < NT; s++) dmma(gacc[s][0], gacc[s][1], a[s], b[s]);
+    }
+  }
+}
+
 template <int MODE, int XN>
 __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const double *hpsi, int kk, double *tiles,
                                               const double *tmat, uint64_t *full, uint64_t *empty, int warp, int lane,
-                                              const int32_t *bo, int nact) {
+                                              const int32_t *bo, int nact, double *gpart) {
   const int g = lane >> 2, q = lane & 3;
+  double gacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // fused B^2 partial tiles of this warp (ORTHO with gpart != null)
   const int mt[3] = {2 * warp, 2 * warp + 1, 16 + (warp >> 2)};
   const int w4 = warp & 3;
   const int xn[2] = {(warp == 6) ? 2 : (warp == 7) ? 4 : w4, ((warp == 6) ? 2 : (warp == 7) ? 4 : w4) + 1};
@@ -976,8 +1012,11 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
           const int c = xn[x] * 8 + 2 * q + e;
           if (valid(2, c)) xacc[x][e] += ad[sofs(2, c)];
         }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[slot]);
+      if (!gpart) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+      }
+      double *adw = const_cast<double *>(ad);
 #pragma unroll
       for (int i = 0; i < 2; i++)
 #pragma unroll
@@ -985,15 +1024,22 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
 #pragma unroll
           for (int e = 0; e < 2; e++) {
             const int c = nt * 8 + 2 * q + e;
-            if (valid(i, c)) pmn[gofs(i, c)] = acc[i][nt][e];
+            if (valid(i, c)) { pmn[gofs(i, c)] = acc[i][nt][e]; if (gpart) adw[sofs(i, c)] = acc[i][nt][e]; }
           }
 #pragma unroll
       for (int x = 0; x < XN; x++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int c = xn[x] * 8 + 2 * q + e;
-          if (valid(2, c)) pmn[gofs(2, c)] = xacc[x][e];
+          if (valid(2, c)) { pmn[gofs(2, c)] = xacc[x][e]; if (gpart) adw[sofs(2, c)] = xacc[x][e]; }
         }
+      if (gpart) {
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * DM_CONSUMERS) : "memory");  // the orthogonalised tile is complete in shared memory
+        const int ns = min(DM_S, kk - site0);
+        if (warp + 8 < 15) rmul_gram<2>(ad, ns, warp, lane, gacc); else rmul_gram<1>(ad, ns, warp, lane, gacc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+      }
     } else {
       mbar_wait(&full[slot], (it >> 1) & 1);
       // tile 0 = pmn, tile 1 = psi;  tmat 0 = Binv, tmat 1 = B
@@ -1024,6 +1070,20 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
       }
     }
   }
+  if (MODE == RM_ORTHO && gpart) {  // this warp's tiles of the per-CTA partial of B^2 (matrix 0 of the slot, complex column-major)
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      const int t = warp + 8 * s;
+      if (t < 15) {
+        const int R = (t / 5) * 8 + g;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int C = (t % 5) * 8 + 2 * q + e;
+          if (R < NB && C < 2 * NB) gpart[2 * (R + NB * (C % NB)) + (C / NB)] = gacc[s][e];
+        }
+      }
+    }
+  }
 }
 
 // grid = (ctas, nunits).  m0/m1: complex column-major 18x18 per unit (stride mstride doubles): ORTHO m0 = A;
@@ -1031,7 +1091,8 @@ __device__ __forceinline__ void rmul_consumer(double *psi, double *pmn, const do
 template <int MODE>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const double *m0, const double *m1, size_t mstride,
-            int kk, size_t vstride, const int32_t *__restrict__ border, const int32_t *__restrict__ bcnt, int nblocks) {
+            int kk, size_t vstride, const int32_t *__restrict__ border, const int32_t *__restrict__ bcnt, int nblocks,
+            double *part) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);                       // [2 slots][2 tiles]
   double *tmat = tiles + 2 * 2 * RM_TILE_D;                                   // [2][36x36]: T[c'][j'] = Mhat[j'][c']
@@ -1082,10 +1143,12 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
     }
     return;
   }
+  // ORTHO with part != null: B^2 = sum pmn^H pmn partials of this CTA go to slot [unit][blockIdx.x] (k_lz_eig sums them)
+  double *gpart = (MODE == RM_ORTHO && part) ? part + ((size_t)unit * gridDim.x + blockIdx.x) * (2 * BLKD) : nullptr;
   if (warp == 3 || warp == 6)
-    rmul_consumer<MODE, 2>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane, bo, nact);
+    rmul_consumer<MODE, 2>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
   else
-    rmul_consumer<MODE, 1>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane, bo, nact);
+    rmul_consumer<MODE, 1>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -1324,16 +1387,18 @@ static int dmma_launch_gram(const double *X, size_t xstride, const double *Y, si
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
+static int dmma_rmul_ctas(int kk, int sms, int nunits) { return std::max(1, std::min((kk + DM_S - 1) / DM_S, sms / std::max(1, nunits))); }
 static int dmma_launch_rmul(int mode, double *psi, double *pmn, const double *hpsi, const double *m0, const double *m1,
                             size_t mstride, int kk, size_t vstride, int nunits, int sms, cudaStream_t st,
                             long long *launches, const int32_t *border = nullptr, const int32_t *bcnt = nullptr,
-                            int nblocks = 0) {
+                            int nblocks = 0, double *part = nullptr, int *nparts_out = nullptr) {
   const int ntiles = (kk + DM_S - 1) / DM_S;
-  dim3 grid(std::max(1, std::min(ntiles, sms / nunits)), nunits);
+  dim3 grid(dmma_rmul_ctas(kk, sms, nunits), nunits);
+  if (nparts_out) *nparts_out = (int)grid.x;
   if (mode == RM_ORTHO)
-    k_rmul_dmma<RM_ORTHO><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride, border, bcnt, nblocks);
+    k_rmul_dmma<RM_ORTHO><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride, border, bcnt, nblocks, part);
   else
-    k_rmul_dmma<RM_ROTATE><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride, border, bcnt, nblocks);
+    k_rmul_dmma<RM_ROTATE><<<grid, DM_THREADS, RM_SMEM_BYTES, st>>>(psi, pmn, hpsi, m0, m1, mstride, kk, vstride, border, bcnt, nblocks, nullptr);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -626,7 +626,7 @@ static int launch_gram(H *h, const double *X, const double *Y, int nunits, int n
 static size_t part_doubles(const H *h, int nunits, int nctas) {
   const int simt = std::max(1, std::min(nctas, (6 * h->sms + nunits - 1) / nunits));
   const int dm = std::max(1, std::min(dmma_gram_ctas(h->kk, h->sms), (2 * h->sms) / nunits));
-  const int fused = h->tiles.ntiles > 0 ? dmma_apply_grid(h->tiles, h->sms, nunits) : 2 * h->sms;
+  const int fused = std::max(h->tiles.ntiles > 0 ? dmma_apply_grid(h->tiles, h->sms, nunits) : 2 * h->sms, dmma_rmul_ctas(h->kk, h->sms, nunits));
   return (size_t)nunits * std::max(std::max(std::max(simt, dm), fused), std::min(nctas, nctas_for(h, nunits))) * 2 * BLKD;
 }
 static int launch_reduce(H *h, int nunits, int /*nctas*/, int mode, double *d0, double *d1, size_t dstride,
@@ -714,9 +714,16 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     if (fam1(h)) {
       const int32_t *bo, *bc; int nbk;
       plan_blocks(h, nunits, &bo, &bc, &nbk);
+      if (fused) {  // pmn -= psi A and the per-CTA partials of B^2 = sum pmn^H pmn in one pass over the tiles
+        int np = 0;
+        if (dmma_launch_rmul(RM_ORTHO, psi, pmn, nullptr, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches, bo, bc, nbk, h->part.p, &np) != 0)
+          return fail(RSREC_ECUDA, std::string("k_rmul_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        h->last_parts = np;
+      } else {
       if (dmma_launch_rmul(RM_ORTHO, psi, pmn, nullptr, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches, bo, bc, nbk) != 0)
         return fail(RSREC_ECUDA, std::string("k_rmul_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
       TRY(launch_gram(h, pmn, pmn, nunits, nctas, h->part.p));
+      }
     } else {
       k_lz_ortho_simt<<<grid, SIMT_THREADS, 0, h->st>>>(psi, pmn, hpsi, h->A.p, BLKD, h->kk, vstride(h), h->part.p);
       h->last_parts = nctas;
@@ -726,9 +733,10 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     // B2 -> history slot ll+1, B, B^-1
     {
     PhaseScope ph_(h, PH_BNEXT);
-    TRY(launch_reduce(h, nunits, nctas, 0, h->B2.p, nullptr, BLKD, nullptr, nullptr));
-    k_lz_eig<<<nunits, BLKC, 0, h->st>>>(h->B2.p, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
-                                         BLKD, diag ? 1 : 0, h->sqrt_method, h->bhist.p + (size_t)(ll + 1) * BLKD);
+    // the fixed-order sum of the B^2 partials is the prologue of k_lz_eig (one launch less per step)
+    k_lz_eig<<<nunits, BLKC, 0, h->st>>>(nullptr, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
+                                         BLKD, diag ? 1 : 0, h->sqrt_method, h->bhist.p + (size_t)(ll + 1) * BLKD,
+                                         h->part.p, h->last_parts);
     h->launches++;
     }
     // psi = pmn B^-1 ; pmn = psi_old B
