@@ -8,7 +8,7 @@
 ! unchanged, so self.f90 / green.f90 / density_of_states.f90 / conductivity.f90 compile and run
 ! untouched.  `this%gpu` is one new component of the type: `type(c_ptr) :: gpu = c_null_ptr`.
 ! Work vectors (psi_b, pmn_b, hpsi, ...) are no longer allocated on the host.
-! Procedures here: gpu_export, recur_b, recur_b_ij, recur, zsqr, chebyshev_recur, chebyshev_recur_ij,
+! Procedures here: gpu_export, gpu_report_phases, recur_b, recur_b_ij, recur, zsqr, chebyshev_recur, chebyshev_recur_ij,
 ! compute_moments_stochastic (the consumers' bodies are in green_gpu_shim.f90).  NOT compiled in the build container.
 !------------------------------------------------------------------------------
 module recursion_gpu_shim
@@ -23,19 +23,47 @@ contains
    subroutine gpu_export(this)
       use recursion_mod, only: recursion
       class(recursion), intent(inout), target :: this
-      integer :: nslot
+      integer :: nslot, ndev
+      type(c_ptr) :: p_eeo, p_hall, p_hallo, p_enim
       nslot = size(this%hamiltonian%ee, 3)
       if (.not. c_associated(this%gpu)) then
-         call rsrec_check(rsrec_create(this%gpu, int(mod(rank, 8), c_int), int(this%lattice%kk, c_int), &
+         ! one process per GPU: the device is the rank modulo the devices this process can see (with one rank per node
+         ! slot the launcher's local rank; CUDA_VISIBLE_DEVICES narrows the list further)
+         ndev = max(1, int(rsrec_device_count()))
+         call rsrec_check(rsrec_create(this%gpu, int(mod(rank, ndev), c_int), int(this%lattice%kk, c_int), &
                                        int(size(this%lattice%nn, 2), c_int), int(nslot, c_int), &
                                        int(this%lattice%ntype, c_int), int(this%lattice%nmax, c_int)), __FILE__, __LINE__)
       end if
       call rsrec_check(rsrec_set_lattice(this%gpu, this%lattice%nn, this%lattice%iz), __FILE__, __LINE__)
       call rsrec_check(rsrec_set_positions(this%gpu, this%lattice%cr), __FILE__, __LINE__)   ! work ordering only
-      call rsrec_check(rsrec_set_hamiltonian(this%gpu, c_loc(this%hamiltonian%ee), c_loc(this%hamiltonian%eeo), &
-                                             c_loc(this%hamiltonian%hall), c_loc(this%hamiltonian%hallo), &
-                                             c_loc(this%hamiltonian%lsham), c_loc(this%hamiltonian%enim), &
+      ! arrays the reference leaves unallocated (hall/hallo without a local region, eeo/hallo/enim without hoh) are passed
+      ! as NULL: c_loc of an unallocated array is not defined, and the C side expects NULL for "not used"
+      p_eeo = c_null_ptr; p_hall = c_null_ptr; p_hallo = c_null_ptr; p_enim = c_null_ptr
+      if (this%lattice%nmax > 0 .and. allocated(this%hamiltonian%hall)) p_hall = c_loc(this%hamiltonian%hall)
+      if (this%hamiltonian%hoh) then
+         if (allocated(this%hamiltonian%eeo)) p_eeo = c_loc(this%hamiltonian%eeo)
+         if (allocated(this%hamiltonian%enim)) p_enim = c_loc(this%hamiltonian%enim)
+         if (this%lattice%nmax > 0 .and. allocated(this%hamiltonian%hallo)) p_hallo = c_loc(this%hamiltonian%hallo)
+      end if
+      call rsrec_check(rsrec_set_hamiltonian(this%gpu, c_loc(this%hamiltonian%ee), p_eeo, p_hall, p_hallo, &
+                                             c_loc(this%hamiltonian%lsham), p_enim, &
                                              merge(1_c_int, 0_c_int, this%hamiltonian%hoh)), __FILE__, __LINE__)
+   end subroutine
+
+   !> copies the device phase times of the last call into the host's profile tree under the reference's own labels
+   !> (recursion.f90:1902-1970, 3104-3127).  g_timer measures wall time between start/stop, so the shim brackets an empty
+   !> region and adds the device milliseconds with g_timer%add (a three-line addition to timer.f90, see INTEGRATION.md).
+   subroutine gpu_report_phases(this)
+      use recursion_mod, only: recursion
+      use timer_mod, only: g_timer
+      class(recursion), intent(inout) :: this
+      real(c_double) :: ms(16)
+      integer(c_long_long) :: calls(16)
+      integer :: k
+      call rsrec_check(rsrec_phase_read(this%gpu, ms, calls), __FILE__, __LINE__)
+      do k = 1, int(rsrec_phase_count())
+         if (calls(k) > 0) call g_timer%add(rsrec_phase_label_f(k - 1), ms(k)*1.0d-3, int(calls(k)))
+      end do
    end subroutine
 
    subroutine recur_b(this)
@@ -46,11 +74,13 @@ contains
       complex(c_double_complex), allocatable :: ones(:)
       call get_mpi_variables(rank, this%lattice%nrec)
       call gpu_export(this)
+      call rsrec_check(rsrec_phase_timing(this%gpu, 1_c_int), __FILE__, __LINE__)   ! 'H|PSI_n>', 'B_n+1', ... of crecal_b
       nloc = end_atom - start_atom + 1
       allocate (sites(nloc), none(nloc), ones(nloc))
       sites = this%lattice%irec(start_atom:end_atom); none = 0; ones = (1.0d0, 0.0d0)
       call rsrec_check(rsrec_lanczos_block(this%gpu, int(nloc, c_int), sites, none, ones, ones, &
                                            int(this%lattice%control%lld, c_int), this%a_b, this%b2_b), __FILE__, __LINE__)
+      call gpu_report_phases(this)
       do i = 1, nloc
          do ll = 1, this%lattice%control%lld
             do l = 1, 18
@@ -75,8 +105,10 @@ contains
       allocate (sites(nloc), none(nloc), ones(nloc))
       sites = this%lattice%irec(start_atom:end_atom); none = 0; ones = (1.0d0, 0.0d0)
       ! RSREC_EDIVERGED is the reference's own fatal "Chebyshev moments did not converge" (recursion.f90:2594)
+      call rsrec_check(rsrec_phase_timing(this%gpu, 1_c_int), __FILE__, __LINE__)   ! '<PSI_0|PSI_0>', '<PSI_0|PSI_1>', '<PSI_0|PSI_n>'
       call rsrec_check(rsrec_cheb_moments(this%gpu, int(nloc, c_int), sites, none, ones, ones, &
                                           int(this%lattice%control%lld, c_int), a, b, this%mu_n), __FILE__, __LINE__)
+      call gpu_report_phases(this)
    end subroutine
 
    subroutine zsqr(this)

@@ -18,6 +18,7 @@ module rsrec_c_mod
    integer(c_int), parameter, public :: RSREC_OK = 0, RSREC_EINVAL = -1, RSREC_EDIVERGED = -2, &
                                         RSREC_ECUDA = -3, RSREC_ENOMEM = -4
 
+   public :: rsrec_device_count
    public :: rsrec_create, rsrec_destroy, rsrec_set_lattice, rsrec_set_hamiltonian, rsrec_set_operator
    public :: rsrec_lanczos_block, rsrec_lanczos_scalar, rsrec_zsqr, rsrec_cheb_moments, rsrec_cheb_moments_random
    public :: rsrec_kubo_moments, rsrec_ham_vec_matmul, rsrec_velo_vec_matmul, rsrec_last_error_f, rsrec_check
@@ -45,6 +46,12 @@ module rsrec_c_mod
       function rsrec_last_error() bind(C, name='rsrec_last_error') result(msg)
          import :: c_ptr
          type(c_ptr) :: msg
+      end function
+
+      ! CUDA devices visible to this process: device_ordinal = mod(local_rank, rsrec_device_count())
+      function rsrec_device_count() bind(C, name='rsrec_device_count') result(n)
+         import :: c_int
+         integer(c_int) :: n
       end function
 
       ! recursion constructor: recursion.f90:132-143 / allocation 3713-3826
@@ -514,6 +521,7 @@ module rsrec_c_mod
          type(c_ptr), value :: h
          integer(c_long_long) :: n
       end function
+
 
       ! ---- exchange step: one process per GPU = one MPI rank of the reference (mpi.f90:32-58) ----
       ! rank 0 creates the id, the host broadcasts its 128 bytes (call MPI_Bcast(id, 128, MPI_BYTE, 0, comm, ierr))

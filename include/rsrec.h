@@ -38,6 +38,8 @@ const char *rsrec_last_error(void);
 /* library/ABI version, and the SM architecture the kernels were compiled for (100 => sm_100a) */
 int rsrec_version(void);
 int rsrec_compiled_arch(void);
+/* CUDA devices visible to this process (0 when none): an MPI host picks device_ordinal = mod(local_rank, count) */
+int rsrec_device_count(void);
 
 /* recursion constructor (recursion.f90:132-143, allocation 3713-3826): sizes come from
  * lattice%kk, size(lattice%nn,2), size(hamiltonian%ee,3) = maxval(nn(:,1))+1 (hamiltonian.f90:294),

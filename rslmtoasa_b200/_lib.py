@@ -9,7 +9,7 @@ from . import build as _build
 _lib = None
 
 SYMBOLS = [
-    "rsrec_last_error", "rsrec_version", "rsrec_compiled_arch", "rsrec_create", "rsrec_destroy", "rsrec_set_lattice",
+    "rsrec_last_error", "rsrec_version", "rsrec_compiled_arch", "rsrec_device_count", "rsrec_create", "rsrec_destroy", "rsrec_set_lattice",
     "rsrec_set_hamiltonian", "rsrec_set_operator", "rsrec_lanczos_block", "rsrec_lanczos_scalar", "rsrec_zsqr",
     "rsrec_cheb_moments", "rsrec_cheb_moments_random", "rsrec_kubo_moments", "rsrec_ham_vec_matmul",
     "rsrec_velo_vec_matmul", "rsrec_cheb_begin_random", "rsrec_cheb_begin_sites", "rsrec_cheb_run_steps",

@@ -854,6 +854,11 @@ extern "C" {
 const char *rsrec_last_error(void) { return g_err.c_str(); }
 int rsrec_version(void) { return 100; }
 int rsrec_compiled_arch(void) { return 100; }
+int rsrec_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 
 int rsrec_create(rsrec_handle *out, int device, int kk, int ncols, int nslot, int ntype, int nmax) {
   if (!out) return fail(RSREC_EINVAL, "null handle pointer");

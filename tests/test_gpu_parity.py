@@ -598,3 +598,4 @@ def test_gram_products_inside_the_spmv_kernel(oracle_mod, name):
         rec.close()
     assert res[1][2] < res[0][2]                      # one launch less per step
     assert relerr(res[1][0], res[0][0]) < 1e-12 and relerr(res[1][1], res[0][1]) < 1e-12
+
