@@ -97,6 +97,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
+// non-blocking phase test: issued a few k-steps before the end of a stage for the NEXT stage's barrier, so that the latency of the
+// barrier query (~200 cycles per stage on the critical path of every consumer warp when it is issued at the stage boundary:
+// 7.5 % of the consumer samples in profiles/r02h_ncu_apply_dmma_1M.txt sat on that branch) overlaps the remaining DMMAs
+__device__ __forceinline__ uint32_t mbar_test(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -250,7 +266,7 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
   xoff[0] = min(xn0 * 8 + g, 35) * COLD + q;
   xoff[1] = min(xn1 * 8 + g, 35) * COLD + q;
 
-  uint32_t it = 0;
+  uint32_t it = 0, ready = 0;  // ready: the barrier of the upcoming stage has already been seen complete (mbar_test)
   int u = 0, base = 0, n_u = nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0;
   for (int w = blockIdx.x;; w += gridDim.x) {
     // units left behind are complete for this CTA: flush their Gram partials (zeros where the CTA had no pass)
@@ -300,7 +316,7 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
                                                     : make_double2(0.0, 0.0);
           }
         }
-        mbar_wait(&full[slot], (it / STG) & 1);
+        if (!ready) mbar_wait(&full[slot], (it / STG) & 1);
         const double *sm = stages + (size_t)slot * STGD;
         // fragments of k-step ks+1 are loaded before the DMMAs of k-step ks are issued (register double buffering)
         double b[2][5], a[2][3], xb[2][XN];
@@ -313,6 +329,7 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
 #pragma unroll
         for (int ks = 0; ks < 9; ks++) {
           const int c = ks & 1, n = c ^ 1;
+          if (ks == 6) ready = mbar_test(&full[(it + 1) % STG], ((it + 1) / STG) & 1);  // next stage's data: usually there already
           if (ks < 8) {
 #pragma unroll
             for (int nt = 0; nt < 5; nt++) b[n][nt] = sm[boff[nt] + 4 * (ks + 1)];
@@ -522,7 +539,7 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
 #pragma unroll
   for (int nt = 0; nt < 6; nt++) { er0[nt] = sd_row(nt * 8 + 2 * q); er1[nt] = sd_row(nt * 8 + 2 * q + 1); }
 
-  uint32_t it = 0;
+  uint32_t it = 0, ready = 0;
   int u = 0, base = 0, n_u = nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0;
   for (int w = blockIdx.x;; w += gridDim.x) {
     while (u < nunits && w >= base + n_u) {
@@ -577,7 +594,7 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
           for (int x = 0; x < XN; x++)
             if (gval[2]) fetch_prev(xpv[x], xn0 + x, gbase[2]); else xpv[x][0] = xpv[x][1] = 0.0;
         }
-        mbar_wait(&full[slot], (it / STG) & 1);
+        if (!ready) mbar_wait(&full[slot], (it / STG) & 1);
         const double *sm = stages + (size_t)slot * STGD;
         // fragments of step t+1 are loaded before the DMMAs of step t are issued (register double buffering)
         if (st.sd[j]) {
@@ -597,6 +614,7 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
 #pragma unroll
           for (int t = 0; t < 10; t++) {
             const int c = t & 1, sp = t / 5;
+            if (t == 6) ready = mbar_test(&full[(it + 1) % STG], ((it + 1) / STG) & 1);
             if (t < 9) load(t + 1, c ^ 1);
 #pragma unroll
             for (int t3 = 0; t3 < 3; t3++) {
@@ -623,6 +641,7 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
 #pragma unroll
           for (int ks = 0; ks < 9; ks++) {
             const int c = ks & 1;
+            if (ks == 6) ready = mbar_test(&full[(it + 1) % STG], ((it + 1) / STG) & 1);
             if (ks < 8) load(ks + 1, c ^ 1);
 #pragma unroll
             for (int nt = 0; nt < 6; nt++) {

@@ -78,6 +78,24 @@ def test_kubo_vs_dense(oracle_mod):
 
 
 # ---- invariants --------------------------------------------------------------------------------------------
+def test_kubo_selected_left_indices_are_columns_of_the_full_moments(oracle_mod):
+    """orc_kubo_moments_cols (used by the full-size GPU parity test, where cond_ll^2 contractions over 8000 sites take minutes
+    on a CPU) runs the same chains and contracts a subset of the left indices: bit-identical to those columns"""
+    lat, ham = case("pbc")
+    orc = oracle_mod.Oracle(lat, ham)
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    ph = S.random_phases(lat.kk, 2)
+    full = orc.kubo_moments(6, a, b, phases=ph)
+    msel = np.array([1, 4, 6], dtype=np.int32)
+    sel = orc.kubo_moments_cols(6, a, b, msel, phases=ph)
+    assert sel.shape == (18, 18, 6, 3, 2)
+    assert np.array_equal(sel, full[:, :, :, msel - 1, :])
+    none = orc.kubo_moments_cols(6, a, b, msel[:0], phases=ph[:, :1])     # chains only
+    assert none.shape == (18, 18, 6, 0, 1)
+    full_s = orc.kubo_moments(5, a, b, start_sites=[3])
+    assert np.array_equal(orc.kubo_moments_cols(5, a, b, [2], start_sites=[3])[:, :, :, 0], full_s[:, :, :, 1])
+
+
 def test_mask_is_only_an_optimisation(oracle_mod):
     """inactive sites hold exact zeros: results with and without izero/idum/irlist are identical"""
     for name in ["bulk", "impurity_hoh"]:
