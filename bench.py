@@ -289,6 +289,7 @@ def bench_strong(comm_info, device, rank, world, barrier, max_over_ranks):
     """Fixed-total unit-sharded work on N GPUs (the reference's MPI rank = unit shard, mpi.f90:32-58), the
     exchange inside the timed region and inside the library (NCCL on device-resident results):
       A  config 2 (surface, 16756 sites) x 24 recursion sites: recur_b on this rank's shard + all-gather of a_b/b2_b;
+      C  config 1 (bulk, 5984 sites) x 32 pair start vectors (recur_b_ij);  D  config 3 (impurity, 3838 sites) x 16 sites;
       B  config 4 (8000 sites, cond_ll = 50) x 64 random vectors: Kubo moments + Gamma contraction + all-reduce of the integrand.
     t1 = the same total on ONE GPU, measured in this very run (every rank does it on its own GPU at the same time, max taken),
     so speedup and efficiency come from one box and one build."""
@@ -327,6 +328,46 @@ def bench_strong(comm_info, device, rank, world, barrier, max_over_ranks):
                  "units": 24, "n_gpus": world, "t1_s": t1, "tN_s": tn, "speedup": t1 / tn, "efficiency": t1 / tn / world,
                  "relerr_vs_1gpu": same, "phases_1gpu_s": ph1, "phases_Ngpu_s": phn,
                  "phases_note": "host wall-clock per stage with a stream sync at every stage boundary (max over ranks)"})
+    rec.close()
+    # --- C: config 1 (bulk bccFe, 5984 sites) x 8 pairs = 32 pair start vectors (recur_b_ij, the exchange path)
+    lat = S.sphere_cluster("bcc", 80.0)
+    ham = S.make_hamiltonian(lat, seed=20260101)
+    pairs = np.array([[1, j] for j in range(2, 10)], dtype=np.int32)
+    rec = Recursion(ham, lat, Control(lld=21), Energy(EMIN, EMAX), device=device, ijpair=pairs)
+    rec.recur_b_ij()
+    t1 = min(timed(rec.recur_b_ij) for _ in range(3))
+    ref_a = rec.a_b.copy()
+    ph1 = phases_of(rec, rec.recur_b_ij)
+    with stdout_to_stderr():
+        rec.comm_init_torch()
+    rec.recur_b_ij_sharded()
+    tn = min(timed(rec.recur_b_ij_sharded) for _ in range(3))
+    same = float(np.abs(rec.a_b - ref_a).max() / np.abs(ref_a).max())
+    phn = phases_of(rec, rec.recur_b_ij_sharded)
+    recs.append({"workload": "C: config 1 bulk bccFe (5984 sites) x 8 pairs = 32 pair start vectors, recur_b_ij lld=21, "
+                             "all-gather of a_b/b2_b on the device",
+                 "units": 32, "n_gpus": world, "t1_s": t1, "tN_s": tn, "speedup": t1 / tn, "efficiency": t1 / tn / world,
+                 "relerr_vs_1gpu": same, "phases_1gpu_s": ph1, "phases_Ngpu_s": phn})
+    rec.close()
+    # --- D: config 3 (impurity B2, 3838 sites, 15 site-indexed sites) x 16 recursion sites (the local region + 1)
+    lat = S.sphere_cluster("bcc", 60.0, ntype=3, nmax=15, type_rule="b2")
+    lat.irec = np.arange(1, 17, dtype=np.int32)
+    ham = S.make_hamiltonian(lat, seed=20260103)
+    rec = Recursion(ham, lat, Control(lld=21), Energy(EMIN, EMAX), device=device)
+    rec.recur_b()
+    t1 = min(timed(rec.recur_b) for _ in range(3))
+    ref_a = rec.a_b.copy()
+    ph1 = phases_of(rec, rec.recur_b)
+    with stdout_to_stderr():
+        rec.comm_init_torch()
+    rec.recur_b_sharded()
+    tn = min(timed(rec.recur_b_sharded) for _ in range(3))
+    same = float(np.abs(rec.a_b - ref_a).max() / np.abs(ref_a).max())
+    phn = phases_of(rec, rec.recur_b_sharded)
+    recs.append({"workload": "D: config 3 impurity B2 (3838 sites, nmax=15) x 16 recursion sites, recur_b lld=21, "
+                             "all-gather of a_b/b2_b on the device",
+                 "units": 16, "n_gpus": world, "t1_s": t1, "tN_s": tn, "speedup": t1 / tn, "efficiency": t1 / tn / world,
+                 "relerr_vs_1gpu": same, "phases_1gpu_s": ph1, "phases_Ngpu_s": phn})
     rec.close()
     # --- B
     lat = S.periodic_bcc(10, 20, 20)

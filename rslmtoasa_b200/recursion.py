@@ -444,6 +444,24 @@ class Recursion:
         self.b2_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
         _lib.check(self._L.rsrec_lanczos_block_sharded(self._h, n, _p(sites), None, None, None, lld, _p(self.a_b), _p(self.b2_b)))
 
+    def recur_b_ij_sharded(self):
+        """recur_b_ij over ALL pairs of the job (units = 4 start vectors per pair, 1 for i == j): each rank runs its block-rule
+        shard of the unit list, the coefficients are gathered on the device -> a_b, b2_b (18,18,lld,4*njij) on every rank."""
+        rank, nprocs = self.rank, self.numprocs
+        self.rank, self.numprocs = 0, 1                      # the full unit list; the library shards it
+        try:
+            nloc, slots, (si, sj, asg, bsg) = self._pair_units()
+        finally:
+            self.rank, self.numprocs = rank, nprocs
+        lld, n = self.control.lld, len(si)
+        a_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        b2_b = np.zeros((NB, NB, lld, n), np.complex128, order="F")
+        _lib.check(self._L.rsrec_lanczos_block_sharded(self._h, n, _p(si), _p(sj), _p(asg), _p(bsg), lld, _p(a_b), _p(b2_b)))
+        self.a_b = np.zeros((NB, NB, lld, 4 * nloc), np.complex128, order="F")
+        self.b2_b = np.zeros((NB, NB, lld, 4 * nloc), np.complex128, order="F")
+        self.a_b[..., slots] = a_b
+        self.b2_b[..., slots] = b2_b
+
     def chebyshev_recur_random_sum(self, phases=None, sharded: bool = True):
         """stochastic-trace moments: sum over ALL random vectors of the job (this rank runs its shard of the columns of
         `phases`; the sum over local vectors and over ranks happens on the device) -> mu_sum (18,18,2*lld+2)."""

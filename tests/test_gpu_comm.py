@@ -52,6 +52,11 @@ def test_single_rank_communicator(oracle_mod):
     a_loc = rec.a_b.copy()
     rec.recur_b_sharded()
     assert np.array_equal(rec.a_b, a_loc)
+    rec.ijpair = np.array([[1, 2], [3, 3]], dtype=np.int32)
+    rec.recur_b_ij()
+    a_ij = rec.a_b.copy()
+    rec.recur_b_ij_sharded()
+    assert np.array_equal(rec.a_b, a_ij)
     assert np.array_equal(rec.allgather_units(a_loc, 5), a_loc)
     ph = S.random_phases(lat.kk, 3)
     rec.chebyshev_recur_random(ph)
@@ -80,7 +85,10 @@ def _worker(rank, world, id_bytes, out_dir):
     lat.irec = np.array([1, 4, 9, 12, 30], dtype=np.int32)
     ph = S.random_phases(lat.kk, 5)
     rec = _rec(lat, ham, device=rank, lld=5, cond_ll=6, cond_calctype="random_vec", phases=ph)
+    rec.ijpair = np.array([[1, 2], [3, 3], [2, 7]], dtype=np.int32)
     rec.comm_init(world, rank, id_bytes)
+    rec.recur_b_ij_sharded()                                # pair units sharded, gathered on the device
+    a_ij = rec.a_b.copy()
     rec.recur_b_sharded()                                   # device all-gather of a_b / b2_b
     a_dev = rec.a_b.copy()
     mu_sum = rec.chebyshev_recur_random_sum(ph)             # device sum + all-reduce of the moments
@@ -95,7 +103,7 @@ def _worker(rank, world, id_bytes, out_dir):
     dtot = np.zeros(len(g.ene))
     from rslmtoasa_b200 import _lib
     _lib.check(rec._L.rsrec_bands_dos(rec._h, dtot.ctypes.data, None, None))   # dtot all-reduced on the device (bands.f90:276)
-    np.savez(os.path.join(out_dir, f"c{rank}.npz"), a_dev=a_dev, a_sh=gathered, mu_sum=mu_sum, x=x,
+    np.savez(os.path.join(out_dir, f"c{rank}.npz"), a_dev=a_dev, a_ij=a_ij, a_sh=gathered, mu_sum=mu_sum, x=x,
              integ=integ, dtot=dtot)
     rec.comm_destroy()
     rec.close()
@@ -115,6 +123,9 @@ def test_two_rank_exchange_inside_the_library(tmp_path, oracle_mod):
     lat.irec = np.array([1, 4, 9, 12, 30], dtype=np.int32)
     ph = S.random_phases(lat.kk, 5)
     rec = _rec(lat, ham, lld=5, cond_ll=6, cond_calctype="random_vec", phases=ph)
+    rec.ijpair = np.array([[1, 2], [3, 3], [2, 7]], dtype=np.int32)
+    rec.recur_b_ij()
+    a_ij = rec.a_b.copy()
     rec.recur_b()
     mu_sum = rec.chebyshev_recur_random_sum(ph)
     integ, _ = Conductivity(rec).compute_conductivity()
@@ -127,6 +138,7 @@ def test_two_rank_exchange_inside_the_library(tmp_path, oracle_mod):
         d = np.load(os.path.join(str(tmp_path), f"c{r}.npz"))
         assert relerr(d["a_sh"], rec.a_b) < 1e-13
         assert relerr(d["a_dev"], rec.a_b) < 1e-13
+        assert relerr(d["a_ij"], a_ij) < 1e-13
         assert relerr(d["mu_sum"], mu_sum) < 1e-13
         assert np.array_equal(d["x"], np.full(4, 3.0))
         ok = np.isfinite(integ)
