@@ -138,6 +138,40 @@ class recursion {
     mu_n.assign((size_t)324 * (2 * lld + 2) * n, 0.0);
     check(rsrec_cheb_moments(h_, n, sites.data(), nullptr, nullptr, nullptr, lld, scale(), shift(), rc(mu_n)));
   }
+  // ---- the exchange step inside the library (one process per GPU = one MPI rank of the reference, mpi.f90:32-58) ----
+  // rank 0 creates the id, the host broadcasts its 128 bytes (MPI_Bcast), every rank attaches its handle
+  static std::vector<unsigned char> comm_unique_id() {
+    std::vector<unsigned char> id(RSREC_COMM_ID_BYTES);
+    check(rsrec_comm_unique_id(id.data()));
+    return id;
+  }
+  void comm_init(int nranks, int rank, const std::vector<unsigned char> &id) {
+    check(rsrec_comm_init(h_, nranks, rank, id.data()));
+    rank_ = rank; np_ = nranks;
+  }
+  // recur_b over ALL recursion sites of the job: a_b, b2_b (18,18,lld,nrec) gathered on the device, on every rank
+  void recur_b_sharded() {
+    const int n = (int)lat_.irec.size(), lld = ctl_.lld;
+    a_b.assign((size_t)324 * lld * n, 0.0);
+    b2_b.assign((size_t)324 * lld * n, 0.0);
+    check(rsrec_lanczos_block_sharded(h_, n, lat_.irec.data(), nullptr, nullptr, nullptr, lld, rc(a_b), rc(b2_b)));
+  }
+  // MPI_ALLREDUCE(MPI_IN_PLACE, x, n, MPI_DOUBLE_PRECISION, MPI_SUM) (bands.f90:270-275)
+  void allreduce(std::vector<double> &x) { check(rsrec_allreduce(h_, x.data(), (long long)x.size(), 0)); }
+
+  // ---- device time per phase under the reference's g_timer labels (recursion.f90:1902-1970, 3104-3127) ----
+  void phase_timing(bool on) { check(rsrec_phase_timing(h_, on ? 1 : 0)); }
+  std::vector<std::pair<std::string, double>> phase_read() {  // (label, milliseconds) of the phases that ran
+    const int n = rsrec_phase_count();
+    std::vector<double> ms(n);
+    std::vector<long long> calls(n);
+    check(rsrec_phase_read(h_, ms.data(), calls.data()));
+    std::vector<std::pair<std::string, double>> out;
+    for (int k = 0; k < n; k++)
+      if (calls[k] > 0) out.emplace_back(rsrec_phase_label(k), ms[k]);
+    return out;
+  }
+
   // recur_b_ij / chebyshev_recur_ij (recursion.f90:1655-1737 / 2376-2487): slot ij_loc*4-4+reci
   void recur_b_ij() { pair_run(true); }
   void chebyshev_recur_ij() { pair_run(false); }

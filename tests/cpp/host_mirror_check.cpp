@@ -69,6 +69,17 @@ int main(int argc, char **argv) {
     printf("chebyshev_green g0 %.3e\n", relerr(gr.g0, ref_gk));
     rec.recur_b_ij();
     printf("recur_b_ij a_b %.3e\n", relerr(rec.a_b, ref_aij));
+    {  // exchange inside the library with a single-rank communicator, and the g_timer phase labels
+      rec.comm_init(1, 0, rsrec::recursion::comm_unique_id());
+      rec.phase_timing(true);
+      rec.recur_b_sharded();
+      const auto ph = rec.phase_read();
+      std::vector<double> x = {1.5, 2.5};
+      rec.allreduce(x);
+      printf("sharded a_b %.3e phases %d first %s allreduce %.3e\n", relerr(rec.a_b, ref_a), (int)ph.size(),
+             ph.empty() ? "-" : ph[0].first.c_str(), std::abs(x[0] - 1.5) + std::abs(x[1] - 2.5));
+      rec.phase_timing(false);
+    }
     rsrec::energy bad; bad.energy_min = -0.05; bad.energy_max = 0.05;
     rsrec::control c40; c40.lld = 40;
     rsrec::recursion rec2(ham, lat, c40, bad);

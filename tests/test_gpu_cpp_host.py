@@ -76,12 +76,15 @@ def test_cpp_host_mirror_matches_oracle(tmp_path, oracle_mod):
     vals = {}
     for line in out.stdout.splitlines():
         t = line.split()
-        if t[0] in ("recur_b", "chebyshev_recur", "recur_b_ij", "block_green", "recur_b_green", "chebyshev_green", "bands"):
+        if t[0] == "sharded":
+            vals["sharded.a_b"], vals["sharded.phases"], vals["sharded.label"], vals["sharded.allreduce"] = float(t[2]), int(t[4]), t[6], float(t[8])
+        elif t[0] in ("recur_b", "chebyshev_recur", "recur_b_ij", "block_green", "recur_b_green", "chebyshev_green", "bands"):
             for k, v in zip(t[1::2], t[2::2]):
                 vals[t[0] + "." + k] = float(v)
     assert vals["recur_b.a_b"] < 1e-10 and vals["recur_b.b2_b"] < 1e-10
     assert vals["chebyshev_recur.mu_n"] < 1e-9
     assert vals["recur_b_ij.a_b"] < 1e-10
+    assert vals["sharded.a_b"] < 1e-10 and vals["sharded.phases"] == 4 and vals["sharded.label"] == "H|PSI_n>" and vals["sharded.allreduce"] == 0.0
     assert vals["block_green.g0"] < 1e-8 and vals["recur_b_green.g0"] == 0.0
     assert vals["chebyshev_green.g0"] < 1e-9
     assert vals["bands.fermi"] < 1e-10 and vals["bands.nv1"] == 0.0 and vals["bands.eband"] < 1e-10
