@@ -30,6 +30,7 @@ struct NcclApi {
   const char *(*GetErrorString)(int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, rs_ncclComm_t, cudaStream_t) = nullptr;
   int (*Broadcast)(const void *, void *, size_t, int, int, rs_ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, rs_ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   std::string err;
@@ -56,6 +57,7 @@ static NcclApi *nccl_api() {
   RS_SYM(GetErrorString, "ncclGetErrorString")
   RS_SYM(AllReduce, "ncclAllReduce")
   RS_SYM(Broadcast, "ncclBroadcast")
+  RS_SYM(AllGather, "ncclAllGather")
   RS_SYM(GroupStart, "ncclGroupStart")
   RS_SYM(GroupEnd, "ncclGroupEnd")
 #undef RS_SYM

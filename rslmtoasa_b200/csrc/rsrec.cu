@@ -100,6 +100,7 @@ struct rsrec_handle_s {
   struct {
     bool on = false;
     int level = 0, maxlevel = 0, nunits = 0;
+    std::vector<int32_t> key;  // start sites (i, j per unit) the plan was built for
     int32_t *d_order = nullptr, *d_counts = nullptr;
     size_t order_cap = 0, counts_cap = 0;
     // the same levels for contiguous 8-site blocks (what the site-ordered Gram / right-multiplication kernels walk)
@@ -243,6 +244,7 @@ static int ensure_ready(H *h) {
   h->h2d_bytes += (long long)((nbr.size() + cls.size()) * sizeof(int32_t));
   h->nbr_host.swap(nbr);  // kept for the active-region planner (reverse adjacency is built on first use)
   h->radj_off.clear(); h->radj.clear();
+  h->plan.on = false; h->plan.key.clear();
   const std::vector<int32_t> &nbr_c = h->nbr_host;
   if (dmma_build_tiles(h->tiles, nbr_c, cls, kk, ng, ncls, h->ntype, h->pos.empty() ? nullptr : h->pos.data()) != 0) return fail(RSREC_ENOMEM, "cannot allocate the tile tables");
   h->h2d_bytes += (long long)h->tiles.ntiles * (DM_S + 2 + (long long)ng * DM_S) * 4;
@@ -422,6 +424,13 @@ enum OpKind { OP_HAM = 0, OP_SCALAR = 1, OP_VELO_A = 2, OP_VELO_B = 3, OP_HAM_NO
 // This is exactly the set the reference tracks with izero/idum/irlist (recursion.f90:1604-1636); skipped tiles hold
 // exact zeros, so results are unchanged.
 static int plan_build(H *h, int nunits, const int32_t *site_i, const int32_t *site_j) {
+  // the plan depends on the neighbour table and the start sites only: the SCF loop repeats the same call every iteration
+  {
+    std::vector<int32_t> key((size_t)2 * nunits);
+    for (int u = 0; u < nunits; u++) { key[2 * u] = site_i[u]; key[2 * u + 1] = site_j ? site_j[u] : 0; }
+    if (h->plan.on && h->plan.nunits == nunits && h->plan.key == key && fam1(h)) { h->plan.level = 0; return RSREC_OK; }
+    h->plan.key.swap(key);
+  }
   h->plan.on = false;
   if (!fam1(h) || (size_t)nunits * h->kk > (size_t)64 << 20) return RSREC_OK;
   const int kk = h->kk, nt = h->tiles.ntiles;
@@ -2174,6 +2183,11 @@ static void shard_of(int rank, int nranks, long long n, long long *lo, long long
 static int comm_allgather_units_dev(H *h, double *full, size_t per_unit, long long nunits) {
   if (!h->comm || h->comm_size == 1) return RSREC_OK;
   NcclApi *N = nccl_api();
+  if (nunits % h->comm_size == 0) {  // equal shards: one in-place all-gather (the shard of rank r already sits at r * count)
+    const size_t count = (size_t)(nunits / h->comm_size) * per_unit;
+    NCCL_TRY(N->AllGather(full + (size_t)h->comm_rank * count, full, count, RS_NCCL_FLOAT64, h->comm, h->st));
+    return RSREC_OK;
+  }
   NCCL_TRY(N->GroupStart());
   for (int r = 0; r < h->comm_size; r++) {
     long long lo, hi;
