@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #define DM_S 8                               // sites per tile
@@ -473,17 +474,27 @@ k_apply_dmma(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_site
     dmma_consumer<EPI, ADDEND, 1, S>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
 }
 
-// ---- spin-diagonal variant of the SpMV (S = 4 geometry) -----------------------------------------------------------------
-// In a collinear calculation the hopping blocks ee(:,:,m,type) are spin-diagonal -- only l.s on the on-site block couples
-// the spins -- so the 36x36 real embedding of such a block is two independent 18x18 products.  Stages flagged `sd` run
-// per spin with K = 18 (5 k-steps, the two padding columns point at a column of the OTHER spin, where the block is exactly
-// zero) instead of K = 36 (9 k-steps); the on-site stage stays full.  To let both kinds of stage add into the same
-// accumulators the output rows are grouped by spin, 24 per spin (3 n-tiles, 18 used):
+// ---- spin-resolved variant of the SpMV (S = 4 geometry) -----------------------------------------------------------------------
+// In a collinear calculation the hopping blocks ee(:,:,m,type) are spin-diagonal -- only l.s on the on-site block couples the
+// spins -- so the 36x36 real embedding of such a block is two independent 18x18 products: 2 x 3 x 5 = 30 DMMAs per m-tile
+// and slot instead of 5 x 9 = 45.  With a third less arithmetic per stage the round-1 form of this kernel (ordinary 10 kB
+// HR36 blocks, 3-stage ring of 31 kB stages) waited for its data (DMMA pipe 67 % active, 17 % of the samples in barrier
+// waits).  Round 2: every stage carries a HALF block -- the "HS18" packing, 2 spins x 18 rows x 20 k (5760 B; k padded with
+// explicit zeros) of either the spin-diagonal part of the slot's block (kind 0: output rows of spin s contract psi rows of
+// spin s) or its spin-off-diagonal part (kind 1: rows of spin s contract psi rows of the other spin; only emitted for slots
+// that couple the spins, i.e. the on-site slot with l.s) -- so stages are 26.5 kB and the ring is FOUR deep (three in the
+// variants that also hold the output tile for the fused Gram products).
+// Output rows are grouped by spin, 24 per spin (3 n-tiles, 18 used):
 //   up:   rho 0..8 = Re rows 0..8, rho 9 pad, rho 10..18 = Im rows 18..26, rho 19..23 pad
 //   down: rho 24 pad, 25..33 = Re rows 9..17, rho 34 pad, 35..43 = Im rows 27..35, rho 44..47 pad
 // (the pads are placed so that every accumulator pair (rho, rho+1) of two valid rows is an aligned double2 in RI36).
-// A spin-diagonal stage issues 2 x 3 x 5 = 30 DMMAs per m-tile instead of 5 x 9 = 45; the full stage 6 x 9 = 54.
-// The blocks themselves are the ordinary HR36 ones: only the fragment addresses differ.
+#define SDH 720   // doubles per HS18 half block: [spin][18 rows][20 k]
+template <bool GRAMV> struct SdGeom {
+  static constexpr int kStages = GRAMV ? 3 : 4;
+  static constexpr int kStageD = SDH + 4 * BLKD;                    // 3312 doubles = 26496 B
+  static constexpr int kRing = kStages * kStageD * 8 + 64;
+  static constexpr int kSmem = kRing + (GRAMV ? 4 * BLKD * 8 : 0);  // + the output tile of a pass
+};
 __device__ __forceinline__ int sd_row(int rho) {  // accumulator row -> RI36 row, -1 = padding
   if (rho < 24) {
     if (rho < 9) return rho;
@@ -495,10 +506,28 @@ __device__ __forceinline__ int sd_row(int rho) {  // accumulator row -> RI36 row
   if (r < 10) return 9 + (r - 1);
   return r < 20 ? 27 + (r - 11) : -1;
 }
-__device__ __forceinline__ int sd_kcol(int spin, int kappa) {  // k index of a spin-diagonal stage -> RI36 row of psi / column of H
+__device__ __forceinline__ int sd_prow(int rho) {  // accumulator row -> row (0..17) of its spin's HS18 sub-block, -1 = padding
+  const int r = sd_row(rho);
+  if (r < 0) return -1;
+  return r < NB ? r % 9 : 9 + (r - NB) % 9;
+}
+__device__ __forceinline__ int sd_kcol(int spin, int kappa) {  // k index (0..19) of a half stage -> RI36 row of psi
   if (kappa < 9) return 9 * spin + kappa;
   if (kappa < 18) return 18 + 9 * spin + (kappa - 9);
-  return 9 * (1 - spin);  // padding: a column of the other spin (H is exactly zero there)
+  return 0;  // padding: the HS18 block holds explicit zeros there, any finite psi value will do
+}
+// HR36 set -> HS18 set: dst[(b*2 + kind)][s][r][kappa] = Hreal_b[row(s, r)][kcol(kind ? 1-s : s, kappa)], zero for kappa >= 18
+__global__ void k_pack_hs18(const double *__restrict__ hr36, double *__restrict__ hs18, int nblocks) {
+  const int b = blockIdx.x;
+  if (b >= nblocks) return;
+  for (int e = threadIdx.x; e < 2 * SDH; e += blockDim.x) {
+    const int kind = e / SDH, rem = e % SDH, sp = rem / 360, r = (rem % 360) / 20, kap = rem % 20;
+    const int row = r < 9 ? 9 * sp + r : 18 + 9 * sp + (r - 9);
+    const int ks = kind ? 1 - sp : sp;
+    double v = 0.0;
+    if (kap < 18) v = hr36[(size_t)b * HBLK + row * COLD + (kap < 9 ? 9 * ks + kap : 18 + 9 * ks + (kap - 9))];
+    hs18[(size_t)b * 2 * SDH + e] = v;
+  }
 }
 
 // XN shared-m-tile units of this warp, all of spin XSPIN: warp 0: n-tiles 0,1  warp 1: 2  warp 2: 3,4  warp 3: 5
@@ -511,29 +540,36 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
   typedef EpiTraits<EPI> ET;
   constexpr int GRAM = ET::kGram;
   constexpr int S = 4;
+  typedef SdGeom<(GRAM != 0)> G;
+  constexpr int STG = G::kStages, STGD = G::kStageD;
   double gacc[GR_SLOTS][2];  // fused Gram accumulators of this warp's tiles (GRAM != 0)
 #pragma unroll
   for (int s = 0; s < GR_SLOTS; s++) gacc[s][0] = gacc[s][1] = 0.0;
   const int g = lane >> 2, q = lane & 3;
   const int nst = st.n;
   const double inv_a = 1.0 / p.a;
-  constexpr int STG = ApGeom<S>::kStages, STGD = ApGeom<S>::kStageD;
   const int mt0 = 2 * warp, mt1 = 2 * warp + 1, mt2 = 8;
   const int xn0 = XSPIN * 3 + (warp & 1 ? 2 : 0);  // warp 0: 0,1  warp 1: 2  warp 2: 3,4  warp 3: 5
-  int arow[3];                                     // psi column (m-tile row) base offsets
-  arow[0] = HBLK + (mt0 * 8 + g) * COLD;
-  arow[1] = HBLK + (mt1 * 8 + g) * COLD;
-  arow[2] = HBLK + (mt2 * 8 + g) * COLD;
-  int brow[6], xrow[XN];                           // H row base offsets of this lane's B fragments (pads read row 0)
+  // psi (A fragment) addresses.  k-step kt of spin s reads psi row sd_kcol(s, 4 kt + q) = 9 s + q + {0, 4, c2, 21, 25}: per
+  // m-tile and spin ONE lane-dependent base (a0) and immediates, except k-step 2 (the Re/Im seam: c2 = 8 for q = 0, 17
+  // otherwise) and the two padding lanes of k-step 4 (c4 points them at row 0 of the column; the HS18 block is zero there, the
+  // value only has to be finite).  The round-1 form looked the row up in a table: one IMAD/SEL per shared-memory load.
+  int a0[3][2];
 #pragma unroll
-  for (int nt = 0; nt < 6; nt++) brow[nt] = max(sd_row(nt * 8 + g), 0) * COLD;
+  for (int sp = 0; sp < 2; sp++) {
+    a0[0][sp] = SDH + (mt0 * 8 + g) * COLD + 9 * sp + q;
+    a0[1][sp] = SDH + (mt1 * 8 + g) * COLD + 9 * sp + q;
+    a0[2][sp] = SDH + (mt2 * 8 + g) * COLD + 9 * sp + q;
+  }
+  const int c2 = q == 0 ? 8 : 17;
+  int c4[2];
+  c4[0] = q < 2 ? 25 : -q;
+  c4[1] = q < 2 ? 25 : -(q + 9);
+  int brow[6], xrow[XN];                           // HS18 row base offsets of this lane's B fragments (pads read row 0)
 #pragma unroll
-  for (int x = 0; x < XN; x++) xrow[x] = max(sd_row((xn0 + x) * 8 + g), 0) * COLD;
-  int kc[2][5];                                    // k columns of the spin-diagonal stages
+  for (int nt = 0; nt < 6; nt++) brow[nt] = ((nt / 3) * NB + max(sd_prow(nt * 8 + g), 0)) * 20 + q;
 #pragma unroll
-  for (int sp = 0; sp < 2; sp++)
-#pragma unroll
-    for (int ks = 0; ks < 5; ks++) kc[sp][ks] = sd_kcol(sp, 4 * ks + q);
+  for (int x = 0; x < XN; x++) xrow[x] = (((xn0 + x) / 3) * NB + max(sd_prow((xn0 + x) * 8 + g), 0)) * 20 + q;
   // epilogue rows of this lane's accumulator pairs: RI36 offsets (or -1)
   int er0[6], er1[6];
 #pragma unroll
@@ -596,25 +632,31 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
         }
         if (!ready) mbar_wait(&full[slot], (it / STG) & 1);
         const double *sm = stages + (size_t)slot * STGD;
-        // fragments of step t+1 are loaded before the DMMAs of step t are issued (register double buffering)
-        if (st.sd[j]) {
+        // kind 1 (st.sd[j] != 0): rows of spin s contract the psi rows of the OTHER spin.  Two instantiations of the stage body so
+        // that every address stays base + immediate.  Fragments of step t+1 are loaded before the DMMAs of step t are issued.
+        auto stage = [&](auto cross_tag) {
+          constexpr bool CROSS = decltype(cross_tag)::value;
           double fa[2][3], fb[2][3], fx[2][XN];
+          auto aoff = [&](int i, int sp, int kt) {
+            const int spa = CROSS ? 1 - sp : sp;
+            return a0[i][spa] + (kt < 2 ? 4 * kt : kt == 2 ? c2 : kt == 3 ? 21 : c4[spa]);
+          };
           auto load = [&](int t, int buf) {  // t = 5 * spin + k-step
-            const int sp = t / 5, k = kc[sp][t % 5];
-            fa[buf][0] = sm[arow[0] + k]; fa[buf][1] = sm[arow[1] + k];
+            const int sp = t / 5, kt = t % 5;
+            fa[buf][0] = sm[aoff(0, sp, kt)]; fa[buf][1] = sm[aoff(1, sp, kt)];
 #pragma unroll
-            for (int t3 = 0; t3 < 3; t3++) fb[buf][t3] = sm[brow[3 * sp + t3] + k];
+            for (int t3 = 0; t3 < 3; t3++) fb[buf][t3] = sm[brow[3 * sp + t3] + 4 * kt];
             if (sp == XSPIN) {
-              fa[buf][2] = sm[arow[2] + k];
+              fa[buf][2] = sm[aoff(2, sp, kt)];
 #pragma unroll
-              for (int x = 0; x < XN; x++) fx[buf][x] = sm[xrow[x] + k];
+              for (int x = 0; x < XN; x++) fx[buf][x] = sm[xrow[x] + 4 * kt];
             }
           };
           load(0, 0);
 #pragma unroll
           for (int t = 0; t < 10; t++) {
             const int c = t & 1, sp = t / 5;
-            if (t == 6) ready = mbar_test(&full[(it + 1) % STG], ((it + 1) / STG) & 1);
+            if (t == 7) ready = mbar_test(&full[(it + 1) % STG], ((it + 1) / STG) & 1);
             if (t < 9) load(t + 1, c ^ 1);
 #pragma unroll
             for (int t3 = 0; t3 < 3; t3++) {
@@ -626,32 +668,8 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
               for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], fa[c][2], fx[c][x]);
             }
           }
-        } else {
-          double fa[2][3], fb[2][6], fx[2][XN];
-          auto load = [&](int ks, int buf) {
-            const int k = 4 * ks + q;
-#pragma unroll
-            for (int i = 0; i < 3; i++) fa[buf][i] = sm[arow[i] + k];
-#pragma unroll
-            for (int nt = 0; nt < 6; nt++) fb[buf][nt] = sm[brow[nt] + k];
-#pragma unroll
-            for (int x = 0; x < XN; x++) fx[buf][x] = sm[xrow[x] + k];
-          };
-          load(0, 0);
-#pragma unroll
-          for (int ks = 0; ks < 9; ks++) {
-            const int c = ks & 1;
-            if (ks == 6) ready = mbar_test(&full[(it + 1) % STG], ((it + 1) / STG) & 1);
-            if (ks < 8) load(ks + 1, c ^ 1);
-#pragma unroll
-            for (int nt = 0; nt < 6; nt++) {
-              dmma(acc[0][nt][0], acc[0][nt][1], fa[c][0], fb[c][nt]);
-              dmma(acc[1][nt][0], acc[1][nt][1], fa[c][1], fb[c][nt]);
-            }
-#pragma unroll
-            for (int x = 0; x < XN; x++) dmma(xacc[x][0], xacc[x][1], fa[c][2], fx[c][x]);
-          }
-        }
+        };
+        if (st.sd[j]) stage(std::true_type()); else stage(std::false_type());
         if (j < nst - 1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[slot]);
@@ -665,7 +683,7 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
         const size_t go = gb + r;
         if (ADDEND && valid) v += __ldg(p.addend + go);
         if (ET::kScale) {
-          v = (v - p.b * sm[HBLK + n * COLD + r]) * inv_a;
+          v = (v - p.b * sm[SDH + n * COLD + r]) * inv_a;
           if (ET::kCheb) v = 2.0 * v - pr;
         }
         if (ET::kHop) {
@@ -679,7 +697,7 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
         const size_t go = gb + r;
         if (ADDEND && valid) { const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go)); v0 += ad.x; v1 += ad.y; }
         if (ET::kScale) {
-          const double2 in = *reinterpret_cast<const double2 *>(sm + HBLK + n * COLD + r);
+          const double2 in = *reinterpret_cast<const double2 *>(sm + SDH + n * COLD + r);
           v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
           if (ET::kCheb) { v0 = 2.0 * v0 - pr0; v1 = 2.0 * v1 - pr1; }
         }
@@ -707,7 +725,7 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
         if (GRAM || gval[2]) finish(xacc[x][0], xacc[x][1], ncol[2], xn0 + x, gbase[2], xpv[x], gval[2]);
       if (GRAM) {
         consumer_bar(32 * S);  // the output tile is complete in shared memory
-        gram_accumulate<GRAM, S>(sm + HBLK, gbuf, warp, lane, gacc);
+        gram_accumulate<GRAM, S>(sm + SDH, gbuf, warp, lane, gacc);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[lslot]);
@@ -721,9 +739,10 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
                 const int32_t *__restrict__ tile_nbr, int ntiles, int nunits, const int32_t *__restrict__ order,
                 const int32_t *__restrict__ cnt) {
   constexpr int S = 4;
+  typedef SdGeom<(EpiTraits<EPI>::kGram != 0)> G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stages = reinterpret_cast<double *>(smem_raw);
-  constexpr int STG = ApGeom<S>::kStages, STGD = ApGeom<S>::kStageD, NCONS = ApGeom<S>::kConsumers;
+  constexpr int STG = G::kStages, STGD = G::kStageD, NCONS = ApGeom<S>::kConsumers;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STG * STGD * 8);
   uint64_t *empty = full + STG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -734,9 +753,7 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
   __syncthreads();
   const int nst = st.n, ng = p.ngather;
   if (warp == NCONS) {
-    // producer warp.  The spin-diagonal stages are short (30 instead of 45 DMMAs per m-tile), so the neighbour indices
-    // are fetched TWO stages ahead of the copy that needs them (one stage ahead, as in k_apply_dmma, their L2 latency
-    // paces the ring).
+    // producer warp: the neighbour indices are fetched TWO stages ahead of the copy that needs them
     auto settle = [&](PassCursor &c) {
       while (c.u < nunits && c.w >= c.base + c.n_u) {
         c.base += c.n_u; c.u++;
@@ -769,16 +786,16 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
       if (lane == 0) mbar_expect_tx(&full[slot], STGD * 8);
       __syncwarp();
       if (lane < S) {
-        bulk_g2s(sm + HBLK + lane * BLKD, st.src[j0] + (size_t)c0.u * p.vstride + (size_t)site0 * BLKD, BLKD * 8, &full[slot]);
+        bulk_g2s(sm + SDH + lane * BLKD, st.src[j0] + (size_t)c0.u * p.vstride + (size_t)site0 * BLKD, BLKD * 8, &full[slot]);
       } else if (lane == S) {
-        bulk_g2s(sm, st.H[j0] + (size_t)cls0 * st.hstride[j0], HBLK * 8, &full[slot]);
+        bulk_g2s(sm, st.H[j0] + (size_t)cls0 * st.hstride[j0], SDH * 8, &full[slot]);   // HS18 half block of this stage
       }
       c0 = c1; j0 = j1; site0 = site1; cls0 = cls1;
       c1 = c2; j1 = j2; site1 = site2; cls1 = cls2;
     }
     return;
   }
-  double *gbuf = reinterpret_cast<double *>(smem_raw + ApGeom<S>::kSmem);  // output tile of a pass (Gram variants only)
+  double *gbuf = reinterpret_cast<double *>(smem_raw + G::kRing);  // output tile of a pass (Gram variants only)
   if (warp == 0) dmma_consumer_sd<EPI, ADDEND, 2, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
   else if (warp == 1) dmma_consumer_sd<EPI, ADDEND, 1, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
   else if (warp == 2) dmma_consumer_sd<EPI, ADDEND, 2, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
@@ -1175,10 +1192,10 @@ static int dmma_configure() {
 #define DM_ATTR(E, A) \
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<8>::kSmem) != cudaSuccess) return -3; \
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3; \
-  if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SdGeom<false>::kSmem) != cudaSuccess) return -3;
 #define DM_ATTR_GRAM(E, A) \
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmemGram) != cudaSuccess) return -3; \
-  if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmemGram) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SdGeom<true>::kSmem) != cudaSuccess) return -3;
   DM_ATTR(EPI_STORE, false)
   DM_ATTR(EPI_STORE, true)
   DM_ATTR(EPI_HAM, false)
@@ -1328,13 +1345,25 @@ static int dmma_grid(const DmmaTiles &t, int sms) { return std::max(1, std::min(
 static int dmma_gram_ctas(int kk, int sms) { return std::max(1, std::min(sms, (kk + GR_WARPS - 1) / GR_WARPS)); }
 
 // sdflags(H set, slot) -> true when every block of that slot is spin-diagonal (nullptr: never)
-typedef bool (*SdLookup)(const void *ctx, const double *Hset, int slot);
+// (H set, slot) -> true when every block of that slot is spin-diagonal; *hs18 = the HS18 twin of the set (null: none)
+typedef bool (*SdLookup)(const void *ctx, const double *Hset, int slot, const double **hs18);
 static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, cudaStream_t st, long long *launches,
                              const int32_t *order = nullptr, const int32_t *cnt = nullptr, SdLookup sdl = nullptr,
                              const void *sdctx = nullptr, long long *sd_launches = nullptr, int *nparts_out = nullptr) {
-  DmmaStages sg;
+  DmmaStages sg, sg2;
   memset(&sg, 0, sizeof(sg));
+  memset(&sg2, 0, sizeof(sg2));
   sg.n = 0;
+  bool have_hs18 = sdl != nullptr;
+  // the spin-resolved kernel's list: one HS18 half stage per slot (kind 0), a second one (kind 1) where the slot couples the spins
+  auto add2 = [&](const double *hs18, size_t half_index, int hstride, const double *src, int slot, bool diag) {
+    for (int kind = 0; kind < (diag ? 1 : 2); kind++) {
+      if (!hs18 || sg2.n >= DM_MAXST) { have_hs18 = false; return; }
+      sg2.H[sg2.n] = hs18 + (half_index * 2 + kind) * SDH;
+      sg2.src[sg2.n] = src; sg2.hstride[sg2.n] = hstride; sg2.slot[sg2.n] = slot; sg2.sd[sg2.n] = (unsigned char)kind;
+      sg2.n++;
+    }
+  };
   // neighbour slots of every term first, then the on-site slots, then the on-site extra term (self stage last)
   for (int pass = 0; pass < 2; pass++)
     for (int tm = 0; tm < p.ngterms; tm++)
@@ -1344,26 +1373,30 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
         sg.src[sg.n] = p.g[tm].src;
         sg.hstride[sg.n] = p.nslot_h * HBLK;
         sg.slot[sg.n] = m;
-        sg.sd[sg.n] = sdl && sdl(sdctx, p.g[tm].H, m);
+        const double *hs = nullptr;
+        sg.sd[sg.n] = sdl && sdl(sdctx, p.g[tm].H, m, &hs);
+        if (sdl) add2(hs, (size_t)m, p.nslot_h * 2 * SDH, p.g[tm].src, m, sg.sd[sg.n] != 0);
         sg.n++;
       }
   if (p.Hx) {
     sg.H[sg.n] = p.Hx; sg.src[sg.n] = p.srcx; sg.hstride[sg.n] = HBLK; sg.slot[sg.n] = 0;
-    sg.sd[sg.n] = sdl && sdl(sdctx, p.Hx, 0);
+    const double *hs = nullptr;
+    sg.sd[sg.n] = sdl && sdl(sdctx, p.Hx, 0, &hs);
+    if (sdl) add2(hs, 0, 2 * SDH, p.srcx, 0, sg.sd[sg.n] != 0);
     sg.n++;
   }
   int nsd = 0;
   for (int j = 0; j < sg.n; j++) nsd += sg.sd[j];
   const int geom = dmma_apply_geom();
   const int grid = dmma_apply_grid(t, sms, nunits);
-  // the spin-grouped accumulator layout costs 6 instead of 5 n-tiles on full stages: worth it when most stages are spin-diagonal
-  const bool use_sd = geom == 4 && 2 * nsd > sg.n;
+  // half stages pay off when most slots are spin-diagonal (a coupling slot costs two of them: 60 instead of 45 DMMAs per m-tile)
+  const bool use_sd = geom == 4 && have_hs18 && 2 * nsd > sg.n;
   if (use_sd && sd_launches) (*sd_launches)++;
 #define DM_LAUNCH(E, A)                                                                                                   \
   do {                                                                                                                    \
     if (use_sd)                                                                                                           \
-      k_apply_dmma_sd<E, A><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmem, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,       \
-                                                                              t.ntiles, nunits, order, cnt);             \
+      k_apply_dmma_sd<E, A><<<grid, ApGeom<4>::kThreads, SdGeom<false>::kSmem, st>>>(p, sg2, t.d_sites, t.d_cls, t.d_nbr,  \
+                                                                                  t.ntiles, nunits, order, cnt);         \
     else if (geom == 4)                                                                                                   \
       k_apply_dmma<E, A, 4><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmem, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,       \
                                                                               t.ntiles, nunits, order, cnt);             \
@@ -1374,8 +1407,8 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
 #define DM_LAUNCH_GRAM(E, A)                                                                                              \
   do {                                                                                                                    \
     if (use_sd)                                                                                                           \
-      k_apply_dmma_sd<E, A><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmemGram, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,   \
-                                                                                  t.ntiles, nunits, order, cnt);         \
+      k_apply_dmma_sd<E, A><<<grid, ApGeom<4>::kThreads, SdGeom<true>::kSmem, st>>>(p, sg2, t.d_sites, t.d_cls, t.d_nbr,   \
+                                                                                 t.ntiles, nunits, order, cnt);          \
     else                                                                                                                  \
       k_apply_dmma<E, A, 4><<<grid, ApGeom<4>::kThreads, ApGeom<4>::kSmemGram, st>>>(p, sg, t.d_sites, t.d_cls, t.d_nbr,   \
                                                                                   t.ntiles, nunits, order, cnt);         \

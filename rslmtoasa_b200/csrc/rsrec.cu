@@ -87,6 +87,8 @@ struct rsrec_handle_s {
   DevBuf part, A, B, Bi, B2, mu, ahist, b2hist, bhist /* B = (B^2)^1/2 per level, what zsqr would return */, scratch;
   // per H set (key = device pointer of the packed set): slot -> 1 when every block of the slot is spin-diagonal
   std::map<const double *, std::vector<unsigned char>> sdmap;
+  // HS18 twins of the packed sets (half blocks per spin for the spin-resolved SpMV kernel), keyed like sdmap
+  std::map<const double *, DevBuf> hs18;
   DevBuf post[12];  // work arrays of the post-recursion consumers (terminator, Green functions, Kubo back end)
   // on-site Green function of the last Green-function call, kept for the `bands` consumers (bands.f90)
   DevBuf g0all, bands_y, bands_out;
@@ -356,6 +358,15 @@ static int ensure_ready(H *h) {
       if (h->hoh) h->sdmap[(sx == 0 ? h->Hvoa_neg : h->Hvob_neg).p] = diag(6 + sx, false);   // all-zero set: diagonal too
     }
   }
+  // HS18 twins: [block][kind][spin][18 rows][20 k] from the HR36 blocks (kind 0 = spin-diagonal part, 1 = coupling part)
+  for (auto &kv : h->sdmap) {
+    const size_t nb = (size_t)ncls * kv.second.size();
+    DevBuf &dst = h->hs18[kv.first];
+    TRY(dev_alloc(dst, nb * 2 * SDH, false));
+    k_pack_hs18<<<(unsigned)nb, 256, 0, h->st>>>(kv.first, dst.p, (int)nb);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->st));
   h->dirty_ham = false;
   return RSREC_OK;
@@ -556,10 +567,12 @@ static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas) {
       order = h->plan.d_order;
       cnt = h->plan.d_counts + (size_t)h->plan.level * nunits;
     }
-    auto sdl = [](const void *ctx, const double *Hset, int slot) -> bool {
-      const auto &mp = ((const H *)ctx)->sdmap;
-      auto itf = mp.find(Hset);
-      return itf != mp.end() && slot < (int)itf->second.size() && itf->second[slot];
+    auto sdl = [](const void *ctx, const double *Hset, int slot, const double **hs18) -> bool {
+      const H *hh = (const H *)ctx;
+      auto ith = hh->hs18.find(Hset);
+      *hs18 = ith != hh->hs18.end() ? ith->second.p : nullptr;
+      auto itf = hh->sdmap.find(Hset);
+      return itf != hh->sdmap.end() && slot < (int)itf->second.size() && itf->second[slot];
     };
     int nparts = 0;
     if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches, order, cnt, sdl, h, &h->sd_launches, &nparts) != 0)
@@ -916,6 +929,7 @@ int rsrec_destroy(rsrec_handle h) {
   if (h->d_nbr) cudaFree(h->d_nbr);
   if (h->d_cls) cudaFree(h->d_cls);
   if (h->d_cls_type) cudaFree(h->d_cls_type);
+  for (auto &kv : h->hs18) dev_free(kv.second);
   { DevBuf *cb[] = {&h->cBLK, &h->cBLKO, &h->cLS, &h->cENIM, &h->cOBARM, &h->cV[0], &h->cV[1], &h->cVO[0], &h->cVO[1], &h->gBLK, &h->gBLKO, &h->gENIM}; for (auto b : cb) dev_free(*b); }
   if (h->plan.d_order) cudaFree(h->plan.d_order);
   if (h->plan.d_counts) cudaFree(h->plan.d_counts);
