@@ -802,6 +802,202 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
   else dmma_consumer_sd<EPI, ADDEND, 1, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
 }
 
+// ---- the spin-resolved SpMV with EIGHT consumer warps per CTA ------------------------------------------------------------------
+// The 4-warp form above issues two thirds of the full-block kernel's DMMAs in the same number of instructions and takes the same
+// time: with 2.45 warps per scheduler a warp issues one instruction per ~11 cycles, so the stage is bound by the non-DMMA
+// instruction stream (profiles/r02k_ncu_apply_dmma_sd_config1_collinear.txt).  Here a CTA has 8 consumer warps (4 per scheduler
+// with the two CTAs of an SM), each owning ONE m-tile (8 columns) and, for warps 0..5, one (m-tile 8, n-tile w) unit: 6 or 7
+// independent accumulators per k-step and both spins in the same k-step, no prefetch of `prev`, <= 96 registers.  Epilogues
+// without fused Gram products only (the Lanczos driver uses the separate Gram kernel on collinear Hamiltonians).
+#define SD8_CONS 8
+#define SD8_THREADS (32 * (SD8_CONS + 1))
+template <int EPI, bool ADDEND, int XN, int XSPIN>
+__device__ __forceinline__ void dmma_consumer_sd8(const ApplyParams &p, const DmmaStages &st,
+                                                  const int32_t *__restrict__ tile_sites, double *stages, uint64_t *full,
+                                                  uint64_t *empty, int ntiles, int nunits,
+                                                  const int32_t *__restrict__ order, const int32_t *__restrict__ cnt,
+                                                  int warp, int lane) {
+  typedef EpiTraits<EPI> ET;
+  constexpr int S = 4;
+  typedef SdGeom<false> G;
+  constexpr int STG = G::kStages, STGD = G::kStageD;
+  const int g = lane >> 2, q = lane & 3;
+  const int nst = st.n;
+  const double inv_a = 1.0 / p.a;
+  const int mt0 = warp, mt2 = 8, xn0 = warp;       // own m-tile; the shared m-tile's n-tile of this warp (XN = 1: warps 0..5)
+  int a0[2][2];                                    // [own | shared m-tile][psi spin]: base + q + 9 spin
+#pragma unroll
+  for (int sp = 0; sp < 2; sp++) {
+    a0[0][sp] = SDH + (mt0 * 8 + g) * COLD + 9 * sp + q;
+    a0[1][sp] = SDH + (mt2 * 8 + g) * COLD + 9 * sp + q;
+  }
+  const int c2 = q == 0 ? 8 : 17;
+  int c4[2];
+  c4[0] = q < 2 ? 25 : -q;
+  c4[1] = q < 2 ? 25 : -(q + 9);
+  int brow[6];
+#pragma unroll
+  for (int nt = 0; nt < 6; nt++) brow[nt] = ((nt / 3) * NB + max(sd_prow(nt * 8 + g), 0)) * 20 + q;
+  const int xrow = ((xn0 / 3) * NB + max(sd_prow(xn0 * 8 + g), 0)) * 20 + q;
+
+  uint32_t it = 0, ready = 0;
+  int u = 0, base = 0, n_u = nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0;
+  for (int w = blockIdx.x;; w += gridDim.x) {
+    while (u < nunits && w >= base + n_u) { base += n_u; u++; if (u < nunits) n_u = PassCursor::count<S>(cnt, ntiles, u); }
+    if (u >= nunits) break;
+    const size_t uo = (size_t)u * p.vstride;
+    const int ti = w - base;
+    const int tpos = ti >> 1, half = (ti & 1) * S;
+    const int tile = order ? order[(size_t)u * ntiles + tpos] : tpos;
+    double acc[6][2], xacc[2] = {0.0, 0.0};
+#pragma unroll
+    for (int nt = 0; nt < 6; nt++) acc[nt][0] = acc[nt][1] = 0.0;
+    for (int j = 0; j < nst; j++, it++) {
+      const int slot = it % STG;
+      if (!ready) mbar_wait(&full[slot], (it / STG) & 1);
+      const double *sm = stages + (size_t)slot * STGD;
+      auto stage = [&](auto cross_tag) {
+        constexpr bool CROSS = decltype(cross_tag)::value;
+        constexpr int XS = CROSS ? 1 - XSPIN : XSPIN;
+        auto koff = [&](int kt, int sp) { return kt < 2 ? 4 * kt : kt == 2 ? c2 : kt == 3 ? 21 : c4[sp]; };
+#pragma unroll
+        for (int kt = 0; kt < 5; kt++) {
+          double fa[2], fa2 = 0.0, fb[6], fx = 0.0;
+          fa[0] = sm[a0[0][0] + koff(kt, 0)];
+          fa[1] = sm[a0[0][1] + koff(kt, 1)];
+#pragma unroll
+          for (int nt = 0; nt < 6; nt++) fb[nt] = sm[brow[nt] + 4 * kt];
+          if (XN) { fa2 = sm[a0[1][XS] + koff(kt, XS)]; fx = sm[xrow + 4 * kt]; }
+          if (kt == 3) ready = mbar_test(&full[(it + 1) % STG], ((it + 1) / STG) & 1);
+#pragma unroll
+          for (int nt = 0; nt < 6; nt++) dmma(acc[nt][0], acc[nt][1], fa[CROSS ? 1 - nt / 3 : nt / 3], fb[nt]);
+          if (XN) dmma(xacc[0], xacc[1], fa2, fx);
+        }
+      };
+      if (st.sd[j]) stage(std::true_type()); else stage(std::false_type());
+      if (j < nst - 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+      }
+    }
+    // ===== epilogue: the last stage (self blocks of `in`) is still held =====
+    const int lslot = (it - 1) % STG;
+    const double *sm = stages + (size_t)lslot * STGD;
+    auto out_pair = [&](double v0, double v1, int n, int nt, size_t gb) {
+      const int r0 = sd_row(nt * 8 + 2 * q), r1 = sd_row(nt * 8 + 2 * q + 1);
+      auto one = [&](double v, int r) {
+        const size_t go = gb + r;
+        if (ADDEND) v += __ldg(p.addend + go);
+        if (ET::kScale) {
+          v = (v - p.b * sm[SDH + n * COLD + r]) * inv_a;
+          if (ET::kCheb) v = 2.0 * v - __ldg(p.prev + go);
+        }
+        if (ET::kHop) { p.out2[go] = v; v -= __ldg(p.prev + go); }
+        p.out[go] = v;
+      };
+      if (r0 >= 0 && r1 >= 0) {
+        const size_t go = gb + r0;
+        if (ADDEND) { const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go)); v0 += ad.x; v1 += ad.y; }
+        if (ET::kScale) {
+          const double2 in = *reinterpret_cast<const double2 *>(sm + SDH + n * COLD + r0);
+          v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
+          if (ET::kCheb) { const double2 pr = __ldg(reinterpret_cast<const double2 *>(p.prev + go)); v0 = 2.0 * v0 - pr.x; v1 = 2.0 * v1 - pr.y; }
+        }
+        if (ET::kHop) {
+          *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
+          const double2 pr = __ldg(reinterpret_cast<const double2 *>(p.prev + go));
+          v0 -= pr.x; v1 -= pr.y;
+        }
+        *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
+      } else if (r0 >= 0) one(v0, r0);
+      else if (r1 >= 0) one(v1, r1);
+    };
+    {
+      const int n = mt0 * 8 + g;
+      const int site = tile_sites[tile * DM_S + half + n / NB];
+      if (site < p.kk) {
+        const size_t gb = uo + (size_t)site * BLKD + (n % NB) * COLD;
+#pragma unroll
+        for (int nt = 0; nt < 6; nt++) out_pair(acc[nt][0], acc[nt][1], n, nt, gb);
+      }
+    }
+    if (XN) {
+      const int n = mt2 * 8 + g;
+      const int site = tile_sites[tile * DM_S + half + n / NB];
+      if (site < p.kk) out_pair(xacc[0], xacc[1], n, xn0, uo + (size_t)site * BLKD + (n % NB) * COLD);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[lslot]);
+  }
+}
+
+template <int EPI, bool ADDEND>
+__global__ void __launch_bounds__(SD8_THREADS, 2)
+k_apply_dmma_sd8(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_sites, const int32_t *__restrict__ tile_cls,
+                 const int32_t *__restrict__ tile_nbr, int ntiles, int nunits, const int32_t *__restrict__ order,
+                 const int32_t *__restrict__ cnt) {
+  constexpr int S = 4;
+  typedef SdGeom<false> G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stages = reinterpret_cast<double *>(smem_raw);
+  constexpr int STG = G::kStages, STGD = G::kStageD;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STG * STGD * 8);
+  uint64_t *empty = full + STG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STG; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], SD8_CONS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nst = st.n, ng = p.ngather;
+  if (warp == SD8_CONS) {
+    // producer warp (as in k_apply_dmma_sd): indices fetched two stages ahead of the copy
+    auto settle = [&](PassCursor &c) {
+      while (c.u < nunits && c.w >= c.base + c.n_u) {
+        c.base += c.n_u; c.u++;
+        if (c.u < nunits) c.n_u = PassCursor::count<S>(cnt, ntiles, c.u);
+      }
+    };
+    auto advance = [&](PassCursor &c, int &j) { if (++j == nst) { j = 0; c.w += gridDim.x; settle(c); } };
+    auto fetch = [&](const PassCursor &c, int j, int &site, int &cls) {
+      const int i = c.w - c.base;
+      const int tpos = i >> 1, half = (i & 1) * S;
+      const int tile = order ? order[(size_t)c.u * ntiles + tpos] : tpos;
+      cls = tile_cls[2 * tile + (half ? 1 : 0)];
+      const int m = st.slot[j];
+      site = (lane < S) ? ((m == 0) ? tile_sites[tile * DM_S + half + lane] : tile_nbr[((size_t)tile * ng + m) * DM_S + half + lane]) : 0;
+    };
+    PassCursor c0{(int)blockIdx.x, 0, 0, nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0};
+    int j0 = 0;
+    settle(c0);
+    PassCursor c1 = c0;
+    int j1 = j0;
+    int site0 = 0, cls0 = 0, site1 = 0, cls1 = 0;
+    if (c0.u < nunits) { fetch(c0, j0, site0, cls0); advance(c1, j1); if (c1.u < nunits) fetch(c1, j1, site1, cls1); }
+    for (uint32_t it = 0; c0.u < nunits; it++) {
+      PassCursor c2 = c1;
+      int j2 = j1, site2 = 0, cls2 = 0;
+      if (c2.u < nunits) { advance(c2, j2); if (c2.u < nunits) fetch(c2, j2, site2, cls2); }
+      const int slot = it % STG;
+      mbar_wait(&empty[slot], ((it / STG) & 1) ^ 1);
+      double *sm = stages + (size_t)slot * STGD;
+      if (lane == 0) mbar_expect_tx(&full[slot], STGD * 8);
+      __syncwarp();
+      if (lane < S) {
+        bulk_g2s(sm + SDH + lane * BLKD, st.src[j0] + (size_t)c0.u * p.vstride + (size_t)site0 * BLKD, BLKD * 8, &full[slot]);
+      } else if (lane == S) {
+        bulk_g2s(sm, st.H[j0] + (size_t)cls0 * st.hstride[j0], SDH * 8, &full[slot]);
+      }
+      c0 = c1; j0 = j1; site0 = site1; cls0 = cls1;
+      c1 = c2; j1 = j2; site1 = site2; cls1 = cls2;
+    }
+    return;
+  }
+  if (warp < 3) dmma_consumer_sd8<EPI, ADDEND, 1, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+  else if (warp < 6) dmma_consumer_sd8<EPI, ADDEND, 1, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+  else dmma_consumer_sd8<EPI, ADDEND, 0, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+}
+
 // ---- Gram reductions on the tensor pipe -------------------------------------------------------------------------
 #define GR_WARPS 8
 #define GR_THREADS (32 * GR_WARPS)
@@ -1192,7 +1388,8 @@ static int dmma_configure() {
 #define DM_ATTR(E, A) \
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<8>::kSmem) != cudaSuccess) return -3; \
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmem) != cudaSuccess) return -3; \
-  if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SdGeom<false>::kSmem) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SdGeom<false>::kSmem) != cudaSuccess) return -3; \
+  if (cudaFuncSetAttribute(k_apply_dmma_sd8<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SdGeom<false>::kSmem) != cudaSuccess) return -3;
 #define DM_ATTR_GRAM(E, A) \
   if (cudaFuncSetAttribute(k_apply_dmma<E, A, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ApGeom<4>::kSmemGram) != cudaSuccess) return -3; \
   if (cudaFuncSetAttribute(k_apply_dmma_sd<E, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, SdGeom<true>::kSmem) != cudaSuccess) return -3;
@@ -1392,9 +1589,13 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
   // half stages pay off when most slots are spin-diagonal (a coupling slot costs two of them: 60 instead of 45 DMMAs per m-tile)
   const bool use_sd = geom == 4 && have_hs18 && 2 * nsd > sg.n;
   if (use_sd && sd_launches) (*sd_launches)++;
+  static const bool sd8 = !(getenv("RSREC_SD_WARPS") && atoi(getenv("RSREC_SD_WARPS")) == 4);  // A/B switch: 8 (default) or 4 consumer warps
 #define DM_LAUNCH(E, A)                                                                                                   \
   do {                                                                                                                    \
-    if (use_sd)                                                                                                           \
+    if (use_sd && sd8)                                                                                                    \
+      k_apply_dmma_sd8<E, A><<<grid, SD8_THREADS, SdGeom<false>::kSmem, st>>>(p, sg2, t.d_sites, t.d_cls, t.d_nbr,         \
+                                                                           t.ntiles, nunits, order, cnt);                \
+    else if (use_sd)                                                                                                      \
       k_apply_dmma_sd<E, A><<<grid, ApGeom<4>::kThreads, SdGeom<false>::kSmem, st>>>(p, sg2, t.d_sites, t.d_cls, t.d_nbr,  \
                                                                                   t.ntiles, nunits, order, cnt);         \
     else if (geom == 4)                                                                                                   \
