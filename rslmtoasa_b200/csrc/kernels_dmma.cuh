@@ -802,13 +802,71 @@ k_apply_dmma_sd(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_s
   else dmma_consumer_sd<EPI, ADDEND, 1, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
 }
 
+// ---- A = sum IN^H OUT inside an 8-warp SpMV CTA (EPI_HOP_GRAM) ---------------------------------------------------------------
+// Same products as gram_run<1, ...> (3 x 5 accumulator tiles on the RI36 columns of the pass's `in` and output tiles), spread over
+// eight warps: tile t = 2 w + s (s < 2) -> (m-tile t / 5, n-tile t % 5); warp 7 owns one tile.  Every tile belongs to one warp and
+// is accumulated over the CTA's passes in a fixed order (bitwise reproducible, no cross-warp reduction).
+__device__ __forceinline__ void gram8_tile(int w, int s, int &mt, int &nt) { const int t = min(2 * w + s, 14); mt = t / 5; nt = t % 5; }
+template <int N>
+__device__ __forceinline__ void gram8_run(const double *in_tile, const double *out_tile, int warp, int lane, double (&gacc)[2][2]) {
+  const int g = lane >> 2, q = lane & 3;
+  int aoff[N], boff[N];
+  bool bswap[N];
+#pragma unroll
+  for (int s = 0; s < N; s++) {
+    int mt, nt;
+    gram8_tile(warp, s, mt, nt);
+    const int i = mt * 8 + g, j = nt * 8 + g;
+    aoff[s] = min(i, NB - 1) * COLD;
+    bswap[s] = j >= NB;
+    boff[s] = min(bswap[s] ? j - NB : j, NB - 1) * COLD;
+  }
+#pragma unroll 1
+  for (int site = 0; site < 4; site++) {
+    const double *xin = in_tile + site * BLKD, *xout = out_tile + site * BLKD;
+#pragma unroll
+    for (int ks = 0; ks < 9; ks++) {
+      const int k = 4 * ks + q;
+      const int kj = k < NB ? k + NB : k - NB;   // row of (J X): (J X)[k] = k < 18 ? X[k+18] : -X[k-18]
+      double a[N], b[N];
+#pragma unroll
+      for (int s = 0; s < N; s++) {
+        a[s] = xin[aoff[s] + k];
+        b[s] = xout[boff[s] + (bswap[s] ? kj : k)];
+        if (bswap[s] && k >= NB) b[s] = -b[s];
+      }
+#pragma unroll
+      for (int s = 0; s < N; s++) dmma(gacc[s][0], gacc[s][1], a[s], b[s]);
+    }
+  }
+}
+__device__ __forceinline__ void gram8_flush(double *pp, int warp, int lane, double (&gacc)[2][2]) {
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    if (2 * warp + s < 15) {
+      int mt, nt;
+      gram8_tile(warp, s, mt, nt);
+      const int R = mt * 8 + g;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int C = nt * 8 + 2 * q + e;
+        if (R < NB && C < 2 * NB) pp[2 * (R + NB * (C % NB)) + (C / NB)] = gacc[s][e];
+      }
+    }
+    gacc[s][0] = gacc[s][1] = 0.0;
+  }
+  for (int e = warp * 32 + lane; e < BLKD; e += 32 * 8) pp[BLKD + e] = 0.0;  // matrix 1 is not produced: the reduction still reads it
+}
+
 // ---- the spin-resolved SpMV with EIGHT consumer warps per CTA ------------------------------------------------------------------
 // The 4-warp form above issues two thirds of the full-block kernel's DMMAs in the same number of instructions and takes the same
 // time: with 2.45 warps per scheduler a warp issues one instruction per ~11 cycles, so the stage is bound by the non-DMMA
 // instruction stream (profiles/r02k_ncu_apply_dmma_sd_config1_collinear.txt).  Here a CTA has 8 consumer warps (4 per scheduler
 // with the two CTAs of an SM), each owning ONE m-tile (8 columns) and, for warps 0..5, one (m-tile 8, n-tile w) unit: 6 or 7
-// independent accumulators per k-step and both spins in the same k-step, no prefetch of `prev`, <= 96 registers.  Epilogues
-// without fused Gram products only (the Lanczos driver uses the separate Gram kernel on collinear Hamiltonians).
+// independent accumulators per k-step and both spins in the same k-step, no prefetch of `prev`, <= 96 registers.  EPI_HOP_GRAM
+// (hop_b of the Lanczos step: A = sum psi^H H psi from the output tile in shared memory, 3-stage ring) is carried too;
+// EPI_CHEB (opt-in) stays with the 4-warp kernel.
 #define SD8_CONS 8
 #define SD8_THREADS (32 * (SD8_CONS + 1))
 template <int EPI, bool ADDEND, int XN, int XSPIN>
@@ -816,10 +874,13 @@ __device__ __forceinline__ void dmma_consumer_sd8(const ApplyParams &p, const Dm
                                                   const int32_t *__restrict__ tile_sites, double *stages, uint64_t *full,
                                                   uint64_t *empty, int ntiles, int nunits,
                                                   const int32_t *__restrict__ order, const int32_t *__restrict__ cnt,
-                                                  int warp, int lane) {
+                                                  int warp, int lane, double *gbuf) {
   typedef EpiTraits<EPI> ET;
   constexpr int S = 4;
-  typedef SdGeom<false> G;
+  constexpr int GRAM = ET::kGram;
+  static_assert(GRAM != 2, "EPI_CHEB runs on the 4-warp kernel");
+  typedef SdGeom<(GRAM != 0)> G;
+  double gacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // fused Gram accumulators of this warp's tiles (GRAM == 1)
   constexpr int STG = G::kStages, STGD = G::kStageD;
   const int g = lane >> 2, q = lane & 3;
   const int nst = st.n;
@@ -843,7 +904,11 @@ __device__ __forceinline__ void dmma_consumer_sd8(const ApplyParams &p, const Dm
   uint32_t it = 0, ready = 0;
   int u = 0, base = 0, n_u = nunits > 0 ? PassCursor::count<S>(cnt, ntiles, 0) : 0;
   for (int w = blockIdx.x;; w += gridDim.x) {
-    while (u < nunits && w >= base + n_u) { base += n_u; u++; if (u < nunits) n_u = PassCursor::count<S>(cnt, ntiles, u); }
+    while (u < nunits && w >= base + n_u) {
+      if (GRAM) gram8_flush(p.part + ((size_t)u * gridDim.x + blockIdx.x) * (2 * BLKD), warp, lane, gacc);
+      base += n_u; u++;
+      if (u < nunits) n_u = PassCursor::count<S>(cnt, ntiles, u);
+    }
     if (u >= nunits) break;
     const size_t uo = (size_t)u * p.vstride;
     const int ti = w - base;
@@ -883,48 +948,58 @@ __device__ __forceinline__ void dmma_consumer_sd8(const ApplyParams &p, const Dm
     // ===== epilogue: the last stage (self blocks of `in`) is still held =====
     const int lslot = (it - 1) % STG;
     const double *sm = stages + (size_t)lslot * STGD;
-    auto out_pair = [&](double v0, double v1, int n, int nt, size_t gb) {
+    if (GRAM) consumer_bar(32 * SD8_CONS);  // every warp is done reading the previous pass's output tile
+    // `valid` is false only in the Gram variant (columns of a null site still fill the output tile in shared memory)
+    auto out_pair = [&](double v0, double v1, int n, int nt, size_t gb, bool valid) {
       const int r0 = sd_row(nt * 8 + 2 * q), r1 = sd_row(nt * 8 + 2 * q + 1);
       auto one = [&](double v, int r) {
         const size_t go = gb + r;
-        if (ADDEND) v += __ldg(p.addend + go);
+        if (ADDEND && valid) v += __ldg(p.addend + go);
         if (ET::kScale) {
           v = (v - p.b * sm[SDH + n * COLD + r]) * inv_a;
           if (ET::kCheb) v = 2.0 * v - __ldg(p.prev + go);
         }
-        if (ET::kHop) { p.out2[go] = v; v -= __ldg(p.prev + go); }
-        p.out[go] = v;
+        if (ET::kHop) {
+          if (GRAM == 1) gbuf[n * COLD + r] = v; else p.out2[go] = v;
+          if (valid) v -= __ldg(p.prev + go);
+        }
+        if (valid) p.out[go] = v;
       };
       if (r0 >= 0 && r1 >= 0) {
         const size_t go = gb + r0;
-        if (ADDEND) { const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go)); v0 += ad.x; v1 += ad.y; }
+        if (ADDEND && valid) { const double2 ad = __ldg(reinterpret_cast<const double2 *>(p.addend + go)); v0 += ad.x; v1 += ad.y; }
         if (ET::kScale) {
           const double2 in = *reinterpret_cast<const double2 *>(sm + SDH + n * COLD + r0);
           v0 = (v0 - p.b * in.x) * inv_a; v1 = (v1 - p.b * in.y) * inv_a;
           if (ET::kCheb) { const double2 pr = __ldg(reinterpret_cast<const double2 *>(p.prev + go)); v0 = 2.0 * v0 - pr.x; v1 = 2.0 * v1 - pr.y; }
         }
         if (ET::kHop) {
-          *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
-          const double2 pr = __ldg(reinterpret_cast<const double2 *>(p.prev + go));
-          v0 -= pr.x; v1 -= pr.y;
+          if (GRAM == 1) *reinterpret_cast<double2 *>(gbuf + n * COLD + r0) = make_double2(v0, v1);
+          else *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
+          if (valid) { const double2 pr = __ldg(reinterpret_cast<const double2 *>(p.prev + go)); v0 -= pr.x; v1 -= pr.y; }
         }
-        *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
+        if (valid) *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
       } else if (r0 >= 0) one(v0, r0);
       else if (r1 >= 0) one(v1, r1);
     };
     {
       const int n = mt0 * 8 + g;
       const int site = tile_sites[tile * DM_S + half + n / NB];
-      if (site < p.kk) {
+      if (GRAM || site < p.kk) {
         const size_t gb = uo + (size_t)site * BLKD + (n % NB) * COLD;
 #pragma unroll
-        for (int nt = 0; nt < 6; nt++) out_pair(acc[nt][0], acc[nt][1], n, nt, gb);
+        for (int nt = 0; nt < 6; nt++) out_pair(acc[nt][0], acc[nt][1], n, nt, gb, site < p.kk);
       }
     }
     if (XN) {
       const int n = mt2 * 8 + g;
       const int site = tile_sites[tile * DM_S + half + n / NB];
-      if (site < p.kk) out_pair(xacc[0], xacc[1], n, xn0, uo + (size_t)site * BLKD + (n % NB) * COLD);
+      if (GRAM || site < p.kk) out_pair(xacc[0], xacc[1], n, xn0, uo + (size_t)site * BLKD + (n % NB) * COLD, site < p.kk);
+    }
+    if (GRAM) {
+      consumer_bar(32 * SD8_CONS);  // the output tile is complete in shared memory
+      if (warp < 7) gram8_run<2>(sm + SDH, gbuf, warp, lane, gacc);
+      else gram8_run<1>(sm + SDH, gbuf, warp, lane, gacc);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[lslot]);
@@ -937,12 +1012,13 @@ k_apply_dmma_sd8(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_
                  const int32_t *__restrict__ tile_nbr, int ntiles, int nunits, const int32_t *__restrict__ order,
                  const int32_t *__restrict__ cnt) {
   constexpr int S = 4;
-  typedef SdGeom<false> G;
+  typedef SdGeom<(EpiTraits<EPI>::kGram != 0)> G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stages = reinterpret_cast<double *>(smem_raw);
   constexpr int STG = G::kStages, STGD = G::kStageD;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STG * STGD * 8);
   uint64_t *empty = full + STG;
+  double *gbuf = reinterpret_cast<double *>(smem_raw + G::kRing);  // output tile of a pass (Gram variant only)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < STG; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], SD8_CONS); }
@@ -993,9 +1069,9 @@ k_apply_dmma_sd8(ApplyParams p, DmmaStages st, const int32_t *__restrict__ tile_
     }
     return;
   }
-  if (warp < 3) dmma_consumer_sd8<EPI, ADDEND, 1, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
-  else if (warp < 6) dmma_consumer_sd8<EPI, ADDEND, 1, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
-  else dmma_consumer_sd8<EPI, ADDEND, 0, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane);
+  if (warp < 3) dmma_consumer_sd8<EPI, ADDEND, 1, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
+  else if (warp < 6) dmma_consumer_sd8<EPI, ADDEND, 1, 1>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
+  else dmma_consumer_sd8<EPI, ADDEND, 0, 0>(p, st, tile_sites, stages, full, empty, ntiles, nunits, order, cnt, warp, lane, gbuf);
 }
 
 // ---- Gram reductions on the tensor pipe -------------------------------------------------------------------------
@@ -1405,6 +1481,8 @@ static int dmma_configure() {
   DM_ATTR_GRAM(EPI_CHEB, true)
   DM_ATTR_GRAM(EPI_HOP_GRAM, false)
   DM_ATTR_GRAM(EPI_HOP_GRAM, true)
+  if (cudaFuncSetAttribute(k_apply_dmma_sd8<EPI_HOP_GRAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SdGeom<true>::kSmem) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_apply_dmma_sd8<EPI_HOP_GRAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SdGeom<true>::kSmem) != cudaSuccess) return -3;
 #undef DM_ATTR
 #undef DM_ATTR_GRAM
   if (cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES) != cudaSuccess) return -3;
@@ -1607,7 +1685,10 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
   } while (0)
 #define DM_LAUNCH_GRAM(E, A)                                                                                              \
   do {                                                                                                                    \
-    if (use_sd)                                                                                                           \
+    if (use_sd && sd8 && E == EPI_HOP_GRAM)                                                                               \
+      k_apply_dmma_sd8<EPI_HOP_GRAM, A><<<grid, SD8_THREADS, SdGeom<true>::kSmem, st>>>(p, sg2, t.d_sites, t.d_cls,        \
+                                                                                     t.d_nbr, t.ntiles, nunits, order, cnt); \
+    else if (use_sd)                                                                                                      \
       k_apply_dmma_sd<E, A><<<grid, ApGeom<4>::kThreads, SdGeom<true>::kSmem, st>>>(p, sg2, t.d_sites, t.d_cls, t.d_nbr,   \
                                                                                  t.ntiles, nunits, order, cnt);          \
     else                                                                                                                  \
