@@ -198,8 +198,11 @@ def _relerr(x, r):
     return float(np.abs(np.asarray(x) - np.asarray(r)).max() / np.abs(np.asarray(r)).max())
 
 
-def _best(fn, reps=3):
-    fn()
+def _best(fn, reps=3, warm=1):
+    """best of `reps` host-timed calls after `warm` untimed ones (a millisecond-sized call needs tens of repetitions: the GPU
+    has idled through the CPU baseline that ran just before and takes a few calls to come back to its clocks)"""
+    for _ in range(warm):
+        fn()
     best = 1e30
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -218,7 +221,8 @@ def bench_configs(device, with_cpu=True):
     def lanczos_case(name, lat, ham, lld, tol=1e-10):
         nnb = lat.ncols
         rec = Recursion(ham, lat, Control(lld=lld), Energy(EMIN, EMAX), device=device)
-        t = _best(rec.recur_b)
+        small = lat.kk * len(lat.irec) < 20000
+        t = _best(rec.recur_b, reps=25 if small else 5, warm=5 if small else 1)
         units, steps = len(lat.irec), (lld - 1) * len(lat.irec)
         fl = (nnb + 1 + 4) * P18                      # SpMV + A, then psi A, pmn^H pmn, pmn B^-1, psi B  
         act = _active_site_steps(lat, [int(x) for x in lat.irec], lld - 1)
