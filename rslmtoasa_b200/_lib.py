@@ -37,6 +37,26 @@ class RsrecError(RuntimeError):
         self.code = code
 
 
+def _prefer_bundled_nccl():
+    """librsrec.so opens libnccl.so.2 with dlopen on the first rsrec_comm_* call.  In a Python process that ALSO imports torch
+    the library with that SONAME must be the one torch was built against (the nvidia-nccl wheel): if the older system NCCL
+    is loaded first, `import torch` later resolves its NCCL symbols against it and fails (undefined ncclDevCommCreate).
+    RSREC_NCCL_LIB (honoured by csrc/comm_nccl.cuh before the SONAME search) is pointed at the wheel's file, found without
+    importing torch.  A Fortran / C++ host has no such wheel and uses the system library."""
+    if os.environ.get("RSREC_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["RSREC_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def load():
     """Load librsrec.so (never builds implicitly on a GPU box: the .so travels in-tree).  Fails loudly."""
     global _lib
@@ -45,6 +65,7 @@ def load():
     if not os.path.exists(_build.LIB):
         raise RuntimeError(f"{_build.LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")
+    _prefer_bundled_nccl()
     L = C.CDLL(_build.LIB)
     vp, i, d = C.c_void_p, C.c_int, C.c_double
     L.rsrec_last_error.restype = C.c_char_p

@@ -1667,7 +1667,8 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
   // half stages pay off when most slots are spin-diagonal (a coupling slot costs two of them: 60 instead of 45 DMMAs per m-tile)
   const bool use_sd = geom == 4 && have_hs18 && 2 * nsd > sg.n;
   if (use_sd && sd_launches) (*sd_launches)++;
-  static const bool sd8 = !(getenv("RSREC_SD_WARPS") && atoi(getenv("RSREC_SD_WARPS")) == 4);  // A/B switch: 8 (default) or 4 consumer warps
+  const char *sdw = getenv("RSREC_SD_WARPS");      // A/B switch, read per launch: 8 (default) or 4 consumer warps
+  const bool sd8 = !(sdw && atoi(sdw) == 4);
 #define DM_LAUNCH(E, A)                                                                                                   \
   do {                                                                                                                    \
     if (use_sd && sd8)                                                                                                    \

@@ -36,6 +36,33 @@ def test_config2_surface_full_size(oracle_mod):
 
 
 @pytest.mark.parametrize("hoh", [False, True])
+def test_config1_collinear_full_size(oracle_mod, hoh, monkeypatch):
+    """config 1 (bcc sphere r^2 = 80 -> 5984 sites, lld = 21) with collinear blocks -- what every bccFe regression case of the
+    reference runs: the spin-resolved SpMV with 8 consumer warps (k_apply_dmma_sd8, Lanczos A-products inside) against the
+    oracle, against its 4-warp form (RSREC_SD_WARPS=4) and, for the Chebyshev moments, the same"""
+    lat = S.sphere_cluster("bcc", 80.0)
+    assert lat.kk == 5984
+    ham = S.make_hamiltonian(lat, seed=20260101, spin_orbit=False, hoh=hoh)
+    orc = oracle_mod.Oracle(lat, ham)
+    a_b, b2_b = orc.lanczos_block(lat.irec, 21)
+    a, b = oracle_mod.cheb_scale(EMIN, EMAX)
+    mu, _ = orc.cheb_moments(lat.irec, 21, a, b)
+    got = {}
+    for warps in ("8", "4"):
+        monkeypatch.setenv("RSREC_SD_WARPS", warps)
+        rec = _rec(lat, ham, lld=21)
+        rec.recur_b()
+        rec.chebyshev_recur()
+        assert rec._L.rsrec_spin_diag_launch_count(rec._h) > 0
+        assert relerr(rec.a_b, a_b) < TOL_AB and relerr(rec.b2_b, b2_b) < TOL_AB
+        assert relerr(rec.mu_n, mu) < TOL_MU
+        got[warps] = (rec.a_b.copy(), rec.b2_b.copy(), rec.mu_n.copy())
+        rec.close()
+    for x, y in zip(got["8"], got["4"]):
+        assert relerr(x, y) < 1e-12
+
+
+@pytest.mark.parametrize("hoh", [False, True])
 def test_config3_impurity_full_size(oracle_mod, hoh):
     """config 3: B2 sphere r^2 = 60 -> 3838 sites, 3 types, 15 site-indexed (hall) sites, lld = 21."""
     lat = S.sphere_cluster("bcc", 60.0, ntype=3, nmax=15, type_rule="b2")
