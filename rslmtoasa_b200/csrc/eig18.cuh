@@ -246,6 +246,7 @@ __device__ __forceinline__ void eig18_func(const Eig18Smem &s, const double *f, 
   out[2 * tid] = orr; out[2 * tid + 1] = oi;
 }
 
+#define LZ_EIG_ALONE_SMEM (128 * 1024)  // dynamic shared memory requested (not used) when k_lz_eig must not share its SM
 // crecal_b "B_n+1": take the reduced B^2 of unit blockIdx.x (k_reduce_parts), record it in the history slot, then
 // B = U sqrt(L) U^H and B^-1 = U L^-1/2 U^H.  diag != 0: scalar Lanczos, everything diagonal & real.
 __global__ void __launch_bounds__(BLKC) k_lz_eig(const double *b2, size_t b2stride, double *b2_hist_slot, size_t hstride,

@@ -308,13 +308,13 @@ __device__ __forceinline__ void dmma_consumer(const ApplyParams &p, const DmmaSt
           for (int i = 0; i < 2; i++)
 #pragma unroll
             for (int nt = 0; nt < 5; nt++)
-              pv[i][nt] = (gval[i] && (nt < 4 || q < 2)) ? __ldg(reinterpret_cast<const double2 *>(p.prev + goff[i] + nt * 8))
-                                                         : make_double2(0.0, 0.0);
+              pv[i][nt] = (gval[i] && p.prev && (nt < 4 || q < 2)) ? __ldg(reinterpret_cast<const double2 *>(p.prev + goff[i] + nt * 8))
+                                                                   : make_double2(0.0, 0.0);  // prev == null: plain W = H in
 #pragma unroll
           for (int x = 0; x < XN; x++) {
             const int nt = x == 0 ? xn0 : xn1;
-            xpv[x] = (gval[2] && (nt < 4 || q < 2)) ? __ldg(reinterpret_cast<const double2 *>(p.prev + goff[2] + nt * 8))
-                                                    : make_double2(0.0, 0.0);
+            xpv[x] = (gval[2] && p.prev && (nt < 4 || q < 2)) ? __ldg(reinterpret_cast<const double2 *>(p.prev + goff[2] + nt * 8))
+                                                              : make_double2(0.0, 0.0);
           }
         }
         if (!ready) mbar_wait(&full[slot], (it / STG) & 1);
@@ -625,10 +625,10 @@ __device__ __forceinline__ void dmma_consumer_sd(const ApplyParams &p, const Dmm
           for (int i = 0; i < 2; i++)
 #pragma unroll
             for (int nt = 0; nt < 6; nt++)
-              if (gval[i]) fetch_prev(pv[i][nt], nt, gbase[i]); else pv[i][nt][0] = pv[i][nt][1] = 0.0;
+              if (gval[i] && p.prev) fetch_prev(pv[i][nt], nt, gbase[i]); else pv[i][nt][0] = pv[i][nt][1] = 0.0;
 #pragma unroll
           for (int x = 0; x < XN; x++)
-            if (gval[2]) fetch_prev(xpv[x], xn0 + x, gbase[2]); else xpv[x][0] = xpv[x][1] = 0.0;
+            if (gval[2] && p.prev) fetch_prev(xpv[x], xn0 + x, gbase[2]); else xpv[x][0] = xpv[x][1] = 0.0;
         }
         if (!ready) mbar_wait(&full[slot], (it / STG) & 1);
         const double *sm = stages + (size_t)slot * STGD;
@@ -961,7 +961,7 @@ __device__ __forceinline__ void dmma_consumer_sd8(const ApplyParams &p, const Dm
         }
         if (ET::kHop) {
           if (GRAM == 1) gbuf[n * COLD + r] = v; else p.out2[go] = v;
-          if (valid) v -= __ldg(p.prev + go);
+          if (valid && p.prev) v -= __ldg(p.prev + go);
         }
         if (valid) p.out[go] = v;
       };
@@ -976,7 +976,7 @@ __device__ __forceinline__ void dmma_consumer_sd8(const ApplyParams &p, const Dm
         if (ET::kHop) {
           if (GRAM == 1) *reinterpret_cast<double2 *>(gbuf + n * COLD + r0) = make_double2(v0, v1);
           else *reinterpret_cast<double2 *>(p.out2 + go) = make_double2(v0, v1);
-          if (valid) { const double2 pr = __ldg(reinterpret_cast<const double2 *>(p.prev + go)); v0 -= pr.x; v1 -= pr.y; }
+          if (valid && p.prev) { const double2 pr = __ldg(reinterpret_cast<const double2 *>(p.prev + go)); v0 -= pr.x; v1 -= pr.y; }
         }
         if (valid) *reinterpret_cast<double2 *>(p.out + go) = make_double2(v0, v1);
       } else if (r0 >= 0) one(v0, r0);
@@ -1459,6 +1459,252 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
     rmul_consumer<MODE, 1>(psi, pmn, hpsi, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
 }
 
+// ---- pipelined block Lanczos: rotate + orthogonalise in ONE pass ---------------------------------------------------------------
+// crecal_b (recursion.f90:1873-1973) computes, per step,  hpsi = H psi_n ; R = hpsi - psi_{n-1} B_n - psi_n A_n ; B_{n+1}^2 = R^H R ;
+// B_{n+1} = (B^2)^1/2 ; psi_{n+1} = R B^-1 -- a chain in which the 18x18 square root (a single-CTA kernel, ~25 us) sits between two
+// passes over the vectors.  Right-multiplication by B^-1 commutes with H, so the driver applies H to the UNNORMALISED residual,
+//     W = H R_n ,  G = R_n^H W          (the SpMV kernel with its fused Gram product, running WHILE k_lz_eig forms B, B^-1 on a
+//                                         second stream)
+// and everything else of the step is right-multiplications by 18x18 matrices known once B^-1 and G are:
+//     psi_{n+1} = R_n B^-1 ,   A_{n+1} = psi_{n+1}^H H psi_{n+1} = B^-1 G B^-1 ,
+//     R_{n+1}   = W B^-1 - psi_n B - R_n (B^-1 A_{n+1}) ,   B_{n+2}^2 = sum R_{n+1}^H R_{n+1}.
+// k_rotortho_dmma does that in one pass: three launches on the critical path of a step (SpMV, reduce, this) instead of five, one
+// pass over the vectors instead of two, and the square root off the critical path.  Same algebra as the reference, different
+// association of the products (results agree to rounding, parity tolerance 1e-10).
+// Geometry: one CTA per SM, 8 consumer warps + TMA producer, tiles of FOUR sites (three input tiles R, W, psi per ring slot:
+// 62 kB, two slots); warp w owns m-tile w of the 9 (72 rows) and, for w < 5, unit (m-tile 8, n-tile w).
+#define RO_S 4
+#define RO_TILE_D (RO_S * BLKD)                                       // 2592 doubles = 20736 B
+#define RO_SMEM_BYTES (2 * 3 * RO_TILE_D * 8 + 3 * HBLK * 8 + 64)     // 155 584 B
+
+// acc (+)= X * M for this warp's units: X tile in shared memory (RI36), ts = transposed real embedding of M
+template <int XN, bool ACCUM>
+__device__ __forceinline__ void ro_product(const double *xs, const double *ts, int aoff0, int aoff2, const int (&koff)[9],
+                                           const int (&boff)[5], int xoff, double (&acc)[5][2], double (&xacc)[2]) {
+  if (!ACCUM) {
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) acc[nt][0] = acc[nt][1] = 0.0;
+    xacc[0] = xacc[1] = 0.0;
+  }
+#pragma unroll
+  for (int ks = 0; ks < 9; ks++) {
+    double b[5], xb = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) b[nt] = ts[boff[nt] + 4 * ks];
+    const double a0 = xs[aoff0 + koff[ks]];
+    if (XN) { xb = ts[xoff + 4 * ks]; a2 = xs[aoff2 + koff[ks]]; }
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) dmma(acc[nt][0], acc[nt][1], a0, b[nt]);
+    if (XN) dmma(xacc[0], xacc[1], a2, xb);
+  }
+}
+
+// the two products that read the R tile in one sweep (shared psi-side fragments, twice the independent DMMAs per k-step):
+// acc1 = X * Ma, acc2 = X * Mb
+template <int XN>
+__device__ __forceinline__ void ro_product2(const double *xs, const double *ta, const double *tb, int aoff0, int aoff2,
+                                            const int (&koff)[9], const int (&boff)[5], int xoff, double (&acc1)[5][2],
+                                            double (&xacc1)[2], double (&acc2)[5][2], double (&xacc2)[2]) {
+#pragma unroll
+  for (int nt = 0; nt < 5; nt++) acc1[nt][0] = acc1[nt][1] = acc2[nt][0] = acc2[nt][1] = 0.0;
+  xacc1[0] = xacc1[1] = xacc2[0] = xacc2[1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 9; ks++) {
+    double b1[5], b2[5], xb1 = 0.0, xb2 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) { b1[nt] = ta[boff[nt] + 4 * ks]; b2[nt] = tb[boff[nt] + 4 * ks]; }
+    const double a0 = xs[aoff0 + koff[ks]];
+    if (XN) { xb1 = ta[xoff + 4 * ks]; xb2 = tb[xoff + 4 * ks]; a2 = xs[aoff2 + koff[ks]]; }
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++) {
+      dmma(acc1[nt][0], acc1[nt][1], a0, b1[nt]);
+      dmma(acc2[nt][0], acc2[nt][1], a0, b2[nt]);
+    }
+    if (XN) { dmma(xacc1[0], xacc1[1], a2, xb1); dmma(xacc2[0], xacc2[1], a2, xb2); }
+  }
+}
+
+template <int XN>
+__device__ __forceinline__ void rotortho_consumer(double *psi, double *pmn, int kk, double *tiles, const double *tmat,
+                                                  uint64_t *full, uint64_t *empty, int warp, int lane, const int32_t *bo,
+                                                  int nact, double *gpart) {
+  const int g = lane >> 2, q = lane & 3;
+  double gacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  const int mt[2] = {warp, 8};
+  const int xn = warp;  // n-tile of the shared m-tile (XN = 1: warps 0..4)
+  int aoff[2], rows[2], rowk[2], koff[9], boff[5];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const int n = mt[i] * 8 + g;
+    rows[i] = n / NB; rowk[i] = n % NB;
+    aoff[i] = rows[i] * BLKD + rowk[i];
+  }
+#pragma unroll
+  for (int ks = 0; ks < 9; ks++) { const int j = 4 * ks + q; koff[ks] = (j % NB) * COLD + (j / NB) * NB; }
+#pragma unroll
+  for (int nt = 0; nt < 5; nt++) boff[nt] = min(nt * 8 + g, 35) * COLD + q;
+  const int xoff = min(xn * 8 + g, 35) * COLD + q;
+  const double *M1 = tmat, *M2 = tmat + HBLK, *M3 = tmat + 2 * HBLK;  // B^-1, -B, -B^-1 A
+  uint32_t it = 0;
+  for (int ti = blockIdx.x; ti < 2 * nact; ti += gridDim.x) {
+    const int blk = ti >> 1;
+    const int site0 = (bo ? bo[blk] : blk) * DM_S + (ti & 1) * RO_S;
+    if (site0 >= kk) continue;  // second half of a last, partial block (the producer skips it too)
+    const int slot = it & 1;
+    double *tR = tiles + (size_t)slot * 3 * RO_TILE_D;
+    const double *tW = tR + RO_TILE_D, *tP = tR + 2 * RO_TILE_D;
+    auto gofs = [&](int i, int c) { return (size_t)(site0 + rows[i]) * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
+    auto sofs = [&](int i, int c) { return rows[i] * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
+    auto valid = [&](int i, int c) { return c < 2 * NB && site0 + rows[i] < kk; };
+    double acc[5][2], xacc[2];
+    mbar_wait(&full[slot], (it >> 1) & 1);
+    {
+      // psi_{n+1} = R B^-1 and the first term of R_{n+1} = R (-B^-1 A) + W B^-1 + psi_n (-B)
+      double pacc[5][2], pxacc[2];
+      ro_product2<XN>(tR, M1, M3, aoff[0], aoff[1], koff, boff, xoff, pacc, pxacc, acc, xacc);
+#pragma unroll
+      for (int nt = 0; nt < 5; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = nt * 8 + 2 * q + e;
+          if (valid(0, c)) psi[gofs(0, c)] = pacc[nt][e];
+        }
+      if (XN) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = xn * 8 + 2 * q + e;
+          if (valid(1, c)) psi[gofs(1, c)] = pxacc[e];
+        }
+      }
+    }
+    ro_product<XN, true>(tW, M1, aoff[0], aoff[1], koff, boff, xoff, acc, xacc);
+    ro_product<XN, true>(tP, M2, aoff[0], aoff[1], koff, boff, xoff, acc, xacc);
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * DM_CONSUMERS) : "memory");  // every warp is done reading the R tile
+#pragma unroll
+    for (int nt = 0; nt < 5; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = nt * 8 + 2 * q + e;
+        if (valid(0, c)) { pmn[gofs(0, c)] = acc[nt][e]; tR[sofs(0, c)] = acc[nt][e]; }
+      }
+    if (XN) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = xn * 8 + 2 * q + e;
+        if (valid(1, c)) { pmn[gofs(1, c)] = xacc[e]; tR[sofs(1, c)] = xacc[e]; }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * DM_CONSUMERS) : "memory");  // the new residual tile is complete in shared memory
+    const int ns = min(RO_S, kk - site0);
+    if (warp + 8 < 15) rmul_gram<2>(tR, ns, warp, lane, gacc); else rmul_gram<1>(tR, ns, warp, lane, gacc);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+    it++;
+  }
+#pragma unroll
+  for (int s = 0; s < 2; s++) {  // this warp's tiles of the per-CTA partial of B^2 (matrix 0 of the slot, complex column-major)
+    const int t = warp + 8 * s;
+    if (t < 15) {
+      const int R = (t / 5) * 8 + g;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int C = (t % 5) * 8 + 2 * q + e;
+        if (R < NB && C < 2 * NB) gpart[2 * (R + NB * (C % NB)) + (C / NB)] = gacc[s][e];
+      }
+    }
+  }
+}
+
+// grid = (ctas, nunits).  Bmat, Bimat, Gmat: complex column-major 18x18 per unit (stride mstride doubles).  wv = W = H R.
+// a_out (stride mstride) and a_hist (stride hstride): A_{n+1} = B^-1 G B^-1 (written by CTA 0 of each unit).  diag: scalar Lanczos
+// (18 independent chains: only the real diagonal of G counts, like k_reduce_parts mode 2).
+__global__ void __launch_bounds__(DM_THREADS, 1)
+k_rotortho_dmma(double *psi_all, double *pmn_all, const double *w_all, const double *Bmat, const double *Bimat,
+                const double *Gmat, size_t mstride, double *a_out, double *a_hist, size_t hstride, int diag, int kk,
+                size_t vstride, const int32_t *__restrict__ border, const int32_t *__restrict__ bcnt, int nblocks,
+                double *part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *tiles = reinterpret_cast<double *>(smem_raw);            // [2 slots][3 tiles]
+  double *tmat = tiles + 2 * 3 * RO_TILE_D;                        // [3][36x36]: T[c'][j'] = Mhat[j'][c']
+  uint64_t *full = reinterpret_cast<uint64_t *>(tmat + 3 * HBLK);
+  uint64_t *empty = full + 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, unit = blockIdx.y;
+  double *psi = psi_all + (size_t)unit * vstride, *pmn = pmn_all + (size_t)unit * vstride;
+  const double *wv = w_all + (size_t)unit * vstride;
+  if (tid == 0) {
+    for (int s = 0; s < 2; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], DM_CONSUMERS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- the three 18x18 matrices of the step (complex column-major in the not yet used tile area) ----
+  double *cB = tiles, *cBi = cB + BLKD, *cG = cBi + BLKD, *cT = cG + BLKD, *cA = cT + BLKD, *cM3 = cA + BLKD;
+  for (int e = tid; e < BLKD; e += DM_THREADS) {
+    cB[e] = Bmat[(size_t)unit * mstride + e];
+    cBi[e] = Bimat[(size_t)unit * mstride + e];
+    double gv = Gmat[(size_t)unit * mstride + e];
+    if (diag) { const int ce = e >> 1, i = ce % NB, j = ce / NB; if (i != j || (e & 1)) gv = 0.0; }
+    cG[e] = gv;
+  }
+  __syncthreads();
+  auto cmul18 = [&](const double *X, const double *Y, double *Z, double sgn) {  // Z = sgn * X Y
+    for (int e = tid; e < BLKC; e += DM_THREADS) {
+      const int r = e % NB, c = e / NB;
+      double zr = 0.0, zi = 0.0;
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        const double xr = X[2 * (r + NB * k)], xi = X[2 * (r + NB * k) + 1], yr = Y[2 * (k + NB * c)], yi = Y[2 * (k + NB * c) + 1];
+        zr = fma(xr, yr, zr); zr = fma(-xi, yi, zr);
+        zi = fma(xr, yi, zi); zi = fma(xi, yr, zi);
+      }
+      Z[2 * e] = sgn * zr; Z[2 * e + 1] = sgn * zi;
+    }
+    __syncthreads();
+  };
+  cmul18(cG, cBi, cT, 1.0);     // T = G B^-1
+  cmul18(cBi, cT, cA, 1.0);     // A = B^-1 G B^-1
+  cmul18(cBi, cA, cM3, -1.0);   // M3 = -B^-1 A
+  if (blockIdx.x == 0)
+    for (int e = tid; e < BLKD; e += DM_THREADS) {
+      double v = cA[e];
+      if (diag) { const int ce = e >> 1, i = ce % NB, j = ce / NB; if (i != j || (e & 1)) v = 0.0; }
+      a_out[(size_t)unit * mstride + e] = v;
+      if (a_hist) a_hist[(size_t)unit * hstride + e] = v;
+    }
+  for (int e = tid; e < 3 * HBLK; e += DM_THREADS) {
+    const int w = e / HBLK, r = e % HBLK, c = r / COLD, j = r % COLD;  // T[c'][j']
+    const double *m = w == 0 ? cBi : w == 1 ? cB : cM3;
+    const double re = m[2 * ((j % NB) + NB * (c % NB))], im = m[2 * ((j % NB) + NB * (c % NB)) + 1];
+    double v = (j < NB) == (c < NB) ? re : (j < NB ? im : -im);
+    if (w == 1) v = -v;
+    tmat[e] = v;
+  }
+  __syncthreads();  // the scratch matrices are dead: the producer may fill the tile area
+  const int nact = border ? bcnt[unit] : (kk + DM_S - 1) / DM_S;
+  const int32_t *bo = border ? border + (size_t)unit * nblocks : nullptr;
+  if (warp == DM_CONSUMERS) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int ti = blockIdx.x; ti < 2 * nact; ti += gridDim.x) {
+        const int blk = ti >> 1;
+        const int site0 = (bo ? bo[blk] : blk) * DM_S + (ti & 1) * RO_S, ns = min(RO_S, kk - site0);
+        if (site0 >= kk) continue;
+        const int slot = it & 1;
+        mbar_wait(&empty[slot], ((it >> 1) & 1) ^ 1);
+        const uint32_t bytes = (uint32_t)ns * BLKD * 8;
+        double *sm = tiles + (size_t)slot * 3 * RO_TILE_D;
+        mbar_expect_tx(&full[slot], 3 * bytes);
+        bulk_g2s(sm, pmn + (size_t)site0 * BLKD, bytes, &full[slot]);
+        bulk_g2s(sm + RO_TILE_D, wv + (size_t)site0 * BLKD, bytes, &full[slot]);
+        bulk_g2s(sm + 2 * RO_TILE_D, psi + (size_t)site0 * BLKD, bytes, &full[slot]);
+        it++;
+      }
+    }
+    return;
+  }
+  double *gpart = part + ((size_t)unit * gridDim.x + blockIdx.x) * (2 * BLKD);
+  if (warp < 5) rotortho_consumer<1>(psi, pmn, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
+  else rotortho_consumer<0>(psi, pmn, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 static int dmma_configure() {
 #define DM_ATTR(E, A) \
@@ -1488,6 +1734,7 @@ static int dmma_configure() {
   if (cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES) != cudaSuccess) return -3;
   if (cudaFuncSetAttribute(k_rmul_dmma<RM_ORTHO>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES) != cudaSuccess) return -3;
   if (cudaFuncSetAttribute(k_rmul_dmma<RM_ROTATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, RM_SMEM_BYTES) != cudaSuccess) return -3;
+  if (cudaFuncSetAttribute(k_rotortho_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, RO_SMEM_BYTES) != cudaSuccess) return -3;
   return 0;
 }
 
@@ -1709,6 +1956,17 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
   }
 #undef DM_LAUNCH
 #undef DM_LAUNCH_GRAM
+  (*launches)++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+static int dmma_launch_rotortho(double *psi, double *pmn, const double *w, const double *B, const double *Bi, const double *G,
+                                size_t mstride, double *a_out, double *a_hist, size_t hstride, int diag, int kk, size_t vstride,
+                                int nunits, int ctas, cudaStream_t st, long long *launches, const int32_t *border,
+                                const int32_t *bcnt, int nblocks, double *part) {
+  dim3 grid(ctas, nunits);
+  k_rotortho_dmma<<<grid, DM_THREADS, RO_SMEM_BYTES, st>>>(psi, pmn, w, B, Bi, G, mstride, a_out, a_hist, hstride, diag, kk,
+                                                           vstride, border, bcnt, nblocks, part);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -52,6 +52,9 @@ struct rsrec_handle_s {
   bool fam_ok = true;  // every operator application of this handle fits the tensor pipeline's stage list (set by ensure_ready)
   int sms = 148;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;               // side stream of the pipelined Lanczos step (k_lz_eig beside the SpMV), created on first use
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int sm_reserve = 0;                       // SMs the next gather-SpMV launch leaves one CTA slot free on (for the side stream's kernel)
   long long launches = 0;
   long long sd_launches = 0;  // SpMV launches that took the spin-diagonal two-block kernel
   int last_parts = 0;  // partial-sum slots per unit written by the last fused apply
@@ -150,8 +153,8 @@ struct HostScope {
 // records a CUDA event pair around a phase on the handle's stream while phase timing is enabled (two event records per
 // phase; nothing otherwise)
 struct PhaseScope {
-  H *h; size_t idx = (size_t)-1;
-  PhaseScope(H *h_, int phase) : h(h_) {
+  H *h; size_t idx = (size_t)-1; cudaStream_t s;
+  PhaseScope(H *h_, int phase, cudaStream_t stream = nullptr) : h(h_), s(stream ? stream : h_->st) {
     if (!h->phase_on) return;
     if (h->phase_used == h->phase_events.size()) {
       rsrec_handle_s::PhaseEv e; e.phase = phase;
@@ -160,9 +163,9 @@ struct PhaseScope {
     }
     idx = h->phase_used++;
     h->phase_events[idx].phase = phase;
-    cudaEventRecord(h->phase_events[idx].a, h->st);
+    cudaEventRecord(h->phase_events[idx].a, s);
   }
-  ~PhaseScope() { if (idx != (size_t)-1) cudaEventRecord(h->phase_events[idx].b, h->st); }
+  ~PhaseScope() { if (idx != (size_t)-1) cudaEventRecord(h->phase_events[idx].b, s); }
 };
 static int post_configure();
 static int comm_allreduce_dev(rsrec_handle_s *h, double *d, size_t n);
@@ -408,7 +411,21 @@ static bool fused_gram(const H *h) { return fam1(h) && h->fuse_lanczos && dmma_a
 // by the FP64 tensor pipe, the stand-alone Gram kernel keeps it 96 % busy, and the fused form measured 27.8 ms per step
 // against 26.4 ms at 10^6 sites (profiles/r02b_*).  RSREC_FUSED_CHEB=1 turns it on.
 static bool fused_cheb(const H *h) { return fam1(h) && h->fuse_cheb && dmma_apply_geom() == 4; }
-static int lanczos_nvec(const H *h, bool diag) { return 2 + ((fam1(h) && !fused_gram(h)) ? 1 : 0) + ((h->hoh && !diag) ? 1 : 0); }
+// Pipelined step (kernels_dmma.cuh, k_rotortho_dmma): H is applied to the unnormalised residual while k_lz_eig runs on a second
+// stream, rotate + orthogonalise are one pass.  Needs the fused Gram products.  One more block vector per unit (W = H R).
+// It pays where a step is bound by launch and single-CTA latencies, i.e. on one unit of the small lattices of the reference's own
+// cases (5984 sites: 4.22 -> 3.94 ms, 3838 sites: 3.41 -> 3.00 ms); on batches the extra right-multiplication (4 instead of 3 per
+// site and step) costs more than the square root it hides (2 x 5984 sites: 7.05 vs 7.04 ms, 8 x: 26.4 vs 23.7; config 2,
+// 6 x 16 756 sites: 51.0 vs 46.6 ms; profiles/r02r_*).  RSREC_LZ_PIPELINE=1 / 0 forces it on / off.
+#define LZ_PIPELINE_MAX_SITES 8192
+static bool lz_pipelined(const H *h, int nunits) {
+  const char *env = getenv("RSREC_LZ_PIPELINE");  // read per call (tests switch it)
+  if (!fused_gram(h)) return false;
+  if (env && *env) return atoi(env) != 0;
+  return (long long)nunits * h->kk <= LZ_PIPELINE_MAX_SITES;
+}
+// (the pipelined form holds W = H R; sized for it whenever a batch could take it)
+static int lanczos_nvec(const H *h, bool diag) { return 2 + ((fam1(h) && (!fused_gram(h) || lz_pipelined(h, 1))) ? 1 : 0) + ((h->hoh && !diag) ? 1 : 0); }
 static int cheb_nvec(const H *h) { return 2 + (h->hoh ? 1 : 0); }
 // largest unit batch whose `nvec` work vectors (+ extra bytes per unit: histories, a non-resident g0) fit
 static int unit_batch(H *h, int nunits, int nvec, size_t extra_bytes_per_unit = 0) {
@@ -575,7 +592,7 @@ static int launch_apply_inner(H *h, ApplyParams &p, int nunits, int nctas) {
       return itf != hh->sdmap.end() && slot < (int)itf->second.size() && itf->second[slot];
     };
     int nparts = 0;
-    if (dmma_launch_apply(h->tiles, p, nunits, h->sms, h->st, &h->launches, order, cnt, sdl, h, &h->sd_launches, &nparts) != 0)
+    if (dmma_launch_apply(h->tiles, p, nunits, h->sms - h->sm_reserve, h->st, &h->launches, order, cnt, sdl, h, &h->sd_launches, &nparts) != 0)
       return fail(RSREC_ECUDA, std::string("k_apply_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     h->last_parts = (p.epi == EPI_CHEB || p.epi == EPI_HOP_GRAM) ? nparts : 0;  // one partial slot per CTA of the launch
     return RSREC_OK;
@@ -692,8 +709,11 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   if (h->hoh && !diag) TRY(get_vec(h, 2, nunits, &tmp));
   double *hpsi = nullptr;
   const bool fused = fused_gram(h);
-  if (fam1(h) && !fused) TRY(get_vec(h, 3, nunits, &hpsi));
-  TRY(dev_alloc(h->part, part_doubles(h, nunits, nctas), false));
+  const bool pipelined = lz_pipelined(h, nunits) && lld >= 2;
+  if (fam1(h) && (!fused || pipelined)) TRY(get_vec(h, 3, nunits, &hpsi));  // hpsi of the staged form / W = H R of the pipelined one
+  const size_t pd = part_doubles(h, nunits, nctas);
+  TRY(dev_alloc(h->part, pipelined ? 2 * pd : pd, false));  // pipelined: second half = the B^2 partials (read by the side stream)
+  double *part2 = h->part.p + pd;
   TRY(dev_alloc(h->A, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->B, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->Bi, (size_t)nunits * BLKD, false));
@@ -714,6 +734,67 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   k_set_identity<<<nunits, 64, 0, h->st>>>(h->bhist.p, hs, nunits);   // and its square root
   h->launches += 3;
   const dim3 grid(nctas, nunits);
+  if (pipelined) {
+    if (!h->st2) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    const OpKind op = diag ? OP_SCALAR : OP_HAM;
+    cudaStream_t st2 = h->st2;
+    double *W = hpsi, *G = h->B2.p;
+    int np2 = 0;
+    const int32_t *bo, *bc; int nbk;
+    // step 0 in the reference's order: pmn = H psi_0 (pmn was zero), A_0, R_0 = pmn - psi_0 A_0, partials of B_1^2
+    {
+      PhaseScope ph_(h, PH_HPSI);
+      TRY(apply_op(h, op, psi, pmn, pmn, tmp, EPI_HOP_GRAM, 1.0, 0.0, nunits, nctas, h->part.p));
+      TRY(launch_reduce(h, nunits, nctas, diag ? 2 : 0, h->A.p, nullptr, BLKD, nullptr, nullptr, h->ahist.p, hs));
+    }
+    {
+      PhaseScope ph_(h, PH_ORTHO);
+      plan_blocks(h, nunits, &bo, &bc, &nbk);
+      if (dmma_launch_rmul(RM_ORTHO, psi, pmn, nullptr, h->A.p, nullptr, BLKD, h->kk, vstride(h), nunits, h->sms, h->st, &h->launches, bo, bc, nbk, part2, &np2) != 0)
+        return fail(RSREC_ECUDA, std::string("k_rmul_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    for (int ll = 0; ll < lld - 1; ll++) {
+      // B_{ll+1}^2 -> history, B, B^-1 on the side stream ...
+      CUDA_TRY(cudaEventRecord(h->ev_fork, h->st));
+      CUDA_TRY(cudaStreamWaitEvent(st2, h->ev_fork, 0));
+      {
+        PhaseScope ph_(h, PH_BNEXT, st2);
+        // 128 kB of (unused) dynamic shared memory: no SpMV CTA (>= 93 kB) fits beside this CTA, so the square root has an SM --
+        // and its FP64 pipe, which a co-resident DMMA kernel saturates (the iteration took 93 us instead of 25) -- to itself
+        k_lz_eig<<<nunits, BLKC, LZ_EIG_ALONE_SMEM, st2>>>(nullptr, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
+                                              BLKD, diag ? 1 : 0, h->sqrt_method, h->bhist.p + (size_t)(ll + 1) * BLKD,
+                                              part2, np2);
+        h->launches++;
+      }
+      CUDA_TRY(cudaEventRecord(h->ev_join, st2));
+      if (ll == lld - 2) { CUDA_TRY(cudaStreamWaitEvent(h->st, h->ev_join, 0)); break; }  // the last level needs no further A
+      // ... while H is applied to the unnormalised residual: W = H R, G = sum R^H W (one SM per eig CTA left free)
+      {
+        PhaseScope ph_(h, PH_HPSI);
+        h->sm_reserve = std::min(h->sms / 2, nunits);
+        const int rc = apply_op(h, op, pmn, W, nullptr, tmp, EPI_HOP_GRAM, 1.0, 0.0, nunits, nctas, h->part.p);
+        h->sm_reserve = 0;
+        TRY(rc);
+        TRY(launch_reduce(h, nunits, nctas, diag ? 2 : 0, G, nullptr, BLKD, nullptr, nullptr));
+      }
+      CUDA_TRY(cudaStreamWaitEvent(h->st, h->ev_join, 0));
+      // psi_{ll+1} = R B^-1 ; A_{ll+1} = B^-1 G B^-1 ; R_{ll+1} = W B^-1 - psi_ll B - R B^-1 A_{ll+1} ; partials of B_{ll+2}^2
+      {
+        PhaseScope ph_(h, PH_ORTHO);
+        plan_blocks(h, nunits, &bo, &bc, &nbk);
+        np2 = dmma_rmul_ctas(h->kk, h->sms, nunits);
+        if (dmma_launch_rotortho(psi, pmn, W, h->B.p, h->Bi.p, G, BLKD, h->A.p, h->ahist.p + (size_t)(ll + 1) * BLKD, hs, diag ? 1 : 0,
+                                 h->kk, vstride(h), nunits, np2, h->st, &h->launches, bo, bc, nbk, part2) != 0)
+          return fail(RSREC_ECUDA, std::string("k_rotortho_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+      }
+      { PhaseScope ph_(h, PH_ROTATE); }  // '<PSI|B_n+1|PSI>' is part of the merged pass: the label stays in the host's timer tree (calls counted, ~0 ms)
+      CUDA_TRY(cudaGetLastError());
+    }
+  } else
   for (int ll = 0; ll < lld - 1; ll++) {
     // hop_b / hop_b_hoh: pmn = H psi - pmn ; A = sum psi^H H psi
     {
@@ -775,6 +856,16 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     }
     }
     CUDA_TRY(cudaGetLastError());
+  }
+  if (h->phase_on && getenv("RSREC_LZ_TIMELINE")) {  // diagnostics: start / end of every timed phase of this call, us from the first
+    cudaStreamSynchronize(h->st);
+    if (h->st2) cudaStreamSynchronize(h->st2);
+    for (size_t i = 0; i < h->phase_used; i++) {
+      float ta = 0.f, tb = 0.f;
+      cudaEventElapsedTime(&ta, h->phase_events[0].a, h->phase_events[i].a);
+      cudaEventElapsedTime(&tb, h->phase_events[0].a, h->phase_events[i].b);
+      fprintf(stderr, "timeline phase %d  %9.1f -> %9.1f us\n", h->phase_events[i].phase, 1e3 * ta, 1e3 * tb);
+    }
   }
   if (a_host) { CUDA_TRY(cudaMemcpyAsync(a_host, h->ahist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double)); }
   if (b2_host) { CUDA_TRY(cudaMemcpyAsync(b2_host, h->b2hist.p, (size_t)nunits * hs * sizeof(double), cudaMemcpyDeviceToHost, h->st)); h->d2h_bytes += (long long)((size_t)nunits * hs * sizeof(double)); }
@@ -940,6 +1031,7 @@ int rsrec_destroy(rsrec_handle h) {
   for (auto &ev : h->phase_events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   if (h->comm && nccl_api()->dl) nccl_api()->CommDestroy(h->comm);
   dev_free(h->comm_buf); dev_free(h->comm_res);
+  if (h->st2) { cudaStreamDestroy(h->st2); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
   cudaStreamDestroy(h->st);
   delete h;
   return RSREC_OK;
@@ -1341,6 +1433,7 @@ static int bgreen_smem(int nw) { return (2 * BG_MAT + nw * BG_WSTRIDE) * (int)si
 static int post_configure() {
   if (cudaFuncSetAttribute(k_bgreen<BG_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bgreen_smem(BG_WARPS)) != cudaSuccess) return -1;
   if (cudaFuncSetAttribute(k_bgreen<BG_WARPS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bgreen_smem(BG_WARPS_WIDE)) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_lz_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ_EIG_ALONE_SMEM) != cudaSuccess) return -1;
   return 0;
 }
 static int to_dev(H *h, DevBuf &b, const void *src, size_t ndoubles) {

@@ -28,7 +28,11 @@ def test_phase_timers_carry_the_reference_labels():
     rec.recur_b()
     ph = rec.phase_read()
     assert set(ph) == {"H|PSI_n>", "H|Psi_n-A_n|Psi_n-B_n|Psi_n-1", "B_n+1", "<PSI|B_n+1|PSI>"}
-    assert all(calls == 6 and ms > 0.0 for ms, calls in ph.values())
+    assert all(ms > 0.0 for ms, _ in ph.values())
+    assert all(ph[k][1] == 6 for k in ("H|PSI_n>", "H|Psi_n-A_n|Psi_n-B_n|Psi_n-1", "B_n+1"))
+    # the pipelined step (small lattices, one unit) merges the rotation into the orthogonalisation pass and skips the last one,
+    # whose result nothing reads; the five-launch step rotates after every level like the reference
+    assert ph["<PSI|B_n+1|PSI>"][1] in (5, 6)
     rec.chebyshev_recur()
     ph = rec.phase_read()
     assert ph["<PSI_0|PSI_0>"][1] == 1 and ph["<PSI_0|PSI_1>"][1] == 1 and ph["<PSI_0|PSI_n>"][1] == 7

@@ -599,3 +599,51 @@ def test_gram_products_inside_the_spmv_kernel(oracle_mod, name):
     assert res[1][2] < res[0][2]                      # one launch less per step
     assert relerr(res[1][0], res[0][0]) < 1e-12 and relerr(res[1][1], res[0][1]) < 1e-12
 
+
+
+# ---- pipelined block Lanczos step (k_rotortho_dmma + the square root on a second stream) ------------------------------------------
+@pytest.mark.parametrize("name", ["bulk", "bulk_hoh", "impurity", "impurity_hoh", "surface", "pbc"])
+def test_pipelined_lanczos_step_against_the_oracle_and_the_five_launch_step(oracle_mod, name, monkeypatch):
+    """H applied to the unnormalised residual while B = (B^2)^1/2 is formed on a second stream, rotation + three-term update +
+    orthogonalisation in one pass (A_n = B^-1 (R^H H R) B^-1): same algebra as crecal_b (recursion.f90:1873-1973), different
+    association -- a_b / b2_b must agree with the oracle to 1e-10 and with the five-launch step to rounding, for site and pair
+    starts, with hoh, a site-indexed region, several units in a batch, and for the scalar recursion."""
+    from rslmtoasa_b200 import Recursion, Control, Energy
+    lat, ham = case(name)
+    lld = 9
+    orc = oracle_mod.Oracle(lat, ham)
+    a_o, b_o = orc.lanczos_block(lat.irec, lld)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RSREC_LZ_PIPELINE", mode)
+        rec = Recursion(ham, lat, Control(lld=lld), Energy(EMIN, EMAX))
+        n0 = rec.launch_count
+        rec.recur_b()
+        launches = rec.launch_count - n0
+        assert relerr(rec.a_b, a_o) < 1e-10 and relerr(rec.b2_b, b_o) < 1e-10, mode
+        out = [rec.a_b.copy(), rec.b2_b.copy()]
+        rec.ijpair = np.array([[1, 2], [3, 3]], dtype=np.int32)
+        rec.recur_b_ij()
+        out += [rec.a_b.copy(), rec.b2_b.copy()]
+        res[mode] = (out, launches)
+        rec.close()
+    assert res["1"][1] < res["0"][1]          # four launches per step (one of them off the critical path) instead of five
+    for x, y in zip(res["1"][0], res["0"][0]):
+        assert relerr(x, y) < 1e-11
+
+
+def test_pipelined_scalar_lanczos(oracle_mod, monkeypatch):
+    from rslmtoasa_b200 import Recursion, Control, Energy
+    lat, ham = case("impurity")
+    lld = 9
+    a_o, b_o = oracle_mod.Oracle(lat, ham).lanczos_scalar(lat.irec, lld)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RSREC_LZ_PIPELINE", mode)
+        rec = Recursion(ham, lat, Control(lld=lld), Energy(EMIN, EMAX))
+        rec.recur()
+        assert relerr(rec.a[..., 0], a_o) < 1e-10 and relerr(rec.b2[..., 0], b_o) < 1e-10, mode
+        res[mode] = (rec.a.copy(), rec.b2.copy())
+        rec.close()
+    for x, y in zip(res["1"], res["0"]):
+        assert relerr(x, y) < 1e-11
