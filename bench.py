@@ -547,21 +547,27 @@ def main():
     if not args.no_e2e:
         e2e_lld = args.e2e_lld
         rec.control.lld = e2e_lld
-        barrier()
-        torch.cuda.synchronize()
-        h0, d0 = rec.h2d_bytes, rec.d2h_bytes
-        t0 = time.perf_counter()
-        rec.upload()                       # set_lattice + set_hamiltonian (tables rebuilt and re-uploaded)
-        # this rank's vector (its block-rule shard of the `world` columns): phases H2D, lld steps, moments summed over
-        # vectors and all-reduced over NVLink on the device (rsrec_cheb_moments_random_sum), one D2H of the summed moments
-        mu_sum = rec.chebyshev_recur_random_sum(ph_local, sharded=False)   # ph_local: pinned host memory
-        t1 = time.perf_counter()
-        assert np.isfinite(mu_sum).all()
-        e2e_s = max_over_ranks(t1 - t0)
+        # two complete passes, the faster one reported (a single 7 s shot through the host API showed 6.7 ... 7.5 s on one box)
+        passes = []
+        for _ in range(2):
+            barrier()
+            torch.cuda.synchronize()
+            h0, d0 = rec.h2d_bytes, rec.d2h_bytes
+            t0 = time.perf_counter()
+            rec.upload()                       # set_lattice + set_hamiltonian (tables rebuilt and re-uploaded)
+            # this rank's vector (its block-rule shard of the `world` columns): phases H2D, lld steps, moments summed over
+            # vectors and all-reduced over NVLink on the device (rsrec_cheb_moments_random_sum), one D2H of the summed moments
+            mu_sum = rec.chebyshev_recur_random_sum(ph_local, sharded=False)   # ph_local: pinned host memory
+            t1 = time.perf_counter()
+            assert np.isfinite(mu_sum).all()
+            passes.append(max_over_ranks(t1 - t0))
+            h2d_step, d2h_step = (rec.h2d_bytes - h0) / e2e_lld, (rec.d2h_bytes - d0) / e2e_lld
+        e2e_s = min(passes)
         e2e = {"value": world * e2e_lld / e2e_s, "unit": "steps/s",
-               "h2d_bytes_per_step": (rec.h2d_bytes - h0) / e2e_lld, "d2h_bytes_per_step": (rec.d2h_bytes - d0) / e2e_lld,
-               "steps": e2e_lld, "seconds": e2e_s,
-               "what": "rsrec_set_lattice + rsrec_set_hamiltonian + rsrec_cheb_moments_random_sum(lld=%d) from host arrays"
+               "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+               "steps": e2e_lld, "seconds": e2e_s, "passes_s": passes,
+               "what": "rsrec_set_lattice + rsrec_set_hamiltonian + rsrec_cheb_moments_random_sum(lld=%d) from host arrays, "
+                       "faster of two complete passes"
                        "%s" % (e2e_lld, " (moments all-reduced by the library's NCCL communicator, %d ranks)" % world if world > 1 else "")}
 
     # ---------------- strong scaling of unit-sharded work (N > 1): fixed total, sharded by the reference's block rule ----
