@@ -1466,13 +1466,17 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
 //     W = H R_n ,  G = R_n^H W          (the SpMV kernel with its fused Gram product, running WHILE k_lz_eig forms B, B^-1 on a
 //                                         second stream)
 // and everything else of the step is right-multiplications by 18x18 matrices known once B^-1 and G are:
-//     psi_{n+1} = R_n B^-1 ,   A_{n+1} = psi_{n+1}^H H psi_{n+1} = B^-1 G B^-1 ,
-//     R_{n+1}   = W B^-1 - psi_n B - R_n (B^-1 A_{n+1}) ,   B_{n+2}^2 = sum R_{n+1}^H R_{n+1}.
-// k_rotortho_dmma does that in one pass: three launches on the critical path of a step (SpMV, reduce, this) instead of five, one
-// pass over the vectors instead of two, and the square root off the critical path.  Same algebra as the reference, different
-// association of the products (results agree to rounding, parity tolerance 1e-10).
-// Geometry: one CTA per SM, 8 consumer warps + TMA producer, tiles of FOUR sites (three input tiles R, W, psi per ring slot:
-// 62 kB, two slots); warp w owns m-tile w of the 9 (72 rows) and, for w < 5, unit (m-tile 8, n-tile w).
+//     psi_{n+1} = R_n B_{n+1}^-1 ,   A_{n+1} = psi_{n+1}^H H psi_{n+1} = B^-1 G B^-1 ,
+//     R_{n+1}   = W B^-1 - psi_n B_{n+1} - R_n (B^-1 A_{n+1}) ,   B_{n+2}^2 = sum R_{n+1}^H R_{n+1}.
+// The normalised vectors are never needed as such: psi_n = R_{n-1} B_n^-1 (R_{-1} = the start vector, B_0 = 1), so the state of
+// the recursion is the last TWO residuals and
+//     R_{n+1} = W B_{n+1}^-1  -  R_{n-1} (B_n^-1 B_{n+1})  -  R_n (B_{n+1}^-1 A_{n+1})
+// is three right-multiplications per site, written over R_{n-1}.  k_rotortho_dmma does that in one pass: three launches on the
+// critical path of a step (SpMV, reduce, this) instead of five, one pass over the vectors instead of two, and the square root
+// off the critical path.  Same algebra as the reference, different association of the products (results agree to rounding,
+// parity tolerance 1e-10).
+// Geometry: one CTA per SM, 8 consumer warps + TMA producer, tiles of FOUR sites (three input tiles R_n, W, R_{n-1} per ring
+// slot: 62 kB, two slots); warp w owns m-tile w of the 9 (72 rows) and, for w < 5, unit (m-tile 8, n-tile w).
 #define RO_S 4
 #define RO_TILE_D (RO_S * BLKD)                                       // 2592 doubles = 20736 B
 #define RO_SMEM_BYTES (2 * 3 * RO_TILE_D * 8 + 3 * HBLK * 8 + 64)     // 155 584 B
@@ -1499,33 +1503,8 @@ __device__ __forceinline__ void ro_product(const double *xs, const double *ts, i
   }
 }
 
-// the two products that read the R tile in one sweep (shared psi-side fragments, twice the independent DMMAs per k-step):
-// acc1 = X * Ma, acc2 = X * Mb
 template <int XN>
-__device__ __forceinline__ void ro_product2(const double *xs, const double *ta, const double *tb, int aoff0, int aoff2,
-                                            const int (&koff)[9], const int (&boff)[5], int xoff, double (&acc1)[5][2],
-                                            double (&xacc1)[2], double (&acc2)[5][2], double (&xacc2)[2]) {
-#pragma unroll
-  for (int nt = 0; nt < 5; nt++) acc1[nt][0] = acc1[nt][1] = acc2[nt][0] = acc2[nt][1] = 0.0;
-  xacc1[0] = xacc1[1] = xacc2[0] = xacc2[1] = 0.0;
-#pragma unroll
-  for (int ks = 0; ks < 9; ks++) {
-    double b1[5], b2[5], xb1 = 0.0, xb2 = 0.0, a2 = 0.0;
-#pragma unroll
-    for (int nt = 0; nt < 5; nt++) { b1[nt] = ta[boff[nt] + 4 * ks]; b2[nt] = tb[boff[nt] + 4 * ks]; }
-    const double a0 = xs[aoff0 + koff[ks]];
-    if (XN) { xb1 = ta[xoff + 4 * ks]; xb2 = tb[xoff + 4 * ks]; a2 = xs[aoff2 + koff[ks]]; }
-#pragma unroll
-    for (int nt = 0; nt < 5; nt++) {
-      dmma(acc1[nt][0], acc1[nt][1], a0, b1[nt]);
-      dmma(acc2[nt][0], acc2[nt][1], a0, b2[nt]);
-    }
-    if (XN) { dmma(xacc1[0], xacc1[1], a2, xb1); dmma(xacc2[0], xacc2[1], a2, xb2); }
-  }
-}
-
-template <int XN>
-__device__ __forceinline__ void rotortho_consumer(double *psi, double *pmn, int kk, double *tiles, const double *tmat,
+__device__ __forceinline__ void rotortho_consumer(double *rnew, int kk, double *tiles, const double *tmat,
                                                   uint64_t *full, uint64_t *empty, int warp, int lane, const int32_t *bo,
                                                   int nact, double *gpart) {
   const int g = lane >> 2, q = lane & 3;
@@ -1544,59 +1523,42 @@ __device__ __forceinline__ void rotortho_consumer(double *psi, double *pmn, int 
 #pragma unroll
   for (int nt = 0; nt < 5; nt++) boff[nt] = min(nt * 8 + g, 35) * COLD + q;
   const int xoff = min(xn * 8 + g, 35) * COLD + q;
-  const double *M1 = tmat, *M2 = tmat + HBLK, *M3 = tmat + 2 * HBLK;  // B^-1, -B, -B^-1 A
+  const double *M1 = tmat, *M2 = tmat + HBLK, *M3 = tmat + 2 * HBLK;  // B^-1, -B_prev^-1 B, -B^-1 A
   uint32_t it = 0;
   for (int ti = blockIdx.x; ti < 2 * nact; ti += gridDim.x) {
     const int blk = ti >> 1;
     const int site0 = (bo ? bo[blk] : blk) * DM_S + (ti & 1) * RO_S;
     if (site0 >= kk) continue;  // second half of a last, partial block (the producer skips it too)
     const int slot = it & 1;
-    double *tR = tiles + (size_t)slot * 3 * RO_TILE_D;
-    const double *tW = tR + RO_TILE_D, *tP = tR + 2 * RO_TILE_D;
+    const double *tC = tiles + (size_t)slot * 3 * RO_TILE_D, *tW = tC + RO_TILE_D;   // R_n, W = H R_n
+    double *tP = tiles + (size_t)slot * 3 * RO_TILE_D + 2 * RO_TILE_D;               // R_{n-1}, replaced by R_{n+1}
     auto gofs = [&](int i, int c) { return (size_t)(site0 + rows[i]) * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
     auto sofs = [&](int i, int c) { return rows[i] * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
     auto valid = [&](int i, int c) { return c < 2 * NB && site0 + rows[i] < kk; };
     double acc[5][2], xacc[2];
     mbar_wait(&full[slot], (it >> 1) & 1);
-    {
-      // psi_{n+1} = R B^-1 and the first term of R_{n+1} = R (-B^-1 A) + W B^-1 + psi_n (-B)
-      double pacc[5][2], pxacc[2];
-      ro_product2<XN>(tR, M1, M3, aoff[0], aoff[1], koff, boff, xoff, pacc, pxacc, acc, xacc);
-#pragma unroll
-      for (int nt = 0; nt < 5; nt++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int c = nt * 8 + 2 * q + e;
-          if (valid(0, c)) psi[gofs(0, c)] = pacc[nt][e];
-        }
-      if (XN) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int c = xn * 8 + 2 * q + e;
-          if (valid(1, c)) psi[gofs(1, c)] = pxacc[e];
-        }
-      }
-    }
+    // R_{n+1} = R_n (-B^-1 A) + W B^-1 + R_{n-1} (-B_prev^-1 B)
+    ro_product<XN, false>(tC, M3, aoff[0], aoff[1], koff, boff, xoff, acc, xacc);
     ro_product<XN, true>(tW, M1, aoff[0], aoff[1], koff, boff, xoff, acc, xacc);
     ro_product<XN, true>(tP, M2, aoff[0], aoff[1], koff, boff, xoff, acc, xacc);
-    asm volatile("bar.sync 1, %0;" ::"r"(32 * DM_CONSUMERS) : "memory");  // every warp is done reading the R tile
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * DM_CONSUMERS) : "memory");  // every warp is done reading the R_{n-1} tile
 #pragma unroll
     for (int nt = 0; nt < 5; nt++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int c = nt * 8 + 2 * q + e;
-        if (valid(0, c)) { pmn[gofs(0, c)] = acc[nt][e]; tR[sofs(0, c)] = acc[nt][e]; }
+        if (valid(0, c)) { rnew[gofs(0, c)] = acc[nt][e]; tP[sofs(0, c)] = acc[nt][e]; }
       }
     if (XN) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int c = xn * 8 + 2 * q + e;
-        if (valid(1, c)) { pmn[gofs(1, c)] = xacc[e]; tR[sofs(1, c)] = xacc[e]; }
+        if (valid(1, c)) { rnew[gofs(1, c)] = xacc[e]; tP[sofs(1, c)] = xacc[e]; }
       }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(32 * DM_CONSUMERS) : "memory");  // the new residual tile is complete in shared memory
     const int ns = min(RO_S, kk - site0);
-    if (warp + 8 < 15) rmul_gram<2>(tR, ns, warp, lane, gacc); else rmul_gram<1>(tR, ns, warp, lane, gacc);
+    if (warp + 8 < 15) rmul_gram<2>(tP, ns, warp, lane, gacc); else rmul_gram<1>(tP, ns, warp, lane, gacc);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[slot]);
     it++;
@@ -1615,12 +1577,13 @@ __device__ __forceinline__ void rotortho_consumer(double *psi, double *pmn, int 
   }
 }
 
-// grid = (ctas, nunits).  Bmat, Bimat, Gmat: complex column-major 18x18 per unit (stride mstride doubles).  wv = W = H R.
+// grid = (ctas, nunits).  Bmat, Bimat, Biprev, Gmat: complex column-major 18x18 per unit (stride mstride doubles; Biprev with its own
+// stride, 0 = one matrix for all units: the identity of the first step).  cur = R_n, wv = W = H R_n, prev = R_{n-1} -> R_{n+1}.
 // a_out (stride mstride) and a_hist (stride hstride): A_{n+1} = B^-1 G B^-1 (written by CTA 0 of each unit).  diag: scalar Lanczos
 // (18 independent chains: only the real diagonal of G counts, like k_reduce_parts mode 2).
 __global__ void __launch_bounds__(DM_THREADS, 1)
-k_rotortho_dmma(double *psi_all, double *pmn_all, const double *w_all, const double *Bmat, const double *Bimat,
-                const double *Gmat, size_t mstride, double *a_out, double *a_hist, size_t hstride, int diag, int kk,
+k_rotortho_dmma(double *prev_all, const double *cur_all, const double *w_all, const double *Bmat, const double *Bimat,
+                const double *Biprev, size_t pstride, const double *Gmat, size_t mstride, double *a_out, double *a_hist, size_t hstride, int diag, int kk,
                 size_t vstride, const int32_t *__restrict__ border, const int32_t *__restrict__ bcnt, int nblocks,
                 double *part) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1629,17 +1592,19 @@ k_rotortho_dmma(double *psi_all, double *pmn_all, const double *w_all, const dou
   uint64_t *full = reinterpret_cast<uint64_t *>(tmat + 3 * HBLK);
   uint64_t *empty = full + 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, unit = blockIdx.y;
-  double *psi = psi_all + (size_t)unit * vstride, *pmn = pmn_all + (size_t)unit * vstride;
-  const double *wv = w_all + (size_t)unit * vstride;
+  double *prev = prev_all + (size_t)unit * vstride;
+  const double *cur = cur_all + (size_t)unit * vstride, *wv = w_all + (size_t)unit * vstride;
   if (tid == 0) {
     for (int s = 0; s < 2; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], DM_CONSUMERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // ---- the three 18x18 matrices of the step (complex column-major in the not yet used tile area) ----
-  double *cB = tiles, *cBi = cB + BLKD, *cG = cBi + BLKD, *cT = cG + BLKD, *cA = cT + BLKD, *cM3 = cA + BLKD;
+  double *cB = tiles, *cBi = cB + BLKD, *cG = cBi + BLKD, *cT = cG + BLKD, *cA = cT + BLKD, *cM3 = cA + BLKD, *cBp = cM3 + BLKD,
+         *cM2 = cBp + BLKD;
   for (int e = tid; e < BLKD; e += DM_THREADS) {
     cB[e] = Bmat[(size_t)unit * mstride + e];
     cBi[e] = Bimat[(size_t)unit * mstride + e];
+    cBp[e] = Biprev[(size_t)unit * pstride + e];
     double gv = Gmat[(size_t)unit * mstride + e];
     if (diag) { const int ce = e >> 1, i = ce % NB, j = ce / NB; if (i != j || (e & 1)) gv = 0.0; }
     cG[e] = gv;
@@ -1662,6 +1627,7 @@ k_rotortho_dmma(double *psi_all, double *pmn_all, const double *w_all, const dou
   cmul18(cG, cBi, cT, 1.0);     // T = G B^-1
   cmul18(cBi, cT, cA, 1.0);     // A = B^-1 G B^-1
   cmul18(cBi, cA, cM3, -1.0);   // M3 = -B^-1 A
+  cmul18(cBp, cB, cM2, -1.0);   // M2 = -B_prev^-1 B
   if (blockIdx.x == 0)
     for (int e = tid; e < BLKD; e += DM_THREADS) {
       double v = cA[e];
@@ -1671,11 +1637,9 @@ k_rotortho_dmma(double *psi_all, double *pmn_all, const double *w_all, const dou
     }
   for (int e = tid; e < 3 * HBLK; e += DM_THREADS) {
     const int w = e / HBLK, r = e % HBLK, c = r / COLD, j = r % COLD;  // T[c'][j']
-    const double *m = w == 0 ? cBi : w == 1 ? cB : cM3;
+    const double *m = w == 0 ? cBi : w == 1 ? cM2 : cM3;
     const double re = m[2 * ((j % NB) + NB * (c % NB))], im = m[2 * ((j % NB) + NB * (c % NB)) + 1];
-    double v = (j < NB) == (c < NB) ? re : (j < NB ? im : -im);
-    if (w == 1) v = -v;
-    tmat[e] = v;
+    tmat[e] = (j < NB) == (c < NB) ? re : (j < NB ? im : -im);
   }
   __syncthreads();  // the scratch matrices are dead: the producer may fill the tile area
   const int nact = border ? bcnt[unit] : (kk + DM_S - 1) / DM_S;
@@ -1692,17 +1656,17 @@ k_rotortho_dmma(double *psi_all, double *pmn_all, const double *w_all, const dou
         const uint32_t bytes = (uint32_t)ns * BLKD * 8;
         double *sm = tiles + (size_t)slot * 3 * RO_TILE_D;
         mbar_expect_tx(&full[slot], 3 * bytes);
-        bulk_g2s(sm, pmn + (size_t)site0 * BLKD, bytes, &full[slot]);
+        bulk_g2s(sm, cur + (size_t)site0 * BLKD, bytes, &full[slot]);
         bulk_g2s(sm + RO_TILE_D, wv + (size_t)site0 * BLKD, bytes, &full[slot]);
-        bulk_g2s(sm + 2 * RO_TILE_D, psi + (size_t)site0 * BLKD, bytes, &full[slot]);
+        bulk_g2s(sm + 2 * RO_TILE_D, prev + (size_t)site0 * BLKD, bytes, &full[slot]);
         it++;
       }
     }
     return;
   }
   double *gpart = part + ((size_t)unit * gridDim.x + blockIdx.x) * (2 * BLKD);
-  if (warp < 5) rotortho_consumer<1>(psi, pmn, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
-  else rotortho_consumer<0>(psi, pmn, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
+  if (warp < 5) rotortho_consumer<1>(prev, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
+  else rotortho_consumer<0>(prev, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -1960,12 +1924,12 @@ static int dmma_launch_apply(DmmaTiles &t, ApplyParams &p, int nunits, int sms, 
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
-static int dmma_launch_rotortho(double *psi, double *pmn, const double *w, const double *B, const double *Bi, const double *G,
-                                size_t mstride, double *a_out, double *a_hist, size_t hstride, int diag, int kk, size_t vstride,
+static int dmma_launch_rotortho(double *prev, const double *cur, const double *w, const double *B, const double *Bi,
+                                const double *Biprev, size_t pstride, const double *G, size_t mstride, double *a_out, double *a_hist, size_t hstride, int diag, int kk, size_t vstride,
                                 int nunits, int ctas, cudaStream_t st, long long *launches, const int32_t *border,
                                 const int32_t *bcnt, int nblocks, double *part) {
   dim3 grid(ctas, nunits);
-  k_rotortho_dmma<<<grid, DM_THREADS, RO_SMEM_BYTES, st>>>(psi, pmn, w, B, Bi, G, mstride, a_out, a_hist, hstride, diag, kk,
+  k_rotortho_dmma<<<grid, DM_THREADS, RO_SMEM_BYTES, st>>>(prev, cur, w, B, Bi, Biprev, pstride, G, mstride, a_out, a_hist, hstride, diag, kk,
                                                            vstride, border, bcnt, nblocks, part);
   (*launches)++;
   return cudaGetLastError() == cudaSuccess ? 0 : -3;

@@ -413,11 +413,11 @@ static bool fused_gram(const H *h) { return fam1(h) && h->fuse_lanczos && dmma_a
 static bool fused_cheb(const H *h) { return fam1(h) && h->fuse_cheb && dmma_apply_geom() == 4; }
 // Pipelined step (kernels_dmma.cuh, k_rotortho_dmma): H is applied to the unnormalised residual while k_lz_eig runs on a second
 // stream, rotate + orthogonalise are one pass.  Needs the fused Gram products.  One more block vector per unit (W = H R).
-// It pays where a step is bound by launch and single-CTA latencies, i.e. on one unit of the small lattices of the reference's own
-// cases (5984 sites: 4.22 -> 3.94 ms, 3838 sites: 3.41 -> 3.00 ms); on batches the extra right-multiplication (4 instead of 3 per
-// site and step) costs more than the square root it hides (2 x 5984 sites: 7.05 vs 7.04 ms, 8 x: 26.4 vs 23.7; config 2,
-// 6 x 16 756 sites: 51.0 vs 46.6 ms; profiles/r02r_*).  RSREC_LZ_PIPELINE=1 / 0 forces it on / off.
-#define LZ_PIPELINE_MAX_SITES 8192
+// It pays where a step is bound by launch and single-CTA latencies, i.e. on the small lattices of the reference's own cases
+// (5984 sites: 4.21 -> 3.67 ms, 3838 sites: 3.42 -> 2.82 ms; 4 units of 5984 sites: 12.6 -> 12.1 ms); on batches that fill the
+// GPU the square root it hides is a negligible part of a step (8 x 5984 sites: 23.97 vs 23.76 ms; profiles/r02r_*).
+// RSREC_LZ_PIPELINE=1 / 0 forces it on / off.
+#define LZ_PIPELINE_MAX_SITES 32768
 static bool lz_pipelined(const H *h, int nunits) {
   const char *env = getenv("RSREC_LZ_PIPELINE");  // read per call (tests switch it)
   if (!fused_gram(h)) return false;
@@ -716,7 +716,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
   double *part2 = h->part.p + pd;
   TRY(dev_alloc(h->A, (size_t)nunits * BLKD, false));
   TRY(dev_alloc(h->B, (size_t)nunits * BLKD, false));
-  TRY(dev_alloc(h->Bi, (size_t)nunits * BLKD, false));
+  TRY(dev_alloc(h->Bi, (size_t)2 * nunits * BLKD, false));  // two: the pipelined step needs B^-1 of the previous level too
   TRY(dev_alloc(h->B2, (size_t)nunits * BLKD, false));
   const size_t hs = (size_t)lld * BLKD;  // history stride per unit (doubles)
   TRY(dev_alloc(h->ahist, (size_t)nunits * hs, false));
@@ -743,6 +743,7 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
     const OpKind op = diag ? OP_SCALAR : OP_HAM;
     cudaStream_t st2 = h->st2;
     double *W = hpsi, *G = h->B2.p;
+    double *prev = psi, *cur = pmn;  // R_{n-1} (R_{-1} = the start vector) and R_n: the state of the pipelined recursion
     int np2 = 0;
     const int32_t *bo, *bc; int nbk;
     // step 0 in the reference's order: pmn = H psi_0 (pmn was zero), A_0, R_0 = pmn - psi_0 A_0, partials of B_1^2
@@ -765,7 +766,8 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
         PhaseScope ph_(h, PH_BNEXT, st2);
         // 128 kB of (unused) dynamic shared memory: no SpMV CTA (>= 93 kB) fits beside this CTA, so the square root has an SM --
         // and its FP64 pipe, which a co-resident DMMA kernel saturates (the iteration took 93 us instead of 25) -- to itself
-        k_lz_eig<<<nunits, BLKC, LZ_EIG_ALONE_SMEM, st2>>>(nullptr, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p, h->Bi.p,
+        k_lz_eig<<<nunits, BLKC, LZ_EIG_ALONE_SMEM, st2>>>(nullptr, BLKD, h->b2hist.p + (size_t)(ll + 1) * BLKD, hs, h->B.p,
+                                              h->Bi.p + (size_t)(ll & 1) * nunits * BLKD,
                                               BLKD, diag ? 1 : 0, h->sqrt_method, h->bhist.p + (size_t)(ll + 1) * BLKD,
                                               part2, np2);
         h->launches++;
@@ -776,20 +778,25 @@ static int lanczos_batch(H *h, int nunits, int lld, bool diag, double *a_host /*
       {
         PhaseScope ph_(h, PH_HPSI);
         h->sm_reserve = std::min(h->sms / 2, nunits);
-        const int rc = apply_op(h, op, pmn, W, nullptr, tmp, EPI_HOP_GRAM, 1.0, 0.0, nunits, nctas, h->part.p);
+        const int rc = apply_op(h, op, cur, W, nullptr, tmp, EPI_HOP_GRAM, 1.0, 0.0, nunits, nctas, h->part.p);
         h->sm_reserve = 0;
         TRY(rc);
         TRY(launch_reduce(h, nunits, nctas, diag ? 2 : 0, G, nullptr, BLKD, nullptr, nullptr));
       }
       CUDA_TRY(cudaStreamWaitEvent(h->st, h->ev_join, 0));
-      // psi_{ll+1} = R B^-1 ; A_{ll+1} = B^-1 G B^-1 ; R_{ll+1} = W B^-1 - psi_ll B - R B^-1 A_{ll+1} ; partials of B_{ll+2}^2
+      // A_{ll+1} = B^-1 G B^-1 ; R_{ll+1} = W B^-1 - R_{ll-1} (B_prev^-1 B) - R_ll B^-1 A_{ll+1} (over R_{ll-1}) ; partials of B_{ll+2}^2
       {
         PhaseScope ph_(h, PH_ORTHO);
         plan_blocks(h, nunits, &bo, &bc, &nbk);
         np2 = dmma_rmul_ctas(h->kk, h->sms, nunits);
-        if (dmma_launch_rotortho(psi, pmn, W, h->B.p, h->Bi.p, G, BLKD, h->A.p, h->ahist.p + (size_t)(ll + 1) * BLKD, hs, diag ? 1 : 0,
-                                 h->kk, vstride(h), nunits, np2, h->st, &h->launches, bo, bc, nbk, part2) != 0)
+        const double *Bi_cur = h->Bi.p + (size_t)(ll & 1) * nunits * BLKD;
+        // B^-1 of the previous level; level 0 is the identity (b2temp_b(:,:,1) = I: slot 0 of the B history)
+        const double *Bi_prev = ll == 0 ? h->bhist.p : h->Bi.p + (size_t)((ll - 1) & 1) * nunits * BLKD;
+        if (dmma_launch_rotortho(prev, cur, W, h->B.p, Bi_cur, Bi_prev, ll == 0 ? hs : (size_t)BLKD, G, BLKD, h->A.p,
+                                 h->ahist.p + (size_t)(ll + 1) * BLKD, hs, diag ? 1 : 0, h->kk, vstride(h), nunits, np2, h->st,
+                                 &h->launches, bo, bc, nbk, part2) != 0)
           return fail(RSREC_ECUDA, std::string("k_rotortho_dmma launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        std::swap(prev, cur);
       }
       { PhaseScope ph_(h, PH_ROTATE); }  // '<PSI|B_n+1|PSI>' is part of the merged pass: the label stays in the host's timer tree (calls counted, ~0 ms)
       CUDA_TRY(cudaGetLastError());
