@@ -647,3 +647,20 @@ def test_pipelined_scalar_lanczos(oracle_mod, monkeypatch):
         rec.close()
     for x, y in zip(res["1"], res["0"]):
         assert relerr(x, y) < 1e-11
+
+
+@pytest.mark.parametrize("lld", [1, 2, 3])
+def test_pipelined_lanczos_shortest_recursions(oracle_mod, lld, monkeypatch):
+    """lld = 1 (no step at all), 2 (one square root, no merged pass) and 3 (one merged pass) through the pipelined driver"""
+    from rslmtoasa_b200 import Recursion, Control, Energy
+    lat, ham = case("bulk")
+    a_o, b_o = oracle_mod.Oracle(lat, ham).lanczos_block(lat.irec, lld)
+    monkeypatch.setenv("RSREC_LZ_PIPELINE", "1")
+    rec = Recursion(ham, lat, Control(lld=lld), Energy(EMIN, EMAX))
+    rec.recur_b()
+    assert relerr(rec.b2_b, b_o) < 1e-10
+    if lld > 1:
+        assert relerr(rec.a_b, a_o) < 1e-10
+    else:
+        assert not rec.a_b.any() and not np.abs(a_o).any()
+    rec.close()
