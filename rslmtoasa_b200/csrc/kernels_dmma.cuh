@@ -1479,7 +1479,7 @@ k_rmul_dmma(double *psi_all, double *pmn_all, const double *hpsi_all, const doub
 // slot: 62 kB, two slots); warp w owns m-tile w of the 9 (72 rows) and, for w < 5, unit (m-tile 8, n-tile w).
 #define RO_S 4
 #define RO_TILE_D (RO_S * BLKD)                                       // 2592 doubles = 20736 B
-#define RO_SMEM_BYTES (2 * 3 * RO_TILE_D * 8 + 3 * HBLK * 8 + 64)     // 155 584 B
+#define RO_SMEM_BYTES (2 * 3 * RO_TILE_D * 8 + 3 * HBLK * 8 + 8 * BLKD * 8 + 64)   // tiles, three matrices, prologue scratch: 197 056 B
 
 // acc (+)= X * M for this warp's units: X tile in shared memory (RI36), ts = transposed real embedding of M
 template <int XN, bool ACCUM>
@@ -1589,7 +1589,8 @@ k_rotortho_dmma(double *prev_all, const double *cur_all, const double *w_all, co
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *tiles = reinterpret_cast<double *>(smem_raw);            // [2 slots][3 tiles]
   double *tmat = tiles + 2 * 3 * RO_TILE_D;                        // [3][36x36]: T[c'][j'] = Mhat[j'][c']
-  uint64_t *full = reinterpret_cast<uint64_t *>(tmat + 3 * HBLK);
+  double *scratch = tmat + 3 * HBLK;                               // eight 18x18 complex matrices of the prologue
+  uint64_t *full = reinterpret_cast<uint64_t *>(scratch + 8 * BLKD);
   uint64_t *empty = full + 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, unit = blockIdx.y;
   double *prev = prev_all + (size_t)unit * vstride;
@@ -1598,53 +1599,11 @@ k_rotortho_dmma(double *prev_all, const double *cur_all, const double *w_all, co
     for (int s = 0; s < 2; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], DM_CONSUMERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // ---- the three 18x18 matrices of the step (complex column-major in the not yet used tile area) ----
-  double *cB = tiles, *cBi = cB + BLKD, *cG = cBi + BLKD, *cT = cG + BLKD, *cA = cT + BLKD, *cM3 = cA + BLKD, *cBp = cM3 + BLKD,
-         *cM2 = cBp + BLKD;
-  for (int e = tid; e < BLKD; e += DM_THREADS) {
-    cB[e] = Bmat[(size_t)unit * mstride + e];
-    cBi[e] = Bimat[(size_t)unit * mstride + e];
-    cBp[e] = Biprev[(size_t)unit * pstride + e];
-    double gv = Gmat[(size_t)unit * mstride + e];
-    if (diag) { const int ce = e >> 1, i = ce % NB, j = ce / NB; if (i != j || (e & 1)) gv = 0.0; }
-    cG[e] = gv;
-  }
   __syncthreads();
-  auto cmul18 = [&](const double *X, const double *Y, double *Z, double sgn) {  // Z = sgn * X Y
-    for (int e = tid; e < BLKC; e += DM_THREADS) {
-      const int r = e % NB, c = e / NB;
-      double zr = 0.0, zi = 0.0;
-#pragma unroll
-      for (int k = 0; k < NB; k++) {
-        const double xr = X[2 * (r + NB * k)], xi = X[2 * (r + NB * k) + 1], yr = Y[2 * (k + NB * c)], yi = Y[2 * (k + NB * c) + 1];
-        zr = fma(xr, yr, zr); zr = fma(-xi, yi, zr);
-        zi = fma(xr, yi, zi); zi = fma(xi, yr, zi);
-      }
-      Z[2 * e] = sgn * zr; Z[2 * e + 1] = sgn * zi;
-    }
-    __syncthreads();
-  };
-  cmul18(cG, cBi, cT, 1.0);     // T = G B^-1
-  cmul18(cBi, cT, cA, 1.0);     // A = B^-1 G B^-1
-  cmul18(cBi, cA, cM3, -1.0);   // M3 = -B^-1 A
-  cmul18(cBp, cB, cM2, -1.0);   // M2 = -B_prev^-1 B
-  if (blockIdx.x == 0)
-    for (int e = tid; e < BLKD; e += DM_THREADS) {
-      double v = cA[e];
-      if (diag) { const int ce = e >> 1, i = ce % NB, j = ce / NB; if (i != j || (e & 1)) v = 0.0; }
-      a_out[(size_t)unit * mstride + e] = v;
-      if (a_hist) a_hist[(size_t)unit * hstride + e] = v;
-    }
-  for (int e = tid; e < 3 * HBLK; e += DM_THREADS) {
-    const int w = e / HBLK, r = e % HBLK, c = r / COLD, j = r % COLD;  // T[c'][j']
-    const double *m = w == 0 ? cBi : w == 1 ? cM2 : cM3;
-    const double re = m[2 * ((j % NB) + NB * (c % NB))], im = m[2 * ((j % NB) + NB * (c % NB)) + 1];
-    tmat[e] = (j < NB) == (c < NB) ? re : (j < NB ? im : -im);
-  }
-  __syncthreads();  // the scratch matrices are dead: the producer may fill the tile area
   const int nact = border ? bcnt[unit] : (kk + DM_S - 1) / DM_S;
   const int32_t *bo = border ? border + (size_t)unit * nblocks : nullptr;
   if (warp == DM_CONSUMERS) {
+    // the tiles do not depend on the matrices: the copies of the first two start while the consumer warps form them
     if (lane == 0) {
       uint32_t it = 0;
       for (int ti = blockIdx.x; ti < 2 * nact; ti += gridDim.x) {
@@ -1664,6 +1623,57 @@ k_rotortho_dmma(double *prev_all, const double *cur_all, const double *w_all, co
     }
     return;
   }
+  // ---- the three 18x18 matrices of the step, formed by the 8 consumer warps (complex column-major in `scratch`) ----
+  constexpr int NT = 32 * DM_CONSUMERS;
+  auto cbar = [&]() { asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory"); };
+  double *cB = scratch, *cBi = cB + BLKD, *cG = cBi + BLKD, *cT = cG + BLKD, *cA = cT + BLKD, *cM3 = cA + BLKD, *cBp = cM3 + BLKD,
+         *cM2 = cBp + BLKD;
+  for (int e = tid; e < BLKD; e += NT) {
+    cB[e] = Bmat[(size_t)unit * mstride + e];
+    cBi[e] = Bimat[(size_t)unit * mstride + e];
+    cBp[e] = Biprev[(size_t)unit * pstride + e];
+    double gv = Gmat[(size_t)unit * mstride + e];
+    if (diag) { const int ce = e >> 1, i = ce % NB, j = ce / NB; if (i != j || (e & 1)) gv = 0.0; }
+    cG[e] = gv;
+  }
+  cbar();
+  // Z0 = s0 X0 Y0 and (n == 2) Z1 = s1 X1 Y1 in one sweep
+  auto cmul18 = [&](int n, const double *X0, const double *Y0, double *Z0, double s0, const double *X1, const double *Y1, double *Z1,
+                    double s1) {
+    for (int e2 = tid; e2 < n * BLKC; e2 += NT) {
+      const bool second = e2 >= BLKC;
+      const int e = second ? e2 - BLKC : e2, r = e % NB, c = e / NB;
+      const double *X = second ? X1 : X0, *Y = second ? Y1 : Y0;
+      double zr = 0.0, zi = 0.0;
+#pragma unroll
+      for (int k = 0; k < NB; k++) {
+        const double xr = X[2 * (r + NB * k)], xi = X[2 * (r + NB * k) + 1], yr = Y[2 * (k + NB * c)], yi = Y[2 * (k + NB * c) + 1];
+        zr = fma(xr, yr, zr); zr = fma(-xi, yi, zr);
+        zi = fma(xr, yi, zi); zi = fma(xi, yr, zi);
+      }
+      double *Z = second ? Z1 : Z0;
+      const double sg = second ? s1 : s0;
+      Z[2 * e] = sg * zr; Z[2 * e + 1] = sg * zi;
+    }
+    cbar();
+  };
+  cmul18(2, cG, cBi, cT, 1.0, cBp, cB, cM2, -1.0);            // T = G B^-1 ;  M2 = -B_prev^-1 B
+  cmul18(1, cBi, cT, cA, 1.0, nullptr, nullptr, nullptr, 0.0);   // A = B^-1 G B^-1
+  cmul18(1, cBi, cA, cM3, -1.0, nullptr, nullptr, nullptr, 0.0); // M3 = -B^-1 A
+  if (blockIdx.x == 0)
+    for (int e = tid; e < BLKD; e += NT) {
+      double v = cA[e];
+      if (diag) { const int ce = e >> 1, i = ce % NB, j = ce / NB; if (i != j || (e & 1)) v = 0.0; }
+      a_out[(size_t)unit * mstride + e] = v;
+      if (a_hist) a_hist[(size_t)unit * hstride + e] = v;
+    }
+  for (int e = tid; e < 3 * HBLK; e += NT) {
+    const int w = e / HBLK, r = e % HBLK, c = r / COLD, j = r % COLD;  // T[c'][j']
+    const double *m = w == 0 ? cBi : w == 1 ? cM2 : cM3;
+    const double re = m[2 * ((j % NB) + NB * (c % NB))], im = m[2 * ((j % NB) + NB * (c % NB)) + 1];
+    tmat[e] = (j < NB) == (c < NB) ? re : (j < NB ? im : -im);
+  }
+  cbar();
   double *gpart = part + ((size_t)unit * gridDim.x + blockIdx.x) * (2 * BLKD);
   if (warp < 5) rotortho_consumer<1>(prev, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
   else rotortho_consumer<0>(prev, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);

@@ -670,7 +670,7 @@ static size_t part_doubles(const H *h, int nunits, int nctas) {
 }
 static int launch_reduce(H *h, int nunits, int /*nctas*/, int mode, double *d0, double *d1, size_t dstride,
                          const double *m0, const double *m1, double *hist0 = nullptr, size_t hstride = 0) {
-  k_reduce_parts<<<dim3((2 * BLKD + 7) / 8, nunits), 256, 0, h->st>>>(h->part.p, h->last_parts, mode, d0, d1, dstride, m0, m1, hist0, hstride);
+  k_reduce_parts<<<dim3((2 * BLKD + RP_ELEMS - 1) / RP_ELEMS, nunits), RP_ELEMS * RP_GROUPS, 0, h->st>>>(h->part.p, h->last_parts, mode, d0, d1, dstride, m0, m1, hist0, hstride);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return RSREC_OK;
