@@ -180,3 +180,47 @@ def simpson_to_fermi(y, ene, edel, fermi, nv1, e1, nexp):
     if e1 != fermi:
         val = val + (fermi - e1) * (f[nv1 - 1] + 4.0 * f[nv1] + f[nv1 + 1]) / 6.0
     return val
+
+
+def orbital_tail(mu_n_orb, kk, ene, fermi, emin, emax, nv1):
+    """tail of chebyshev_orbital_mod (recursion.f90:3009-3049), loop for loop: -> rows (E - E_F, -lz/pi, -lzi/pi) of fort.50.
+    Test infrastructure (the product's vectorised form is Recursion.chebyshev_orbital_tail)."""
+    import cmath
+    import math
+    mu = np.array(mu_n_orb, dtype=np.complex128)
+    lld = mu.shape[2]
+    nv = len(ene)
+    a = (emax - emin) / (2 - 0.3)
+    b = (emax + emin) / 2
+    kernel = jackson_kernel(lld)
+    mu = mu / float(kk)
+    for l in range(18):
+        for m in range(18):
+            mu[l, m, :] = mu[l, m, :] * kernel
+    mu[:, :, 1:] = mu[:, :, 1:] * 2.0
+    lzi = np.zeros(nv)
+    for ie in range(nv):
+        g0 = np.zeros((18, 18), np.complex128)
+        wsc = (ene[ie] - b) / a
+        for i in range(1, lld + 1):
+            exp_factor = -1j * cmath.exp(-1j * (i - 1) * math.acos(wsc))   # |wsc| < 1 on the reference's meshes (10 points past energy_max)
+            g0 += mu[:, :, i - 1] * exp_factor.imag
+        g0 = g0 / math.sqrt(a * a - (ene[ie] - b) ** 2)
+        lzi[ie] = sum(g0[k, k].real for k in range(18))
+    h = ene[1] - ene[0]
+    out = np.zeros((nv, 3))
+
+    def fermifun(e, ef, kbt):
+        x = (e - ef) / kbt
+        return 0.0 if x > 700.0 else 1.0 / (math.exp(x) + 1.0)
+
+    def y(i1, ef):   # Y(I) * fermifun(Ene(I)) with 1-based I; one past the mesh (reference reads out of bounds there) counts as zero
+        return lzi[i1 - 1] * fermifun(ene[i1 - 1], ef, 1.0e-15) if i1 <= nv else 0.0
+
+    for ie in range(nv):
+        aint = 0.0
+        for i1 in range(2, nv1 + 10, 2):
+            aint += y(i1 - 1, ene[ie]) + 4.0 * y(i1, ene[ie]) + y(i1 + 1, ene[ie])
+        lz = h * aint / 3.0
+        out[ie] = (ene[ie] - fermi, -(lz / math.pi), -(1 / math.pi) * lzi[ie])
+    return out

@@ -78,6 +78,56 @@ def _fc(a):
     return None if a is None else np.asfortranarray(a, dtype=np.complex128)
 
 
+def orbital_tail(mu_n_orb, nstart, en, path=None):
+    """Tail of chebyshev_orbital_mod (recursion.f90:3009-3049), host side like in the reference: the moments are divided by the
+    number of start sites (the reference loops over all kk sites and divides by kk), weighted with the Jackson kernel
+    (math.f90:1641-1655), doubled for n >= 2 and summed to g0(E) = sum_i mu_i Im(-i e^{-i (i-1) acos w(E)}) / sqrt(a^2 - (E-b)^2)
+    on the mesh en%ene; lzi(E) = Re tr g0(E); lz(E) = its T = 0 Fermi-weighted Simpson integral up to E (simpson_f,
+    math.f90:1600-1632, fermi = .true.).  Returns (rows, lz, lzi): rows = the three columns of the reference's `fort.50`
+    (E - E_F, -lz/pi, -lzi/pi) and writes them in its format ('(3es16.6)') when `path` is given.  The reference reads one
+    element past the mesh in simpson_f when channels_ldos is even (nv1 + 10 > size(ene)); that term is taken as zero."""
+    mu = np.array(mu_n_orb, dtype=np.complex128)
+    lld = mu.shape[2]
+    if en.ene is None:
+        en.e_mesh()
+    ene = np.asarray(en.ene, dtype=np.float64)
+    nv = len(ene)
+    a, b = en.scale_shift()
+    n = float(lld)
+    theta = np.pi * np.arange(lld) / (n + 1.0)
+    kernel = ((n - np.arange(lld) + 1.0) * np.cos(theta) + np.sin(theta) / np.tan(np.pi / (n + 1.0))) / (n + 1.0)
+    mu = mu / float(nstart)
+    mu = mu * kernel[None, None, :]
+    mu[:, :, 1:] *= 2.0
+    w = (ene - b) / a
+    ang = np.arange(lld)[:, None] * np.arccos(w)[None, :]                      # (i-1) acos(wscale(ie))
+    fac = np.imag(-1j * np.exp(-1j * ang))                                     # aimag(exp_factor)
+    tr = np.einsum("lli->i", mu)                                               # trace of every moment
+    lzi = np.real(tr @ fac) / np.sqrt(a * a - (ene - b) ** 2)                  # rtrace(g0(:,:,ie))
+    # simpson_f(lz, ene, ene(ie), nv1, lzi, fermi=.true., T=0): panels I = 2, 4, ..., nv1+9 (1-based), weights 1,4,1
+    npts = en.nv1
+    wgt = np.zeros(nv + 1)
+    for i1 in range(2, npts + 10, 2):
+        for off, c in ((-1, 1.0), (0, 4.0), (1, 1.0)):
+            k = i1 + off - 1
+            if k < nv:
+                wgt[k] += c
+    wgt = wgt[:nv]
+    h = ene[1] - ene[0]
+    lz = np.zeros(nv)
+    with np.errstate(over="ignore"):
+        for ie in range(nv):
+            f = 1.0 / (np.exp((ene - ene[ie]) / 1.0e-15) + 1.0)                # fermifun (math.f90:994-1000), kBT = kB*0 + 1e-15
+            lz[ie] = h * np.sum(wgt * lzi * f) / 3.0
+    out = np.stack([ene - en.fermi, -lz / np.pi, -lzi / np.pi], axis=1)
+    if path is not None:
+        with open(path, "w") as fh:
+            for row in out:
+                fh.write("".join("%16.6E" % v for v in row) + "\n")
+    return out, lz, lzi
+
+
+
 class Recursion:
     def __init__(self, hamiltonian, lattice, control: Control | None = None, energy: Energy | None = None,
                  device: int = 0, rank: int = 0, numprocs: int = 1, ijpair=None, atlist=None, phases=None):
@@ -317,6 +367,12 @@ class Recursion:
         _lib.check(self._L.rsrec_orbital_moments(self._h, len(s), _p(s), _p(crf), float(alat), self.control.lld, a, b, _p(mu)))
         self.mu_n_orb = mu
         return mu
+
+    def chebyshev_orbital_tail(self, mu_n_orb=None, nstart=None, path=None):
+        """tail of chebyshev_orbital_mod on the moments of the last `chebyshev_orbital_mod` call (see `orbital_tail`)"""
+        out, self.lz_orb, self.lzi_orb = orbital_tail(self.mu_n_orb if mu_n_orb is None else mu_n_orb,
+                                                      self.lattice.kk if nstart is None else nstart, self.en, path)
+        return out
 
     # -- single operator applications -------------------------------------------------------------------------
     def ham_vec_matmul(self, psi_in, a, b):

@@ -310,6 +310,13 @@ def test_chebyshev_orbital_mod(oracle_mod, name, family):
     ref = oracle_mod.Oracle(lat, ham).orbital_moments(starts, cr, 5.42, 7, a, b)
     assert relerr(mu, ref) < TOL_MU
     assert np.array_equal(mu, rec.chebyshev_orbital_mod(starts, cr, 5.42))       # reproducible
+    # the tail of the routine (Jackson weights, Chebyshev sum, trace, Simpson integral -> the rows of fort.50) on both moment sets
+    from oracle import dense_check_post as D
+    rec.en.channels_ldos, rec.en.fermi = 400, 0.0
+    rec.en.e_mesh()
+    rows = rec.chebyshev_orbital_tail(nstart=len(starts))
+    want = D.orbital_tail(ref, len(starts), rec.en.ene, rec.en.fermi, rec.en.energy_min, rec.en.energy_max, rec.en.nv1)
+    assert np.abs(rows - want).max() <= 1e-9 * np.abs(want).max()
 
 
 def test_fresh_handles_give_identical_kubo_moments():

@@ -289,3 +289,27 @@ def test_conductivity_cumulative_is_a_running_simpson_sum(oracle_mod):
     from math import erf, sqrt, pi
     exact = np.array([sqrt(pi) / 2 * (erf(w) - erf(ws[0])) for w in ws])
     assert np.abs(s2[0, 0, 2::2, 0] - exact[2::2]).max() < 1e-6       # odd (1-based) points close whole Simpson panels
+
+
+@pytest.mark.parametrize("channels", [400, 401])
+def test_orbital_tail_vectorised_form_equals_the_loop_restatement(channels):
+    """tail of chebyshev_orbital_mod (recursion.f90:3009-3049: Jackson weights, Chebyshev sum, trace, Fermi-weighted Simpson
+    integral, fort.50 rows): the host mirror's vectorised form against the loop-for-loop restatement, and sanity of the result"""
+    from rslmtoasa_b200.recursion import orbital_tail, Energy
+    from oracle import dense_check_post as D
+    rng = np.random.default_rng(11)
+    lld = 14
+    mu = rng.normal(size=(18, 18, lld)) + 1j * rng.normal(size=(18, 18, lld))
+    en = Energy(-1.0, 1.2, channels_ldos=channels, fermi=0.1)
+    en.e_mesh()
+    rows, lz, lzi = orbital_tail(mu, 77, en)
+    ref = D.orbital_tail(mu, 77, en.ene, en.fermi, -1.0, 1.2, en.nv1)
+    assert rows.shape == (len(en.ene), 3) and np.isfinite(rows).all()
+    assert np.abs(rows - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.allclose(rows[:, 0], en.ene - en.fermi) and np.allclose(rows[:, 2], -lzi / np.pi)
+    # the running integral at mesh point k (0-based) holds every point below k with its full Simpson weight and point k with
+    # the Fermi function's value at its own energy, 1/2 (simpson_f with fermi = .true. at kBT = 1e-15)
+    h = en.ene[1] - en.ene[0]
+    W = np.ones(len(en.ene)); W[1::2] = 4.0; W[2::2] = 2.0; W[0] = 1.0
+    k = 22
+    assert abs(lz[k] - h / 3.0 * (np.sum(W[:k] * lzi[:k]) + 0.5 * W[k] * lzi[k])) < 1e-12 * max(1.0, np.abs(lzi).max())
