@@ -1959,7 +1959,6 @@ static int dmma_launch_rmul(int mode, double *psi, double *pmn, const double *hp
                             size_t mstride, int kk, size_t vstride, int nunits, int sms, cudaStream_t st,
                             long long *launches, const int32_t *border = nullptr, const int32_t *bcnt = nullptr,
                             int nblocks = 0, double *part = nullptr, int *nparts_out = nullptr) {
-  const int ntiles = (kk + DM_S - 1) / DM_S;
   dim3 grid(dmma_rmul_ctas(kk, sms, nunits), nunits);
   if (nparts_out) *nparts_out = (int)grid.x;
   if (mode == RM_ORTHO)
