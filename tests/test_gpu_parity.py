@@ -629,6 +629,8 @@ def test_pipelined_lanczos_step_against_the_oracle_and_the_five_launch_step(orac
         launches = rec.launch_count - n0
         assert relerr(rec.a_b, a_o) < 1e-10 and relerr(rec.b2_b, b_o) < 1e-10, mode
         out = [rec.a_b.copy(), rec.b2_b.copy()]
+        rec.recur_b()                        # two streams, fixed-order reductions: run-to-run bitwise reproducible
+        assert np.array_equal(rec.a_b, out[0]) and np.array_equal(rec.b2_b, out[1]), mode
         rec.ijpair = np.array([[1, 2], [3, 3]], dtype=np.int32)
         rec.recur_b_ij()
         out += [rec.a_b.copy(), rec.b2_b.copy()]
