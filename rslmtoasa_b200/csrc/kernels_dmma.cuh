@@ -1504,7 +1504,7 @@ __device__ __forceinline__ void ro_product(const double *xs, const double *ts, i
 }
 
 template <int XN>
-__device__ __forceinline__ void rotortho_consumer(double *rnew, int kk, double *tiles, const double *tmat,
+__device__ __forceinline__ void rotortho_consumer(double *rnew, int kk, double *tiles, const double *tmat, double *outbuf,
                                                   uint64_t *full, uint64_t *empty, int warp, int lane, const int32_t *bo,
                                                   int nact, double *gpart) {
   const int g = lane >> 2, q = lane & 3;
@@ -1530,8 +1530,8 @@ __device__ __forceinline__ void rotortho_consumer(double *rnew, int kk, double *
     const int site0 = (bo ? bo[blk] : blk) * DM_S + (ti & 1) * RO_S;
     if (site0 >= kk) continue;  // second half of a last, partial block (the producer skips it too)
     const int slot = it & 1;
-    const double *tC = tiles + (size_t)slot * 3 * RO_TILE_D, *tW = tC + RO_TILE_D;   // R_n, W = H R_n
-    double *tP = tiles + (size_t)slot * 3 * RO_TILE_D + 2 * RO_TILE_D;               // R_{n-1}, replaced by R_{n+1}
+    const double *tC = tiles + (size_t)slot * 3 * RO_TILE_D, *tW = tC + RO_TILE_D, *tP = tC + 2 * RO_TILE_D;   // R_n, W = H R_n, R_{n-1}
+    double *tN = outbuf + (size_t)slot * RO_TILE_D;   // R_{n+1} of this tile (the prologue's scratch area: dead by now)
     auto gofs = [&](int i, int c) { return (size_t)(site0 + rows[i]) * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
     auto sofs = [&](int i, int c) { return rows[i] * BLKD + (c % NB) * COLD + (c / NB) * NB + rowk[i]; };
     auto valid = [&](int i, int c) { return c < 2 * NB && site0 + rows[i] < kk; };
@@ -1541,26 +1541,26 @@ __device__ __forceinline__ void rotortho_consumer(double *rnew, int kk, double *
     ro_product<XN, false>(tC, M3, aoff[0], aoff[1], koff, boff, xoff, acc, xacc);
     ro_product<XN, true>(tW, M1, aoff[0], aoff[1], koff, boff, xoff, acc, xacc);
     ro_product<XN, true>(tP, M2, aoff[0], aoff[1], koff, boff, xoff, acc, xacc);
-    asm volatile("bar.sync 1, %0;" ::"r"(32 * DM_CONSUMERS) : "memory");  // every warp is done reading the R_{n-1} tile
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);  // the input tiles are free: the producer refills the slot during the stores and the Gram products
+    // R_{n+1} goes to its own tile (two tiles ago every warp passed the barrier below, i.e. finished the Gram products that read it)
 #pragma unroll
     for (int nt = 0; nt < 5; nt++)
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int c = nt * 8 + 2 * q + e;
-        if (valid(0, c)) { rnew[gofs(0, c)] = acc[nt][e]; tP[sofs(0, c)] = acc[nt][e]; }
+        if (valid(0, c)) { rnew[gofs(0, c)] = acc[nt][e]; tN[sofs(0, c)] = acc[nt][e]; }
       }
     if (XN) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int c = xn * 8 + 2 * q + e;
-        if (valid(1, c)) { rnew[gofs(1, c)] = xacc[e]; tP[sofs(1, c)] = xacc[e]; }
+        if (valid(1, c)) { rnew[gofs(1, c)] = xacc[e]; tN[sofs(1, c)] = xacc[e]; }
       }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(32 * DM_CONSUMERS) : "memory");  // the new residual tile is complete in shared memory
     const int ns = min(RO_S, kk - site0);
-    if (warp + 8 < 15) rmul_gram<2>(tP, ns, warp, lane, gacc); else rmul_gram<1>(tP, ns, warp, lane, gacc);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);
+    if (warp + 8 < 15) rmul_gram<2>(tN, ns, warp, lane, gacc); else rmul_gram<1>(tN, ns, warp, lane, gacc);
     it++;
   }
 #pragma unroll
@@ -1675,8 +1675,8 @@ k_rotortho_dmma(double *prev_all, const double *cur_all, const double *w_all, co
   }
   cbar();
   double *gpart = part + ((size_t)unit * gridDim.x + blockIdx.x) * (2 * BLKD);
-  if (warp < 5) rotortho_consumer<1>(prev, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
-  else rotortho_consumer<0>(prev, kk, tiles, tmat, full, empty, warp, lane, bo, nact, gpart);
+  if (warp < 5) rotortho_consumer<1>(prev, kk, tiles, tmat, scratch, full, empty, warp, lane, bo, nact, gpart);
+  else rotortho_consumer<0>(prev, kk, tiles, tmat, scratch, full, empty, warp, lane, bo, nact, gpart);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
