@@ -231,8 +231,7 @@ __device__ __forceinline__ void gram_flush(double *pp, int warp, int lane, doubl
     }
     gacc[s][0] = gacc[s][1] = 0.0;
   }
-  if (GRAM == 1)  // matrix 1 is not produced: the reduction still reads it
-    for (int e = warp * 32 + lane; e < BLKD; e += 32 * 4) pp[BLKD + e] = 0.0;
+  // GRAM == 1: matrix 1 of the slot is not produced and k_reduce_parts does not read it (modes 0 / 2 without a second destination)
 }
 __device__ __forceinline__ void consumer_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
@@ -856,7 +855,7 @@ __device__ __forceinline__ void gram8_flush(double *pp, int warp, int lane, doub
     }
     gacc[s][0] = gacc[s][1] = 0.0;
   }
-  for (int e = warp * 32 + lane; e < BLKD; e += 32 * 8) pp[BLKD + e] = 0.0;  // matrix 1 is not produced: the reduction still reads it
+  // matrix 1 of the slot is not produced and k_reduce_parts does not read it (modes 0 / 2 without a second destination)
 }
 
 // ---- the spin-resolved SpMV with EIGHT consumer warps per CTA ------------------------------------------------------------------

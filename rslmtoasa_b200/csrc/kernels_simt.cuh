@@ -145,7 +145,9 @@ k_reduce_parts(const double *part, int nctas, int mode, double *dst0, double *ds
   const int unit = blockIdx.y, l = threadIdx.x % RP_ELEMS, g = threadIdx.x / RP_ELEMS;
   const int e = blockIdx.x * RP_ELEMS + l;
   double acc = 0.0;
-  if (e < 2 * BLKD) {
+  // matrix 1 of the slots is only wanted by the Chebyshev finish (mode 1) or when the caller asks for it (dst1)
+  const bool wanted = e < 2 * BLKD && (e < BLKD || mode == 1 || dst1 != nullptr);
+  if (wanted) {
     const double *pp = part + (size_t)unit * nctas * (2 * BLKD) + e;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int cta = g;
@@ -159,7 +161,7 @@ k_reduce_parts(const double *part, int nctas, int mode, double *dst0, double *ds
   }
   gs[g][l] = acc;
   __syncthreads();
-  if (g != 0 || e >= 2 * BLKD) return;
+  if (g != 0 || !wanted) return;
   double s = 0.0;
 #pragma unroll
   for (int k = 0; k < RP_GROUPS; k++) s += gs[k][l];
